@@ -1,0 +1,28 @@
+# Builds libmosdepth_b200.so (sm_100a only), the host CLI stand-in, the BAM generator and the test oracle.
+NVCC ?= /usr/local/cuda/bin/nvcc
+CXX ?= g++
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v --fmad=false
+LIB := mosdepth_b200/libmosdepth_b200.so
+CSRC := $(wildcard mosdepth_b200/csrc/*.cu mosdepth_b200/csrc/*.cuh) include/mosdepth_b200.h
+
+all: $(LIB) mosdepth_b200/bin/mosdepth-b200 tools/gen_bam oracle
+
+$(LIB): $(CSRC)
+	$(NVCC) $(NVFLAGS) -shared -o $@ mosdepth_b200/csrc/msd_api.cu 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
+	@grep -E "error|warning" build_ptxas.log | grep -v "ptxas info" || true
+
+mosdepth_b200/bin/mosdepth-b200: mosdepth_b200/host/main.cpp $(wildcard mosdepth_b200/host/*.hpp) include/mosdepth_b200.h $(LIB)
+	mkdir -p mosdepth_b200/bin
+	$(CXX) -O2 -g -std=c++17 -Wall -o $@ mosdepth_b200/host/main.cpp -Iinclude -Lmosdepth_b200 -lmosdepth_b200 -lz -Wl,-rpath,'$$ORIGIN/..'
+
+tools/gen_bam: tools/gen_bam.cpp
+	$(CXX) -O3 -std=c++17 -Wall -pthread -o $@ $< -lz
+
+oracle:
+	$(MAKE) -s -C oracle
+
+clean:
+	rm -f $(LIB) mosdepth_b200/bin/mosdepth-b200 tools/gen_bam build_ptxas.log
+	$(MAKE) -C oracle clean
+.PHONY: all oracle clean

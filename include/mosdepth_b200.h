@@ -1,0 +1,171 @@
+/*
+ * mosdepth_b200.h -- C ABI of libmosdepth_b200.so: the depth hot path of brentp/mosdepth on one B200 (sm_100a).
+ *
+ * The reference (Nim, /root/reference/mosdepth.nim, v0.3.14) has no plugin/FFI seam for this path; every
+ * step is a direct call inside one module.  The seam is therefore cut at the reference's own function
+ * boundaries; each entry point below names the reference code it replaces.  The host
+ * (the Nim CLI in the reference; the C++ stand-in `mosdepth-b200` here) keeps: flag parsing, BAM header and
+ * BAI/CSI parsing, BED loading, and all text/BGZF output writing.
+ *
+ * Conventions: every call returns >= 0 on success and a negative MSD_E* code on failure, message via
+ * msd_last_error().  One host thread per context.  There is NO CPU fallback: msd_create() fails unless an
+ * sm_100 device is present.  All pointers are plain host pointers; sizes are in elements unless noted.
+ */
+#ifndef MOSDEPTH_B200_H
+#define MOSDEPTH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSD_ABI_VERSION 1
+
+/* error codes */
+#define MSD_OK 0
+#define MSD_ENODEV (-10)     /* no sm_100 device / CUDA failure at create */
+#define MSD_EINVAL (-11)     /* bad argument or call order */
+#define MSD_EIO (-12)        /* file / BGZF framing error */
+#define MSD_ECUDA (-13)      /* CUDA runtime error */
+#define MSD_EDATA (-14)      /* corrupt DEFLATE stream or BAM record (reference: quit on hts.BamError, mosdepth.nim:190-191) */
+#define MSD_ENOMEM (-15)     /* a device-side table overflowed (message says which knob) */
+#define MSD_ENEGDEPTH (-16)  /* negative depth met in median mode (reference raises IndexDefect, depthstat.nim:18-19) */
+
+/* msd_set_filters mode: which branch of coverage() is taken (mosdepth.nim:292,342,346,355) */
+#define MSD_MODE_DEFAULT 0   /* CIGAR blocks + mate-overlap correction */
+#define MSD_MODE_FAST 1      /* -x / --fast-mode */
+#define MSD_MODE_FRAGMENT 2  /* -a / --fragment-mode */
+
+/* mirrors depth_stat, depthstat.nim:2-6 */
+typedef struct msd_depth_stat {
+    int64_t cum_length;
+    uint64_t cum_depth;
+    uint32_t min_depth;   /* UINT32_MAX when nothing was accumulated (clear(), depthstat.nim:47-51) */
+    uint32_t max_depth;
+} msd_depth_stat;
+
+/* per-stage device times of the last msd_run(), CUDA events on the library's own stream (milliseconds) and
+ * the byte/record counts a roofline needs.  Filled by msd_last_run_info(). */
+typedef struct msd_run_info {
+    double ms_total;           /* first launch .. last launch of msd_run on the compute stream */
+    double ms_h2d;             /* summed host->device copies of compressed bytes (0 when staged) */
+    double ms_inflate;         /* summed bgzf_inflate kernel time */
+    double ms_frame;           /* summed framing kernels */
+    double ms_records;         /* summed filter / delta kernels (+ mate join in default mode) */
+    double ms_scan;            /* summed prefix-sum + contig stats kernels */
+    double ms_zero;            /* depth arena zero-fill */
+    uint64_t bytes_compressed; /* BGZF bytes consumed (whole blocks) */
+    uint64_t bytes_inflated;   /* bytes produced by inflate */
+    uint64_t n_blocks;         /* BGZF blocks inflated */
+    uint64_t n_records;        /* BAM records framed (before any filter) */
+    uint64_t n_events;         /* +1/-1 events applied to the depth arrays */
+    uint64_t n_depth_cells;    /* sum of (tlen+1) over contigs that had records */
+    uint32_t n_launches;       /* kernels launched by the library during the run */
+    uint32_t n_inflate_launches;
+} msd_run_info;
+
+typedef struct msd_ctx msd_ctx;
+
+/* -- lifetime ------------------------------------------------------------------------------------------- */
+int msd_abi_version(void);
+/* device: CUDA ordinal.  Fails with MSD_ENODEV unless the device is compute capability 10.x. */
+int msd_create(int device, msd_ctx **out);
+void msd_destroy(msd_ctx *ctx);
+/* ctx may be NULL: returns the message of the last failed msd_create on this thread. */
+const char *msd_last_error(const msd_ctx *ctx);
+
+/* -- input: replaces open(bam, threads, index=true) mosdepth.nim:968 and bam.hdr.targets :596 ----------- *
+ * The host has parsed the BAM header: it passes the target lengths and the virtual offset
+ * (coffset<<16 | uoffset) of the first alignment record.  The library reads the compressed bytes itself. */
+int msd_open(msd_ctx *ctx, const char *bam_path, int n_targets, const uint32_t *target_len, uint64_t first_record_voff);
+/* Same, for a BAM image already in host memory (pinned or pageable); the caller keeps it alive. */
+int msd_open_mem(msd_ctx *ctx, const void *bam_bytes, uint64_t n_bytes, int n_targets, const uint32_t *target_len,
+                 uint64_t first_record_voff);
+/* Optional: copy the compressed bytes of the current spans into HBM now, so later msd_run() calls start from
+ * device-resident input (no host->device traffic inside the run). */
+int msd_stage(msd_ctx *ctx);
+
+/* -- what to read: replaces the index iterator behind bam.query(tid, 0, len), mosdepth.nim:185 ----------- *
+ * n virtual-offset ranges [beg, end) taken by the host from the BAI/CSI (pseudo-bin ref_beg/ref_end or bin
+ * chunks); each beg must be the start of a record, end = 0 means "to end of file".  Default (never called, or
+ * n = 0): one span from first_record_voff to end of file.  want_target (n_targets bytes, may be NULL = all)
+ * selects the contigs whose records are counted: the per-contig loop's skip rule (mosdepth.nim:703-705), -c, and
+ * the multi-GPU shard assignment all reduce to this mask. */
+int msd_set_spans(msd_ctx *ctx, int n, const uint64_t *voff_beg, const uint64_t *voff_end);
+int msd_set_targets(msd_ctx *ctx, const uint8_t *want_target);
+
+/* -- coverage() parameters, mosdepth.nim:250-254 (filters :276-285) ---------------------------------------- */
+int msd_set_filters(msd_ctx *ctx, int mapq, int64_t min_len, int64_t max_len, uint16_t eflag, uint16_t iflag,
+                    const char *const *read_groups, int n_read_groups, int mode);
+
+/* -- coverage() + to_coverage() for every selected contig, mosdepth.nim:707,713 --------------------------- *
+ * BGZF inflate -> record framing -> filters -> +1/-1 events (-> mate-overlap correction) -> per-contig int32
+ * prefix sum, fused with the whole-contig depth distribution (:746) and depth_stat (:747).  After it returns,
+ * the depth arrays of all selected contigs are resident in HBM and the query calls below can be made in any
+ * order. */
+int msd_run(msd_ctx *ctx);
+int msd_last_run_info(const msd_ctx *ctx, msd_run_info *out);
+
+/* coverage()'s return convention (mosdepth.nim:255-258): returns tid when the contig had >= 1 record (counted
+ * BEFORE the filters, :272-275), -2 when it had none, -1 when tid is out of range / not selected. */
+int msd_contig_records(msd_ctx *ctx, int tid, int64_t *n_records_prefilter);
+
+/* inc(chrom_global_distribution, arr, 0, len-1) :746 and newDepthStat(arr[0..<len-1]) :747.
+ * dist: caller array of dist_cap int64 bins; *dist_len = 1 + highest non-zero bin (values > 400000 land in
+ * bin 399990, negatives are skipped, :415-437).  MSD_EINVAL if dist_cap is too small (*dist_len is still set). */
+int msd_contig_stats(msd_ctx *ctx, int tid, msd_depth_stat *chrom_stat, int64_t *dist, int64_t dist_cap, int64_t *dist_len);
+
+/* window loop mosdepth.nim:720-741 with window_gen :382-388 evaluated on the device.
+ * value_out[n_windows]: imean() result per window (:399-413): the sequential float64 mean, or the CountStat
+ * median when use_median != 0.  region_stat: sum of newDepthStat over the windows (:723-724).
+ * region_dist[512]: bin min(toInt(mean), 511) per window (:737-739).  Returns n_windows written;
+ * value_cap is the capacity of value_out (MSD_EINVAL if too small; msd_n_windows() gives the count). */
+int64_t msd_n_windows(uint32_t tlen, uint32_t window);
+int64_t msd_windows(msd_ctx *ctx, int tid, uint32_t window, int use_median, double *value_out, int64_t value_cap,
+                    msd_depth_stat *region_stat, int64_t *region_dist512);
+
+/* BED loop mosdepth.nim:720-743 for n host-sorted regions of one contig.
+ * value_out[n] as above; region_stat accumulates newDepthStat(arr[min(start,L)..<min(L,stop)]) with L = tlen+1
+ * (:719,:724); region_dist: per-base histogram inside the regions (inc, :741), same convention as
+ * msd_contig_stats; thresholds (ascending, n_thr may be 0): thr_counts[i*n_thr + j] = #bases of region i with
+ * depth >= thresholds[j] (:549-553; slices are clamped to the array, see DESIGN.md "Divergences"). */
+int msd_regions(msd_ctx *ctx, int tid, int64_t n, const uint32_t *start, const uint32_t *stop, int use_median,
+                double *value_out, msd_depth_stat *region_stat, int64_t *region_dist, int64_t dist_cap,
+                int64_t *dist_len, const int32_t *thresholds, int n_thr, int64_t *thr_counts);
+
+/* gen_depths(arr) mosdepth.nim:58-96 as consumed at :785-793: run-length segments of arr[0..tlen).
+ * The three arrays are library-owned pinned host memory, valid until the next call on this context that
+ * returns runs.  stop[i] == start[i+1]; stop[n-1] == tlen. */
+int msd_per_base_runs(msd_ctx *ctx, int tid, const int32_t **start, const int32_t **stop, const int32_t **depth,
+                      int64_t *n_runs);
+
+/* gen_quantized(quants, arr) mosdepth.nim:124-141 with linear_search :98-109.  quants: the n_q sorted values of
+ * get_quantize_args (:501-519; INT64_MAX for an open last bin).  Returns only the segments the reference
+ * yields (bin != -1 and bin < n_q-1; the scan stops before the last base, :132; the last segment is closed
+ * at tlen, :140-141).  bin indexes the host's make_lookup() labels (:111-122). */
+int msd_quantized_runs(msd_ctx *ctx, int tid, const int64_t *quants, int n_q, const int32_t **start,
+                       const int32_t **stop, const int32_t **bin, int64_t *n_runs);
+
+/* -- multi-GPU plumbing ---------------------------------------------------------------------------------- *
+ * Device pointer + element count of this context's genome-wide accumulators, kept up to date by
+ * msd_contig_stats / msd_windows / msd_regions (sum_into, mosdepth.nim:761-764): int64 global dist bins,
+ * int64 region dist bins, and {cum_length, cum_depth, min, max} x {global, region} packed as 8 int64.
+ * A host running one process per GPU all-reduces these over NCCL (sum; min/max for the two extremes) to get
+ * the `total` rows (mosdepth.nim:807-813).  msd_totals_reset() zeroes them. */
+int msd_totals_device(msd_ctx *ctx, void **global_dist, void **region_dist, int64_t *n_bins, void **stats8);
+int msd_totals_reset(msd_ctx *ctx);
+
+/* -- test hooks (used by tests/ to check single stages against zlib / numpy) ----------------------------- */
+/* Inflate every BGZF block of a host BGZF image; out must hold the sum of ISIZE fields. Returns bytes written. */
+int64_t msd_debug_inflate(msd_ctx *ctx, const void *bgzf_bytes, uint64_t n_bytes, void *out, uint64_t out_cap);
+/* Copy depth[0..tlen] (tlen+1 int32, after the prefix sum) of a contig to host memory. */
+int msd_debug_depth(msd_ctx *ctx, int tid, int32_t *out, int64_t out_cap);
+/* In-place inclusive int32 prefix sum of a host array on the device (the scan kernel alone). */
+int msd_debug_cumsum(msd_ctx *ctx, int32_t *inout, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOSDEPTH_B200_H */

@@ -1,0 +1,937 @@
+// msd_api.cu -- C ABI of libmosdepth_b200.so (include/mosdepth_b200.h): context, chunk pipeline, query calls.
+// Host code here only plans work (BSIZE chase, chunk descriptors) and moves bytes; every byte of decode, filter,
+// accumulate and reduce work runs in the sm_100a kernels of the *.cuh files.  There is no CPU fallback.
+#include "../../include/mosdepth_b200.h"
+
+#include <algorithm>
+#include <cerrno>
+#include <climits>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <fcntl.h>
+#include <string>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <vector>
+
+#include "common.cuh"
+#include "frame.cuh"
+#include "inflate.cuh"
+#include "records.cuh"
+#include "regions.cuh"
+#include "runs.cuh"
+#include "scan.cuh"
+
+using namespace msd;
+
+namespace {
+
+thread_local char g_create_error[512] = "";
+
+struct Span { uint64_t beg, end; };
+
+struct StageSet {              // pinned host staging for one in-flight chunk
+    BlockDesc* h_desc = nullptr; uint32_t* h_rel = nullptr;
+    uint8_t* h_bounce = nullptr;   // pinned copy of the compressed bytes when the source is pageable
+    cudaEvent_t free_ev = nullptr; // recorded when the device no longer needs this set
+    bool used = false;
+};
+
+struct ContigResult {
+    bool have = false;
+    msd_depth_stat stat{};
+    std::vector<int64_t> dist;
+};
+
+}  // namespace
+
+struct msd_ctx {
+    int device = 0;
+    char err[512] = "";
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    // input
+    const uint8_t* bytes = nullptr; uint64_t n_bytes = 0; bool mapped = false; bool src_pinned = false;
+    int n_targets = 0; std::vector<uint32_t> tlen; uint64_t first_voff = 0;
+    std::vector<Span> spans; std::vector<uint8_t> want;
+    // staged compressed bytes
+    uint8_t* d_staged = nullptr; uint64_t staged_beg = 0, staged_end = 0;
+    // filters
+    FilterParams fp{}; std::string rg_blob; char* d_rg = nullptr; bool filters_set = false;
+    // depth arena
+    int32_t* d_arena = nullptr; uint64_t arena_cells = 0; std::vector<uint64_t> depth_off;
+    uint64_t* d_depth_off = nullptr; uint32_t* d_tlen = nullptr;
+    unsigned long long* d_nprefilter = nullptr; std::vector<long long> n_prefilter;
+    std::vector<ContigResult> results; bool ran = false;
+    // chunk buffers
+    uint64_t comp_cap = 0, infl_cap = 0; uint32_t carry_cap = 0, max_blocks = 0, rec_cap = 0;
+    uint8_t* d_comp[2] = {nullptr, nullptr}; uint8_t* d_infl[2] = {nullptr, nullptr};
+    BlockDesc* d_desc[2] = {nullptr, nullptr}; uint32_t* d_rel[2] = {nullptr, nullptr};
+    uint32_t *d_bstart = nullptr, *d_land = nullptr, *d_count = nullptr, *d_first = nullptr, *d_cnt = nullptr, *d_recbase = nullptr, *d_recoff = nullptr;
+    uint32_t *d_status = nullptr, *d_ticket = nullptr, *d_inflate_err = nullptr;
+    ChunkState* d_cs = nullptr; RunCounters* d_rc = nullptr;
+    StageSet stage[2];
+    cudaEvent_t comp_free[2] = {nullptr, nullptr}, h2d_done[2] = {nullptr, nullptr};
+    // mate join (default mode only)
+    MateChunk mc{}; MateTable mt{}; LiveList live[2]{}; bool mate_ready = false; uint32_t mate_slots = 0;
+    // scan + queries
+    unsigned long long* d_tile_state = nullptr; uint64_t tile_state_cap = 0; uint32_t* d_scan_ticket = nullptr;
+    unsigned long long* d_hist = nullptr; ContigAccum* d_acc = nullptr; RegionAccum* d_racc = nullptr;
+    unsigned long long* d_dist512 = nullptr; unsigned long long* d_rdist = nullptr;
+    // totals for multi-GPU reduction
+    long long* d_tot_global = nullptr; long long* d_tot_region = nullptr; long long* d_tot_stats = nullptr;
+    // run buffers (library-owned pinned host memory)
+    int32_t *h_run_start = nullptr, *h_run_stop = nullptr, *h_run_val = nullptr; uint64_t h_run_cap = 0;
+    int32_t *d_run_start = nullptr, *d_run_stop = nullptr, *d_run_val = nullptr; uint64_t d_run_cap = 0;
+    uint32_t* d_tile_count = nullptr; unsigned long long* d_tile_base = nullptr; uint64_t run_tile_cap = 0; unsigned long long* d_run_total = nullptr;
+    // generic scratch
+    void* d_scratch = nullptr; uint64_t scratch_cap = 0;
+    msd_run_info info{};
+    std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+};
+
+namespace {
+
+int ctx_fail(msd_ctx* ctx, int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    if (ctx) vsnprintf(ctx->err, sizeof ctx->err, fmt, ap); else vsnprintf(g_create_error, sizeof g_create_error, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+template <class T> int dev_alloc(msd_ctx* ctx, T** p, uint64_t n) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    cudaError_t e = cudaMalloc((void**)p, (n ? n : 1) * sizeof(T));
+    if (e != cudaSuccess) return ctx_fail(ctx, MSD_ECUDA, "cudaMalloc(%llu bytes): %s", (unsigned long long)(n * sizeof(T)), cudaGetErrorString(e));
+    return 0;
+}
+template <class T> void dev_free(T** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+
+cudaEvent_t next_event(msd_ctx* ctx) {
+    if (ctx->ev_used == ctx->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
+    return ctx->ev_pool[ctx->ev_used++];
+}
+
+uint64_t env_u64(const char* name, uint64_t dflt) { const char* v = getenv(name); return (v && *v) ? strtoull(v, nullptr, 10) : dflt; }
+
+void release_input(msd_ctx* ctx) {
+    if (ctx->mapped && ctx->bytes) munmap((void*)ctx->bytes, ctx->n_bytes);
+    ctx->bytes = nullptr; ctx->n_bytes = 0; ctx->mapped = false; ctx->src_pinned = false;
+    dev_free(&ctx->d_staged); ctx->staged_beg = ctx->staged_end = 0;
+    ctx->ran = false;
+}
+
+int grid_for(uint64_t n, int threads, int max_ctas) { uint64_t g = (n + threads - 1) / threads; if (g < 1) g = 1; if (g > (uint64_t)max_ctas) g = max_ctas; return (int)g; }
+
+// parse one BGZF header at `pos`; returns block length or 0 on error
+uint32_t bgzf_header(const uint8_t* f, uint64_t n, uint64_t pos, uint32_t* xlen_out, uint32_t* isize_out) {
+    if (pos + 18 > n) return 0;
+    const uint8_t* h = f + pos;
+    if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return 0;
+    uint32_t xlen = h[10] | (h[11] << 8), q = 12, bsize = 0; bool have = false;
+    if (pos + 12 + xlen > n) return 0;
+    while (q + 4 <= 12 + xlen) {
+        uint32_t slen = h[q + 2] | (h[q + 3] << 8);
+        if (h[q] == 66 && h[q + 1] == 67 && slen == 2) { bsize = h[q + 4] | (h[q + 5] << 8); have = true; }
+        q += 4 + slen;
+    }
+    if (!have) return 0;
+    uint32_t blen = bsize + 1;
+    if (blen < xlen + 20 || pos + blen > n) return 0;
+    memcpy(isize_out, f + pos + blen - 4, 4);
+    *xlen_out = xlen;
+    return blen;
+}
+
+int setup_common(msd_ctx* ctx, int n_targets, const uint32_t* target_len, uint64_t first_voff) {
+    if (n_targets < 0 || (n_targets > 0 && !target_len)) return ctx_fail(ctx, MSD_EINVAL, "bad target list");
+    ctx->n_targets = n_targets; ctx->tlen.assign(target_len, target_len + n_targets); ctx->first_voff = first_voff;
+    ctx->spans.clear(); ctx->want.assign(n_targets, 1);
+    ctx->results.assign(n_targets, ContigResult()); ctx->n_prefilter.assign(n_targets, 0);
+    cudaPointerAttributes pa; memset(&pa, 0, sizeof pa);
+    ctx->src_pinned = (cudaPointerGetAttributes(&pa, ctx->bytes) == cudaSuccess && pa.type == cudaMemoryTypeHost);
+    cudaGetLastError();
+    // chunk geometry
+    ctx->comp_cap = std::min<uint64_t>(env_u64("MSD_CHUNK_COMP_MB", 192) << 20, ((ctx->n_bytes + 65536 + 255) / 256) * 256);
+    ctx->infl_cap = std::min<uint64_t>(env_u64("MSD_CHUNK_INFL_MB", 512) << 20, std::max<uint64_t>(8ull << 20, ctx->n_bytes * 16));
+    ctx->carry_cap = (uint32_t)std::min<uint64_t>(env_u64("MSD_CARRY_MB", 64) << 20, ctx->infl_cap);
+    ctx->max_blocks = (uint32_t)std::min<uint64_t>(env_u64("MSD_CHUNK_BLOCKS", 16384), ctx->n_bytes / 28 + 2);
+    ctx->rec_cap = (uint32_t)((ctx->infl_cap + ctx->carry_cap) / 37 + 2);
+    return 0;
+}
+
+int ensure_chunk_buffers(msd_ctx* ctx) {
+    if (ctx->d_infl[0]) return 0;
+    int rc;
+    const uint64_t infl_bytes = (uint64_t)ctx->carry_cap + ctx->infl_cap + 256;
+    for (int k = 0; k < 2; k++) {
+        if ((rc = dev_alloc(ctx, &ctx->d_comp[k], ctx->comp_cap + 256))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_infl[k], infl_bytes))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_desc[k], ctx->max_blocks))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_rel[k], ctx->max_blocks + 1))) return rc;
+        MSD_CUDA_OK(cudaMemset(ctx->d_infl[k], 0, infl_bytes));
+        MSD_CUDA_OK(cudaMallocHost((void**)&ctx->stage[k].h_desc, sizeof(BlockDesc) * ctx->max_blocks));
+        MSD_CUDA_OK(cudaMallocHost((void**)&ctx->stage[k].h_rel, sizeof(uint32_t) * (ctx->max_blocks + 1)));
+        MSD_CUDA_OK(cudaEventCreateWithFlags(&ctx->stage[k].free_ev, cudaEventDisableTiming));
+        MSD_CUDA_OK(cudaEventCreateWithFlags(&ctx->comp_free[k], cudaEventDisableTiming));
+        MSD_CUDA_OK(cudaEventCreateWithFlags(&ctx->h2d_done[k], cudaEventDisableTiming));
+    }
+    const uint32_t nb = ctx->max_blocks + 2;
+    if ((rc = dev_alloc(ctx, &ctx->d_bstart, nb + 1))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_land, nb))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_count, nb))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_first, nb))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_cnt, nb))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_recbase, nb))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_recoff, ctx->rec_cap))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_status, ctx->max_blocks))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_ticket, 4))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_inflate_err, 4))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_cs, 1))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_rc, 1))) return rc;
+    return 0;
+}
+
+int ensure_bounce(msd_ctx* ctx) {
+    if (ctx->src_pinned || ctx->stage[0].h_bounce) return 0;
+    for (int k = 0; k < 2; k++) MSD_CUDA_OK(cudaMallocHost((void**)&ctx->stage[k].h_bounce, ctx->comp_cap + 256));
+    return 0;
+}
+
+int ensure_mate(msd_ctx* ctx) {
+    if (ctx->mate_ready) return 0;
+    int rc;
+    const uint64_t R = ctx->rec_cap;
+    if ((rc = dev_alloc(ctx, &ctx->mc.cls, R))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->mc.qhash, R))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->mc.endpos, R))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->mc.next, R))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->mc.slot, R))) return rc;
+    const uint32_t live_cap = (uint32_t)std::min<uint64_t>(env_u64("MSD_LIVE_CAP", 8u << 20), std::max<uint64_t>(R * 4, 1024));
+    uint32_t slots = 1024; while (slots < 2ull * (R + live_cap) && slots < (1u << 26)) slots <<= 1;
+    slots = (uint32_t)std::min<uint64_t>(slots, env_u64("MSD_MATE_SLOTS", slots));
+    ctx->mate_slots = slots;
+    if ((rc = dev_alloc(ctx, &ctx->mt.word, slots))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->mt.head, slots))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->mt.live, slots))) return rc;
+    ctx->mt.mask = slots - 1;
+    const uint32_t arena_cap = (uint32_t)std::min<uint64_t>(env_u64("MSD_LIVE_ARENA_MB", 512) << 20, std::max<uint64_t>((uint64_t)live_cap * 64, 1 << 20));
+    for (int k = 0; k < 2; k++) {
+        if ((rc = dev_alloc(ctx, &ctx->live[k].e, live_cap))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->live[k].arena, arena_cap))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->live[k].n, 1))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->live[k].arena_used, 1))) return rc;
+        ctx->live[k].cap = live_cap; ctx->live[k].arena_cap = arena_cap;
+    }
+    ctx->mate_ready = true;
+    return 0;
+}
+
+int ensure_arena(msd_ctx* ctx) {
+    // every selected contig gets tlen+1 cells (mosdepth.nim:274), padded to 128 B so 128-bit accesses stay aligned
+    std::vector<uint64_t> off(ctx->n_targets, ~0ull);
+    uint64_t cells = 0;
+    for (int t = 0; t < ctx->n_targets; t++) if (ctx->want[t]) { off[t] = cells; cells += (((uint64_t)ctx->tlen[t] + 1 + 31) / 32) * 32; }
+    int rc;
+    if (cells > ctx->arena_cells || !ctx->d_arena) { if ((rc = dev_alloc(ctx, &ctx->d_arena, cells + 32))) return rc; ctx->arena_cells = cells; }
+    ctx->depth_off = off;
+    if (!ctx->d_depth_off) {
+        if ((rc = dev_alloc(ctx, &ctx->d_depth_off, (uint64_t)ctx->n_targets))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_tlen, (uint64_t)ctx->n_targets))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_nprefilter, (uint64_t)ctx->n_targets))) return rc;
+    }
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_depth_off, off.data(), sizeof(uint64_t) * ctx->n_targets, cudaMemcpyHostToDevice, ctx->s_compute));
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_tlen, ctx->tlen.data(), sizeof(uint32_t) * ctx->n_targets, cudaMemcpyHostToDevice, ctx->s_compute));
+    MSD_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));   // `off` is a stack vector
+    return 0;
+}
+
+int ensure_query_buffers(msd_ctx* ctx) {
+    if (ctx->d_hist) return 0;
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_hist, (uint64_t)kDistBins))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_rdist, (uint64_t)kDistBins))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_dist512, (uint64_t)kWindowDistBins))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_acc, 1))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_racc, 1))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_scan_ticket, 4))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_tot_global, (uint64_t)kDistBins))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_tot_region, (uint64_t)kDistBins))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_tot_stats, 8))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_run_total, 1))) return rc;
+    return msd_totals_reset(ctx);
+}
+
+int ensure_scratch(msd_ctx* ctx, uint64_t bytes) {
+    if (bytes <= ctx->scratch_cap) return 0;
+    if (ctx->d_scratch) { cudaFree(ctx->d_scratch); ctx->d_scratch = nullptr; }
+    cudaError_t e = cudaMalloc(&ctx->d_scratch, bytes);
+    if (e != cudaSuccess) return ctx_fail(ctx, MSD_ECUDA, "cudaMalloc scratch %llu: %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    ctx->scratch_cap = bytes;
+    return 0;
+}
+
+// totals accumulation kernels (sum_into, mosdepth.nim:491-499, and depth_stat `+`, depthstat.nim:53-57)
+__global__ void add_hist_kernel(long long* __restrict__ to, const unsigned long long* __restrict__ from, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { unsigned long long v = from[i]; if (v) to[i] += (long long)v; }
+}
+__global__ void add_stats_kernel(long long* __restrict__ tot, long long cum_length, unsigned long long cum_depth, unsigned int mn, unsigned int mx) {
+    tot[0] += cum_length; tot[1] += (long long)cum_depth;
+    if ((long long)mn < tot[2]) tot[2] = mn;
+    if ((long long)mx > tot[3]) tot[3] = mx;
+}
+__global__ void init_stats_kernel(long long* __restrict__ tot) { tot[0] = 0; tot[1] = 0; tot[2] = 0xffffffffll; tot[3] = 0; tot[4] = 0; tot[5] = 0; tot[6] = 0xffffffffll; tot[7] = 0; }
+__global__ void init_accum_kernel(ContigAccum* a, RegionAccum* r) {
+    if (a) { a->cum_depth = 0; a->min_depth = 0xffffffffu; a->max_depth = 0; a->neg_seen = 0; a->pad = 0; }
+    if (r) { r->cum_length = 0; r->cum_depth = 0; r->min_depth = 0xffffffffu; r->max_depth = 0; r->neg_seen = 0; r->pad = 0; }
+}
+
+struct StageTimes { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> h2d, inflate, frame, records; };
+
+double sum_ms(const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v) {
+    double s = 0; for (auto& p : v) { float ms = 0; if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) s += ms; } return s;
+}
+
+int run_scan(msd_ctx* ctx, int32_t* arr, uint32_t n_scan, uint32_t n_stat, int do_stats) {
+    const uint64_t n_tiles = ((uint64_t)n_scan + kScanTile - 1) / kScanTile;
+    if (n_tiles > ctx->tile_state_cap) { int rc = dev_alloc(ctx, &ctx->d_tile_state, n_tiles); if (rc) return rc; ctx->tile_state_cap = n_tiles; }
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_tile_state, 0, n_tiles * 8, ctx->s_compute));
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_scan_ticket, 0, 4, ctx->s_compute));
+    const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)kSMs * 8);
+    scan_fused_kernel<<<grid, kScanThreads, 0, ctx->s_compute>>>(arr, n_scan, n_stat, ctx->d_tile_state, ctx->d_scan_ticket, ctx->d_hist, ctx->d_acc, do_stats);
+    ctx->info.n_launches++;
+    MSD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int check_tid(msd_ctx* ctx, int tid, const char* who) {
+    if (!ctx) return MSD_EINVAL;
+    if (!ctx->ran) return ctx_fail(ctx, MSD_EINVAL, "%s: call msd_run first", who);
+    if (tid < 0 || tid >= ctx->n_targets || !ctx->want[tid]) return ctx_fail(ctx, MSD_EINVAL, "%s: contig %d not selected", who, tid);
+    if (ctx->n_prefilter[tid] <= 0) return ctx_fail(ctx, MSD_EINVAL, "%s: contig %d has no records (coverage() returned -2)", who, tid);
+    cudaSetDevice(ctx->device);
+    return 0;
+}
+
+
+static void fetch_region_accum(msd_ctx* ctx, msd_depth_stat* out, RegionAccum* h) {
+    cudaMemcpy(h, ctx->d_racc, sizeof *h, cudaMemcpyDeviceToHost);
+    if (out) { out->cum_length = (int64_t)h->cum_length; out->cum_depth = h->cum_depth; out->min_depth = h->min_depth; out->max_depth = h->max_depth; }
+}
+
+
+template <class F>
+static int compute_runs(msd_ctx* ctx, const int32_t* arr, uint32_t n, int32_t end, F f, uint64_t* n_runs_out) {
+    cudaStream_t sc = ctx->s_compute;
+    const uint32_t n_tiles = (n + kRunTile - 1) / kRunTile;
+    int rc;
+    if (n_tiles > ctx->run_tile_cap) {
+        if ((rc = dev_alloc(ctx, &ctx->d_tile_count, (uint64_t)n_tiles))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_tile_base, (uint64_t)n_tiles))) return rc;
+        ctx->run_tile_cap = n_tiles;
+    }
+    *n_runs_out = 0;
+    if (n == 0) return 0;
+    runs_count_kernel<F><<<n_tiles, kRunThreads, 0, sc>>>(arr, n, f, ctx->d_tile_count);
+    runs_scan_kernel<<<1, 1024, 0, sc>>>(ctx->d_tile_count, n_tiles, ctx->d_tile_base, ctx->d_run_total);
+    unsigned long long total = 0;
+    MSD_CUDA_OK(cudaMemcpyAsync(&total, ctx->d_run_total, 8, cudaMemcpyDeviceToHost, sc));
+    MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    if (total > ctx->d_run_cap) {
+        const uint64_t cap = total + total / 8 + 1024;
+        if ((rc = dev_alloc(ctx, &ctx->d_run_start, cap))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_run_stop, cap))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_run_val, cap))) return rc;
+        ctx->d_run_cap = cap;
+    }
+    if (total > ctx->h_run_cap) {
+        const uint64_t cap = total + total / 8 + 1024;
+        if (ctx->h_run_start) cudaFreeHost(ctx->h_run_start);
+        if (ctx->h_run_stop) cudaFreeHost(ctx->h_run_stop);
+        if (ctx->h_run_val) cudaFreeHost(ctx->h_run_val);
+        ctx->h_run_start = ctx->h_run_stop = ctx->h_run_val = nullptr; ctx->h_run_cap = 0;
+        MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_run_start, cap * 4));
+        MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_run_stop, cap * 4));
+        MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_run_val, cap * 4));
+        ctx->h_run_cap = cap;
+    }
+    runs_write_kernel<F><<<n_tiles, kRunThreads, 0, sc>>>(arr, n, f, ctx->d_tile_base, ctx->d_run_start, ctx->d_run_val);
+    runs_stops_kernel<<<grid_for(total, 256, kSMs * 8), 256, 0, sc>>>(ctx->d_run_start, total, end, ctx->d_run_stop);
+    MSD_CUDA_OK(cudaGetLastError());
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_run_start, ctx->d_run_start, total * 4, cudaMemcpyDeviceToHost, sc));
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_run_stop, ctx->d_run_stop, total * 4, cudaMemcpyDeviceToHost, sc));
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_run_val, ctx->d_run_val, total * 4, cudaMemcpyDeviceToHost, sc));
+    MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    *n_runs_out = total;
+    return 0;
+}
+
+
+}  // namespace
+
+extern "C" {
+
+int msd_abi_version(void) { return MSD_ABI_VERSION; }
+
+int msd_create(int device, msd_ctx** out) {
+    if (!out) return MSD_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) return ctx_fail(nullptr, MSD_ENODEV, "no CUDA device: %s (libmosdepth_b200 has no CPU fallback)", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return ctx_fail(nullptr, MSD_ENODEV, "device %d out of range (%d devices)", device, n);
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return ctx_fail(nullptr, MSD_ENODEV, "cudaGetDeviceProperties failed");
+    if (p.major != 10) return ctx_fail(nullptr, MSD_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, p.major, p.minor);
+    if (cudaSetDevice(device) != cudaSuccess) return ctx_fail(nullptr, MSD_ENODEV, "cudaSetDevice failed");
+    msd_ctx* ctx = new msd_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cudaStreamCreate failed");
+    }
+    cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(InflateWarpState) * kInflateWarps));
+    cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    // default filters = mosdepth defaults (-F 1796, -Q 0, no length limits, default mode)
+    ctx->fp.mapq = 0; ctx->fp.min_len = -1; ctx->fp.max_len = INT64_MAX; ctx->fp.eflag = 1796; ctx->fp.iflag = 0; ctx->fp.mode = MSD_MODE_DEFAULT; ctx->fp.n_rg = 0; ctx->fp.rg_names = nullptr;
+    *out = ctx;
+    return MSD_OK;
+}
+
+void msd_destroy(msd_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    release_input(ctx);
+    dev_free(&ctx->d_rg); dev_free(&ctx->d_arena); dev_free(&ctx->d_depth_off); dev_free(&ctx->d_tlen); dev_free(&ctx->d_nprefilter);
+    for (int k = 0; k < 2; k++) {
+        dev_free(&ctx->d_comp[k]); dev_free(&ctx->d_infl[k]); dev_free(&ctx->d_desc[k]); dev_free(&ctx->d_rel[k]);
+        if (ctx->stage[k].h_desc) cudaFreeHost(ctx->stage[k].h_desc);
+        if (ctx->stage[k].h_rel) cudaFreeHost(ctx->stage[k].h_rel);
+        if (ctx->stage[k].h_bounce) cudaFreeHost(ctx->stage[k].h_bounce);
+        if (ctx->stage[k].free_ev) cudaEventDestroy(ctx->stage[k].free_ev);
+        if (ctx->comp_free[k]) cudaEventDestroy(ctx->comp_free[k]);
+        if (ctx->h2d_done[k]) cudaEventDestroy(ctx->h2d_done[k]);
+        dev_free(&ctx->live[k].e); dev_free(&ctx->live[k].arena); dev_free(&ctx->live[k].n); dev_free(&ctx->live[k].arena_used);
+    }
+    dev_free(&ctx->d_bstart); dev_free(&ctx->d_land); dev_free(&ctx->d_count); dev_free(&ctx->d_first); dev_free(&ctx->d_cnt);
+    dev_free(&ctx->d_recbase); dev_free(&ctx->d_recoff); dev_free(&ctx->d_status); dev_free(&ctx->d_ticket); dev_free(&ctx->d_inflate_err);
+    dev_free(&ctx->d_cs); dev_free(&ctx->d_rc);
+    dev_free(&ctx->mc.cls); dev_free(&ctx->mc.qhash); dev_free(&ctx->mc.endpos); dev_free(&ctx->mc.next); dev_free(&ctx->mc.slot);
+    dev_free(&ctx->mt.word); dev_free(&ctx->mt.head); dev_free(&ctx->mt.live);
+    dev_free(&ctx->d_tile_state); dev_free(&ctx->d_scan_ticket); dev_free(&ctx->d_hist); dev_free(&ctx->d_acc); dev_free(&ctx->d_racc);
+    dev_free(&ctx->d_dist512); dev_free(&ctx->d_rdist); dev_free(&ctx->d_tot_global); dev_free(&ctx->d_tot_region); dev_free(&ctx->d_tot_stats);
+    dev_free(&ctx->d_run_start); dev_free(&ctx->d_run_stop); dev_free(&ctx->d_run_val); dev_free(&ctx->d_tile_count); dev_free(&ctx->d_tile_base); dev_free(&ctx->d_run_total);
+    if (ctx->h_run_start) cudaFreeHost(ctx->h_run_start);
+    if (ctx->h_run_stop) cudaFreeHost(ctx->h_run_stop);
+    if (ctx->h_run_val) cudaFreeHost(ctx->h_run_val);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+    if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    delete ctx;
+}
+
+const char* msd_last_error(const msd_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+int msd_open_mem(msd_ctx* ctx, const void* bam_bytes, uint64_t n_bytes, int n_targets, const uint32_t* target_len, uint64_t first_record_voff) {
+    if (!ctx || !bam_bytes || n_bytes < 28) return ctx_fail(ctx, MSD_EINVAL, "msd_open_mem: bad buffer");
+    cudaSetDevice(ctx->device);
+    release_input(ctx);
+    // chunk buffers depend on the input size: drop the old ones
+    for (int k = 0; k < 2; k++) { dev_free(&ctx->d_comp[k]); dev_free(&ctx->d_infl[k]); dev_free(&ctx->d_desc[k]); dev_free(&ctx->d_rel[k]);
+        if (ctx->stage[k].h_desc) { cudaFreeHost(ctx->stage[k].h_desc); ctx->stage[k].h_desc = nullptr; }
+        if (ctx->stage[k].h_rel) { cudaFreeHost(ctx->stage[k].h_rel); ctx->stage[k].h_rel = nullptr; }
+        if (ctx->stage[k].h_bounce) { cudaFreeHost(ctx->stage[k].h_bounce); ctx->stage[k].h_bounce = nullptr; }
+        if (ctx->stage[k].free_ev) { cudaEventDestroy(ctx->stage[k].free_ev); ctx->stage[k].free_ev = nullptr; }
+        if (ctx->comp_free[k]) { cudaEventDestroy(ctx->comp_free[k]); ctx->comp_free[k] = nullptr; }
+        if (ctx->h2d_done[k]) { cudaEventDestroy(ctx->h2d_done[k]); ctx->h2d_done[k] = nullptr; }
+        ctx->stage[k].used = false;
+        dev_free(&ctx->live[k].e); dev_free(&ctx->live[k].arena); dev_free(&ctx->live[k].n); dev_free(&ctx->live[k].arena_used);
+    }
+    dev_free(&ctx->mc.cls); dev_free(&ctx->mc.qhash); dev_free(&ctx->mc.endpos); dev_free(&ctx->mc.next); dev_free(&ctx->mc.slot);
+    dev_free(&ctx->mt.word); dev_free(&ctx->mt.head); dev_free(&ctx->mt.live); ctx->mate_ready = false;
+    dev_free(&ctx->d_depth_off); dev_free(&ctx->d_tlen); dev_free(&ctx->d_nprefilter);
+    ctx->bytes = (const uint8_t*)bam_bytes; ctx->n_bytes = n_bytes; ctx->mapped = false;
+    return setup_common(ctx, n_targets, target_len, first_record_voff);
+}
+
+int msd_open(msd_ctx* ctx, const char* bam_path, int n_targets, const uint32_t* target_len, uint64_t first_record_voff) {
+    if (!ctx || !bam_path) return ctx_fail(ctx, MSD_EINVAL, "msd_open: bad arguments");
+    int fd = open(bam_path, O_RDONLY);
+    if (fd < 0) return ctx_fail(ctx, MSD_EIO, "cannot open %s: %s", bam_path, strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 28) { close(fd); return ctx_fail(ctx, MSD_EIO, "%s: not a BAM file (too short)", bam_path); }
+    void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return ctx_fail(ctx, MSD_EIO, "mmap(%s) failed: %s", bam_path, strerror(errno));
+    madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+    int rc = msd_open_mem(ctx, m, (uint64_t)st.st_size, n_targets, target_len, first_record_voff);
+    if (rc != 0) { munmap(m, (size_t)st.st_size); ctx->bytes = nullptr; return rc; }
+    ctx->mapped = true;
+    return MSD_OK;
+}
+
+int msd_set_spans(msd_ctx* ctx, int n, const uint64_t* voff_beg, const uint64_t* voff_end) {
+    if (!ctx || n < 0 || (n > 0 && (!voff_beg || !voff_end))) return ctx_fail(ctx, MSD_EINVAL, "msd_set_spans: bad arguments");
+    ctx->spans.clear();
+    for (int i = 0; i < n; i++) {
+        if ((voff_beg[i] >> 16) >= ctx->n_bytes) return ctx_fail(ctx, MSD_EINVAL, "span %d starts past end of file", i);
+        if (voff_end[i] && voff_end[i] <= voff_beg[i]) continue;   // empty span
+        ctx->spans.push_back({voff_beg[i], voff_end[i]});
+    }
+    if (n > 0 && ctx->spans.empty()) ctx->spans.push_back({~0ull, ~0ull});   // explicit "nothing to read"
+    dev_free(&ctx->d_staged); ctx->staged_beg = ctx->staged_end = 0;
+    return MSD_OK;
+}
+
+int msd_set_targets(msd_ctx* ctx, const uint8_t* want_target) {
+    if (!ctx) return MSD_EINVAL;
+    if (want_target) ctx->want.assign(want_target, want_target + ctx->n_targets); else ctx->want.assign(ctx->n_targets, 1);
+    return MSD_OK;
+}
+
+int msd_set_filters(msd_ctx* ctx, int mapq, int64_t min_len, int64_t max_len, uint16_t eflag, uint16_t iflag,
+                    const char* const* read_groups, int n_read_groups, int mode) {
+    if (!ctx || mode < 0 || mode > 2 || n_read_groups < 0) return ctx_fail(ctx, MSD_EINVAL, "msd_set_filters: bad arguments");
+    cudaSetDevice(ctx->device);
+    ctx->fp.mapq = mapq; ctx->fp.min_len = min_len; ctx->fp.max_len = max_len; ctx->fp.eflag = eflag; ctx->fp.iflag = iflag; ctx->fp.mode = mode;
+    ctx->rg_blob.clear();
+    for (int i = 0; i < n_read_groups; i++) { ctx->rg_blob.append(read_groups[i]); ctx->rg_blob.push_back('\0'); }
+    ctx->fp.n_rg = n_read_groups;
+    dev_free(&ctx->d_rg);
+    if (n_read_groups) {
+        int rc = dev_alloc(ctx, &ctx->d_rg, ctx->rg_blob.size() + 1); if (rc) return rc;
+        MSD_CUDA_OK(cudaMemcpy(ctx->d_rg, ctx->rg_blob.data(), ctx->rg_blob.size(), cudaMemcpyHostToDevice));
+    }
+    ctx->fp.rg_names = ctx->d_rg;
+    return MSD_OK;
+}
+
+int msd_stage(msd_ctx* ctx) {
+    if (!ctx || !ctx->bytes) return ctx_fail(ctx, MSD_EINVAL, "msd_stage: no input open");
+    cudaSetDevice(ctx->device);
+    uint64_t beg = ctx->first_voff >> 16, end = ctx->n_bytes;
+    if (!ctx->spans.empty()) {
+        beg = ~0ull; end = 0;
+        for (auto& s : ctx->spans) { if (s.beg == ~0ull) continue; beg = std::min(beg, s.beg >> 16); uint64_t e = s.end ? std::min<uint64_t>((s.end >> 16) + 65536 + 64, ctx->n_bytes) : ctx->n_bytes; end = std::max(end, e); }
+        if (beg == ~0ull) { beg = 0; end = 0; }
+    }
+    dev_free(&ctx->d_staged);
+    int rc = dev_alloc(ctx, &ctx->d_staged, end - beg + 256); if (rc) return rc;
+    MSD_CUDA_OK(cudaMemcpy(ctx->d_staged, ctx->bytes + beg, end - beg, cudaMemcpyHostToDevice));
+    ctx->staged_beg = beg; ctx->staged_end = end;
+    return MSD_OK;
+}
+
+int msd_run(msd_ctx* ctx) {
+    if (!ctx || !ctx->bytes) return ctx_fail(ctx, MSD_EINVAL, "msd_run: no input open");
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure_chunk_buffers(ctx))) return rc;
+    if ((rc = ensure_arena(ctx))) return rc;
+    if ((rc = ensure_query_buffers(ctx))) return rc;
+    const bool default_mode = ctx->fp.mode == MSD_MODE_DEFAULT;
+    if (default_mode && (rc = ensure_mate(ctx))) return rc;
+    ctx->fp.n_targets = ctx->n_targets;
+    ctx->ev_used = 0;
+    memset(&ctx->info, 0, sizeof ctx->info);
+    ctx->ran = false;
+    for (auto& r : ctx->results) { r.have = false; r.dist.clear(); }
+    cudaStream_t sc = ctx->s_compute, sx = ctx->s_copy;
+    StageTimes times;
+    cudaEvent_t ev_begin = next_event(ctx), ev_zero_end = next_event(ctx), ev_chunks_end = next_event(ctx), ev_end = next_event(ctx);
+
+    MSD_CUDA_OK(cudaEventRecord(ev_begin, sc));
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_arena, 0, ctx->arena_cells * 4, sc));                       // init, mosdepth.nim:238-248
+    MSD_CUDA_OK(cudaEventRecord(ev_zero_end, sc));
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_nprefilter, 0, sizeof(unsigned long long) * ctx->n_targets, sc));
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_rc, 0, sizeof(RunCounters), sc));
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_cs, 0, sizeof(ChunkState), sc));
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_inflate_err, 0, 4, sc));
+    int live_cur = 0;
+    if (default_mode) for (int k = 0; k < 2; k++) { MSD_CUDA_OK(cudaMemsetAsync(ctx->live[k].n, 0, 4, sc)); MSD_CUDA_OK(cudaMemsetAsync(ctx->live[k].arena_used, 0, 4, sc)); }
+
+    ContigTable ct{ctx->d_depth_off, ctx->d_tlen};
+    const uint32_t base = ctx->carry_cap;
+    std::vector<Span> spans = ctx->spans;
+    if (spans.empty()) spans.push_back({ctx->first_voff, 0});
+    uint64_t chunk_idx = 0;
+    const uint8_t* F = ctx->bytes; const uint64_t N = ctx->n_bytes;
+
+    for (const Span& sp : spans) {
+        if (sp.beg == ~0ull) continue;
+        uint64_t pos = sp.beg >> 16;
+        const uint32_t first_uoff = (uint32_t)(sp.beg & 0xffff);
+        const uint64_t end_c = sp.end ? (sp.end >> 16) : N; const uint32_t end_u = sp.end ? (uint32_t)(sp.end & 0xffff) : 0;
+        bool first_of_span = true, span_done = false;
+        while (!span_done) {
+            // ---- plan one chunk (host: BSIZE chase) -------------------------------------------------------
+            const int k = (int)(chunk_idx & 1);
+            StageSet& st = ctx->stage[k];
+            if (st.used) MSD_CUDA_OK(cudaEventSynchronize(st.free_ev));
+            uint32_t nb = 0; uint64_t comp_bytes = 0, infl = 0; const uint64_t chunk_src = pos; uint32_t total = 0; bool truncated_last = false;
+            while (nb < ctx->max_blocks) {
+                if (pos >= N || pos > end_c || (pos == end_c && end_u == 0)) { span_done = true; break; }
+                uint32_t xlen = 0, isize = 0;
+                uint32_t blen = bgzf_header(F, N, pos, &xlen, &isize);
+                if (!blen) return ctx_fail(ctx, MSD_EIO, "invalid BGZF block header at file offset %llu", (unsigned long long)pos);
+                if (isize > 65536) return ctx_fail(ctx, MSD_EIO, "BGZF block at %llu claims %u inflated bytes", (unsigned long long)pos, isize);
+                if (comp_bytes + blen > ctx->comp_cap || infl + isize > ctx->infl_cap) { if (nb == 0 && comp_bytes == 0) return ctx_fail(ctx, MSD_ENOMEM, "chunk buffers too small for one BGZF block"); break; }
+                if (isize > 0) {
+                    st.h_desc[nb].src = (pos - chunk_src) + 12 + xlen; st.h_desc[nb].clen = blen - xlen - 20; st.h_desc[nb].isize = isize;
+                    st.h_desc[nb].dst = (uint64_t)base + infl; st.h_rel[nb] = (uint32_t)infl; nb++;
+                }
+                const bool is_end_block = (pos == end_c);
+                comp_bytes += blen; pos += blen;
+                if (is_end_block) { total = (uint32_t)infl + std::min(end_u, isize); truncated_last = true; infl += isize; span_done = true; break; }
+                infl += isize;
+            }
+            if (!truncated_last) total = (uint32_t)infl;
+            if (first_of_span && nb && first_uoff > st.h_desc[0].isize) return ctx_fail(ctx, MSD_EINVAL, "span start offset %u beyond its block", first_uoff);
+            if (nb == 0) { if (span_done) break; continue; }
+            st.h_rel[nb] = (uint32_t)infl;
+            st.used = true;
+            // ---- compressed bytes -> device -------------------------------------------------------------------
+            const uint8_t* d_comp;
+            if (ctx->d_staged && chunk_src >= ctx->staged_beg && chunk_src + comp_bytes <= ctx->staged_end) {
+                d_comp = ctx->d_staged + (chunk_src - ctx->staged_beg);
+                // descriptor src offsets assume a 4-byte aligned base: fold the misalignment into src
+                const uint32_t mis = (uint32_t)((uintptr_t)d_comp & 3u);
+                if (mis) { d_comp -= mis; for (uint32_t i = 0; i < nb; i++) st.h_desc[i].src += mis; }
+            } else {
+                if ((rc = ensure_bounce(ctx))) return rc;
+                MSD_CUDA_OK(cudaStreamWaitEvent(sx, ctx->comp_free[k], 0));
+                cudaEvent_t h0 = next_event(ctx), h1 = next_event(ctx);
+                MSD_CUDA_OK(cudaEventRecord(h0, sx));
+                const uint8_t* srcp = F + chunk_src;
+                if (!ctx->src_pinned) { memcpy(st.h_bounce, srcp, comp_bytes); srcp = st.h_bounce; }
+                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_comp[k], srcp, comp_bytes, cudaMemcpyHostToDevice, sx));
+                MSD_CUDA_OK(cudaEventRecord(h1, sx));
+                MSD_CUDA_OK(cudaEventRecord(ctx->h2d_done[k], sx));
+                MSD_CUDA_OK(cudaStreamWaitEvent(sc, ctx->h2d_done[k], 0));
+                times.h2d.push_back({h0, h1});
+                d_comp = ctx->d_comp[k];
+            }
+            MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_desc[k], st.h_desc, sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, sc));
+            MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_rel[k], st.h_rel, sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, sc));
+            MSD_CUDA_OK(cudaEventRecord(st.free_ev, sc));
+            // ---- K1 inflate ---------------------------------------------------------------------------------
+            uint8_t* infl_buf = ctx->d_infl[k];
+            cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
+            MSD_CUDA_OK(cudaMemsetAsync(ctx->d_ticket, 0, 4, sc));
+            MSD_CUDA_OK(cudaEventRecord(e0, sc));
+            {
+                const int ctas = std::min<int>((nb + kInflateWarps - 1) / kInflateWarps, kSMs * 4);
+                bgzf_inflate_kernel<<<ctas, kInflateWarps * 32, sizeof(InflateWarpState) * kInflateWarps, sc>>>(
+                    d_comp, infl_buf, ctx->d_desc[k], (int)nb, ctx->d_ticket, ctx->d_status, ctx->d_inflate_err);
+                ctx->info.n_launches++; ctx->info.n_inflate_launches++;
+            }
+            MSD_CUDA_OK(cudaEventRecord(e1, sc));
+            MSD_CUDA_OK(cudaEventRecord(ctx->comp_free[k], sc));
+            // ---- K2 framing ---------------------------------------------------------------------------------
+            const int nblk = (int)nb + 1;   // + carry pseudo-block
+            frame_setup_kernel<<<(nb + 255) / 256, 256, 0, sc>>>(ctx->d_cs, ctx->d_rel[k], (int)nb, base, first_of_span ? first_uoff : 0u, total, first_of_span ? 1 : 0, ctx->d_bstart);
+            frame_spec_kernel<<<(nblk + 127) / 128, 128, 0, sc>>>(infl_buf, ctx->d_cs, ctx->d_bstart, nblk, ctx->d_land, ctx->d_count);
+            frame_link_kernel<<<1, 1024, 0, sc>>>(infl_buf, ctx->d_cs, ctx->d_bstart, nblk, ctx->d_land, ctx->d_count, ctx->d_first, ctx->d_cnt, ctx->d_recbase);
+            frame_emit_kernel<<<(nblk + 127) / 128, 128, 0, sc>>>(infl_buf, ctx->d_first, ctx->d_cnt, ctx->d_recbase, nblk, ctx->d_recoff);
+            ctx->info.n_launches += 4;
+            MSD_CUDA_OK(cudaEventRecord(e2, sc));
+            // ---- K3/K5 (+K4) ------------------------------------------------------------------------------------
+            const int rgrid = kSMs * 8;
+            records_kernel<<<rgrid, 256, 0, sc>>>(infl_buf, ctx->d_recoff, ctx->d_cs, ctx->fp, ct, ctx->d_arena, ctx->d_nprefilter, ctx->mc, ctx->d_rc);
+            ctx->info.n_launches++;
+            if (default_mode) {
+                LiveList& L = ctx->live[live_cur]; LiveList& Ln = ctx->live[live_cur ^ 1];
+                MSD_CUDA_OK(cudaMemsetAsync(ctx->mt.word, 0xff, 8ull * ctx->mate_slots, sc));
+                MSD_CUDA_OK(cudaMemsetAsync(ctx->mt.head, 0xff, 4ull * ctx->mate_slots, sc));
+                MSD_CUDA_OK(cudaMemsetAsync(ctx->mt.live, 0xff, 4ull * ctx->mate_slots, sc));
+                MSD_CUDA_OK(cudaMemsetAsync(Ln.n, 0, 4, sc));
+                MSD_CUDA_OK(cudaMemsetAsync(Ln.arena_used, 0, 4, sc));
+                mate_reinsert_kernel<<<kSMs * 2, 256, 0, sc>>>(ctx->mt, L, infl_buf, ctx->d_recoff, ctx->d_rc);
+                mate_link_kernel<<<rgrid, 256, 0, sc>>>(ctx->mt, L, infl_buf, ctx->d_recoff, ctx->d_cs, ctx->mc, 0, ctx->d_rc);
+                mate_link_kernel<<<rgrid, 256, 0, sc>>>(ctx->mt, L, infl_buf, ctx->d_recoff, ctx->d_cs, ctx->mc, 1, ctx->d_rc);
+                mate_replay_kernel<<<rgrid, 256, 0, sc>>>(ctx->mt, L, Ln, infl_buf, ctx->d_recoff, ctx->d_cs, ctx->mc, ct, ctx->d_arena, ctx->d_rc);
+                mate_carry_kernel<<<kSMs * 2, 256, 0, sc>>>(L, Ln, ctx->d_rc);
+                ctx->info.n_launches += 5;
+                live_cur ^= 1;
+            }
+            MSD_CUDA_OK(cudaEventRecord(e3, sc));
+            // unfinished tail -> front of the other inflated buffer
+            carry_copy_kernel<<<64, 256, 0, sc>>>(infl_buf, ctx->d_infl[k ^ 1], ctx->d_cs, base, ctx->carry_cap, &ctx->d_rc->error);
+            ctx->info.n_launches++;
+            MSD_CUDA_OK(cudaGetLastError());
+            times.inflate.push_back({e0, e1}); times.frame.push_back({e1, e2}); times.records.push_back({e2, e3});
+            ctx->info.bytes_compressed += comp_bytes; ctx->info.bytes_inflated += infl; ctx->info.n_blocks += nb;
+            first_of_span = false;
+            chunk_idx++;
+        }
+    }
+    MSD_CUDA_OK(cudaEventRecord(ev_chunks_end, sc));
+    MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    // ---- errors raised by the kernels --------------------------------------------------------------------------
+    uint32_t inflate_err = 0; ChunkState cs_h; RunCounters rc_h;
+    MSD_CUDA_OK(cudaMemcpy(&inflate_err, ctx->d_inflate_err, 4, cudaMemcpyDeviceToHost));
+    MSD_CUDA_OK(cudaMemcpy(&cs_h, ctx->d_cs, sizeof cs_h, cudaMemcpyDeviceToHost));
+    MSD_CUDA_OK(cudaMemcpy(&rc_h, ctx->d_rc, sizeof rc_h, cudaMemcpyDeviceToHost));
+    if (inflate_err) return ctx_fail(ctx, MSD_EDATA, "%u BGZF block(s) failed to inflate (corrupt DEFLATE stream)", inflate_err);
+    if (cs_h.error) return ctx_fail(ctx, MSD_EDATA, "corrupt BAM record chain (bad block_size)");
+    if (rc_h.error == 1) return ctx_fail(ctx, MSD_ENOMEM, "mate hash table full: raise MSD_MATE_SLOTS");
+    if (rc_h.error == 2) return ctx_fail(ctx, MSD_ENOMEM, "live mate list full: raise MSD_LIVE_CAP or unfinished record larger than MSD_CARRY_MB");
+    if (rc_h.error == 3) return ctx_fail(ctx, MSD_ENOMEM, "live mate arena full: raise MSD_LIVE_ARENA_MB");
+    ctx->info.n_events = rc_h.n_events; ctx->info.n_records = rc_h.n_records;
+    // ---- per contig: prefix sum + whole-contig stats -----------------------------------------------------------
+    std::vector<unsigned long long> npre(ctx->n_targets);
+    MSD_CUDA_OK(cudaMemcpy(npre.data(), ctx->d_nprefilter, sizeof(unsigned long long) * ctx->n_targets, cudaMemcpyDeviceToHost));
+    cudaEvent_t s0 = next_event(ctx), s1 = next_event(ctx);
+    MSD_CUDA_OK(cudaEventRecord(s0, sc));
+    for (int t = 0; t < ctx->n_targets; t++) {
+        ctx->n_prefilter[t] = (long long)npre[t];
+        if (!ctx->want[t] || npre[t] == 0) continue;
+        const uint32_t tlen = ctx->tlen[t];
+        ctx->info.n_depth_cells += (uint64_t)tlen + 1;
+        init_accum_kernel<<<1, 1, 0, sc>>>(ctx->d_acc, nullptr);
+        MSD_CUDA_OK(cudaMemsetAsync(ctx->d_hist, 0, 8ull * kDistBins, sc));
+        if ((rc = run_scan(ctx, ctx->d_arena + ctx->depth_off[t], tlen + 1, tlen, 1))) return rc;
+        ContigAccum acc;
+        MSD_CUDA_OK(cudaMemcpyAsync(&acc, ctx->d_acc, sizeof acc, cudaMemcpyDeviceToHost, sc));
+        add_hist_kernel<<<kSMs, 256, 0, sc>>>(ctx->d_tot_global, ctx->d_hist, kDistBins);
+        MSD_CUDA_OK(cudaStreamSynchronize(sc));
+        ContigResult& R = ctx->results[t];
+        R.have = true; R.stat.cum_length = tlen; R.stat.cum_depth = acc.cum_depth; R.stat.min_depth = acc.min_depth; R.stat.max_depth = acc.max_depth;
+        add_stats_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats, (long long)tlen, acc.cum_depth, acc.min_depth, acc.max_depth);
+        // distribution: bins up to the maximum depth seen (signed view: negative depths are skipped by inc())
+        int64_t top = 0;
+        if (tlen) { uint32_t mx = acc.max_depth; top = (mx > 0x7fffffffu) ? (int64_t)kMaxCoverage : (int64_t)std::min<uint32_t>(mx, kMaxCoverage); }
+        R.dist.assign((size_t)top + 1, 0);
+        MSD_CUDA_OK(cudaMemcpy(R.dist.data(), ctx->d_hist, 8ull * (top + 1), cudaMemcpyDeviceToHost));
+        while (R.dist.size() > 1 && R.dist.back() == 0) R.dist.pop_back();
+        ctx->info.n_launches += 4;
+    }
+    MSD_CUDA_OK(cudaEventRecord(s1, sc));
+    MSD_CUDA_OK(cudaEventRecord(ev_end, sc));
+    MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev_begin, ev_end); ctx->info.ms_total = ms;
+    cudaEventElapsedTime(&ms, ev_begin, ev_zero_end); ctx->info.ms_zero = ms;
+    cudaEventElapsedTime(&ms, s0, s1); ctx->info.ms_scan = ms;
+    ctx->info.ms_h2d = sum_ms(times.h2d); ctx->info.ms_inflate = sum_ms(times.inflate); ctx->info.ms_frame = sum_ms(times.frame); ctx->info.ms_records = sum_ms(times.records);
+    ctx->ran = true;
+    return MSD_OK;
+}
+
+int msd_last_run_info(const msd_ctx* ctx, msd_run_info* out) { if (!ctx || !out) return MSD_EINVAL; *out = ctx->info; return MSD_OK; }
+
+int msd_contig_records(msd_ctx* ctx, int tid, int64_t* n) {
+    if (!ctx || !ctx->ran) return ctx_fail(ctx, MSD_EINVAL, "msd_contig_records: call msd_run first");
+    if (tid < 0 || tid >= ctx->n_targets || !ctx->want[tid]) { if (n) *n = 0; return -1; }
+    if (n) *n = ctx->n_prefilter[tid];
+    return ctx->n_prefilter[tid] > 0 ? tid : -2;
+}
+
+int msd_contig_stats(msd_ctx* ctx, int tid, msd_depth_stat* chrom_stat, int64_t* dist, int64_t dist_cap, int64_t* dist_len) {
+    int rc = check_tid(ctx, tid, "msd_contig_stats"); if (rc) return rc;
+    const ContigResult& R = ctx->results[tid];
+    if (chrom_stat) *chrom_stat = R.stat;
+    if (dist_len) *dist_len = (int64_t)R.dist.size();
+    if (dist) {
+        if (dist_cap < (int64_t)R.dist.size()) return ctx_fail(ctx, MSD_EINVAL, "msd_contig_stats: dist_cap %lld < %zu", (long long)dist_cap, R.dist.size());
+        memcpy(dist, R.dist.data(), 8 * R.dist.size());
+    }
+    return MSD_OK;
+}
+
+int64_t msd_n_windows(uint32_t tlen, uint32_t window) {
+    // window_gen (mosdepth.nim:382-388): [k*w, (k+1)*w) while start + w < tlen, then [start, tlen) if start != tlen
+    if (tlen == 0) return 0;
+    if (window == 0) return -1;
+    return ((int64_t)tlen + window - 1) / window;
+}
+
+int64_t msd_windows(msd_ctx* ctx, int tid, uint32_t window, int use_median, double* value_out, int64_t value_cap,
+                    msd_depth_stat* region_stat, int64_t* region_dist512) {
+    int rc = check_tid(ctx, tid, "msd_windows"); if (rc) return rc;
+    if (window == 0) return ctx_fail(ctx, MSD_EINVAL, "msd_windows: window must be > 0");
+    const uint32_t tlen = ctx->tlen[tid];
+    const int64_t nw = msd_n_windows(tlen, window);
+    if (value_out && value_cap < nw) return ctx_fail(ctx, MSD_EINVAL, "msd_windows: value_cap %lld < %lld windows", (long long)value_cap, (long long)nw);
+    if ((rc = ensure_scratch(ctx, (uint64_t)std::max<int64_t>(nw, 1) * 8))) return rc;
+    cudaStream_t sc = ctx->s_compute;
+    init_accum_kernel<<<1, 1, 0, sc>>>(nullptr, ctx->d_racc);
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_dist512, 0, 8 * kWindowDistBins, sc));
+    if (nw > 0) {
+        windows_kernel<<<grid_for((uint64_t)nw, 256, kSMs * 8), 256, 0, sc>>>(ctx->d_arena + ctx->depth_off[tid], tlen, window, nw, use_median,
+                                                                            (double*)ctx->d_scratch, ctx->d_racc, ctx->d_dist512);
+        MSD_CUDA_OK(cudaGetLastError());
+    }
+    add_hist_kernel<<<2, 256, 0, sc>>>(ctx->d_tot_region, ctx->d_dist512, kWindowDistBins);
+    MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    RegionAccum h; fetch_region_accum(ctx, region_stat, &h);
+    if (h.neg_seen) return ctx_fail(ctx, MSD_ENEGDEPTH, "error setting negative depth value (median mode)");
+    add_stats_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats + 4, (long long)h.cum_length, h.cum_depth, h.min_depth, h.max_depth);
+    if (value_out && nw > 0) MSD_CUDA_OK(cudaMemcpy(value_out, ctx->d_scratch, (size_t)nw * 8, cudaMemcpyDeviceToHost));
+    if (region_dist512) MSD_CUDA_OK(cudaMemcpy(region_dist512, ctx->d_dist512, 8 * kWindowDistBins, cudaMemcpyDeviceToHost));
+    MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    return nw;
+}
+
+int msd_regions(msd_ctx* ctx, int tid, int64_t n, const uint32_t* start, const uint32_t* stop, int use_median, double* value_out,
+                msd_depth_stat* region_stat, int64_t* region_dist, int64_t dist_cap, int64_t* dist_len, const int32_t* thresholds,
+                int n_thr, int64_t* thr_counts) {
+    int rc = check_tid(ctx, tid, "msd_regions"); if (rc) return rc;
+    if (n < 0 || (n > 0 && (!start || !stop)) || n_thr < 0 || (n_thr > 0 && (!thresholds || !thr_counts))) return ctx_fail(ctx, MSD_EINVAL, "msd_regions: bad arguments");
+    const uint32_t tlen = ctx->tlen[tid];
+    cudaStream_t sc = ctx->s_compute;
+    // scratch layout: starts | stops | values | thresholds | thr_counts
+    const uint64_t nn = (uint64_t)std::max<int64_t>(n, 1);
+    const uint64_t o_start = 0, o_stop = o_start + nn * 4, o_val = ((o_stop + nn * 4 + 7) / 8) * 8, o_thr = o_val + nn * 8, o_cnt = ((o_thr + (uint64_t)std::max(n_thr, 1) * 4 + 7) / 8) * 8;
+    const uint64_t bytes = o_cnt + nn * (uint64_t)std::max(n_thr, 1) * 8;
+    if ((rc = ensure_scratch(ctx, bytes))) return rc;
+    uint8_t* S = (uint8_t*)ctx->d_scratch;
+    init_accum_kernel<<<1, 1, 0, sc>>>(nullptr, ctx->d_racc);
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_rdist, 0, 8ull * kDistBins, sc));
+    if (n > 0) {
+        MSD_CUDA_OK(cudaMemcpyAsync(S + o_start, start, (size_t)n * 4, cudaMemcpyHostToDevice, sc));
+        MSD_CUDA_OK(cudaMemcpyAsync(S + o_stop, stop, (size_t)n * 4, cudaMemcpyHostToDevice, sc));
+        if (n_thr) MSD_CUDA_OK(cudaMemcpyAsync(S + o_thr, thresholds, (size_t)n_thr * 4, cudaMemcpyHostToDevice, sc));
+        regions_kernel<<<grid_for((uint64_t)n, 256, kSMs * 8), 256, 0, sc>>>(ctx->d_arena + ctx->depth_off[tid], tlen, n, (const uint32_t*)(S + o_start),
+                                                                           (const uint32_t*)(S + o_stop), use_median, (double*)(S + o_val), ctx->d_racc, ctx->d_rdist,
+                                                                           (const int32_t*)(S + o_thr), n_thr, (unsigned long long*)(S + o_cnt));
+        MSD_CUDA_OK(cudaGetLastError());
+    }
+    add_hist_kernel<<<kSMs, 256, 0, sc>>>(ctx->d_tot_region, ctx->d_rdist, kDistBins);
+    MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    RegionAccum h; fetch_region_accum(ctx, region_stat, &h);
+    if (h.neg_seen) return ctx_fail(ctx, MSD_ENEGDEPTH, "error setting negative depth value (median mode)");
+    add_stats_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats + 4, (long long)h.cum_length, h.cum_depth, h.min_depth, h.max_depth);
+    if (n > 0 && value_out) MSD_CUDA_OK(cudaMemcpy(value_out, S + o_val, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    if (n > 0 && n_thr) MSD_CUDA_OK(cudaMemcpy(thr_counts, S + o_cnt, (size_t)n * n_thr * 8, cudaMemcpyDeviceToHost));
+    if (region_dist || dist_len) {
+        // length = 1 + highest non-zero bin, bounded by the region maximum
+        int64_t top = (h.max_depth > 0x7fffffffu) ? (int64_t)kMaxCoverage : (int64_t)std::min<uint32_t>(h.max_depth, kMaxCoverage);
+        std::vector<int64_t> tmp((size_t)top + 1, 0);
+        MSD_CUDA_OK(cudaMemcpy(tmp.data(), ctx->d_rdist, 8ull * (top + 1), cudaMemcpyDeviceToHost));
+        while (tmp.size() > 1 && tmp.back() == 0) tmp.pop_back();
+        if (dist_len) *dist_len = (int64_t)tmp.size();
+        if (region_dist) { if (dist_cap < (int64_t)tmp.size()) return ctx_fail(ctx, MSD_EINVAL, "msd_regions: dist_cap too small"); memcpy(region_dist, tmp.data(), 8 * tmp.size()); }
+    }
+    MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    return MSD_OK;
+}
+
+int msd_per_base_runs(msd_ctx* ctx, int tid, const int32_t** start, const int32_t** stop, const int32_t** depth, int64_t* n_runs) {
+    int rc = check_tid(ctx, tid, "msd_per_base_runs"); if (rc) return rc;
+    if ((rc = ensure_query_buffers(ctx))) return rc;
+    const uint32_t tlen = ctx->tlen[tid];
+    uint64_t total = 0;
+    if ((rc = compute_runs(ctx, ctx->d_arena + ctx->depth_off[tid], tlen, (int32_t)tlen, IdentityF(), &total))) return rc;
+    if (start) *start = ctx->h_run_start; if (stop) *stop = ctx->h_run_stop; if (depth) *depth = ctx->h_run_val;
+    if (n_runs) *n_runs = (int64_t)total;
+    return MSD_OK;
+}
+
+int msd_quantized_runs(msd_ctx* ctx, int tid, const int64_t* quants, int n_q, const int32_t** start, const int32_t** stop,
+                       const int32_t** bin, int64_t* n_runs) {
+    int rc = check_tid(ctx, tid, "msd_quantized_runs"); if (rc) return rc;
+    if (!quants || n_q < 2 || n_q > kMaxQuants) return ctx_fail(ctx, MSD_EINVAL, "msd_quantized_runs: need 2..%d quantize values", kMaxQuants);
+    if ((rc = ensure_query_buffers(ctx))) return rc;
+    const uint32_t tlen = ctx->tlen[tid];
+    QuantF f; f.qa.n = n_q; for (int i = 0; i < n_q; i++) f.qa.q[i] = quants[i];
+    // gen_quantized scans pos in 0 ..< arr.high-1 = tlen-1 (:132) but seeds from arr[0] even when that range is empty (:129)
+    const uint32_t n_eff = tlen >= 2 ? tlen - 1 : (tlen ? 1u : 0u);
+    uint64_t total = 0;
+    if ((rc = compute_runs(ctx, ctx->d_arena + ctx->depth_off[tid], n_eff, (int32_t)tlen, f, &total))) return rc;
+    // keep what the reference yields: bin != -1 and bin < len(lookup) = n_q-1 (:136,:140); segments stay in order
+    uint64_t w = 0;
+    for (uint64_t i = 0; i < total; i++) {
+        const int32_t b = ctx->h_run_val[i];
+        if (b == -1 || b >= n_q - 1) continue;
+        ctx->h_run_start[w] = ctx->h_run_start[i]; ctx->h_run_stop[w] = ctx->h_run_stop[i]; ctx->h_run_val[w] = b; w++;
+    }
+    if (start) *start = ctx->h_run_start; if (stop) *stop = ctx->h_run_stop; if (bin) *bin = ctx->h_run_val;
+    if (n_runs) *n_runs = (int64_t)w;
+    return MSD_OK;
+}
+
+int msd_totals_device(msd_ctx* ctx, void** global_dist, void** region_dist, int64_t* n_bins, void** stats8) {
+    if (!ctx) return MSD_EINVAL;
+    cudaSetDevice(ctx->device);
+    int rc = ensure_query_buffers(ctx); if (rc) return rc;
+    if (global_dist) *global_dist = ctx->d_tot_global; if (region_dist) *region_dist = ctx->d_tot_region;
+    if (n_bins) *n_bins = kDistBins; if (stats8) *stats8 = ctx->d_tot_stats;
+    return MSD_OK;
+}
+
+int msd_totals_reset(msd_ctx* ctx) {
+    if (!ctx || !ctx->d_tot_global) return MSD_EINVAL;
+    cudaSetDevice(ctx->device);
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_tot_global, 0, 8ull * kDistBins, ctx->s_compute));
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_tot_region, 0, 8ull * kDistBins, ctx->s_compute));
+    init_stats_kernel<<<1, 1, 0, ctx->s_compute>>>(ctx->d_tot_stats);
+    MSD_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));
+    return MSD_OK;
+}
+
+int64_t msd_debug_inflate(msd_ctx* ctx, const void* bgzf_bytes, uint64_t n_bytes, void* out, uint64_t out_cap) {
+    if (!ctx || !bgzf_bytes || !out) return ctx_fail(ctx, MSD_EINVAL, "msd_debug_inflate: bad arguments");
+    cudaSetDevice(ctx->device);
+    const uint8_t* F = (const uint8_t*)bgzf_bytes;
+    std::vector<BlockDesc> desc; uint64_t pos = 0, infl = 0;
+    while (pos < n_bytes) {
+        uint32_t xlen = 0, isize = 0; uint32_t blen = bgzf_header(F, n_bytes, pos, &xlen, &isize);
+        if (!blen) return ctx_fail(ctx, MSD_EIO, "invalid BGZF block header at %llu", (unsigned long long)pos);
+        if (isize) { BlockDesc d; d.src = pos + 12 + xlen; d.clen = blen - xlen - 20; d.isize = isize; d.dst = infl; desc.push_back(d); infl += isize; }
+        pos += blen;
+    }
+    if (infl > out_cap) return ctx_fail(ctx, MSD_EINVAL, "msd_debug_inflate: need %llu bytes", (unsigned long long)infl);
+    if (desc.empty()) return 0;
+    uint8_t *d_c = nullptr, *d_o = nullptr; BlockDesc* d_d = nullptr; uint32_t *d_s = nullptr, *d_t = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, &d_c, n_bytes + 256)) || (rc = dev_alloc(ctx, &d_o, infl + 256)) || (rc = dev_alloc(ctx, &d_d, desc.size())) ||
+        (rc = dev_alloc(ctx, &d_s, desc.size())) || (rc = dev_alloc(ctx, &d_t, 2))) { dev_free(&d_c); dev_free(&d_o); dev_free(&d_d); dev_free(&d_s); dev_free(&d_t); return rc; }
+    cudaStream_t sc = ctx->s_compute;
+    cudaMemcpyAsync(d_c, F, n_bytes, cudaMemcpyHostToDevice, sc);
+    cudaMemcpyAsync(d_d, desc.data(), sizeof(BlockDesc) * desc.size(), cudaMemcpyHostToDevice, sc);
+    cudaMemsetAsync(d_t, 0, 8, sc);
+    const int nb = (int)desc.size();
+    const int ctas = std::min<int>((nb + kInflateWarps - 1) / kInflateWarps, kSMs * 4);
+    bgzf_inflate_kernel<<<ctas, kInflateWarps * 32, sizeof(InflateWarpState) * kInflateWarps, sc>>>(d_c, d_o, d_d, nb, d_t, d_s, d_t + 1);
+    cudaError_t e = cudaGetLastError();
+    uint32_t errs[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(errs, d_t, 8, cudaMemcpyDeviceToHost, sc);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, infl, cudaMemcpyDeviceToHost, sc);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sc);
+    std::vector<uint32_t> status(desc.size());
+    if (e == cudaSuccess && errs[1]) cudaMemcpy(status.data(), d_s, 4 * desc.size(), cudaMemcpyDeviceToHost);
+    dev_free(&d_c); dev_free(&d_o); dev_free(&d_d); dev_free(&d_s); dev_free(&d_t);
+    if (e != cudaSuccess) return ctx_fail(ctx, MSD_ECUDA, "msd_debug_inflate: %s", cudaGetErrorString(e));
+    if (errs[1]) { size_t b = 0; while (b < status.size() && !status[b]) b++; return ctx_fail(ctx, MSD_EDATA, "%u block(s) failed to inflate; first: block %zu status %u", errs[1], b, b < status.size() ? status[b] : 0u); }
+    return (int64_t)infl;
+}
+
+int msd_debug_depth(msd_ctx* ctx, int tid, int32_t* out, int64_t out_cap) {
+    if (!ctx || !ctx->ran || tid < 0 || tid >= ctx->n_targets || !ctx->want[tid] || !out) return ctx_fail(ctx, MSD_EINVAL, "msd_debug_depth: bad arguments");
+    cudaSetDevice(ctx->device);
+    const int64_t n = (int64_t)ctx->tlen[tid] + 1;
+    if (out_cap < n) return ctx_fail(ctx, MSD_EINVAL, "msd_debug_depth: need %lld cells", (long long)n);
+    MSD_CUDA_OK(cudaMemcpy(out, ctx->d_arena + ctx->depth_off[tid], (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return MSD_OK;
+}
+
+int msd_debug_cumsum(msd_ctx* ctx, int32_t* inout, int64_t n) {
+    if (!ctx || !inout || n < 0 || n > 0xfffffff0ll) return ctx_fail(ctx, MSD_EINVAL, "msd_debug_cumsum: bad arguments");
+    cudaSetDevice(ctx->device);
+    int rc = ensure_query_buffers(ctx); if (rc) return rc;
+    if (n == 0) return MSD_OK;
+    int32_t* d = nullptr;
+    if ((rc = dev_alloc(ctx, &d, (uint64_t)n + 32))) return rc;
+    cudaError_t e = cudaMemcpyAsync(d, inout, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->s_compute);
+    if (e == cudaSuccess) { rc = run_scan(ctx, d, (uint32_t)n, 0, 0); if (rc) { dev_free(&d); return rc; } }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(inout, d, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->s_compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_compute);
+    dev_free(&d);
+    if (e != cudaSuccess) return ctx_fail(ctx, MSD_ECUDA, "msd_debug_cumsum: %s", cudaGetErrorString(e));
+    return MSD_OK;
+}
+
+}  // extern "C"

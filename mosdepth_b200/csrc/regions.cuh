@@ -1,0 +1,149 @@
+// regions.cuh -- K7 region_reduce: the per-region consumers of the depth array.
+//
+//   imean() mean branch, mosdepth.nim:410-413: result += float64(v[i]) / L, strictly in index order.  The
+//   formatted value depends on that order at rounding ties, so each region's chain is run by
+//   one thread with IEEE round-to-nearest division and addition (__ddiv_rn / __dadd_rn, no reassociation, no
+//   fast-math).  The quotient is only recomputed when the depth value changes (same bits, fewer divisions).
+//   imean() median branch :404-408 + CountStat depthstat.nim:16-30: the stop_n-th smallest of min(v, 65535),
+//   found by bisection on the value range instead of a 65536-bin table.
+//   newDepthStat over the region slice :723-724, window-dist bin :737-739, per-base region dist :741,
+//   threshold counts :549-553.
+#pragma once
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace msd {
+
+struct RegionAccum {
+    unsigned long long cum_length, cum_depth;
+    unsigned int min_depth, max_depth;
+    unsigned int neg_seen, pad;
+};
+
+// CountStat.median over arr[a, b) (depthstat.nim:23-30): values clipped to 65535; negative -> error flag
+MSD_D double region_median(const int32_t* __restrict__ arr, uint32_t a, uint32_t b, unsigned int* neg_seen) {
+    const int64_t n = (int64_t)b - (int64_t)a;
+    if (n <= 0) return 0.0;
+    const int64_t stop_n = (int64_t)(0.5 + (double)n * 0.5);
+    int32_t lo = 65535, hi = 0;
+    for (uint32_t i = a; i < b; i++) {
+        int32_t v = arr[i];
+        if (v < 0) { atomicExch(neg_seen, 1u); v = 0; }
+        if (v > 65535) v = 65535;
+        lo = v < lo ? v : lo; hi = v > hi ? v : hi;
+    }
+    if (stop_n <= 0) return 0.0;   // cum(0) >= 0 at i = 0
+    // smallest x in [lo, hi] with #{v <= x} >= stop_n
+    while (lo < hi) {
+        const int32_t mid = lo + ((hi - lo) >> 1);
+        int64_t c = 0;
+        for (uint32_t i = a; i < b; i++) { int32_t v = arr[i]; if (v < 0) v = 0; if (v > 65535) v = 65535; c += (v <= mid); }
+        if (c >= stop_n) hi = mid; else lo = mid + 1;
+    }
+    return (double)lo;
+}
+
+// sequential float64 mean of arr[a, e) with divisor L (mosdepth.nim:411-413) + slice stats
+MSD_D double region_mean_seq(const int32_t* __restrict__ arr, uint32_t a, uint32_t e, double L) {
+    double acc = 0.0, q = 0.0; int32_t last = 0; bool have = false;
+    for (uint32_t i = a; i < e; i++) {
+        const int32_t v = __ldg(arr + i);
+        if (!have || v != last) { q = __ddiv_rn((double)v, L); last = v; have = true; }
+        acc = __dadd_rn(acc, q);
+    }
+    return acc;
+}
+
+MSD_D void slice_stats(const int32_t* __restrict__ arr, uint32_t a, uint32_t b, unsigned long long& sum, uint32_t& mn, uint32_t& mx) {
+    for (uint32_t i = a; i < b; i++) { const int32_t d = __ldg(arr + i); sum += (unsigned long long)(long long)d; const uint32_t u = (uint32_t)d; mn = u < mn ? u : mn; mx = u > mx ? u : mx; }
+}
+
+MSD_D void block_accumulate(RegionAccum* __restrict__ acc, unsigned long long len, unsigned long long sum, uint32_t mn, uint32_t mx) {
+    // warp reduce, then one atomic set per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        len += __shfl_down_sync(0xffffffffu, len, o); sum += __shfl_down_sync(0xffffffffu, sum, o);
+        uint32_t a = __shfl_down_sync(0xffffffffu, mn, o), b = __shfl_down_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn; mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (len) atomicAdd(&acc->cum_length, len);
+        if (sum) atomicAdd(&acc->cum_depth, sum);
+        atomicMin(&acc->min_depth, mn); atomicMax(&acc->max_depth, mx);
+    }
+}
+
+// window mode: window_gen (mosdepth.nim:382-388) evaluated in closed form, one thread per window
+__global__ void __launch_bounds__(256)
+windows_kernel(const int32_t* __restrict__ arr, uint32_t tlen, uint32_t window, long long n_windows, int use_median,
+               double* __restrict__ value_out, RegionAccum* __restrict__ acc, unsigned long long* __restrict__ dist512) {
+    __shared__ uint32_t s_hist[kWindowDistBins];
+    for (int i = threadIdx.x; i < kWindowDistBins; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    unsigned long long len = 0, sum = 0; uint32_t mn = 0xffffffffu, mx = 0;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < n_windows; w += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long s64 = (unsigned long long)w * window;
+        const uint32_t start = (uint32_t)s64;
+        const uint32_t stop = (s64 + window < tlen) ? (uint32_t)(s64 + window) : tlen;
+        double me;
+        if (use_median) me = region_median(arr, start, stop, &acc->neg_seen);
+        else me = region_mean_seq(arr, start, stop, (double)(uint32_t)(stop - start));
+        value_out[w] = me;
+        slice_stats(arr, start, stop, sum, mn, mx);
+        len += stop - start;
+        // chrom_region_distribution[min(me.toInt, 511)] += 1 (:737-739); toInt rounds half away from zero
+        long long bin = me >= 0 ? (long long)__dadd_rn(me, 0.5) : (long long)__dadd_rn(me, -0.5);
+        if (bin > kWindowDistBins - 1) bin = kWindowDistBins - 1;
+        if (bin >= 0) atomicAdd(&s_hist[bin], 1u);
+    }
+    block_accumulate(acc, len, sum, mn, mx);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kWindowDistBins; i += blockDim.x) { uint32_t c = s_hist[i]; if (c) atomicAdd(&dist512[i], (unsigned long long)c); }
+}
+
+// BED mode: one thread per region (regions sorted by start on the host, mosdepth.nim:376-377)
+__global__ void __launch_bounds__(256)
+regions_kernel(const int32_t* __restrict__ arr, uint32_t tlen, long long n, const uint32_t* __restrict__ starts,
+               const uint32_t* __restrict__ stops, int use_median, double* __restrict__ value_out, RegionAccum* __restrict__ acc,
+               unsigned long long* __restrict__ dist, const int32_t* __restrict__ thresholds, int n_thr,
+               unsigned long long* __restrict__ thr_counts) {
+    __shared__ uint32_t s_hist[kHistSmemBins];
+    for (int i = threadIdx.x; i < kHistSmemBins; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t L = tlen + 1;   // len(arr), mosdepth.nim:274,719
+    unsigned long long len = 0, sum = 0; uint32_t mn = 0xffffffffu, mx = 0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        const uint32_t start = starts[r], stop = stops[r];
+        const uint32_t e = stop < L ? stop : L;
+        double me = 0.0;
+        if (!(start > L)) {                                                 // imean :401-402
+            if (use_median) me = region_median(arr, start, e > start ? e : start, &acc->neg_seen);
+            else me = region_mean_seq(arr, start, e, (double)(uint32_t)(stop - start));
+        }
+        value_out[r] = me;
+        const uint32_t a = start < L ? start : L, b = L < stop ? L : stop;   // :724
+        if (b > a) { slice_stats(arr, a, b, sum, mn, mx); len += b - a; }
+        if (start < L) {                                                    // inc(): start >= len -> warning + return (:421-424)
+            int32_t cur = 0; uint32_t cnt = 0;
+            for (uint32_t i = start; i < e; i++) {
+                const int32_t d = __ldg(arr + i);
+                if (cnt && d == cur) cnt++;
+                else { if (cnt) hist_add(s_hist, dist, cur, cnt); cur = d; cnt = 1; }
+            }
+            if (cnt) hist_add(s_hist, dist, cur, cnt);
+        }
+        if (n_thr > 0) {                                                    // :549-553 (slice clamped to the array)
+            for (int j = 0; j < n_thr; j++) {
+                const int32_t th = thresholds[j];
+                unsigned long long c = 0;
+                for (uint32_t i = start; i < e; i++) c += (__ldg(arr + i) >= th);
+                thr_counts[r * n_thr + j] = c;
+            }
+        }
+    }
+    block_accumulate(acc, len, sum, mn, mx);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHistSmemBins; i += blockDim.x) { uint32_t c = s_hist[i]; if (c) atomicAdd(&dist[i], (unsigned long long)c); }
+}
+
+}  // namespace msd
