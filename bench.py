@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the mosdepth depth hot path on B200.
+
+Metric (BASELINE.json): reads/s (and wall seconds) for a synthetic 30X whole-genome BAM with `--by 500 -n -x`
+(config C3: fast mode, 500-bp windows, no per-base output), contigs sharded across 1/2/4/8 GPUs.
+
+A "step" is one full pass of the hot path over the synthetic BAM: BGZF inflate -> record framing -> filters ->
++1/-1 depth events -> per-contig prefix sum + contig stats + global dist -> window means / window stats /
+window dist for every contig (what the reference's main loop computes for `--by 500 -n -x`, mosdepth.nim:691-764),
+plus the NCCL all-reduce of the `total` histograms/stats when N > 1.
+
+  value : compressed BAM bytes already staged in HBM (msd_stage) when the timed region starts.
+  e2e   : the same pass from a pinned HOST buffer holding the BAM file (host->device copies of the compressed
+          bytes and device->host copies of every result inside the timed region), through the C ABI.
+  --impl reference : the CPU oracle (oracle/mosdepth_oracle, a restatement of mosdepth; the real binary cannot be
+          built here) on the same BAM with all host threads, `-t nproc-1 --by 500 -n -x`.
+
+The genome is scaled by --genome-fraction (25 GRCh38 contigs, 30X, 150-bp pairs are kept) because a full 30X
+WGS BAM (~60 GB) cannot be generated on the box inside the bench budget; reads/s is what is reported.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+
+def sh(cmd, **kw):
+    return subprocess.run(cmd, check=True, capture_output=True, text=True, **kw)
+
+
+def ensure_built():
+    if not (ROOT / "mosdepth_b200" / "libmosdepth_b200.so").exists() or not (ROOT / "tools" / "gen_bam").exists() \
+            or not (ROOT / "oracle" / "mosdepth_oracle").exists():
+        import __graft_entry__ as ge
+        ge.build()
+
+
+def data_dir():
+    for d in (os.environ.get("MSD_BENCH_DIR"), "/dev/shm", "/tmp"):
+        if d and os.path.isdir(d) and os.access(d, os.W_OK):
+            p = Path(d) / "msd_bench"
+            p.mkdir(exist_ok=True)
+            return p
+    raise RuntimeError("no writable data dir")
+
+
+def make_bam(config, fraction, seed, threads, level=6):
+    """Generate (or reuse) the synthetic BAM. Returns (path, n_reads, n_bytes)."""
+    d = data_dir()
+    tag = f"{config}_f{fraction:g}_s{seed}_l{level}"
+    bam = d / f"{tag}.bam"
+    meta = d / f"{tag}.json"
+    if not (bam.exists() and meta.exists() and Path(str(bam) + ".bai").exists()):
+        tmp = d / f"{tag}.tmp.{os.getpid()}.bam"
+        r = sh([str(ROOT / "tools" / "gen_bam"), "--config", config, "--genome-fraction", str(fraction), "--seed", str(seed),
+                "--threads", str(threads), "--level", str(level), "-o", str(tmp)])
+        info = json.loads(r.stdout.strip().splitlines()[-1])
+        os.replace(str(tmp) + ".bai", str(bam) + ".bai")
+        os.replace(tmp, bam)
+        meta.write_text(json.dumps(info))
+    info = json.loads(meta.read_text())
+    return bam, info["reads"], info["bytes"]
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks + throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def lpt_shards(weights, n):
+    """Longest-processing-time bin packing of contigs onto n ranks."""
+    loads = [0] * n
+    assign = [[] for _ in range(n)]
+    for tid in sorted(range(len(weights)), key=lambda t: -weights[t]):
+        if weights[tid] <= 0:
+            continue
+        r = min(range(n), key=lambda i: loads[i])
+        loads[r] += weights[tid]
+        assign[r].append(tid)
+    return [sorted(a) for a in assign]
+
+
+def run_reference(args):
+    """CPU arm: the oracle restatement with all host threads on the same BAM."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ensure_built()
+    ncores = os.cpu_count() or 1
+    threads = max(0, min(ncores - 1, 64))
+    bam, n_reads, n_bytes = make_bam(args.config, args.cpu_fraction or args.genome_fraction, args.seed, ncores)
+    outp = data_dir() / "ref_out"
+    cmd = [str(ROOT / "oracle" / "mosdepth_oracle"), "-t", str(threads), "-n", "-x", "--by", "500", str(outp), str(bam)]
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        subprocess.run(cmd, check=True, capture_output=True)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    val = n_reads / sec
+    sample = f"{args.config} synthetic 30X WGS, genome_fraction={args.cpu_fraction or args.genome_fraction:g}, {n_reads} reads, {n_bytes} BAM bytes, whole file per step"
+    line = {"metric": "reads_per_s", "value": val, "unit": "reads/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"C3 synthetic 30X WGS --by 500 -n -x, genome_fraction={args.cpu_fraction or args.genome_fraction:g}", "reads": n_reads, "bam_bytes": n_bytes,
+                       "flags": "--by 500 -n -x", "note": "CPU oracle restatement of mosdepth (zlib inflate threads + single record thread); the mosdepth binary cannot be built in this image"},
+            "cpu_baseline": {"value": val, "unit": "reads/s", "cores": threads + 1, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3")
+    ap.add_argument("--genome-fraction", type=float, default=float(os.environ.get("MSD_BENCH_FRACTION", "0.03")))
+    ap.add_argument("--cpu-fraction", type=float, default=0.0, help="genome fraction for the CPU arm (default: same BAM)")
+    ap.add_argument("--seed", type=int, default=20261022)
+    ap.add_argument("--window", type=int, default=500)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        ensure_built()
+    if world > 1:
+        dist.barrier()
+    import mosdepth_b200 as m
+    from mosdepth_b200 import hostio
+
+    # ---- data: weak scaling = every rank count sees `fraction * world` of the genome, i.e. fixed work per GPU --------
+    fraction = args.genome_fraction * world
+    ncores = os.cpu_count() or 1
+    if rank == 0:
+        bam, n_reads, n_bytes = make_bam(args.config, fraction, args.seed, ncores)
+    if world > 1:
+        dist.barrier()
+    bam, n_reads, n_bytes = make_bam(args.config, fraction, args.seed, ncores)
+    hdr = hostio.read_bam_header(bam)
+    index = hostio.read_index(bam)
+    nt = len(hdr.names)
+    weights = [((c.ref_end >> 16) - (c.ref_beg >> 16) + 1) if c.has_data else 0 for c in index]
+    shards = lpt_shards(weights, world)
+    mine = shards[rank]
+    want = np.zeros(nt, dtype=np.uint8); want[mine] = 1
+    begs = [index[t].ref_beg for t in mine]; ends = [index[t].ref_end for t in mine]
+    my_reads = sum(index[t].n_mapped + index[t].n_unmapped for t in mine)
+
+    # pinned host image of the BAM file (the e2e input)
+    raw = np.fromfile(bam, dtype=np.uint8)
+    host = torch.empty(raw.size, dtype=torch.uint8, pin_memory=True)
+    host.numpy()[:] = raw
+    del raw
+
+    ctx = m.Context(local)
+    ctx.open_mem(host, hdr)
+    ctx.set_targets(want)
+    ctx.set_spans(begs, ends)
+    ctx.set_filters(mode=m.MODE_FAST)   # -x; defaults -F 1796 -Q 0
+    g_ptr, r_ptr, n_bins, s_ptr = ctx.totals_device()
+
+    class DevView:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+    tot_g = torch.as_tensor(DevView(g_ptr, n_bins), device=f"cuda:{local}")
+    tot_r = torch.as_tensor(DevView(r_ptr, n_bins), device=f"cuda:{local}")
+    tot_s = torch.as_tensor(DevView(s_ptr, 8), device=f"cuda:{local}")
+
+    d2h = {"bytes": 0}
+
+    def step():
+        """One pass of the hot path for this rank's contigs + the cross-rank reduction of the totals."""
+        ctx.totals_reset()
+        info = ctx.run()
+        nbytes = 0
+        for t in mine:
+            rc, _n = ctx.contig_records(t)
+            if rc < 0:
+                continue
+            st, distv = ctx.contig_stats(t)
+            vals, rst, rdist = ctx.windows(t, args.window)
+            nbytes += vals.nbytes + rdist.nbytes + distv.nbytes + 48
+        if world > 1:
+            dist.all_reduce(tot_g[:1024]); dist.all_reduce(tot_r[:512])
+            mm = torch.stack([tot_s[2], tot_s[6]]); dist.all_reduce(mm, op=dist.ReduceOp.MIN)
+            mx = torch.stack([tot_s[3], tot_s[7]]); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sums = torch.stack([tot_s[0], tot_s[1], tot_s[4], tot_s[5]]); dist.all_reduce(sums)
+        d2h["bytes"] = nbytes
+        return info
+
+    def timed(resident):
+        if resident:
+            ctx.stage()
+        else:
+            ctx.set_spans(begs, ends)   # drops the staged copy
+        for _ in range(args.warmup):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local); sampler.start()
+        infos = []
+        lc0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        ctx.mark(0)
+        for _ in range(args.steps):
+            infos.append(step())
+        ctx.mark(1)
+        torch.cuda.synchronize()
+        ms_dev = ctx.elapsed_ms(0, 1)
+        wall = time.perf_counter() - t0
+        if world > 1:
+            dist.barrier()
+        sampler.stop_flag.set(); sampler.join()
+        # the step makes blocking host calls (results come back per contig), so the device-side span between
+        # the two marks is the honest step time; the host wall clock is reported beside it
+        tt = torch.tensor([ms_dev, wall * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tt[0].item() / args.steps, tt[1].item() / args.steps, infos, ctx.launch_count() - lc0, sampler.summary()
+
+    total_reads = n_reads
+    ms_res, wall_res, infos_res, launches, clocks = timed(True)
+    ms_e2e, wall_e2e, infos_e2e, _, clocks2 = timed(False)
+    info = infos_res[-1]
+    value = total_reads / (ms_res / 1e3)
+    e2e_val = total_reads / (ms_e2e / 1e3)
+
+    # roofline of the dominant kernel (bgzf_inflate): algorithmic bytes per launch = compressed bytes read once
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    inf_ms = sum(i.ms_inflate for i in infos_res) / len(infos_res)
+    inf_launches = info.n_inflate_launches
+    alg_bytes_per_launch = info.bytes_compressed / max(inf_launches, 1)
+    achieved = (info.bytes_compressed / 1e9) / (inf_ms / 1e3) if inf_ms > 0 else 0.0
+    roofline = {"kernel": "bgzf_inflate_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launches_per_step": inf_launches, "ms_per_launch": inf_ms / max(inf_launches, 1),
+                "inflated_gbs": (info.bytes_inflated / 1e9) / (inf_ms / 1e3) if inf_ms > 0 else 0.0,
+                "stage_ms_per_step": {"inflate": inf_ms, "frame": sum(i.ms_frame for i in infos_res) / len(infos_res),
+                                      "records": sum(i.ms_records for i in infos_res) / len(infos_res), "scan": sum(i.ms_scan for i in infos_res) / len(infos_res),
+                                      "zero": sum(i.ms_zero for i in infos_res) / len(infos_res), "run_total": sum(i.ms_total for i in infos_res) / len(infos_res)},
+                "note": "inflate is serial-Huffman bound, not HBM bound; compressed GB/s and inflated GB/s are quoted against the HBM peak as north_star asks"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = max(0, min(ncores - 1, 64))
+        outp = data_dir() / "cpu_out"
+        cmd = [str(ROOT / "oracle" / "mosdepth_oracle"), "-t", str(threads), "-n", "-x", "--by", str(args.window), str(outp), str(bam)]
+        subprocess.run(cmd, check=True, capture_output=True)   # warm page cache
+        t0 = time.perf_counter(); subprocess.run(cmd, check=True, capture_output=True); dt = time.perf_counter() - t0
+        cpu_baseline = {"value": n_reads / dt, "unit": "reads/s", "cores": threads + 1, "kind": "port", "seconds": dt,
+                        "sample": f"whole bench BAM ({n_reads} reads, genome_fraction={fraction:g}), oracle -t {threads} --by {args.window} -n -x"}
+
+    if rank == 0:
+        line = {"metric": "reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": f"C3 synthetic 30X WGS (25 GRCh38 contigs x {fraction:g}, 150-bp pairs) --by {args.window} -n -x", "genome_fraction": fraction,
+                           "reads": n_reads, "bam_bytes": n_bytes, "flags": f"--by {args.window} -n -x", "sharding": f"contigs LPT over {world} GPU(s)",
+                           "l2": "inputs (compressed BAM, depth arrays) are far larger than the 126 MB L2; no flush needed",
+                           "wall_s_per_step": wall_res / 1e3, "extrapolated_full_genome_wall_s": (ms_res / 1e3) / fraction * world},
+                "e2e": {"value": e2e_val, "unit": "reads/s", "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e,
+                        "h2d_bytes_per_step": int(infos_e2e[-1].bytes_compressed), "d2h_bytes_per_step": int(d2h["bytes"])},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -157,6 +157,14 @@ int msd_quantized_runs(msd_ctx *ctx, int tid, const int64_t *quants, int n_q, co
 int msd_totals_device(msd_ctx *ctx, void **global_dist, void **region_dist, int64_t *n_bins, void **stats8);
 int msd_totals_reset(msd_ctx *ctx);
 
+/* -- measurement hooks (bench.py): CUDA events on the library's own compute stream --------------------- */
+/* Record event `slot` (0..7) on the compute stream now. */
+int msd_mark(msd_ctx *ctx, int slot);
+/* Milliseconds between two recorded marks (synchronises on the later one). */
+int msd_elapsed_ms(msd_ctx *ctx, int slot_from, int slot_to, double *ms);
+/* Kernels launched by this context since it was created. */
+uint64_t msd_launch_count(const msd_ctx *ctx);
+
 /* -- test hooks (used by tests/ to check single stages against zlib / numpy) ----------------------------- */
 /* Inflate every BGZF block of a host BGZF image; out must hold the sum of ISIZE fields. Returns bytes written. */
 int64_t msd_debug_inflate(msd_ctx *ctx, const void *bgzf_bytes, uint64_t n_bytes, void *out, uint64_t out_cap);

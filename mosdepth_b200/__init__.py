@@ -23,7 +23,7 @@ EXPORTS = [
     "msd_abi_version", "msd_create", "msd_destroy", "msd_last_error", "msd_open", "msd_open_mem", "msd_stage",
     "msd_set_spans", "msd_set_targets", "msd_set_filters", "msd_run", "msd_last_run_info", "msd_contig_records",
     "msd_contig_stats", "msd_n_windows", "msd_windows", "msd_regions", "msd_per_base_runs", "msd_quantized_runs",
-    "msd_totals_device", "msd_totals_reset", "msd_debug_inflate", "msd_debug_depth", "msd_debug_cumsum",
+    "msd_totals_device", "msd_totals_reset", "msd_mark", "msd_elapsed_ms", "msd_launch_count", "msd_debug_inflate", "msd_debug_depth", "msd_debug_cumsum",
 ]
 
 
@@ -81,6 +81,9 @@ def load_library():
     lib.msd_quantized_runs.argtypes = [p, i32, p, i32, C.POINTER(p), C.POINTER(p), C.POINTER(p), C.POINTER(i64)]
     lib.msd_totals_device.argtypes = [p, C.POINTER(p), C.POINTER(p), C.POINTER(i64), C.POINTER(p)]
     lib.msd_totals_reset.argtypes = [p]
+    lib.msd_mark.argtypes = [p, i32]
+    lib.msd_elapsed_ms.argtypes = [p, i32, i32, C.POINTER(C.c_double)]
+    lib.msd_launch_count.argtypes = [p]; lib.msd_launch_count.restype = u64
     lib.msd_debug_inflate.argtypes = [p, p, u64, p, u64]; lib.msd_debug_inflate.restype = i64
     lib.msd_debug_depth.argtypes = [p, i32, p, i64]
     lib.msd_debug_cumsum.argtypes = [p, p, i64]
@@ -227,6 +230,17 @@ class Context:
 
     def totals_reset(self):
         self._check(self.lib.msd_totals_reset(self.h))
+
+    def mark(self, slot):
+        self._check(self.lib.msd_mark(self.h, slot))
+
+    def elapsed_ms(self, a, b):
+        ms = C.c_double()
+        self._check(self.lib.msd_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self.lib.msd_launch_count(self.h))
 
     # -- test hooks -------------------------------------------------------------------------------------------------
     def debug_inflate(self, data: bytes, out_size: int):

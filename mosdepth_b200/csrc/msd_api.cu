@@ -88,6 +88,7 @@ struct msd_ctx {
     // generic scratch
     void* d_scratch = nullptr; uint64_t scratch_cap = 0;
     msd_run_info info{};
+    uint64_t launches = 0; cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
 };
 
@@ -358,6 +359,7 @@ static int compute_runs(msd_ctx* ctx, const int32_t* arr, uint32_t n, int32_t en
     }
     runs_write_kernel<F><<<n_tiles, kRunThreads, 0, sc>>>(arr, n, f, ctx->d_tile_base, ctx->d_run_start, ctx->d_run_val);
     runs_stops_kernel<<<grid_for(total, 256, kSMs * 8), 256, 0, sc>>>(ctx->d_run_start, total, end, ctx->d_run_stop);
+    ctx->launches += 4;
     MSD_CUDA_OK(cudaGetLastError());
     MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_run_start, ctx->d_run_start, total * 4, cudaMemcpyDeviceToHost, sc));
     MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_run_stop, ctx->d_run_stop, total * 4, cudaMemcpyDeviceToHost, sc));
@@ -427,6 +429,7 @@ void msd_destroy(msd_ctx* ctx) {
     if (ctx->h_run_val) cudaFreeHost(ctx->h_run_val);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (auto e : ctx->marks) if (e) cudaEventDestroy(e);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     delete ctx;
@@ -717,6 +720,7 @@ int msd_run(msd_ctx* ctx) {
     cudaEventElapsedTime(&ms, s0, s1); ctx->info.ms_scan = ms;
     ctx->info.ms_h2d = sum_ms(times.h2d); ctx->info.ms_inflate = sum_ms(times.inflate); ctx->info.ms_frame = sum_ms(times.frame); ctx->info.ms_records = sum_ms(times.records);
     ctx->ran = true;
+    ctx->launches += ctx->info.n_launches;
     return MSD_OK;
 }
 
@@ -766,6 +770,7 @@ int64_t msd_windows(msd_ctx* ctx, int tid, uint32_t window, int use_median, doub
     }
     add_hist_kernel<<<2, 256, 0, sc>>>(ctx->d_tot_region, ctx->d_dist512, kWindowDistBins);
     MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    ctx->launches += 4;
     RegionAccum h; fetch_region_accum(ctx, region_stat, &h);
     if (h.neg_seen) return ctx_fail(ctx, MSD_ENEGDEPTH, "error setting negative depth value (median mode)");
     add_stats_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats + 4, (long long)h.cum_length, h.cum_depth, h.min_depth, h.max_depth);
@@ -801,6 +806,7 @@ int msd_regions(msd_ctx* ctx, int tid, int64_t n, const uint32_t* start, const u
     }
     add_hist_kernel<<<kSMs, 256, 0, sc>>>(ctx->d_tot_region, ctx->d_rdist, kDistBins);
     MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    ctx->launches += 4;
     RegionAccum h; fetch_region_accum(ctx, region_stat, &h);
     if (h.neg_seen) return ctx_fail(ctx, MSD_ENEGDEPTH, "error setting negative depth value (median mode)");
     add_stats_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats + 4, (long long)h.cum_length, h.cum_depth, h.min_depth, h.max_depth);
@@ -871,6 +877,25 @@ int msd_totals_reset(msd_ctx* ctx) {
     MSD_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));
     return MSD_OK;
 }
+
+int msd_mark(msd_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 8) return MSD_EINVAL;
+    cudaSetDevice(ctx->device);
+    if (!ctx->marks[slot]) MSD_CUDA_OK(cudaEventCreate(&ctx->marks[slot]));
+    MSD_CUDA_OK(cudaEventRecord(ctx->marks[slot], ctx->s_compute));
+    return MSD_OK;
+}
+
+int msd_elapsed_ms(msd_ctx* ctx, int a, int b, double* ms) {
+    if (!ctx || a < 0 || a >= 8 || b < 0 || b >= 8 || !ctx->marks[a] || !ctx->marks[b] || !ms) return MSD_EINVAL;
+    cudaSetDevice(ctx->device);
+    MSD_CUDA_OK(cudaEventSynchronize(ctx->marks[b]));
+    float f = 0; MSD_CUDA_OK(cudaEventElapsedTime(&f, ctx->marks[a], ctx->marks[b]));
+    *ms = f;
+    return MSD_OK;
+}
+
+uint64_t msd_launch_count(const msd_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int64_t msd_debug_inflate(msd_ctx* ctx, const void* bgzf_bytes, uint64_t n_bytes, void* out, uint64_t out_cap) {
     if (!ctx || !bgzf_bytes || !out) return ctx_fail(ctx, MSD_EINVAL, "msd_debug_inflate: bad arguments");

@@ -1,0 +1,419 @@
+// mosdepth-b200: C++ stand-in for the reference's Nim host (mosdepth.nim:864-989 CLI, :589-840 main loop).
+//
+// The reference's host cannot be compiled in this image (no Nim, no hts-nim/htslib), so this program mirrors it
+// one-to-one in C++ above the C ABI of libmosdepth_b200.so: same flags, same per-contig emission order, same text
+// grammars.  What stays on the host (as in the reference): flag parsing, BAM header and BAI/CSI parsing, BED
+// loading, label/precision environment variables, and writing the output files.  Everything numeric comes from
+// the library (GPU); there is no CPU depth computation in this file.
+//
+// Output files: <prefix>.mosdepth.{global,region}.dist.txt, <prefix>.mosdepth.summary.txt and the bed.gz files
+// (BGZF-compressed with system zlib; no .csi index is written in this stand-in -- the reference's writer is
+// hts-nim's BGZI, which stays untouched when the Nim host binds the C ABI).
+#include <algorithm>
+#include <cerrno>
+#include <cinttypes>
+#include <climits>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include <zlib.h>
+
+#include "mosdepth_b200.h"
+
+static void die(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3), noreturn));
+#include <cstdarg>
+static void die(int code, const char* fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); fputc('\n', stderr); exit(code); }
+
+// ---- BGZF text writer (replaces hts-nim wopen_bgzi / write_interval for the stand-in) ----------------------------
+struct BgzWriter {
+    FILE* f = nullptr; std::string buf; int level = 1; bool plain = false;
+    bool open(const std::string& path, int lvl, bool plain_text) { f = fopen(path.c_str(), "wb"); level = lvl; plain = plain_text; buf.reserve(1 << 17); return f != nullptr; }
+    void flush_block(size_t n) {
+        if (!n) return;
+        static uint8_t out[65536 + 1024];
+        z_stream zs; memset(&zs, 0, sizeof zs);
+        deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+        zs.next_in = (Bytef*)buf.data(); zs.avail_in = (uInt)n; zs.next_out = out + 18; zs.avail_out = sizeof out - 26;
+        if (deflate(&zs, Z_FINISH) != Z_STREAM_END) die(1, "[mosdepth] deflate failed");
+        uint32_t clen = (uint32_t)zs.total_out, blen = clen + 26; deflateEnd(&zs);
+        static const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+        memcpy(out, hdr, 16); out[16] = (uint8_t)(blen - 1); out[17] = (uint8_t)((blen - 1) >> 8);
+        uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef*)buf.data(), (uInt)n), isz = (uint32_t)n;
+        memcpy(out + 18 + clen, &crc, 4); memcpy(out + 22 + clen, &isz, 4);
+        fwrite(out, 1, blen, f);
+        buf.erase(0, n);
+    }
+    void write(const char* s, size_t n) {
+        if (plain) { fwrite(s, 1, n, f); return; }
+        buf.append(s, n);
+        while (buf.size() >= 0xff00) flush_block(0xff00);
+    }
+    void write(const std::string& s) { write(s.data(), s.size()); }
+    int close() {
+        if (!f) return 0;
+        if (!plain) { flush_block(buf.size()); static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 0x42, 0x43, 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0}; fwrite(eof, 1, 28, f); }
+        int r = fclose(f); f = nullptr; return r;
+    }
+};
+
+// ---- BAM header + index parsing (what hts-nim does for the reference's host) -----------------------------------
+struct Target { std::string name; uint32_t length; };
+struct Header { std::vector<Target> targets; uint64_t first_voff = 0; };
+
+static std::vector<uint8_t> read_file(const std::string& p, bool required) {
+    FILE* f = fopen(p.c_str(), "rb"); if (!f) { if (required) die(1, "[mosdepth] cannot open %s", p.c_str()); return {}; }
+    fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> v((size_t)n); if (n && fread(v.data(), 1, (size_t)n, f) != (size_t)n) die(1, "[mosdepth] read error on %s", p.c_str()); fclose(f); return v;
+}
+static bool file_exists(const std::string& p) { FILE* f = fopen(p.c_str(), "rb"); if (!f) return false; fclose(f); return true; }
+
+static Header read_header(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "rb"); if (!f) die(1, "[mosdepth] cannot open %s", path.c_str());
+    std::vector<uint8_t> inflated; std::vector<std::pair<uint64_t, uint64_t>> starts;   // (uncompressed start, coffset)
+    std::vector<uint32_t> isizes; uint64_t coff = 0; bool eof = false;
+    auto need = [&](size_t n) {
+        while (inflated.size() < n && !eof) {
+            uint8_t h[18]; if (fread(h, 1, 18, f) != 18) { eof = true; break; }
+            if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) die(1, "[mosdepth] %s is not BGZF", path.c_str());
+            uint32_t xlen = h[10] | (h[11] << 8);
+            std::vector<uint8_t> extra(xlen); memcpy(extra.data(), h + 12, std::min<uint32_t>(xlen, 6)); if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, f) != xlen - 6) die(1, "truncated");
+            uint32_t bsize = 0; for (uint32_t q = 0; q + 4 <= xlen;) { uint32_t sl = extra[q + 2] | (extra[q + 3] << 8); if (extra[q] == 66 && extra[q + 1] == 67 && sl == 2) bsize = extra[q + 4] | (extra[q + 5] << 8); q += 4 + sl; }
+            uint32_t blen = bsize + 1, clen = blen - xlen - 20;
+            std::vector<uint8_t> c(clen + 8); if (fread(c.data(), 1, clen + 8, f) != clen + 8) die(1, "[mosdepth] truncated BAM header");
+            uint32_t isz; memcpy(&isz, c.data() + clen + 4, 4);
+            std::vector<uint8_t> o(isz ? isz : 1);
+            z_stream zs; memset(&zs, 0, sizeof zs); inflateInit2(&zs, -15); zs.next_in = c.data(); zs.avail_in = clen; zs.next_out = o.data(); zs.avail_out = isz;
+            int r = inflate(&zs, Z_FINISH); inflateEnd(&zs); if (r != Z_STREAM_END) die(1, "[mosdepth] corrupt BAM header block");
+            starts.push_back({inflated.size(), coff}); isizes.push_back(isz);
+            inflated.insert(inflated.end(), o.begin(), o.begin() + isz); coff += blen;
+        }
+        if (inflated.size() < n) die(1, "[mosdepth] truncated BAM header");
+    };
+    need(12);
+    if (memcmp(inflated.data(), "BAM\1", 4)) die(1, "[mosdepth] %s is not a BAM file", path.c_str());
+    int32_t l_text; memcpy(&l_text, inflated.data() + 4, 4); need(12 + (size_t)l_text);
+    size_t off = 8 + (size_t)l_text; int32_t n_ref; memcpy(&n_ref, inflated.data() + off, 4); off += 4;
+    Header H;
+    for (int i = 0; i < n_ref; i++) {
+        need(off + 4); int32_t l_name; memcpy(&l_name, inflated.data() + off, 4); need(off + 8 + (size_t)l_name);
+        Target t; t.name.assign((const char*)inflated.data() + off + 4, (size_t)l_name - 1); int32_t l; memcpy(&l, inflated.data() + off + 4 + l_name, 4); t.length = (uint32_t)l;
+        H.targets.push_back(t); off += 8 + (size_t)l_name;
+    }
+    bool found = false;
+    for (size_t b = 0; b < starts.size(); b++) if (off >= starts[b].first && off < starts[b].first + isizes[b]) { H.first_voff = (starts[b].second << 16) | (off - starts[b].first); found = true; }
+    if (!found) H.first_voff = coff << 16;   // header ends exactly at a block boundary
+    fclose(f);
+    return H;
+}
+
+struct ContigIndex { bool has = false; uint64_t beg = 0, end = 0; };
+static std::vector<uint8_t> gunzip_all(const std::vector<uint8_t>& raw) {
+    if (raw.size() < 2 || raw[0] != 0x1f || raw[1] != 0x8b) return raw;
+    std::vector<uint8_t> out; size_t p = 0;
+    while (p < raw.size()) {
+        z_stream zs; memset(&zs, 0, sizeof zs); inflateInit2(&zs, 31); zs.next_in = (Bytef*)raw.data() + p; zs.avail_in = (uInt)(raw.size() - p);
+        int r; do { size_t o = out.size(); out.resize(o + 65536); zs.next_out = out.data() + o; zs.avail_out = 65536; r = inflate(&zs, Z_NO_FLUSH); out.resize(o + 65536 - zs.avail_out); } while (r == Z_OK);
+        if (r != Z_STREAM_END) die(1, "[mosdepth] corrupt index"); p = raw.size() - zs.avail_in; inflateEnd(&zs);
+    }
+    return out;
+}
+static bool load_index(const std::string& bam, std::vector<ContigIndex>& out) {
+    std::string p; bool csi = false;
+    if (file_exists(bam + ".csi")) { p = bam + ".csi"; csi = true; } else if (file_exists(bam + ".bai")) p = bam + ".bai";
+    else if (bam.size() > 4 && file_exists(bam.substr(0, bam.size() - 4) + ".bai")) p = bam.substr(0, bam.size() - 4) + ".bai"; else return false;
+    std::vector<uint8_t> d = gunzip_all(read_file(p, true)); size_t q = 4; uint32_t pseudo = 37450;
+    if (csi) { int32_t depth, l_aux; memcpy(&depth, d.data() + 8, 4); memcpy(&l_aux, d.data() + 12, 4); q = 16 + (size_t)l_aux; pseudo = (uint32_t)(((1u << ((depth + 1) * 3)) - 1) / 7 + 1); }
+    int32_t n_ref; memcpy(&n_ref, d.data() + q, 4); q += 4; out.assign((size_t)n_ref, ContigIndex());
+    for (int r = 0; r < n_ref; r++) {
+        int32_t n_bin; memcpy(&n_bin, d.data() + q, 4); q += 4; uint64_t mn = UINT64_MAX, mx = 0;
+        for (int b = 0; b < n_bin; b++) {
+            uint32_t bin; memcpy(&bin, d.data() + q, 4); q += 4; if (csi) q += 8;
+            int32_t nc; memcpy(&nc, d.data() + q, 4); q += 4;
+            for (int c = 0; c < nc; c++) { uint64_t cb, ce; memcpy(&cb, d.data() + q, 8); memcpy(&ce, d.data() + q + 8, 8); q += 16; if (bin != pseudo) { mn = std::min(mn, cb); mx = std::max(mx, ce); } }
+        }
+        if (!csi) { int32_t ni; memcpy(&ni, d.data() + q, 4); q += 4 + 8 * (size_t)ni; }
+        if (mn != UINT64_MAX) { out[r].has = true; out[r].beg = mn; out[r].end = mx; }
+    }
+    return true;
+}
+
+// ---- regions (bed_to_table mosdepth.nim:362-380, bed_line_to_region :195-209) --------------------------------------
+struct Region { uint32_t start, stop; std::string name; };
+static int64_t nim_parse_int(const std::string& s) { if (s.empty()) die(1, "invalid integer: %s", s.c_str()); char* e; errno = 0; long long v = strtoll(s.c_str(), &e, 10); if (*e || errno) die(1, "invalid integer: %s", s.c_str()); return v; }
+static std::string strip(const std::string& s) { size_t a = 0, b = s.size(); while (a < b && isspace((unsigned char)s[a])) a++; while (b > a && isspace((unsigned char)s[b - 1])) b--; return s.substr(a, b - a); }
+static std::vector<std::pair<std::string, std::vector<Region>>> bed_to_table(const std::string& path) {
+    std::vector<uint8_t> d = gunzip_all(read_file(path, true));
+    std::vector<std::pair<std::string, std::vector<Region>>> tab;
+    size_t p = 0;
+    while (p < d.size()) {
+        size_t e = p; while (e < d.size() && d[e] != '\n') e++;
+        std::string line((const char*)d.data() + p, e - p); p = e + 1;
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty()) break;                                   // hts_getline(...) > 0 (:366)
+        if (line[0] == 't' && line.rfind("track ", 0) == 0) continue;
+        if (line[0] == '#') continue;
+        std::vector<std::string> f; size_t a = 0;
+        while (f.size() < 5) { size_t t = line.find('\t', a); if (t == std::string::npos) break; f.push_back(line.substr(a, t - a)); a = t + 1; }
+        f.push_back(line.substr(a));
+        if (f.size() < 3) { fprintf(stderr, "[mosdepth] skipping bad bed line:%s\n", strip(line).c_str()); continue; }
+        int64_t s = nim_parse_int(f[1]), en = nim_parse_int(f[2]);
+        if (s > en) die(1, "[slivar] ERROR: start > end in bed line:%s", line.c_str());
+        Region r; r.start = (uint32_t)s; r.stop = (uint32_t)en; if (f.size() > 3) r.name = strip(f[3]);
+        auto it = std::find_if(tab.begin(), tab.end(), [&](auto& kv) { return kv.first == f[0]; });
+        if (it == tab.end()) { tab.push_back({f[0], {}}); it = tab.end() - 1; }
+        it->second.push_back(r);
+    }
+    for (auto& kv : tab) std::stable_sort(kv.second.begin(), kv.second.end(), [](const Region& a, const Region& b) { return (int64_t)a.start - (int64_t)b.start < 0; });
+    return tab;
+}
+
+// ---- text (write_distribution :439-458, write_summary :460-480, make_lookup :111-122) -----------------------------
+static int g_precision = 2; static bool g_summary_header = true;
+static void write_distribution(const std::string& chrom, const std::vector<int64_t>& d, FILE* fh) {
+    int64_t sum = 0; for (int64_t v : d) sum += v;
+    if (sum < 1) return;
+    double cum = 0;
+    for (size_t i = 0; i < d.size(); i++) {
+        int64_t irev = (int64_t)d.size() - (int64_t)i - 1, v = d[(size_t)irev];
+        if (irev > 300 && v == 0) continue;
+        cum += (double)v / (double)sum;
+        if (cum < 8e-5) continue;
+        fprintf(fh, "%s\t%" PRId64 "\t%.*f\n", chrom.c_str(), irev, g_precision, cum);
+    }
+}
+static void write_summary(const std::string& region, const msd_depth_stat& st, FILE* fh) {
+    double mean = st.cum_length > 0 ? (double)st.cum_depth / (double)st.cum_length : 0.0;
+    uint32_t mn = st.min_depth == UINT32_MAX ? 0 : st.min_depth;
+    if (g_summary_header) { fputs("chrom\tlength\tbases\tmean\tmin\tmax\n", fh); g_summary_header = false; }
+    fprintf(fh, "%s\t%" PRId64 "\t%" PRIu64 "\t%.*f\t%u\t%u\n", region.c_str(), st.cum_length, st.cum_depth, g_precision, mean, mn, st.max_depth);
+}
+static void stat_clear(msd_depth_stat& s) { s.cum_length = 0; s.cum_depth = 0; s.min_depth = UINT32_MAX; s.max_depth = 0; }
+static msd_depth_stat stat_add(const msd_depth_stat& a, const msd_depth_stat& b) { msd_depth_stat r; r.cum_length = a.cum_length + b.cum_length; r.cum_depth = a.cum_depth + b.cum_depth; r.min_depth = std::min(a.min_depth, b.min_depth); r.max_depth = std::max(a.max_depth, b.max_depth); return r; }
+static void sum_into(const std::vector<int64_t>& from, std::vector<int64_t>& to) { if (from.size() > to.size()) to.resize(from.size(), 0); for (size_t i = 0; i < from.size(); i++) to[i] += from[i]; }
+
+static std::vector<int64_t> get_quantize_args(const char* qa) {   // :501-519
+    std::vector<int64_t> q; if (!qa) return q;
+    std::string a = qa;
+    if (a.find(':') == std::string::npos) a = ":" + a + ":";
+    if (a[0] == ':') a = "0" + a;
+    if (a.back() == ':') a += std::to_string(INT64_MAX);
+    size_t p = 0;
+    for (;;) { size_t c = a.find(':', p); std::string tok = a.substr(p, c == std::string::npos ? std::string::npos : c - p); char* e; errno = 0; long long v = strtoll(tok.c_str(), &e, 10);
+        if (tok.empty() || *e || errno) { fprintf(stderr, "[mosdepth] invalid quantize string: '%s'\n", a.c_str()); exit(2); } q.push_back(v); if (c == std::string::npos) break; p = c + 1; }
+    std::sort(q.begin(), q.end());
+    return q;
+}
+static std::vector<std::string> make_lookup(const std::vector<int64_t>& q) {
+    std::vector<std::string> L;
+    for (size_t i = 0; i + 1 < q.size(); i++) { std::string env = "MOSDEPTH_Q" + std::to_string(i); const char* t = getenv(env.c_str());
+        if (!t || !*t) L.push_back(q[i + 1] == INT64_MAX ? std::to_string(q[i]) + ":inf" : std::to_string(q[i]) + ":" + std::to_string(q[i + 1])); else L.push_back(t); }
+    return L;
+}
+static inline char* fmt_u32(char* p, uint32_t v) { char t[12]; int n = 0; do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) *p++ = t[--n]; return p; }
+static inline char* fmt_i32(char* p, int32_t v) { if (v < 0) { *p++ = '-'; return fmt_u32(p, (uint32_t)(-(int64_t)v)); } return fmt_u32(p, (uint32_t)v); }
+
+#define MSD(call) do { int _rc = (int)(call); if (_rc < 0) die(1, "[mosdepth] %s", msd_last_error(ctx)); } while (0)
+
+int main(int argc, char** argv) {
+    const char *chrom_arg = nullptr, *by = nullptr, *quant_arg = nullptr, *thr_arg = nullptr, *rg_arg = nullptr;
+    int no_per_base = 0, fast_mode = 0, fragment_mode = 0, use_median = 0, mapq = 0, device = 0, plain = 0; int64_t min_len = -1, max_len = -1;
+    uint16_t eflag = 1796, iflag = 0; std::vector<std::string> pos;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto val = [&]() -> const char* { if (i + 1 >= argc) die(1, "error parsing arguments"); return argv[++i]; };
+        auto is = [&](const char* s, const char* l) { return a == s || a == l; };
+        if (is("-t", "--threads")) (void)nim_parse_int(val());            // BAM decompression threads: inflate runs on the GPU
+        else if (is("-c", "--chrom")) chrom_arg = val();
+        else if (is("-b", "--by")) by = val();
+        else if (is("-n", "--no-per-base")) no_per_base = 1;
+        else if (is("-f", "--fasta")) (void)val();
+        else if (is("-F", "--flag")) eflag = (uint16_t)nim_parse_int(val());
+        else if (is("-i", "--include-flag")) iflag = (uint16_t)nim_parse_int(val());
+        else if (is("-x", "--fast-mode")) fast_mode = 1;
+        else if (is("-a", "--fragment-mode")) fragment_mode = 1;
+        else if (is("-q", "--quantize")) quant_arg = val();
+        else if (is("-Q", "--mapq")) mapq = (int)nim_parse_int(val());
+        else if (is("-l", "--min-frag-len")) min_len = nim_parse_int(val());
+        else if (is("-u", "--max-frag-len")) max_len = nim_parse_int(val());
+        else if (is("-T", "--thresholds")) thr_arg = val();
+        else if (is("-m", "--use-median")) use_median = 1;
+        else if (is("-R", "--read-groups")) rg_arg = val();
+        else if (a == "--device") device = (int)nim_parse_int(val());
+        else if (a == "--plain") plain = 1;                                // write *.bed (uncompressed) instead of *.bed.gz
+        else if (a.size() > 1 && a[0] == '-') die(1, "error parsing arguments");
+        else pos.push_back(a);
+    }
+    if (pos.size() != 2) die(1, "error parsing arguments");
+    const std::string prefix = pos[0], bam_path = pos[1];
+    { const char* e = getenv("MOSDEPTH_PRECISION"); if (e && *e) { char* end; long v = strtol(e, &end, 10); g_precision = *end ? 2 : (int)v; } }
+    if (max_len < 0) max_len = INT64_MAX;
+    if (max_len < min_len) { fprintf(stderr, "[mosdepth] error --max-frag-len was lower than --min-frag-len.\n"); return 2; }
+    std::vector<int32_t> thr;
+    if (thr_arg) { std::string s = thr_arg; size_t p = 0; for (;;) { size_t c = s.find(',', p); thr.push_back((int32_t)nim_parse_int(s.substr(p, c == std::string::npos ? std::string::npos : c - p))); if (c == std::string::npos) break; p = c + 1; } std::sort(thr.begin(), thr.end()); }
+    if (fragment_mode && fast_mode) { fprintf(stderr, "[mosdepth] error only one of --fast-mode and --fragment-mode can be specified\n"); return 2; }
+    if (!by && !thr.empty()) { fprintf(stderr, "[mosdepth] error --thresholds can only be used when --by is specified.\n"); return 2; }
+    if (bam_path.size() > 5 && bam_path.substr(bam_path.size() - 5) == ".cram") { fprintf(stderr, "[mosdepth] ERROR: specify a reference file (or set REF_PATH env var) for decoding CRAM\n"); return 1; }
+
+    Header H = read_header(bam_path);
+    std::vector<ContigIndex> index;
+    if (!load_index(bam_path, index)) { fprintf(stderr, "[mosdepth] error alignment file must be indexed\n"); return 2; }
+    const int nt = (int)H.targets.size();
+    std::string chrom;
+    if (chrom_arg && *chrom_arg && strcmp(chrom_arg, "nil")) {
+        chrom = chrom_arg;
+        if (chrom.find(':') != std::string::npos) { int seps = 0; size_t cut = std::string::npos; for (size_t k = chrom.size(); k-- > 0;) if (chrom[k] == ':' || chrom[k] == '-') { if (++seps == 2) { cut = k; break; } } if (cut == std::string::npos) cut = chrom.rfind(':'); chrom = chrom.substr(0, cut); }
+        bool ok = false; for (auto& t : H.targets) if (t.name == chrom) ok = true;
+        if (!ok) { fprintf(stderr, "[mosdepth] chromosome %s not found\n", chrom.c_str()); return 1; }
+    }
+    std::vector<int64_t> quant = get_quantize_args(quant_arg);
+    std::vector<std::string> lookup = quant.empty() ? std::vector<std::string>() : make_lookup(quant);
+    uint32_t window = 0; bool by_digit = false; std::vector<std::pair<std::string, std::vector<Region>>> bed; bool have_bed = false;
+    if (by) { by_digit = *by != 0; for (const char* p = by; *p; p++) if (*p < '0' || *p > '9') by_digit = false; if (by_digit) window = (uint32_t)nim_parse_int(by); else { bed = bed_to_table(by); have_bed = true; } }
+
+    // ---- which contigs does the main loop visit (get_targets :482-488, skip rule :703-705)? ------------------------
+    std::vector<uint8_t> want(nt, 0); std::vector<uint64_t> sb, se;
+    auto bed_find = [&](const std::string& name) -> std::vector<Region>* { for (auto& kv : bed) if (kv.first == name) return &kv.second; return nullptr; };
+    for (int t = 0; t < nt; t++) {
+        if (!chrom.empty() && H.targets[t].name != chrom) continue;
+        if (no_per_base && thr.empty() && quant.empty() && have_bed && !bed_find(H.targets[t].name)) continue;
+        want[t] = 1;
+        if (t < (int)index.size() && index[t].has) { sb.push_back(index[t].beg); se.push_back(index[t].end); }
+    }
+    msd_ctx* ctx = nullptr;
+    if (msd_create(device, &ctx) != 0) die(1, "[mosdepth] %s", msd_last_error(nullptr));
+    std::vector<uint32_t> tl(nt); for (int t = 0; t < nt; t++) tl[t] = H.targets[t].length;
+    MSD(msd_open(ctx, bam_path.c_str(), nt, tl.data(), H.first_voff));
+    MSD(msd_set_targets(ctx, want.data()));
+    // merge adjacent contig spans so neighbouring contigs are read in one go
+    { std::vector<uint64_t> mb, me; for (size_t i = 0; i < sb.size(); i++) { if (!mb.empty() && (sb[i] >> 16) <= (me.back() >> 16) + 1 && sb[i] >= me.back()) me.back() = se[i]; else { mb.push_back(sb[i]); me.push_back(se[i]); } }
+      if (mb.empty()) { mb.push_back(1ull << 16); me.push_back(1ull << 16); }   // nothing indexed: read nothing
+      MSD(msd_set_spans(ctx, (int)mb.size(), mb.data(), me.data())); }
+    std::vector<const char*> rgs; std::vector<std::string> rg_store;
+    if (rg_arg) { std::string s = rg_arg; size_t p = 0; for (;;) { size_t c = s.find(',', p); rg_store.push_back(s.substr(p, c == std::string::npos ? std::string::npos : c - p)); if (c == std::string::npos) break; p = c + 1; } for (auto& r : rg_store) rgs.push_back(r.c_str()); }
+    MSD(msd_set_filters(ctx, mapq, min_len, max_len, eflag, iflag, rgs.empty() ? nullptr : rgs.data(), (int)rgs.size(), fast_mode ? MSD_MODE_FAST : fragment_mode ? MSD_MODE_FRAGMENT : MSD_MODE_DEFAULT));
+    MSD(msd_run(ctx));   // coverage() + to_coverage() for every visited contig
+
+    // ---- outputs (mosdepth.nim:641-682) -------------------------------------------------------------------------------
+    const std::string gz = plain ? "" : ".gz";
+    BgzWriter fbase, fquant, fthr, fregion; FILE *fh_gd, *fh_sum, *fh_rd = nullptr;
+    if (!no_per_base && !fbase.open(prefix + ".per-base.bed" + gz, 1, plain)) die(1, "[mosdepth] could not open per-base file");
+    if (!quant.empty() && !fquant.open(prefix + ".quantized.bed" + gz, 1, plain)) die(1, "[mosdepth] could not open quantized file");
+    if (!thr.empty()) { if (!fthr.open(prefix + ".thresholds.bed" + gz, 1, plain)) die(1, "[mosdepth] could not open thresholds file"); std::string h = "#chrom\tstart\tend\tregion"; for (int32_t t : thr) h += "\t" + std::to_string(t) + "X"; h += "\n"; fthr.write(h); }
+    if (!(fh_gd = fopen((prefix + ".mosdepth.global.dist.txt").c_str(), "w"))) die(1, "[mosdepth] could not open file:%s.mosdepth.global.dist.txt", prefix.c_str());
+    if (!(fh_sum = fopen((prefix + ".mosdepth.summary.txt").c_str(), "w"))) die(1, "[mosdepth] could not open file:%s.mosdepth.summary.txt", prefix.c_str());
+    if (by) { if (!(fh_rd = fopen((prefix + ".mosdepth.region.dist.txt").c_str(), "w"))) die(1, "could not open region dist"); if (!fregion.open(prefix + ".regions.bed" + gz, 6, plain)) die(1, "[mosdepth] could not open regions file"); }
+
+    msd_depth_stat global_stat, global_region_stat; stat_clear(global_stat); stat_clear(global_region_stat);
+    std::vector<int64_t> region_distribution(512, 0), global_distribution(512, 0);
+    std::vector<double> values; std::vector<int64_t> thr_counts; std::vector<uint32_t> rs, re; std::string line; line.reserve(1 << 20);
+    char num[64];
+
+    for (int ti = 0; ti < nt; ti++) {
+        const Target& target = H.targets[ti];
+        if (!chrom.empty() && target.name != chrom) continue;
+        std::vector<Region>* bc = have_bed ? bed_find(target.name) : nullptr;
+        if (no_per_base && thr.empty() && quant.empty() && have_bed && !bc) continue;       // :703-705
+        int64_t nrec = 0;
+        int tid = msd_contig_records(ctx, ti, &nrec);                                          // coverage() return value
+        if (tid < -2) die(1, "[mosdepth] %s", msd_last_error(ctx));
+        std::vector<int64_t> chrom_global(512, 0), chrom_region(512, 0);
+        msd_depth_stat chrom_stat, chrom_region_stat; stat_clear(chrom_stat); stat_clear(chrom_region_stat);
+        if (by) {
+            // region_gen :390-397
+            std::vector<Region> wins; const std::vector<Region>* regs = bc;
+            size_t n_regions = 0;
+            if (!have_bed) n_regions = (size_t)std::max<int64_t>(0, msd_n_windows(target.length, window)); else n_regions = bc ? bc->size() : 0;
+            values.assign(n_regions ? n_regions : 1, 0.0);
+            if (!thr.empty()) thr_counts.assign((n_regions ? n_regions : 1) * thr.size(), 0);
+            if (tid != -2 && n_regions) {
+                if (!have_bed) {
+                    int64_t d512[512];
+                    if (!thr.empty() || false) { /* thresholds in window mode go through the region call below */ }
+                    MSD(msd_windows(ctx, ti, window, use_median, values.data(), (int64_t)values.size(), &chrom_region_stat, d512));
+                    chrom_region.assign(d512, d512 + 512);
+                    if (!thr.empty()) {   // thresholds need per-window counts: same windows as explicit regions
+                        rs.resize(n_regions); re.resize(n_regions);
+                        for (size_t k = 0; k < n_regions; k++) { rs[k] = (uint32_t)(k * (uint64_t)window); re[k] = (uint32_t)std::min<uint64_t>((k + 1) * (uint64_t)window, target.length); }
+                        std::vector<double> dummy(n_regions); msd_depth_stat dst; int64_t dl = 0;
+                        MSD(msd_regions(ctx, ti, (int64_t)n_regions, rs.data(), re.data(), use_median, dummy.data(), &dst, nullptr, 0, &dl, thr.data(), (int)thr.size(), thr_counts.data()));
+                    }
+                } else {
+                    rs.resize(n_regions); re.resize(n_regions);
+                    for (size_t k = 0; k < n_regions; k++) { rs[k] = (*regs)[k].start; re[k] = (*regs)[k].stop; }
+                    int64_t dl = 0; chrom_region.assign(400001, 0);
+                    MSD(msd_regions(ctx, ti, (int64_t)n_regions, rs.data(), re.data(), use_median, values.data(), &chrom_region_stat, chrom_region.data(), (int64_t)chrom_region.size(), &dl,
+                                    thr.empty() ? nullptr : thr.data(), (int)thr.size(), thr.empty() ? nullptr : thr_counts.data()));
+                    chrom_region.resize((size_t)std::max<int64_t>(dl, 512));
+                }
+            }
+            // region lines (:725-735) + thresholds (:743 -> :522-557)
+            for (size_t k = 0; k < n_regions; k++) {
+                uint32_t s, e; const std::string* name = nullptr;
+                if (!have_bed) { s = (uint32_t)(k * (uint64_t)window); e = (uint32_t)std::min<uint64_t>((k + 1) * (uint64_t)window, target.length); } else { s = (*regs)[k].start; e = (*regs)[k].stop; name = &(*regs)[k].name; }
+                line.clear(); line += target.name; line += '\t'; char* p = fmt_u32(num, s); line.append(num, p - num); line += '\t'; p = fmt_u32(num, e); line.append(num, p - num); line += '\t';
+                if (name && !name->empty()) { line += *name; line += '\t'; }
+                int n = snprintf(num, sizeof num, "%.*f", g_precision, tid != -2 ? values[k] : 0.0); line.append(num, (size_t)n); line += '\n';
+                fregion.write(line);
+                if (!thr.empty()) {
+                    line.clear(); line += target.name; line += '\t'; p = fmt_u32(num, s); line.append(num, p - num); line += '\t'; p = fmt_u32(num, e); line.append(num, p - num); line += '\t';
+                    line += (name && !name->empty()) ? *name : std::string("unknown");
+                    for (size_t j = 0; j < thr.size(); j++) { line += '\t'; line += tid == -2 ? std::string("0") : std::to_string(thr_counts[k * thr.size() + j]); }
+                    line += '\n'; fthr.write(line);
+                }
+            }
+            if (bc) bc->clear(), bed.erase(std::find_if(bed.begin(), bed.end(), [&](auto& kv) { return kv.first == target.name; }));   // bed_regions.del (:397)
+        }
+        if (tid != -2) {                                                                       // :745-753
+            int64_t dl = 0; std::vector<int64_t> d(400001);
+            MSD(msd_contig_stats(ctx, ti, &chrom_stat, d.data(), (int64_t)d.size(), &dl));
+            d.resize((size_t)std::max<int64_t>(dl, 512)); chrom_global = d;
+            global_stat = stat_add(global_stat, chrom_stat);
+            write_summary(target.name, chrom_stat, fh_sum);
+            if (by) write_summary(target.name + "_region", chrom_region_stat, fh_sum);
+            global_region_stat = stat_add(global_region_stat, chrom_region_stat);
+        }
+        write_distribution(target.name, chrom_global, fh_gd);                                 // :756-758
+        if (by) write_distribution(target.name, chrom_region, fh_rd);
+        if (tid >= 0) { if (by) sum_into(chrom_region, region_distribution); sum_into(chrom_global, global_distribution); }   // :761-764
+        if (!no_per_base) {                                                                    // :766-793
+            if (tid == -2) { line = target.name + "\t0\t" + std::to_string(target.length) + "\t0\n"; fbase.write(line); }
+            else {
+                const int32_t *st, *en, *dp; int64_t nr = 0;
+                MSD(msd_per_base_runs(ctx, ti, &st, &en, &dp, &nr));
+                std::string pre = target.name + "\t"; line.clear();
+                for (int64_t k = 0; k < nr; k++) {
+                    line += pre; char* p = fmt_i32(num, st[k]); *p++ = '\t'; p = fmt_i32(p, en[k]); *p++ = '\t'; p = fmt_i32(p, dp[k]); *p++ = '\n'; line.append(num, p - num);
+                    if (line.size() > (1 << 19)) { fbase.write(line); line.clear(); }
+                }
+                fbase.write(line);
+            }
+        }
+        if (!quant.empty()) {                                                                  // :794-805
+            if (tid == -2 && quant[0] == 0) { line = target.name + "\t0\t" + std::to_string(target.length) + "\t" + lookup[0] + "\n"; fquant.write(line); }
+            else if (tid != -2) {
+                const int32_t *st, *en, *bn; int64_t nr = 0;
+                MSD(msd_quantized_runs(ctx, ti, quant.data(), (int)quant.size(), &st, &en, &bn, &nr));
+                line.clear();
+                for (int64_t k = 0; k < nr; k++) { line += target.name; line += '\t'; line += std::to_string(st[k]); line += '\t'; line += std::to_string(en[k]); line += '\t'; line += lookup[(size_t)bn[k]]; line += '\n'; if (line.size() > (1 << 19)) { fquant.write(line); line.clear(); } }
+                fquant.write(line);
+            }
+        }
+    }
+    write_summary("total", global_stat, fh_sum);                                               // :807-813
+    if (by) write_summary("total_region", global_region_stat, fh_sum);
+    write_distribution("total", global_distribution, fh_gd);
+    if (by) { write_distribution("total", region_distribution, fh_rd); fclose(fh_rd); }
+    if (have_bed && chrom.empty()) for (auto& kv : bed) fprintf(stderr, "[mosdepth] warning chromosome:%s from bed with %zu regions not found\n", kv.first.c_str(), kv.second.size());
+    if (fregion.f && fregion.close() != 0) { fprintf(stderr, "[mosdepth] error writing region file\n\n"); return 1; }
+    if (fquant.f && fquant.close() != 0) { fprintf(stderr, "[mosdepth] error writing quantize file\n\n"); return 1; }
+    if (fthr.f && fthr.close() != 0) { fprintf(stderr, "[mosdepth] error writing thresholds file\n\n"); return 1; }
+    if (fbase.f && fbase.close() != 0) { fprintf(stderr, "[mosdepth] error writing per-base file\n\n"); return 1; }
+    fclose(fh_gd); fclose(fh_sum);
+    if (getenv("MOSDEPTH_B200_STATS")) { msd_run_info ri; msd_last_run_info(ctx, &ri); fprintf(stderr, "[mosdepth-b200] records=%llu blocks=%llu inflate_ms=%.3f frame_ms=%.3f records_ms=%.3f scan_ms=%.3f total_ms=%.3f\n", (unsigned long long)ri.n_records, (unsigned long long)ri.n_blocks, ri.ms_inflate, ri.ms_frame, ri.ms_records, ri.ms_scan, ri.ms_total); }
+    msd_destroy(ctx);
+    return 0;
+}
