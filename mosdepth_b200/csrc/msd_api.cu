@@ -154,10 +154,10 @@ int setup_common(msd_ctx* ctx, int n_targets, const uint32_t* target_len, uint64
     ctx->src_pinned = (cudaPointerGetAttributes(&pa, ctx->bytes) == cudaSuccess && pa.type == cudaMemoryTypeHost);
     cudaGetLastError();
     // chunk geometry
-    ctx->comp_cap = std::min<uint64_t>(env_u64("MSD_CHUNK_COMP_MB", 192) << 20, ((ctx->n_bytes + 65536 + 255) / 256) * 256);
-    ctx->infl_cap = std::min<uint64_t>(env_u64("MSD_CHUNK_INFL_MB", 512) << 20, std::max<uint64_t>(8ull << 20, ctx->n_bytes * 16));
+    ctx->comp_cap = std::min<uint64_t>(env_u64("MSD_CHUNK_COMP_MB", 768) << 20, ((ctx->n_bytes + 65536 + 255) / 256) * 256);
+    ctx->infl_cap = std::min<uint64_t>(env_u64("MSD_CHUNK_INFL_MB", 2048) << 20, std::max<uint64_t>(8ull << 20, ctx->n_bytes * 16));
     ctx->carry_cap = (uint32_t)std::min<uint64_t>(env_u64("MSD_CARRY_MB", 64) << 20, ctx->infl_cap);
-    ctx->max_blocks = (uint32_t)std::min<uint64_t>(env_u64("MSD_CHUNK_BLOCKS", 16384), ctx->n_bytes / 28 + 2);
+    ctx->max_blocks = (uint32_t)std::min<uint64_t>(env_u64("MSD_CHUNK_BLOCKS", 40000), ctx->n_bytes / 28 + 2);
     ctx->rec_cap = (uint32_t)((ctx->infl_cap + ctx->carry_cap) / 37 + 2);
     return 0;
 }
@@ -557,8 +557,20 @@ int msd_run(msd_ctx* ctx) {
 
     ContigTable ct{ctx->d_depth_off, ctx->d_tlen};
     const uint32_t base = ctx->carry_cap;
-    std::vector<Span> spans = ctx->spans;
-    if (spans.empty()) spans.push_back({ctx->first_voff, 0});
+    std::vector<Span> spans;
+    {   // neighbouring spans are read in one go: the bytes between two record boundaries are whole records, and
+        // records of contigs that are not selected are dropped by the target mask anyway
+        std::vector<Span> in = ctx->spans;
+        if (in.empty()) in.push_back({ctx->first_voff, 0});
+        std::sort(in.begin(), in.end(), [](const Span& a, const Span& b) { return a.beg < b.beg; });
+        const uint64_t max_gap = env_u64("MSD_SPAN_MERGE_KB", 1024) << 10;
+        for (const Span& s : in) {
+            if (s.beg == ~0ull) continue;
+            if (!spans.empty() && spans.back().end != 0 && s.beg >= spans.back().end && (s.beg >> 16) - (spans.back().end >> 16) <= max_gap) { spans.back().end = s.end; continue; }
+            if (!spans.empty() && (spans.back().end == 0 || s.beg < spans.back().end)) { if (spans.back().end != 0 && (s.end == 0 || s.end > spans.back().end)) spans.back().end = s.end; continue; }
+            spans.push_back(s);
+        }
+    }
     uint64_t chunk_idx = 0;
     const uint8_t* F = ctx->bytes; const uint64_t N = ctx->n_bytes;
 

@@ -1,0 +1,66 @@
+## mosdepth_b200.nim -- {.importc, dynlib.} binding of libmosdepth_b200.so for the reference's Nim host.
+## SOURCE ONLY: there is no Nim toolchain in the build image, so this file has not been compiled (INTEGRATION.md).
+## It mirrors include/mosdepth_b200.h one to one; `check` turns a negative return into the reference's own
+## failure mode (`quit msg`, mosdepth.nim:190-191).
+
+const libmsd = "libmosdepth_b200.so"
+
+type
+  MsdCtx* = pointer
+  MsdDepthStat* {.bycopy.} = object   # depth_stat, depthstat.nim:2-6
+    cum_length*: int64
+    cum_depth*: uint64
+    min_depth*: uint32
+    max_depth*: uint32
+
+const
+  MSD_MODE_DEFAULT* = 0.cint
+  MSD_MODE_FAST* = 1.cint
+  MSD_MODE_FRAGMENT* = 2.cint
+
+proc msd_create*(device: cint, ctx: ptr MsdCtx): cint {.importc, dynlib: libmsd.}
+proc msd_destroy*(ctx: MsdCtx) {.importc, dynlib: libmsd.}
+proc msd_last_error*(ctx: MsdCtx): cstring {.importc, dynlib: libmsd.}
+proc msd_open*(ctx: MsdCtx, bam_path: cstring, n_targets: cint, target_len: ptr uint32, first_record_voff: uint64): cint {.importc, dynlib: libmsd.}
+proc msd_set_spans*(ctx: MsdCtx, n: cint, voff_beg, voff_end: ptr uint64): cint {.importc, dynlib: libmsd.}
+proc msd_set_targets*(ctx: MsdCtx, want: ptr uint8): cint {.importc, dynlib: libmsd.}
+proc msd_set_filters*(ctx: MsdCtx, mapq: cint, min_len, max_len: int64, eflag, iflag: uint16,
+                      read_groups: cstringArray, n_read_groups: cint, mode: cint): cint {.importc, dynlib: libmsd.}
+proc msd_run*(ctx: MsdCtx): cint {.importc, dynlib: libmsd.}
+proc msd_contig_records*(ctx: MsdCtx, tid: cint, n: ptr int64): cint {.importc, dynlib: libmsd.}
+proc msd_contig_stats*(ctx: MsdCtx, tid: cint, stat: ptr MsdDepthStat, dist: ptr int64, dist_cap: int64, dist_len: ptr int64): cint {.importc, dynlib: libmsd.}
+proc msd_n_windows*(tlen, window: uint32): int64 {.importc, dynlib: libmsd.}
+proc msd_windows*(ctx: MsdCtx, tid: cint, window: uint32, use_median: cint, value_out: ptr float64, value_cap: int64,
+                  region_stat: ptr MsdDepthStat, region_dist512: ptr int64): int64 {.importc, dynlib: libmsd.}
+proc msd_regions*(ctx: MsdCtx, tid: cint, n: int64, start, stop: ptr uint32, use_median: cint, value_out: ptr float64,
+                  region_stat: ptr MsdDepthStat, region_dist: ptr int64, dist_cap: int64, dist_len: ptr int64,
+                  thresholds: ptr int32, n_thr: cint, thr_counts: ptr int64): cint {.importc, dynlib: libmsd.}
+proc msd_per_base_runs*(ctx: MsdCtx, tid: cint, start, stop, depth: ptr ptr int32, n_runs: ptr int64): cint {.importc, dynlib: libmsd.}
+proc msd_quantized_runs*(ctx: MsdCtx, tid: cint, quants: ptr int64, n_q: cint, start, stop, bin: ptr ptr int32, n_runs: ptr int64): cint {.importc, dynlib: libmsd.}
+
+template check*(ctx: MsdCtx, call: untyped) =
+  ## negative return -> the reference's own failure mode for iterator errors (mosdepth.nim:190-191)
+  if call < 0: quit $msd_last_error(ctx)
+
+# ---------------------------------------------------------------------------------------------------------------
+# How main() (mosdepth.nim:589-840) changes.  `coverage()` (:250-360) and `to_coverage()` (:54-56) are replaced
+# by one msd_run() before the per-target loop; inside the loop every consumer of `arr` becomes one call:
+#
+#   var ctx: MsdCtx
+#   if msd_create(0, addr ctx) != 0: quit $msd_last_error(nil)
+#   var tlens = newSeq[uint32](targets.len); for t in targets: tlens[t.tid] = t.length
+#   check ctx, msd_open(ctx, bam_path, targets.len.cint, addr tlens[0], first_record_voff)  # bgzf_tell after the header
+#   check ctx, msd_set_spans(ctx, n, addr begs[0], addr ends[0])       # from bam.idx: per-contig chunk min/max
+#   check ctx, msd_set_targets(ctx, addr want[0])                      # get_targets + skip rule :703-705
+#   check ctx, msd_set_filters(ctx, mapq.cint, min_len, max_len, eflag, iflag, rgs, n_rg, mode)
+#   check ctx, msd_run(ctx)
+#   for target in sub_targets:
+#     var nrec: int64
+#     let tid = msd_contig_records(ctx, target.tid.cint, addr nrec)    # coverage()'s tid / -2 (:707-712)
+#     if region != "" and tid != -2:
+#       if region.isdigit: discard msd_windows(ctx, tid, window, use_median.cint, addr vals[0], vals.len, addr chrom_region_stat, addr d512[0])
+#       else:              check ctx, msd_regions(ctx, tid, n, addr starts[0], addr stops[0], ...)   # :720-743
+#     if tid != -2: check ctx, msd_contig_stats(ctx, tid, addr chrom_stat, addr dist[0], dist.len, addr dist_len)  # :746-747
+#     if not skip_per_base and tid != -2: check ctx, msd_per_base_runs(ctx, tid, addr s, addr e, addr d, addr n)   # :785
+#     if quantize.len != 0 and tid != -2: check ctx, msd_quantized_runs(ctx, tid, addr quantize[0], quantize.len.cint, ...)  # :802
+#   # formatting (write_summary, write_distribution, fastIntToStr lines, BGZI writers) is unchanged.

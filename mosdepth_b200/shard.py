@@ -1,0 +1,69 @@
+"""Host-side sharding of a BAM across GPUs/ranks: contigs are independent units (the reference
+itself processes one contig at a time, mosdepth.nim:691), so each rank takes a set of contigs chosen by
+longest-processing-time bin packing on their compressed span size, reads only those byte ranges of the file, and
+only the small `total` histograms / stats are combined across ranks (sum_into, mosdepth.nim:761-764,807-813)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def contig_weights(index):
+    """Compressed bytes spanned by each contig (from the BAI/CSI bin chunks)."""
+    return [((c.ref_end >> 16) - (c.ref_beg >> 16) + 1) if c.has_data else 0 for c in index]
+
+
+def lpt_shards(weights, n):
+    """Longest-processing-time bin packing: returns n sorted lists of contig ids; every contig with weight > 0 is
+    assigned exactly once."""
+    loads = [0] * n
+    assign = [[] for _ in range(n)]
+    for tid in sorted(range(len(weights)), key=lambda t: (-weights[t], t)):
+        if weights[tid] <= 0:
+            continue
+        r = min(range(n), key=lambda i: (loads[i], i))
+        loads[r] += weights[tid]
+        assign[r].append(tid)
+    return [sorted(a) for a in assign]
+
+
+MAX_BGZF_BLOCK = 65536
+
+
+def load_compact(bam_path, begs, ends, alloc=None):
+    """Read only the byte ranges that the spans [beg, end) (virtual offsets) need into one host buffer and rebase the
+    virtual offsets onto it.  alloc(nbytes) -> writable uint8 numpy array (e.g. a view of pinned memory).
+    Returns (buffer, new_begs, new_ends)."""
+    fsize = os.path.getsize(bam_path)
+    spans = sorted(zip(begs, ends))
+    ranges = []   # [file_lo, file_hi)
+    for b, e in spans:
+        lo = b >> 16
+        hi = fsize if e == 0 else min(fsize, (e >> 16) + (MAX_BGZF_BLOCK if (e & 0xFFFF) else 0))
+        if ranges and lo <= ranges[-1][1]:
+            ranges[-1][1] = max(ranges[-1][1], hi)
+        else:
+            ranges.append([lo, hi])
+    total = sum(hi - lo for lo, hi in ranges)
+    buf = alloc(total + 64) if alloc else np.zeros(total + 64, dtype=np.uint8)
+    base, off = [], 0
+    with open(bam_path, "rb") as f:
+        for lo, hi in ranges:
+            f.seek(lo)
+            n = f.readinto(memoryview(buf)[off:off + (hi - lo)])
+            assert n == hi - lo
+            base.append((lo, hi, off))
+            off += hi - lo
+    buf[off:] = 0
+
+    def rebase(v):
+        c, u = v >> 16, v & 0xFFFF
+        for lo, hi, o in base:
+            if lo <= c < hi or (c == hi and u == 0):
+                return ((c - lo + o) << 16) | u
+        raise ValueError("virtual offset outside the loaded ranges")
+
+    nb = [rebase(b) for b in begs]
+    ne = [0 if e == 0 else rebase(e) for e in ends]
+    return buf[:off + 64], nb, ne, off

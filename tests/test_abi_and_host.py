@@ -1,0 +1,122 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/mosdepth_b200.h declares, fails loudly
+without a GPU (no CPU fallback), and the host-side logic (header/index parsing, window arithmetic, sharding)."""
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, run_tool
+
+
+@pytest.fixture(scope="module")
+def built():
+    lib = ROOT / "mosdepth_b200" / "libmosdepth_b200.so"
+    if not lib.exists() or not (ROOT / "mosdepth_b200" / "bin" / "mosdepth-b200").exists() or not (ROOT / "tools" / "gen_bam").exists():
+        import __graft_entry__ as ge
+        ge.build()
+    return lib
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = (ROOT / "include" / "mosdepth_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(msd_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(str(built))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    import mosdepth_b200 as m
+    assert set(m.EXPORTS) == declared
+    assert m.load_library().msd_abi_version() == 1
+
+
+def test_no_cpu_fallback(built):
+    """Without an sm_100 device msd_create must fail with MSD_ENODEV and say so."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import mosdepth_b200 as m
+    with pytest.raises(m.MsdError) as ei:
+        m.Context(0)
+    assert ei.value.code == -10
+    r = run_tool(ROOT / "mosdepth_b200" / "bin" / "mosdepth-b200", ["t", ROOT / "tests/golden/fixtures/ovl.bam"], ROOT / "tests", check=False)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+def test_product_never_references_oracle():
+    for p in list((ROOT / "mosdepth_b200").rglob("*")) + [ROOT / "Makefile"]:
+        if p.is_file() and p.suffix in (".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", "") and p.name != "Makefile":
+            try:
+                txt = p.read_text()
+            except UnicodeDecodeError:
+                continue
+            assert "mosdepth_oracle" not in txt and "oracle/" not in txt, p
+
+
+def test_n_windows_matches_window_gen(built):
+    import mosdepth_b200 as m
+    lib = m.load_library()
+
+    def window_gen(window, tlen):   # mosdepth.nim:382-388 in uint32 arithmetic
+        out, start = 0, 0
+        while ((start + window) & 0xFFFFFFFF) < tlen:
+            out += 1; start = (start + window) & 0xFFFFFFFF
+        if start != tlen:
+            out += 1
+        return out
+    for tlen, w in [(0, 5), (1, 1), (1, 500), (499, 500), (500, 500), (501, 500), (16569, 100), (600000045, 500), (1000, 7)]:
+        assert lib.msd_n_windows(tlen, w) == window_gen(w, tlen), (tlen, w)
+
+
+def test_header_and_index_parsing(fixtures):
+    from mosdepth_b200 import hostio
+    h = hostio.read_bam_header(fixtures / "ovl.bam")
+    assert len(h.names) == 87 and h.names[24] == "MT" and h.lengths[24] == 16569
+    ix = hostio.read_index(fixtures / "ovl.bam")
+    assert [i for i, c in enumerate(ix) if c.has_data] == [24] and ix[24].n_mapped == 2 and ix[24].ref_beg == h.first_record_voff
+    h = hostio.read_bam_header(fixtures / "big.bam")
+    assert h.names == ["ref"] and h.lengths == [600000045]
+    ix = hostio.read_index(fixtures / "big.bam")   # BGZF-compressed CSI, depth 6
+    assert ix[0].has_data and ix[0].ref_beg == (69 << 16) and ix[0].ref_end == (166 << 16) and ix[0].n_mapped == 1
+    ix = hostio.read_index(fixtures / "empty-tids.bam")
+    assert sum(c.has_data for c in ix) == 13
+    with pytest.raises(FileNotFoundError):
+        hostio.read_index(fixtures / "track.bed")
+
+
+def test_cli_argument_errors_need_no_gpu(built, fixtures, tmp_path):
+    cli = ROOT / "mosdepth_b200" / "bin" / "mosdepth-b200"
+    r = run_tool(cli, ["-c", "nonexistent", "--by", "20000", "t", fixtures / "ovl.bam"], tmp_path, check=False)
+    assert r.returncode == 1 and "[mosdepth] chromosome nonexistent not found" in r.stderr
+    r = run_tool(cli, ["t", fixtures / "ovl.bam", "--min-frag-len", "10", "--max-frag-len", "9"], tmp_path, check=False)
+    assert r.returncode == 2 and "--max-frag-len was lower than --min-frag-len." in r.stderr
+    r = run_tool(cli, ["xx", "tests/tt.cram"], tmp_path, check=False)
+    assert r.returncode == 1
+    r = run_tool(cli, ["--by", fixtures / "bad.bed", "t", fixtures / "ovl.bam"], tmp_path, check=False)
+    assert r.returncode == 1 and "skipping bad bed line:MT\t2" in r.stderr and "invalid integer: asdf" in r.stderr
+    r = run_tool(cli, ["-t4prefix", "sample.bam"], tmp_path, check=False)
+    assert r.returncode == 1 and "error parsing arguments" in r.stderr
+
+
+def test_lpt_shards_cover_and_balance():
+    from mosdepth_b200.shard import lpt_shards
+    grch38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717, 133797422, 135086622,
+              133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285, 58617616, 64444167, 46709983, 50818468, 156040895, 57227415, 16569]
+    for n in (1, 2, 4, 8):
+        sh = lpt_shards(grch38, n)
+        assert sorted(t for s in sh for t in s) == list(range(25))
+        loads = [sum(grch38[t] for t in s) for s in sh]
+        assert max(loads) <= 1.05 * sum(grch38) / n
+    assert lpt_shards([0, 5, 0, 3], 2) == [[1], [3]]
+
+
+def test_generator_is_thread_count_independent(built, tmp_path):
+    gen = ROOT / "tools" / "gen_bam"
+    for t in (1, 5):
+        subprocess.run([str(gen), "--config", "c3", "--genome-fraction", "0.0003", "--threads", str(t), "-o", str(tmp_path / f"t{t}.bam")], check=True, capture_output=True)
+    from mosdepth_b200 import hostio
+    a = hostio.inflate_all((tmp_path / "t1.bam").read_bytes()); b = hostio.inflate_all((tmp_path / "t5.bam").read_bytes())
+    assert a == b
