@@ -166,7 +166,7 @@ def main():
         dist.barrier()
     import mosdepth_b200 as m
     from mosdepth_b200 import hostio
-    from mosdepth_b200.shard import contig_weights, load_compact, lpt_shards
+    from mosdepth_b200.shard import contig_weights, load_compact, lpt_shards, merge_adjacent_spans
 
     # ---- data: weak scaling = every rank count sees `fraction * world` of the genome, i.e. fixed work per GPU --------
     fraction = args.genome_fraction * world
@@ -183,7 +183,7 @@ def main():
     shards = lpt_shards(weights, world)
     mine = shards[rank]
     want = np.zeros(nt, dtype=np.uint8); want[mine] = 1
-    begs = [index[t].ref_beg for t in mine]; ends = [index[t].ref_end for t in mine]
+    begs, ends = merge_adjacent_spans([index[t].ref_beg for t in mine], [index[t].ref_end for t in mine])
     my_reads = sum(index[t].n_mapped + index[t].n_unmapped for t in mine)
 
     # pinned host image of this rank's byte ranges of the BAM file (the e2e input), virtual offsets rebased onto it

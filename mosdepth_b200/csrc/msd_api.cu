@@ -557,20 +557,11 @@ int msd_run(msd_ctx* ctx) {
 
     ContigTable ct{ctx->d_depth_off, ctx->d_tlen};
     const uint32_t base = ctx->carry_cap;
-    std::vector<Span> spans;
-    {   // neighbouring spans are read in one go: the bytes between two record boundaries are whole records, and
-        // records of contigs that are not selected are dropped by the target mask anyway
-        std::vector<Span> in = ctx->spans;
-        if (in.empty()) in.push_back({ctx->first_voff, 0});
-        std::sort(in.begin(), in.end(), [](const Span& a, const Span& b) { return a.beg < b.beg; });
-        const uint64_t max_gap = env_u64("MSD_SPAN_MERGE_KB", 1024) << 10;
-        for (const Span& s : in) {
-            if (s.beg == ~0ull) continue;
-            if (!spans.empty() && spans.back().end != 0 && s.beg >= spans.back().end && (s.beg >> 16) - (spans.back().end >> 16) <= max_gap) { spans.back().end = s.end; continue; }
-            if (!spans.empty() && (spans.back().end == 0 || s.beg < spans.back().end)) { if (spans.back().end != 0 && (s.end == 0 || s.end > spans.back().end)) spans.back().end = s.end; continue; }
-            spans.push_back(s);
-        }
-    }
+    // spans are taken as given (the caller merges neighbouring contigs when the bytes between them are genuine
+    // file bytes; a compact per-rank buffer has cut points between its ranges, so the library must not guess)
+    std::vector<Span> spans = ctx->spans;
+    if (spans.empty()) spans.push_back({ctx->first_voff, 0});
+    std::sort(spans.begin(), spans.end(), [](const Span& a, const Span& b) { return a.beg < b.beg; });
     uint64_t chunk_idx = 0;
     const uint8_t* F = ctx->bytes; const uint64_t N = ctx->n_bytes;
 

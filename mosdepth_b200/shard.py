@@ -28,7 +28,34 @@ def lpt_shards(weights, n):
     return [sorted(a) for a in assign]
 
 
-MAX_BGZF_BLOCK = 65536
+def merge_adjacent_spans(begs, ends, max_gap_bytes=1 << 20):
+    """Merge spans of one genuine BAM file whose compressed gap is small: the bytes between two record boundaries are
+    whole records, and records of contigs that are not selected are dropped by the library's target mask."""
+    out = []
+    for b, e in sorted(zip(begs, ends)):
+        if out and out[-1][1] != 0 and b >= out[-1][1] and (b >> 16) - (out[-1][1] >> 16) <= max_gap_bytes:
+            out[-1][1] = e
+        else:
+            out.append([b, e])
+    return [o[0] for o in out], [o[1] for o in out]
+
+
+def _block_len(f, coff):
+    f.seek(coff)
+    h = f.read(18)
+    assert len(h) == 18 and h[:2] == b"\x1f\x8b", "span end is not at a BGZF block"
+    xlen = h[10] | (h[11] << 8)
+    if xlen == 6 and h[12:14] == b"BC":
+        return (h[16] | (h[17] << 8)) + 1
+    f.seek(coff + 12)
+    extra = f.read(xlen)
+    q = 0
+    while q + 4 <= xlen:
+        slen = extra[q + 2] | (extra[q + 3] << 8)
+        if extra[q] == 66 and extra[q + 1] == 67 and slen == 2:
+            return (extra[q + 4] | (extra[q + 5] << 8)) + 1
+        q += 4 + slen
+    raise ValueError("BGZF block without BC subfield")
 
 
 def load_compact(bam_path, begs, ends, alloc=None):
@@ -37,14 +64,15 @@ def load_compact(bam_path, begs, ends, alloc=None):
     Returns (buffer, new_begs, new_ends)."""
     fsize = os.path.getsize(bam_path)
     spans = sorted(zip(begs, ends))
-    ranges = []   # [file_lo, file_hi)
-    for b, e in spans:
-        lo = b >> 16
-        hi = fsize if e == 0 else min(fsize, (e >> 16) + (MAX_BGZF_BLOCK if (e & 0xFFFF) else 0))
-        if ranges and lo <= ranges[-1][1]:
-            ranges[-1][1] = max(ranges[-1][1], hi)
-        else:
-            ranges.append([lo, hi])
+    ranges = []   # [file_lo, file_hi): whole BGZF blocks only
+    with open(bam_path, "rb") as f:
+        for b, e in spans:
+            lo = b >> 16
+            hi = fsize if e == 0 else ((e >> 16) + _block_len(f, e >> 16) if (e & 0xFFFF) else (e >> 16))
+            if ranges and lo <= ranges[-1][1]:
+                ranges[-1][1] = max(ranges[-1][1], hi)
+            else:
+                ranges.append([lo, hi])
     total = sum(hi - lo for lo, hi in ranges)
     buf = alloc(total + 64) if alloc else np.zeros(total + 64, dtype=np.uint8)
     base, off = [], 0

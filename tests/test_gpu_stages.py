@@ -130,3 +130,43 @@ def test_per_base_runs_match_oracle(ctx, oracle_bin, fixtures, tmp_path, name, m
         got = list(zip(s.tolist(), e.tolist(), d.tolist()))
         assert got == want, cname
     assert n_with >= 1
+
+
+def test_sharded_compact_buffers_match_whole_file(ctx, tmp_path):
+    """Emulates the N-rank path on one GPU: every 'rank' loads only its contigs' byte ranges (rebased offsets,
+    merged neighbours) and must reproduce the whole-file per-contig results."""
+    import subprocess
+    import mosdepth_b200 as m
+    from conftest import ROOT
+    from mosdepth_b200 import hostio
+    from mosdepth_b200.shard import contig_weights, load_compact, lpt_shards, merge_adjacent_spans
+    bam = tmp_path / "s.bam"
+    subprocess.run([str(ROOT / "tools" / "gen_bam"), "--config", "c3", "--genome-fraction", "0.001", "--threads", "8", "-o", str(bam)], check=True, capture_output=True)
+    hdr = ctx.open(bam)
+    ctx.set_filters(mode=m.MODE_FAST)
+    ctx.run()
+    whole = {}
+    for t in range(len(hdr.names)):
+        rc, n = ctx.contig_records(t)
+        st, dist = ctx.contig_stats(t)
+        vals, rst, rd = ctx.windows(t, 500)
+        whole[t] = (n, st.cum_depth, st.max_depth, dist.tolist(), vals.tobytes(), rd.tolist())
+    index = hostio.read_index(bam)
+    for world in (2, 3):
+        seen = set()
+        for rank, mine in enumerate(lpt_shards(contig_weights(index), world)):
+            begs, ends = merge_adjacent_spans([index[t].ref_beg for t in mine], [index[t].ref_end for t in mine])
+            buf, nb, ne, used = load_compact(bam, begs, ends)
+            c2 = m.Context(0)
+            c2.open_mem(buf, hdr)
+            want = np.zeros(len(hdr.names), dtype=np.uint8); want[mine] = 1
+            c2.set_targets(want); c2.set_spans(nb, ne); c2.set_filters(mode=m.MODE_FAST)
+            c2.run()
+            for t in mine:
+                rc, n = c2.contig_records(t)
+                st, dist = c2.contig_stats(t)
+                vals, rst, rd = c2.windows(t, 500)
+                assert (n, st.cum_depth, st.max_depth, dist.tolist(), vals.tobytes(), rd.tolist()) == whole[t], (world, rank, t)
+                seen.add(t)
+            c2.close()
+        assert seen == set(range(len(hdr.names)))
