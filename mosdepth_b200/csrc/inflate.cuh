@@ -1,376 +1,458 @@
-// inflate.cuh -- K1 bgzf_inflate: raw DEFLATE (RFC 1951) decoder, one warp per BGZF block.
+// inflate.cuh -- K1 bgzf_inflate: raw DEFLATE (RFC 1951) decoder for BGZF blocks.
 //
 // Replaces htslib's bgzf inflate (+ its thread pool, `open(bam, threads=)`, mosdepth.nim:888,968) [ext].
 // Each BGZF block is an independent DEFLATE stream (the LZ77 window never crosses blocks), so the only
-// parallelism is across blocks: a 30X WGS BAM has ~3.3 M of them.  Design:
-//   * one warp decodes one block; warps pull block indices from an atomic ticket (blocks differ in cost);
-//   * per warp ~7 KB of shared memory: 10-bit lit/len and 8-bit distance lookup tables (one probe per
-//     symbol; longer codes fall back to a canonical bit-by-bit walk), the code-length arrays, a 512-byte ring
-//     of compressed words that all lanes refill with coalesced 128-byte loads, and a 32-entry symbol queue;
-//   * lane 0 runs the serial Huffman chain for up to 32 symbols, then the whole warp resolves the queue:
-//     literals are stored in parallel, matches are copied cooperatively straight in global memory
-//     (the output block is the LZ77 window: sources are L2 hits).
-//   * 8 warps per CTA, 4 CTAs per SM -> 32 concurrent decoders per SM, 4736 per B200.
+// parallelism is across blocks: a 30X WGS BAM has ~3.3 M of them.
+//
+// Design (r1c; the r1a profile showed one-decoder-per-warp to be issue bound with 1 active lane in 75 % of the
+// instructions, profiles/README.md):
+//   * a warp is four independent "octets" of 8 lanes; each octet decodes its own BGZF block, so every instruction of
+//     the serial Huffman chain advances up to four symbols (lanes 0, 8, 16, 24 run four chains in SIMT lock step);
+//   * octets pull block indices from an atomic ticket (blocks differ in cost) and never wait for each other
+//     except at one warp-wide vote per round;
+//   * 2.5 KB of shared memory per octet: 9-bit lit/len and 7-bit distance root tables with 16-bit entries (length /
+//     distance bases are computed arithmetically), canonical-order symbol arrays + left-aligned limits for the ~5 % of
+//     symbols with longer codes, a 64-word ring of compressed words refilled by the octet with 32-byte loads, and a
+//     32-entry match queue; the code lengths of a dynamic header are parked inside the not-yet-built lit/len table;
+//   * the octet leader stores literals straight to global memory while decoding; matches are queued and then
+//     copied by the 8 lanes of the octet in stream order (the output block is the LZ77 window: sources hit L1/L2);
+//   * 2 warps (8 octets) per CTA, 11 CTAs per SM -> 88 concurrent decoders per SM, 13024 per B200 (the kernel is
+//     latency bound on the serial chains, so decoders per SM is what buys throughput).
 #pragma once
 #include "common.cuh"
 
 namespace msd {
 
-constexpr int kLitBits = 10;
-constexpr int kDistBits = 8;
-constexpr int kInflateWarps = 8;
-constexpr int kRingWords = 96;           // compressed-word ring per warp; a round never needs more than 56 words
-constexpr int kQueue = 32;               // symbols decoded per cooperative round
+constexpr int kLitBits = 9;
+constexpr int kDistBits = 7;
+constexpr int kInflateWarps = 2;         // warps per CTA
+constexpr int kOctetsPerWarp = 4;
+constexpr int kRingWords = 64;           // compressed-word ring per octet (power of two)
+constexpr int kRoundSymbols = 32;        // lit/len symbols decoded per round (bounds the ring words a round can eat: 48)
+constexpr int kQueue = 32;               // matches queued per round
 
-// table entry: [3:0] code length, [7:4] extra-bit count, [9:8] kind, [31:16] value
-constexpr uint32_t kKindLit = 0u << 8, kKindLen = 1u << 8, kKindEob = 2u << 8, kKindLong = 3u << 8, kKindMask = 3u << 8;
-constexpr uint32_t kMatchFlag = 0x80000000u;
+// 16-bit table entry: [3:0] code length (0 = invalid), [5:4] kind, [13:6] value
+//   lit/len table: kind 0 literal (value = byte), 1 length (value = symbol - 257), 2 end of block, 3 longer code / invalid
+//   distance table: kind 0 distance (value = symbol), 3 longer code / invalid
+constexpr uint32_t kKindLit = 0u, kKindLen = 1u, kKindEob = 2u, kKindLong = 3u;
 
 enum InflateStatus : uint32_t {
     kInfOk = 0, kInfBadBlockType = 1, kInfBadStored = 2, kInfBadCodeLengths = 3, kInfBadSymbol = 4, kInfBadDistance = 5,
     kInfOverflow = 6, kInfShort = 7, kInfOversubscribed = 8
 };
 
-struct __align__(16) InflateWarpState {
-    uint32_t lit_tab[1 << kLitBits];     // 4096 B
-    uint32_t dist_tab[1 << kDistBits];   // 1024 B
-    uint32_t ring[kRingWords];           //  384 B
-    uint32_t q_sym[kQueue];              //  128 B
-    uint32_t q_pos[kQueue];              //  128 B
-    uint16_t lit_sorted[288];            //  576 B  symbols in canonical order (slow path / table fill)
+struct __align__(16) InflateOctetState {
+    uint16_t lit_tab[1 << kLitBits];     // 1024 B; while a dynamic header is read: [0,256) code-length-code table, [256,576) code lengths
+    uint16_t dist_tab[1 << kDistBits];   //  256 B
+    uint32_t ring[kRingWords];           //  256 B
+    uint32_t q_sym[kQueue];              //  128 B  match queue: [8:0] length, [30:16] distance - 1   (also table-build scratch)
+    uint16_t q_pos[kQueue];              //   64 B  output offset of the match inside the block        (also table-build scratch)
+    uint16_t lit_sorted[288];            //  576 B  symbols in canonical order (longer codes / table fill)
     uint16_t dist_sorted[32];            //   64 B
-    uint16_t lit_count[16];              //   32 B  codes per length
-    uint16_t dist_count[16];             //   32 B
-    uint16_t cl_tab[128];                //  256 B  code-length-code lookup (7 bits): [3:0] len, [15:4] symbol
-    uint8_t lens[320];                   //  320 B  lit/len + distance code lengths
+    uint16_t lit_limit[16], lit_base[16];    // 64 B  canonical decode of codes longer than the root: left-aligned limits, index bases
+    uint16_t dist_limit[16], dist_base[16];  // 64 B
 };
-static_assert(sizeof(InflateWarpState) <= 7040, "8 warps x 7040 B + 1 KB reserve = 56 KB per CTA -> 4 CTAs (32 decoders) per SM");
+static_assert(sizeof(InflateOctetState) == 2496, "8 octets x 2496 B + 1 KB reserve per CTA -> 11 CTAs (88 decoders) per SM");
+constexpr int kInflateCtasPerSm = 11;
 
-__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-__constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-__constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
+// RFC 1951 length code (symbol - 257): base and extra bits, computed instead of looked up
+MSD_D void len_base_extra(uint32_t idx, uint32_t& base, uint32_t& extra) {
+    if (idx < 8) { base = 3 + idx; extra = 0; }
+    else if (idx == 28) { base = 258; extra = 0; }
+    else { extra = (idx - 4) >> 2; base = 3 + ((4 + (idx & 3)) << extra); }
+}
+MSD_D void dist_base_extra(uint32_t sym, uint32_t& base, uint32_t& extra) {
+    if (sym < 4) { base = 1 + sym; extra = 0; }
+    else { extra = (sym >> 1) - 1; base = 1 + ((2 + (sym & 1)) << extra); }
+}
+
 MSD_D uint32_t litlen_entry(uint32_t sym, uint32_t len) {
-    if (sym < 256) return (sym << 16) | kKindLit | len;
-    if (sym == 256) return kKindEob | len;
+    if (sym < 256) return (sym << 6) | (kKindLit << 4) | len;
+    if (sym == 256) return (kKindEob << 4) | len;
     if (sym > 285) return 0;   // 286, 287 never appear in valid data
-    return ((uint32_t)c_len_base[sym - 257] << 16) | kKindLen | ((uint32_t)c_len_extra[sym - 257] << 4) | len;
+    return ((sym - 257) << 6) | (kKindLen << 4) | len;
 }
 MSD_D uint32_t dist_entry(uint32_t sym, uint32_t len) {
     if (sym > 29) return 0;
-    return ((uint32_t)c_dist_base[sym] << 16) | ((uint32_t)c_dist_extra[sym] << 4) | len;
+    return (sym << 6) | len;
 }
 
-// lane-0 bit reader over the shared ring
+// leader-lane bit reader over the octet's ring
 struct BitReader {
     uint64_t bb;
     int bc;
     uint32_t wpos;   // next ring word (absolute word index in the block's aligned stream)
     MSD_D void refill(const uint32_t* ring) {
-        if (bc <= 32) { bb |= (uint64_t)ring[wpos % kRingWords] << bc; bc += 32; wpos++; }
+        if (bc <= 32) { bb |= (uint64_t)ring[wpos & (kRingWords - 1)] << bc; bc += 32; wpos++; }
     }
     MSD_D uint32_t peek(int n) const { return (uint32_t)bb & ((1u << n) - 1u); }
     MSD_D void drop(int n) { bb >>= n; bc -= n; }
     MSD_D uint32_t take(int n) { uint32_t v = peek(n); drop(n); return v; }
 };
 
-// Build one decode table from code lengths.  All 32 lanes call it.  Returns 0 ok, else InflateStatus.
-// lens[0..n): code lengths; tab: 1<<bits entries; sorted/count: canonical order + per-length counts;
-// scratch: 64 words of shared memory (the symbol queue, idle while tables are built).
-template <bool kIsDist>
-MSD_D uint32_t build_table(const uint8_t* lens, int n, uint32_t* tab, int bits, uint16_t* sorted, uint16_t* count,
-                           uint32_t* scratch, int lane) {
-    uint32_t* first_code = scratch;        // [16]
-    uint32_t* first_idx = scratch + 16;    // [16]; first_idx[0] = number of coded symbols
-    uint32_t* offs = scratch + 32;         // [16]
+// Table construction, pass 1 (octet leader, serial: ~300 iterations per DEFLATE block, ~1 % of its decode time):
+// canonical order of the coded symbols, per-length end indices, and the limit/base arrays of the canonical decoder.
+// cnt: 16 words of scratch.  Returns 0 or an InflateStatus.
+MSD_D uint32_t table_pass1(const uint8_t* lens, int n, uint16_t* sorted, uint16_t* limit, uint16_t* base, uint32_t* end, uint32_t* cnt) {
     uint32_t status = 0;
-    if (lane < 16) count[lane] = 0;
-    for (int i = lane; i < (1 << bits); i += 32) tab[i] = 0;
-    __syncwarp();
-    if (lane == 0) {
-        // serial: ~300 iterations per DEFLATE block, <1% of the block's decode time
-        for (int s = 0; s < n; s++) count[lens[s]]++;
-        count[0] = 0;
-        int left = 1;
-        uint32_t code = 0, idx = 0;
-        for (int l = 1; l < 16; l++) {
-            left <<= 1; left -= (int)count[l]; if (left < 0) status = kInfOversubscribed;
-            code = (code + count[l - 1]) << 1;
-            first_code[l] = code; first_idx[l] = idx; offs[l] = idx; idx += count[l];
-        }
-        first_idx[0] = idx; first_code[0] = 0;
-        for (int s = 0; s < n; s++) { int l = lens[s]; if (l) sorted[offs[l]++] = (uint16_t)s; }
+    for (int l = 0; l < 16; l++) cnt[l] = 0;
+    for (int s = 0; s < n; s++) cnt[lens[s]]++;
+    cnt[0] = 0;
+    int left = 1;
+    uint32_t code = 0, idx = 0;
+    end[0] = 0; limit[0] = 0; base[0] = 0;
+    for (int l = 1; l < 16; l++) {
+        left <<= 1; left -= (int)cnt[l]; if (left < 0) status = kInfOversubscribed;
+        code = (code + cnt[l - 1]) << 1;
+        base[l] = (uint16_t)(idx - code);                              // sorted index = base + code (mod 2^16)
+        limit[l] = (uint16_t)((code + cnt[l]) << (15 - l));            // exclusive, left aligned to 15 bits (0x8000 = complete)
+        end[l] = idx; idx += cnt[l];
     }
-    status = __shfl_sync(0xffffffffu, status, 0);
-    __syncwarp();
-    if (status) return status;
-    const int total = (int)first_idx[0];
-    for (int i = lane; i < total; i += 32) {
-        uint32_t sym = sorted[i];
-        uint32_t len = lens[sym];
-        uint32_t code = first_code[len] + ((uint32_t)i - first_idx[len]);
-        uint32_t rev = __brev(code) >> (32 - len);   // DEFLATE packs Huffman codes MSB-first into an LSB-first stream
-        if ((int)len <= bits) {
-            uint32_t e = kIsDist ? dist_entry(sym, len) : litlen_entry(sym, len);
-            for (uint32_t k = rev; k < (1u << bits); k += (1u << len)) tab[k] = e;
-        } else {
-            tab[rev & ((1u << bits) - 1u)] = kKindLong | 15u;   // resolved by the canonical walk
-        }
-    }
-    __syncwarp();
-    return 0;
+    for (int s = 0; s < n; s++) { const int l = lens[s]; if (l) sorted[end[l]++] = (uint16_t)s; }   // end[l] now ends length l
+    return status;
 }
 
-// canonical bit-by-bit decode (codes longer than the root table); lane 0 only.  Returns symbol or 0xffff.
-MSD_D uint32_t slow_decode(BitReader& br, const uint16_t* count, const uint16_t* sorted) {
-    uint32_t code = 0, first = 0, index = 0;
-    for (int len = 1; len < 16; len++) {
-        code |= br.take(1);
-        uint32_t c = count[len];
-        if (code - first < c) return sorted[index + (code - first)];
-        index += c; first += c; first <<= 1; code <<= 1;
+// pass 2 (8 lanes): fill the root table from the canonical order; codes longer than the root keep the "long" marker
+template <bool kIsDist>
+MSD_D void table_pass2(uint16_t* tab, int bits, const uint16_t* sorted, const uint16_t* base, const uint32_t* end, int gl) {
+    for (int i = gl; i < (1 << bits); i += 8) tab[i] = (uint16_t)(kKindLong << 4);
+    uint32_t start = 0;
+    for (int l = 1; l <= bits; l++) {
+        const uint32_t e = end[l];
+        for (uint32_t i = start + gl; i < e; i += 8) {
+            const uint32_t sym = sorted[i];
+            const uint32_t code = (i - base[l]) & 0xffffu;
+            const uint32_t rev = __brev(code) >> (32 - l);   // DEFLATE packs Huffman codes MSB-first into an LSB-first stream
+            uint16_t ent = (uint16_t)(kIsDist ? dist_entry(sym, (uint32_t)l) : litlen_entry(sym, (uint32_t)l));
+            if (!ent) ent = (uint16_t)((kKindLong << 4) | 15u);   // symbol that must never occur: flagged when met
+            for (uint32_t k = rev; k < (1u << bits); k += (1u << l)) tab[k] = ent;
+        }
+        start = e;
+    }
+}
+
+// canonical decode of a code longer than the root table (leader only): compare the next 15 bits, MSB first, with the
+// left-aligned per-length limits.  Returns the symbol (0xffff: no such code) and consumes its bits.
+MSD_D uint32_t slow_decode(BitReader& br, int root_bits, const uint16_t* limit, const uint16_t* base, const uint16_t* sorted) {
+    const uint32_t c = __brev((uint32_t)br.bb) >> 17;
+    for (int l = root_bits + 1; l < 16; l++) {
+        if (c < limit[l]) { br.drop(l); return sorted[(base[l] + (c >> (15 - l))) & 0xffffu]; }
     }
     return 0xffffu;
 }
 
+enum OctetPhase : int { kPhIdle = 0, kPhHeader = 1, kPhLengths = 2, kPhSymbols = 3, kPhStored = 4, kPhFinished = 5 };
+
 // The kernel.  comp: compressed chunk buffer; out: inflated chunk buffer; status[b] receives InflateStatus.
-__global__ void __launch_bounds__(kInflateWarps * 32, 4)
+__global__ void __launch_bounds__(kInflateWarps * 32, kInflateCtasPerSm)
 bgzf_inflate_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, int n_blocks,
                     uint32_t* __restrict__ ticket, uint32_t* __restrict__ status_out, uint32_t* __restrict__ error_count) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    InflateWarpState& S = reinterpret_cast<InflateWarpState*>(smem_raw)[warp];
+    const int gl = lane & 7;                       // lane inside the octet
+    const int leader_lane = lane & 24;             // warp lane id of this octet's leader
+    const unsigned gmask = 0xffu << leader_lane;
+    const bool leader = gl == 0;
+    InflateOctetState& S = reinterpret_cast<InflateOctetState*>(smem_raw)[warp * kOctetsPerWarp + (lane >> 3)];
+    uint8_t* const lens = reinterpret_cast<uint8_t*>(S.lit_tab) + 256;   // code lengths live inside lit_tab until the tables are built
+
+    // per-octet state; the decoder state proper lives in the leader's registers
+    int phase = kPhIdle;
+    int b = 0;
+    const uint32_t* __restrict__ src_words = nullptr;
+    uint8_t* __restrict__ dst = nullptr;
+    uint32_t total_words = 0, isize = 0, lead = 0, clen = 0, loaded = 0;
+    BitReader br; br.bb = 0; br.bc = 0; br.wpos = 0;
+    uint32_t outp = 0, err = 0;
+    int bfinal = 0, hlit = 0, hdist = 0, cl_idx = 0;
+    uint32_t stored_pos = 0, stored_len = 0, guard = 0;
+    bool first_fill = false;
 
     for (;;) {
-        int b = 0;
-        if (lane == 0) b = (int)atomicAdd(ticket, 1u);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= n_blocks) break;
-        const BlockDesc bd = blocks[b];
-        const uint32_t lead = (uint32_t)(bd.src & 3);
-        const uint32_t* __restrict__ src_words = reinterpret_cast<const uint32_t*>(comp + (bd.src - lead));
-        const uint32_t total_words = (lead + bd.clen + 3) / 4;
-        uint8_t* __restrict__ dst = out + bd.dst;
-        const uint32_t isize = bd.isize;
-
-        uint32_t loaded = 0;                 // words fetched into the ring so far (uniform)
-        BitReader br; br.bb = 0; br.bc = 0; br.wpos = 0;
-        uint32_t outp = 0;                   // lane 0: bytes produced
-        uint32_t err = 0;                    // lane 0
-        int state = 0;                       // lane 0: 0 header, 1 code lengths, 2 symbols, 3 stored, 4 done
-        int bfinal = 0, hlit = 0, hdist = 0, cl_idx = 0;
-        uint32_t stored_pos = 0, stored_len = 0;
-        bool first_fill = true;
-        uint32_t guard = 0;
-
-        for (;;) {
-            // ---- refill the ring (all lanes): keep > 64 words ahead of the reader --------------------------
-            uint32_t consumed = __shfl_sync(0xffffffffu, br.wpos, 0);
-            while (loaded < total_words && loaded + 32 - consumed <= (uint32_t)kRingWords) {
-                uint32_t w = loaded + lane;
-                if (w < total_words) S.ring[w % kRingWords] = __ldg(src_words + w);
-                else S.ring[w % kRingWords] = 0;
-                loaded += 32;
+        // ---- octets that finished a block take the next ticket ----------------------------------------------------
+        if (phase == kPhIdle) {
+            int nb = 0;
+            if (leader) nb = (int)atomicAdd(ticket, 1u);
+            b = __shfl_sync(gmask, nb, leader_lane);
+            if (b >= n_blocks) phase = kPhFinished;
+            else {
+                const BlockDesc bd = blocks[b];
+                lead = (uint32_t)(bd.src & 3); clen = bd.clen;
+                src_words = reinterpret_cast<const uint32_t*>(comp + (bd.src - lead));
+                total_words = (lead + bd.clen + 3) / 4;
+                dst = out + bd.dst; isize = bd.isize;
+                loaded = 0; br.bb = 0; br.bc = 0; br.wpos = 0; outp = 0; err = 0; guard = 0; bfinal = 0;
+                first_fill = true;
+                phase = kPhHeader;
             }
-            __syncwarp();
-            if (lane == 0 && first_fill) { br.refill(S.ring); br.drop((int)lead * 8); br.refill(S.ring); }
+        }
+        if (__all_sync(0xffffffffu, phase == kPhFinished)) break;   // also re-converges the four octets once per round
+        if (phase == kPhFinished) continue;
+
+        // ---- refill the ring (8 lanes): keep > 56 words ahead of the reader ---------------------------------------
+        {
+            const uint32_t consumed = __shfl_sync(gmask, br.wpos, leader_lane);
+            while (loaded < total_words && loaded + 8 - consumed <= (uint32_t)kRingWords) {
+                const uint32_t w = loaded + gl;
+                S.ring[w & (kRingWords - 1)] = (w < total_words) ? __ldg(src_words + w) : 0u;
+                loaded += 8;
+            }
+            __syncwarp(gmask);
+            if (leader && first_fill) { br.refill(S.ring); br.drop((int)lead * 8); br.refill(S.ring); }
             first_fill = false;
+        }
+        if (++guard > 400000u && leader) err = kInfShort;
+        {
+            const uint32_t e_any = __shfl_sync(gmask, err, leader_lane);
+            if (e_any) { if (leader) { status_out[b] = err; atomicAdd(error_count, 1u); } phase = kPhIdle; continue; }
+        }
 
-            int st = __shfl_sync(0xffffffffu, state, 0);
-            uint32_t e_any = __shfl_sync(0xffffffffu, err, 0);
-            if (st == 4 || e_any) break;
-            if (++guard > 200000u) { if (lane == 0) err = kInfShort; break; }
-
-            if (st == 0) {
-                // ---- DEFLATE block header -----------------------------------------------------------------
-                int btype = 0;
-                if (lane == 0) {
+        if (phase == kPhSymbols) {
+            // ---- leader: up to kRoundSymbols symbols through the Huffman chain; literals go straight to global -----
+            int n = 0;          // matches queued
+            int next_phase = kPhSymbols;
+            const uint32_t round_start_outp = outp;
+            if (leader) {
+                for (int it = 0; it < kRoundSymbols; it++) {
                     br.refill(S.ring);
-                    bfinal = (int)br.take(1);
-                    btype = (int)br.take(2);
-                    if (btype == 0) {
-                        br.drop(br.bc & 7);
-                        br.refill(S.ring);
-                        uint32_t len = br.take(16), nlen = br.take(16);
-                        if ((len ^ 0xffffu) != nlen) err = kInfBadStored;
-                        stored_len = len;
-                        stored_pos = br.wpos * 4u - (uint32_t)br.bc / 8u;   // byte index in the aligned stream
-                        if (outp + len > isize) err = kInfOverflow;
-                        if (stored_pos + len > lead + bd.clen) err = kInfBadStored;
-                        state = 3;
-                    } else if (btype == 2) {
-                        hlit = (int)br.take(5) + 257; hdist = (int)br.take(5) + 1;
-                        int hclen = (int)br.take(4) + 4;
-                        if (hlit > 286 || hdist > 30) err = kInfBadCodeLengths;
-                        for (int i = 0; i < 19; i++) S.lens[i] = 0;
-                        for (int i = 0; i < hclen; i++) { br.refill(S.ring); S.lens[c_cl_order[i]] = (uint8_t)br.take(3); }
-                        // code-length code table (7-bit root, serial: 19 symbols)
-                        uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, next[8];
-                        for (int i = 0; i < 19; i++) cnt[S.lens[i]]++;
-                        cnt[0] = 0;
-                        int left = 1;
-                        for (int l = 1; l < 8; l++) { left <<= 1; left -= (int)cnt[l]; }
-                        if (left < 0) err = kInfOversubscribed;
-                        uint32_t code = 0;
-                        for (int l = 1; l < 8; l++) { code = (code + cnt[l - 1]) << 1; next[l] = code; }
-                        for (int i = 0; i < 128; i++) S.cl_tab[i] = 0;
-                        for (int s = 0; s < 19; s++) {
-                            uint32_t l = S.lens[s];
-                            if (!l) continue;
-                            uint32_t c = next[l]++;
-                            uint32_t rev = __brev(c) >> (32 - l);
-                            for (uint32_t k = rev; k < 128; k += (1u << l)) S.cl_tab[k] = (uint16_t)((s << 4) | l);
-                        }
-                        cl_idx = 0;
-                        state = 1;
-                    } else if (btype == 1) {
-                        hlit = 288; hdist = 30;
-                        state = 2;
-                    } else {
-                        err = kInfBadBlockType;
+                    uint32_t e = S.lit_tab[br.peek(kLitBits)];
+                    uint32_t kind = (e >> 4) & 3u;
+                    if (kind == kKindLit) {
+                        if (outp >= isize) { err = kInfOverflow; break; }
+                        br.drop((int)(e & 15u));
+                        dst[outp++] = (uint8_t)(e >> 6);
+                        continue;
                     }
-                }
-                btype = __shfl_sync(0xffffffffu, btype, 0);
-                if (btype == 1) {
-                    // fixed Huffman code lengths, then the same table builder
-                    for (int i = lane; i < 288; i += 32) S.lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
-                    if (lane < 30) S.lens[288 + lane] = 5;
-                    __syncwarp();
-                    uint32_t e1 = build_table<false>(S.lens, 288, S.lit_tab, kLitBits, S.lit_sorted, S.lit_count, S.q_sym, lane);
-                    uint32_t e2 = build_table<true>(S.lens + 288, 30, S.dist_tab, kDistBits, S.dist_sorted, S.dist_count, S.q_sym, lane);
-                    if (lane == 0 && (e1 | e2)) err = e1 ? e1 : e2;
-                }
-                __syncwarp();
-            } else if (st == 1) {
-                // ---- dynamic block: read up to 128 code lengths per round -----------------------------------
-                int done = 0;
-                if (lane == 0) {
-                    const int total = hlit + hdist;
-                    int budget = 128;
-                    while (cl_idx < total && budget-- > 0 && !err) {
-                        br.refill(S.ring);
-                        uint32_t e = S.cl_tab[br.peek(7)];
-                        uint32_t l = e & 15u, sym = e >> 4;
-                        if (!l) { err = kInfBadCodeLengths; break; }
-                        br.drop((int)l);
-                        if (sym < 16) { S.lens[cl_idx++] = (uint8_t)sym; continue; }
-                        uint32_t rep, val = 0;
-                        if (sym == 16) { if (cl_idx == 0) { err = kInfBadCodeLengths; break; } val = S.lens[cl_idx - 1]; rep = 3 + br.take(2); }
-                        else if (sym == 17) rep = 3 + br.take(3);
-                        else rep = 11 + br.take(7);
-                        if (cl_idx + (int)rep > total) { err = kInfBadCodeLengths; break; }
-                        while (rep--) S.lens[cl_idx++] = (uint8_t)val;
-                    }
-                    done = (cl_idx >= total) && !err;
-                    if (done && S.lens[256] == 0) { err = kInfBadCodeLengths; done = 0; }
-                }
-                done = __shfl_sync(0xffffffffu, done, 0);
-                __syncwarp();
-                if (done) {
-                    int hl = __shfl_sync(0xffffffffu, hlit, 0), hd = __shfl_sync(0xffffffffu, hdist, 0);
-                    uint32_t e1 = build_table<false>(S.lens, hl, S.lit_tab, kLitBits, S.lit_sorted, S.lit_count, S.q_sym, lane);
-                    uint32_t e2 = build_table<true>(S.lens + hl, hd, S.dist_tab, kDistBits, S.dist_sorted, S.dist_count, S.q_sym, lane);
-                    if (lane == 0) { if (e1 | e2) err = e1 ? e1 : e2; state = 2; }
-                }
-                __syncwarp();
-            } else if (st == 2) {
-                // ---- lane 0: up to kQueue symbols through the Huffman chain ---------------------------------
-                int n = 0;
-                if (lane == 0) {
-                    while (n < kQueue) {
-                        br.refill(S.ring);
-                        uint32_t e = S.lit_tab[br.peek(kLitBits)];
-                        if ((e & kKindMask) == kKindLong) {
-                            uint32_t sym = slow_decode(br, S.lit_count, S.lit_sorted);
-                            e = sym == 0xffffu ? 0u : litlen_entry(sym, 1);
-                            if (!e) { err = kInfBadSymbol; break; }
-                        } else {
-                            if (!(e & 15u)) { err = kInfBadSymbol; break; }
-                            br.drop((int)(e & 15u));
-                        }
-                        uint32_t kind = e & kKindMask;
+                    if (kind == kKindLong) {
+                        if (e & 15u) { err = kInfBadSymbol; break; }
+                        uint32_t sym = slow_decode(br, kLitBits, S.lit_limit, S.lit_base, S.lit_sorted);
+                        e = sym == 0xffffu ? 0u : litlen_entry(sym, 1);
+                        if (!e) { err = kInfBadSymbol; break; }
+                        kind = (e >> 4) & 3u;
                         if (kind == kKindLit) {
-                            S.q_sym[n] = e >> 16; S.q_pos[n] = outp; n++; outp += 1;
-                        } else if (kind == kKindEob) {
-                            state = bfinal ? 4 : 0;
-                            break;
-                        } else {
-                            uint32_t len = (e >> 16) + br.take((int)((e >> 4) & 15u));
-                            br.refill(S.ring);
-                            uint32_t d = S.dist_tab[br.peek(kDistBits)];
-                            if ((d & kKindMask) == kKindLong) {
-                                uint32_t sym = slow_decode(br, S.dist_count, S.dist_sorted);
-                                d = sym == 0xffffu ? 0u : dist_entry(sym, 1);
-                                if (!d) { err = kInfBadDistance; break; }
-                                br.refill(S.ring);
-                            } else {
-                                if (!(d & 15u)) { err = kInfBadDistance; break; }
-                                br.drop((int)(d & 15u));
-                            }
-                            uint32_t dist = (d >> 16) + br.take((int)((d >> 4) & 15u));
-                            if (dist > outp) { err = kInfBadDistance; break; }
-                            S.q_sym[n] = kMatchFlag | ((dist - 1u) << 16) | len; S.q_pos[n] = outp; n++; outp += len;
+                            if (outp >= isize) { err = kInfOverflow; break; }
+                            dst[outp++] = (uint8_t)(e >> 6);
+                            continue;
                         }
-                        if (outp > isize) { err = kInfOverflow; break; }
-                    }
-                    if (err) n = 0;
-                }
-                n = __shfl_sync(0xffffffffu, n, 0);
-                __syncwarp();
-                // ---- whole warp: resolve the queue -----------------------------------------------------------
-                uint32_t s = 0, p = 0;
-                if (lane < n) { s = S.q_sym[lane]; p = S.q_pos[lane]; }
-                bool is_match = (lane < n) && (s & kMatchFlag);
-                if (lane < n && !is_match) dst[p] = (uint8_t)s;
-                uint32_t mm = __ballot_sync(0xffffffffu, is_match);
-                __syncwarp();
-                while (mm) {
-                    int i = __ffs((int)mm) - 1; mm &= mm - 1;
-                    uint32_t ms = __shfl_sync(0xffffffffu, s, i), mp = __shfl_sync(0xffffffffu, p, i);
-                    uint32_t len = ms & 0x1ffu, dist = ((ms >> 16) & 0x7fffu) + 1u;
-                    const uint8_t* from = dst + mp - dist;
-                    if (dist >= len) {
-                        for (uint32_t k = lane; k < len; k += 32) dst[mp + k] = from[k];
                     } else {
-                        for (uint32_t k = lane; k < len; k += 32) dst[mp + k] = from[k % dist];
+                        br.drop((int)(e & 15u));
                     }
-                    __syncwarp();
+                    if (kind == kKindEob) { next_phase = bfinal ? kPhIdle : kPhHeader; break; }
+                    // length + distance
+                    uint32_t lbase, lextra; len_base_extra((e >> 6) & 0xffu, lbase, lextra);
+                    const uint32_t len = lbase + br.take((int)lextra);
+                    br.refill(S.ring);
+                    uint32_t d = S.dist_tab[br.peek(kDistBits)];
+                    uint32_t dsym;
+                    if (((d >> 4) & 3u) == kKindLong) {
+                        if (d & 15u) { err = kInfBadDistance; break; }
+                        dsym = slow_decode(br, kDistBits, S.dist_limit, S.dist_base, S.dist_sorted);
+                        if (dsym > 29u) { err = kInfBadDistance; break; }
+                        br.refill(S.ring);
+                    } else {
+                        br.drop((int)(d & 15u));
+                        dsym = d >> 6;
+                    }
+                    uint32_t dbase, dextra; dist_base_extra(dsym, dbase, dextra);
+                    const uint32_t dist = dbase + br.take((int)dextra);
+                    if (dist > outp) { err = kInfBadDistance; break; }
+                    if (outp + len > isize) { err = kInfOverflow; break; }
+                    S.q_sym[n] = ((dist - 1u) << 16) | len; S.q_pos[n] = (uint16_t)outp; n++;
+                    outp += len;
                 }
-            } else {
-                // ---- stored block: cooperative byte copy, then re-seed the bit reader -------------------------
-                uint32_t sp = __shfl_sync(0xffffffffu, stored_pos, 0), sl = __shfl_sync(0xffffffffu, stored_len, 0);
-                uint32_t op = __shfl_sync(0xffffffffu, outp, 0);
-                const uint8_t* sb = reinterpret_cast<const uint8_t*>(src_words) + sp;
-                for (uint32_t k = lane; k < sl; k += 32) dst[op + k] = sb[k];
-                uint32_t np = sp + sl;
-                loaded = np / 4;
-                if (lane == 0) {
-                    outp += sl;
-                    br.bb = 0; br.bc = 0; br.wpos = np / 4;
-                    state = bfinal ? 4 : 0;
-                }
-                __syncwarp();
-                // refill now so lane 0 can drop the sub-word offset
-                uint32_t consumed2 = np / 4;
-                while (loaded < total_words && loaded + 32 - consumed2 <= (uint32_t)kRingWords) {
-                    uint32_t w = loaded + lane;
-                    S.ring[w % kRingWords] = (w < total_words) ? __ldg(src_words + w) : 0u;
-                    loaded += 32;
-                }
-                __syncwarp();
-                if (lane == 0) { br.refill(S.ring); br.drop((int)(np & 3u) * 8); br.refill(S.ring); }
-                __syncwarp();
+                if (err) n = 0;
             }
+            n = __shfl_sync(gmask, n, leader_lane);
+            next_phase = __shfl_sync(gmask, next_phase, leader_lane);
+            const uint32_t round_start = __shfl_sync(gmask, round_start_outp, leader_lane);
+            __syncwarp(gmask);   // literal stores and the queue are visible to the octet
+            // ---- octet: copy the queued matches ---------------------------------------------------------------------
+            // Pass A: matches whose source lies entirely before this round's output are independent of everything
+            // decoded in this round; four of them are loaded before any is stored, so their L2 round trips overlap.
+            // Pass B: the others (short distances into this round's own output) go one by one in stream order.
+            uint32_t dep_mask = 0;
+            for (int i0 = 0; i0 < n; i0 += 4) {
+                uint32_t v[4]; uint32_t dstoff[4]; bool act[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int i = i0 + j;
+                    act[j] = false;
+                    if (i < n) {
+                        const uint32_t ms = S.q_sym[i], mp = S.q_pos[i];
+                        const uint32_t len = ms & 0x1ffu, dist = (ms >> 16) + 1u;
+                        const uint32_t span = len < dist ? len : dist;
+                        if (mp - dist + span <= round_start && len <= 8) {
+                            act[j] = gl < len; dstoff[j] = mp + gl;
+                            if (act[j]) v[j] = dst[mp - dist + (dist >= len ? gl : gl % dist)];
+                        } else dep_mask |= 1u << i;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (act[j]) dst[dstoff[j]] = (uint8_t)v[j];
+            }
+            __syncwarp(gmask);
+            while (dep_mask) {
+                const int i = __ffs((int)dep_mask) - 1; dep_mask &= dep_mask - 1;
+                const uint32_t ms = S.q_sym[i], mp = S.q_pos[i];
+                const uint32_t len = ms & 0x1ffu, dist = (ms >> 16) + 1u;
+                const uint8_t* from = dst + mp - dist;
+                if (dist >= len) {
+                    // up to 32 bytes per step: four loads in flight per lane
+                    for (uint32_t k0 = 0; k0 < len; k0 += 32) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) { const uint32_t k = k0 + 8 * j + gl; if (k < len) w[j] = from[k]; }
+#pragma unroll
+                        for (int j = 0; j < 4; j++) { const uint32_t k = k0 + 8 * j + gl; if (k < len) dst[mp + k] = (uint8_t)w[j]; }
+                    }
+                } else {
+                    for (uint32_t k = gl; k < len; k += 8) dst[mp + k] = from[k % dist];
+                }
+                __syncwarp(gmask);
+            }
+            if (next_phase == kPhIdle) {   // final block done
+                if (leader) { const uint32_t st = (outp != isize) ? (uint32_t)kInfShort : 0u; status_out[b] = st; if (st) atomicAdd(error_count, 1u); }
+            }
+            phase = next_phase;
+        } else if (phase == kPhHeader) {
+            // ---- DEFLATE block header ---------------------------------------------------------------------------------
+            int btype = 0;
+            if (leader) {
+                br.refill(S.ring);
+                bfinal = (int)br.take(1);
+                btype = (int)br.take(2);
+                if (btype == 0) {
+                    br.drop(br.bc & 7);
+                    br.refill(S.ring);
+                    const uint32_t len = br.take(16), nlen = br.take(16);
+                    if ((len ^ 0xffffu) != nlen) err = kInfBadStored;
+                    stored_len = len;
+                    stored_pos = br.wpos * 4u - (uint32_t)br.bc / 8u;   // byte index in the aligned stream
+                    if (outp + len > isize) err = kInfOverflow;
+                    if (stored_pos + len > lead + clen) err = kInfBadStored;
+                } else if (btype == 2) {
+                    hlit = (int)br.take(5) + 257; hdist = (int)br.take(5) + 1;
+                    const int hclen = (int)br.take(4) + 4;
+                    if (hlit > 286 || hdist > 30) err = kInfBadCodeLengths;
+                    for (int i = 0; i < 19; i++) lens[i] = 0;
+                    for (int i = 0; i < hclen; i++) { br.refill(S.ring); lens[c_cl_order[i]] = (uint8_t)br.take(3); }
+                    // code-length code table (7-bit root, 19 symbols) in the first 256 B of lit_tab
+                    uint16_t* cl_tab = S.lit_tab;
+                    uint32_t* cnt = S.q_sym;          // [8]
+                    uint32_t* next = S.q_sym + 8;     // [8]
+                    for (int i = 0; i < 8; i++) cnt[i] = 0;
+                    for (int i = 0; i < 19; i++) cnt[lens[i]]++;
+                    cnt[0] = 0;
+                    int left = 1;
+                    for (int l = 1; l < 8; l++) { left <<= 1; left -= (int)cnt[l]; }
+                    if (left < 0) err = kInfOversubscribed;
+                    uint32_t code = 0;
+                    for (int l = 1; l < 8; l++) { code = (code + cnt[l - 1]) << 1; next[l] = code; }
+                    for (int i = 0; i < 128; i++) cl_tab[i] = 0;
+                    for (int s = 0; s < 19; s++) {
+                        const uint32_t l = lens[s];
+                        if (!l) continue;
+                        const uint32_t c = next[l]++;
+                        const uint32_t rev = __brev(c) >> (32 - l);
+                        for (uint32_t k = rev; k < 128; k += (1u << l)) cl_tab[k] = (uint16_t)((s << 4) | l);
+                    }
+                    cl_idx = 0;
+                } else if (btype == 1) {
+                    hlit = 288; hdist = 30;
+                } else {
+                    err = kInfBadBlockType;
+                }
+            }
+            btype = __shfl_sync(gmask, btype, leader_lane);
+            __syncwarp(gmask);
+            if (btype == 0) phase = kPhStored;
+            else if (btype == 2) phase = kPhLengths;
+            else if (btype == 1) {
+                // fixed Huffman code lengths, then the same table builder
+                for (int i = gl; i < 288; i += 8) lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
+                for (int i = gl; i < 30; i += 8) lens[288 + i] = 5;
+                __syncwarp(gmask);
+                uint32_t e12 = 0;
+                if (leader) {
+                    e12 = table_pass1(lens, 288, S.lit_sorted, S.lit_limit, S.lit_base, S.q_sym, reinterpret_cast<uint32_t*>(S.q_pos));
+                    e12 |= table_pass1(lens + 288, 30, S.dist_sorted, S.dist_limit, S.dist_base, S.q_sym + 16, reinterpret_cast<uint32_t*>(S.q_pos));
+                    if (e12) err = e12;
+                }
+                __syncwarp(gmask);
+                table_pass2<false>(S.lit_tab, kLitBits, S.lit_sorted, S.lit_base, S.q_sym, gl);
+                table_pass2<true>(S.dist_tab, kDistBits, S.dist_sorted, S.dist_base, S.q_sym + 16, gl);
+                __syncwarp(gmask);
+                phase = kPhSymbols;
+            }
+        } else if (phase == kPhLengths) {
+            // ---- dynamic block: read up to 100 code lengths per round (<= 175 ring bytes) ---------------------------------
+            int done = 0;
+            if (leader) {
+                const uint16_t* cl_tab = S.lit_tab;
+                const int total = hlit + hdist;
+                int budget = 100;
+                while (cl_idx < total && budget-- > 0 && !err) {
+                    br.refill(S.ring);
+                    const uint32_t e = cl_tab[br.peek(7)];
+                    const uint32_t l = e & 15u, sym = e >> 4;
+                    if (!l) { err = kInfBadCodeLengths; break; }
+                    br.drop((int)l);
+                    if (sym < 16) { lens[cl_idx++] = (uint8_t)sym; continue; }
+                    uint32_t rep, val = 0;
+                    if (sym == 16) { if (cl_idx == 0) { err = kInfBadCodeLengths; break; } val = lens[cl_idx - 1]; rep = 3 + br.take(2); }
+                    else if (sym == 17) rep = 3 + br.take(3);
+                    else rep = 11 + br.take(7);
+                    if (cl_idx + (int)rep > total) { err = kInfBadCodeLengths; break; }
+                    while (rep--) lens[cl_idx++] = (uint8_t)val;
+                }
+                done = (cl_idx >= total) && !err;
+                if (done && lens[256] == 0) { err = kInfBadCodeLengths; done = 0; }
+            }
+            done = __shfl_sync(gmask, done, leader_lane);
+            __syncwarp(gmask);
+            if (done) {
+                uint32_t e12 = 0;
+                if (leader) {
+                    e12 = table_pass1(lens, hlit, S.lit_sorted, S.lit_limit, S.lit_base, S.q_sym, reinterpret_cast<uint32_t*>(S.q_pos));
+                    e12 |= table_pass1(lens + hlit, hdist, S.dist_sorted, S.dist_limit, S.dist_base, S.q_sym + 16, reinterpret_cast<uint32_t*>(S.q_pos));
+                    if (e12) err = e12;
+                }
+                __syncwarp(gmask);   // code lengths are dead from here on: pass 2 overwrites them with the lit/len table
+                table_pass2<false>(S.lit_tab, kLitBits, S.lit_sorted, S.lit_base, S.q_sym, gl);
+                table_pass2<true>(S.dist_tab, kDistBits, S.dist_sorted, S.dist_base, S.q_sym + 16, gl);
+                __syncwarp(gmask);
+                phase = kPhSymbols;
+            }
+        } else if (phase == kPhStored) {
+            // ---- stored block: octet byte copy, then re-seed the bit reader ------------------------------------------------
+            const uint32_t sp = __shfl_sync(gmask, stored_pos, leader_lane), sl = __shfl_sync(gmask, stored_len, leader_lane);
+            const uint32_t op = __shfl_sync(gmask, outp, leader_lane);
+            const int bf = __shfl_sync(gmask, bfinal, leader_lane);
+            const uint8_t* sb = reinterpret_cast<const uint8_t*>(src_words) + sp;
+            for (uint32_t k = gl; k < sl; k += 8) dst[op + k] = sb[k];
+            const uint32_t np = sp + sl;
+            loaded = np / 4;
+            if (leader) { outp += sl; br.bb = 0; br.bc = 0; br.wpos = np / 4; }
+            __syncwarp(gmask);
+            while (loaded < total_words && loaded + 8 - np / 4 <= (uint32_t)kRingWords) {
+                const uint32_t w = loaded + gl;
+                S.ring[w & (kRingWords - 1)] = (w < total_words) ? __ldg(src_words + w) : 0u;
+                loaded += 8;
+            }
+            __syncwarp(gmask);
+            if (leader) { br.refill(S.ring); br.drop((int)(np & 3u) * 8); br.refill(S.ring); }
+            if (bf) {
+                if (leader) { const uint32_t st = (outp != isize) ? (uint32_t)kInfShort : 0u; status_out[b] = st; if (st) atomicAdd(error_count, 1u); }
+                phase = kPhIdle;
+            } else phase = kPhHeader;
         }
-        if (lane == 0) {
-            if (!err && outp != isize) err = kInfShort;
-            status_out[b] = err;
-            if (err) atomicAdd(error_count, 1u);
-        }
-        __syncwarp();
     }
 }
+
+constexpr int kInflateThreads = kInflateWarps * 32;
+constexpr size_t kInflateSmem = sizeof(InflateOctetState) * kInflateWarps * kOctetsPerWarp;
+constexpr int kInflateOctetsPerCta = kInflateWarps * kOctetsPerWarp;
 
 }  // namespace msd

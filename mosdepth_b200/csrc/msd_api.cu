@@ -392,7 +392,7 @@ int msd_create(int device, msd_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cudaStreamCreate failed");
     }
-    cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(InflateWarpState) * kInflateWarps));
+    cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInflateSmem);
     cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     // default filters = mosdepth defaults (-F 1796, -Q 0, no length limits, default mode)
     ctx->fp.mapq = 0; ctx->fp.min_len = -1; ctx->fp.max_len = INT64_MAX; ctx->fp.eflag = 1796; ctx->fp.iflag = 0; ctx->fp.mode = MSD_MODE_DEFAULT; ctx->fp.n_rg = 0; ctx->fp.rg_names = nullptr;
@@ -628,8 +628,8 @@ int msd_run(msd_ctx* ctx) {
             MSD_CUDA_OK(cudaMemsetAsync(ctx->d_ticket, 0, 4, sc));
             MSD_CUDA_OK(cudaEventRecord(e0, sc));
             {
-                const int ctas = std::min<int>((nb + kInflateWarps - 1) / kInflateWarps, kSMs * 4);
-                bgzf_inflate_kernel<<<ctas, kInflateWarps * 32, sizeof(InflateWarpState) * kInflateWarps, sc>>>(
+                const int ctas = std::min<int>((nb + kInflateOctetsPerCta - 1) / kInflateOctetsPerCta, kSMs * kInflateCtasPerSm);
+                bgzf_inflate_kernel<<<ctas, kInflateThreads, kInflateSmem, sc>>>(
                     d_comp, infl_buf, ctx->d_desc[k], (int)nb, ctx->d_ticket, ctx->d_status, ctx->d_inflate_err);
                 ctx->info.n_launches++; ctx->info.n_inflate_launches++;
             }
@@ -922,8 +922,8 @@ int64_t msd_debug_inflate(msd_ctx* ctx, const void* bgzf_bytes, uint64_t n_bytes
     cudaMemcpyAsync(d_d, desc.data(), sizeof(BlockDesc) * desc.size(), cudaMemcpyHostToDevice, sc);
     cudaMemsetAsync(d_t, 0, 8, sc);
     const int nb = (int)desc.size();
-    const int ctas = std::min<int>((nb + kInflateWarps - 1) / kInflateWarps, kSMs * 4);
-    bgzf_inflate_kernel<<<ctas, kInflateWarps * 32, sizeof(InflateWarpState) * kInflateWarps, sc>>>(d_c, d_o, d_d, nb, d_t, d_s, d_t + 1);
+    const int ctas = std::min<int>((nb + kInflateOctetsPerCta - 1) / kInflateOctetsPerCta, kSMs * kInflateCtasPerSm);
+    bgzf_inflate_kernel<<<ctas, kInflateThreads, kInflateSmem, sc>>>(d_c, d_o, d_d, nb, d_t, d_s, d_t + 1);
     cudaError_t e = cudaGetLastError();
     uint32_t errs[2] = {0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(errs, d_t, 8, cudaMemcpyDeviceToHost, sc);
