@@ -289,7 +289,7 @@ int main(int argc, char** argv) {
     MSD(msd_open(ctx, bam_path.c_str(), nt, tl.data(), H.first_voff));
     MSD(msd_set_targets(ctx, want.data()));
     // merge adjacent contig spans so neighbouring contigs are read in one go
-    { std::vector<uint64_t> mb, me; for (size_t i = 0; i < sb.size(); i++) { if (!mb.empty() && sb[i] >= me.back() && (sb[i] >> 16) - (me.back() >> 16) <= (1u << 20)) me.back() = se[i];   // bytes in between are whole records of other contigs else { mb.push_back(sb[i]); me.push_back(se[i]); } }
+    { std::vector<uint64_t> mb, me; for (size_t i = 0; i < sb.size(); i++) { if (!mb.empty() && sb[i] >= me.back() && (sb[i] >> 16) - (me.back() >> 16) <= (1u << 20)) me.back() = se[i]; /* bytes in between are whole records of other contigs */ else { mb.push_back(sb[i]); me.push_back(se[i]); } }
       if (mb.empty()) { mb.push_back(1ull << 16); me.push_back(1ull << 16); }   // nothing indexed: read nothing
       MSD(msd_set_spans(ctx, (int)mb.size(), mb.data(), me.data())); }
     std::vector<const char*> rgs; std::vector<std::string> rg_store;
