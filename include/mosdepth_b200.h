@@ -51,7 +51,7 @@ typedef struct msd_depth_stat {
 typedef struct msd_run_info {
     double ms_total;           /* first launch .. last launch of msd_run on the compute stream */
     double ms_h2d;             /* summed host->device copies of compressed bytes (0 when staged) */
-    double ms_inflate;         /* summed bgzf_inflate kernel time */
+    double ms_inflate;         /* summed bgzf_inflate kernel time (launches overlap: see ms_inflate_span) */
     double ms_frame;           /* summed framing kernels */
     double ms_records;         /* summed filter / delta kernels (+ mate join in default mode) */
     double ms_scan;            /* summed prefix-sum + contig stats kernels */
@@ -64,6 +64,7 @@ typedef struct msd_run_info {
     uint64_t n_depth_cells;    /* sum of (tlen+1) over contigs that had records */
     uint32_t n_launches;       /* kernels launched by the library during the run */
     uint32_t n_inflate_launches;
+    double ms_inflate_span;    /* first inflate launch start .. last inflate launch end (launches of consecutive chunks overlap) */
 } msd_run_info;
 
 typedef struct msd_ctx msd_ctx;

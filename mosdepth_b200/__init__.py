@@ -36,7 +36,7 @@ class RunInfo(C.Structure):
                 ("ms_records", C.c_double), ("ms_scan", C.c_double), ("ms_zero", C.c_double),
                 ("bytes_compressed", C.c_uint64), ("bytes_inflated", C.c_uint64), ("n_blocks", C.c_uint64),
                 ("n_records", C.c_uint64), ("n_events", C.c_uint64), ("n_depth_cells", C.c_uint64),
-                ("n_launches", C.c_uint32), ("n_inflate_launches", C.c_uint32)]
+                ("n_launches", C.c_uint32), ("n_inflate_launches", C.c_uint32), ("ms_inflate_span", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

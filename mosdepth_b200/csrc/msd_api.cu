@@ -50,7 +50,7 @@ struct ContigResult {
 struct msd_ctx {
     int device = 0;
     char err[512] = "";
-    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_inflate[2] = {nullptr, nullptr};
     // input
     const uint8_t* bytes = nullptr; uint64_t n_bytes = 0; bool mapped = false; bool src_pinned = false;
     int n_targets = 0; std::vector<uint32_t> tlen; uint64_t first_voff = 0;
@@ -72,7 +72,7 @@ struct msd_ctx {
     uint32_t *d_status = nullptr, *d_ticket = nullptr, *d_inflate_err = nullptr;
     ChunkState* d_cs = nullptr; RunCounters* d_rc = nullptr;
     StageSet stage[2];
-    cudaEvent_t comp_free[2] = {nullptr, nullptr}, h2d_done[2] = {nullptr, nullptr};
+    cudaEvent_t comp_free[2] = {nullptr, nullptr}, h2d_done[2] = {nullptr, nullptr}, infl_done[2] = {nullptr, nullptr}, infl_free[2] = {nullptr, nullptr};
     // mate join (default mode only)
     MateChunk mc{}; MateTable mt{}; LiveList live[2]{}; bool mate_ready = false; uint32_t mate_slots = 0;
     // scan + queries
@@ -177,6 +177,8 @@ int ensure_chunk_buffers(msd_ctx* ctx) {
         MSD_CUDA_OK(cudaEventCreateWithFlags(&ctx->stage[k].free_ev, cudaEventDisableTiming));
         MSD_CUDA_OK(cudaEventCreateWithFlags(&ctx->comp_free[k], cudaEventDisableTiming));
         MSD_CUDA_OK(cudaEventCreateWithFlags(&ctx->h2d_done[k], cudaEventDisableTiming));
+        MSD_CUDA_OK(cudaEventCreateWithFlags(&ctx->infl_done[k], cudaEventDisableTiming));
+        MSD_CUDA_OK(cudaEventCreateWithFlags(&ctx->infl_free[k], cudaEventDisableTiming));
     }
     const uint32_t nb = ctx->max_blocks + 2;
     if ((rc = dev_alloc(ctx, &ctx->d_bstart, nb + 1))) return rc;
@@ -186,7 +188,7 @@ int ensure_chunk_buffers(msd_ctx* ctx) {
     if ((rc = dev_alloc(ctx, &ctx->d_cnt, nb))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_recbase, nb))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_recoff, ctx->rec_cap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_status, ctx->max_blocks))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_status, 2ull * ctx->max_blocks))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_ticket, 4))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_inflate_err, 4))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_cs, 1))) return rc;
@@ -392,6 +394,7 @@ int msd_create(int device, msd_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cudaStreamCreate failed");
     }
+    for (int k = 0; k < 2; k++) if (cudaStreamCreateWithFlags(&ctx->s_inflate[k], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cudaStreamCreate failed"); }
     cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInflateSmem);
     cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     // default filters = mosdepth defaults (-F 1796, -Q 0, no length limits, default mode)
@@ -414,6 +417,9 @@ void msd_destroy(msd_ctx* ctx) {
         if (ctx->stage[k].free_ev) cudaEventDestroy(ctx->stage[k].free_ev);
         if (ctx->comp_free[k]) cudaEventDestroy(ctx->comp_free[k]);
         if (ctx->h2d_done[k]) cudaEventDestroy(ctx->h2d_done[k]);
+        if (ctx->infl_done[k]) cudaEventDestroy(ctx->infl_done[k]);
+        if (ctx->infl_free[k]) cudaEventDestroy(ctx->infl_free[k]);
+        if (ctx->s_inflate[k]) cudaStreamDestroy(ctx->s_inflate[k]);
         dev_free(&ctx->live[k].e); dev_free(&ctx->live[k].arena); dev_free(&ctx->live[k].n); dev_free(&ctx->live[k].arena_used);
     }
     dev_free(&ctx->d_bstart); dev_free(&ctx->d_land); dev_free(&ctx->d_count); dev_free(&ctx->d_first); dev_free(&ctx->d_cnt);
@@ -449,6 +455,8 @@ int msd_open_mem(msd_ctx* ctx, const void* bam_bytes, uint64_t n_bytes, int n_ta
         if (ctx->stage[k].free_ev) { cudaEventDestroy(ctx->stage[k].free_ev); ctx->stage[k].free_ev = nullptr; }
         if (ctx->comp_free[k]) { cudaEventDestroy(ctx->comp_free[k]); ctx->comp_free[k] = nullptr; }
         if (ctx->h2d_done[k]) { cudaEventDestroy(ctx->h2d_done[k]); ctx->h2d_done[k] = nullptr; }
+        if (ctx->infl_done[k]) { cudaEventDestroy(ctx->infl_done[k]); ctx->infl_done[k] = nullptr; }
+        if (ctx->infl_free[k]) { cudaEventDestroy(ctx->infl_free[k]); ctx->infl_free[k] = nullptr; }
         ctx->stage[k].used = false;
         dev_free(&ctx->live[k].e); dev_free(&ctx->live[k].arena); dev_free(&ctx->live[k].n); dev_free(&ctx->live[k].arena_used);
     }
@@ -555,6 +563,12 @@ int msd_run(msd_ctx* ctx) {
     int live_cur = 0;
     if (default_mode) for (int k = 0; k < 2; k++) { MSD_CUDA_OK(cudaMemsetAsync(ctx->live[k].n, 0, 4, sc)); MSD_CUDA_OK(cudaMemsetAsync(ctx->live[k].arena_used, 0, 4, sc)); }
 
+    {   // the inflate streams must not run ahead of the per-run resets above
+        cudaEvent_t ev_init = next_event(ctx);
+        MSD_CUDA_OK(cudaEventRecord(ev_init, sc));
+        for (int k = 0; k < 2; k++) MSD_CUDA_OK(cudaStreamWaitEvent(ctx->s_inflate[k], ev_init, 0));
+        MSD_CUDA_OK(cudaStreamWaitEvent(sx, ev_init, 0));
+    }
     ContigTable ct{ctx->d_depth_off, ctx->d_tlen};
     const uint32_t base = ctx->carry_cap;
     // spans are taken as given (the caller merges neighbouring contigs when the bytes between them are genuine
@@ -563,6 +577,7 @@ int msd_run(msd_ctx* ctx) {
     if (spans.empty()) spans.push_back({ctx->first_voff, 0});
     std::sort(spans.begin(), spans.end(), [](const Span& a, const Span& b) { return a.beg < b.beg; });
     uint64_t chunk_idx = 0;
+    const uint32_t ramp0 = (uint32_t)env_u64("MSD_RAMP0_BLOCKS", 6000), ramp1 = (uint32_t)env_u64("MSD_RAMP1_BLOCKS", 20000);
     const uint8_t* F = ctx->bytes; const uint64_t N = ctx->n_bytes;
 
     for (const Span& sp : spans) {
@@ -577,7 +592,11 @@ int msd_run(msd_ctx* ctx) {
             StageSet& st = ctx->stage[k];
             if (st.used) MSD_CUDA_OK(cudaEventSynchronize(st.free_ev));
             uint32_t nb = 0; uint64_t comp_bytes = 0, infl = 0; const uint64_t chunk_src = pos; uint32_t total = 0; bool truncated_last = false;
-            while (nb < ctx->max_blocks) {
+            // when the compressed bytes still have to cross PCIe, the first chunks are small so that the pipeline
+            // (copy k+1 | inflate k) starts after a few milliseconds instead of after a full-size copy
+            const bool will_copy = !(ctx->d_staged && pos >= ctx->staged_beg && pos < ctx->staged_end);
+            const uint32_t blk_limit = !will_copy ? ctx->max_blocks : std::min<uint32_t>(ctx->max_blocks, chunk_idx == 0 ? ramp0 : chunk_idx == 1 ? ramp1 : ctx->max_blocks);
+            while (nb < blk_limit) {
                 if (pos >= N || pos > end_c || (pos == end_c && end_u == 0)) { span_done = true; break; }
                 uint32_t xlen = 0, isize = 0;
                 uint32_t blen = bgzf_header(F, N, pos, &xlen, &isize);
@@ -599,42 +618,55 @@ int msd_run(msd_ctx* ctx) {
             st.h_rel[nb] = (uint32_t)infl;
             st.used = true;
             // ---- compressed bytes -> device -------------------------------------------------------------------
+            cudaStream_t si = ctx->s_inflate[k];   // inflate launches alternate between two streams so that chunk k+1 fills
+                                                   // the SMs while the last blocks of chunk k drain (a block takes ~10 ms)
             const uint8_t* d_comp;
             if (ctx->d_staged && chunk_src >= ctx->staged_beg && chunk_src + comp_bytes <= ctx->staged_end) {
                 d_comp = ctx->d_staged + (chunk_src - ctx->staged_beg);
                 // descriptor src offsets assume a 4-byte aligned base: fold the misalignment into src
                 const uint32_t mis = (uint32_t)((uintptr_t)d_comp & 3u);
                 if (mis) { d_comp -= mis; for (uint32_t i = 0; i < nb; i++) st.h_desc[i].src += mis; }
+                MSD_CUDA_OK(cudaStreamWaitEvent(si, ctx->comp_free[k], 0));
+                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_desc[k], st.h_desc, sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, si));
+                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_rel[k], st.h_rel, sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, si));
+                MSD_CUDA_OK(cudaEventRecord(st.free_ev, si));
             } else {
                 if ((rc = ensure_bounce(ctx))) return rc;
+                // everything this chunk needs goes through the copy stream in one batch, small descriptor copies first:
+                // a copy engine is FIFO, so a descriptor copy queued behind the NEXT chunk's bulk copy would hold this
+                // chunk's kernels back until that bulk copy ends
                 MSD_CUDA_OK(cudaStreamWaitEvent(sx, ctx->comp_free[k], 0));
+                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_desc[k], st.h_desc, sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, sx));
+                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_rel[k], st.h_rel, sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, sx));
                 cudaEvent_t h0 = next_event(ctx), h1 = next_event(ctx);
                 MSD_CUDA_OK(cudaEventRecord(h0, sx));
                 const uint8_t* srcp = F + chunk_src;
                 if (!ctx->src_pinned) { memcpy(st.h_bounce, srcp, comp_bytes); srcp = st.h_bounce; }
                 MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_comp[k], srcp, comp_bytes, cudaMemcpyHostToDevice, sx));
                 MSD_CUDA_OK(cudaEventRecord(h1, sx));
+                MSD_CUDA_OK(cudaEventRecord(st.free_ev, sx));       // h_desc, h_rel and h_bounce of this set are free again
                 MSD_CUDA_OK(cudaEventRecord(ctx->h2d_done[k], sx));
-                MSD_CUDA_OK(cudaStreamWaitEvent(sc, ctx->h2d_done[k], 0));
+                MSD_CUDA_OK(cudaStreamWaitEvent(si, ctx->h2d_done[k], 0));
                 times.h2d.push_back({h0, h1});
                 d_comp = ctx->d_comp[k];
             }
-            MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_desc[k], st.h_desc, sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, sc));
-            MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_rel[k], st.h_rel, sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, sc));
-            MSD_CUDA_OK(cudaEventRecord(st.free_ev, sc));
             // ---- K1 inflate ---------------------------------------------------------------------------------
             uint8_t* infl_buf = ctx->d_infl[k];
             cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
-            MSD_CUDA_OK(cudaMemsetAsync(ctx->d_ticket, 0, 4, sc));
-            MSD_CUDA_OK(cudaEventRecord(e0, sc));
+            cudaEvent_t f0 = next_event(ctx);
+            MSD_CUDA_OK(cudaStreamWaitEvent(si, ctx->infl_free[k], 0));      // consumers of the previous contents of d_infl[k] are done
+            MSD_CUDA_OK(cudaMemsetAsync(ctx->d_ticket + k, 0, 4, si));
+            MSD_CUDA_OK(cudaEventRecord(e0, si));
             {
                 const int ctas = std::min<int>((nb + kInflateOctetsPerCta - 1) / kInflateOctetsPerCta, kSMs * kInflateCtasPerSm);
-                bgzf_inflate_kernel<<<ctas, kInflateThreads, kInflateSmem, sc>>>(
-                    d_comp, infl_buf, ctx->d_desc[k], (int)nb, ctx->d_ticket, ctx->d_status, ctx->d_inflate_err);
+                bgzf_inflate_kernel<<<ctas, kInflateThreads, kInflateSmem, si>>>(
+                    d_comp, infl_buf, ctx->d_desc[k], (int)nb, ctx->d_ticket + k, ctx->d_status + (size_t)k * ctx->max_blocks, ctx->d_inflate_err);
                 ctx->info.n_launches++; ctx->info.n_inflate_launches++;
             }
-            MSD_CUDA_OK(cudaEventRecord(e1, sc));
-            MSD_CUDA_OK(cudaEventRecord(ctx->comp_free[k], sc));
+            MSD_CUDA_OK(cudaEventRecord(e1, si));
+            MSD_CUDA_OK(cudaEventRecord(ctx->infl_done[k], si));
+            MSD_CUDA_OK(cudaStreamWaitEvent(sc, ctx->infl_done[k], 0));
+            MSD_CUDA_OK(cudaEventRecord(f0, sc));
             // ---- K2 framing ---------------------------------------------------------------------------------
             const int nblk = (int)nb + 1;   // + carry pseudo-block
             frame_setup_kernel<<<(nb + 255) / 256, 256, 0, sc>>>(ctx->d_cs, ctx->d_rel[k], (int)nb, base, first_of_span ? first_uoff : 0u, total, first_of_span ? 1 : 0, ctx->d_bstart);
@@ -666,8 +698,10 @@ int msd_run(msd_ctx* ctx) {
             // unfinished tail -> front of the other inflated buffer
             carry_copy_kernel<<<64, 256, 0, sc>>>(infl_buf, ctx->d_infl[k ^ 1], ctx->d_cs, base, ctx->carry_cap, &ctx->d_rc->error);
             ctx->info.n_launches++;
+            MSD_CUDA_OK(cudaEventRecord(ctx->comp_free[k], sc));   // d_comp[k], d_desc[k], d_rel[k] may be overwritten from here on
+            MSD_CUDA_OK(cudaEventRecord(ctx->infl_free[k], sc));   // ... and so may d_infl[k]
             MSD_CUDA_OK(cudaGetLastError());
-            times.inflate.push_back({e0, e1}); times.frame.push_back({e1, e2}); times.records.push_back({e2, e3});
+            times.inflate.push_back({e0, e1}); times.frame.push_back({f0, e2}); times.records.push_back({e2, e3});
             ctx->info.bytes_compressed += comp_bytes; ctx->info.bytes_inflated += infl; ctx->info.n_blocks += nb;
             first_of_span = false;
             chunk_idx++;
@@ -721,6 +755,14 @@ int msd_run(msd_ctx* ctx) {
     cudaEventElapsedTime(&ms, ev_begin, ev_end); ctx->info.ms_total = ms;
     cudaEventElapsedTime(&ms, ev_begin, ev_zero_end); ctx->info.ms_zero = ms;
     cudaEventElapsedTime(&ms, s0, s1); ctx->info.ms_scan = ms;
+    if (getenv("MSD_TRACE")) {
+        auto rel = [&](cudaEvent_t e) { float m = 0; cudaEventElapsedTime(&m, ev_begin, e); return m; };
+        for (size_t i = 0; i < times.inflate.size(); i++)
+            fprintf(stderr, "[msd trace] chunk %zu: h2d %.2f..%.2f  inflate %.2f..%.2f  frame ..%.2f  records ..%.2f\n", i,
+                    i < times.h2d.size() ? rel(times.h2d[i].first) : -1.f, i < times.h2d.size() ? rel(times.h2d[i].second) : -1.f,
+                    rel(times.inflate[i].first), rel(times.inflate[i].second), rel(times.frame[i].second), rel(times.records[i].second));
+    }
+    if (!times.inflate.empty()) { float sp = 0; cudaEventElapsedTime(&sp, times.inflate.front().first, times.inflate.back().second); ctx->info.ms_inflate_span = sp; }
     ctx->info.ms_h2d = sum_ms(times.h2d); ctx->info.ms_inflate = sum_ms(times.inflate); ctx->info.ms_frame = sum_ms(times.frame); ctx->info.ms_records = sum_ms(times.records);
     ctx->ran = true;
     ctx->launches += ctx->info.n_launches;
