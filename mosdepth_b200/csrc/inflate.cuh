@@ -23,8 +23,8 @@
 
 namespace msd {
 
-constexpr int kLitBits = 9;
-constexpr int kDistBits = 7;
+constexpr int kLitBits = 8;
+constexpr int kDistBits = 6;
 constexpr int kInflateWarps = 2;         // warps per CTA
 constexpr int kOctetsPerWarp = 4;
 constexpr int kRingWords = 64;           // compressed-word ring per octet (power of two)
@@ -52,8 +52,8 @@ struct __align__(16) InflateOctetState {
     uint16_t lit_limit[16], lit_base[16];    // 64 B  canonical decode of codes longer than the root: left-aligned limits, index bases
     uint16_t dist_limit[16], dist_base[16];  // 64 B
 };
-static_assert(sizeof(InflateOctetState) == 2496, "8 octets x 2496 B + 1 KB reserve per CTA -> 11 CTAs (88 decoders) per SM");
-constexpr int kInflateCtasPerSm = 11;
+static_assert(sizeof(InflateOctetState) == 1856, "8 octets x 1856 B + 1 KB reserve per CTA -> 14 CTAs (112 decoders) per SM");
+constexpr int kInflateCtasPerSm = 14;
 
 __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
@@ -259,6 +259,9 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ out,
                     const uint32_t dist = dbase + br.take((int)dextra);
                     if (dist > outp) { err = kInfBadDistance; break; }
                     if (outp + len > isize) { err = kInfOverflow; break; }
+                    // 13k blocks are in flight per GPU, so their 64 KB windows (850 MB) overflow the 126 MB L2: start pulling
+                    // the match source towards L2 now; the copy runs after the rest of the round has been decoded
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(dst + outp - dist));
                     S.q_sym[n] = ((dist - 1u) << 16) | len; S.q_pos[n] = (uint16_t)outp; n++;
                     outp += len;
                 }
