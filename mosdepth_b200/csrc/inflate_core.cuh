@@ -1,0 +1,92 @@
+// inflate_core.cuh -- arithmetic shared by the two inflate kernels (K1a huffman_decode, K1b lz77_resolve):
+// table-entry encodings, canonical-Huffman bookkeeping, the per-lane region layout and the token format.
+// Everything here is MSD_HD so that a host program (tools/inflate_model.cpp) can replay the same formulas against
+// zlib without a GPU; the product path is the CUDA kernels in inflate.cuh only.
+//
+// Replaces htslib's BGZF inflate [ext] behind `open(bam, threads=)`, mosdepth.nim:888,968.  RFC 1951 throughout.
+#pragma once
+#include "common.cuh"
+
+namespace msd {
+namespace inf {
+
+constexpr int kLitRootBits = 8;      // lit/len root table: 256 entries
+constexpr int kDistRootBits = 7;     // distance root table: 128 entries
+
+// ---- per-decoder (per-lane) shared-memory region, 344 32-bit words; word j of lane L lives at smem32[j * 32 + L]
+//      so that a warp-wide access to "the same field of every lane's table" never has a bank conflict ----------------
+constexpr int kLitRootHw = 0;        // halfword index of the lit/len root table (256 halfwords)
+constexpr int kDistRootHw = 256;     // distance root table (128 halfwords)
+constexpr int kLongLitHw = 384;      // lit/len symbols with codes longer than the root, canonical order (<= 286 halfwords)
+constexpr int kLongDistByte = 1340;  // distance symbols with codes longer than the root, canonical order (<= 30 bytes)
+constexpr int kLaneWords = 344;      // 1376 B
+// while a dynamic header is being read the (dead) tables hold:
+constexpr int kClTabByte = 0;        // 128-entry code-length-code table, one byte per entry: sym << 3 | len
+constexpr int kLensByte = 128;       // hlit + hdist code lengths, one byte each (<= 316)
+
+// ---- table entries (16 bit) ----------------------------------------------------------------------------------------
+// lit/len: [3:0] code length (0 in the root = "longer than the root, or no such code"; 0 in the long list)
+//          [7:4] 0..5 = length code with that many extra bits, 6 = end of block, 7 = symbol that must not occur,
+//                8 = literal
+//          [15:8] literal byte, or length base - 3
+// distance: [3:0] code length, [7:4] extra bits 0..13 (15 = symbol that must not occur), [9:8] mantissa m:
+//          distance = 1 + (m << extra) + extra bits
+constexpr uint32_t kNibEob = 6, kNibBad = 7, kNibLit = 8, kDistNibBad = 15;
+
+MSD_HD uint32_t lit_entry_of(uint32_t sym) {
+    if (sym < 256) return (sym << 8) | (kNibLit << 4);
+    if (sym == 256) return kNibEob << 4;
+    if (sym > 285) return kNibBad << 4;
+    const uint32_t idx = sym - 257;
+    uint32_t base, extra;
+    if (idx < 8) { base = 3 + idx; extra = 0; }
+    else if (idx == 28) { base = 258; extra = 0; }
+    else { extra = (idx - 4) >> 2; base = 3 + ((4 + (idx & 3)) << extra); }
+    return ((base - 3) << 8) | (extra << 4);
+}
+MSD_HD uint32_t dist_entry_of(uint32_t sym) {
+    if (sym > 29) return kDistNibBad << 4;
+    if (sym < 4) return sym << 8;
+    const uint32_t extra = (sym >> 1) - 1;
+    return ((2 + (sym & 1)) << 8) | (extra << 4);
+}
+
+// ---- canonical code bookkeeping for one alphabet, from the per-length symbol counts --------------------------------
+// first[l]: first code of length l; offs[l]: number of coded symbols shorter than l (index of the first length-l symbol
+// in canonical order); end[l] = first[l] + cnt[l].  A code is over-subscribed iff end[l] > 2^l for some l.
+struct Canon {
+    uint32_t first[16], offs[16], end[16];
+    bool oversubscribed;
+};
+MSD_HD void canon_from_counts(const uint32_t* cnt /*[16], cnt[0] ignored*/, Canon& c) {
+    uint32_t code = 0, idx = 0;
+    c.oversubscribed = false;
+    c.first[0] = c.offs[0] = c.end[0] = 0;
+    for (int l = 1; l < 16; l++) {
+        code <<= 1;
+        c.first[l] = code; c.offs[l] = idx;
+        code += cnt[l]; idx += cnt[l];
+        c.end[l] = code;
+        if (code > (1u << l)) c.oversubscribed = true;
+    }
+}
+// limit of length l left-aligned to `bits` bits (l <= bits): a `bits`-bit MSB-first window c starts with a code of
+// length <= l iff c < limit
+MSD_HD uint32_t canon_limit(const Canon& c, int l, int bits) { return c.end[l] << (bits - l); }
+// index base (mod 2^16) into the long list for codes of length l > root: idx = (base + code) & 0xffff
+MSD_HD uint32_t canon_long_base(const Canon& c, int l, int root) { return (c.offs[l] - c.offs[root + 1] - c.first[l]) & 0xffffu; }
+
+// ---- match tokens handed from K1a to K1b (32 bit) ---------------------------------------------------------------
+// [31:23] literals since the previous token (0..510), [22:8] distance - 1, [7:0] length - 3
+// [31:23] == 511: no match, [22:0] literals to skip (emitted in front of a match whose literal run is > 510)
+constexpr uint32_t kTokSkip = 511;
+constexpr int kTokenCap = 22016;     // per BGZF block: 65536 / 3 matches + 65536 / 511 skips, rounded up
+MSD_HD uint32_t make_token(uint32_t lit_run, uint32_t len, uint32_t dist) { return (lit_run << 23) | ((dist - 1u) << 8) | (len - 3u); }
+
+enum Status : uint32_t {
+    kOk = 0, kBadBlockType = 1, kBadStored = 2, kBadCodeLengths = 3, kBadSymbol = 4, kBadDistance = 5,
+    kOverflow = 6, kShort = 7, kOversubscribed = 8, kTruncated = 9
+};
+
+}  // namespace inf
+}  // namespace msd

@@ -70,6 +70,7 @@ struct msd_ctx {
     BlockDesc* d_desc[2] = {nullptr, nullptr}; uint32_t* d_rel[2] = {nullptr, nullptr};
     uint32_t *d_bstart = nullptr, *d_land = nullptr, *d_count = nullptr, *d_first = nullptr, *d_cnt = nullptr, *d_recbase = nullptr, *d_recoff = nullptr;
     uint32_t *d_status = nullptr, *d_ticket = nullptr, *d_inflate_err = nullptr;
+    uint32_t* d_tokens[2] = {nullptr, nullptr}; uint32_t* d_ntok[2] = {nullptr, nullptr};   // match tokens between K1a and K1b
     ChunkState* d_cs = nullptr; RunCounters* d_rc = nullptr;
     StageSet stage[2];
     cudaEvent_t comp_free[2] = {nullptr, nullptr}, h2d_done[2] = {nullptr, nullptr}, infl_done[2] = {nullptr, nullptr}, infl_free[2] = {nullptr, nullptr};
@@ -171,6 +172,8 @@ int ensure_chunk_buffers(msd_ctx* ctx) {
         if ((rc = dev_alloc(ctx, &ctx->d_infl[k], infl_bytes))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_desc[k], ctx->max_blocks))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_rel[k], ctx->max_blocks + 1))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_tokens[k], (uint64_t)ctx->max_blocks * kTokenCap))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_ntok[k], ctx->max_blocks))) return rc;
         MSD_CUDA_OK(cudaMemset(ctx->d_infl[k], 0, infl_bytes));
         MSD_CUDA_OK(cudaMallocHost((void**)&ctx->stage[k].h_desc, sizeof(BlockDesc) * ctx->max_blocks));
         MSD_CUDA_OK(cudaMallocHost((void**)&ctx->stage[k].h_rel, sizeof(uint32_t) * (ctx->max_blocks + 1)));
@@ -189,7 +192,7 @@ int ensure_chunk_buffers(msd_ctx* ctx) {
     if ((rc = dev_alloc(ctx, &ctx->d_recbase, nb))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_recoff, ctx->rec_cap))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_status, 2ull * ctx->max_blocks))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_ticket, 4))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_ticket, 8))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_inflate_err, 4))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_cs, 1))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_rc, 1))) return rc;
@@ -395,8 +398,8 @@ int msd_create(int device, msd_ctx** out) {
         delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cudaStreamCreate failed");
     }
     for (int k = 0; k < 2; k++) if (cudaStreamCreateWithFlags(&ctx->s_inflate[k], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cudaStreamCreate failed"); }
-    cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInflateSmem);
-    cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(huffman_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecSmem);
+    cudaFuncSetAttribute(huffman_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     // default filters = mosdepth defaults (-F 1796, -Q 0, no length limits, default mode)
     ctx->fp.mapq = 0; ctx->fp.min_len = -1; ctx->fp.max_len = INT64_MAX; ctx->fp.eflag = 1796; ctx->fp.iflag = 0; ctx->fp.mode = MSD_MODE_DEFAULT; ctx->fp.n_rg = 0; ctx->fp.rg_names = nullptr;
     *out = ctx;
@@ -410,7 +413,7 @@ void msd_destroy(msd_ctx* ctx) {
     release_input(ctx);
     dev_free(&ctx->d_rg); dev_free(&ctx->d_arena); dev_free(&ctx->d_depth_off); dev_free(&ctx->d_tlen); dev_free(&ctx->d_nprefilter);
     for (int k = 0; k < 2; k++) {
-        dev_free(&ctx->d_comp[k]); dev_free(&ctx->d_infl[k]); dev_free(&ctx->d_desc[k]); dev_free(&ctx->d_rel[k]);
+        dev_free(&ctx->d_comp[k]); dev_free(&ctx->d_infl[k]); dev_free(&ctx->d_desc[k]); dev_free(&ctx->d_rel[k]); dev_free(&ctx->d_tokens[k]); dev_free(&ctx->d_ntok[k]);
         if (ctx->stage[k].h_desc) cudaFreeHost(ctx->stage[k].h_desc);
         if (ctx->stage[k].h_rel) cudaFreeHost(ctx->stage[k].h_rel);
         if (ctx->stage[k].h_bounce) cudaFreeHost(ctx->stage[k].h_bounce);
@@ -655,14 +658,11 @@ int msd_run(msd_ctx* ctx) {
             cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
             cudaEvent_t f0 = next_event(ctx);
             MSD_CUDA_OK(cudaStreamWaitEvent(si, ctx->infl_free[k], 0));      // consumers of the previous contents of d_infl[k] are done
-            MSD_CUDA_OK(cudaMemsetAsync(ctx->d_ticket + k, 0, 4, si));
+            MSD_CUDA_OK(cudaMemsetAsync(ctx->d_ticket + 2 * k, 0, 8, si));
             MSD_CUDA_OK(cudaEventRecord(e0, si));
-            {
-                const int ctas = std::min<int>((nb + kInflateOctetsPerCta - 1) / kInflateOctetsPerCta, kSMs * kInflateCtasPerSm);
-                bgzf_inflate_kernel<<<ctas, kInflateThreads, kInflateSmem, si>>>(
-                    d_comp, infl_buf, ctx->d_desc[k], (int)nb, ctx->d_ticket + k, ctx->d_status + (size_t)k * ctx->max_blocks, ctx->d_inflate_err);
-                ctx->info.n_launches++; ctx->info.n_inflate_launches++;
-            }
+            launch_inflate(si, d_comp, infl_buf, ctx->d_desc[k], (int)nb, ctx->d_ticket + 2 * k, ctx->d_tokens[k], ctx->d_ntok[k],
+                           ctx->d_status + (size_t)k * ctx->max_blocks, ctx->d_inflate_err);
+            ctx->info.n_launches += 2; ctx->info.n_inflate_launches++;
             MSD_CUDA_OK(cudaEventRecord(e1, si));
             MSD_CUDA_OK(cudaEventRecord(ctx->infl_done[k], si));
             MSD_CUDA_OK(cudaStreamWaitEvent(sc, ctx->infl_done[k], 0));
@@ -955,25 +955,25 @@ int64_t msd_debug_inflate(msd_ctx* ctx, const void* bgzf_bytes, uint64_t n_bytes
     }
     if (infl > out_cap) return ctx_fail(ctx, MSD_EINVAL, "msd_debug_inflate: need %llu bytes", (unsigned long long)infl);
     if (desc.empty()) return 0;
-    uint8_t *d_c = nullptr, *d_o = nullptr; BlockDesc* d_d = nullptr; uint32_t *d_s = nullptr, *d_t = nullptr;
+    uint8_t *d_c = nullptr, *d_o = nullptr; BlockDesc* d_d = nullptr; uint32_t *d_s = nullptr, *d_t = nullptr, *d_tok = nullptr, *d_nt = nullptr;
     int rc;
     if ((rc = dev_alloc(ctx, &d_c, n_bytes + 256)) || (rc = dev_alloc(ctx, &d_o, infl + 256)) || (rc = dev_alloc(ctx, &d_d, desc.size())) ||
-        (rc = dev_alloc(ctx, &d_s, desc.size())) || (rc = dev_alloc(ctx, &d_t, 2))) { dev_free(&d_c); dev_free(&d_o); dev_free(&d_d); dev_free(&d_s); dev_free(&d_t); return rc; }
+        (rc = dev_alloc(ctx, &d_s, desc.size())) || (rc = dev_alloc(ctx, &d_t, 4)) || (rc = dev_alloc(ctx, &d_tok, desc.size() * (uint64_t)kTokenCap)) ||
+        (rc = dev_alloc(ctx, &d_nt, desc.size()))) { dev_free(&d_c); dev_free(&d_o); dev_free(&d_d); dev_free(&d_s); dev_free(&d_t); dev_free(&d_tok); dev_free(&d_nt); return rc; }
     cudaStream_t sc = ctx->s_compute;
     cudaMemcpyAsync(d_c, F, n_bytes, cudaMemcpyHostToDevice, sc);
     cudaMemcpyAsync(d_d, desc.data(), sizeof(BlockDesc) * desc.size(), cudaMemcpyHostToDevice, sc);
-    cudaMemsetAsync(d_t, 0, 8, sc);
+    cudaMemsetAsync(d_t, 0, 16, sc);
     const int nb = (int)desc.size();
-    const int ctas = std::min<int>((nb + kInflateOctetsPerCta - 1) / kInflateOctetsPerCta, kSMs * kInflateCtasPerSm);
-    bgzf_inflate_kernel<<<ctas, kInflateThreads, kInflateSmem, sc>>>(d_c, d_o, d_d, nb, d_t, d_s, d_t + 1);
+    launch_inflate(sc, d_c, d_o, d_d, nb, d_t, d_tok, d_nt, d_s, d_t + 2);   // tickets: d_t[0], d_t[1]; error count: d_t[2]
     cudaError_t e = cudaGetLastError();
     uint32_t errs[2] = {0, 0};
-    if (e == cudaSuccess) e = cudaMemcpyAsync(errs, d_t, 8, cudaMemcpyDeviceToHost, sc);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(errs, d_t + 1, 8, cudaMemcpyDeviceToHost, sc);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, infl, cudaMemcpyDeviceToHost, sc);
     if (e == cudaSuccess) e = cudaStreamSynchronize(sc);
     std::vector<uint32_t> status(desc.size());
     if (e == cudaSuccess && errs[1]) cudaMemcpy(status.data(), d_s, 4 * desc.size(), cudaMemcpyDeviceToHost);
-    dev_free(&d_c); dev_free(&d_o); dev_free(&d_d); dev_free(&d_s); dev_free(&d_t);
+    dev_free(&d_c); dev_free(&d_o); dev_free(&d_d); dev_free(&d_s); dev_free(&d_t); dev_free(&d_tok); dev_free(&d_nt);
     if (e != cudaSuccess) return ctx_fail(ctx, MSD_ECUDA, "msd_debug_inflate: %s", cudaGetErrorString(e));
     if (errs[1]) { size_t b = 0; while (b < status.size() && !status[b]) b++; return ctx_fail(ctx, MSD_EDATA, "%u block(s) failed to inflate; first: block %zu status %u", errs[1], b, b < status.size() ? status[b] : 0u); }
     return (int64_t)infl;

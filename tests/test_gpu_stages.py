@@ -30,42 +30,38 @@ def test_inflate_matches_zlib(ctx, fixtures, name):
     assert got == want
 
 
-def _bgzf(payloads, level):
-    out = b""
-    for p in payloads:
-        if level == "stored":
-            co = zlib.compressobj(0, zlib.DEFLATED, -15)
-        elif level == "fixed":
-            co = zlib.compressobj(6, zlib.DEFLATED, -15, 9, zlib.Z_FIXED)
-        else:
-            co = zlib.compressobj(level, zlib.DEFLATED, -15)
-        d = co.compress(p) + co.flush()
-        blen = len(d) + 26
-        hdr = b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + b"\x06\0" + b"BC\x02\0" + (blen - 1).to_bytes(2, "little")
-        out += hdr + d + zlib.crc32(p).to_bytes(4, "little") + len(p).to_bytes(4, "little")
-    return out
+from bgzf_cases import basic_payloads, bgzf as _bgzf, tricky_members
 
 
-@pytest.mark.parametrize("level", [1, 6, 9, "fixed", "stored"])
+@pytest.mark.parametrize("level", [1, 6, 9, "fixed", "stored", "rle", "huffman"])
 def test_inflate_synthetic_blocks(ctx, level):
-    rng = np.random.default_rng(7)
-    payloads = []
-    for i in range(300):
-        n = int(rng.integers(1, 65280))
-        kind = i % 5
-        if kind == 0:
-            p = rng.integers(0, 256, n, dtype=np.uint8).tobytes()                      # incompressible
-        elif kind == 1:
-            p = bytes([int(rng.integers(0, 256))]) * n                                  # dist=1 runs
-        elif kind == 2:
-            p = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), n).tobytes()        # tiny alphabet
-        elif kind == 3:
-            w = rng.integers(0, 256, 37, dtype=np.uint8).tobytes(); p = (w * (n // 37 + 1))[:n]   # period 37
-        else:
-            words = [rng.integers(97, 123, int(rng.integers(2, 12)), dtype=np.uint8).tobytes() for _ in range(200)]
-            p = b" ".join(words[int(j)] for j in rng.integers(0, 200, n // 5 + 1))[:n]   # text-like
-        payloads.append(p)
+    payloads = basic_payloads(max_len=65000 if level == "stored" else 65280)
     data = _bgzf(payloads, level)
+    want = b"".join(payloads)
+    assert ctx.debug_inflate(data, len(want)) == want
+
+
+def test_inflate_tricky_members(ctx):
+    """15-bit codes, several DEFLATE blocks + empty stored blocks per member, 258-byte matches at short periods,
+    32 KB distances, ISIZE 65536, literal runs > 510 (skip tokens), 1-byte members and the empty EOF member."""
+    cases = tricky_members()
+    for i, (p, m) in enumerate(cases):
+        assert ctx.debug_inflate(m, max(len(p), 1)) == p, f"case {i} alone"
+    data = b"".join(m for _, m in cases)
+    want = b"".join(p for p, _ in cases)
+    assert ctx.debug_inflate(data, len(want)) == want
+
+
+def test_inflate_many_blocks_lock_step(ctx):
+    """More blocks than decoder lanes on the device with very uneven sizes: lanes finish at different times, take new
+    tickets and rebuild tables while their neighbours keep decoding."""
+    rng = np.random.default_rng(3)
+    payloads = []
+    for i in range(3000):
+        n = int(rng.integers(1, 400)) if i % 3 else int(rng.integers(1, 65000))
+        words = [rng.integers(65, 91, int(rng.integers(2, 9)), dtype=np.uint8).tobytes() for _ in range(50)]
+        payloads.append(b"".join(words[int(j)] for j in rng.integers(0, 50, n // 4 + 1))[:n])
+    data = _bgzf(payloads, 6)
     want = b"".join(payloads)
     assert ctx.debug_inflate(data, len(want)) == want
 
