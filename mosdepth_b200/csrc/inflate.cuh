@@ -13,13 +13,16 @@
 //       __syncwarp(), so every issued instruction advances up to 32 chains.  A lane writes literal bytes straight to
 //       their final position and appends one 4-byte token per match; it never reads its own output, so no memory
 //       round trip sits on the chain (the next compressed word is prefetched one refill ahead).
-//       Tables: 8-bit lit/len root + 7-bit distance root (16-bit entries carrying length base / extra-bit count, so a
-//       symbol costs one shared-memory load), canonical-order lists for longer codes whose per-length limits live in
-//       REGISTERS (5 warps/SM leave 400 registers per lane).  1376 B of shared memory per lane, word-interleaved
-//       across the warp (bank = lane: conflict free) -> 5 warps = 160 decoders per SM, 23,680 per B200.
+//       Tables: NO root lookup tables.  In lock step a warp pays for the slowest lane, and with 32 lanes some lane
+//       always has a code longer than any affordable root table (r1g first cut: 85 % of iterations), so every symbol
+//       is decoded the same, branch-free way: the 15 per-length limits of the canonical code live in REGISTERS, the
+//       code length is the number of limits <= the next 15 bits (15 independent compares), and shared memory holds
+//       only the symbols in canonical order as 16-bit entries (literal byte | length base, extra-bit count) plus
+//       the 16 index bases: 704 B per lane, halfword-interleaved across the warp -> 9 warps = 288 decoders per SM,
+//       42,624 per B200 (the first cut, with 8/7-bit root tables, needed 1376 B: 5 warps per SM, latency bound).
 //       Dynamic headers are read by their lane (lanes in the header phase run together); the tables of one lane are
-//       then built by all 32 lanes (__match_any_sync ranks, redundant uniform canonical bookkeeping, root filled
-//       by table index).  Lanes re-synchronise their phases every kBurst symbols.
+//       then built by all 32 lanes (__match_any_sync ranks, redundant uniform canonical bookkeeping).
+//       Lanes re-synchronise their phases every kBurst symbols.
 //   K1b lz77_resolve_kernel -- ONE WARP PER BLOCK.  32 tokens per batch (warp scan -> output offsets); the batch's
 //       output range is walked in 32-byte windows, one output byte per lane: a position-indexed bit mask of token
 //       starts (redux.or) + popc gives every byte its token, match bytes load dst[p - dist] and store dst[p]
@@ -32,54 +35,77 @@ namespace msd {
 using namespace inf;
 
 constexpr int kDecThreads = 32;             // one warp per CTA
-constexpr int kDecCtasPerSm = 5;
+constexpr int kDecCtasPerSm = 9;
 constexpr int kBurst = 256;                 // symbol iterations between phase re-synchronisations
-constexpr int kScratchWords = 48 + 160;     // cnt[16] first[16] offs[16] + 320 sorted halfwords
-constexpr size_t kDecSmem = (size_t)(kLaneWords * 32 + kScratchWords) * 4;
-static_assert(kDecCtasPerSm * (kDecSmem + 1024) <= 233472, "5 decoder CTAs must fit one SM's shared memory");
+constexpr int kScratchWords = 32;           // cnt[16] offs[16]
+constexpr size_t kDecSmem = (size_t)kLaneHw * 32 * 2 + kScratchWords * 4;
+static_assert(kDecCtasPerSm * (kDecSmem + 1024) <= 233472, "9 decoder CTAs must fit one SM's shared memory");
 
 __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-// one lane's table region: word j at base[j * 32]
+// one lane's table region: halfword i at base[i * 32]
 struct LaneMem {
-    uint32_t* base;
-    MSD_D uint32_t ld16(uint32_t hw) const { return reinterpret_cast<const uint16_t*>(base)[(hw >> 1) * 64 + (hw & 1)]; }
-    MSD_D void st16(uint32_t hw, uint32_t v) const { reinterpret_cast<uint16_t*>(base)[(hw >> 1) * 64 + (hw & 1)] = (uint16_t)v; }
-    MSD_D uint32_t ld8(uint32_t b) const { return reinterpret_cast<const uint8_t*>(base)[(b >> 2) * 128 + (b & 3)]; }
-    MSD_D void st8(uint32_t b, uint32_t v) const { reinterpret_cast<uint8_t*>(base)[(b >> 2) * 128 + (b & 3)] = (uint8_t)v; }
-    MSD_D void stw(uint32_t j, uint32_t v) const { base[j * 32] = v; }
+    uint16_t* base;
+    MSD_D uint32_t ld16(uint32_t hw) const { return base[hw * 32]; }
+    MSD_D int lds16(uint32_t hw) const { return reinterpret_cast<const int16_t*>(base)[hw * 32]; }
+    MSD_D void st16(uint32_t hw, uint32_t v) const { base[hw * 32] = (uint16_t)v; }
+    MSD_D uint32_t ld8(uint32_t b) const { return reinterpret_cast<const uint8_t*>(base + (b >> 1) * 32)[b & 1]; }
+    MSD_D void st8(uint32_t b, uint32_t v) const { reinterpret_cast<uint8_t*>(base + (b >> 1) * 32)[b & 1] = (uint8_t)v; }
 };
 
-// per-lane bit reader: 64-bit buffer, next compressed word prefetched one refill ahead
+// per-lane bit reader: 64-bit buffer, the next two compressed words prefetched (a refill right after a refill -- a
+// long lit/len code followed by its distance -- must not wait for a load issued a few instructions earlier)
 struct BitReader {
     uint64_t bb;
     int bc;
-    uint32_t widx;    // index of the word held in `ahead` == words already shifted into bb
-    uint32_t ahead;
+    uint32_t widx;    // index of the word held in a0 == words already shifted into bb
+    uint32_t a0, a1;
     MSD_D void seed(const uint32_t* __restrict__ words, uint32_t wlast, uint32_t byte_pos) {
         bb = 0; bc = 0; widx = byte_pos >> 2;
-        ahead = __ldg(words + min(widx, wlast));
+        a0 = __ldg(words + min(widx, wlast)); a1 = __ldg(words + min(widx + 1, wlast));
         refill(words, wlast); drop((int)(byte_pos & 3u) * 8); refill(words, wlast);
     }
     MSD_D void refill(const uint32_t* __restrict__ words, uint32_t wlast) {
-        if (bc <= 32) {
-            bb |= (uint64_t)ahead << bc; bc += 32; widx++;
-            ahead = __ldg(words + min(widx, wlast));
-        }
+        const bool need = bc <= 32;
+        if (need) { bb |= (uint64_t)a0 << bc; bc += 32; widx++; a0 = a1; }
+        // The load is written as a predicated PTX instruction whose destination IS a1: left to the compiler, the
+        // conditional `a1 = __ldg(...)` became a load into a temporary plus a move in the same iteration, which put
+        // the full load latency of the slowest lane on every iteration (39 % of all stall samples, profiles/README.md).
+        // Now the first reader of the loaded word is the next refill's `a0 = a1`.
+        const uint32_t* addr = words + min(widx + 1, wlast);
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}" : "+r"(a1) : "l"(addr), "r"((uint32_t)need));
+        // In lock step an iteration lasts as long as its slowest lane, and with ~10 lanes refilling per iteration one of
+        // them crosses into a new 32-byte sector most of the time: pull the sector after next into L1 (no destination
+        // register, so nothing waits on it); its first word is loaded 8 refills from here.
+        if (need) asm volatile("prefetch.global.L1 [%0];" ::"l"(words + min(widx + 9, wlast)));
     }
     MSD_D uint32_t lo() const { return (uint32_t)bb; }
     MSD_D void drop(int n) { bb >>= n; bc -= n; }
     MSD_D uint32_t take(int n) { const uint32_t v = (uint32_t)bb & ((1u << n) - 1u); drop(n); return v; }
 };
 
+// code length of the canonical code that the 15-bit MSB-first window c starts with, minus 1 (15 = no such code):
+// the number of per-length limits that are <= c.  The 15 limits (each <= 0x8000) are packed two per register;
+// (0x8000 + c) - limit is computed for both halves by ONE subtraction (no borrow can cross: each half stays >= 0) and
+// its bit 15 says c >= limit.  8 subtractions, 8 shift+mask-or's into two accumulators, one popc: short chains.
+MSD_D uint32_t canon_len_minus1(uint32_t c, const uint32_t (&limp)[8]) {
+    const uint32_t cc = c * 0x10001u + 0x80008000u;
+    uint32_t acc0 = 0, acc1 = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t t = ((cc - limp[j]) >> j) & (0x80008000u >> j);
+        if (j & 1) acc1 |= t; else acc0 |= t;
+    }
+    return (uint32_t)__popc(acc0 | acc1);
+}
+
 // Build the tables of lane `X` with all 32 lanes.  XM: X's region (same pointer in every lane).  Code lengths are
-// read from the region first (they alias the tables).  `keep` is true in lane X only: it keeps the canonical
-// limits/bases of the longer codes in its registers.  Returns a Status (uniform across the warp).
+// read from the region first (they alias the tables).  `keep` is true in lane X only: it keeps the per-length limits
+// in its registers.  Returns a Status (uniform across the warp).
 MSD_D uint32_t coop_build(const LaneMem XM, uint32_t* scratch, int hlit, int hdist, int lane, bool keep,
-                          uint32_t (&llim)[7], uint32_t (&lbase)[7], uint32_t (&dlim)[8], uint32_t (&dbase)[8]) {
+                          uint32_t (&llim)[8], uint32_t (&dlim)[8]) {
     constexpr unsigned full = 0xffffffffu;
-    uint32_t* cnt = scratch; uint32_t* first = scratch + 16; uint32_t* offs = scratch + 32;
-    uint16_t* sorted = reinterpret_cast<uint16_t*>(scratch + 48);
+    uint32_t* cnt = scratch; uint32_t* offs = scratch + 16;
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t status = kOk;
 
@@ -105,41 +131,25 @@ MSD_D uint32_t coop_build(const LaneMem XM, uint32_t* scratch, int hlit, int hdi
     }
     {
         // canonical bookkeeping, computed redundantly by every lane (uniform) so that lane X simply keeps its copy
-        uint32_t code = 0, idx = 0, lim8[9], offs9 = 0;
+        uint32_t code = 0, idx = 0, lp[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) lp[j] = j == 7 ? 0x80000000u : 0u;      // the 16th "limit" is never reached
 #pragma unroll
         for (int k = 1; k < 16; k++) {
             const uint32_t c = cnt[k];
             code <<= 1;
-            const uint32_t f = code, o = idx;
-            if (k == kLitRootBits + 1) offs9 = idx;
+            if (lane == k) { offs[k] = idx; XM.st16(kLitBaseHw + k, (idx - code) & 0xffffu); }
             code += c; idx += c;
             if (code > (1u << k)) status = kOversubscribed;
-            if (lane == 0) { first[k] = f; offs[k] = o; }
-            if (k <= kLitRootBits) lim8[k] = code << (kLitRootBits - k);
-            else if (keep) { llim[k - 9] = code << (15 - k); lbase[k - 9] = (o - offs9 - f) & 0xffffu; }
+            lp[(k - 1) >> 1] |= min(code << (15 - k), 0x8000u) << (16 * ((k - 1) & 1));
         }
-        const uint32_t n_syms = idx;
+        if (keep) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) llim[j] = lp[j];
+        }
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 9; j++) if (l[j]) sorted[offs[l[j]] + rank[j]] = (uint16_t)(lane + 32 * j);
-        __syncwarp();
-        // root table by index: 8 entries per lane
-#pragma unroll
-        for (int t = 0; t < 8; t++) {
-            const uint32_t i = (uint32_t)lane + 32u * t;
-            const uint32_t c = __brev(i) >> 24;
-            uint32_t len = 1;
-#pragma unroll
-            for (int k = 1; k <= kLitRootBits; k++) len += (c >= lim8[k]) ? 1u : 0u;
-            uint32_t ent = 0;
-            if (len <= (uint32_t)kLitRootBits) {
-                const uint32_t sym = sorted[offs[len] + (c >> (kLitRootBits - len)) - first[len]];
-                ent = lit_entry_of(sym) | len;
-            }
-            XM.st16(kLitRootHw + i, ent);
-        }
-        const uint32_t n_long = n_syms - offs9;
-        for (uint32_t i = lane; i < n_long; i += 32) XM.st16(kLongLitHw + i, lit_entry_of(sorted[offs9 + i]));
+        for (int j = 0; j < 9; j++) if (l[j]) XM.st16(kLitSymHw + offs[l[j]] + rank[j], lit_entry_of((uint32_t)(lane + 32 * j)));
         __syncwarp();
     }
 
@@ -151,39 +161,24 @@ MSD_D uint32_t coop_build(const LaneMem XM, uint32_t* scratch, int hlit, int hdi
         const uint32_t r = __popc(m & lt);
         if (r == 0) cnt[dl] = __popc(m);
         __syncwarp();
-        uint32_t code = 0, idx = 0, lim7[8], offs8 = 0;
+        uint32_t code = 0, idx = 0, lp[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) lp[j] = j == 7 ? 0x80000000u : 0u;
 #pragma unroll
         for (int k = 1; k < 16; k++) {
             const uint32_t c = cnt[k];
             code <<= 1;
-            const uint32_t f = code, o = idx;
-            if (k == kDistRootBits + 1) offs8 = idx;
+            if (lane == k) { offs[k] = idx; XM.st16(kDistBaseHw + k, (idx - code) & 0xffffu); }
             code += c; idx += c;
             if (code > (1u << k)) status = kOversubscribed;
-            if (lane == 0) { first[k] = f; offs[k] = o; }
-            if (k <= kDistRootBits) lim7[k] = code << (kDistRootBits - k);
-            else if (keep) { dlim[k - 8] = code << (15 - k); dbase[k - 8] = (o - offs8 - f) & 0xffffu; }
+            lp[(k - 1) >> 1] |= min(code << (15 - k), 0x8000u) << (16 * ((k - 1) & 1));
         }
-        const uint32_t n_syms = idx;
-        __syncwarp();
-        if (dl) sorted[offs[dl] + r] = (uint16_t)lane;
-        __syncwarp();
+        if (keep) {
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const uint32_t i = (uint32_t)lane + 32u * t;
-            const uint32_t c = __brev(i) >> 25;
-            uint32_t len = 1;
-#pragma unroll
-            for (int k = 1; k <= kDistRootBits; k++) len += (c >= lim7[k]) ? 1u : 0u;
-            uint32_t ent = 0;
-            if (len <= (uint32_t)kDistRootBits) {
-                const uint32_t sym = sorted[offs[len] + (c >> (kDistRootBits - len)) - first[len]];
-                ent = dist_entry_of(sym) | len;
-            }
-            XM.st16(kDistRootHw + i, ent);
+            for (int j = 0; j < 8; j++) dlim[j] = lp[j];
         }
-        const uint32_t n_long = n_syms - offs8;
-        if ((uint32_t)lane < n_long) XM.st8(kLongDistByte + lane, dist_entry_of(sorted[offs8 + lane]) >> 4);
+        __syncwarp();
+        if (dl) XM.st16(kDistSymHw + offs[dl] + r, dist_entry_of((uint32_t)lane));
         __syncwarp();
     }
     return status;
@@ -197,30 +192,28 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm)
 huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, int n_blocks,
                       uint32_t* __restrict__ ticket, uint32_t* __restrict__ tokens, uint32_t* __restrict__ n_tokens,
                       uint32_t* __restrict__ status_out, uint32_t* __restrict__ error_count) {
-    extern __shared__ __align__(16) uint32_t smem32[];
+    extern __shared__ __align__(16) uint16_t smem16[];
     constexpr unsigned full = 0xffffffffu;
     const int lane = threadIdx.x;
-    const LaneMem M{smem32 + lane};
-    uint32_t* const scratch = smem32 + kLaneWords * 32;
+    const LaneMem M{smem16 + lane};
+    uint32_t* const scratch = reinterpret_cast<uint32_t*>(smem16 + kLaneHw * 32);
 
     int phase = kPhNeed, b = 0, bfinal = 0, hlit = 0, hdist = 0;
     const uint32_t* __restrict__ words = nullptr;
     uint8_t* __restrict__ dst = nullptr;
-    uint32_t* __restrict__ tok = nullptr;
-    uint32_t* tok_begin = nullptr;
-    uint32_t wlast = 0, total_words = 0, isize = 0, lead = 0, clen = 0, outp = 0, lit_run = 0, err = 0;
-    BitReader br; br.bb = 0; br.bc = 0; br.widx = 0; br.ahead = 0;
-    uint32_t llim[7], lbase[7], dlim[8], dbase[8];
+    uint32_t* __restrict__ tok = nullptr;   // this block's token list
+    uint32_t ntok = 0;
+    uint32_t wlast = 0, total_words = 0, isize = 0, lead = 0, clen = 0, outp = 0, run_base = 0, err = 0;
+    BitReader br; br.bb = 0; br.bc = 0; br.widx = 0; br.a0 = 0; br.a1 = 0;
+    uint32_t llim[8], dlim[8];     // per-length limits of the two canonical codes, packed two per register
 #pragma unroll
-    for (int k = 0; k < 7; k++) { llim[k] = 0; lbase[k] = 0; }
-#pragma unroll
-    for (int k = 0; k < 8; k++) { dlim[k] = 0; dbase[k] = 0; }
+    for (int k = 0; k < 8; k++) { llim[k] = 0; dlim[k] = 0; }
 
     for (;;) {
         // ---- blocks that ended during the last burst; new tickets --------------------------------------------------
         if (phase == kPhFinish) {
             if (outp != isize) { err = kShort; phase = kPhFail; }
-            else { n_tokens[b] = (uint32_t)(tok - tok_begin); status_out[b] = kOk; phase = kPhNeed; }
+            else { n_tokens[b] = ntok; status_out[b] = kOk; phase = kPhNeed; }
         }
         if (phase == kPhFail) {
             n_tokens[b] = 0; status_out[b] = err ? err : (uint32_t)kBadSymbol; atomicAdd(error_count, 1u); phase = kPhNeed;
@@ -234,8 +227,8 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
                 words = reinterpret_cast<const uint32_t*>(comp + (bd.src - lead));
                 total_words = max((lead + clen + 3) / 4, 1u); wlast = total_words - 1;
                 dst = out + bd.dst;
-                tok_begin = tokens + (size_t)b * kTokenCap; tok = tok_begin;
-                outp = 0; lit_run = 0; err = 0; bfinal = 0;
+                tok = tokens + (size_t)b * kTokenCap; ntok = 0;
+                outp = 0; run_base = 0; err = 0; bfinal = 0;
                 br.seed(words, wlast, lead);
                 phase = kPhHeader;
             }
@@ -259,7 +252,7 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
                 else {
                     const uint8_t* sb = reinterpret_cast<const uint8_t*>(words) + sp;
                     for (uint32_t k = 0; k < len; k++) dst[outp + k] = sb[k];
-                    outp += len; lit_run += len;
+                    outp += len;                                            // stored bytes count as literals of the next token
                     br.seed(words, wlast, sp + len);
                     if (bfinal) phase = kPhFinish;
                 }
@@ -288,7 +281,7 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
                 }
                 if (left < 0) err = kOversubscribed;
                 if (!err) {
-                    for (int j = 0; j < 32; j++) M.stw(kClTabByte / 4 + j, 0u);
+                    for (int j = 0; j < 64; j++) M.st16(kClTabByte / 2 + j, 0u);
                     for (int s = 0; s < 19; s++) {
                         const uint32_t q = (uint32_t)(clp >> (3 * s)) & 7u;
                         if (!q) continue;
@@ -329,7 +322,7 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
             while (bm) {
                 const int X = __ffs((int)bm) - 1; bm &= bm - 1;
                 const int hl = __shfl_sync(full, hlit, X), hd = __shfl_sync(full, hdist, X);
-                const uint32_t st = coop_build(LaneMem{smem32 + X}, scratch, hl, hd, lane, lane == X, llim, lbase, dlim, dbase);
+                const uint32_t st = coop_build(LaneMem{smem16 + X}, scratch, hl, hd, lane, lane == X, llim, dlim);
                 if (lane == X) { if (st) { err = st; phase = kPhFail; } else phase = kPhSym; }
             }
         }
@@ -343,46 +336,38 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
                 if (phase == kPhSym) {
                     br.refill(words, wlast);
                     uint32_t lo = br.lo();
-                    uint32_t e = M.ld16(kLitRootHw + (lo & 255u));
-                    if ((e & 15u) == 0) {
-                        // code longer than the root: canonical search over the per-length limits (registers)
-                        const uint32_t c = __brev(lo) >> 17;
-                        uint32_t n = 0, base = lbase[0];
-#pragma unroll
-                        for (int k = 0; k < 6; k++) if (c >= llim[k]) { n = k + 1; base = lbase[k + 1]; }
-                        if (c >= llim[6]) { err = kBadSymbol; e = (kNibBad << 4) | 1u; }
-                        else { const uint32_t l = 9 + n; e = M.ld16(kLongLitHw + ((base + (c >> (15 - l))) & 0xffffu)) | l; }
-                    }
-                    br.drop((int)(e & 15u));
-                    const uint32_t nib = (e >> 4) & 15u;
-                    if (nib & 8u) {
-                        if (outp < isize) { dst[outp] = (uint8_t)(e >> 8); outp++; lit_run++; }
+                    uint32_t c = __brev(lo) >> 17;
+                    uint32_t l1 = canon_len_minus1(c, llim);                       // code length - 1
+                    uint32_t idx = (uint32_t)(M.lds16(kLitBaseHw + 1 + l1) + (int)(c >> ((14u - l1) & 31u)));
+                    const uint32_t e = M.ld16(kLitSymHw + min(idx, 287u));
+                    const uint32_t nib = (l1 < 15u) ? ((e >> 4) & 15u) : kNibBad;
+                    const uint32_t x = nib < 8u ? nib : 0u;                        // extra bits of a length code
+                    const uint32_t ext = (lo >> (l1 + 1)) & ((1u << x) - 1u);
+                    br.drop((int)(l1 + 1 + x));
+                    if (nib == kNibLit) {
+                        if (outp < isize) { dst[outp] = (uint8_t)(e >> 8); outp++; }
                         else err = kOverflow;
-                    } else if (nib >= kNibEob) {
+                    } else if (nib >= 8u) {
                         if (nib == kNibEob) phase = bfinal ? kPhFinish : kPhHeader;
-                        else if (!err) err = kBadSymbol;
+                        else err = kBadSymbol;
                     } else {
-                        const uint32_t len = 3u + ((e >> 8) & 0xffu) + br.take((int)nib);
+                        const uint32_t len = 3u + (e >> 8) + ext;
                         br.refill(words, wlast);
                         lo = br.lo();
-                        uint32_t d = M.ld16(kDistRootHw + (lo & 127u));
-                        if ((d & 15u) == 0) {
-                            const uint32_t c = __brev(lo) >> 17;
-                            uint32_t n = 0, base = dbase[0];
-#pragma unroll
-                            for (int k = 0; k < 7; k++) if (c >= dlim[k]) { n = k + 1; base = dbase[k + 1]; }
-                            if (c >= dlim[7]) d = (kDistNibBad << 4) | 1u;
-                            else { const uint32_t l = 8 + n; d = (M.ld8(kLongDistByte + ((base + (c >> (15 - l))) & 0xffffu)) << 4) | l; }
-                        }
-                        br.drop((int)(d & 15u));
-                        const uint32_t x = (d >> 4) & 15u;
-                        const uint32_t dist = 1u + (((d >> 8) & 3u) << x) + br.take((int)x);
-                        if (x == kDistNibBad || dist > outp) err = kBadDistance;
+                        c = __brev(lo) >> 17;
+                        l1 = canon_len_minus1(c, dlim);
+                        idx = (uint32_t)(M.lds16(kDistBaseHw + 1 + l1) + (int)(c >> ((14u - l1) & 31u)));
+                        const uint32_t d = M.ld16(kDistSymHw + min(idx, 29u));
+                        const uint32_t dx = (l1 < 15u) ? ((d >> 4) & 15u) : kDistNibBad;
+                        const uint32_t dist = 1u + (((d >> 8) & 3u) << dx) + ((lo >> (l1 + 1)) & ((1u << dx) - 1u));
+                        br.drop((int)(l1 + 1 + dx));
+                        if (dx == kDistNibBad || dist > outp) err = kBadDistance;
                         else if (outp + len > isize) err = kOverflow;
                         else {
-                            if (lit_run > 510u) { *tok++ = (kTokSkip << 23) | lit_run; lit_run = 0; }
-                            *tok++ = make_token(lit_run, len, dist);
-                            lit_run = 0; outp += len;
+                            uint32_t lit_run = outp - run_base;
+                            if (lit_run > 510u) { tok[ntok++] = (kTokSkip << 23) | lit_run; lit_run = 0; }
+                            tok[ntok++] = make_token(lit_run, len, dist);
+                            outp += len; run_base = outp;
                         }
                     }
                     if (err) phase = kPhFail;
@@ -396,7 +381,7 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
 
 // K1b.  One warp per BGZF block: copies every match of the block's token list; literals are already in place.
 constexpr int kResolveWarps = 4;
-constexpr int kResolveCtasPerSm = 12;
+constexpr int kResolveCtasPerSm = 16;
 
 __global__ void __launch_bounds__(kResolveWarps * 32, kResolveCtasPerSm)
 lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_blocks, uint32_t* __restrict__ ticket,
@@ -414,41 +399,58 @@ lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_bl
         const uint32_t* __restrict__ tok = tokens + (size_t)b * kTokenCap;
         const uint32_t nt = n_tokens[b];
         int pos_base = 0;
+        uint32_t w_next = lane < (int)nt ? __ldg(tok + lane) : 0u;
         for (uint32_t t0 = 0; t0 < nt; t0 += 32) {
-            const uint32_t t = t0 + lane;
-            int lr = 0, len = 0, dist = 0, adv = 0;
-            if (t < nt) {
-                const uint32_t w = __ldg(tok + t);
+            const uint32_t w = w_next;
+            const bool have = t0 + lane < nt;
+            { const uint32_t tn = t0 + 32 + lane; w_next = tn < nt ? __ldg(tok + tn) : 0u; }   // next batch's tokens: in flight during this one
+            int lr = 0, dist = 0, adv = 0;
+            bool is_match = false;
+            if (have) {
                 lr = (int)(w >> 23);
                 if (lr == (int)kTokSkip) { lr = (int)(w & 0x7fffffu); adv = lr; }
-                else { len = (int)(w & 0xffu) + 3; dist = (int)((w >> 8) & 0x7fffu) + 1; adv = lr + len; }
+                else { dist = (int)((w >> 8) & 0x7fffu) + 1; adv = lr + (int)(w & 0xffu) + 3; is_match = true; }
             }
             int incl = adv;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, incl, o); if (lane >= o) incl += y; }
             const int total = __shfl_sync(full, incl, 31);
-            const int start = pos_base + incl - adv;        // first output byte of this token (its literals)
-            const int mstart = start + lr;                  // first byte of its match
+            const int start = pos_base + incl - adv;                 // first output byte of this token (its literals)
+            const int mstart = is_match ? start + lr : 0x7fffffff;   // first byte of its match
             const int hi = pos_base + total;
-            int before = 0;                                  // tokens of the batch that start before the window
-            for (int wb = ((pos_base + mis) & ~31) - mis; wb < hi; wb += 32) {
-                const uint32_t my_head = (adv > 0 && start >= wb && start < wb + 32) ? (1u << (start - wb)) : 0u;
-                const uint32_t heads = __reduce_or_sync(full, my_head);
-                const int p = wb + lane;
-                const int m = before + __popc(heads & le) - 1;
+            const int wb0 = ((pos_base + mis) & ~31) - mis;          // windows are 32-byte aligned in memory
+            const int head_win = adv > 0 ? (start - wb0) >> 5 : -1;  // window in which this token starts
+            const uint32_t head_bit = 1u << ((start - wb0) & 31);
+            int before = 0;                                          // tokens of the batch that start before the window
+            int j = 0;
+            for (int wb = wb0; wb < hi; wb += 32, j++) {
+                const uint32_t heads = __reduce_or_sync(full, head_win == j ? head_bit : 0u);
+                const int m = before + __popc(heads & le) - 1;      // this byte's token (-1: before the batch)
                 before += __popc(heads);
                 const int ms = __shfl_sync(full, mstart, m & 31);
                 const int md = __shfl_sync(full, dist, m & 31);
-                bool pend = p >= pos_base && p < hi && m >= 0 && md > 0 && p >= ms;
+                const int p = wb + lane;
+                const int k = p - ms;
+                const bool is_copy = (uint32_t)(p - pos_base) < (uint32_t)total && k >= 0;
                 int src = p - md;
-                if (pend && p - ms >= md) src = ms - md + (p - ms) % md;   // dist < len: fold onto the first period
-                uint32_t done = __ballot_sync(full, !pend);
-                while (done != full) {
-                    const bool ready = pend && (src < wb || ((done >> (src - wb)) & 1u));
-                    if (ready) { dst[p] = dst[src]; pend = false; }
+                if (is_copy && k >= md) src = ms - md + k % md;     // dist < len: fold onto the first period
+                const bool far = is_copy && src < wb;               // source lies before this window: final already
+                bool near = is_copy && src >= wb;                   // source is a byte of this window
+                uint8_t v = 0;
+                if (far) v = dst[src];
+                const bool any_near = __any_sync(full, near);
+                if (far) dst[p] = v;
+                if (any_near) {
                     __syncwarp();
-                    done = __ballot_sync(full, !pend);
+                    uint32_t done = __ballot_sync(full, !near);
+                    while (done != full) {
+                        const bool ready = near && ((done >> (src - wb)) & 1u);
+                        if (ready) { dst[p] = dst[src]; near = false; }
+                        __syncwarp();
+                        done = __ballot_sync(full, !near);
+                    }
                 }
+                __syncwarp();
             }
             pos_base = hi;
         }

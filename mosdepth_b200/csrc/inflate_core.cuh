@@ -10,28 +10,23 @@
 namespace msd {
 namespace inf {
 
-constexpr int kLitRootBits = 8;      // lit/len root table: 256 entries
-constexpr int kDistRootBits = 7;     // distance root table: 128 entries
-
-// ---- per-decoder (per-lane) shared-memory region, 344 32-bit words; word j of lane L lives at smem32[j * 32 + L]
-//      so that a warp-wide access to "the same field of every lane's table" never has a bank conflict ----------------
-constexpr int kLitRootHw = 0;        // halfword index of the lit/len root table (256 halfwords)
-constexpr int kDistRootHw = 256;     // distance root table (128 halfwords)
-constexpr int kLongLitHw = 384;      // lit/len symbols with codes longer than the root, canonical order (<= 286 halfwords)
-constexpr int kLongDistByte = 1340;  // distance symbols with codes longer than the root, canonical order (<= 30 bytes)
-constexpr int kLaneWords = 344;      // 1376 B
-// while a dynamic header is being read the (dead) tables hold:
+// ---- per-decoder (per-lane) shared-memory region: 352 halfwords; halfword i of lane L lives at smem16[i * 32 + L]
+//      (one shift-add per lookup; at most 2-way bank conflicts, between the two lanes that share a 32-bit word) ------
+constexpr int kLitSymHw = 0;         // lit/len symbols in canonical order, as table entries (<= 288: the fixed code has 288)
+constexpr int kDistSymHw = 288;      // distance symbols in canonical order, as table entries (<= 30)
+constexpr int kLitBaseHw = 318;      // [l]: (index of the first length-l symbol - first length-l code) mod 2^16, l = 1..15
+constexpr int kDistBaseHw = 334;
+constexpr int kLaneHw = 352;         // 704 B per decoder ([l] is read with l = 16 for an invalid code: keep it inside)
+// while a dynamic header is being read the (dead) tables hold, as bytes (byte b = half (b & 1) of halfword b >> 1):
 constexpr int kClTabByte = 0;        // 128-entry code-length-code table, one byte per entry: sym << 3 | len
 constexpr int kLensByte = 128;       // hlit + hdist code lengths, one byte each (<= 316)
 
-// ---- table entries (16 bit) ----------------------------------------------------------------------------------------
-// lit/len: [3:0] code length (0 in the root = "longer than the root, or no such code"; 0 in the long list)
-//          [7:4] 0..5 = length code with that many extra bits, 6 = end of block, 7 = symbol that must not occur,
-//                8 = literal
-//          [15:8] literal byte, or length base - 3
-// distance: [3:0] code length, [7:4] extra bits 0..13 (15 = symbol that must not occur), [9:8] mantissa m:
+// ---- table entries (16 bit; the code length is not stored: the canonical search yields it) --------------------------
+// lit/len: [7:4] 0..5 = length code with that many extra bits, 8 = literal, 9 = end of block, 10 = symbol that must
+//                not occur;  [15:8] literal byte, or length base - 3
+// distance: [7:4] extra bits 0..13 (15 = symbol that must not occur), [9:8] mantissa m:
 //          distance = 1 + (m << extra) + extra bits
-constexpr uint32_t kNibEob = 6, kNibBad = 7, kNibLit = 8, kDistNibBad = 15;
+constexpr uint32_t kNibLit = 8, kNibEob = 9, kNibBad = 10, kDistNibBad = 15;
 
 MSD_HD uint32_t lit_entry_of(uint32_t sym) {
     if (sym < 256) return (sym << 8) | (kNibLit << 4);
@@ -70,11 +65,11 @@ MSD_HD void canon_from_counts(const uint32_t* cnt /*[16], cnt[0] ignored*/, Cano
         if (code > (1u << l)) c.oversubscribed = true;
     }
 }
-// limit of length l left-aligned to `bits` bits (l <= bits): a `bits`-bit MSB-first window c starts with a code of
-// length <= l iff c < limit
-MSD_HD uint32_t canon_limit(const Canon& c, int l, int bits) { return c.end[l] << (bits - l); }
-// index base (mod 2^16) into the long list for codes of length l > root: idx = (base + code) & 0xffff
-MSD_HD uint32_t canon_long_base(const Canon& c, int l, int root) { return (c.offs[l] - c.offs[root + 1] - c.first[l]) & 0xffffu; }
+// limit of length l left-aligned to 15 bits: a 15-bit MSB-first window c starts with a code of length <= l iff
+// c < limit; the limits are non-decreasing in l, so the code length is 1 + #{l in 1..14 : c >= limit(l)}
+MSD_HD uint32_t canon_limit(const Canon& c, int l) { return c.end[l] << (15 - l); }
+// index base (mod 2^16) into the canonical-order symbol list: idx = (base + (c >> (15 - l))) & 0xffff
+MSD_HD uint32_t canon_base(const Canon& c, int l) { return (c.offs[l] - c.first[l]) & 0xffffu; }
 
 // ---- match tokens handed from K1a to K1b (32 bit) ---------------------------------------------------------------
 // [31:23] literals since the previous token (0..510), [22:8] distance - 1, [7:0] length - 3

@@ -1,5 +1,5 @@
 // inflate_model.cpp -- host replay of the arithmetic of the two inflate kernels (mosdepth_b200/csrc/inflate.cuh):
-// same table-entry encodings, canonical bookkeeping, root-by-index fill, long-code search, token format and the
+// same table-entry encodings, canonical bookkeeping, limit-compare code search, token format and the
 // 32-byte-window resolve schedule, executed lane by lane on the CPU and compared with zlib.  A design/debug aid and a
 // CPU test of inflate_core.cuh (tests/test_inflate_model.py); it is NOT a fallback and nothing in the library uses it.
 //   usage: inflate_model file.bam|file.gz [max_blocks]      (any BGZF file)
@@ -14,55 +14,43 @@
 using namespace msd::inf;
 
 struct Tables {
-    uint16_t lit_root[256], dist_root[128], long_lit[286];
-    uint8_t long_dist[30];
-    uint32_t llim[7], lbase[7], dlim[8], dbase[8];
+    uint16_t lit_sym[288], dist_sym[30], lit_base[17], dist_base[17];
+    uint32_t llim[15], dlim[15];
 };
 
 static uint32_t brev32(uint32_t v) { uint32_t r = 0; for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i); return r; }
 
-// mirrors coop_build(): ranks by (length, symbol order), canonical bookkeeping, root filled by index
+// mirrors coop_build(): ranks by (length, symbol order), canonical bookkeeping, symbols stored as entries
 static uint32_t build(const uint8_t* lens, int hlit, int hdist, Tables& T) {
     uint32_t status = kOk;
+    memset(&T, 0xA5, sizeof T);   // stale entries of an earlier block
     for (int pass = 0; pass < 2; pass++) {
-        const int n = pass ? hdist : hlit, root = pass ? kDistRootBits : kLitRootBits;
+        const int n = pass ? hdist : hlit;
         const uint8_t* L = pass ? lens + hlit : lens;
         uint32_t cnt[16] = {0};
         std::vector<uint32_t> rank(n);
         for (int s = 0; s < n; s++) rank[s] = cnt[L[s]]++;
         msd::inf::Canon c; canon_from_counts(cnt, c);
         if (c.oversubscribed) status = kOversubscribed;
-        uint16_t sorted[320];
-        uint32_t nsyms = 0;
-        for (int s = 0; s < n; s++) if (L[s]) { sorted[c.offs[L[s]] + rank[s]] = (uint16_t)s; nsyms++; }
-        for (uint32_t i = 0; i < (1u << root); i++) {
-            const uint32_t cw = brev32(i) >> (32 - root);
-            uint32_t len = 1;
-            for (int k = 1; k <= root; k++) len += cw >= canon_limit(c, k, root);
-            uint32_t ent = 0;
-            if (len <= (uint32_t)root) {
-                const uint32_t sym = sorted[c.offs[len] + (cw >> (root - len)) - c.first[len]];
-                ent = (pass ? dist_entry_of(sym) : lit_entry_of(sym)) | len;
-            }
-            if (pass) T.dist_root[i] = (uint16_t)ent; else T.lit_root[i] = (uint16_t)ent;
+        for (int s = 0; s < n; s++) if (L[s]) {
+            const uint32_t at = c.offs[L[s]] + rank[s];
+            if (pass) T.dist_sym[at] = (uint16_t)dist_entry_of(s); else T.lit_sym[at] = (uint16_t)lit_entry_of(s);
         }
-        const uint32_t offs_long = c.offs[root + 1];
-        for (uint32_t i = 0; i + offs_long < nsyms; i++) {
-            if (pass) T.long_dist[i] = (uint8_t)(dist_entry_of(sorted[offs_long + i]) >> 4); else T.long_lit[i] = (uint16_t)lit_entry_of(sorted[offs_long + i]);
-        }
-        for (int k = root + 1; k < 16; k++) {
-            if (pass) { T.dlim[k - 8] = canon_limit(c, k, 15); T.dbase[k - 8] = canon_long_base(c, k, root); }
-            else { T.llim[k - 9] = canon_limit(c, k, 15); T.lbase[k - 9] = canon_long_base(c, k, root); }
+        for (int k = 1; k < 16; k++) {
+            if (pass) { T.dlim[k - 1] = canon_limit(c, k); T.dist_base[k] = (uint16_t)canon_base(c, k); }
+            else { T.llim[k - 1] = canon_limit(c, k); T.lit_base[k] = (uint16_t)canon_base(c, k); }
         }
     }
     return status;
 }
 
+static uint32_t len_minus1(uint32_t c, const uint32_t* lim) { uint32_t n = 0; for (int k = 0; k < 15; k++) n += c >= lim[k]; return n; }
+
 struct BitReader {
-    uint64_t bb = 0; int bc = 0; uint32_t widx = 0, ahead = 0;
+    uint64_t bb = 0; int bc = 0; uint32_t widx = 0, a0 = 0, a1 = 0;
     const uint32_t* words; uint32_t wlast;
-    void seed(uint32_t byte_pos) { bb = 0; bc = 0; widx = byte_pos >> 2; ahead = words[std::min(widx, wlast)]; refill(); drop((int)(byte_pos & 3u) * 8); refill(); }
-    void refill() { if (bc <= 32) { bb |= (uint64_t)ahead << bc; bc += 32; widx++; ahead = words[std::min(widx, wlast)]; } }
+    void seed(uint32_t byte_pos) { bb = 0; bc = 0; widx = byte_pos >> 2; a0 = words[std::min(widx, wlast)]; a1 = words[std::min(widx + 1, wlast)]; refill(); drop((int)(byte_pos & 3u) * 8); refill(); }
+    void refill() { if (bc <= 32) { bb |= (uint64_t)a0 << bc; bc += 32; widx++; a0 = a1; a1 = words[std::min(widx + 1, wlast)]; } }
     uint32_t lo() const { return (uint32_t)bb; }
     void drop(int n) { bb >>= n; bc -= n; }
     uint32_t take(int n) { const uint32_t v = (uint32_t)bb & ((1u << n) - 1u); drop(n); return v; }
@@ -75,7 +63,7 @@ static uint32_t decode_block(const uint8_t* comp_aligned, uint32_t lead, uint32_
     BitReader br; br.words = reinterpret_cast<const uint32_t*>(comp_aligned);
     const uint32_t total_words = std::max((lead + clen + 3) / 4, 1u); br.wlast = total_words - 1;
     br.seed(lead);
-    uint32_t outp = 0, lit_run = 0; int bfinal = 0;
+    uint32_t outp = 0, run_base = 0; int bfinal = 0;
     Tables T;
     while (!bfinal) {
         br.refill();
@@ -90,7 +78,7 @@ static uint32_t decode_block(const uint8_t* comp_aligned, uint32_t lead, uint32_
             if ((len ^ 0xffffu) != nlen || sp + len > lead + clen) return kBadStored;
             if (outp + len > isize) return kOverflow;
             memcpy(dst + outp, comp_aligned + sp, len);
-            outp += len; lit_run += len;
+            outp += len;
             br.seed(sp + len);
             continue;
         } else if (btype == 1) {
@@ -140,36 +128,31 @@ static uint32_t decode_block(const uint8_t* comp_aligned, uint32_t lead, uint32_
         for (;;) {
             br.refill();
             uint32_t lo = br.lo();
-            uint32_t e = T.lit_root[lo & 255u];
-            if ((e & 15u) == 0) {
-                const uint32_t c = brev32(lo) >> 17;
-                uint32_t n = 0, base = T.lbase[0];
-                for (int k = 0; k < 6; k++) if (c >= T.llim[k]) { n = k + 1; base = T.lbase[k + 1]; }
-                if (c >= T.llim[6]) return kBadSymbol;
-                const uint32_t l = 9 + n; e = T.long_lit[(base + (c >> (15 - l))) & 0xffffu] | l;
-            }
-            br.drop((int)(e & 15u));
-            const uint32_t nib = (e >> 4) & 15u;
-            if (nib & 8u) { if (outp >= isize) return kOverflow; dst[outp++] = (uint8_t)(e >> 8); lit_run++; continue; }
-            if (nib >= kNibEob) { if (nib == kNibEob) break; return kBadSymbol; }
-            const uint32_t len = 3u + ((e >> 8) & 0xffu) + br.take((int)nib);
+            uint32_t c = brev32(lo) >> 17;
+            uint32_t l1 = len_minus1(c, T.llim);
+            uint32_t idx = (T.lit_base[(1 + l1) & 15] + (c >> ((14u - l1) & 31u))) & 0xffffu;
+            const uint32_t e = T.lit_sym[std::min(idx, 287u)];
+            const uint32_t nib = (l1 < 15u) ? ((e >> 4) & 15u) : kNibBad;
+            const uint32_t x = nib < 8u ? nib : 0u;
+            const uint32_t ext = (lo >> (l1 + 1)) & ((1u << x) - 1u);
+            br.drop((int)(l1 + 1 + x));
+            if (nib == kNibLit) { if (outp >= isize) return kOverflow; dst[outp++] = (uint8_t)(e >> 8); continue; }
+            if (nib >= 8u) { if (nib == kNibEob) break; return kBadSymbol; }
+            const uint32_t len = 3u + (e >> 8) + ext;
             br.refill();
             lo = br.lo();
-            uint32_t d = T.dist_root[lo & 127u];
-            if ((d & 15u) == 0) {
-                const uint32_t c = brev32(lo) >> 17;
-                uint32_t n = 0, base = T.dbase[0];
-                for (int k = 0; k < 7; k++) if (c >= T.dlim[k]) { n = k + 1; base = T.dbase[k + 1]; }
-                if (c >= T.dlim[7]) return kBadDistance;
-                const uint32_t l = 8 + n; d = ((uint32_t)T.long_dist[(base + (c >> (15 - l))) & 0xffffu] << 4) | l;
-            }
-            br.drop((int)(d & 15u));
-            const uint32_t x = (d >> 4) & 15u;
-            const uint32_t dist = 1u + (((d >> 8) & 3u) << x) + br.take((int)x);
-            if (x == kDistNibBad || dist > outp) return kBadDistance;
+            c = brev32(lo) >> 17;
+            l1 = len_minus1(c, T.dlim);
+            idx = (T.dist_base[(1 + l1) & 15] + (c >> ((14u - l1) & 31u))) & 0xffffu;
+            const uint32_t d = T.dist_sym[std::min(idx, 29u)];
+            const uint32_t dx = (l1 < 15u) ? ((d >> 4) & 15u) : kDistNibBad;
+            const uint32_t dist = 1u + (((d >> 8) & 3u) << dx) + ((lo >> (l1 + 1)) & ((1u << dx) - 1u));
+            br.drop((int)(l1 + 1 + dx));
+            if (dx == kDistNibBad || dist > outp) return kBadDistance;
             if (outp + len > isize) return kOverflow;
+            uint32_t lit_run = outp - run_base;
             if (lit_run > 510u) { tok.push_back((kTokSkip << 23) | lit_run); lit_run = 0; }
-            tok.push_back(make_token(lit_run, len, dist)); lit_run = 0; outp += len;
+            tok.push_back(make_token(lit_run, len, dist)); outp += len; run_base = outp;
         }
     }
     return outp == isize ? kOk : kShort;
@@ -180,45 +163,48 @@ static void resolve_block(uint8_t* dst, const std::vector<uint32_t>& tok, int mi
     const uint32_t nt = (uint32_t)tok.size();
     int pos_base = 0;
     for (uint32_t t0 = 0; t0 < nt; t0 += 32) {
-        int lr[32], len[32], dist[32], adv[32], incl[32], start[32], mstart[32];
+        int lr[32], dist[32], adv[32], incl[32], start[32], mstart[32], head_win[32]; uint32_t head_bit[32];
         int run = 0;
         for (int lane = 0; lane < 32; lane++) {
-            lr[lane] = len[lane] = dist[lane] = adv[lane] = 0;
+            lr[lane] = dist[lane] = adv[lane] = 0; bool is_match = false;
             const uint32_t t = t0 + lane;
             if (t < nt) {
                 const uint32_t w = tok[t];
                 lr[lane] = (int)(w >> 23);
                 if (lr[lane] == (int)kTokSkip) { lr[lane] = (int)(w & 0x7fffffu); adv[lane] = lr[lane]; }
-                else { len[lane] = (int)(w & 0xffu) + 3; dist[lane] = (int)((w >> 8) & 0x7fffu) + 1; adv[lane] = lr[lane] + len[lane]; }
+                else { dist[lane] = (int)((w >> 8) & 0x7fffu) + 1; adv[lane] = lr[lane] + (int)(w & 0xffu) + 3; is_match = true; }
             }
             run += adv[lane]; incl[lane] = run;
-            start[lane] = pos_base + incl[lane] - adv[lane]; mstart[lane] = start[lane] + lr[lane];
+            start[lane] = pos_base + incl[lane] - adv[lane]; mstart[lane] = is_match ? start[lane] + lr[lane] : 0x7fffffff;
         }
         const int total = incl[31], hi = pos_base + total;
-        int before = 0;
-        for (int wb = ((pos_base + mis) & ~31) - mis; wb < hi; wb += 32) {
+        const int wb0 = ((pos_base + mis) & ~31) - mis;
+        for (int lane = 0; lane < 32; lane++) { head_win[lane] = adv[lane] > 0 ? (start[lane] - wb0) >> 5 : -1; head_bit[lane] = 1u << ((start[lane] - wb0) & 31); }
+        int before = 0, j = 0;
+        for (int wb = wb0; wb < hi; wb += 32, j++) {
             uint32_t heads = 0;
-            for (int lane = 0; lane < 32; lane++) if (adv[lane] > 0 && start[lane] >= wb && start[lane] < wb + 32) heads |= 1u << (start[lane] - wb);
-            bool pend[32]; int src[32];
+            for (int lane = 0; lane < 32; lane++) if (head_win[lane] == j) heads |= head_bit[lane];
+            bool far[32], near[32]; int src[32]; uint8_t v[32];
             for (int lane = 0; lane < 32; lane++) {
                 const uint32_t le = 0xffffffffu >> (31 - lane);
                 const int p = wb + lane, m = before + __builtin_popcount(heads & le) - 1;
                 const int ms = mstart[m & 31], md = dist[m & 31];
-                pend[lane] = p >= pos_base && p < hi && m >= 0 && md > 0 && p >= ms;
+                const int k = p - ms;
+                const bool is_copy = (uint32_t)(p - pos_base) < (uint32_t)total && k >= 0;
                 src[lane] = p - md;
-                if (pend[lane] && p - ms >= md) src[lane] = ms - md + (p - ms) % md;
+                if (is_copy && k >= md) src[lane] = ms - md + k % md;
+                far[lane] = is_copy && src[lane] < wb; near[lane] = is_copy && src[lane] >= wb;
+                if (far[lane]) v[lane] = dst[src[lane]];
             }
             before += __builtin_popcount(heads);
+            for (int lane = 0; lane < 32; lane++) if (far[lane]) dst[wb + lane] = v[lane];
             for (;;) {
                 uint32_t done = 0;
-                for (int lane = 0; lane < 32; lane++) if (!pend[lane]) done |= 1u << lane;
+                for (int lane = 0; lane < 32; lane++) if (!near[lane]) done |= 1u << lane;
                 if (done == 0xffffffffu) break;
-                uint8_t v[32]; bool ready[32];
-                for (int lane = 0; lane < 32; lane++) {
-                    ready[lane] = pend[lane] && (src[lane] < wb || ((done >> (src[lane] - wb)) & 1u));
-                    if (ready[lane]) v[lane] = dst[src[lane]];
-                }
-                for (int lane = 0; lane < 32; lane++) if (ready[lane]) { dst[wb + lane] = v[lane]; pend[lane] = false; }
+                bool ready[32];
+                for (int lane = 0; lane < 32; lane++) { ready[lane] = near[lane] && ((done >> (src[lane] - wb)) & 1u); if (ready[lane]) v[lane] = dst[src[lane]]; }
+                for (int lane = 0; lane < 32; lane++) if (ready[lane]) { dst[wb + lane] = v[lane]; near[lane] = false; }
             }
         }
         pos_base = hi;
