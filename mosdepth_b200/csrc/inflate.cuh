@@ -26,8 +26,8 @@
 //   K1b lz77_resolve_kernel -- ONE WARP PER BLOCK.  32 tokens per batch (warp scan -> output offsets); the batch's
 //       output range is walked in 32-byte windows, one output byte per lane: a position-indexed bit mask of token
 //       starts (redux.or) + popc gives every byte its token, match bytes load dst[p - dist] and store dst[p]
-//       (one 32-byte sector per store instruction).  Bytes whose source lies inside their own window wait for it
-//       (ballot rounds; period folding for dist < len).
+//       (one 32-byte sector per store instruction).  Bytes whose source lies inside their own window find their
+//       root byte by pointer doubling over shuffles (5 steps; period folding for dist < len).
 #pragma once
 #include "inflate_core.cuh"
 
@@ -38,10 +38,16 @@ constexpr int kDecThreads = 32;             // one warp per CTA
 constexpr int kDecCtasPerSm = 9;
 constexpr int kBurst = 256;                 // symbol iterations between phase re-synchronisations
 constexpr int kScratchWords = 32;           // cnt[16] offs[16]
-constexpr size_t kDecSmem = (size_t)kLaneHw * 32 * 2 + kScratchWords * 4;
+constexpr int kRingWords = 16;              // compressed words staged per lane
+constexpr size_t kDecSmem = (size_t)kLaneHw * 32 * 2 + kRingWords * 32 * 4 + kScratchWords * 4;
 static_assert(kDecCtasPerSm * (kDecSmem + 1024) <= 233472, "9 decoder CTAs must fit one SM's shared memory");
 
 __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// output of K1a is written once and read by another kernel: streaming stores, so that the few KB of L1 left beside the
+// tables keep the compressed words (at full occupancy the L1 hit rate of the refill loads was 1 %, profiles/README.md)
+MSD_D void st_stream_u8(uint8_t* p, uint32_t v) { asm volatile("st.global.cs.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+MSD_D void st_stream_u32(uint32_t* p, uint32_t v) { asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // one lane's table region: halfword i at base[i * 32]
 struct LaneMem {
@@ -53,31 +59,46 @@ struct LaneMem {
     MSD_D void st8(uint32_t b, uint32_t v) const { reinterpret_cast<uint8_t*>(base + (b >> 1) * 32)[b & 1] = (uint8_t)v; }
 };
 
-// per-lane bit reader: 64-bit buffer, the next two compressed words prefetched (a refill right after a refill -- a
-// long lit/len code followed by its distance -- must not wait for a load issued a few instructions earlier)
+// per-lane bit reader.  64-bit bit buffer; the next two compressed words wait in registers (a refill right after a
+// refill -- a long lit/len code followed by its distance -- must not wait for a load issued a few instructions earlier).
+// The words come from a 16-word ring per lane in shared memory that is topped up 16 bytes at a time: one 128-bit global
+// load per 4 words, issued three 16-byte chunks ahead and parked in four registers until the lane enters the next
+// chunk.  (r1g/r1h read the stream with one 32-bit global load per word: with 214 KB of the SM's 256 KB carved out as
+// shared memory the L1 hit rate of those loads was 1 %, every word cost an L2 round trip that the slowest lane of the
+// warp exposed, 39 % of all stall samples; profiles/README.md.)
 struct BitReader {
     uint64_t bb;
     int bc;
     uint32_t widx;    // index of the word held in a0 == words already shifted into bb
-    uint32_t a0, a1;
-    MSD_D void seed(const uint32_t* __restrict__ words, uint32_t wlast, uint32_t byte_pos) {
-        bb = 0; bc = 0; widx = byte_pos >> 2;
-        a0 = __ldg(words + min(widx, wlast)); a1 = __ldg(words + min(widx + 1, wlast));
-        refill(words, wlast); drop((int)(byte_pos & 3u) * 8); refill(words, wlast);
+    uint32_t a0, a1;  // words widx, widx + 1
+    uint32_t p0, p1, p2, p3;   // chunk (widx / 4) + 3, in flight or landed, not yet in the ring
+    static MSD_D uint32_t ring_ld(const uint32_t* ring, uint32_t w) { return ring[(w & 15u) * 32]; }
+    static MSD_D void ring_st(uint32_t* ring, uint32_t chunk, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+        uint32_t* r = ring + (chunk & 3u) * 128;
+        r[0] = x; r[32] = y; r[64] = z; r[96] = w;
     }
-    MSD_D void refill(const uint32_t* __restrict__ words, uint32_t wlast) {
-        const bool need = bc <= 32;
-        if (need) { bb |= (uint64_t)a0 << bc; bc += 32; widx++; a0 = a1; }
-        // The load is written as a predicated PTX instruction whose destination IS a1: left to the compiler, the
-        // conditional `a1 = __ldg(...)` became a load into a temporary plus a move in the same iteration, which put
-        // the full load latency of the slowest lane on every iteration (39 % of all stall samples, profiles/README.md).
-        // Now the first reader of the loaded word is the next refill's `a0 = a1`.
-        const uint32_t* addr = words + min(widx + 1, wlast);
-        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}" : "+r"(a1) : "l"(addr), "r"((uint32_t)need));
-        // In lock step an iteration lasts as long as its slowest lane, and with ~10 lanes refilling per iteration one of
-        // them crosses into a new 32-byte sector most of the time: pull the sector after next into L1 (no destination
-        // register, so nothing waits on it); its first word is loaded 8 refills from here.
-        if (need) asm volatile("prefetch.global.L1 [%0];" ::"l"(words + min(widx + 9, wlast)));
+    MSD_D void seed(const uint4* __restrict__ chunks, uint32_t clast, uint32_t* ring, uint32_t byte_pos) {
+        bb = 0; bc = 0; widx = byte_pos >> 2;
+        const uint32_t c0 = widx >> 2;
+#pragma unroll
+        for (uint32_t i = 0; i < 3; i++) { const uint4 v = __ldg(chunks + min(c0 + i, clast)); ring_st(ring, c0 + i, v.x, v.y, v.z, v.w); }
+        { const uint4 v = __ldg(chunks + min(c0 + 3, clast)); p0 = v.x; p1 = v.y; p2 = v.z; p3 = v.w; }
+        a0 = ring_ld(ring, widx); a1 = ring_ld(ring, widx + 1);
+        refill(chunks, clast, ring); drop((int)(byte_pos & 3u) * 8); refill(chunks, clast, ring);
+    }
+    MSD_D void refill(const uint4* __restrict__ chunks, uint32_t clast, uint32_t* ring) {
+        if (bc <= 32) {
+            bb |= (uint64_t)a0 << bc; bc += 32; widx++;
+            a0 = a1;
+            const bool entered = (widx & 3u) == 0;          // first word of a new chunk c: park chunk c + 2, fetch c + 3
+            if (entered) ring_st(ring, (widx >> 2) + 2, p0, p1, p2, p3);
+            // predicated PTX load whose destinations ARE p0..p3: left to the compiler a conditional load becomes a load
+            // into temporaries plus moves in the same iteration, i.e. a wait for the full L2 latency
+            const uint4* addr = chunks + min((widx >> 2) + 3, clast);
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+                         : "+r"(p0), "+r"(p1), "+r"(p2), "+r"(p3) : "l"(addr), "r"((uint32_t)entered));
+            a1 = ring_ld(ring, widx + 1);
+        }
     }
     MSD_D uint32_t lo() const { return (uint32_t)bb; }
     MSD_D void drop(int n) { bb >>= n; bc -= n; }
@@ -90,13 +111,10 @@ struct BitReader {
 // its bit 15 says c >= limit.  8 subtractions, 8 shift+mask-or's into two accumulators, one popc: short chains.
 MSD_D uint32_t canon_len_minus1(uint32_t c, const uint32_t (&limp)[8]) {
     const uint32_t cc = c * 0x10001u + 0x80008000u;
-    uint32_t acc0 = 0, acc1 = 0;
+    uint32_t t[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const uint32_t t = ((cc - limp[j]) >> j) & (0x80008000u >> j);
-        if (j & 1) acc1 |= t; else acc0 |= t;
-    }
-    return (uint32_t)__popc(acc0 | acc1);
+    for (int j = 0; j < 8; j++) t[j] = ((cc - limp[j]) >> j) & (0x80008000u >> j);
+    return (uint32_t)__popc(((t[0] | t[1] | t[2]) | (t[3] | t[4] | t[5])) | (t[6] | t[7]));
 }
 
 // Build the tables of lane `X` with all 32 lanes.  XM: X's region (same pointer in every lane).  Code lengths are
@@ -147,6 +165,7 @@ MSD_D uint32_t coop_build(const LaneMem XM, uint32_t* scratch, int hlit, int hdi
 #pragma unroll
             for (int j = 0; j < 8; j++) llim[j] = lp[j];
         }
+        if (lane == 16) { XM.st16(kLitBaseHw + 16, kLitBadSlot); XM.st16(kLitSymHw + kLitBadSlot, kEntBad); }
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 9; j++) if (l[j]) XM.st16(kLitSymHw + offs[l[j]] + rank[j], lit_entry_of((uint32_t)(lane + 32 * j)));
@@ -177,6 +196,7 @@ MSD_D uint32_t coop_build(const LaneMem XM, uint32_t* scratch, int hlit, int hdi
 #pragma unroll
             for (int j = 0; j < 8; j++) dlim[j] = lp[j];
         }
+        if (lane == 16) { XM.st16(kDistBaseHw + 16, kDistBadSlot); XM.st16(kDistSymHw + kDistBadSlot, kDistNibBad << 4); }
         __syncwarp();
         if (dl) XM.st16(kDistSymHw + offs[dl] + r, dist_entry_of((uint32_t)lane));
         __syncwarp();
@@ -196,15 +216,16 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
     constexpr unsigned full = 0xffffffffu;
     const int lane = threadIdx.x;
     const LaneMem M{smem16 + lane};
-    uint32_t* const scratch = reinterpret_cast<uint32_t*>(smem16 + kLaneHw * 32);
+    uint32_t* const ring = reinterpret_cast<uint32_t*>(smem16 + kLaneHw * 32) + lane;   // word w of this lane: ring[(w & 15) * 32]
+    uint32_t* const scratch = reinterpret_cast<uint32_t*>(smem16 + kLaneHw * 32) + kRingWords * 32;
 
     int phase = kPhNeed, b = 0, bfinal = 0, hlit = 0, hdist = 0;
-    const uint32_t* __restrict__ words = nullptr;
+    const uint4* __restrict__ chunks = nullptr;   // the block's DEFLATE stream from the 16-byte boundary at or before its first byte
     uint8_t* __restrict__ dst = nullptr;
     uint32_t* __restrict__ tok = nullptr;   // this block's token list
     uint32_t ntok = 0;
-    uint32_t wlast = 0, total_words = 0, isize = 0, lead = 0, clen = 0, outp = 0, run_base = 0, err = 0;
-    BitReader br; br.bb = 0; br.bc = 0; br.widx = 0; br.a0 = 0; br.a1 = 0;
+    uint32_t clast = 0, total_words = 0, isize = 0, lead = 0, clen = 0, outp = 0, run_base = 0, err = 0;
+    BitReader br; br.bb = 0; br.bc = 0; br.widx = 0; br.a0 = 0; br.a1 = 0; br.p0 = br.p1 = br.p2 = br.p3 = 0;
     uint32_t llim[8], dlim[8];     // per-length limits of the two canonical codes, packed two per register
 #pragma unroll
     for (int k = 0; k < 8; k++) { llim[k] = 0; dlim[k] = 0; }
@@ -223,13 +244,14 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
             if (b >= n_blocks) phase = kPhDone;
             else {
                 const BlockDesc bd = blocks[b];
-                lead = (uint32_t)(bd.src & 3); clen = bd.clen; isize = bd.isize;
-                words = reinterpret_cast<const uint32_t*>(comp + (bd.src - lead));
-                total_words = max((lead + clen + 3) / 4, 1u); wlast = total_words - 1;
+                const uint8_t* first = comp + bd.src;
+                lead = (uint32_t)((uintptr_t)first & 15u); clen = bd.clen; isize = bd.isize;
+                chunks = reinterpret_cast<const uint4*>(first - lead);
+                total_words = (lead + clen + 3) / 4; clast = (lead + clen + 15) / 16; if (clast) clast--;
                 dst = out + bd.dst;
                 tok = tokens + (size_t)b * kTokenCap; ntok = 0;
                 outp = 0; run_base = 0; err = 0; bfinal = 0;
-                br.seed(words, wlast, lead);
+                br.seed(chunks, clast, ring, lead);
                 phase = kPhHeader;
             }
         }
@@ -237,23 +259,23 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
 
         // ---- DEFLATE block headers (lanes in this phase run together) ------------------------------------------------------
         if (phase == kPhHeader) {
-            br.refill(words, wlast);
+            br.refill(chunks, clast, ring);
             if (br.widx > total_words + 4u) err = kTruncated;
             bfinal = (int)br.take(1);
             const int btype = (int)br.take(2);
             if (err) {
             } else if (btype == 0) {
                 br.drop(br.bc & 7);
-                br.refill(words, wlast);
+                br.refill(chunks, clast, ring);
                 const uint32_t len = br.take(16), nlen = br.take(16);
                 const uint32_t sp = br.widx * 4u - (uint32_t)br.bc / 8u;   // byte index in the aligned stream
                 if ((len ^ 0xffffu) != nlen || sp + len > lead + clen) err = kBadStored;
                 else if (outp + len > isize) err = kOverflow;
                 else {
-                    const uint8_t* sb = reinterpret_cast<const uint8_t*>(words) + sp;
+                    const uint8_t* sb = reinterpret_cast<const uint8_t*>(chunks) + sp;
                     for (uint32_t k = 0; k < len; k++) dst[outp + k] = sb[k];
                     outp += len;                                            // stored bytes count as literals of the next token
-                    br.seed(words, wlast, sp + len);
+                    br.seed(chunks, clast, ring, sp + len);
                     if (bfinal) phase = kPhFinish;
                 }
             } else if (btype == 1) {
@@ -267,7 +289,7 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
                 if (hlit > 286 || hdist > 30) err = kBadCodeLengths;
                 // the 19 code-length-code lengths, 3 bits each, packed; counts 5 bits x 8; next codes 8 bits x 8
                 uint64_t clp = 0;
-                for (int i = 0; i < hclen; i++) { br.refill(words, wlast); clp |= (uint64_t)br.take(3) << (3 * c_cl_order[i]); }
+                for (int i = 0; i < hclen; i++) { br.refill(chunks, clast, ring); clp |= (uint64_t)br.take(3) << (3 * c_cl_order[i]); }
                 uint64_t cntp = 0;
                 for (int s = 0; s < 19; s++) cntp += 1ull << (5 * (int)((clp >> (3 * s)) & 7));
                 cntp &= ~31ull;
@@ -293,7 +315,7 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
                     const int total = hlit + hdist;
                     int idx = 0;
                     while (idx < total) {
-                        br.refill(words, wlast);
+                        br.refill(chunks, clast, ring);
                         const uint32_t e = M.ld8(kClTabByte + (br.lo() & 127u));
                         const uint32_t q = e & 7u, sym = e >> 3;
                         if (!q) { err = kBadCodeLengths; break; }
@@ -334,39 +356,38 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
 #pragma unroll 1
             for (int it = 0; it < 32; it++) {
                 if (phase == kPhSym) {
-                    br.refill(words, wlast);
+                    br.refill(chunks, clast, ring);
                     uint32_t lo = br.lo();
                     uint32_t c = __brev(lo) >> 17;
-                    uint32_t l1 = canon_len_minus1(c, llim);                       // code length - 1
+                    uint32_t l1 = canon_len_minus1(c, llim);                       // code length - 1 (15: no such code)
                     uint32_t idx = (uint32_t)(M.lds16(kLitBaseHw + 1 + l1) + (int)(c >> ((14u - l1) & 31u)));
-                    const uint32_t e = M.ld16(kLitSymHw + min(idx, 287u));
-                    const uint32_t nib = (l1 < 15u) ? ((e >> 4) & 15u) : kNibBad;
-                    const uint32_t x = nib < 8u ? nib : 0u;                        // extra bits of a length code
+                    const uint32_t e = M.ld16(kLitSymHw + min(idx, (uint32_t)kLitBadSlot));
+                    const uint32_t x = (e >> 4) & 7u;                              // extra bits of a length code
                     const uint32_t ext = (lo >> (l1 + 1)) & ((1u << x) - 1u);
                     br.drop((int)(l1 + 1 + x));
-                    if (nib == kNibLit) {
-                        if (outp < isize) { dst[outp] = (uint8_t)(e >> 8); outp++; }
+                    if ((e & 0x83u) == kEntNotLen) {                               // literal
+                        if (outp < isize) { st_stream_u8(dst + outp, e >> 8); outp++; }
                         else err = kOverflow;
-                    } else if (nib >= 8u) {
-                        if (nib == kNibEob) phase = bfinal ? kPhFinish : kPhHeader;
+                    } else if (e & kEntNotLen) {
+                        if (e == kEntEob) phase = bfinal ? kPhFinish : kPhHeader;
                         else err = kBadSymbol;
                     } else {
                         const uint32_t len = 3u + (e >> 8) + ext;
-                        br.refill(words, wlast);
+                        br.refill(chunks, clast, ring);
                         lo = br.lo();
                         c = __brev(lo) >> 17;
                         l1 = canon_len_minus1(c, dlim);
                         idx = (uint32_t)(M.lds16(kDistBaseHw + 1 + l1) + (int)(c >> ((14u - l1) & 31u)));
-                        const uint32_t d = M.ld16(kDistSymHw + min(idx, 29u));
-                        const uint32_t dx = (l1 < 15u) ? ((d >> 4) & 15u) : kDistNibBad;
+                        const uint32_t d = M.ld16(kDistSymHw + min(idx, (uint32_t)kDistBadSlot));
+                        const uint32_t dx = (d >> 4) & 15u;
                         const uint32_t dist = 1u + (((d >> 8) & 3u) << dx) + ((lo >> (l1 + 1)) & ((1u << dx) - 1u));
                         br.drop((int)(l1 + 1 + dx));
                         if (dx == kDistNibBad || dist > outp) err = kBadDistance;
                         else if (outp + len > isize) err = kOverflow;
                         else {
                             uint32_t lit_run = outp - run_base;
-                            if (lit_run > 510u) { tok[ntok++] = (kTokSkip << 23) | lit_run; lit_run = 0; }
-                            tok[ntok++] = make_token(lit_run, len, dist);
+                            if (lit_run > 510u) { st_stream_u32(tok + ntok++, (kTokSkip << 23) | lit_run); lit_run = 0; }
+                            st_stream_u32(tok + ntok++, make_token(lit_run, len, dist));
                             outp += len; run_base = outp;
                         }
                     }
@@ -380,8 +401,11 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
 }
 
 // K1b.  One warp per BGZF block: copies every match of the block's token list; literals are already in place.
+// A batch is 31 tokens in lanes 1..31 (lane 0 is a sentinel "no token"), so that a byte's token index -- the number of
+// token starts at or before it -- is used as a shuffle lane directly.
 constexpr int kResolveWarps = 4;
 constexpr int kResolveCtasPerSm = 16;
+constexpr int kResolveBatch = 31;
 
 __global__ void __launch_bounds__(kResolveWarps * 32, kResolveCtasPerSm)
 lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_blocks, uint32_t* __restrict__ ticket,
@@ -395,15 +419,16 @@ lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_bl
         b = __shfl_sync(full, b, 0);
         if (b >= n_blocks) return;
         uint8_t* dst = out + blocks[b].dst;
+        asm volatile("" : "+l"(dst));                  // keep the block base as ONE 64-bit register pair
         const int mis = (int)((uintptr_t)dst & 31u);
         const uint32_t* __restrict__ tok = tokens + (size_t)b * kTokenCap;
-        const uint32_t nt = n_tokens[b];
+        const int nt = (int)n_tokens[b];
         int pos_base = 0;
-        uint32_t w_next = lane < (int)nt ? __ldg(tok + lane) : 0u;
-        for (uint32_t t0 = 0; t0 < nt; t0 += 32) {
+        uint32_t w_next = (lane >= 1 && lane - 1 < nt) ? __ldg(tok + lane - 1) : 0u;
+        for (int t0 = 0; t0 < nt; t0 += kResolveBatch) {
             const uint32_t w = w_next;
-            const bool have = t0 + lane < nt;
-            { const uint32_t tn = t0 + 32 + lane; w_next = tn < nt ? __ldg(tok + tn) : 0u; }   // next batch's tokens: in flight during this one
+            const bool have = lane >= 1 && t0 + lane - 1 < nt;
+            { const int tn = t0 + kResolveBatch + lane - 1; w_next = (lane >= 1 && tn < nt) ? __ldg(tok + tn) : 0u; }   // next batch: in flight during this one
             int lr = 0, dist = 0, adv = 0;
             bool is_match = false;
             if (have) {
@@ -416,40 +441,39 @@ lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_bl
             for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, incl, o); if (lane >= o) incl += y; }
             const int total = __shfl_sync(full, incl, 31);
             const int start = pos_base + incl - adv;                 // first output byte of this token (its literals)
-            const int mstart = is_match ? start + lr : 0x7fffffff;   // first byte of its match
+            const int mstart = is_match ? start + lr : 0x3fffffff;   // first byte of its match (sentinel / skip: never)
             const int hi = pos_base + total;
             const int wb0 = ((pos_base + mis) & ~31) - mis;          // windows are 32-byte aligned in memory
             const int head_win = adv > 0 ? (start - wb0) >> 5 : -1;  // window in which this token starts
             const uint32_t head_bit = 1u << ((start - wb0) & 31);
             int before = 0;                                          // tokens of the batch that start before the window
             int j = 0;
-            for (int wb = wb0; wb < hi; wb += 32, j++) {
+            uint8_t* pp = dst + wb0 + lane;                          // this lane's byte of the window
+            for (int wb = wb0; wb < hi; wb += 32, j++, pp += 32) {
                 const uint32_t heads = __reduce_or_sync(full, head_win == j ? head_bit : 0u);
-                const int m = before + __popc(heads & le) - 1;      // this byte's token (-1: before the batch)
+                const int m = before + __popc(heads & le);          // lane that holds this byte's token (0: none yet)
                 before += __popc(heads);
-                const int ms = __shfl_sync(full, mstart, m & 31);
-                const int md = __shfl_sync(full, dist, m & 31);
+                const int ms = __shfl_sync(full, mstart, m);
+                const int md = __shfl_sync(full, dist, m);
                 const int p = wb + lane;
                 const int k = p - ms;
-                const bool is_copy = (uint32_t)(p - pos_base) < (uint32_t)total && k >= 0;
-                int src = p - md;
-                if (is_copy && k >= md) src = ms - md + k % md;     // dist < len: fold onto the first period
-                const bool far = is_copy && src < wb;               // source lies before this window: final already
-                bool near = is_copy && src >= wb;                   // source is a byte of this window
+                const bool is_copy = k >= 0 && p < hi;
+                int back = md;                                       // source = p - back
+                if (is_copy && k >= md) back = k - k % md + md;      // dist < len: fold onto the first period
+                const bool far = is_copy && back > lane;            // source lies before this window: final already
+                const bool near = is_copy && back <= lane;          // source is a byte of this window
                 uint8_t v = 0;
-                if (far) v = dst[src];
-                const bool any_near = __any_sync(full, near);
-                if (far) dst[p] = v;
-                if (any_near) {
-                    __syncwarp();
-                    uint32_t done = __ballot_sync(full, !near);
-                    while (done != full) {
-                        const bool ready = near && ((done >> (src - wb)) & 1u);
-                        if (ready) { dst[p] = dst[src]; near = false; }
-                        __syncwarp();
-                        done = __ballot_sync(full, !near);
-                    }
+                if (far) v = *(pp - back);
+                if (__any_sync(full, near)) {
+                    // sources inside the window: every lane follows its source lane to a root (a byte that is final:
+                    // a literal, a byte of an earlier batch, or a far copy) by pointer doubling, then takes its value
+                    if (!is_copy && p >= 0 && p < hi) v = *pp;
+                    int root = near ? lane - back : lane;
+#pragma unroll
+                    for (int r = 0; r < 5; r++) root = __shfl_sync(full, root, root);
+                    v = (uint8_t)__shfl_sync(full, (int)v, root);
                 }
+                if (is_copy) *pp = v;
                 __syncwarp();
             }
             pos_base = hi;

@@ -10,28 +10,33 @@
 namespace msd {
 namespace inf {
 
-// ---- per-decoder (per-lane) shared-memory region: 352 halfwords; halfword i of lane L lives at smem16[i * 32 + L]
+// ---- per-decoder (per-lane) shared-memory region: 354 halfwords; halfword i of lane L lives at smem16[i * 32 + L]
 //      (one shift-add per lookup; at most 2-way bank conflicts, between the two lanes that share a 32-bit word) ------
-constexpr int kLitSymHw = 0;         // lit/len symbols in canonical order, as table entries (<= 288: the fixed code has 288)
-constexpr int kDistSymHw = 288;      // distance symbols in canonical order, as table entries (<= 30)
-constexpr int kLitBaseHw = 318;      // [l]: (index of the first length-l symbol - first length-l code) mod 2^16, l = 1..15
-constexpr int kDistBaseHw = 334;
-constexpr int kLaneHw = 352;         // 704 B per decoder ([l] is read with l = 16 for an invalid code: keep it inside)
+constexpr int kLitSymHw = 0;         // lit/len symbols in canonical order, as table entries (<= 288: the fixed code has
+                                     // 288), + slot 288 = "no such code"
+constexpr int kLitBadSlot = 288;
+constexpr int kDistSymHw = 289;      // distance symbols in canonical order, as table entries (<= 30), + slot 30 = "no such code"
+constexpr int kDistBadSlot = 30;
+constexpr int kLitBaseHw = 320;      // [l], l = 1..15: (index of the first length-l symbol - first length-l code), int16;
+                                     // [16] = the bad slot (a window that matches no code counts 16 limits)
+constexpr int kDistBaseHw = 337;
+constexpr int kLaneHw = 354;         // 708 B per decoder
 // while a dynamic header is being read the (dead) tables hold, as bytes (byte b = half (b & 1) of halfword b >> 1):
 constexpr int kClTabByte = 0;        // 128-entry code-length-code table, one byte per entry: sym << 3 | len
 constexpr int kLensByte = 128;       // hlit + hdist code lengths, one byte each (<= 316)
 
 // ---- table entries (16 bit; the code length is not stored: the canonical search yields it) --------------------------
-// lit/len: [7:4] 0..5 = length code with that many extra bits, 8 = literal, 9 = end of block, 10 = symbol that must
-//                not occur;  [15:8] literal byte, or length base - 3
+// lit/len: bit 7 = not a length code; [6:4] extra bits of a length code (0 otherwise, so the bits to drop are always
+//          code length + [6:4]); [1:0] 1 = end of block, 2 = symbol that must not occur; [15:8] literal byte or
+//          length base - 3
 // distance: [7:4] extra bits 0..13 (15 = symbol that must not occur), [9:8] mantissa m:
 //          distance = 1 + (m << extra) + extra bits
-constexpr uint32_t kNibLit = 8, kNibEob = 9, kNibBad = 10, kDistNibBad = 15;
+constexpr uint32_t kEntNotLen = 0x80, kEntEob = 0x81, kEntBad = 0x82, kDistNibBad = 15;
 
 MSD_HD uint32_t lit_entry_of(uint32_t sym) {
-    if (sym < 256) return (sym << 8) | (kNibLit << 4);
-    if (sym == 256) return kNibEob << 4;
-    if (sym > 285) return kNibBad << 4;
+    if (sym < 256) return (sym << 8) | kEntNotLen;
+    if (sym == 256) return kEntEob;
+    if (sym > 285) return kEntBad;
     const uint32_t idx = sym - 257;
     uint32_t base, extra;
     if (idx < 8) { base = 3 + idx; extra = 0; }

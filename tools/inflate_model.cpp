@@ -14,7 +14,7 @@
 using namespace msd::inf;
 
 struct Tables {
-    uint16_t lit_sym[288], dist_sym[30], lit_base[17], dist_base[17];
+    uint16_t lit_sym[289], dist_sym[31]; int16_t lit_base[17], dist_base[17];
     uint32_t llim[15], dlim[15];
 };
 
@@ -37,9 +37,11 @@ static uint32_t build(const uint8_t* lens, int hlit, int hdist, Tables& T) {
             if (pass) T.dist_sym[at] = (uint16_t)dist_entry_of(s); else T.lit_sym[at] = (uint16_t)lit_entry_of(s);
         }
         for (int k = 1; k < 16; k++) {
-            if (pass) { T.dlim[k - 1] = canon_limit(c, k); T.dist_base[k] = (uint16_t)canon_base(c, k); }
-            else { T.llim[k - 1] = canon_limit(c, k); T.lit_base[k] = (uint16_t)canon_base(c, k); }
+            if (pass) { T.dlim[k - 1] = canon_limit(c, k); T.dist_base[k] = (int16_t)canon_base(c, k); }
+            else { T.llim[k - 1] = canon_limit(c, k); T.lit_base[k] = (int16_t)canon_base(c, k); }
         }
+        if (pass) { T.dist_base[16] = kDistBadSlot; T.dist_sym[kDistBadSlot] = kDistNibBad << 4; }
+        else { T.lit_base[16] = kLitBadSlot; T.lit_sym[kLitBadSlot] = kEntBad; }
     }
     return status;
 }
@@ -130,22 +132,21 @@ static uint32_t decode_block(const uint8_t* comp_aligned, uint32_t lead, uint32_
             uint32_t lo = br.lo();
             uint32_t c = brev32(lo) >> 17;
             uint32_t l1 = len_minus1(c, T.llim);
-            uint32_t idx = (T.lit_base[(1 + l1) & 15] + (c >> ((14u - l1) & 31u))) & 0xffffu;
-            const uint32_t e = T.lit_sym[std::min(idx, 287u)];
-            const uint32_t nib = (l1 < 15u) ? ((e >> 4) & 15u) : kNibBad;
-            const uint32_t x = nib < 8u ? nib : 0u;
+            uint32_t idx = (uint32_t)(T.lit_base[1 + l1] + (int)(c >> ((14u - l1) & 31u)));
+            const uint32_t e = T.lit_sym[std::min(idx, (uint32_t)kLitBadSlot)];
+            const uint32_t x = (e >> 4) & 7u;
             const uint32_t ext = (lo >> (l1 + 1)) & ((1u << x) - 1u);
             br.drop((int)(l1 + 1 + x));
-            if (nib == kNibLit) { if (outp >= isize) return kOverflow; dst[outp++] = (uint8_t)(e >> 8); continue; }
-            if (nib >= 8u) { if (nib == kNibEob) break; return kBadSymbol; }
+            if ((e & 0x83u) == kEntNotLen) { if (outp >= isize) return kOverflow; dst[outp++] = (uint8_t)(e >> 8); continue; }
+            if (e & kEntNotLen) { if (e == kEntEob) break; return kBadSymbol; }
             const uint32_t len = 3u + (e >> 8) + ext;
             br.refill();
             lo = br.lo();
             c = brev32(lo) >> 17;
             l1 = len_minus1(c, T.dlim);
-            idx = (T.dist_base[(1 + l1) & 15] + (c >> ((14u - l1) & 31u))) & 0xffffu;
-            const uint32_t d = T.dist_sym[std::min(idx, 29u)];
-            const uint32_t dx = (l1 < 15u) ? ((d >> 4) & 15u) : kDistNibBad;
+            idx = (uint32_t)(T.dist_base[1 + l1] + (int)(c >> ((14u - l1) & 31u)));
+            const uint32_t d = T.dist_sym[std::min(idx, (uint32_t)kDistBadSlot)];
+            const uint32_t dx = (d >> 4) & 15u;
             const uint32_t dist = 1u + (((d >> 8) & 3u) << dx) + ((lo >> (l1 + 1)) & ((1u << dx) - 1u));
             br.drop((int)(l1 + 1 + dx));
             if (dx == kDistNibBad || dist > outp) return kBadDistance;
@@ -158,24 +159,24 @@ static uint32_t decode_block(const uint8_t* comp_aligned, uint32_t lead, uint32_
     return outp == isize ? kOk : kShort;
 }
 
-// K1b for one block, lane by lane with the kernel's window/round schedule.  `mis` plays the output misalignment.
+// K1b for one block, lane by lane with the kernel's batch/window/round schedule (31 tokens in lanes 1..31, lane 0 a
+// sentinel).  `mis` plays the output misalignment.
 static void resolve_block(uint8_t* dst, const std::vector<uint32_t>& tok, int mis) {
-    const uint32_t nt = (uint32_t)tok.size();
+    const int nt = (int)tok.size();
     int pos_base = 0;
-    for (uint32_t t0 = 0; t0 < nt; t0 += 32) {
+    for (int t0 = 0; t0 < nt; t0 += 31) {
         int lr[32], dist[32], adv[32], incl[32], start[32], mstart[32], head_win[32]; uint32_t head_bit[32];
         int run = 0;
         for (int lane = 0; lane < 32; lane++) {
             lr[lane] = dist[lane] = adv[lane] = 0; bool is_match = false;
-            const uint32_t t = t0 + lane;
-            if (t < nt) {
-                const uint32_t w = tok[t];
+            if (lane >= 1 && t0 + lane - 1 < nt) {
+                const uint32_t w = tok[t0 + lane - 1];
                 lr[lane] = (int)(w >> 23);
                 if (lr[lane] == (int)kTokSkip) { lr[lane] = (int)(w & 0x7fffffu); adv[lane] = lr[lane]; }
                 else { dist[lane] = (int)((w >> 8) & 0x7fffu) + 1; adv[lane] = lr[lane] + (int)(w & 0xffu) + 3; is_match = true; }
             }
             run += adv[lane]; incl[lane] = run;
-            start[lane] = pos_base + incl[lane] - adv[lane]; mstart[lane] = is_match ? start[lane] + lr[lane] : 0x7fffffff;
+            start[lane] = pos_base + incl[lane] - adv[lane]; mstart[lane] = is_match ? start[lane] + lr[lane] : 0x3fffffff;
         }
         const int total = incl[31], hi = pos_base + total;
         const int wb0 = ((pos_base + mis) & ~31) - mis;
@@ -184,28 +185,34 @@ static void resolve_block(uint8_t* dst, const std::vector<uint32_t>& tok, int mi
         for (int wb = wb0; wb < hi; wb += 32, j++) {
             uint32_t heads = 0;
             for (int lane = 0; lane < 32; lane++) if (head_win[lane] == j) heads |= head_bit[lane];
-            bool far[32], near[32]; int src[32]; uint8_t v[32];
+            bool far[32], near[32]; int back[32]; uint8_t v[32];
             for (int lane = 0; lane < 32; lane++) {
                 const uint32_t le = 0xffffffffu >> (31 - lane);
-                const int p = wb + lane, m = before + __builtin_popcount(heads & le) - 1;
-                const int ms = mstart[m & 31], md = dist[m & 31];
+                const int p = wb + lane, m = before + __builtin_popcount(heads & le);
+                const int ms = mstart[m], md = dist[m];
                 const int k = p - ms;
-                const bool is_copy = (uint32_t)(p - pos_base) < (uint32_t)total && k >= 0;
-                src[lane] = p - md;
-                if (is_copy && k >= md) src[lane] = ms - md + k % md;
-                far[lane] = is_copy && src[lane] < wb; near[lane] = is_copy && src[lane] >= wb;
-                if (far[lane]) v[lane] = dst[src[lane]];
+                const bool is_copy = k >= 0 && p < hi;
+                back[lane] = md;
+                if (is_copy && k >= md) back[lane] = k - k % md + md;
+                far[lane] = is_copy && back[lane] > lane; near[lane] = is_copy && back[lane] <= lane;
+                if (far[lane]) v[lane] = dst[p - back[lane]];
             }
             before += __builtin_popcount(heads);
-            for (int lane = 0; lane < 32; lane++) if (far[lane]) dst[wb + lane] = v[lane];
-            for (;;) {
-                uint32_t done = 0;
-                for (int lane = 0; lane < 32; lane++) if (!near[lane]) done |= 1u << lane;
-                if (done == 0xffffffffu) break;
-                bool ready[32];
-                for (int lane = 0; lane < 32; lane++) { ready[lane] = near[lane] && ((done >> (src[lane] - wb)) & 1u); if (ready[lane]) v[lane] = dst[src[lane]]; }
-                for (int lane = 0; lane < 32; lane++) if (ready[lane]) { dst[wb + lane] = v[lane]; near[lane] = false; }
+            bool any_near = false;
+            for (int lane = 0; lane < 32; lane++) any_near |= near[lane];
+            if (any_near) {
+                int root[32];
+                for (int lane = 0; lane < 32; lane++) {
+                    const int p = wb + lane;
+                    if (!far[lane] && !near[lane] && p >= 0 && p < hi) v[lane] = dst[p];
+                    root[lane] = near[lane] ? lane - back[lane] : lane;
+                }
+                for (int r = 0; r < 5; r++) { int nr[32]; for (int lane = 0; lane < 32; lane++) nr[lane] = root[root[lane]]; memcpy(root, nr, sizeof nr); }
+                uint8_t nv[32];
+                for (int lane = 0; lane < 32; lane++) nv[lane] = v[root[lane]];
+                memcpy(v, nv, sizeof nv);
             }
+            for (int lane = 0; lane < 32; lane++) if (far[lane] || near[lane]) dst[wb + lane] = v[lane];
         }
         pos_base = hi;
     }
