@@ -26,7 +26,8 @@
 //   K1b lz77_resolve_kernel -- ONE WARP PER BLOCK.  32 tokens per batch (warp scan -> output offsets); the batch's
 //       output range is walked in 32-byte windows, one output byte per lane: a position-indexed bit mask of token
 //       starts (redux.or) + popc gives every byte its token, match bytes load dst[p - dist] and store dst[p]
-//       (one 32-byte sector per store instruction).  Bytes whose source lies inside their own window find their
+//       (one 32-byte sector per store instruction; 64-byte windows with two bytes per lane were tried and lost:
+//       a third of them contain a source of their own and had to be redone in halves).  Bytes whose source lies inside their own window find their
 //       root byte by pointer doubling over shuffles (5 steps; period folding for dist < len).
 #pragma once
 #include "inflate_core.cuh"
@@ -481,11 +482,13 @@ lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_bl
     }
 }
 
-// K1 = K1a + K1b on one stream.  tickets: two zeroed words (K1a, K1b).
+// K1 = K1a + K1b on one stream.  tickets: two zeroed words (K1a, K1b).  comp_read (may be null) is recorded after K1a:
+// from then on the compressed chunk buffer may be overwritten.
 inline void launch_inflate(cudaStream_t s, const uint8_t* d_comp, uint8_t* d_out, const BlockDesc* d_desc, int nb, uint32_t* tickets,
-                           uint32_t* d_tokens, uint32_t* d_ntok, uint32_t* d_status, uint32_t* d_error_count) {
+                           uint32_t* d_tokens, uint32_t* d_ntok, uint32_t* d_status, uint32_t* d_error_count, cudaEvent_t comp_read) {
     const int dctas = (nb + kDecThreads - 1) / kDecThreads < kSMs * kDecCtasPerSm ? (nb + kDecThreads - 1) / kDecThreads : kSMs * kDecCtasPerSm;
     huffman_decode_kernel<<<dctas, kDecThreads, kDecSmem, s>>>(d_comp, d_out, d_desc, nb, tickets, d_tokens, d_ntok, d_status, d_error_count);
+    if (comp_read) cudaEventRecord(comp_read, s);
     const int want = (nb + kResolveWarps - 1) / kResolveWarps;
     const int rctas = want < kSMs * kResolveCtasPerSm ? want : kSMs * kResolveCtasPerSm;
     lz77_resolve_kernel<<<rctas, kResolveWarps * 32, 0, s>>>(d_out, d_desc, nb, tickets + 1, d_tokens, d_ntok);

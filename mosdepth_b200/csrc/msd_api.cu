@@ -32,6 +32,11 @@ thread_local char g_create_error[512] = "";
 
 struct Span { uint64_t beg, end; };
 
+// Chunks in flight.  One decode wave costs the same ~7 ms for 6,000 blocks as for 42,624 (the chain per block is serial), so
+// the pipeline wants several modest chunks whose decode launches share the SMs, not two big ones run back to back.
+constexpr int kSlots = 4;
+constexpr int kDescSets = 8;    // block descriptors: deeper than the slots, so that the copy stream never waits for a chunk's framing
+
 struct StageSet {              // pinned host staging for one in-flight chunk
     BlockDesc* h_desc = nullptr; uint32_t* h_rel = nullptr;
     uint8_t* h_bounce = nullptr;   // pinned copy of the compressed bytes when the source is pageable
@@ -50,7 +55,7 @@ struct ContigResult {
 struct msd_ctx {
     int device = 0;
     char err[512] = "";
-    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_inflate[2] = {nullptr, nullptr};
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_inflate[kSlots] = {};
     // input
     const uint8_t* bytes = nullptr; uint64_t n_bytes = 0; bool mapped = false; bool src_pinned = false;
     int n_targets = 0; std::vector<uint32_t> tlen; uint64_t first_voff = 0;
@@ -66,14 +71,15 @@ struct msd_ctx {
     std::vector<ContigResult> results; bool ran = false;
     // chunk buffers
     uint64_t comp_cap = 0, infl_cap = 0; uint32_t carry_cap = 0, max_blocks = 0, rec_cap = 0;
-    uint8_t* d_comp[2] = {nullptr, nullptr}; uint8_t* d_infl[2] = {nullptr, nullptr};
-    BlockDesc* d_desc[2] = {nullptr, nullptr}; uint32_t* d_rel[2] = {nullptr, nullptr};
+    uint8_t* d_comp[kSlots] = {}; uint8_t* d_infl[kSlots] = {};
+    BlockDesc* d_desc[kDescSets] = {}; uint32_t* d_rel[kDescSets] = {};
     uint32_t *d_bstart = nullptr, *d_land = nullptr, *d_count = nullptr, *d_first = nullptr, *d_cnt = nullptr, *d_recbase = nullptr, *d_recoff = nullptr;
     uint32_t *d_status = nullptr, *d_ticket = nullptr, *d_inflate_err = nullptr;
-    uint32_t* d_tokens[2] = {nullptr, nullptr}; uint32_t* d_ntok[2] = {nullptr, nullptr};   // match tokens between K1a and K1b
+    uint32_t* d_tokens[kSlots] = {}; uint32_t* d_ntok[kSlots] = {};   // match tokens between K1a and K1b
     ChunkState* d_cs = nullptr; RunCounters* d_rc = nullptr;
-    StageSet stage[2];
-    cudaEvent_t comp_free[2] = {nullptr, nullptr}, h2d_done[2] = {nullptr, nullptr}, infl_done[2] = {nullptr, nullptr}, infl_free[2] = {nullptr, nullptr};
+    StageSet stage[kDescSets];   // h_desc / h_rel per descriptor set; h_bounce in the first kSlots sets only
+    cudaEvent_t desc_free[kDescSets] = {}, bounce_free[kSlots] = {}; bool bounce_used[kSlots] = {};
+    cudaEvent_t comp_free[kSlots] = {}, h2d_done[kSlots] = {}, infl_done[kSlots] = {}, infl_free[kSlots] = {};
     // mate join (default mode only)
     MateChunk mc{}; MateTable mt{}; LiveList live[2]{}; bool mate_ready = false; uint32_t mate_slots = 0;
     // scan + queries
@@ -155,33 +161,53 @@ int setup_common(msd_ctx* ctx, int n_targets, const uint32_t* target_len, uint64
     ctx->src_pinned = (cudaPointerGetAttributes(&pa, ctx->bytes) == cudaSuccess && pa.type == cudaMemoryTypeHost);
     cudaGetLastError();
     // chunk geometry
-    ctx->comp_cap = std::min<uint64_t>(env_u64("MSD_CHUNK_COMP_MB", 768) << 20, ((ctx->n_bytes + 65536 + 255) / 256) * 256);
-    ctx->infl_cap = std::min<uint64_t>(env_u64("MSD_CHUNK_INFL_MB", 2048) << 20, std::max<uint64_t>(8ull << 20, ctx->n_bytes * 16));
+    ctx->comp_cap = std::min<uint64_t>(env_u64("MSD_CHUNK_COMP_MB", 512) << 20, ((ctx->n_bytes + 65536 + 255) / 256) * 256);
+    ctx->infl_cap = std::min<uint64_t>(env_u64("MSD_CHUNK_INFL_MB", 1600) << 20, std::max<uint64_t>(8ull << 20, ctx->n_bytes * 16));
     ctx->carry_cap = (uint32_t)std::min<uint64_t>(env_u64("MSD_CARRY_MB", 64) << 20, ctx->infl_cap);
-    ctx->max_blocks = (uint32_t)std::min<uint64_t>(env_u64("MSD_CHUNK_BLOCKS", 40000), ctx->n_bytes / 28 + 2);
+    ctx->max_blocks = (uint32_t)std::min<uint64_t>(env_u64("MSD_CHUNK_BLOCKS", 24000), ctx->n_bytes / 28 + 2);
     ctx->rec_cap = (uint32_t)((ctx->infl_cap + ctx->carry_cap) / 37 + 2);
     return 0;
+}
+
+// chunk buffers, staging and their events depend on the input size: dropped when a new input is opened and on destroy
+void free_chunk_buffers(msd_ctx* ctx) {
+    for (int k = 0; k < kDescSets; k++) {
+        dev_free(&ctx->d_desc[k]); dev_free(&ctx->d_rel[k]);
+        if (ctx->stage[k].h_desc) { cudaFreeHost(ctx->stage[k].h_desc); ctx->stage[k].h_desc = nullptr; }
+        if (ctx->stage[k].h_rel) { cudaFreeHost(ctx->stage[k].h_rel); ctx->stage[k].h_rel = nullptr; }
+        if (ctx->stage[k].h_bounce) { cudaFreeHost(ctx->stage[k].h_bounce); ctx->stage[k].h_bounce = nullptr; }
+        cudaEvent_t* evs[] = {&ctx->stage[k].free_ev, &ctx->desc_free[k]};
+        for (cudaEvent_t* e : evs) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+        ctx->stage[k].used = false;
+    }
+    for (int k = 0; k < kSlots; k++) {
+        dev_free(&ctx->d_comp[k]); dev_free(&ctx->d_infl[k]); dev_free(&ctx->d_tokens[k]); dev_free(&ctx->d_ntok[k]);
+        cudaEvent_t* evs[] = {&ctx->comp_free[k], &ctx->h2d_done[k], &ctx->infl_done[k], &ctx->infl_free[k], &ctx->bounce_free[k]};
+        for (cudaEvent_t* e : evs) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+        ctx->bounce_used[k] = false;
+    }
 }
 
 int ensure_chunk_buffers(msd_ctx* ctx) {
     if (ctx->d_infl[0]) return 0;
     int rc;
     const uint64_t infl_bytes = (uint64_t)ctx->carry_cap + ctx->infl_cap + 256;
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < kSlots; k++) {
         if ((rc = dev_alloc(ctx, &ctx->d_comp[k], ctx->comp_cap + 256))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_infl[k], infl_bytes))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->d_desc[k], ctx->max_blocks))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->d_rel[k], ctx->max_blocks + 1))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_tokens[k], (uint64_t)ctx->max_blocks * kTokenCap))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_ntok[k], ctx->max_blocks))) return rc;
         MSD_CUDA_OK(cudaMemset(ctx->d_infl[k], 0, infl_bytes));
+        cudaEvent_t* evs[] = {&ctx->comp_free[k], &ctx->h2d_done[k], &ctx->infl_done[k], &ctx->infl_free[k], &ctx->bounce_free[k]};
+        for (cudaEvent_t* e : evs) MSD_CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    for (int k = 0; k < kDescSets; k++) {
+        if ((rc = dev_alloc(ctx, &ctx->d_desc[k], ctx->max_blocks))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_rel[k], ctx->max_blocks + 1))) return rc;
         MSD_CUDA_OK(cudaMallocHost((void**)&ctx->stage[k].h_desc, sizeof(BlockDesc) * ctx->max_blocks));
         MSD_CUDA_OK(cudaMallocHost((void**)&ctx->stage[k].h_rel, sizeof(uint32_t) * (ctx->max_blocks + 1)));
-        MSD_CUDA_OK(cudaEventCreateWithFlags(&ctx->stage[k].free_ev, cudaEventDisableTiming));
-        MSD_CUDA_OK(cudaEventCreateWithFlags(&ctx->comp_free[k], cudaEventDisableTiming));
-        MSD_CUDA_OK(cudaEventCreateWithFlags(&ctx->h2d_done[k], cudaEventDisableTiming));
-        MSD_CUDA_OK(cudaEventCreateWithFlags(&ctx->infl_done[k], cudaEventDisableTiming));
-        MSD_CUDA_OK(cudaEventCreateWithFlags(&ctx->infl_free[k], cudaEventDisableTiming));
+        cudaEvent_t* evs[] = {&ctx->stage[k].free_ev, &ctx->desc_free[k]};
+        for (cudaEvent_t* e : evs) MSD_CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
     const uint32_t nb = ctx->max_blocks + 2;
     if ((rc = dev_alloc(ctx, &ctx->d_bstart, nb + 1))) return rc;
@@ -191,8 +217,8 @@ int ensure_chunk_buffers(msd_ctx* ctx) {
     if ((rc = dev_alloc(ctx, &ctx->d_cnt, nb))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_recbase, nb))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_recoff, ctx->rec_cap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_status, 2ull * ctx->max_blocks))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_ticket, 8))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_status, (uint64_t)kSlots * ctx->max_blocks))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_ticket, 2 * kSlots))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_inflate_err, 4))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_cs, 1))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_rc, 1))) return rc;
@@ -201,7 +227,7 @@ int ensure_chunk_buffers(msd_ctx* ctx) {
 
 int ensure_bounce(msd_ctx* ctx) {
     if (ctx->src_pinned || ctx->stage[0].h_bounce) return 0;
-    for (int k = 0; k < 2; k++) MSD_CUDA_OK(cudaMallocHost((void**)&ctx->stage[k].h_bounce, ctx->comp_cap + 256));
+    for (int k = 0; k < kSlots; k++) MSD_CUDA_OK(cudaMallocHost((void**)&ctx->stage[k].h_bounce, ctx->comp_cap + 256));
     return 0;
 }
 
@@ -397,7 +423,7 @@ int msd_create(int device, msd_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cudaStreamCreate failed");
     }
-    for (int k = 0; k < 2; k++) if (cudaStreamCreateWithFlags(&ctx->s_inflate[k], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cudaStreamCreate failed"); }
+    for (int k = 0; k < kSlots; k++) if (cudaStreamCreateWithFlags(&ctx->s_inflate[k], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cudaStreamCreate failed"); }
     cudaFuncSetAttribute(huffman_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecSmem);
     cudaFuncSetAttribute(huffman_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     // default filters = mosdepth defaults (-F 1796, -Q 0, no length limits, default mode)
@@ -412,19 +438,9 @@ void msd_destroy(msd_ctx* ctx) {
     cudaDeviceSynchronize();
     release_input(ctx);
     dev_free(&ctx->d_rg); dev_free(&ctx->d_arena); dev_free(&ctx->d_depth_off); dev_free(&ctx->d_tlen); dev_free(&ctx->d_nprefilter);
-    for (int k = 0; k < 2; k++) {
-        dev_free(&ctx->d_comp[k]); dev_free(&ctx->d_infl[k]); dev_free(&ctx->d_desc[k]); dev_free(&ctx->d_rel[k]); dev_free(&ctx->d_tokens[k]); dev_free(&ctx->d_ntok[k]);
-        if (ctx->stage[k].h_desc) cudaFreeHost(ctx->stage[k].h_desc);
-        if (ctx->stage[k].h_rel) cudaFreeHost(ctx->stage[k].h_rel);
-        if (ctx->stage[k].h_bounce) cudaFreeHost(ctx->stage[k].h_bounce);
-        if (ctx->stage[k].free_ev) cudaEventDestroy(ctx->stage[k].free_ev);
-        if (ctx->comp_free[k]) cudaEventDestroy(ctx->comp_free[k]);
-        if (ctx->h2d_done[k]) cudaEventDestroy(ctx->h2d_done[k]);
-        if (ctx->infl_done[k]) cudaEventDestroy(ctx->infl_done[k]);
-        if (ctx->infl_free[k]) cudaEventDestroy(ctx->infl_free[k]);
-        if (ctx->s_inflate[k]) cudaStreamDestroy(ctx->s_inflate[k]);
-        dev_free(&ctx->live[k].e); dev_free(&ctx->live[k].arena); dev_free(&ctx->live[k].n); dev_free(&ctx->live[k].arena_used);
-    }
+    free_chunk_buffers(ctx);
+    for (int k = 0; k < kSlots; k++) if (ctx->s_inflate[k]) cudaStreamDestroy(ctx->s_inflate[k]);
+    for (int k = 0; k < 2; k++) { dev_free(&ctx->live[k].e); dev_free(&ctx->live[k].arena); dev_free(&ctx->live[k].n); dev_free(&ctx->live[k].arena_used); }
     dev_free(&ctx->d_bstart); dev_free(&ctx->d_land); dev_free(&ctx->d_count); dev_free(&ctx->d_first); dev_free(&ctx->d_cnt);
     dev_free(&ctx->d_recbase); dev_free(&ctx->d_recoff); dev_free(&ctx->d_status); dev_free(&ctx->d_ticket); dev_free(&ctx->d_inflate_err);
     dev_free(&ctx->d_cs); dev_free(&ctx->d_rc);
@@ -451,18 +467,8 @@ int msd_open_mem(msd_ctx* ctx, const void* bam_bytes, uint64_t n_bytes, int n_ta
     cudaSetDevice(ctx->device);
     release_input(ctx);
     // chunk buffers depend on the input size: drop the old ones
-    for (int k = 0; k < 2; k++) { dev_free(&ctx->d_comp[k]); dev_free(&ctx->d_infl[k]); dev_free(&ctx->d_desc[k]); dev_free(&ctx->d_rel[k]);
-        if (ctx->stage[k].h_desc) { cudaFreeHost(ctx->stage[k].h_desc); ctx->stage[k].h_desc = nullptr; }
-        if (ctx->stage[k].h_rel) { cudaFreeHost(ctx->stage[k].h_rel); ctx->stage[k].h_rel = nullptr; }
-        if (ctx->stage[k].h_bounce) { cudaFreeHost(ctx->stage[k].h_bounce); ctx->stage[k].h_bounce = nullptr; }
-        if (ctx->stage[k].free_ev) { cudaEventDestroy(ctx->stage[k].free_ev); ctx->stage[k].free_ev = nullptr; }
-        if (ctx->comp_free[k]) { cudaEventDestroy(ctx->comp_free[k]); ctx->comp_free[k] = nullptr; }
-        if (ctx->h2d_done[k]) { cudaEventDestroy(ctx->h2d_done[k]); ctx->h2d_done[k] = nullptr; }
-        if (ctx->infl_done[k]) { cudaEventDestroy(ctx->infl_done[k]); ctx->infl_done[k] = nullptr; }
-        if (ctx->infl_free[k]) { cudaEventDestroy(ctx->infl_free[k]); ctx->infl_free[k] = nullptr; }
-        ctx->stage[k].used = false;
-        dev_free(&ctx->live[k].e); dev_free(&ctx->live[k].arena); dev_free(&ctx->live[k].n); dev_free(&ctx->live[k].arena_used);
-    }
+    free_chunk_buffers(ctx);
+    for (int k = 0; k < 2; k++) { dev_free(&ctx->live[k].e); dev_free(&ctx->live[k].arena); dev_free(&ctx->live[k].n); dev_free(&ctx->live[k].arena_used); }
     dev_free(&ctx->mc.cls); dev_free(&ctx->mc.qhash); dev_free(&ctx->mc.endpos); dev_free(&ctx->mc.next); dev_free(&ctx->mc.slot);
     dev_free(&ctx->mt.word); dev_free(&ctx->mt.head); dev_free(&ctx->mt.live); ctx->mate_ready = false;
     dev_free(&ctx->d_depth_off); dev_free(&ctx->d_tlen); dev_free(&ctx->d_nprefilter);
@@ -569,7 +575,7 @@ int msd_run(msd_ctx* ctx) {
     {   // the inflate streams must not run ahead of the per-run resets above
         cudaEvent_t ev_init = next_event(ctx);
         MSD_CUDA_OK(cudaEventRecord(ev_init, sc));
-        for (int k = 0; k < 2; k++) MSD_CUDA_OK(cudaStreamWaitEvent(ctx->s_inflate[k], ev_init, 0));
+        for (int k = 0; k < kSlots; k++) MSD_CUDA_OK(cudaStreamWaitEvent(ctx->s_inflate[k], ev_init, 0));
         MSD_CUDA_OK(cudaStreamWaitEvent(sx, ev_init, 0));
     }
     ContigTable ct{ctx->d_depth_off, ctx->d_tlen};
@@ -580,7 +586,9 @@ int msd_run(msd_ctx* ctx) {
     if (spans.empty()) spans.push_back({ctx->first_voff, 0});
     std::sort(spans.begin(), spans.end(), [](const Span& a, const Span& b) { return a.beg < b.beg; });
     uint64_t chunk_idx = 0;
-    const uint32_t ramp0 = (uint32_t)env_u64("MSD_RAMP0_BLOCKS", 6000), ramp1 = (uint32_t)env_u64("MSD_RAMP1_BLOCKS", 20000);
+    // when the bytes still cross PCIe: a small first chunk (the pipeline starts after ~2 ms of copy), then chunks of
+    // MSD_COPY_BLOCKS so that the serial tail behind the last byte is one modest chunk
+    const uint32_t ramp0 = (uint32_t)env_u64("MSD_RAMP0_BLOCKS", 6000), copy_blocks = (uint32_t)env_u64("MSD_COPY_BLOCKS", 16000);
     const uint8_t* F = ctx->bytes; const uint64_t N = ctx->n_bytes;
 
     for (const Span& sp : spans) {
@@ -591,14 +599,14 @@ int msd_run(msd_ctx* ctx) {
         bool first_of_span = true, span_done = false;
         while (!span_done) {
             // ---- plan one chunk (host: BSIZE chase) -------------------------------------------------------
-            const int k = (int)(chunk_idx & 1);
-            StageSet& st = ctx->stage[k];
+            const int k = (int)(chunk_idx % kSlots), kd = (int)(chunk_idx % kDescSets);
+            StageSet& st = ctx->stage[kd];
             if (st.used) MSD_CUDA_OK(cudaEventSynchronize(st.free_ev));
             uint32_t nb = 0; uint64_t comp_bytes = 0, infl = 0; const uint64_t chunk_src = pos; uint32_t total = 0; bool truncated_last = false;
             // when the compressed bytes still have to cross PCIe, the first chunks are small so that the pipeline
             // (copy k+1 | inflate k) starts after a few milliseconds instead of after a full-size copy
             const bool will_copy = !(ctx->d_staged && pos >= ctx->staged_beg && pos < ctx->staged_end);
-            const uint32_t blk_limit = !will_copy ? ctx->max_blocks : std::min<uint32_t>(ctx->max_blocks, chunk_idx == 0 ? ramp0 : chunk_idx == 1 ? ramp1 : ctx->max_blocks);
+            const uint32_t blk_limit = !will_copy ? ctx->max_blocks : std::min<uint32_t>(ctx->max_blocks, chunk_idx == 0 ? ramp0 : copy_blocks);
             while (nb < blk_limit) {
                 if (pos >= N || pos > end_c || (pos == end_c && end_u == 0)) { span_done = true; break; }
                 uint32_t xlen = 0, isize = 0;
@@ -629,25 +637,30 @@ int msd_run(msd_ctx* ctx) {
                 // descriptor src offsets assume a 4-byte aligned base: fold the misalignment into src
                 const uint32_t mis = (uint32_t)((uintptr_t)d_comp & 3u);
                 if (mis) { d_comp -= mis; for (uint32_t i = 0; i < nb; i++) st.h_desc[i].src += mis; }
-                MSD_CUDA_OK(cudaStreamWaitEvent(si, ctx->comp_free[k], 0));
-                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_desc[k], st.h_desc, sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, si));
-                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_rel[k], st.h_rel, sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, si));
+                MSD_CUDA_OK(cudaStreamWaitEvent(si, ctx->desc_free[kd], 0));
+                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_desc[kd], st.h_desc, sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, si));
+                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_rel[kd], st.h_rel, sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, si));
                 MSD_CUDA_OK(cudaEventRecord(st.free_ev, si));
             } else {
                 if ((rc = ensure_bounce(ctx))) return rc;
                 // everything this chunk needs goes through the copy stream in one batch, small descriptor copies first:
                 // a copy engine is FIFO, so a descriptor copy queued behind the NEXT chunk's bulk copy would hold this
                 // chunk's kernels back until that bulk copy ends
-                MSD_CUDA_OK(cudaStreamWaitEvent(sx, ctx->comp_free[k], 0));
-                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_desc[k], st.h_desc, sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, sx));
-                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_rel[k], st.h_rel, sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, sx));
+                MSD_CUDA_OK(cudaStreamWaitEvent(sx, ctx->desc_free[kd], 0));   // four sets: chunk k-4 is long gone
+                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_desc[kd], st.h_desc, sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, sx));
+                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_rel[kd], st.h_rel, sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, sx));
+                MSD_CUDA_OK(cudaEventRecord(st.free_ev, sx));       // h_desc and h_rel of this set are free again
+                MSD_CUDA_OK(cudaStreamWaitEvent(sx, ctx->comp_free[k], 0));     // the decode kernel of chunk k-2 has read d_comp[k]
                 cudaEvent_t h0 = next_event(ctx), h1 = next_event(ctx);
                 MSD_CUDA_OK(cudaEventRecord(h0, sx));
                 const uint8_t* srcp = F + chunk_src;
-                if (!ctx->src_pinned) { memcpy(st.h_bounce, srcp, comp_bytes); srcp = st.h_bounce; }
+                if (!ctx->src_pinned) {
+                    if (ctx->bounce_used[k]) MSD_CUDA_OK(cudaEventSynchronize(ctx->bounce_free[k]));
+                    memcpy(ctx->stage[k].h_bounce, srcp, comp_bytes); srcp = ctx->stage[k].h_bounce;
+                }
                 MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_comp[k], srcp, comp_bytes, cudaMemcpyHostToDevice, sx));
                 MSD_CUDA_OK(cudaEventRecord(h1, sx));
-                MSD_CUDA_OK(cudaEventRecord(st.free_ev, sx));       // h_desc, h_rel and h_bounce of this set are free again
+                if (!ctx->src_pinned) { MSD_CUDA_OK(cudaEventRecord(ctx->bounce_free[k], sx)); ctx->bounce_used[k] = true; }
                 MSD_CUDA_OK(cudaEventRecord(ctx->h2d_done[k], sx));
                 MSD_CUDA_OK(cudaStreamWaitEvent(si, ctx->h2d_done[k], 0));
                 times.h2d.push_back({h0, h1});
@@ -660,8 +673,8 @@ int msd_run(msd_ctx* ctx) {
             MSD_CUDA_OK(cudaStreamWaitEvent(si, ctx->infl_free[k], 0));      // consumers of the previous contents of d_infl[k] are done
             MSD_CUDA_OK(cudaMemsetAsync(ctx->d_ticket + 2 * k, 0, 8, si));
             MSD_CUDA_OK(cudaEventRecord(e0, si));
-            launch_inflate(si, d_comp, infl_buf, ctx->d_desc[k], (int)nb, ctx->d_ticket + 2 * k, ctx->d_tokens[k], ctx->d_ntok[k],
-                           ctx->d_status + (size_t)k * ctx->max_blocks, ctx->d_inflate_err);
+            launch_inflate(si, d_comp, infl_buf, ctx->d_desc[kd], (int)nb, ctx->d_ticket + 2 * k, ctx->d_tokens[k], ctx->d_ntok[k],
+                           ctx->d_status + (size_t)k * ctx->max_blocks, ctx->d_inflate_err, ctx->comp_free[k]);
             ctx->info.n_launches += 2; ctx->info.n_inflate_launches++;
             MSD_CUDA_OK(cudaEventRecord(e1, si));
             MSD_CUDA_OK(cudaEventRecord(ctx->infl_done[k], si));
@@ -669,7 +682,7 @@ int msd_run(msd_ctx* ctx) {
             MSD_CUDA_OK(cudaEventRecord(f0, sc));
             // ---- K2 framing ---------------------------------------------------------------------------------
             const int nblk = (int)nb + 1;   // + carry pseudo-block
-            frame_setup_kernel<<<(nb + 255) / 256, 256, 0, sc>>>(ctx->d_cs, ctx->d_rel[k], (int)nb, base, first_of_span ? first_uoff : 0u, total, first_of_span ? 1 : 0, ctx->d_bstart);
+            frame_setup_kernel<<<(nb + 255) / 256, 256, 0, sc>>>(ctx->d_cs, ctx->d_rel[kd], (int)nb, base, first_of_span ? first_uoff : 0u, total, first_of_span ? 1 : 0, ctx->d_bstart);
             frame_spec_kernel<<<(nblk + 127) / 128, 128, 0, sc>>>(infl_buf, ctx->d_cs, ctx->d_bstart, nblk, ctx->d_land, ctx->d_count);
             frame_link_kernel<<<1, 1024, 0, sc>>>(infl_buf, ctx->d_cs, ctx->d_bstart, nblk, ctx->d_land, ctx->d_count, ctx->d_first, ctx->d_cnt, ctx->d_recbase);
             frame_emit_kernel<<<(nblk + 127) / 128, 128, 0, sc>>>(infl_buf, ctx->d_first, ctx->d_cnt, ctx->d_recbase, nblk, ctx->d_recoff);
@@ -696,9 +709,9 @@ int msd_run(msd_ctx* ctx) {
             }
             MSD_CUDA_OK(cudaEventRecord(e3, sc));
             // unfinished tail -> front of the other inflated buffer
-            carry_copy_kernel<<<64, 256, 0, sc>>>(infl_buf, ctx->d_infl[k ^ 1], ctx->d_cs, base, ctx->carry_cap, &ctx->d_rc->error);
+            carry_copy_kernel<<<64, 256, 0, sc>>>(infl_buf, ctx->d_infl[(k + 1) % kSlots], ctx->d_cs, base, ctx->carry_cap, &ctx->d_rc->error);
             ctx->info.n_launches++;
-            MSD_CUDA_OK(cudaEventRecord(ctx->comp_free[k], sc));   // d_comp[k], d_desc[k], d_rel[k] may be overwritten from here on
+            MSD_CUDA_OK(cudaEventRecord(ctx->desc_free[kd], sc));  // d_desc[kd], d_rel[kd] may be overwritten from here on (d_comp[k]: after the decode kernel)
             MSD_CUDA_OK(cudaEventRecord(ctx->infl_free[k], sc));   // ... and so may d_infl[k]
             MSD_CUDA_OK(cudaGetLastError());
             times.inflate.push_back({e0, e1}); times.frame.push_back({f0, e2}); times.records.push_back({e2, e3});
@@ -761,6 +774,7 @@ int msd_run(msd_ctx* ctx) {
             fprintf(stderr, "[msd trace] chunk %zu: h2d %.2f..%.2f  inflate %.2f..%.2f  frame ..%.2f  records ..%.2f\n", i,
                     i < times.h2d.size() ? rel(times.h2d[i].first) : -1.f, i < times.h2d.size() ? rel(times.h2d[i].second) : -1.f,
                     rel(times.inflate[i].first), rel(times.inflate[i].second), rel(times.frame[i].second), rel(times.records[i].second));
+        fprintf(stderr, "[msd trace] chunks end %.2f  scans %.2f..%.2f  end %.2f\n", rel(ev_chunks_end), rel(s0), rel(s1), rel(ev_end));
     }
     if (!times.inflate.empty()) { float sp = 0; cudaEventElapsedTime(&sp, times.inflate.front().first, times.inflate.back().second); ctx->info.ms_inflate_span = sp; }
     ctx->info.ms_h2d = sum_ms(times.h2d); ctx->info.ms_inflate = sum_ms(times.inflate); ctx->info.ms_frame = sum_ms(times.frame); ctx->info.ms_records = sum_ms(times.records);
@@ -965,7 +979,7 @@ int64_t msd_debug_inflate(msd_ctx* ctx, const void* bgzf_bytes, uint64_t n_bytes
     cudaMemcpyAsync(d_d, desc.data(), sizeof(BlockDesc) * desc.size(), cudaMemcpyHostToDevice, sc);
     cudaMemsetAsync(d_t, 0, 16, sc);
     const int nb = (int)desc.size();
-    launch_inflate(sc, d_c, d_o, d_d, nb, d_t, d_tok, d_nt, d_s, d_t + 2);   // tickets: d_t[0], d_t[1]; error count: d_t[2]
+    launch_inflate(sc, d_c, d_o, d_d, nb, d_t, d_tok, d_nt, d_s, d_t + 2, nullptr);   // tickets: d_t[0], d_t[1]; error count: d_t[2]
     cudaError_t e = cudaGetLastError();
     uint32_t errs[2] = {0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(errs, d_t + 1, 8, cudaMemcpyDeviceToHost, sc);
