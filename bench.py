@@ -201,6 +201,7 @@ def main():
     ctx.set_targets(want)
     ctx.set_spans(begs, ends)
     ctx.set_filters(mode=m.MODE_FAST)   # -x; defaults -F 1796 -Q 0
+    ctx.prefetch_windows(args.window)   # --by 500: the host will ask for every contig's windows
     g_ptr, r_ptr, n_bins, s_ptr = ctx.totals_device()
 
     class DevView:

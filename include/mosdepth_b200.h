@@ -124,6 +124,11 @@ int msd_contig_stats(msd_ctx *ctx, int tid, msd_depth_stat *chrom_stat, int64_t 
  * region_dist[512]: bin min(toInt(mean), 511) per window (:737-739).  Returns n_windows written;
  * value_cap is the capacity of value_out (MSD_EINVAL if too small; msd_n_windows() gives the count). */
 int64_t msd_n_windows(uint32_t tlen, uint32_t window);
+/* Optional hint, call before msd_run(): the host is going to ask msd_windows(tid, window, use_median = 0) for every
+ * contig (mosdepth --by <window>, the loop :720-741 inside `for target in sub_targets` :691).  msd_run() then computes
+ * the windows of all contigs in one launch and msd_windows() returns them from pinned host memory -- same values, no
+ * launch/sync latency per contig.  window = 0 switches the hint off.  Nothing in the reference corresponds to it. */
+int msd_prefetch_windows(msd_ctx *ctx, uint32_t window);
 int64_t msd_windows(msd_ctx *ctx, int tid, uint32_t window, int use_median, double *value_out, int64_t value_cap,
                     msd_depth_stat *region_stat, int64_t *region_dist512);
 

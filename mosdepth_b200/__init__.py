@@ -22,7 +22,7 @@ MODE_DEFAULT, MODE_FAST, MODE_FRAGMENT = 0, 1, 2
 EXPORTS = [
     "msd_abi_version", "msd_create", "msd_destroy", "msd_last_error", "msd_open", "msd_open_mem", "msd_stage",
     "msd_set_spans", "msd_set_targets", "msd_set_filters", "msd_run", "msd_last_run_info", "msd_contig_records",
-    "msd_contig_stats", "msd_n_windows", "msd_windows", "msd_regions", "msd_per_base_runs", "msd_quantized_runs",
+    "msd_contig_stats", "msd_n_windows", "msd_prefetch_windows", "msd_windows", "msd_regions", "msd_per_base_runs", "msd_quantized_runs",
     "msd_totals_device", "msd_totals_reset", "msd_mark", "msd_elapsed_ms", "msd_launch_count", "msd_debug_inflate", "msd_debug_depth", "msd_debug_cumsum",
 ]
 
@@ -75,6 +75,7 @@ def load_library():
     lib.msd_contig_records.argtypes = [p, i32, C.POINTER(i64)]
     lib.msd_contig_stats.argtypes = [p, i32, C.POINTER(DepthStat), p, i64, C.POINTER(i64)]
     lib.msd_n_windows.argtypes = [u32, u32]; lib.msd_n_windows.restype = i64
+    lib.msd_prefetch_windows.argtypes = [p, u32]
     lib.msd_windows.argtypes = [p, i32, u32, i32, p, i64, C.POINTER(DepthStat), p]; lib.msd_windows.restype = i64
     lib.msd_regions.argtypes = [p, i32, i64, p, p, i32, p, C.POINTER(DepthStat), p, i64, C.POINTER(i64), p, i32, p]
     lib.msd_per_base_runs.argtypes = [p, i32, C.POINTER(p), C.POINTER(p), C.POINTER(p), C.POINTER(i64)]
@@ -189,6 +190,10 @@ class Context:
         dist = np.zeros(n.value, dtype=np.int64)
         self._check(self.lib.msd_contig_stats(self.h, tid, C.byref(st), _ptr(dist), dist.size, C.byref(n)))
         return st, dist
+
+    def prefetch_windows(self, window):
+        """Hint: msd_run() computes the windows of every contig in one launch; windows() then reads the host cache."""
+        self._check(self.lib.msd_prefetch_windows(self.h, int(window)))
 
     def windows(self, tid, window, use_median=False):
         nw = self.lib.msd_n_windows(int(self.tlen[tid]), window)

@@ -94,6 +94,11 @@ struct msd_ctx {
     uint32_t* d_tile_count = nullptr; unsigned long long* d_tile_base = nullptr; uint64_t run_tile_cap = 0; unsigned long long* d_run_total = nullptr;
     // generic scratch
     void* d_scratch = nullptr; uint64_t scratch_cap = 0;
+    // msd_prefetch_windows: every contig's windows computed by one launch at the end of msd_run, results cached on the host
+    uint32_t pf_window = 0; bool pf_valid = false; uint64_t pf_cap_windows = 0; int pf_cap_contigs = 0;
+    double *d_pf_values = nullptr, *h_pf_values = nullptr; RegionAccum *d_pf_acc = nullptr, *h_pf_acc = nullptr;
+    unsigned long long *d_pf_dist = nullptr, *h_pf_dist = nullptr; WinContig *d_pf_table = nullptr, *h_pf_table = nullptr;
+    std::vector<int> pf_slot;   // tid -> row of the tables (-1: not prefetched)
     msd_run_info info{};
     uint64_t launches = 0; cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
@@ -453,6 +458,8 @@ void msd_destroy(msd_ctx* ctx) {
     if (ctx->h_run_stop) cudaFreeHost(ctx->h_run_stop);
     if (ctx->h_run_val) cudaFreeHost(ctx->h_run_val);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    dev_free(&ctx->d_pf_values); dev_free(&ctx->d_pf_acc); dev_free(&ctx->d_pf_dist); dev_free(&ctx->d_pf_table);
+    if (ctx->h_pf_values) cudaFreeHost(ctx->h_pf_values); if (ctx->h_pf_acc) cudaFreeHost(ctx->h_pf_acc); if (ctx->h_pf_dist) cudaFreeHost(ctx->h_pf_dist); if (ctx->h_pf_table) cudaFreeHost(ctx->h_pf_table);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto e : ctx->marks) if (e) cudaEventDestroy(e);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
@@ -544,6 +551,66 @@ int msd_stage(msd_ctx* ctx) {
     return MSD_OK;
 }
 
+// msd_prefetch_windows: the window loop (mosdepth.nim:720-741) of every contig that has records, in one launch; results
+// go to pinned host memory and msd_windows() serves them from there.
+static int run_prefetch_windows(msd_ctx* ctx) {
+    ctx->pf_valid = false;
+    ctx->pf_slot.assign(ctx->n_targets, -1);
+    if (!ctx->pf_window) return MSD_OK;
+    std::vector<WinContig> table;
+    long long groups = 0, windows = 0;
+    for (int t = 0; t < ctx->n_targets; t++) {
+        if (!ctx->results[t].have) continue;
+        const long long nw = msd_n_windows(ctx->tlen[t], ctx->pf_window);
+        if (nw <= 0) continue;
+        WinContig c; c.arr_off = ctx->depth_off[t]; c.first_group = groups; c.first_window = windows; c.n_windows = nw; c.tlen = ctx->tlen[t]; c.pad = 0;
+        ctx->pf_slot[t] = (int)table.size();
+        table.push_back(c);
+        groups += (nw + 31) / 32; windows += nw;
+    }
+    if (table.empty()) { ctx->pf_valid = true; return MSD_OK; }
+    if ((uint64_t)windows * 8 > (1ull << 30)) { ctx->pf_slot.assign(ctx->n_targets, -1); return MSD_OK; }   // too many windows to keep: msd_windows computes per call
+    const int nc = (int)table.size();
+    if ((uint64_t)windows > ctx->pf_cap_windows) {
+        dev_free(&ctx->d_pf_values); if (ctx->h_pf_values) { cudaFreeHost(ctx->h_pf_values); ctx->h_pf_values = nullptr; }
+        int rc = dev_alloc(ctx, &ctx->d_pf_values, (uint64_t)windows); if (rc) return rc;
+        MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_pf_values, (size_t)windows * 8));
+        ctx->pf_cap_windows = (uint64_t)windows;
+    }
+    if (nc > ctx->pf_cap_contigs) {
+        dev_free(&ctx->d_pf_acc); dev_free(&ctx->d_pf_dist); dev_free(&ctx->d_pf_table);
+        if (ctx->h_pf_acc) cudaFreeHost(ctx->h_pf_acc); if (ctx->h_pf_dist) cudaFreeHost(ctx->h_pf_dist); if (ctx->h_pf_table) cudaFreeHost(ctx->h_pf_table);
+        ctx->h_pf_acc = nullptr; ctx->h_pf_dist = nullptr; ctx->h_pf_table = nullptr;
+        int rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_pf_acc, (uint64_t)nc)) || (rc = dev_alloc(ctx, &ctx->d_pf_dist, (uint64_t)nc * kWindowDistBins)) || (rc = dev_alloc(ctx, &ctx->d_pf_table, (uint64_t)nc))) return rc;
+        MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_pf_acc, sizeof(RegionAccum) * nc));
+        MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_pf_dist, 8ull * kWindowDistBins * nc));
+        MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_pf_table, sizeof(WinContig) * nc));
+        ctx->pf_cap_contigs = nc;
+    }
+    cudaStream_t sc = ctx->s_compute;
+    memcpy(ctx->h_pf_table, table.data(), sizeof(WinContig) * nc);
+    for (int i = 0; i < nc; i++) { RegionAccum& a = ctx->h_pf_acc[i]; a.cum_length = 0; a.cum_depth = 0; a.min_depth = 0xffffffffu; a.max_depth = 0; a.neg_seen = 0; a.pad = 0; }
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_pf_table, ctx->h_pf_table, sizeof(WinContig) * nc, cudaMemcpyHostToDevice, sc));
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_pf_acc, ctx->h_pf_acc, sizeof(RegionAccum) * nc, cudaMemcpyHostToDevice, sc));
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_pf_dist, 0, 8ull * kWindowDistBins * nc, sc));
+    const int grid = (int)std::min<long long>((groups + kWinWarps - 1) / kWinWarps, (long long)kSMs * 6);
+    windows_all_kernel<<<grid, kWinWarps * 32, 0, sc>>>(ctx->d_arena, ctx->d_pf_table, nc, groups, ctx->pf_window, ctx->d_pf_values, ctx->d_pf_acc, ctx->d_pf_dist);
+    MSD_CUDA_OK(cudaGetLastError());
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_pf_values, ctx->d_pf_values, (size_t)windows * 8, cudaMemcpyDeviceToHost, sc));
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_pf_acc, ctx->d_pf_acc, sizeof(RegionAccum) * nc, cudaMemcpyDeviceToHost, sc));
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_pf_dist, ctx->d_pf_dist, 8ull * kWindowDistBins * nc, cudaMemcpyDeviceToHost, sc));
+    ctx->info.n_launches += 1;
+    ctx->pf_valid = true;    // the caller synchronises the stream before msd_run returns
+    return MSD_OK;
+}
+
+int msd_prefetch_windows(msd_ctx* ctx, uint32_t window) {
+    if (!ctx) return MSD_EINVAL;
+    ctx->pf_window = window; ctx->pf_valid = false;
+    return MSD_OK;
+}
+
 int msd_run(msd_ctx* ctx) {
     if (!ctx || !ctx->bytes) return ctx_fail(ctx, MSD_EINVAL, "msd_run: no input open");
     cudaSetDevice(ctx->device);
@@ -556,7 +623,7 @@ int msd_run(msd_ctx* ctx) {
     ctx->fp.n_targets = ctx->n_targets;
     ctx->ev_used = 0;
     memset(&ctx->info, 0, sizeof ctx->info);
-    ctx->ran = false;
+    ctx->ran = false; ctx->pf_valid = false;
     for (auto& r : ctx->results) { r.have = false; r.dist.clear(); }
     cudaStream_t sc = ctx->s_compute, sx = ctx->s_copy;
     StageTimes times;
@@ -762,6 +829,7 @@ int msd_run(msd_ctx* ctx) {
         ctx->info.n_launches += 4;
     }
     MSD_CUDA_OK(cudaEventRecord(s1, sc));
+    if ((rc = run_prefetch_windows(ctx))) return rc;
     MSD_CUDA_OK(cudaEventRecord(ev_end, sc));
     MSD_CUDA_OK(cudaStreamSynchronize(sc));
     float ms = 0;
@@ -818,13 +886,31 @@ int64_t msd_windows(msd_ctx* ctx, int tid, uint32_t window, int use_median, doub
     const uint32_t tlen = ctx->tlen[tid];
     const int64_t nw = msd_n_windows(tlen, window);
     if (value_out && value_cap < nw) return ctx_fail(ctx, MSD_EINVAL, "msd_windows: value_cap %lld < %lld windows", (long long)value_cap, (long long)nw);
+    if (ctx->pf_valid && window == ctx->pf_window && !use_median && nw > 0 && tid < (int)ctx->pf_slot.size() && ctx->pf_slot[tid] >= 0) {
+        // computed by msd_run (msd_prefetch_windows): serve from the host cache; the totals are still added per call (sum_into)
+        const int i = ctx->pf_slot[tid];
+        const RegionAccum& h = ctx->h_pf_acc[i];
+        cudaStream_t sc = ctx->s_compute;
+        add_hist_kernel<<<2, 256, 0, sc>>>(ctx->d_tot_region, ctx->d_pf_dist + (size_t)i * kWindowDistBins, kWindowDistBins);
+        add_stats_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats + 4, (long long)h.cum_length, h.cum_depth, h.min_depth, h.max_depth);
+        ctx->launches += 2;
+        if (region_stat) { region_stat->cum_length = (int64_t)h.cum_length; region_stat->cum_depth = h.cum_depth; region_stat->min_depth = h.min_depth; region_stat->max_depth = h.max_depth; }
+        if (value_out) memcpy(value_out, ctx->h_pf_values + ctx->h_pf_table[i].first_window, (size_t)nw * 8);
+        if (region_dist512) memcpy(region_dist512, ctx->h_pf_dist + (size_t)i * kWindowDistBins, 8 * kWindowDistBins);
+        MSD_CUDA_OK(cudaStreamSynchronize(sc));
+        return nw;
+    }
     if ((rc = ensure_scratch(ctx, (uint64_t)std::max<int64_t>(nw, 1) * 8))) return rc;
     cudaStream_t sc = ctx->s_compute;
     init_accum_kernel<<<1, 1, 0, sc>>>(nullptr, ctx->d_racc);
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_dist512, 0, 8 * kWindowDistBins, sc));
     if (nw > 0) {
-        windows_kernel<<<grid_for((uint64_t)nw, 256, kSMs * 8), 256, 0, sc>>>(ctx->d_arena + ctx->depth_off[tid], tlen, window, nw, use_median,
-                                                                            (double*)ctx->d_scratch, ctx->d_racc, ctx->d_dist512);
+        if (use_median)
+            windows_kernel<<<grid_for((uint64_t)nw, 256, kSMs * 8), 256, 0, sc>>>(ctx->d_arena + ctx->depth_off[tid], tlen, window, nw, use_median,
+                                                                                (double*)ctx->d_scratch, ctx->d_racc, ctx->d_dist512);
+        else
+            windows_mean_kernel<<<grid_for((uint64_t)nw, kWinWarps * 32, kSMs * 4), kWinWarps * 32, 0, sc>>>(ctx->d_arena + ctx->depth_off[tid], tlen, window, nw,
+                                                                                                     (double*)ctx->d_scratch, ctx->d_racc, ctx->d_dist512);
         MSD_CUDA_OK(cudaGetLastError());
     }
     add_hist_kernel<<<2, 256, 0, sc>>>(ctx->d_tot_region, ctx->d_dist512, kWindowDistBins);

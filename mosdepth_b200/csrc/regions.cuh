@@ -101,6 +101,137 @@ windows_kernel(const int32_t* __restrict__ arr, uint32_t tlen, uint32_t window, 
     for (int i = threadIdx.x; i < kWindowDistBins; i += blockDim.x) { uint32_t c = s_hist[i]; if (c) atomicAdd(&dist512[i], (unsigned long long)c); }
 }
 
+// window mode, mean: the same results as windows_kernel(use_median = 0) with coalesced loads.  A warp owns 32
+// consecutive windows, one per lane.  The windows are walked in column chunks of 32 cells: the warp loads the chunk
+// of every window with one coalesced 128-byte access per window into a padded shared-memory tile, then every lane
+// runs its own window's strictly sequential float64 chain (Q1) and slice stats over its row of the tile.
+// (windows_kernel reads with one scalar load per cell and lane, 2 KB apart between lanes, twice: 93 GB/s.)
+constexpr int kWinWarps = 8;
+constexpr int kWinQuot = 1024;
+__global__ void __launch_bounds__(kWinWarps * 32)
+windows_mean_kernel(const int32_t* __restrict__ arr, uint32_t tlen, uint32_t window, long long n_windows,
+                    double* __restrict__ value_out, RegionAccum* __restrict__ acc, unsigned long long* __restrict__ dist512) {
+    __shared__ uint32_t s_hist[kWindowDistBins];
+    __shared__ int32_t s_tile[kWinWarps][32][33];
+    // float64(v) / window for v < 1024, the very doubles the sequential chain adds (every full window divides by the
+    // same L).  In lock step a warp would otherwise run the ~300-cycle division at every cell, because some lane's depth
+    // changes at almost every cell (r1k launch list: 133 us per launch whatever the grid, 290 cycles per cell).
+    __shared__ double s_q[kWinQuot];
+    for (int i = threadIdx.x; i < kWindowDistBins; i += blockDim.x) s_hist[i] = 0;
+    for (int i = threadIdx.x; i < kWinQuot; i += blockDim.x) s_q[i] = __ddiv_rn((double)i, (double)window);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t (*tile)[33] = s_tile[warp];
+    unsigned long long len = 0, sum = 0; uint32_t mn = 0xffffffffu, mx = 0;
+    const long long n_groups = (n_windows + 31) / 32;
+    for (long long g = (long long)blockIdx.x * kWinWarps + warp; g < n_groups; g += (long long)gridDim.x * kWinWarps) {
+        const long long w0 = g * 32, w = w0 + lane;
+        const bool valid = w < n_windows;
+        const unsigned long long s64 = (unsigned long long)w * window;
+        const unsigned long long e64 = (s64 + window < tlen) ? s64 + window : (unsigned long long)tlen;   // window_gen :382-388
+        const long long my_len = valid ? (long long)(e64 - s64) : 0;
+        const double L = (double)(uint32_t)my_len;
+        const int n_rows = (int)((n_windows - w0) < 32 ? (n_windows - w0) : 32);
+        double a = 0.0, q = 0.0; int32_t last = 0; bool have = false;
+        const bool full_len = my_len == (long long)window;
+        const unsigned long long g0 = (unsigned long long)w0 * window;                 // first cell of the group (< tlen)
+        const uint32_t max_len = (uint32_t)(((unsigned long long)tlen - g0) < window ? ((unsigned long long)tlen - g0) : window);   // its first window is the longest
+        for (uint32_t c0 = 0; c0 < max_len; c0 += 32) {
+            unsigned long long idx = g0 + c0 + lane;
+            const bool col_ok = c0 + lane < window;
+#pragma unroll 8
+            for (int r = 0; r < n_rows; r++, idx += window) tile[r][lane] = (col_ok && idx < tlen) ? __ldg(arr + idx) : 0;
+            __syncwarp();
+            long long n = my_len - (long long)c0; if (n > 32) n = 32;
+            for (int j = 0; j < (int)n; j++) {
+                const int32_t v = tile[lane][j];
+                if (full_len && (uint32_t)v < (uint32_t)kWinQuot) q = s_q[v];
+                else if (full_len) q = __ddiv_rn((double)v, L);                                        // depth >= 1024, or negative
+                else if (!have || v != last) { q = __ddiv_rn((double)v, L); last = v; have = true; }   // the contig's last, shorter window
+                a = __dadd_rn(a, q);
+                sum += (unsigned long long)(long long)v;
+                const uint32_t u = (uint32_t)v; mn = u < mn ? u : mn; mx = u > mx ? u : mx;
+            }
+            __syncwarp();
+        }
+        if (valid) {
+            value_out[w] = a;
+            len += (unsigned long long)my_len;
+            long long bin = a >= 0 ? (long long)__dadd_rn(a, 0.5) : (long long)__dadd_rn(a, -0.5);   // toInt, :737-739
+            if (bin > kWindowDistBins - 1) bin = kWindowDistBins - 1;
+            if (bin >= 0) atomicAdd(&s_hist[bin], 1u);
+        }
+    }
+    block_accumulate(acc, len, sum, mn, mx);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kWindowDistBins; i += blockDim.x) { uint32_t c = s_hist[i]; if (c) atomicAdd(&dist512[i], (unsigned long long)c); }
+}
+
+// window mode, mean, EVERY contig in one launch (msd_prefetch_windows): the float64 chain makes one window a fixed
+// ~100 us of latency whatever the grid, so 25 per-contig launches cost 25 x that; one launch over all contigs costs it once.
+// Same per-window arithmetic as windows_mean_kernel.  A warp owns a group of 32 consecutive windows of ONE contig.
+struct WinContig {
+    unsigned long long arr_off;     // first cell of the contig in the depth arena
+    long long first_group;          // index of the contig's first 32-window group among all groups
+    long long first_window;         // index of its first window in value_out
+    long long n_windows;
+    uint32_t tlen, pad;
+};
+__global__ void __launch_bounds__(kWinWarps * 32)
+windows_all_kernel(const int32_t* __restrict__ arena, const WinContig* __restrict__ contigs, int n_contigs, long long n_groups, uint32_t window,
+                   double* __restrict__ value_out, RegionAccum* __restrict__ acc /*[n_contigs]*/, unsigned long long* __restrict__ dist512 /*[n_contigs][512]*/) {
+    __shared__ int32_t s_tile[kWinWarps][32][33];
+    __shared__ double s_q[kWinQuot];
+    for (int i = threadIdx.x; i < kWinQuot; i += blockDim.x) s_q[i] = __ddiv_rn((double)i, (double)window);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t (*tile)[33] = s_tile[warp];
+    for (long long g = (long long)blockIdx.x * kWinWarps + warp; g < n_groups; g += (long long)gridDim.x * kWinWarps) {
+        int lo = 0, hi = n_contigs - 1;                                   // last contig with first_group <= g
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (contigs[mid].first_group <= g) lo = mid; else hi = mid - 1; }
+        const WinContig C = contigs[lo];
+        const int32_t* __restrict__ arr = arena + C.arr_off;
+        const uint32_t tlen = C.tlen;
+        const long long w0 = (g - C.first_group) * 32, w = w0 + lane;
+        const bool valid = w < C.n_windows;
+        const unsigned long long s64 = (unsigned long long)w * window;
+        const unsigned long long e64 = (s64 + window < tlen) ? s64 + window : (unsigned long long)tlen;
+        const long long my_len = valid ? (long long)(e64 - s64) : 0;
+        const double L = (double)(uint32_t)my_len;
+        const int n_rows = (int)((C.n_windows - w0) < 32 ? (C.n_windows - w0) : 32);
+        double a = 0.0, q = 0.0; int32_t last = 0; bool have = false;
+        const bool full_len = my_len == (long long)window;
+        unsigned long long sum = 0; uint32_t mn = 0xffffffffu, mx = 0;
+        const unsigned long long g0 = (unsigned long long)w0 * window;
+        const uint32_t max_len = (uint32_t)(((unsigned long long)tlen - g0) < window ? ((unsigned long long)tlen - g0) : window);
+        for (uint32_t c0 = 0; c0 < max_len; c0 += 32) {
+            unsigned long long idx = g0 + c0 + lane;
+            const bool col_ok = c0 + lane < window;
+#pragma unroll 8
+            for (int r = 0; r < n_rows; r++, idx += window) tile[r][lane] = (col_ok && idx < tlen) ? __ldg(arr + idx) : 0;
+            __syncwarp();
+            long long n = my_len - (long long)c0; if (n > 32) n = 32;
+            for (int j = 0; j < (int)n; j++) {
+                const int32_t v = tile[lane][j];
+                if (full_len && (uint32_t)v < (uint32_t)kWinQuot) q = s_q[v];
+                else if (full_len) q = __ddiv_rn((double)v, L);
+                else if (!have || v != last) { q = __ddiv_rn((double)v, L); last = v; have = true; }
+                a = __dadd_rn(a, q);
+                sum += (unsigned long long)(long long)v;
+                const uint32_t u = (uint32_t)v; mn = u < mn ? u : mn; mx = u > mx ? u : mx;
+            }
+            __syncwarp();
+        }
+        if (valid) {
+            value_out[C.first_window + w] = a;
+            long long bin = a >= 0 ? (long long)__dadd_rn(a, 0.5) : (long long)__dadd_rn(a, -0.5);
+            if (bin > kWindowDistBins - 1) bin = kWindowDistBins - 1;
+            if (bin >= 0) atomicAdd(&dist512[(size_t)lo * kWindowDistBins + bin], 1ull);
+        }
+        block_accumulate(acc + lo, (unsigned long long)my_len, sum, mn, mx);
+    }
+}
+
 // BED mode: one thread per region (regions sorted by start on the host, mosdepth.nim:376-377)
 __global__ void __launch_bounds__(256)
 regions_kernel(const int32_t* __restrict__ arr, uint32_t tlen, long long n, const uint32_t* __restrict__ starts,

@@ -295,6 +295,7 @@ int main(int argc, char** argv) {
     std::vector<const char*> rgs; std::vector<std::string> rg_store;
     if (rg_arg) { std::string s = rg_arg; size_t p = 0; for (;;) { size_t c = s.find(',', p); rg_store.push_back(s.substr(p, c == std::string::npos ? std::string::npos : c - p)); if (c == std::string::npos) break; p = c + 1; } for (auto& r : rg_store) rgs.push_back(r.c_str()); }
     MSD(msd_set_filters(ctx, mapq, min_len, max_len, eflag, iflag, rgs.empty() ? nullptr : rgs.data(), (int)rgs.size(), fast_mode ? MSD_MODE_FAST : fragment_mode ? MSD_MODE_FRAGMENT : MSD_MODE_DEFAULT));
+    if (by_digit && window && !use_median) MSD(msd_prefetch_windows(ctx, window));   // --by <int>: every contig's window loop in one launch
     MSD(msd_run(ctx));   // coverage() + to_coverage() for every visited contig
 
     // ---- outputs (mosdepth.nim:641-682) -------------------------------------------------------------------------------
