@@ -163,6 +163,27 @@ int msd_quantized_runs(msd_ctx *ctx, int tid, const int64_t *quants, int n_q, co
 int msd_totals_device(msd_ctx *ctx, void **global_dist, void **region_dist, int64_t *n_bins, void **stats8);
 int msd_totals_reset(msd_ctx *ctx);
 
+/* ---- intra-contig sharding across GPUs (nothing in the single-process reference corresponds to it) --------
+ * One context per GPU.  msd_set_contig_range(tid, lo, hi) before msd_run() makes this context the OWNER of the records of
+ * contig tid with lo <= pos < hi (hi = 0: to the contig end; lo a multiple of 32, and of the window / 16384 if windows
+ * will be asked for).  The spans given to msd_set_spans() must cover every owned record, at least one record at or
+ * beyond hi (msd_run fails otherwise: extend the span) and, in default mode, the records up to one read length before
+ * lo (an owned record may have to take its mate from them: they go through the filters and the `seen` table but emit
+ * nothing).  After msd_run() the contig's array holds the prefix sum of this shard's own events.  Reads that start
+ * before hi still cover [hi, hi + n): msd_contig_spill() says how far; that piece of depth is copied out
+ * (msd_depth_copy) and added by the next shard (msd_depth_add) -- the prefix-sum carry across the shard boundary, as
+ * depth rather than as one integer, because the reads of a shard all end within one read length of it.  Host or device
+ * pointers (device: send/receive the piece with NCCL straight out of / into GPU memory).  msd_contig_finalize() then
+ * computes the shard's part of msd_contig_stats() (cum_length = hi - lo; the caller sums the shards), after which
+ * msd_windows() returns the windows that start in [lo, hi).  msd_regions / msd_per_base_runs / msd_quantized_runs are
+ * not available on a shard; fragment mode is not supported with ranges (a fragment starts before its read 1).
+ * msd_contig_records() counts owned records only. */
+int msd_set_contig_range(msd_ctx *ctx, int tid, uint32_t lo, uint32_t hi);
+int msd_contig_spill(msd_ctx *ctx, int tid, uint32_t *from, uint32_t *n);
+int msd_depth_copy(msd_ctx *ctx, int tid, uint32_t pos, uint32_t n, int32_t *dst, int dst_is_device);
+int msd_depth_add(msd_ctx *ctx, int tid, uint32_t pos, uint32_t n, const int32_t *src, int src_is_device);
+int msd_contig_finalize(msd_ctx *ctx, int tid);
+
 /* -- measurement hooks (bench.py): CUDA events on the library's own compute stream --------------------- */
 /* Record event `slot` (0..7) on the compute stream now. */
 int msd_mark(msd_ctx *ctx, int slot);

@@ -23,6 +23,7 @@ EXPORTS = [
     "msd_abi_version", "msd_create", "msd_destroy", "msd_last_error", "msd_open", "msd_open_mem", "msd_stage",
     "msd_set_spans", "msd_set_targets", "msd_set_filters", "msd_run", "msd_last_run_info", "msd_contig_records",
     "msd_contig_stats", "msd_n_windows", "msd_prefetch_windows", "msd_windows", "msd_regions", "msd_per_base_runs", "msd_quantized_runs",
+    "msd_set_contig_range", "msd_contig_spill", "msd_depth_copy", "msd_depth_add", "msd_contig_finalize",
     "msd_totals_device", "msd_totals_reset", "msd_mark", "msd_elapsed_ms", "msd_launch_count", "msd_debug_inflate", "msd_debug_depth", "msd_debug_cumsum",
 ]
 
@@ -76,6 +77,11 @@ def load_library():
     lib.msd_contig_stats.argtypes = [p, i32, C.POINTER(DepthStat), p, i64, C.POINTER(i64)]
     lib.msd_n_windows.argtypes = [u32, u32]; lib.msd_n_windows.restype = i64
     lib.msd_prefetch_windows.argtypes = [p, u32]
+    lib.msd_set_contig_range.argtypes = [p, i32, u32, u32]
+    lib.msd_contig_spill.argtypes = [p, i32, C.POINTER(u32), C.POINTER(u32)]
+    lib.msd_depth_copy.argtypes = [p, i32, u32, u32, p, i32]
+    lib.msd_depth_add.argtypes = [p, i32, u32, u32, p, i32]
+    lib.msd_contig_finalize.argtypes = [p, i32]
     lib.msd_windows.argtypes = [p, i32, u32, i32, p, i64, C.POINTER(DepthStat), p]; lib.msd_windows.restype = i64
     lib.msd_regions.argtypes = [p, i32, i64, p, p, i32, p, C.POINTER(DepthStat), p, i64, C.POINTER(i64), p, i32, p]
     lib.msd_per_base_runs.argtypes = [p, i32, C.POINTER(p), C.POINTER(p), C.POINTER(p), C.POINTER(i64)]
@@ -191,6 +197,32 @@ class Context:
         self._check(self.lib.msd_contig_stats(self.h, tid, C.byref(st), _ptr(dist), dist.size, C.byref(n)))
         return st, dist
 
+    # ---- intra-contig sharding (include/mosdepth_b200.h) ----
+    def set_contig_range(self, tid, lo, hi):
+        self._check(self.lib.msd_set_contig_range(self.h, tid, int(lo), int(hi)))
+
+    def contig_spill(self, tid):
+        a, n = C.c_uint32(), C.c_uint32()
+        self._check(self.lib.msd_contig_spill(self.h, tid, C.byref(a), C.byref(n)))
+        return a.value, n.value
+
+    def depth_copy(self, tid, pos, n, device_ptr=None):
+        """Depth of [pos, pos + n) of a shard after run(): to a numpy array, or to device memory at device_ptr."""
+        if device_ptr is not None:
+            self._check(self.lib.msd_depth_copy(self.h, tid, int(pos), int(n), C.c_void_p(device_ptr), 1)); return None
+        out = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.msd_depth_copy(self.h, tid, int(pos), int(n), _ptr(out), 0))
+        return out
+
+    def depth_add(self, tid, pos, cells=None, device_ptr=None, n=None):
+        if device_ptr is not None:
+            self._check(self.lib.msd_depth_add(self.h, tid, int(pos), int(n), C.c_void_p(device_ptr), 1)); return
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        self._check(self.lib.msd_depth_add(self.h, tid, int(pos), cells.size, _ptr(cells), 0))
+
+    def contig_finalize(self, tid):
+        self._check(self.lib.msd_contig_finalize(self.h, tid))
+
     def prefetch_windows(self, window):
         """Hint: msd_run() computes the windows of every contig in one launch; windows() then reads the host cache."""
         self._check(self.lib.msd_prefetch_windows(self.h, int(window)))
@@ -198,8 +230,9 @@ class Context:
     def windows(self, tid, window, use_median=False):
         nw = self.lib.msd_n_windows(int(self.tlen[tid]), window)
         vals = np.zeros(max(nw, 1), dtype=np.float64); st = DepthStat(); dist = np.zeros(512, dtype=np.int64)
-        self._check(self.lib.msd_windows(self.h, tid, window, int(use_median), _ptr(vals), vals.size, C.byref(st), _ptr(dist)))
-        return vals[:nw], st, dist
+        got = self.lib.msd_windows(self.h, tid, window, int(use_median), _ptr(vals), vals.size, C.byref(st), _ptr(dist))
+        self._check(got)
+        return vals[:got], st, dist     # a shard of a contig (set_contig_range) returns only the windows that start in it
 
     def regions(self, tid, starts, stops, use_median=False, thresholds=()):
         s = np.ascontiguousarray(starts, dtype=np.uint32); e = np.ascontiguousarray(stops, dtype=np.uint32)

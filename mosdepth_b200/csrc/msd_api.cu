@@ -67,6 +67,9 @@ struct msd_ctx {
     // depth arena
     int32_t* d_arena = nullptr; uint64_t arena_cells = 0; std::vector<uint64_t> depth_off;
     uint64_t* d_depth_off = nullptr; uint32_t* d_tlen = nullptr;
+    // intra-contig sharding (msd_set_contig_range)
+    std::vector<uint32_t> range_lo, range_hi, max_end; std::vector<uint8_t> ranged, pending; bool any_ranged = false;
+    uint32_t *d_range_lo = nullptr, *d_range_hi = nullptr, *d_max_end = nullptr; unsigned long long* d_n_beyond = nullptr;
     unsigned long long* d_nprefilter = nullptr; std::vector<long long> n_prefilter;
     std::vector<ContigResult> results; bool ran = false;
     // chunk buffers
@@ -162,6 +165,8 @@ int setup_common(msd_ctx* ctx, int n_targets, const uint32_t* target_len, uint64
     ctx->n_targets = n_targets; ctx->tlen.assign(target_len, target_len + n_targets); ctx->first_voff = first_voff;
     ctx->spans.clear(); ctx->want.assign(n_targets, 1);
     ctx->results.assign(n_targets, ContigResult()); ctx->n_prefilter.assign(n_targets, 0);
+    ctx->range_lo.assign(n_targets, 0); ctx->range_hi.assign(n_targets, 0xffffffffu); ctx->max_end.assign(n_targets, 0);
+    ctx->ranged.assign(n_targets, 0); ctx->pending.assign(n_targets, 0); ctx->any_ranged = false;
     cudaPointerAttributes pa; memset(&pa, 0, sizeof pa);
     ctx->src_pinned = (cudaPointerGetAttributes(&pa, ctx->bytes) == cudaSuccess && pa.type == cudaMemoryTypeHost);
     cudaGetLastError();
@@ -277,7 +282,13 @@ int ensure_arena(msd_ctx* ctx) {
         if ((rc = dev_alloc(ctx, &ctx->d_depth_off, (uint64_t)ctx->n_targets))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_tlen, (uint64_t)ctx->n_targets))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_nprefilter, (uint64_t)ctx->n_targets))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_range_lo, (uint64_t)ctx->n_targets))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_range_hi, (uint64_t)ctx->n_targets))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_max_end, (uint64_t)ctx->n_targets))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_n_beyond, (uint64_t)ctx->n_targets))) return rc;
     }
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_range_lo, ctx->range_lo.data(), sizeof(uint32_t) * ctx->n_targets, cudaMemcpyHostToDevice, ctx->s_compute));
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_range_hi, ctx->range_hi.data(), sizeof(uint32_t) * ctx->n_targets, cudaMemcpyHostToDevice, ctx->s_compute));
     MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_depth_off, off.data(), sizeof(uint64_t) * ctx->n_targets, cudaMemcpyHostToDevice, ctx->s_compute));
     MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_tlen, ctx->tlen.data(), sizeof(uint32_t) * ctx->n_targets, cudaMemcpyHostToDevice, ctx->s_compute));
     MSD_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));   // `off` is a stack vector
@@ -346,7 +357,10 @@ static int check_tid(msd_ctx* ctx, int tid, const char* who) {
     if (!ctx) return MSD_EINVAL;
     if (!ctx->ran) return ctx_fail(ctx, MSD_EINVAL, "%s: call msd_run first", who);
     if (tid < 0 || tid >= ctx->n_targets || !ctx->want[tid]) return ctx_fail(ctx, MSD_EINVAL, "%s: contig %d not selected", who, tid);
-    if (ctx->n_prefilter[tid] <= 0) return ctx_fail(ctx, MSD_EINVAL, "%s: contig %d has no records (coverage() returned -2)", who, tid);
+    if (ctx->ranged[tid]) {
+        if (ctx->pending[tid]) return ctx_fail(ctx, MSD_EINVAL, "%s: contig %d is a shard: call msd_contig_finalize first", who, tid);
+        if (strcmp(who, "msd_windows") && strcmp(who, "msd_contig_stats")) return ctx_fail(ctx, MSD_EINVAL, "%s is not available on a shard of a contig (msd_set_contig_range)", who);
+    } else if (ctx->n_prefilter[tid] <= 0) return ctx_fail(ctx, MSD_EINVAL, "%s: contig %d has no records (coverage() returned -2)", who, tid);
     cudaSetDevice(ctx->device);
     return 0;
 }
@@ -442,7 +456,7 @@ void msd_destroy(msd_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     release_input(ctx);
-    dev_free(&ctx->d_rg); dev_free(&ctx->d_arena); dev_free(&ctx->d_depth_off); dev_free(&ctx->d_tlen); dev_free(&ctx->d_nprefilter);
+    dev_free(&ctx->d_rg); dev_free(&ctx->d_arena); dev_free(&ctx->d_depth_off); dev_free(&ctx->d_tlen); dev_free(&ctx->d_nprefilter); dev_free(&ctx->d_range_lo); dev_free(&ctx->d_range_hi); dev_free(&ctx->d_max_end); dev_free(&ctx->d_n_beyond);
     free_chunk_buffers(ctx);
     for (int k = 0; k < kSlots; k++) if (ctx->s_inflate[k]) cudaStreamDestroy(ctx->s_inflate[k]);
     for (int k = 0; k < 2; k++) { dev_free(&ctx->live[k].e); dev_free(&ctx->live[k].arena); dev_free(&ctx->live[k].n); dev_free(&ctx->live[k].arena_used); }
@@ -478,7 +492,7 @@ int msd_open_mem(msd_ctx* ctx, const void* bam_bytes, uint64_t n_bytes, int n_ta
     for (int k = 0; k < 2; k++) { dev_free(&ctx->live[k].e); dev_free(&ctx->live[k].arena); dev_free(&ctx->live[k].n); dev_free(&ctx->live[k].arena_used); }
     dev_free(&ctx->mc.cls); dev_free(&ctx->mc.qhash); dev_free(&ctx->mc.endpos); dev_free(&ctx->mc.next); dev_free(&ctx->mc.slot);
     dev_free(&ctx->mt.word); dev_free(&ctx->mt.head); dev_free(&ctx->mt.live); ctx->mate_ready = false;
-    dev_free(&ctx->d_depth_off); dev_free(&ctx->d_tlen); dev_free(&ctx->d_nprefilter);
+    dev_free(&ctx->d_depth_off); dev_free(&ctx->d_tlen); dev_free(&ctx->d_nprefilter); dev_free(&ctx->d_range_lo); dev_free(&ctx->d_range_hi); dev_free(&ctx->d_max_end); dev_free(&ctx->d_n_beyond);
     ctx->bytes = (const uint8_t*)bam_bytes; ctx->n_bytes = n_bytes; ctx->mapped = false;
     return setup_common(ctx, n_targets, target_len, first_record_voff);
 }
@@ -633,6 +647,9 @@ int msd_run(msd_ctx* ctx) {
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_arena, 0, ctx->arena_cells * 4, sc));                       // init, mosdepth.nim:238-248
     MSD_CUDA_OK(cudaEventRecord(ev_zero_end, sc));
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_nprefilter, 0, sizeof(unsigned long long) * ctx->n_targets, sc));
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_max_end, 0, sizeof(uint32_t) * ctx->n_targets, sc));
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_n_beyond, 0, sizeof(unsigned long long) * ctx->n_targets, sc));
+    std::fill(ctx->pending.begin(), ctx->pending.end(), 0);
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_rc, 0, sizeof(RunCounters), sc));
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_cs, 0, sizeof(ChunkState), sc));
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_inflate_err, 0, 4, sc));
@@ -645,7 +662,8 @@ int msd_run(msd_ctx* ctx) {
         for (int k = 0; k < kSlots; k++) MSD_CUDA_OK(cudaStreamWaitEvent(ctx->s_inflate[k], ev_init, 0));
         MSD_CUDA_OK(cudaStreamWaitEvent(sx, ev_init, 0));
     }
-    ContigTable ct{ctx->d_depth_off, ctx->d_tlen};
+    ContigTable ct{ctx->d_depth_off, ctx->d_tlen, ctx->d_range_lo, ctx->d_range_hi, ctx->any_ranged ? ctx->d_max_end : nullptr, ctx->d_n_beyond};
+    if (ctx->any_ranged && ctx->fp.mode == MSD_MODE_FRAGMENT) return ctx_fail(ctx, MSD_EINVAL, "msd_set_contig_range is not supported in fragment mode (a fragment starts before its read 1)");
     const uint32_t base = ctx->carry_cap;
     // spans are taken as given (the caller merges neighbouring contigs when the bytes between them are genuine
     // file bytes; a compact per-rank buffer has cut points between its ranges, so the library must not guess)
@@ -805,8 +823,25 @@ int msd_run(msd_ctx* ctx) {
     MSD_CUDA_OK(cudaMemcpy(npre.data(), ctx->d_nprefilter, sizeof(unsigned long long) * ctx->n_targets, cudaMemcpyDeviceToHost));
     cudaEvent_t s0 = next_event(ctx), s1 = next_event(ctx);
     MSD_CUDA_OK(cudaEventRecord(s0, sc));
+    std::vector<unsigned long long> nbey(ctx->n_targets, 0);
+    if (ctx->any_ranged) {
+        MSD_CUDA_OK(cudaMemcpy(ctx->max_end.data(), ctx->d_max_end, sizeof(uint32_t) * ctx->n_targets, cudaMemcpyDeviceToHost));
+        MSD_CUDA_OK(cudaMemcpy(nbey.data(), ctx->d_n_beyond, sizeof(unsigned long long) * ctx->n_targets, cudaMemcpyDeviceToHost));
+    }
     for (int t = 0; t < ctx->n_targets; t++) {
         ctx->n_prefilter[t] = (long long)npre[t];
+        if (ctx->want[t] && ctx->ranged[t]) {
+            // a shard of a contig: prefix sum of this shard's own events over [lo, last event]; the depth it leaves
+            // beyond hi goes to the next shard (msd_depth_copy / msd_depth_add), then msd_contig_finalize()
+            const uint32_t lo = ctx->range_lo[t], hi = std::min(ctx->range_hi[t], ctx->tlen[t]);
+            if (hi < ctx->tlen[t] && nbey[t] == 0)
+                return ctx_fail(ctx, MSD_EINVAL, "contig %d: the span ends before any record at or beyond %u was seen; extend the span of this shard", t, hi);
+            const uint32_t last = std::max(ctx->max_end[t], lo);
+            if ((rc = run_scan(ctx, ctx->d_arena + ctx->depth_off[t] + lo, std::min<uint32_t>(last, ctx->tlen[t]) + 1 - lo, 0, 0))) return rc;
+            ctx->pending[t] = 1;
+            ctx->info.n_depth_cells += (uint64_t)hi - lo;
+            continue;
+        }
         if (!ctx->want[t] || npre[t] == 0) continue;
         const uint32_t tlen = ctx->tlen[t];
         ctx->info.n_depth_cells += (uint64_t)tlen + 1;
@@ -853,6 +888,86 @@ int msd_run(msd_ctx* ctx) {
 
 int msd_last_run_info(const msd_ctx* ctx, msd_run_info* out) { if (!ctx || !out) return MSD_EINVAL; *out = ctx->info; return MSD_OK; }
 
+// ---- intra-contig sharding ------------------------------------------------------------------------------------------------
+int msd_set_contig_range(msd_ctx* ctx, int tid, uint32_t lo, uint32_t hi) {
+    if (!ctx || tid < 0 || tid >= ctx->n_targets) return ctx_fail(ctx, MSD_EINVAL, "msd_set_contig_range: bad contig");
+    const uint32_t tlen = ctx->tlen[tid];
+    if (hi == 0 || hi > tlen) hi = tlen;
+    if (lo == 0 && hi == tlen) { ctx->ranged[tid] = 0; ctx->range_lo[tid] = 0; ctx->range_hi[tid] = 0xffffffffu; }
+    else {
+        if (lo >= hi || (lo & 31u)) return ctx_fail(ctx, MSD_EINVAL, "msd_set_contig_range: need lo < hi and lo a multiple of 32");
+        ctx->ranged[tid] = 1; ctx->range_lo[tid] = lo; ctx->range_hi[tid] = hi == tlen ? 0xffffffffu : hi;
+    }
+    ctx->any_ranged = false;
+    for (int t = 0; t < ctx->n_targets; t++) ctx->any_ranged |= ctx->ranged[t] != 0;
+    ctx->ran = false;
+    return MSD_OK;
+}
+
+static int check_pending(msd_ctx* ctx, int tid, const char* who) {
+    if (!ctx || tid < 0 || tid >= ctx->n_targets || !ctx->ranged[tid] || !ctx->pending[tid]) return ctx_fail(ctx, MSD_EINVAL, "%s: contig is not a shard waiting for msd_contig_finalize()", who);
+    cudaSetDevice(ctx->device);
+    return MSD_OK;
+}
+
+int msd_contig_spill(msd_ctx* ctx, int tid, uint32_t* from, uint32_t* n) {
+    int rc = check_pending(ctx, tid, "msd_contig_spill"); if (rc) return rc;
+    const uint32_t tlen = ctx->tlen[tid], hi = std::min(ctx->range_hi[tid], tlen);
+    if (from) *from = hi;
+    if (n) *n = ctx->max_end[tid] > hi ? std::min(ctx->max_end[tid], tlen) - hi : 0;
+    return MSD_OK;
+}
+
+int msd_depth_copy(msd_ctx* ctx, int tid, uint32_t pos, uint32_t n, int32_t* dst, int dst_is_device) {
+    int rc = check_pending(ctx, tid, "msd_depth_copy"); if (rc) return rc;
+    if (!dst || (uint64_t)pos + n > (uint64_t)ctx->tlen[tid] + 1) return ctx_fail(ctx, MSD_EINVAL, "msd_depth_copy: bad range");
+    if (n) MSD_CUDA_OK(cudaMemcpyAsync(dst, ctx->d_arena + ctx->depth_off[tid] + pos, 4ull * n, dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->s_compute));
+    MSD_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));
+    return MSD_OK;
+}
+
+int msd_depth_add(msd_ctx* ctx, int tid, uint32_t pos, uint32_t n, const int32_t* src, int src_is_device) {
+    int rc = check_pending(ctx, tid, "msd_depth_add"); if (rc) return rc;
+    if (!src || (uint64_t)pos + n > (uint64_t)ctx->tlen[tid] + 1) return ctx_fail(ctx, MSD_EINVAL, "msd_depth_add: bad range");
+    if (!n) return MSD_OK;
+    const int32_t* d_src = src;
+    if (!src_is_device) {
+        if ((rc = ensure_scratch(ctx, 4ull * n))) return rc;
+        MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_scratch, src, 4ull * n, cudaMemcpyHostToDevice, ctx->s_compute));
+        d_src = (const int32_t*)ctx->d_scratch;
+    }
+    add_cells_kernel<<<grid_for(n, 256, kSMs * 8), 256, 0, ctx->s_compute>>>(ctx->d_arena + ctx->depth_off[tid] + pos, d_src, n);
+    ctx->launches++;
+    MSD_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));
+    return MSD_OK;
+}
+
+int msd_contig_finalize(msd_ctx* ctx, int tid) {
+    int rc = check_pending(ctx, tid, "msd_contig_finalize"); if (rc) return rc;
+    if ((rc = ensure_query_buffers(ctx))) return rc;
+    cudaStream_t sc = ctx->s_compute;
+    const uint32_t tlen = ctx->tlen[tid], lo = ctx->range_lo[tid], hi = std::min(ctx->range_hi[tid], tlen);
+    const uint32_t n = hi - lo;
+    init_accum_kernel<<<1, 1, 0, sc>>>(ctx->d_acc, nullptr);
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_hist, 0, 8ull * kDistBins, sc));
+    range_stats_kernel<<<grid_for(n, 256, kSMs * 8), 256, 0, sc>>>(ctx->d_arena + ctx->depth_off[tid] + lo, n, ctx->d_hist, ctx->d_acc);
+    ContigAccum acc;
+    MSD_CUDA_OK(cudaMemcpyAsync(&acc, ctx->d_acc, sizeof acc, cudaMemcpyDeviceToHost, sc));
+    add_hist_kernel<<<kSMs, 256, 0, sc>>>(ctx->d_tot_global, ctx->d_hist, kDistBins);
+    MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    ContigResult& R = ctx->results[tid];
+    R.have = true; R.stat.cum_length = n; R.stat.cum_depth = acc.cum_depth; R.stat.min_depth = acc.min_depth; R.stat.max_depth = acc.max_depth;
+    add_stats_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats, (long long)n, acc.cum_depth, acc.min_depth, acc.max_depth);
+    int64_t top = 0;
+    if (n) { uint32_t mx = acc.max_depth; top = (mx > 0x7fffffffu) ? (int64_t)kMaxCoverage : (int64_t)std::min<uint32_t>(mx, kMaxCoverage); }
+    R.dist.assign((size_t)top + 1, 0);
+    MSD_CUDA_OK(cudaMemcpy(R.dist.data(), ctx->d_hist, 8ull * (top + 1), cudaMemcpyDeviceToHost));
+    while (R.dist.size() > 1 && R.dist.back() == 0) R.dist.pop_back();
+    ctx->launches += 4;
+    ctx->pending[tid] = 0;
+    return MSD_OK;
+}
+
 int msd_contig_records(msd_ctx* ctx, int tid, int64_t* n) {
     if (!ctx || !ctx->ran) return ctx_fail(ctx, MSD_EINVAL, "msd_contig_records: call msd_run first");
     if (tid < 0 || tid >= ctx->n_targets || !ctx->want[tid]) { if (n) *n = 0; return -1; }
@@ -883,7 +998,11 @@ int64_t msd_windows(msd_ctx* ctx, int tid, uint32_t window, int use_median, doub
                     msd_depth_stat* region_stat, int64_t* region_dist512) {
     int rc = check_tid(ctx, tid, "msd_windows"); if (rc) return rc;
     if (window == 0) return ctx_fail(ctx, MSD_EINVAL, "msd_windows: window must be > 0");
-    const uint32_t tlen = ctx->tlen[tid];
+    // a shard [lo, hi) of a contig is the array arr + lo of length hi - lo: lo is a multiple of the window and hi is one too
+    // or the contig end, so window_gen (:382-388) over the shard yields exactly the contig's windows that start in it
+    const uint32_t lo = ctx->ranged[tid] ? ctx->range_lo[tid] : 0;
+    const uint32_t tlen = ctx->ranged[tid] ? std::min(ctx->range_hi[tid], ctx->tlen[tid]) - lo : ctx->tlen[tid];
+    if (ctx->ranged[tid] && (lo % window || (tlen % window && lo + tlen != ctx->tlen[tid]))) return ctx_fail(ctx, MSD_EINVAL, "msd_windows: the shard [%u, %u) does not start and end on multiples of the window %u", lo, lo + tlen, window);
     const int64_t nw = msd_n_windows(tlen, window);
     if (value_out && value_cap < nw) return ctx_fail(ctx, MSD_EINVAL, "msd_windows: value_cap %lld < %lld windows", (long long)value_cap, (long long)nw);
     if (ctx->pf_valid && window == ctx->pf_window && !use_median && nw > 0 && tid < (int)ctx->pf_slot.size() && ctx->pf_slot[tid] >= 0) {
@@ -906,10 +1025,10 @@ int64_t msd_windows(msd_ctx* ctx, int tid, uint32_t window, int use_median, doub
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_dist512, 0, 8 * kWindowDistBins, sc));
     if (nw > 0) {
         if (use_median)
-            windows_kernel<<<grid_for((uint64_t)nw, 256, kSMs * 8), 256, 0, sc>>>(ctx->d_arena + ctx->depth_off[tid], tlen, window, nw, use_median,
+            windows_kernel<<<grid_for((uint64_t)nw, 256, kSMs * 8), 256, 0, sc>>>(ctx->d_arena + ctx->depth_off[tid] + lo, tlen, window, nw, use_median,
                                                                                 (double*)ctx->d_scratch, ctx->d_racc, ctx->d_dist512);
         else
-            windows_mean_kernel<<<grid_for((uint64_t)nw, kWinWarps * 32, kSMs * 4), kWinWarps * 32, 0, sc>>>(ctx->d_arena + ctx->depth_off[tid], tlen, window, nw,
+            windows_mean_kernel<<<grid_for((uint64_t)nw, kWinWarps * 32, kSMs * 4), kWinWarps * 32, 0, sc>>>(ctx->d_arena + ctx->depth_off[tid] + lo, tlen, window, nw,
                                                                                                      (double*)ctx->d_scratch, ctx->d_racc, ctx->d_dist512);
         MSD_CUDA_OK(cudaGetLastError());
     }

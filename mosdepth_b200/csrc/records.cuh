@@ -29,7 +29,25 @@ struct FilterParams {
 struct ContigTable {
     const uint64_t* depth_off;   // [n_targets] offset (in int32 cells) of the contig's array in the arena; ~0ull = not selected
     const uint32_t* tlen;        // [n_targets]
+    // intra-contig sharding (msd_set_contig_range): this context OWNS the records with range_lo <= pos < range_hi.
+    // Records outside still go through the filters and the mate join (an owned record may have to take its mate from
+    // them), but emit nothing: every +1/-1 and every overlap correction is emitted by the owner of the record that is
+    // being processed when the reference would emit it.  Unsharded contigs: [0, 0xffffffff).
+    const uint32_t* range_lo;    // [n_targets]
+    const uint32_t* range_hi;    // [n_targets]
+    uint32_t* max_end;           // [n_targets] largest end position of an owned record (how far the depth spills past range_hi)
+    unsigned long long* n_beyond;   // [n_targets] records with pos >= range_hi seen: proves that the span covered every owned record
+    MSD_D bool owned(int32_t tid, int32_t pos) const { return (uint32_t)pos >= range_lo[tid] && (uint32_t)pos < range_hi[tid]; }
 };
+
+// only when some contig is sharded (max_end != nullptr): one atomicMax per warp and contig
+MSD_D void note_end(const ContigTable& ct, int32_t tid, int64_t e, uint32_t tlen) {
+    if (!ct.max_end) return;
+    const uint32_t v = (uint32_t)(e < 0 ? 0 : e < (int64_t)tlen ? e : (int64_t)tlen);
+    const unsigned m = __match_any_sync(__activemask(), tid);
+    const uint32_t mx = __reduce_max_sync(m, v);
+    if ((int)(__ffs(m) - 1) == (int)(threadIdx.x & 31)) atomicMax(ct.max_end + tid, mx);
+}
 
 constexpr uint8_t kClsNone = 0, kClsU = 1, kClsE = 2, kClsT = 3;
 
@@ -180,10 +198,14 @@ records_kernel(const uint8_t* __restrict__ buf, const uint32_t* __restrict__ rec
         if (doff == ~0ull) continue;                                          // contig not selected
         const uint32_t tlen = ct.tlen[c.tid];
         if (c.pos < 0 || (uint32_t)c.pos >= tlen) continue;                  // iterator overlap rule: pos < end
+        const bool own = ct.owned(c.tid, c.pos);
         // `found` is set before the filters (mosdepth.nim:272-275): count every record the query would yield
         {
-            unsigned m = __match_any_sync(__activemask(), c.tid);
-            if ((int)(__ffs(m) - 1) == (int)(threadIdx.x & 31)) atomicAdd(n_prefilter + c.tid, (unsigned long long)__popc(m));
+            unsigned m = __match_any_sync(__activemask(), (c.tid << 1) | (own ? 1 : 0));
+            if ((int)(__ffs(m) - 1) == (int)(threadIdx.x & 31)) {
+                if (own) atomicAdd(n_prefilter + c.tid, (unsigned long long)__popc(m));
+                else if ((uint32_t)c.pos >= ct.range_hi[c.tid]) atomicAdd(ct.n_beyond + c.tid, (unsigned long long)__popc(m));
+            }
         }
         if ((int32_t)c.mapq < fp.mapq) continue;                             // :276
         const int64_t ais = c.tlen < 0 ? -(int64_t)c.tlen : (int64_t)c.tlen;
@@ -194,13 +216,18 @@ records_kernel(const uint8_t* __restrict__ buf, const uint32_t* __restrict__ rec
         int32_t* __restrict__ arr = arena + doff;
         const uint32_t cig = p + 36 + c.l_qname;
         if (fp.mode == MSD_MODE_FAST) {                                      // :342-344
+            if (!own) continue;
+            const int64_t stop = rec_endpos(buf, cig, c.n_cigar, c.flag, c.pos);
             depth_add(arr, tlen, c.pos, 1, n_events);
-            depth_add(arr, tlen, rec_endpos(buf, cig, c.n_cigar, c.flag, c.pos), -1, n_events);
+            depth_add(arr, tlen, stop, -1, n_events);
+            note_end(ct, c.tid, stop, tlen);
         } else if (fp.mode == MSD_MODE_FRAGMENT) {                           // :346-353
+            if (!own) continue;
             if ((c.flag & kFlagRead2) || !(c.flag & kFlagProper) || (c.flag & kFlagSupp)) continue;
             int64_t fs = c.pos < c.mpos ? c.pos : c.mpos;
             depth_add(arr, tlen, fs, 1, n_events);
             depth_add(arr, tlen, fs + ais, -1, n_events);
+            note_end(ct, c.tid, fs + ais, tlen);
         } else {
             // classify for the mate join (:292-298) and emit the read's own blocks (:355-356)
             if ((c.flag & kFlagProper) && !(c.flag & kFlagSupp)) {
@@ -212,9 +239,12 @@ records_kernel(const uint8_t* __restrict__ buf, const uint32_t* __restrict__ rec
                 mc.qhash[r] = hash_qname(buf, p + 36, c.l_qname ? c.l_qname - 1 : 0, c.tid);
                 mc.slot[r] = kNoOff;
             }
-            BlockIter it; it.init(buf, cig, c.n_cigar, c.pos);
-            int64_t s, e;
-            while (it.next(s, e)) { depth_add(arr, tlen, s, 1, n_events); depth_add(arr, tlen, e, -1, n_events); }
+            if (own) {
+                BlockIter it; it.init(buf, cig, c.n_cigar, c.pos);
+                int64_t s, e, last_e = c.pos;
+                while (it.next(s, e)) { depth_add(arr, tlen, s, 1, n_events); depth_add(arr, tlen, e, -1, n_events); last_e = e; }
+                note_end(ct, c.tid, last_e, tlen);
+            }
         }
     }
     n_events = __reduce_add_sync(0xffffffffu, n_events);
@@ -359,9 +389,12 @@ __global__ void mate_replay_kernel(MateTable T, LiveList L, LiveList Lnew, const
                 uint32_t m_ncig; int64_t m_start, m_stop; const uint8_t* m_buf; uint32_t m_cig;
                 if (kind == 1) { const LiveEntry& e = L.e[sidx]; m_ncig = e.n_cigar; m_start = e.start; m_stop = e.stop; m_buf = L.arena; m_cig = e.cigar_off; }
                 else { const uint32_t pm = rec_off[sidx]; const RecCore cm = load_core(buf, pm); m_ncig = cm.n_cigar; m_start = cm.pos; m_stop = mc.endpos[sidx]; m_buf = buf; m_cig = pm + 36 + cm.l_qname; }
-                if (cx.n_cigar == 1 && m_ncig == 1) {                         // :307-309
+                if (!ct.owned(cx.tid, cx.pos)) {
+                    // the taker belongs to another shard: that shard applies the correction
+                } else if (cx.n_cigar == 1 && m_ncig == 1) {                  // :307-309
                     depth_add(arr, tlen, cx.pos, -1, n_events);
                     depth_add(arr, tlen, m_stop, 1, n_events);
+                    note_end(ct, cx.tid, m_stop, tlen);
                 } else {                                                      // :323-338
                     BlockIter a, b;
                     a.init(buf, px + 36 + cx.l_qname, cx.n_cigar, cx.pos);

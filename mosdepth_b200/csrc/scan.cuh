@@ -143,4 +143,35 @@ scan_fused_kernel(int32_t* __restrict__ arr, uint32_t n_scan, uint32_t n_stat, u
     for (int i = t; i < kHistSmemBins; i += kScanThreads) { uint32_t c = s_hist[i]; if (c) atomicAdd(&hist[i], (unsigned long long)c); }
 }
 
+// The two whole-contig consumers (inc :417-437, newDepthStat depthstat.nim:39-45) over cells [0, n) of an array that is
+// already a depth array: the shard of a contig after msd_depth_add() (msd_contig_finalize).  Same arithmetic as the
+// do_stats branch of scan_fused_kernel.
+__global__ void __launch_bounds__(256)
+range_stats_kernel(const int32_t* __restrict__ arr, uint32_t n, unsigned long long* __restrict__ hist, ContigAccum* __restrict__ acc) {
+    __shared__ uint32_t s_hist[kHistSmemBins];
+    for (int i = threadIdx.x; i < kHistSmemBins; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    unsigned long long my_sum = 0; uint32_t my_mn = 0xffffffffu, my_mx = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int32_t d = __ldg(arr + i);
+        my_sum += (unsigned long long)(long long)d;
+        const uint32_t u = (uint32_t)d;
+        my_mn = u < my_mn ? u : my_mn; my_mx = u > my_mx ? u : my_mx;
+        hist_add(s_hist, hist, d, 1u);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_sum += __shfl_down_sync(0xffffffffu, my_sum, o);
+        uint32_t a = __shfl_down_sync(0xffffffffu, my_mn, o), b = __shfl_down_sync(0xffffffffu, my_mx, o);
+        my_mn = a < my_mn ? a : my_mn; my_mx = b > my_mx ? b : my_mx;
+    }
+    if ((threadIdx.x & 31) == 0) { if (my_sum) atomicAdd(&acc->cum_depth, my_sum); atomicMin(&acc->min_depth, my_mn); atomicMax(&acc->max_depth, my_mx); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHistSmemBins; i += blockDim.x) { const uint32_t c = s_hist[i]; if (c) atomicAdd(&hist[i], (unsigned long long)c); }
+}
+
+__global__ void add_cells_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, uint32_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
 }  // namespace msd

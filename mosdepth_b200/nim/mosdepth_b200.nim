@@ -31,6 +31,11 @@ proc msd_contig_records*(ctx: MsdCtx, tid: cint, n: ptr int64): cint {.importc, 
 proc msd_contig_stats*(ctx: MsdCtx, tid: cint, stat: ptr MsdDepthStat, dist: ptr int64, dist_cap: int64, dist_len: ptr int64): cint {.importc, dynlib: libmsd.}
 proc msd_n_windows*(tlen, window: uint32): int64 {.importc, dynlib: libmsd.}
 proc msd_prefetch_windows*(ctx: MsdCtx, window: uint32): cint {.importc, dynlib: libmsd.}
+proc msd_set_contig_range*(ctx: MsdCtx, tid: cint, lo, hi: uint32): cint {.importc, dynlib: libmsd.}
+proc msd_contig_spill*(ctx: MsdCtx, tid: cint, `from`, n: ptr uint32): cint {.importc, dynlib: libmsd.}
+proc msd_depth_copy*(ctx: MsdCtx, tid: cint, pos, n: uint32, dst: ptr int32, dst_is_device: cint): cint {.importc, dynlib: libmsd.}
+proc msd_depth_add*(ctx: MsdCtx, tid: cint, pos, n: uint32, src: ptr int32, src_is_device: cint): cint {.importc, dynlib: libmsd.}
+proc msd_contig_finalize*(ctx: MsdCtx, tid: cint): cint {.importc, dynlib: libmsd.}
 proc msd_windows*(ctx: MsdCtx, tid: cint, window: uint32, use_median: cint, value_out: ptr float64, value_cap: int64,
                   region_stat: ptr MsdDepthStat, region_dist512: ptr int64): int64 {.importc, dynlib: libmsd.}
 proc msd_regions*(ctx: MsdCtx, tid: cint, n: int64, start, stop: ptr uint32, use_median: cint, value_out: ptr float64,

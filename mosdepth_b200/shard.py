@@ -40,6 +40,63 @@ def merge_adjacent_spans(begs, ends, max_gap_bytes=1 << 20):
     return [o[0] for o in out], [o[1] for o in out]
 
 
+def split_contig(ci, tlen, n_parts, window=0, margin_bp=65536, beyond_windows=8):
+    """Intra-contig sharding: cut one contig into n_parts position ranges of roughly equal
+    compressed size at BAI linear-index entries (16,384-bp windows), cut positions being multiples of
+    lcm(16384, window) so that no --by window straddles a cut.  Returns a list of (lo, hi, voff_beg, voff_end):
+    part i owns the records with lo <= pos < hi; its span starts `margin_bp` before lo (default mode: an owned record may
+    have to take its mate from there) and ends `beyond_windows` index windows after hi, so that it holds every owned
+    record and at least one record at or beyond hi (the library checks that).  Fewer parts come back when the contig
+    has too few possible cut positions."""
+    import math
+    lin = list(ci.linear)
+    if n_parts <= 1 or not ci.has_data or len(lin) < 2:
+        return [(0, tlen, ci.ref_beg, ci.ref_end)]
+    align = 16384 if not window else 16384 * window // math.gcd(16384, window)
+
+    def voff_at_window(w):
+        if w <= 0:
+            return ci.ref_beg
+        if w >= len(lin):
+            return ci.ref_end
+        return lin[w] if lin[w] else ci.ref_beg
+
+    beg_c, end_c = ci.ref_beg >> 16, ci.ref_end >> 16
+    cuts = []
+    for i in range(1, n_parts):
+        target = beg_c + (end_c - beg_c) * i // n_parts
+        w = next((k for k in range(len(lin)) if lin[k] and (lin[k] >> 16) >= target), len(lin))
+        cut = (w * 16384 + align // 2) // align * align
+        if cut <= (cuts[-1] if cuts else 0) or cut >= tlen:
+            continue
+        cuts.append(cut)
+    bounds = [0] + cuts + [tlen]
+    parts = []
+    for i in range(len(bounds) - 1):
+        lo, hi = bounds[i], bounds[i + 1]
+        vb = ci.ref_beg if lo == 0 else voff_at_window(max(0, (lo - margin_bp) // 16384))
+        ve = ci.ref_end if hi >= tlen else voff_at_window(hi // 16384 + beyond_windows)
+        parts.append((lo, hi, vb, ve))
+    return parts
+
+
+def exchange_spill(ctx, tid, rank_prev, rank_next, send, recv, lo, hi):
+    """The carry across a shard boundary: copy out the depth this shard's reads leave beyond its hi, hand it to the next
+    shard and add what the previous shard hands over (include/mosdepth_b200.h, "intra-contig sharding").
+    send(dst_rank, array) / recv(src_rank) -> array move int32 numpy arrays between ranks (None: no such neighbour)."""
+    start, n = ctx.contig_spill(tid)
+    mine = ctx.depth_copy(tid, start, n) if (n and rank_next is not None) else np.zeros(0, dtype=np.int32)
+    if rank_next is not None:
+        send(rank_next, mine)
+    if rank_prev is not None:
+        got = recv(rank_prev)
+        if got.size > hi - lo:
+            raise ValueError("a shard is shorter than the reach of its predecessor's reads")
+        if got.size:
+            ctx.depth_add(tid, lo, got)
+    ctx.contig_finalize(tid)
+
+
 def _block_len(f, coff):
     f.seek(coff)
     h = f.read(18)

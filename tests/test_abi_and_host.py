@@ -120,3 +120,53 @@ def test_generator_is_thread_count_independent(built, tmp_path):
     from mosdepth_b200 import hostio
     a = hostio.inflate_all((tmp_path / "t1.bam").read_bytes()); b = hostio.inflate_all((tmp_path / "t5.bam").read_bytes())
     assert a == b
+
+
+def test_split_contig_spans_hold_every_owned_record(tmp_path):
+    """Intra-contig sharding, host side (no GPU): cuts are aligned to the index windows and the --by window, the parts
+    partition [0, tlen), and the span of each part contains every record it owns plus one at or beyond its end."""
+    import struct
+    from mosdepth_b200 import hostio
+    from mosdepth_b200.shard import split_contig
+    bam = tmp_path / "c2.bam"
+    subprocess.run([str(ROOT / "tools" / "gen_bam"), "--config", "c2", "--genome-fraction", "0.008", "--threads", "2", "-o", str(bam)], check=True, capture_output=True)
+    hdr = hostio.read_bam_header(bam); index = hostio.read_index(bam)
+    data = bam.read_bytes()
+    tid, tlen = 0, hdr.lengths[0]
+
+    def positions(vb, ve):
+        pos, stream, first = vb >> 16, b"", True
+        end_c, end_u = ve >> 16, ve & 0xFFFF
+        for p, bl, xl, isz in hostio.iter_bgzf_blocks(data, pos):
+            if p > end_c or (p == end_c and end_u == 0):
+                break
+            blk = hostio.inflate_block(data, p, bl, xl)
+            if p == end_c:
+                blk = blk[:end_u]
+            if first:
+                blk = blk[vb & 0xFFFF:]; first = False
+            stream += blk
+        out, o = [], 0
+        while o + 12 <= len(stream):
+            bs, t, ps = struct.unpack_from("<iii", stream, o)
+            if o + 4 + bs > len(stream):
+                break
+            if t == tid:
+                out.append(ps)
+            o += 4 + bs
+        return out
+
+    every = positions(index[tid].ref_beg, index[tid].ref_end)
+    for n_parts in (2, 4):
+        parts = split_contig(index[tid], tlen, n_parts, window=512)
+        assert len(parts) == n_parts
+        assert parts[0][0] == 0 and parts[-1][1] == tlen and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        owned_total = 0
+        for lo, hi, vb, ve in parts:
+            assert lo % 16384 == 0 and lo % 512 == 0
+            got = positions(vb, ve)
+            owned = [p for p in got if lo <= p < hi]
+            assert len(owned) == sum(1 for p in every if lo <= p < hi)
+            assert hi == tlen or any(p >= hi for p in got)
+            owned_total += len(owned)
+        assert owned_total == len(every)
