@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--seed", type=int, default=20261022)
     ap.add_argument("--window", type=int, default=500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharding", default="contigs", choices=["contigs", "intra"],
+                    help="N > 1: whole contigs per rank (LPT, no data-path exchange) or every contig cut into N position ranges (depth spill exchanged over NCCL)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)
@@ -159,6 +161,8 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
         ensure_built()
@@ -166,7 +170,7 @@ def main():
         dist.barrier()
     import mosdepth_b200 as m
     from mosdepth_b200 import hostio
-    from mosdepth_b200.shard import contig_weights, load_compact, lpt_shards, merge_adjacent_spans
+    from mosdepth_b200.shard import contig_weights, load_compact, lpt_shards, merge_adjacent_spans, split_contig
 
     # ---- data: weak scaling = every rank count sees `fraction * world` of the genome, i.e. fixed work per GPU --------
     fraction = args.genome_fraction * world
@@ -180,11 +184,29 @@ def main():
     index = hostio.read_index(bam)
     nt = len(hdr.names)
     weights = contig_weights(index)
-    shards = lpt_shards(weights, world)
-    mine = shards[rank]
+    intra = args.sharding == "intra" and world > 1
+    parts = {}      # tid -> (lo, hi) owned by this rank (intra-contig sharding)
+    if intra:
+        # every contig is cut into `world` position ranges at index windows; rank r owns range r of every contig
+        mine, sb, se = [], [], []
+        for t in range(nt):
+            if weights[t] <= 0:
+                continue
+            pr = split_contig(index[t], hdr.lengths[t], world, window=args.window)
+            if len(pr) != world:            # too short to cut (chrM): rank 0 takes it whole
+                if rank == 0:
+                    mine.append(t); sb.append(index[t].ref_beg); se.append(index[t].ref_end)
+                continue
+            lo, hi, vb, ve = pr[rank]
+            mine.append(t); parts[t] = (lo, hi); sb.append(vb); se.append(ve)
+        my_reads = None
+        begs, ends = merge_adjacent_spans(sb, se)
+    else:
+        shards = lpt_shards(weights, world)
+        mine = shards[rank]
+        begs, ends = merge_adjacent_spans([index[t].ref_beg for t in mine], [index[t].ref_end for t in mine])
+        my_reads = sum(index[t].n_mapped + index[t].n_unmapped for t in mine)
     want = np.zeros(nt, dtype=np.uint8); want[mine] = 1
-    begs, ends = merge_adjacent_spans([index[t].ref_beg for t in mine], [index[t].ref_end for t in mine])
-    my_reads = sum(index[t].n_mapped + index[t].n_unmapped for t in mine)
 
     # pinned host image of this rank's byte ranges of the BAM file (the e2e input), virtual offsets rebased onto it
     keep = {}
@@ -202,6 +224,8 @@ def main():
     ctx.set_spans(begs, ends)
     ctx.set_filters(mode=m.MODE_FAST)   # -x; defaults -F 1796 -Q 0
     ctx.prefetch_windows(args.window)   # --by 500: the host will ask for every contig's windows
+    for t, (lo, hi) in parts.items():
+        ctx.set_contig_range(t, lo, hi)
     g_ptr, r_ptr, n_bins, s_ptr = ctx.totals_device()
 
     class DevView:
@@ -213,16 +237,54 @@ def main():
     tot_s = torch.as_tensor(DevView(s_ptr, 8), device=f"cuda:{local}")
 
     d2h = {"bytes": 0}
+    check = {}
+
+    def exchange_spills():
+        """Intra-contig sharding: the depth that this rank's reads leave beyond the end of its ranges goes to the next rank
+        (one NCCL send/recv pair per neighbour, straight out of / into GPU memory), then every shard is finalised."""
+        dev = f"cuda:{local}"
+        tids = sorted(parts)
+        spill = [ctx.contig_spill(t) for t in tids]
+        n_out = torch.tensor([n for _, n in spill], dtype=torch.int64, device=dev)
+        all_n = [torch.zeros_like(n_out) for _ in range(world)]
+        dist.all_gather(all_n, n_out)
+        send_buf = torch.empty(max(int(n_out.sum()), 1), dtype=torch.int32, device=dev)
+        off = 0
+        for t, (start, n) in zip(tids, spill):
+            if n and rank + 1 < world:
+                ctx.depth_copy(t, start, n, device_ptr=send_buf.data_ptr() + 4 * off)
+            off += n
+        n_in = all_n[rank - 1].tolist() if rank > 0 else [0] * len(tids)
+        recv_buf = torch.empty(max(sum(n_in), 1), dtype=torch.int32, device=dev)
+        ops = []
+        if rank + 1 < world and int(n_out.sum()):
+            ops.append(dist.P2POp(dist.isend, send_buf[:int(n_out.sum())], rank + 1))
+        if rank > 0 and sum(n_in):
+            ops.append(dist.P2POp(dist.irecv, recv_buf[:sum(n_in)], rank - 1))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        torch.cuda.synchronize()
+        off = 0
+        for t, n in zip(tids, n_in):
+            if n:
+                ctx.depth_add(t, parts[t][0], device_ptr=recv_buf.data_ptr() + 4 * off, n=n)
+            off += n
+            ctx.contig_finalize(t)
+        return 4 * int(n_out.sum())
 
     def step():
         """One pass of the hot path for this rank's contigs + the cross-rank reduction of the totals."""
         ctx.totals_reset()
         info = ctx.run()
         nbytes = 0
+        if parts:
+            nbytes += exchange_spills()
         for t in mine:
-            rc, _n = ctx.contig_records(t)
-            if rc < 0:
-                continue
+            if t not in parts:
+                rc, _n = ctx.contig_records(t)
+                if rc < 0:
+                    continue
             st, distv = ctx.contig_stats(t)
             vals, rst, rdist = ctx.windows(t, args.window)
             nbytes += vals.nbytes + rdist.nbytes + distv.nbytes + 48
@@ -231,6 +293,9 @@ def main():
             mm = torch.stack([tot_s[2], tot_s[6]]); dist.all_reduce(mm, op=dist.ReduceOp.MIN)
             mx = torch.stack([tot_s[3], tot_s[7]]); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             sums = torch.stack([tot_s[0], tot_s[1], tot_s[4], tot_s[5]]); dist.all_reduce(sums)
+            check["totals"] = [int(tot_g[:1024].sum()), int((tot_g[:1024] * torch.arange(1024, device=tot_g.device)).sum()), int(tot_r[:512].sum()), int(sums[0]), int(sums[1]), int(mm[0]), int(mx[0])]
+        else:
+            check["totals"] = [int(tot_g[:1024].sum()), int((tot_g[:1024] * torch.arange(1024, device=tot_g.device)).sum()), int(tot_r[:512].sum()), int(tot_s[0]), int(tot_s[1]), int(tot_s[2]), int(tot_s[3])]
         d2h["bytes"] = nbytes
         return info
 
@@ -312,7 +377,8 @@ def main():
         line = {"metric": "reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                 "config": {"workload": f"C3 synthetic 30X WGS (25 GRCh38 contigs x {fraction:g}, 150-bp pairs) --by {args.window} -n -x", "genome_fraction": fraction,
-                           "reads": n_reads, "bam_bytes": n_bytes, "flags": f"--by {args.window} -n -x", "sharding": f"contigs LPT over {world} GPU(s)",
+                           "reads": n_reads, "bam_bytes": n_bytes, "flags": f"--by {args.window} -n -x", "sharding": (f"every contig cut into {world} position ranges, depth spill over NCCL send/recv" if intra else f"contigs LPT over {world} GPU(s)"),
+                           "totals_check": check.get("totals"),
                            "l2": "inputs (compressed BAM, depth arrays) are far larger than the 126 MB L2; no flush needed",
                            "wall_s_per_step": wall_res / 1e3, "extrapolated_full_genome_wall_s": (ms_res / 1e3) / fraction * world},
                 "e2e": {"value": e2e_val, "unit": "reads/s", "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e,

@@ -95,3 +95,75 @@ def test_two_rank_sharding_and_reduction(tmp_path):
     assert mn == 0 and mx == len(index) - 1
     assert sum(sizes) == sum(1 for w in want if w)
     assert used < os.path.getsize(bam)   # each rank reads only its own byte ranges
+
+
+class _FakeShard:
+    """numpy stand-in for a Context that holds one shard of a contig after msd_run(): `own` is the depth of the shard's own
+    reads over the whole contig (zero before lo).  Implements the calls exchange_spill() makes."""
+
+    def __init__(self, own, lo, hi):
+        self.arr = own.astype(np.int32).copy(); self.lo, self.hi = lo, hi; self.final = False
+
+    def contig_spill(self, tid):
+        nz = np.nonzero(self.arr[self.hi:])[0]
+        return self.hi, (int(nz[-1]) + 1 if nz.size else 0)
+
+    def depth_copy(self, tid, pos, n):
+        return self.arr[pos:pos + n].copy()
+
+    def depth_add(self, tid, pos, cells):
+        self.arr[pos:pos + cells.size] += cells
+
+    def contig_finalize(self, tid):
+        self.final = True
+
+
+def _spill_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, str(ROOT))
+    from mosdepth_b200.shard import exchange_spill
+    tlen, read_len = 4000, 150
+    rng = np.random.default_rng(5)
+    starts = np.sort(rng.integers(0, tlen - read_len, 900))
+    cuts = [0, 1024, 2048 + 512, tlen][: world + 1]; cuts[-1] = tlen
+    lo, hi = cuts[rank], cuts[rank + 1]
+    own = np.zeros(tlen + 1, dtype=np.int64)
+    for s in starts[(starts >= lo) & (starts < hi)]:
+        own[s] += 1; own[s + read_len] -= 1
+    shard = _FakeShard(np.cumsum(own), lo, hi)
+
+    def send(dst, a):
+        dist.send(torch.tensor([a.size], dtype=torch.int64), dst)
+        if a.size:
+            dist.send(torch.from_numpy(a.copy()), dst)
+
+    def recv(src):
+        n = torch.zeros(1, dtype=torch.int64); dist.recv(n, src)
+        t = torch.zeros(int(n), dtype=torch.int32)
+        if int(n):
+            dist.recv(t, src)
+        return t.numpy()
+
+    exchange_spill(shard, 0, rank - 1 if rank > 0 else None, rank + 1 if rank + 1 < world else None, send, recv, lo, hi)
+    full = np.zeros(tlen + 1, dtype=np.int64)
+    for s in starts:
+        full[s] += 1; full[s + read_len] -= 1
+    want = np.cumsum(full)[lo:hi]
+    q.put((rank, bool(shard.final and np.array_equal(shard.arr[lo:hi], want))))
+    dist.destroy_process_group()
+
+
+def test_spill_exchange_between_ranks():
+    """The depth carry across shard boundaries (shard.exchange_spill) over gloo send/recv, world size 3."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_spill_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(3))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == {0: True, 1: True, 2: True}
