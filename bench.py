@@ -146,8 +146,8 @@ def main():
     ap.add_argument("--seed", type=int, default=20261022)
     ap.add_argument("--window", type=int, default=500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sharding", default="contigs", choices=["contigs", "intra"],
-                    help="N > 1: whole contigs per rank (LPT, no data-path exchange) or every contig cut into N position ranges (depth spill exchanged over NCCL)")
+    ap.add_argument("--sharding", default="offsets", choices=["contigs", "offsets", "intra"],
+                    help="N > 1: whole contigs per rank (LPT, no data-path exchange); N equal BGZF offset ranges of the file, cut inside contigs (the depth that reads leave beyond a cut goes to the next rank over NCCL); or every contig cut into N ranges")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)
@@ -161,8 +161,7 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / debug lines: off stdout, rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
         ensure_built()
@@ -170,7 +169,7 @@ def main():
         dist.barrier()
     import mosdepth_b200 as m
     from mosdepth_b200 import hostio
-    from mosdepth_b200.shard import contig_weights, load_compact, lpt_shards, merge_adjacent_spans, split_contig
+    from mosdepth_b200.shard import contig_weights, load_compact, lpt_shards, merge_adjacent_spans, offset_shards, split_contig
 
     # ---- data: weak scaling = every rank count sees `fraction * world` of the genome, i.e. fixed work per GPU --------
     fraction = args.genome_fraction * world
@@ -199,13 +198,19 @@ def main():
                 continue
             lo, hi, vb, ve = pr[rank]
             mine.append(t); parts[t] = (lo, hi); sb.append(vb); se.append(ve)
-        my_reads = None
+        begs, ends = merge_adjacent_spans(sb, se)
+    elif args.sharding == "offsets" and world > 1:
+        intra = True
+        mine, sb, se = [], [], []
+        for t, lo, hi, vb, ve in offset_shards(index, hdr.lengths, world, window=args.window)[rank]:
+            mine.append(t); sb.append(vb); se.append(ve)
+            if lo > 0 or hi < hdr.lengths[t]:
+                parts[t] = (lo, hi)
         begs, ends = merge_adjacent_spans(sb, se)
     else:
         shards = lpt_shards(weights, world)
         mine = shards[rank]
         begs, ends = merge_adjacent_spans([index[t].ref_beg for t in mine], [index[t].ref_end for t in mine])
-        my_reads = sum(index[t].n_mapped + index[t].n_unmapped for t in mine)
     want = np.zeros(nt, dtype=np.uint8); want[mine] = 1
 
     # pinned host image of this rank's byte ranges of the BAM file (the e2e input), virtual offsets rebased onto it
@@ -240,25 +245,31 @@ def main():
     check = {}
 
     def exchange_spills():
-        """Intra-contig sharding: the depth that this rank's reads leave beyond the end of its ranges goes to the next rank
-        (one NCCL send/recv pair per neighbour, straight out of / into GPU memory), then every shard is finalised."""
+        """Sharding inside contigs: the depth that this rank's reads leave beyond the end of a range it owns goes to the rank
+        that owns the next range of that contig (always rank + 1): one NCCL send/recv pair per neighbour, straight out of /
+        into GPU memory; then every shard is finalised."""
         dev = f"cuda:{local}"
-        tids = sorted(parts)
-        spill = [ctx.contig_spill(t) for t in tids]
-        n_out = torch.tensor([n for _, n in spill], dtype=torch.int64, device=dev)
+        out_t = [t for t in sorted(parts) if parts[t][1] < hdr.lengths[t]]     # ranges that end inside their contig
+        in_t = [t for t in sorted(parts) if parts[t][0] > 0]                   # ranges that start inside their contig
+        n_out = torch.zeros(nt, dtype=torch.int64, device=dev)
+        spill = {t: ctx.contig_spill(t) for t in out_t}
+        for t in out_t:
+            n_out[t] = spill[t][1]
         all_n = [torch.zeros_like(n_out) for _ in range(world)]
         dist.all_gather(all_n, n_out)
-        send_buf = torch.empty(max(int(n_out.sum()), 1), dtype=torch.int32, device=dev)
+        total_out = int(n_out.sum())
+        send_buf = torch.empty(max(total_out, 1), dtype=torch.int32, device=dev)
         off = 0
-        for t, (start, n) in zip(tids, spill):
-            if n and rank + 1 < world:
+        for t in out_t:
+            start, n = spill[t]
+            if n:
                 ctx.depth_copy(t, start, n, device_ptr=send_buf.data_ptr() + 4 * off)
             off += n
-        n_in = all_n[rank - 1].tolist() if rank > 0 else [0] * len(tids)
+        n_in = [int(all_n[rank - 1][t]) for t in in_t] if rank > 0 else []
         recv_buf = torch.empty(max(sum(n_in), 1), dtype=torch.int32, device=dev)
         ops = []
-        if rank + 1 < world and int(n_out.sum()):
-            ops.append(dist.P2POp(dist.isend, send_buf[:int(n_out.sum())], rank + 1))
+        if rank + 1 < world and total_out:
+            ops.append(dist.P2POp(dist.isend, send_buf[:total_out], rank + 1))
         if rank > 0 and sum(n_in):
             ops.append(dist.P2POp(dist.irecv, recv_buf[:sum(n_in)], rank - 1))
         if ops:
@@ -266,12 +277,13 @@ def main():
                 r.wait()
         torch.cuda.synchronize()
         off = 0
-        for t, n in zip(tids, n_in):
+        for t, n in zip(in_t, n_in):
             if n:
                 ctx.depth_add(t, parts[t][0], device_ptr=recv_buf.data_ptr() + 4 * off, n=n)
             off += n
+        for t in sorted(parts):
             ctx.contig_finalize(t)
-        return 4 * int(n_out.sum())
+        return 4 * total_out
 
     def step():
         """One pass of the hot path for this rank's contigs + the cross-rank reduction of the totals."""
@@ -377,7 +389,7 @@ def main():
         line = {"metric": "reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                 "config": {"workload": f"C3 synthetic 30X WGS (25 GRCh38 contigs x {fraction:g}, 150-bp pairs) --by {args.window} -n -x", "genome_fraction": fraction,
-                           "reads": n_reads, "bam_bytes": n_bytes, "flags": f"--by {args.window} -n -x", "sharding": (f"every contig cut into {world} position ranges, depth spill over NCCL send/recv" if intra else f"contigs LPT over {world} GPU(s)"),
+                           "reads": n_reads, "bam_bytes": n_bytes, "flags": f"--by {args.window} -n -x", "sharding": (f"{world} equal BGZF offset ranges cut inside contigs, depth spill to the next rank over NCCL send/recv" if (args.sharding == "offsets" and world > 1) else f"every contig cut into {world} position ranges, depth spill over NCCL send/recv" if intra else f"contigs LPT over {world} GPU(s)"),
                            "totals_check": check.get("totals"),
                            "l2": "inputs (compressed BAM, depth arrays) are far larger than the 126 MB L2; no flush needed",
                            "wall_s_per_step": wall_res / 1e3, "extrapolated_full_genome_wall_s": (ms_res / 1e3) / fraction * world},

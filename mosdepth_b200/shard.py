@@ -42,8 +42,8 @@ def merge_adjacent_spans(begs, ends, max_gap_bytes=1 << 20):
 
 def split_contig(ci, tlen, n_parts, window=0, margin_bp=65536, beyond_windows=8):
     """Intra-contig sharding: cut one contig into n_parts position ranges of roughly equal
-    compressed size at BAI linear-index entries (16,384-bp windows), cut positions being multiples of
-    lcm(16384, window) so that no --by window straddles a cut.  Returns a list of (lo, hi, voff_beg, voff_end):
+    compressed size near BAI linear-index entries (16,384-bp windows), cut positions being multiples of
+    lcm(32, window) so that no --by window straddles a cut.  Returns a list of (lo, hi, voff_beg, voff_end):
     part i owns the records with lo <= pos < hi; its span starts `margin_bp` before lo (default mode: an owned record may
     have to take its mate from there) and ends `beyond_windows` index windows after hi, so that it holds every owned
     record and at least one record at or beyond hi (the library checks that).  Fewer parts come back when the contig
@@ -52,7 +52,7 @@ def split_contig(ci, tlen, n_parts, window=0, margin_bp=65536, beyond_windows=8)
     lin = list(ci.linear)
     if n_parts <= 1 or not ci.has_data or len(lin) < 2:
         return [(0, tlen, ci.ref_beg, ci.ref_end)]
-    align = 16384 if not window else 16384 * window // math.gcd(16384, window)
+    align = 32 if not window else 32 * window // math.gcd(32, window)   # scans are 128-bit aligned; no window straddles a cut
 
     def voff_at_window(w):
         if w <= 0:
@@ -78,6 +78,62 @@ def split_contig(ci, tlen, n_parts, window=0, margin_bp=65536, beyond_windows=8)
         ve = ci.ref_end if hi >= tlen else voff_at_window(hi // 16384 + beyond_windows)
         parts.append((lo, hi, vb, ve))
     return parts
+
+
+def offset_shards(index, lengths, n, window=0, margin_bp=65536, beyond_windows=8):
+    """Shard the genome into n contiguous BGZF offset ranges of equal compressed size (north_star: "index-derived BGZF
+    offset ranges"): the cuts fall inside contigs, at BAI linear-index entries aligned like split_contig()'s.  Returns,
+    per rank, a list of (tid, lo, hi, voff_beg, voff_end) in file order; lo == 0 and hi == tlen mark a whole contig.  A
+    rank's pieces are adjacent in the file, so they merge into one span; only the (at most two) cut contigs of a rank
+    need the spill exchange."""
+    import math
+    have = [t for t in range(len(index)) if index[t].has_data]
+    if not have:
+        return [[] for _ in range(n)]
+    align = 32 if not window else 32 * window // math.gcd(32, window)   # scans are 128-bit aligned; no window straddles a cut
+    c_beg, c_end = index[have[0]].ref_beg >> 16, index[have[-1]].ref_end >> 16
+    # cut k (1 <= k < n) -> (tid, position); position 0 means "at the start of contig tid"
+    cuts = []
+    for k in range(1, n):
+        target = c_beg + (c_end - c_beg) * k // n
+        t = next((t for t in have if (index[t].ref_end >> 16) > target), have[-1])
+        lin, tlen = index[t].linear, lengths[t]
+        w = next((j for j in range(len(lin)) if lin[j] and (lin[j] >> 16) >= target), len(lin))
+        pos = (w * 16384 + align // 2) // align * align
+        if pos >= tlen:            # nearer to the end of the contig: cut at the next contig's start
+            nxt = [u for u in have if u > t]
+            if not nxt:
+                continue
+            t, pos = nxt[0], 0
+        if cuts and (t, pos) <= cuts[-1]:
+            continue
+        cuts.append((t, pos))
+    bounds = [(have[0], 0)] + cuts + [(None, 0)]
+    out = []
+    for r in range(len(bounds) - 1):
+        (t0, p0), (t1, p1) = bounds[r], bounds[r + 1]
+        pieces = []
+        for t in have:
+            if t < t0 or (t1 is not None and (t > t1 or (t == t1 and p1 == 0))):
+                continue
+            lo = p0 if t == t0 else 0
+            hi = p1 if (t1 is not None and t == t1) else lengths[t]
+            ci, lin = index[t], index[t].linear
+
+            def voff_at(wi, ci=ci, lin=lin):
+                if wi <= 0:
+                    return ci.ref_beg
+                if wi >= len(lin):
+                    return ci.ref_end
+                return lin[wi] if lin[wi] else ci.ref_beg
+
+            vb = ci.ref_beg if lo == 0 else voff_at(max(0, (lo - margin_bp) // 16384))
+            ve = ci.ref_end if hi >= lengths[t] else voff_at(hi // 16384 + beyond_windows)
+            pieces.append((t, lo, hi, vb, ve))
+        out.append(pieces)
+    while len(out) < n:
+        out.append([])
+    return out
 
 
 def exchange_spill(ctx, tid, rank_prev, rank_next, send, recv, lo, hi):

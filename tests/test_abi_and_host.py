@@ -158,12 +158,12 @@ def test_split_contig_spans_hold_every_owned_record(tmp_path):
 
     every = positions(index[tid].ref_beg, index[tid].ref_end)
     for n_parts in (2, 4):
-        parts = split_contig(index[tid], tlen, n_parts, window=512)
+        parts = split_contig(index[tid], tlen, n_parts, window=500)
         assert len(parts) == n_parts
         assert parts[0][0] == 0 and parts[-1][1] == tlen and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
         owned_total = 0
         for lo, hi, vb, ve in parts:
-            assert lo % 16384 == 0 and lo % 512 == 0
+            assert lo % 32 == 0 and lo % 500 == 0
             got = positions(vb, ve)
             owned = [p for p in got if lo <= p < hi]
             assert len(owned) == sum(1 for p in every if lo <= p < hi)

@@ -24,7 +24,7 @@ def test_sharded_contig_equals_unsharded(bam, mode_name, n_parts):
     from mosdepth_b200 import hostio
     from mosdepth_b200.shard import split_contig
     mode = m.MODE_FAST if mode_name == "fast" else m.MODE_DEFAULT
-    window = 512     # lcm(16384, window) must leave room for cuts in this small contig
+    window = 500
     hdr = hostio.read_bam_header(bam); index = hostio.read_index(bam)
     tid = max(range(len(hdr.names)), key=lambda t: index[t].n_mapped)
     tlen = hdr.lengths[tid]
@@ -41,7 +41,7 @@ def test_sharded_contig_equals_unsharded(bam, mode_name, n_parts):
     assert len(parts) == n_parts and parts[0][0] == 0 and parts[-1][1] == tlen
     ctxs, spills = [], []
     for lo, hi, vb, ve in parts:
-        assert lo % 16384 == 0 and lo % window == 0
+        assert lo % 32 == 0 and lo % window == 0
         c = m.Context(0)
         c.open_mem(data, hdr)
         want = np.zeros(len(hdr.names), dtype=np.uint8); want[tid] = 1
@@ -80,7 +80,7 @@ def test_shard_span_too_short_is_refused(bam):
     hdr = hostio.read_bam_header(bam); index = hostio.read_index(bam)
     tid = max(range(len(hdr.names)), key=lambda t: index[t].n_mapped)
     tlen = hdr.lengths[tid]
-    lo, hi, vb, _ve = split_contig(index[tid], tlen, 2, window=512)[0]
+    lo, hi, vb, _ve = split_contig(index[tid], tlen, 2, window=500)[0]
     ve = index[tid].linear[max(1, hi // 16384 - 4)]   # ends before the cut: not every owned record is inside
     c = m.Context(0)
     c.open_mem(np.frombuffer(bam.read_bytes(), dtype=np.uint8), hdr)
