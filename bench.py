@@ -154,6 +154,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE JSON line (rank 0): everything else that native code prints to fd 1 while we run (NCCL's
+    # version banner under NCCL_DEBUG=VERSION/WARN, for one) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -161,7 +167,6 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / debug lines: off stdout, rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
         ensure_built()
@@ -398,7 +403,7 @@ def main():
                         "stage_ms_per_step": {"h2d": infos_e2e[-1].ms_h2d, "inflate": infos_e2e[-1].ms_inflate, "frame": infos_e2e[-1].ms_frame,
                                               "records": infos_e2e[-1].ms_records, "scan": infos_e2e[-1].ms_scan, "run_total": infos_e2e[-1].ms_total}},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
-        print(json.dumps(line))
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
