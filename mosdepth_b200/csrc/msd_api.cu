@@ -88,6 +88,8 @@ struct msd_ctx {
     // scan + queries
     unsigned long long* d_tile_state = nullptr; uint64_t tile_state_cap = 0; uint32_t* d_scan_ticket = nullptr;
     unsigned long long* d_hist = nullptr; ContigAccum* d_acc = nullptr; RegionAccum* d_racc = nullptr;
+    // per-contig results of msd_run gathered without a host round trip per contig
+    ContigAccum *d_acc_all = nullptr, *h_acc_all = nullptr; unsigned long long* h_hist_keep = nullptr; int acc_all_cap = 0, hist_keep_cap = 0;
     unsigned long long* d_dist512 = nullptr; unsigned long long* d_rdist = nullptr;
     // totals for multi-GPU reduction
     long long* d_tot_global = nullptr; long long* d_tot_region = nullptr; long long* d_tot_stats = nullptr;
@@ -324,6 +326,16 @@ int ensure_scratch(msd_ctx* ctx, uint64_t bytes) {
 __global__ void add_hist_kernel(long long* __restrict__ to, const unsigned long long* __restrict__ from, int n) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { unsigned long long v = from[i]; if (v) to[i] += (long long)v; }
 }
+__global__ void add_stats_dev_kernel(long long* __restrict__ tot, long long cum_length, const ContigAccum* __restrict__ a) {
+    tot[0] += cum_length; tot[1] += (long long)a->cum_depth;
+    if ((long long)a->min_depth < tot[2]) tot[2] = a->min_depth;
+    if ((long long)a->max_depth > tot[3]) tot[3] = a->max_depth;
+}
+__global__ void init_acc_all_kernel(ContigAccum* a, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { a[i].cum_depth = 0; a[i].min_depth = 0xffffffffu; a[i].max_depth = 0; a[i].neg_seen = 0; a[i].pad = 0; }
+}
+
 __global__ void add_stats_kernel(long long* __restrict__ tot, long long cum_length, unsigned long long cum_depth, unsigned int mn, unsigned int mx) {
     tot[0] += cum_length; tot[1] += (long long)cum_depth;
     if ((long long)mn < tot[2]) tot[2] = mn;
@@ -341,13 +353,13 @@ double sum_ms(const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v) {
     double s = 0; for (auto& p : v) { float ms = 0; if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) s += ms; } return s;
 }
 
-int run_scan(msd_ctx* ctx, int32_t* arr, uint32_t n_scan, uint32_t n_stat, int do_stats) {
+int run_scan(msd_ctx* ctx, int32_t* arr, uint32_t n_scan, uint32_t n_stat, int do_stats, ContigAccum* acc = nullptr) {
     const uint64_t n_tiles = ((uint64_t)n_scan + kScanTile - 1) / kScanTile;
     if (n_tiles > ctx->tile_state_cap) { int rc = dev_alloc(ctx, &ctx->d_tile_state, n_tiles); if (rc) return rc; ctx->tile_state_cap = n_tiles; }
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_tile_state, 0, n_tiles * 8, ctx->s_compute));
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_scan_ticket, 0, 4, ctx->s_compute));
     const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)kSMs * 8);
-    scan_fused_kernel<<<grid, kScanThreads, 0, ctx->s_compute>>>(arr, n_scan, n_stat, ctx->d_tile_state, ctx->d_scan_ticket, ctx->d_hist, ctx->d_acc, do_stats);
+    scan_fused_kernel<<<grid, kScanThreads, 0, ctx->s_compute>>>(arr, n_scan, n_stat, ctx->d_tile_state, ctx->d_scan_ticket, ctx->d_hist, acc ? acc : ctx->d_acc, do_stats);
     ctx->info.n_launches++;
     MSD_CUDA_OK(cudaGetLastError());
     return 0;
@@ -472,6 +484,7 @@ void msd_destroy(msd_ctx* ctx) {
     if (ctx->h_run_stop) cudaFreeHost(ctx->h_run_stop);
     if (ctx->h_run_val) cudaFreeHost(ctx->h_run_val);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    dev_free(&ctx->d_acc_all); if (ctx->h_acc_all) cudaFreeHost(ctx->h_acc_all); if (ctx->h_hist_keep) cudaFreeHost(ctx->h_hist_keep);
     dev_free(&ctx->d_pf_values); dev_free(&ctx->d_pf_acc); dev_free(&ctx->d_pf_dist); dev_free(&ctx->d_pf_table);
     if (ctx->h_pf_values) cudaFreeHost(ctx->h_pf_values); if (ctx->h_pf_acc) cudaFreeHost(ctx->h_pf_acc); if (ctx->h_pf_dist) cudaFreeHost(ctx->h_pf_dist); if (ctx->h_pf_table) cudaFreeHost(ctx->h_pf_table);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -691,7 +704,7 @@ int msd_run(msd_ctx* ctx) {
             // when the compressed bytes still have to cross PCIe, the first chunks are small so that the pipeline
             // (copy k+1 | inflate k) starts after a few milliseconds instead of after a full-size copy
             const bool will_copy = !(ctx->d_staged && pos >= ctx->staged_beg && pos < ctx->staged_end);
-            const uint32_t blk_limit = !will_copy ? ctx->max_blocks : std::min<uint32_t>(ctx->max_blocks, chunk_idx == 0 ? ramp0 : copy_blocks);
+            const uint32_t blk_limit = !will_copy ? ctx->max_blocks : std::min<uint32_t>(ctx->max_blocks, chunk_idx == 0 ? ramp0 : copy_blocks);   // (a small first chunk for resident input was tried: 5 chunks on 4 slots, 43.3 vs 39.2 ms)
             while (nb < blk_limit) {
                 if (pos >= N || pos > end_c || (pos == end_c && end_u == 0)) { span_done = true; break; }
                 uint32_t xlen = 0, isize = 0;
@@ -823,6 +836,25 @@ int msd_run(msd_ctx* ctx) {
     MSD_CUDA_OK(cudaMemcpy(npre.data(), ctx->d_nprefilter, sizeof(unsigned long long) * ctx->n_targets, cudaMemcpyDeviceToHost));
     cudaEvent_t s0 = next_event(ctx), s1 = next_event(ctx);
     MSD_CUDA_OK(cudaEventRecord(s0, sc));
+    // contigs that get the whole-contig scan: their stats are gathered asynchronously unless there are very many of them
+    constexpr int kHistKeep = 4096;
+    std::vector<int> keep_slot(ctx->n_targets, -1); int n_scan_contigs = 0;
+    for (int t = 0; t < ctx->n_targets; t++) if (ctx->want[t] && npre[t] && !ctx->ranged[t]) keep_slot[t] = n_scan_contigs++;
+    const bool async_stats = n_scan_contigs > 0 && n_scan_contigs <= 2048 && !getenv("MSD_SYNC_STATS");
+    if (async_stats) {
+        if (ctx->n_targets > ctx->acc_all_cap) {
+            dev_free(&ctx->d_acc_all); if (ctx->h_acc_all) { cudaFreeHost(ctx->h_acc_all); ctx->h_acc_all = nullptr; }
+            if ((rc = dev_alloc(ctx, &ctx->d_acc_all, (uint64_t)ctx->n_targets))) return rc;
+            MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_acc_all, sizeof(ContigAccum) * ctx->n_targets));
+            ctx->acc_all_cap = ctx->n_targets;
+        }
+        if (n_scan_contigs > ctx->hist_keep_cap) {
+            if (ctx->h_hist_keep) { cudaFreeHost(ctx->h_hist_keep); ctx->h_hist_keep = nullptr; }
+            MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_hist_keep, 8ull * kHistKeep * n_scan_contigs));
+            ctx->hist_keep_cap = n_scan_contigs;
+        }
+        init_acc_all_kernel<<<(ctx->n_targets + 255) / 256, 256, 0, sc>>>(ctx->d_acc_all, ctx->n_targets);
+    }
     std::vector<unsigned long long> nbey(ctx->n_targets, 0);
     if (ctx->any_ranged) {
         MSD_CUDA_OK(cudaMemcpy(ctx->max_end.data(), ctx->d_max_end, sizeof(uint32_t) * ctx->n_targets, cudaMemcpyDeviceToHost));
@@ -845,15 +877,24 @@ int msd_run(msd_ctx* ctx) {
         if (!ctx->want[t] || npre[t] == 0) continue;
         const uint32_t tlen = ctx->tlen[t];
         ctx->info.n_depth_cells += (uint64_t)tlen + 1;
-        init_accum_kernel<<<1, 1, 0, sc>>>(ctx->d_acc, nullptr);
+        // scan + whole-contig stats; nothing is read back here: the accumulators stay on the device (the `total` rows are
+        // updated from there) and the first kHistKeep dist bins go to pinned memory asynchronously
+        if (!async_stats) init_accum_kernel<<<1, 1, 0, sc>>>(ctx->d_acc, nullptr);
         MSD_CUDA_OK(cudaMemsetAsync(ctx->d_hist, 0, 8ull * kDistBins, sc));
-        if ((rc = run_scan(ctx, ctx->d_arena + ctx->depth_off[t], tlen + 1, tlen, 1))) return rc;
+        if ((rc = run_scan(ctx, ctx->d_arena + ctx->depth_off[t], tlen + 1, tlen, 1, async_stats ? ctx->d_acc_all + t : nullptr))) return rc;
+        add_hist_kernel<<<kSMs, 256, 0, sc>>>(ctx->d_tot_global, ctx->d_hist, kDistBins);
+        ContigResult& R = ctx->results[t];
+        R.have = true;
+        if (async_stats) {
+            add_stats_dev_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats, (long long)tlen, ctx->d_acc_all + t);
+            MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_hist_keep + (size_t)keep_slot[t] * kHistKeep, ctx->d_hist, 8ull * kHistKeep, cudaMemcpyDeviceToHost, sc));
+            ctx->info.n_launches += 3;
+            continue;
+        }
         ContigAccum acc;
         MSD_CUDA_OK(cudaMemcpyAsync(&acc, ctx->d_acc, sizeof acc, cudaMemcpyDeviceToHost, sc));
-        add_hist_kernel<<<kSMs, 256, 0, sc>>>(ctx->d_tot_global, ctx->d_hist, kDistBins);
         MSD_CUDA_OK(cudaStreamSynchronize(sc));
-        ContigResult& R = ctx->results[t];
-        R.have = true; R.stat.cum_length = tlen; R.stat.cum_depth = acc.cum_depth; R.stat.min_depth = acc.min_depth; R.stat.max_depth = acc.max_depth;
+        R.stat.cum_length = tlen; R.stat.cum_depth = acc.cum_depth; R.stat.min_depth = acc.min_depth; R.stat.max_depth = acc.max_depth;
         add_stats_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats, (long long)tlen, acc.cum_depth, acc.min_depth, acc.max_depth);
         // distribution: bins up to the maximum depth seen (signed view: negative depths are skipped by inc())
         int64_t top = 0;
@@ -863,10 +904,34 @@ int msd_run(msd_ctx* ctx) {
         while (R.dist.size() > 1 && R.dist.back() == 0) R.dist.pop_back();
         ctx->info.n_launches += 4;
     }
+    if (async_stats) MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_acc_all, ctx->d_acc_all, sizeof(ContigAccum) * ctx->n_targets, cudaMemcpyDeviceToHost, sc));
     MSD_CUDA_OK(cudaEventRecord(s1, sc));
     if ((rc = run_prefetch_windows(ctx))) return rc;
     MSD_CUDA_OK(cudaEventRecord(ev_end, sc));
     MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    if (async_stats) {
+        for (int t = 0; t < ctx->n_targets; t++) {
+            if (keep_slot[t] < 0) continue;
+            const uint32_t tlen = ctx->tlen[t];
+            const ContigAccum acc = ctx->h_acc_all[t];
+            ContigResult& R = ctx->results[t];
+            R.stat.cum_length = tlen; R.stat.cum_depth = acc.cum_depth; R.stat.min_depth = acc.min_depth; R.stat.max_depth = acc.max_depth;
+            // distribution: bins up to the maximum depth seen (signed view: negative depths are skipped by inc())
+            int64_t top = 0;
+            if (tlen) { uint32_t mx = acc.max_depth; top = (mx > 0x7fffffffu) ? (int64_t)kMaxCoverage : (int64_t)std::min<uint32_t>(mx, kMaxCoverage); }
+            R.dist.assign((size_t)top + 1, 0);
+            if (top < kHistKeep) memcpy(R.dist.data(), ctx->h_hist_keep + (size_t)keep_slot[t] * kHistKeep, 8ull * (top + 1));
+            else {
+                // deeper than the bins kept on the host: count this contig's dist again (the scan's histogram is gone)
+                init_accum_kernel<<<1, 1, 0, sc>>>(ctx->d_acc, nullptr);
+                MSD_CUDA_OK(cudaMemsetAsync(ctx->d_hist, 0, 8ull * kDistBins, sc));
+                range_stats_kernel<<<grid_for(tlen, 256, kSMs * 8), 256, 0, sc>>>(ctx->d_arena + ctx->depth_off[t], tlen, ctx->d_hist, ctx->d_acc);
+                MSD_CUDA_OK(cudaMemcpyAsync(R.dist.data(), ctx->d_hist, 8ull * (top + 1), cudaMemcpyDeviceToHost, sc));
+                MSD_CUDA_OK(cudaStreamSynchronize(sc));
+            }
+            while (R.dist.size() > 1 && R.dist.back() == 0) R.dist.pop_back();
+        }
+    }
     float ms = 0;
     cudaEventElapsedTime(&ms, ev_begin, ev_end); ctx->info.ms_total = ms;
     cudaEventElapsedTime(&ms, ev_begin, ev_zero_end); ctx->info.ms_zero = ms;
