@@ -117,7 +117,8 @@ static std::vector<uint8_t> gunzip_all(const std::vector<uint8_t>& raw) {
     while (p < raw.size()) {
         z_stream zs; memset(&zs, 0, sizeof zs); inflateInit2(&zs, 31); zs.next_in = (Bytef*)raw.data() + p; zs.avail_in = (uInt)(raw.size() - p);
         int r; do { size_t o = out.size(); out.resize(o + 65536); zs.next_out = out.data() + o; zs.avail_out = 65536; r = inflate(&zs, Z_NO_FLUSH); out.resize(o + 65536 - zs.avail_out); } while (r == Z_OK);
-        if (r != Z_STREAM_END) die(1, "[mosdepth] corrupt index"); p = raw.size() - zs.avail_in; inflateEnd(&zs);
+        if (r != Z_STREAM_END) die(1, "[mosdepth] corrupt index");
+        p = raw.size() - zs.avail_in; inflateEnd(&zs);
     }
     return out;
 }
