@@ -212,7 +212,7 @@ enum DecPhase : int { kPhNeed = 0, kPhHeader = 1, kPhBuild = 2, kPhSym = 3, kPhF
 __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm)
 huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, int n_blocks,
                       uint32_t* __restrict__ ticket, uint32_t* __restrict__ tokens, uint32_t* __restrict__ n_tokens,
-                      uint32_t* __restrict__ status_out, uint32_t* __restrict__ error_count) {
+                      uint32_t* __restrict__ status_out, uint32_t* __restrict__ error_count, uint32_t* __restrict__ crc_expected) {
     extern __shared__ __align__(16) uint16_t smem16[];
     constexpr unsigned full = 0xffffffffu;
     const int lane = threadIdx.x;
@@ -248,6 +248,8 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
                 const uint8_t* first = comp + bd.src;
                 lead = (uint32_t)((uintptr_t)first & 15u); clen = bd.clen; isize = bd.isize;
                 chunks = reinterpret_cast<const uint4*>(first - lead);
+                { const uint8_t* tr = first + bd.clen;    // gzip trailer: CRC32, ISIZE (the compressed buffer may be recycled before K1c runs)
+                  crc_expected[b] = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24); }
                 total_words = (lead + clen + 3) / 4; clast = (lead + clen + 15) / 16; if (clast) clast--;
                 dst = out + bd.dst;
                 tok = tokens + (size_t)b * kTokenCap; ntok = 0;
@@ -482,16 +484,88 @@ lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_bl
     }
 }
 
-// K1 = K1a + K1b on one stream.  tickets: two zeroed words (K1a, K1b).  comp_read (may be null) is recorded after K1a:
-// from then on the compressed chunk buffer may be overwritten.
+// K1c.  CRC-32 of every inflated block against the gzip trailer (htslib's bgzf reader checks it [ext]; a corrupt stream can
+// still inflate to ISIZE bytes).  One warp per block: lane i runs slice-by-4 over its own 1/32 of the block, then the 32
+// finalised CRCs are combined in 5 tree levels with crc32_combine's algebra (GF(2) polynomials mod the CRC polynomial):
+// the operators "append L * 2^j bytes" are shared by the whole block, so a block costs ~30 polynomial products.
+constexpr int kCrcWarps = 4;
+__global__ void __launch_bounds__(kCrcWarps * 32, 16)
+bgzf_crc_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, int n_blocks, uint32_t* __restrict__ ticket,
+                const uint32_t* __restrict__ crc_expected, uint32_t* __restrict__ status, uint32_t* __restrict__ error_count) {
+    __shared__ uint32_t T[4][256];
+    __shared__ uint32_t x2n[32];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) T[0][i] = crc_table0_entry((uint32_t)i);
+    if (threadIdx.x == 0) crc_build_x2n(x2n);
+    __syncthreads();
+    for (int k = 1; k < 4; k++) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) T[k][i] = (T[k - 1][i] >> 8) ^ T[0][T[k - 1][i] & 0xffu];
+        __syncthreads();
+    }
+    constexpr unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    // the "append n bytes" operators depend on the block size only, and nearly all blocks of a file have the same size:
+    // keep the last set in registers
+    uint32_t cached_isize = 0xffffffffu, S[5] = {0, 0, 0, 0, 0}, SE[5] = {0, 0, 0, 0, 0};
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = (int)atomicAdd(ticket, 1u);
+        b = __shfl_sync(full, b, 0);
+        if (b >= n_blocks) return;
+        if (status[b] != kOk) continue;                         // already failed in K1a
+        const uint32_t isize = blocks[b].isize;
+        const uint8_t* p = out + blocks[b].dst;
+        const uint32_t L = (isize / 32u) & ~15u;                // lanes 0..30: L bytes each, lane 31: the rest
+        const uint32_t beg = (uint32_t)lane * L, my_len = lane == 31 ? isize - beg : L;
+        uint32_t c = 0xffffffffu;
+        {
+            const uint8_t* q = p + beg; uint32_t n = my_len;
+            while (n && ((uintptr_t)q & 15u)) { c = (c >> 8) ^ T[0][(c ^ *q++) & 0xffu]; n--; }
+            for (; n >= 16; n -= 16, q += 16) {                 // 128-bit loads: a 32-byte sector is fetched twice, not 8 times
+                const uint4 v = *reinterpret_cast<const uint4*>(q);
+                uint32_t w = v.x ^ c;
+                c = T[3][w & 0xffu] ^ T[2][(w >> 8) & 0xffu] ^ T[1][(w >> 16) & 0xffu] ^ T[0][w >> 24];
+                w = v.y ^ c;
+                c = T[3][w & 0xffu] ^ T[2][(w >> 8) & 0xffu] ^ T[1][(w >> 16) & 0xffu] ^ T[0][w >> 24];
+                w = v.z ^ c;
+                c = T[3][w & 0xffu] ^ T[2][(w >> 8) & 0xffu] ^ T[1][(w >> 16) & 0xffu] ^ T[0][w >> 24];
+                w = v.w ^ c;
+                c = T[3][w & 0xffu] ^ T[2][(w >> 8) & 0xffu] ^ T[1][(w >> 16) & 0xffu] ^ T[0][w >> 24];
+            }
+            while (n) { c = (c >> 8) ^ T[0][(c ^ *q++) & 0xffu]; n--; }
+        }
+        uint32_t crc = ~c;
+        if (isize != cached_isize) {                            // uniform across the warp
+            cached_isize = isize;
+            uint32_t s0 = crc_shift_op(L, x2n);                 // append L bytes
+            const uint32_t e = crc_shift_op(isize - 32u * L, x2n);   // ... and the extra bytes of lane 31
+#pragma unroll
+            for (int j = 0; j < 5; j++) { S[j] = s0; SE[j] = crc_multmodp(s0, e); s0 = crc_multmodp(s0, s0); }
+        }
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            const int o = 1 << j;
+            const uint32_t right = __shfl_down_sync(full, crc, o);
+            if ((lane & (2 * o - 1)) == 0) crc = crc_multmodp((lane + 2 * o == 32) ? SE[j] : S[j], crc) ^ right;   // SE: the right group holds lane 31
+        }
+        if (lane == 0 && crc != crc_expected[b]) { status[b] = kBadCrc; atomicAdd(error_count, 1u); }
+    }
+}
+
+// K1 = K1a + K1b (+ K1c) on one stream.  tickets: three zeroed words (K1a, K1b, K1c).  comp_read (may be null) is recorded
+// after K1a: from then on the compressed chunk buffer may be overwritten.
 inline void launch_inflate(cudaStream_t s, const uint8_t* d_comp, uint8_t* d_out, const BlockDesc* d_desc, int nb, uint32_t* tickets,
-                           uint32_t* d_tokens, uint32_t* d_ntok, uint32_t* d_status, uint32_t* d_error_count, cudaEvent_t comp_read) {
+                           uint32_t* d_tokens, uint32_t* d_ntok, uint32_t* d_status, uint32_t* d_error_count, uint32_t* d_crc,
+                           bool check_crc, cudaEvent_t comp_read) {
     const int dctas = (nb + kDecThreads - 1) / kDecThreads < kSMs * kDecCtasPerSm ? (nb + kDecThreads - 1) / kDecThreads : kSMs * kDecCtasPerSm;
-    huffman_decode_kernel<<<dctas, kDecThreads, kDecSmem, s>>>(d_comp, d_out, d_desc, nb, tickets, d_tokens, d_ntok, d_status, d_error_count);
+    huffman_decode_kernel<<<dctas, kDecThreads, kDecSmem, s>>>(d_comp, d_out, d_desc, nb, tickets, d_tokens, d_ntok, d_status, d_error_count, d_crc);
     if (comp_read) cudaEventRecord(comp_read, s);
     const int want = (nb + kResolveWarps - 1) / kResolveWarps;
     const int rctas = want < kSMs * kResolveCtasPerSm ? want : kSMs * kResolveCtasPerSm;
     lz77_resolve_kernel<<<rctas, kResolveWarps * 32, 0, s>>>(d_out, d_desc, nb, tickets + 1, d_tokens, d_ntok);
+    if (check_crc) {
+        const int cw = (nb + kCrcWarps - 1) / kCrcWarps;
+        bgzf_crc_kernel<<<cw < kSMs * 16 ? cw : kSMs * 16, kCrcWarps * 32, 0, s>>>(d_out, d_desc, nb, tickets + 2, d_crc, d_status, d_error_count);
+    }
 }
 
 }  // namespace msd

@@ -85,8 +85,37 @@ MSD_HD uint32_t make_token(uint32_t lit_run, uint32_t len, uint32_t dist) { retu
 
 enum Status : uint32_t {
     kOk = 0, kBadBlockType = 1, kBadStored = 2, kBadCodeLengths = 3, kBadSymbol = 4, kBadDistance = 5,
-    kOverflow = 6, kShort = 7, kOversubscribed = 8, kTruncated = 9
+    kOverflow = 6, kShort = 7, kOversubscribed = 8, kTruncated = 9, kBadCrc = 10
 };
+
+// ---- CRC-32 of the gzip trailer (RFC 1952; reflected polynomial 0xEDB88320), computed in parallel ---------------------
+// Polynomials over GF(2) modulo the CRC polynomial in the reflected representation zlib uses: bit 31 is x^0.
+constexpr uint32_t kCrcPoly = 0xedb88320u;
+MSD_HD uint32_t crc_multmodp(uint32_t a, uint32_t b) {          // a(x) * b(x) mod p(x)
+    uint32_t p = 0;
+#pragma unroll 4
+    for (int i = 31; i >= 0; i--) {
+        p ^= (0u - ((a >> i) & 1u)) & b;
+        b = (b >> 1) ^ ((0u - (b & 1u)) & kCrcPoly);
+    }
+    return p;
+}
+// x2n[k] = x^(2^k) mod p, k = 0..31 (x2n[0] = x^1)
+MSD_HD void crc_build_x2n(uint32_t* x2n) {
+    uint32_t p = 1u << 30;
+    x2n[0] = p;
+    for (int n = 1; n < 32; n++) { p = crc_multmodp(p, p); x2n[n] = p; }
+}
+// x^(8 * n_bytes) mod p: the operator that appends n_bytes zero bytes to a message (crc32_combine: crc(A||B) =
+// multmodp(crc_shift_op(|B|), crc(A)) ^ crc(B) for finalised CRCs)
+MSD_HD uint32_t crc_shift_op(uint32_t n_bytes, const uint32_t* x2n) {
+    uint32_t p = 1u << 31;
+    int k = 3;
+    while (n_bytes) { if (n_bytes & 1u) p = crc_multmodp(x2n[k & 31], p); n_bytes >>= 1; k++; }
+    return p;
+}
+// slice-by-4 tables: t[0] is the classic byte table, t[k][i] = crc of byte i followed by k zero bytes
+MSD_HD uint32_t crc_table0_entry(uint32_t i) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((0u - (c & 1u)) & kCrcPoly); return c; }
 
 }  // namespace inf
 }  // namespace msd

@@ -66,6 +66,20 @@ def test_inflate_many_blocks_lock_step(ctx):
     assert ctx.debug_inflate(data, len(want)) == want
 
 
+def test_inflate_checks_crc32(ctx):
+    """A stored block whose payload byte is flipped still inflates to ISIZE bytes: only the CRC32 of the gzip trailer
+    (which htslib's reader verifies) can tell."""
+    import mosdepth_b200 as m
+    from bgzf_cases import member, deflate
+    p = bytes(range(256)) * 16
+    good = member(p, deflate(p, "stored"))
+    assert ctx.debug_inflate(good, len(p)) == p
+    bad = bytearray(good); bad[18 + 5 + 100] ^= 0x01          # header 18 B, stored-block header 5 B, then the payload
+    with pytest.raises(m.MsdError) as e:
+        ctx.debug_inflate(bytes(bad), len(p))
+    assert e.value.code == -14 and "status 10" in str(e.value)
+
+
 def test_inflate_rejects_corrupt_block(ctx):
     import mosdepth_b200 as m
     p = bytes(range(256)) * 40
