@@ -485,86 +485,102 @@ lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_bl
 }
 
 // K1c.  CRC-32 of every inflated block against the gzip trailer (htslib's bgzf reader checks it [ext]; a corrupt stream can
-// still inflate to ISIZE bytes).  One warp per block: lane i runs slice-by-4 over its own 1/32 of the block, then the 32
-// finalised CRCs are combined in 5 tree levels with crc32_combine's algebra (GF(2) polynomials mod the CRC polynomial):
-// the operators "append L * 2^j bytes" are shared by the whole block, so a block costs ~30 polynomial products.
-constexpr int kCrcWarps = 4;
-__global__ void __launch_bounds__(kCrcWarps * 32, 16)
+// still inflate to ISIZE bytes).  One warp per block, row-strided formulation (inflate_core.cuh, "K1c"): every load is a
+// coalesced 512-byte request, every table lookup goes to the lane's own bank (tables replicated per lane, 128 KB per
+// CTA), so the kernel streams the inflated bytes at HBM speed instead of replaying bank conflicts (profiles/README.md, r1m).
+constexpr int kCrcThreads = 512;
+constexpr int kCrcUWords = 4 * 256 * 32;
+constexpr int kCrcSmemWords = kCrcUWords + 256 + kCrcXaN + kCrcXbN + 3;
+constexpr size_t kCrcSmem = (size_t)kCrcSmemWords * 4;
+__device__ uint32_t g_crc_tables[kCrcTableWords];       // CrcTables, written by msd_create (crc_upload_tables)
+
+inline cudaError_t crc_upload_tables() {
+    static CrcTables host; static bool built = false;
+    if (!built) { crc_build_tables(host); built = true; }
+    cudaError_t e = cudaMemcpyToSymbol(g_crc_tables, &host, sizeof host);
+    return e;
+}
+
+__global__ void __launch_bounds__(kCrcThreads, 1)
 bgzf_crc_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, int n_blocks, uint32_t* __restrict__ ticket,
                 const uint32_t* __restrict__ crc_expected, uint32_t* __restrict__ status, uint32_t* __restrict__ error_count) {
-    __shared__ uint32_t T[4][256];
-    __shared__ uint32_t x2n[32];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) T[0][i] = crc_table0_entry((uint32_t)i);
-    if (threadIdx.x == 0) crc_build_x2n(x2n);
-    __syncthreads();
-    for (int k = 1; k < 4; k++) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) T[k][i] = (T[k - 1][i] >> 8) ^ T[0][T[k - 1][i] & 0xffu];
-        __syncthreads();
-    }
+    extern __shared__ __align__(16) uint32_t crc_sm[];
+    uint32_t* const U = crc_sm;
+    uint32_t* const T0 = U + kCrcUWords;
+    uint32_t* const XA = T0 + 256;
+    uint32_t* const XBI = XA + kCrcXaN;
     constexpr unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    // the "append n bytes" operators depend on the block size only, and nearly all blocks of a file have the same size:
-    // keep the last set in registers
-    uint32_t cached_isize = 0xffffffffu, S[5] = {0, 0, 0, 0, 0}, SE[5] = {0, 0, 0, 0, 0};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const CrcTables* const G = reinterpret_cast<const CrcTables*>(g_crc_tables);
+    for (int e0 = warp * 32; e0 < 1024; e0 += kCrcThreads) {            // entry e0 + s of U goes to all 32 lane copies
+        const uint32_t mine = (&G->u[0][0])[e0 + lane];
+#pragma unroll 8
+        for (int s = 0; s < 32; s++) U[(e0 + s) * 32 + lane] = __shfl_sync(full, mine, s);
+    }
+    for (int i = threadIdx.x; i < 256; i += kCrcThreads) T0[i] = G->t0[i];
+    for (int i = threadIdx.x; i < kCrcXaN; i += kCrcThreads) XA[i] = G->xa[i];
+    for (int i = threadIdx.x; i < kCrcXbN; i += kCrcThreads) XBI[i] = G->xbi[i];
+    const uint32_t xl = G->xl[lane];
+    __syncthreads();
+    // one lookup = byte extract + multiply-add + LDS: entry (m, i) of this lane at Ub + 32768 m + 128 i
+    const uint32_t Ub = (uint32_t)__cvta_generic_to_shared(U) + (uint32_t)lane * 4u;
+    auto lk = [&](uint32_t byte, uint32_t m) -> uint32_t {
+        uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(byte * 128u + (Ub + 32768u * m)));
+        return v;
+    };
+    auto step = [&](uint32_t w) -> uint32_t {
+        uint32_t b0, b1, b2, b3;       // PRMT for all four bytes (the compiler turns `w & 0xff` and `w >> 24` times 128 into shift + and + add)
+        asm("prmt.b32 %0, %1, 0, 0x4440;" : "=r"(b0) : "r"(w)); asm("prmt.b32 %0, %1, 0, 0x4441;" : "=r"(b1) : "r"(w));
+        asm("prmt.b32 %0, %1, 0, 0x4442;" : "=r"(b2) : "r"(w)); asm("prmt.b32 %0, %1, 0, 0x4443;" : "=r"(b3) : "r"(w));
+        return lk(b0, 0) ^ lk(b1, 1) ^ lk(b2, 2) ^ lk(b3, 3);
+    };
+    auto t0 = [&](uint32_t i) -> uint32_t { return T0[i]; };
     for (;;) {
         int b = 0;
         if (lane == 0) b = (int)atomicAdd(ticket, 1u);
         b = __shfl_sync(full, b, 0);
         if (b >= n_blocks) return;
         if (status[b] != kOk) continue;                         // already failed in K1a
-        const uint32_t isize = blocks[b].isize;
+        const uint32_t n = blocks[b].isize;
         const uint8_t* p = out + blocks[b].dst;
-        const uint32_t L = (isize / 32u) & ~15u;                // lanes 0..30: L bytes each, lane 31: the rest
-        const uint32_t beg = (uint32_t)lane * L, my_len = lane == 31 ? isize - beg : L;
-        uint32_t c = 0xffffffffu;
-        {
-            const uint8_t* q = p + beg; uint32_t n = my_len;
-            while (n && ((uintptr_t)q & 15u)) { c = (c >> 8) ^ T[0][(c ^ *q++) & 0xffu]; n--; }
-            for (; n >= 16; n -= 16, q += 16) {                 // 128-bit loads: a 32-byte sector is fetched twice, not 8 times
-                const uint4 v = *reinterpret_cast<const uint4*>(q);
-                uint32_t w = v.x ^ c;
-                c = T[3][w & 0xffu] ^ T[2][(w >> 8) & 0xffu] ^ T[1][(w >> 16) & 0xffu] ^ T[0][w >> 24];
-                w = v.y ^ c;
-                c = T[3][w & 0xffu] ^ T[2][(w >> 8) & 0xffu] ^ T[1][(w >> 16) & 0xffu] ^ T[0][w >> 24];
-                w = v.z ^ c;
-                c = T[3][w & 0xffu] ^ T[2][(w >> 8) & 0xffu] ^ T[1][(w >> 16) & 0xffu] ^ T[0][w >> 24];
-                w = v.w ^ c;
-                c = T[3][w & 0xffu] ^ T[2][(w >> 8) & 0xffu] ^ T[1][(w >> 16) & 0xffu] ^ T[0][w >> 24];
-            }
-            while (n) { c = (c >> 8) ^ T[0][(c ^ *q++) & 0xffu]; n--; }
+        const uint32_t pad = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u), n2 = n + pad, R = n2 / kCrcRow, tail = n2 % kCrcRow;
+        const uint4* q = reinterpret_cast<const uint4*>(p - pad) + lane;
+        uint32_t d[4] = {0u, 0u, 0u, 0u};
+        if (R && pad && lane == 0) {                            // the bytes in front of the message cancel themselves
+            const uint4 v = __ldg(q);
+            const CrcWords c = crc_head_cancel(CrcWords{v.x, v.y, v.z, v.w}, 0, pad);
+            d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
         }
-        uint32_t crc = ~c;
-        if (isize != cached_isize) {                            // uniform across the warp
-            cached_isize = isize;
-            uint32_t s0 = crc_shift_op(L, x2n);                 // append L bytes
-            const uint32_t e = crc_shift_op(isize - 32u * L, x2n);   // ... and the extra bytes of lane 31
-#pragma unroll
-            for (int j = 0; j < 5; j++) { S[j] = s0; SE[j] = crc_multmodp(s0, e); s0 = crc_multmodp(s0, s0); }
+#pragma unroll 4
+        for (uint32_t r = 0; r < R; r++) {
+            const uint4 v = __ldg(q + r * 32);
+            d[0] = step(v.x ^ d[0]); d[1] = step(v.y ^ d[1]); d[2] = step(v.z ^ d[2]); d[3] = step(v.w ^ d[3]);
         }
-#pragma unroll
-        for (int j = 0; j < 5; j++) {
-            const int o = 1 << j;
-            const uint32_t right = __shfl_down_sync(full, crc, o);
-            if ((lane & (2 * o - 1)) == 0) crc = crc_multmodp((lane + 2 * o == 32) ? SE[j] : S[j], crc) ^ right;   // SE: the right group holds lane 31
-        }
+        CrcWords t{0u, 0u, 0u, 0u};
+        const uint32_t g0 = R * kCrcRow + (uint32_t)lane * 16u;
+        if (g0 < n2) { const uint4 v = __ldg(q + R * 32); t = crc_tail_keep(CrcWords{v.x, v.y, v.z, v.w}, g0, pad, n2); }
+        uint32_t v = crc_multmodp(xl, crc_lane_fold(d, t, t0));
+        v = __reduce_xor_sync(full, v);
+        const uint32_t crc = crc_finish(v, XA[tail], XA[n % kCrcRow], XBI[n / kCrcRow]);
         if (lane == 0 && crc != crc_expected[b]) { status[b] = kBadCrc; atomicAdd(error_count, 1u); }
     }
 }
 
 // K1 = K1a + K1b (+ K1c) on one stream.  tickets: three zeroed words (K1a, K1b, K1c).  comp_read (may be null) is recorded
-// after K1a: from then on the compressed chunk buffer may be overwritten.
+// after K1a: from then on the compressed chunk buffer may be overwritten.  resolved (may be null) is recorded after K1b.
 inline void launch_inflate(cudaStream_t s, const uint8_t* d_comp, uint8_t* d_out, const BlockDesc* d_desc, int nb, uint32_t* tickets,
                            uint32_t* d_tokens, uint32_t* d_ntok, uint32_t* d_status, uint32_t* d_error_count, uint32_t* d_crc,
-                           bool check_crc, cudaEvent_t comp_read) {
+                           bool check_crc, cudaEvent_t comp_read, cudaEvent_t resolved = nullptr) {
     const int dctas = (nb + kDecThreads - 1) / kDecThreads < kSMs * kDecCtasPerSm ? (nb + kDecThreads - 1) / kDecThreads : kSMs * kDecCtasPerSm;
     huffman_decode_kernel<<<dctas, kDecThreads, kDecSmem, s>>>(d_comp, d_out, d_desc, nb, tickets, d_tokens, d_ntok, d_status, d_error_count, d_crc);
     if (comp_read) cudaEventRecord(comp_read, s);
     const int want = (nb + kResolveWarps - 1) / kResolveWarps;
     const int rctas = want < kSMs * kResolveCtasPerSm ? want : kSMs * kResolveCtasPerSm;
     lz77_resolve_kernel<<<rctas, kResolveWarps * 32, 0, s>>>(d_out, d_desc, nb, tickets + 1, d_tokens, d_ntok);
+    if (resolved) cudaEventRecord(resolved, s);      // the inflated bytes are final: framing need not wait for the CRC check
     if (check_crc) {
-        const int cw = (nb + kCrcWarps - 1) / kCrcWarps;
-        bgzf_crc_kernel<<<cw < kSMs * 16 ? cw : kSMs * 16, kCrcWarps * 32, 0, s>>>(d_out, d_desc, nb, tickets + 2, d_crc, d_status, d_error_count);
+        const int cw = (nb + kCrcThreads / 32 - 1) / (kCrcThreads / 32);
+        bgzf_crc_kernel<<<cw < kSMs ? cw : kSMs, kCrcThreads, kCrcSmem, s>>>(d_out, d_desc, nb, tickets + 2, d_crc, d_status, d_error_count);
     }
 }
 

@@ -93,7 +93,9 @@ enum Status : uint32_t {
 constexpr uint32_t kCrcPoly = 0xedb88320u;
 MSD_HD uint32_t crc_multmodp(uint32_t a, uint32_t b) {          // a(x) * b(x) mod p(x)
     uint32_t p = 0;
+#if defined(__CUDACC__)
 #pragma unroll 4
+#endif
     for (int i = 31; i >= 0; i--) {
         p ^= (0u - ((a >> i) & 1u)) & b;
         b = (b >> 1) ^ ((0u - (b & 1u)) & kCrcPoly);
@@ -114,8 +116,85 @@ MSD_HD uint32_t crc_shift_op(uint32_t n_bytes, const uint32_t* x2n) {
     while (n_bytes) { if (n_bytes & 1u) p = crc_multmodp(x2n[k & 31], p); n_bytes >>= 1; k++; }
     return p;
 }
-// slice-by-4 tables: t[0] is the classic byte table, t[k][i] = crc of byte i followed by k zero bytes
+// the classic byte table: entry i = byte i pushed through 8 zero bits
 MSD_HD uint32_t crc_table0_entry(uint32_t i) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((0u - (c & 1u)) & kCrcPoly); return c; }
+// x^e mod p for any 32-bit exponent.  x has order 2^32 - 1 modulo the CRC-32 polynomial, so exponents live modulo
+// 2^32 - 1 and a negative power is x^(0xffffffff - k): the combine below divides as well as multiplies.
+MSD_HD uint32_t crc_xpow(uint32_t e, const uint32_t* x2n) {
+    uint32_t p = 1u << 31;
+    for (int k = 0; e; k++, e >>= 1) if (e & 1u) p = crc_multmodp(x2n[k], p);
+    return p;
+}
+
+// ---- K1c: row-strided CRC-32 (bgzf_crc_kernel and its host replay in tools/inflate_model.cpp) -------------------------
+// A warp checks one block.  The message is extended to the left to a 16-byte boundary with `pad` zero bytes (leading zeros
+// do not change a CRC computed from state 0; the 0xffffffff start state is added at the end as 0xffffffff * x^(8n)), and
+// cut into rows of 512 bytes: in row r lane l loads the 16 bytes at 512 r + 16 l (one coalesced 512-byte request per
+// warp) and owns four word STREAMS, one per component of the uint4.  Consecutive words of a stream are 512 bytes apart,
+// so the stream state is kept pre-multiplied, d = (state at the end of its last word) * x^(8*508), and one step is
+//     d' = (d ^ w) * x^(8*512)  =  U[0][b0] ^ U[1][b1] ^ U[2][b2] ^ U[3][b3],   U[m][i] = table0[i] * x^(8*(511-m)),
+// four lookups per word like slice-by-4 (b0 = lowest byte).  Every lane indexes ITS OWN copy of the tables
+// (entry (m, i) of lane l at word (m * 256 + i) * 32 + l, 128 KB per CTA): bank = lane, no conflicts whatever the data.
+// After R full rows, stream (l, c) contributes d * x^(8*(tail - 16 l - 4 c)), tail = (n + pad) mod 512.  The four
+// streams of a lane and its 16-byte piece t of the tail (zero padded: appended zeros are divided out again) fold into
+//     G = (((d0 * x^32 ^ d1) * x^32 ^ d2) * x^32 ^ d3) * x^32 ^ t          (16 classic byte-table steps)
+// which contributes G * x^(8*tail) * x^(-128 (l + 1)): one product with a per-lane constant, an XOR across the warp,
+// one product with x^(8*tail), and the start-state term.
+constexpr uint32_t kCrcRow = 512;
+constexpr int kCrcXaN = 512;      // XA[t]  = x^(8 t), t < 512
+constexpr int kCrcXbN = 129;      // XBI[r] = 0xffffffff * x^(4096 r): start state pushed through 512 r bytes (r <= 128: ISIZE <= 65536)
+MSD_HD uint32_t crc_u_entry(int m, uint32_t i, const uint32_t* x2n) { return crc_multmodp(crc_xpow(8u * (511u - (uint32_t)m), x2n), crc_table0_entry(i)); }
+MSD_HD uint32_t crc_lane_weight(int lane, const uint32_t* x2n) { return crc_xpow(0xffffffffu - 128u * (uint32_t)(lane + 1), x2n); }   // x^(-128 (l+1))
+// bytes [lo, hi) of a little-endian word (lo, hi clamped to 0..4)
+MSD_HD uint32_t crc_byte_mask(int lo, int hi) {
+    lo = lo < 0 ? 0 : lo; hi = hi > 4 ? 4 : hi;
+    if (hi <= lo) return 0u;
+    return (0xffffffffu >> (8 * (4 - hi))) & (0xffffffffu << (8 * lo));
+}
+struct CrcWords { uint32_t x, y, z, w; };
+// c * x^32: four byte steps with the classic table (T0 may be a shared-memory table or a host array)
+template <class T0> MSD_HD uint32_t crc_times_x32(uint32_t c, const T0& t0) {
+    c = (c >> 8) ^ t0(c & 0xffu); c = (c >> 8) ^ t0(c & 0xffu); c = (c >> 8) ^ t0(c & 0xffu); c = (c >> 8) ^ t0(c & 0xffu);
+    return c;
+}
+// the words of row 0 that a lane has to cancel (bytes in front of the message: only lane 0 has any)
+MSD_HD CrcWords crc_head_cancel(CrcWords v, int lane, uint32_t pad) {
+    const int k = (int)pad - 16 * lane;       // leading bytes of this lane's 16 that are not message
+    return CrcWords{v.x & ~crc_byte_mask(k, 4), v.y & ~crc_byte_mask(k - 4, 4), v.z & ~crc_byte_mask(k - 8, 4), v.w & ~crc_byte_mask(k - 12, 4)};
+}
+// a lane's 16 bytes of the tail at message' offset g0 = 512 R + 16 l, restricted to [pad, n2)
+MSD_HD CrcWords crc_tail_keep(CrcWords v, uint32_t g0, uint32_t pad, uint32_t n2) {
+    const int lo = (int)pad - (int)g0, hi = (int)n2 - (int)g0;
+    return CrcWords{v.x & crc_byte_mask(lo, hi), v.y & crc_byte_mask(lo - 4, hi - 4), v.z & crc_byte_mask(lo - 8, hi - 8), v.w & crc_byte_mask(lo - 12, hi - 12)};
+}
+// state-0 CRC of a lane's (masked) tail words, then the fold G of the comment above
+template <class T0> MSD_HD uint32_t crc_lane_fold(const uint32_t d[4], CrcWords t, const T0& t0) {
+    uint32_t c = crc_times_x32(t.x, t0);
+    c = crc_times_x32(c ^ t.y, t0); c = crc_times_x32(c ^ t.z, t0); c = crc_times_x32(c ^ t.w, t0);
+    uint32_t g = crc_times_x32(d[0], t0) ^ d[1];
+    g = crc_times_x32(g, t0) ^ d[2];
+    g = crc_times_x32(g, t0) ^ d[3];
+    return crc_times_x32(g, t0) ^ c;
+}
+// The constants of K1c, built once on the host (msd_create copies them to the device; the kernel replicates u[][] per lane).
+struct CrcTables {
+    uint32_t u[4][256];        // U[m][i]
+    uint32_t t0[256];          // classic byte table
+    uint32_t xa[kCrcXaN];      // x^(8 t)
+    uint32_t xbi[kCrcXbN + 3]; // 0xffffffff * x^(4096 r)
+    uint32_t xl[32];           // x^(-128 (lane + 1))
+};
+constexpr int kCrcTableWords = (int)(sizeof(CrcTables) / 4);
+inline void crc_build_tables(CrcTables& t) {
+    uint32_t x2n[32]; crc_build_x2n(x2n);
+    for (uint32_t i = 0; i < 256; i++) t.t0[i] = crc_table0_entry(i);
+    for (int m = 0; m < 4; m++) { const uint32_t f = crc_xpow(8u * (511u - (uint32_t)m), x2n); for (uint32_t i = 0; i < 256; i++) t.u[m][i] = crc_multmodp(f, t.t0[i]); }
+    for (uint32_t k = 0; k < (uint32_t)kCrcXaN; k++) t.xa[k] = crc_xpow(8u * k, x2n);
+    for (uint32_t r = 0; r < (uint32_t)kCrcXbN + 3; r++) t.xbi[r] = crc_multmodp(0xffffffffu, crc_xpow(4096u * r, x2n));
+    for (int l = 0; l < 32; l++) t.xl[l] = crc_lane_weight(l, x2n);
+}
+// v = XOR over the lanes of G_l * x^(-128 (l+1)); xa_tail = x^(8 tail); xa_n = x^(8 (n mod 512)); xbi = XBI[n / 512]
+MSD_HD uint32_t crc_finish(uint32_t v, uint32_t xa_tail, uint32_t xa_n, uint32_t xbi) { return ~(crc_multmodp(xa_tail, v) ^ crc_multmodp(xa_n, xbi)); }
 
 }  // namespace inf
 }  // namespace msd

@@ -82,7 +82,7 @@ struct msd_ctx {
     uint32_t* d_crc[kSlots] = {}; bool check_crc = true;              // CRC32 fields of the gzip trailers (K1c)
     ChunkState* d_cs = nullptr; RunCounters* d_rc = nullptr;
     StageSet stage[kDescSets];   // h_desc / h_rel per descriptor set; h_bounce in the first kSlots sets only
-    cudaEvent_t desc_free[kDescSets] = {}, bounce_free[kSlots] = {}; bool bounce_used[kSlots] = {};
+    cudaEvent_t desc_free[kDescSets] = {}, crc_done[kDescSets] = {}, bounce_free[kSlots] = {}; bool bounce_used[kSlots] = {};
     cudaEvent_t comp_free[kSlots] = {}, h2d_done[kSlots] = {}, infl_done[kSlots] = {}, infl_free[kSlots] = {};
     // mate join (default mode only)
     MateChunk mc{}; MateTable mt{}; LiveList live[2]{}; bool mate_ready = false; uint32_t mate_slots = 0;
@@ -189,7 +189,7 @@ void free_chunk_buffers(msd_ctx* ctx) {
         if (ctx->stage[k].h_desc) { cudaFreeHost(ctx->stage[k].h_desc); ctx->stage[k].h_desc = nullptr; }
         if (ctx->stage[k].h_rel) { cudaFreeHost(ctx->stage[k].h_rel); ctx->stage[k].h_rel = nullptr; }
         if (ctx->stage[k].h_bounce) { cudaFreeHost(ctx->stage[k].h_bounce); ctx->stage[k].h_bounce = nullptr; }
-        cudaEvent_t* evs[] = {&ctx->stage[k].free_ev, &ctx->desc_free[k]};
+        cudaEvent_t* evs[] = {&ctx->stage[k].free_ev, &ctx->desc_free[k], &ctx->crc_done[k]};
         for (cudaEvent_t* e : evs) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
         ctx->stage[k].used = false;
     }
@@ -220,7 +220,7 @@ int ensure_chunk_buffers(msd_ctx* ctx) {
         if ((rc = dev_alloc(ctx, &ctx->d_rel[k], ctx->max_blocks + 1))) return rc;
         MSD_CUDA_OK(cudaMallocHost((void**)&ctx->stage[k].h_desc, sizeof(BlockDesc) * ctx->max_blocks));
         MSD_CUDA_OK(cudaMallocHost((void**)&ctx->stage[k].h_rel, sizeof(uint32_t) * (ctx->max_blocks + 1)));
-        cudaEvent_t* evs[] = {&ctx->stage[k].free_ev, &ctx->desc_free[k]};
+        cudaEvent_t* evs[] = {&ctx->stage[k].free_ev, &ctx->desc_free[k], &ctx->crc_done[k]};
         for (cudaEvent_t* e : evs) MSD_CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
     const uint32_t nb = ctx->max_blocks + 2;
@@ -460,6 +460,8 @@ int msd_create(int device, msd_ctx** out) {
     for (int k = 0; k < kSlots; k++) if (cudaStreamCreateWithFlags(&ctx->s_inflate[k], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cudaStreamCreate failed"); }
     cudaFuncSetAttribute(huffman_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecSmem);
     cudaFuncSetAttribute(huffman_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(bgzf_crc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCrcSmem);
+    if (crc_upload_tables() != cudaSuccess) { delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cannot upload the CRC tables"); }
     // default filters = mosdepth defaults (-F 1796, -Q 0, no length limits, default mode)
     ctx->fp.mapq = 0; ctx->fp.min_len = -1; ctx->fp.max_len = INT64_MAX; ctx->fp.eflag = 1796; ctx->fp.iflag = 0; ctx->fp.mode = MSD_MODE_DEFAULT; ctx->fp.n_rg = 0; ctx->fp.rg_names = nullptr;
     *out = ctx;
@@ -747,7 +749,8 @@ int msd_run(msd_ctx* ctx) {
                 // everything this chunk needs goes through the copy stream in one batch, small descriptor copies first:
                 // a copy engine is FIFO, so a descriptor copy queued behind the NEXT chunk's bulk copy would hold this
                 // chunk's kernels back until that bulk copy ends
-                MSD_CUDA_OK(cudaStreamWaitEvent(sx, ctx->desc_free[kd], 0));   // four sets: chunk k-4 is long gone
+                MSD_CUDA_OK(cudaStreamWaitEvent(sx, ctx->desc_free[kd], 0));   // eight sets: chunk k-8 is long gone
+                MSD_CUDA_OK(cudaStreamWaitEvent(sx, ctx->crc_done[kd], 0));    // ... and so is its CRC kernel, which reads the descriptors off the critical path
                 MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_desc[kd], st.h_desc, sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, sx));
                 MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_rel[kd], st.h_rel, sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, sx));
                 MSD_CUDA_OK(cudaEventRecord(st.free_ev, sx));       // h_desc and h_rel of this set are free again
@@ -775,10 +778,10 @@ int msd_run(msd_ctx* ctx) {
             MSD_CUDA_OK(cudaMemsetAsync(ctx->d_ticket + 3 * k, 0, 12, si));
             MSD_CUDA_OK(cudaEventRecord(e0, si));
             launch_inflate(si, d_comp, infl_buf, ctx->d_desc[kd], (int)nb, ctx->d_ticket + 3 * k, ctx->d_tokens[k], ctx->d_ntok[k],
-                           ctx->d_status + (size_t)k * ctx->max_blocks, ctx->d_inflate_err, ctx->d_crc[k], ctx->check_crc, ctx->comp_free[k]);
+                           ctx->d_status + (size_t)k * ctx->max_blocks, ctx->d_inflate_err, ctx->d_crc[k], ctx->check_crc, ctx->comp_free[k], ctx->infl_done[k]);
             ctx->info.n_launches += ctx->check_crc ? 3 : 2; ctx->info.n_inflate_launches++;
             MSD_CUDA_OK(cudaEventRecord(e1, si));
-            MSD_CUDA_OK(cudaEventRecord(ctx->infl_done[k], si));
+            MSD_CUDA_OK(cudaEventRecord(ctx->crc_done[kd], si));
             MSD_CUDA_OK(cudaStreamWaitEvent(sc, ctx->infl_done[k], 0));
             MSD_CUDA_OK(cudaEventRecord(f0, sc));
             // ---- K2 framing ---------------------------------------------------------------------------------
@@ -823,6 +826,7 @@ int msd_run(msd_ctx* ctx) {
     }
     MSD_CUDA_OK(cudaEventRecord(ev_chunks_end, sc));
     MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    for (int k = 0; k < kSlots; k++) MSD_CUDA_OK(cudaStreamSynchronize(ctx->s_inflate[k]));   // the CRC kernels run beside framing and records
     // ---- errors raised by the kernels --------------------------------------------------------------------------
     uint32_t inflate_err = 0; ChunkState cs_h; RunCounters rc_h;
     MSD_CUDA_OK(cudaMemcpy(&inflate_err, ctx->d_inflate_err, 4, cudaMemcpyDeviceToHost));

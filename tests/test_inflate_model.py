@@ -42,3 +42,12 @@ def test_model_on_tricky_members(model, tmp_path):
     f.write_bytes(b"".join(m for _, m in cases))
     out = _run(model, f)
     assert out["bad"] == 0 and out["blocks"] == len(cases)
+
+
+def test_crc_model_every_size_class_and_alignment(model):
+    """K1c (bgzf_crc_kernel): the row-strided CRC-32 arithmetic of inflate_core.cuh against zlib's crc32 for block sizes
+    around every row / tail / lane boundary at all 16 alignments of the block inside the inflated buffer."""
+    r = subprocess.run([str(model), "--crc-selftest"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout)
+    assert out["bad"] == 0 and out["crc_cases"] > 400

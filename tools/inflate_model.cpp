@@ -218,8 +218,56 @@ static void resolve_block(uint8_t* dst, const std::vector<uint32_t>& tok, int mi
     }
 }
 
+// ---- K1c replay: bgzf_crc_kernel's arithmetic, lane by lane (32 lanes, four word streams each) -----------------------
+static CrcTables g_crc; static bool g_crc_built = false;
+static uint32_t crc_block_model(const uint8_t* p, uint32_t n) {
+    if (!g_crc_built) { crc_build_tables(g_crc); g_crc_built = true; }
+    const uint32_t pad = (uint32_t)((uintptr_t)p & 15u), n2 = n + pad, R = n2 / kCrcRow, tail = n2 % kCrcRow;
+    const uint8_t* base = p - pad;
+    auto ldw = [&](uint32_t off, bool any_valid) -> CrcWords {   // the kernel's 16-byte load (bytes outside the message are masked by the callers)
+        CrcWords w{0, 0, 0, 0}; if (!any_valid) return w;
+        uint32_t v[4]; memcpy(v, base + off, 16); w.x = v[0]; w.y = v[1]; w.z = v[2]; w.w = v[3]; return w;
+    };
+    auto step = [&](uint32_t w) { return g_crc.u[0][w & 0xffu] ^ g_crc.u[1][(w >> 8) & 0xffu] ^ g_crc.u[2][(w >> 16) & 0xffu] ^ g_crc.u[3][w >> 24]; };
+    auto t0 = [&](uint32_t i) { return g_crc.t0[i]; };
+    uint32_t v = 0;
+    for (int lane = 0; lane < 32; lane++) {
+        uint32_t d[4] = {0, 0, 0, 0};
+        if (R && pad && lane == 0) { const CrcWords c = crc_head_cancel(ldw(0, true), 0, pad); d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w; }
+        for (uint32_t r = 0; r < R; r++) {
+            const CrcWords w = ldw(r * kCrcRow + 16u * lane, true);
+            d[0] = step(w.x ^ d[0]); d[1] = step(w.y ^ d[1]); d[2] = step(w.z ^ d[2]); d[3] = step(w.w ^ d[3]);
+        }
+        CrcWords t{0, 0, 0, 0};
+        const uint32_t g0 = R * kCrcRow + 16u * lane;
+        if (g0 < n2) t = crc_tail_keep(ldw(g0, true), g0, pad, n2);
+        v ^= crc_multmodp(g_crc.xl[lane], crc_lane_fold(d, t, t0));
+    }
+    return crc_finish(v, g_crc.xa[tail], g_crc.xa[n % kCrcRow], g_crc.xbi[n / kCrcRow]);
+}
+// every length class x every alignment of the block inside the inflated buffer, against zlib's crc32
+static int crc_selftest() {
+    std::vector<uint8_t> buf(65536 + 64 + 512);
+    uint64_t x = 0x9e3779b97f4a7c15ull;
+    for (auto& b : buf) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; b = (uint8_t)(x >> 32); }
+    uint8_t* al = buf.data() + ((16 - ((uintptr_t)buf.data() & 15)) & 15) + 16;
+    const uint32_t sizes[] = {1, 2, 3, 4, 5, 15, 16, 17, 31, 33, 496, 497, 511, 512, 513, 527, 528, 1023, 1024, 1025, 4096, 12345, 65279, 65280, 65281, 65519, 65520, 65535, 65536};
+    long bad = 0, n = 0;
+    for (uint32_t sz : sizes) for (int pad = 0; pad < 16; pad++) {
+        const uint32_t want = (uint32_t)crc32(0L, al + pad, sz), got = crc_block_model(al + pad, sz);
+        n++; if (want != got) { if (bad++ < 5) fprintf(stderr, "crc model: size %u pad %d: %08x != %08x\n", sz, pad, got, want); }
+    }
+    std::fill(buf.begin(), buf.end(), 0);                    // all-zero and all-ones messages (start-state term on its own)
+    for (int pad = 0; pad < 16; pad += 5) { n++; if (crc_block_model(al + pad, 65280) != (uint32_t)crc32(0L, al + pad, 65280)) bad++; }
+    std::fill(buf.begin(), buf.end(), 0xff);
+    for (int pad = 0; pad < 16; pad += 5) { n++; if (crc_block_model(al + pad, 777) != (uint32_t)crc32(0L, al + pad, 777)) bad++; }
+    printf("{\"crc_cases\": %ld, \"bad\": %ld}\n", n, bad);
+    return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
-    if (argc < 2) { fprintf(stderr, "usage: inflate_model file [max_blocks]\n"); return 2; }
+    if (argc < 2) { fprintf(stderr, "usage: inflate_model file [max_blocks] | inflate_model --crc-selftest\n"); return 2; }
+    if (!strcmp(argv[1], "--crc-selftest")) return crc_selftest();
     FILE* f = fopen(argv[1], "rb");
     if (!f) { perror(argv[1]); return 2; }
     const long maxb = argc > 2 ? atol(argv[2]) : 1L << 40;
@@ -259,6 +307,13 @@ int main(int argc, char** argv) {
                 if (bad > 5) return 1;
             }
             if ((int)tok.size() > kTokenCap) { fprintf(stderr, "token cap exceeded\n"); return 1; }
+            if (lead == 0) {     // K1c: the block's CRC-32 by the row-strided formulation against the gzip trailer, at a varying alignment
+                static std::vector<uint8_t> crcbuf(65536 + 128);
+                uint8_t* al = crcbuf.data() + ((16 - ((uintptr_t)crcbuf.data() & 15)) & 15) + 16 + (nblk % 16);
+                memcpy(al, want.data(), isize);
+                const uint32_t trailer = cp[clen] | (cp[clen + 1] << 8) | (cp[clen + 2] << 16) | ((uint32_t)cp[clen + 3] << 24);
+                if (crc_block_model(al, isize) != trailer) { bad++; fprintf(stderr, "block %ld: CRC model disagrees with the gzip trailer\n", nblk); if (bad > 5) return 1; }
+            }
             ntok += tok.size(); bytes += isize;
             if (lead) memmove(raw.data() + 8, raw.data() + 8 + lead, clen + 8);
         }
