@@ -72,6 +72,47 @@ MSD_D RecCore load_core(const uint8_t* __restrict__ buf, uint32_t p) {
     return r;
 }
 
+// Where a record's CIGAR really is.  A CIGAR with more than 65,535 operations is stored as the placeholder
+// <l_seq>S<reflen>N with the real operations in a CG:B,I tag; htslib's bam_read1 swaps it back in before hts-nim sees
+// the record [ext: sam.c bam_tag2cigar; SURVEY Q13].  Same conditions: n_cigar > 0, tid >= 0, pos >= 0, first op = S of
+// length l_seq, the first CG tag has type B and subtype I/i, its count is >= n_cigar and < 2^29.  Only records whose
+// first operation soft-clips the whole read pay for the aux walk.
+struct CigarRef { uint32_t off, n; };
+MSD_D CigarRef rec_cigar(const uint8_t* __restrict__ buf, uint32_t p, const RecCore& r) {
+    CigarRef c{p + 36 + r.l_qname, r.n_cigar};
+    if (r.n_cigar == 0 || r.tid < 0 || r.pos < 0) return c;
+    const uint32_t c0 = ld_u32(buf, c.off);
+    if ((c0 & 15u) != 4u || (c0 >> 4) != (uint32_t)r.l_seq) return c;
+    uint32_t a = c.off + 4 * r.n_cigar + (uint32_t)((r.l_seq + 1) / 2) + (uint32_t)r.l_seq;
+    const uint32_t end = p + 4 + r.block_size;
+    while (a + 3 <= end) {
+        const uint8_t t0 = buf[a], t1 = buf[a + 1], ty = buf[a + 2];
+        a += 3;
+        const bool is_cg = (t0 == 'C' && t1 == 'G');
+        switch (ty) {
+            case 'A': case 'c': case 'C': a += 1; break;
+            case 's': case 'S': a += 2; break;
+            case 'i': case 'I': case 'f': a += 4; break;
+            case 'd': a += 8; break;
+            case 'Z': case 'H': while (a < end && buf[a]) a++; a++; break;
+            case 'B': {
+                if (a + 5 > end) return c;
+                const uint8_t st = buf[a]; const uint32_t cnt = ld_u32(buf, a + 1);
+                const uint32_t es = (st == 'c' || st == 'C') ? 1u : (st == 's' || st == 'S') ? 2u : 4u;
+                if (is_cg) {
+                    if ((st == 'I' || st == 'i') && cnt >= r.n_cigar && cnt < (1u << 29) && (uint64_t)a + 5 + 4ull * cnt <= end) { c.off = a + 5; c.n = cnt; }
+                    return c;
+                }
+                if ((uint64_t)a + 5 + (uint64_t)es * cnt > end) return c;
+                a += 5 + es * cnt; break;
+            }
+            default: return c;
+        }
+        if (is_cg) return c;       // the first CG tag is not an array: CIGAR untouched
+    }
+    return c;
+}
+
 // htslib bam_endpos: pos + reference length (unmapped: 0), a length of 0 counts as 1 -> hts-nim Record.stop
 MSD_D int64_t rec_endpos(const uint8_t* __restrict__ buf, uint32_t cig, uint32_t n_cigar, uint32_t flag, int32_t pos) {
     int64_t rlen = 0;
@@ -214,10 +255,11 @@ records_kernel(const uint8_t* __restrict__ buf, const uint32_t* __restrict__ rec
         if (fp.iflag != 0 && (c.flag & fp.iflag) == 0) continue;             // :280-281
         if (fp.n_rg > 0 && !rg_pass(buf, p, c, fp)) continue;                // :282-285
         int32_t* __restrict__ arr = arena + doff;
-        const uint32_t cig = p + 36 + c.l_qname;
+        const CigarRef cg = rec_cigar(buf, p, c);
+        const uint32_t cig = cg.off;
         if (fp.mode == MSD_MODE_FAST) {                                      // :342-344
             if (!own) continue;
-            const int64_t stop = rec_endpos(buf, cig, c.n_cigar, c.flag, c.pos);
+            const int64_t stop = rec_endpos(buf, cig, cg.n, c.flag, c.pos);
             depth_add(arr, tlen, c.pos, 1, n_events);
             depth_add(arr, tlen, stop, -1, n_events);
             note_end(ct, c.tid, stop, tlen);
@@ -231,7 +273,7 @@ records_kernel(const uint8_t* __restrict__ buf, const uint32_t* __restrict__ rec
         } else {
             // classify for the mate join (:292-298) and emit the read's own blocks (:355-356)
             if ((c.flag & kFlagProper) && !(c.flag & kFlagSupp)) {
-                int64_t stop = rec_endpos(buf, cig, c.n_cigar, c.flag, c.pos);
+                int64_t stop = rec_endpos(buf, cig, cg.n, c.flag, c.pos);
                 uint8_t cl = kClsT;
                 if (c.tid == c.mtid && stop > (int64_t)c.mpos) { if (c.pos < c.mpos) cl = kClsU; else if (c.pos == c.mpos) cl = kClsE; }
                 mc.cls[r] = cl;
@@ -240,7 +282,7 @@ records_kernel(const uint8_t* __restrict__ buf, const uint32_t* __restrict__ rec
                 mc.slot[r] = kNoOff;
             }
             if (own) {
-                BlockIter it; it.init(buf, cig, c.n_cigar, c.pos);
+                BlockIter it; it.init(buf, cig, cg.n, c.pos);
                 int64_t s, e, last_e = c.pos;
                 while (it.next(s, e)) { depth_add(arr, tlen, s, 1, n_events); depth_add(arr, tlen, e, -1, n_events); last_e = e; }
                 note_end(ct, c.tid, last_e, tlen);
@@ -388,16 +430,17 @@ __global__ void mate_replay_kernel(MateTable T, LiveList L, LiveList Lnew, const
                 const uint32_t tlen = ct.tlen[cx.tid];
                 uint32_t m_ncig; int64_t m_start, m_stop; const uint8_t* m_buf; uint32_t m_cig;
                 if (kind == 1) { const LiveEntry& e = L.e[sidx]; m_ncig = e.n_cigar; m_start = e.start; m_stop = e.stop; m_buf = L.arena; m_cig = e.cigar_off; }
-                else { const uint32_t pm = rec_off[sidx]; const RecCore cm = load_core(buf, pm); m_ncig = cm.n_cigar; m_start = cm.pos; m_stop = mc.endpos[sidx]; m_buf = buf; m_cig = pm + 36 + cm.l_qname; }
+                else { const uint32_t pm = rec_off[sidx]; const RecCore cm = load_core(buf, pm); const CigarRef gm = rec_cigar(buf, pm, cm); m_ncig = gm.n; m_start = cm.pos; m_stop = mc.endpos[sidx]; m_buf = buf; m_cig = gm.off; }
+                const CigarRef gx = rec_cigar(buf, px, cx);
                 if (!ct.owned(cx.tid, cx.pos)) {
                     // the taker belongs to another shard: that shard applies the correction
-                } else if (cx.n_cigar == 1 && m_ncig == 1) {                  // :307-309
+                } else if (gx.n == 1 && m_ncig == 1) {                        // :307-309
                     depth_add(arr, tlen, cx.pos, -1, n_events);
                     depth_add(arr, tlen, m_stop, 1, n_events);
                     note_end(ct, cx.tid, m_stop, tlen);
                 } else {                                                      // :323-338
                     BlockIter a, b;
-                    a.init(buf, px + 36 + cx.l_qname, cx.n_cigar, cx.pos);
+                    a.init(buf, gx.off, gx.n, cx.pos);
                     b.init(m_buf, m_cig, m_ncig, m_start);
                     subtract_overlap(a, b, arr, tlen, n_events);
                 }
@@ -410,17 +453,18 @@ __global__ void mate_replay_kernel(MateTable T, LiveList L, LiveList Lnew, const
             const uint32_t pm = rec_off[sidx];
             const RecCore cm = load_core(buf, pm);
             const uint32_t lq = cm.l_qname ? cm.l_qname - 1 : 0;
-            const uint32_t bytes = ((lq + 3u) & ~3u) + 4u * cm.n_cigar;
+            const CigarRef gm = rec_cigar(buf, pm, cm);
+            const uint32_t bytes = ((lq + 3u) & ~3u) + 4u * gm.n;
             const uint32_t idx = atomicAdd(Lnew.n, 1u);
             const uint32_t off = atomicAdd(Lnew.arena_used, bytes);
             if (idx >= Lnew.cap) { atomicExch(&rc->error, 2u); continue; }
             if ((uint64_t)off + bytes > Lnew.arena_cap) { atomicExch(&rc->error, 3u); continue; }
             LiveEntry& e = Lnew.e[idx];
-            e.key = mc.qhash[sidx]; e.tid = cm.tid; e.start = cm.pos; e.stop = mc.endpos[sidx]; e.n_cigar = cm.n_cigar; e.l_qname = lq;
+            e.key = mc.qhash[sidx]; e.tid = cm.tid; e.start = cm.pos; e.stop = mc.endpos[sidx]; e.n_cigar = gm.n; e.l_qname = lq;
             e.qname_off = off; e.cigar_off = off + ((lq + 3u) & ~3u); e.state = 0;
             for (uint32_t i = 0; i < lq; i++) Lnew.arena[off + i] = buf[pm + 36 + i];
             uint32_t* cg = reinterpret_cast<uint32_t*>(Lnew.arena + e.cigar_off);
-            for (uint32_t i = 0; i < cm.n_cigar; i++) cg[i] = ld_u32(buf, pm + 36 + cm.l_qname + 4 * i);
+            for (uint32_t i = 0; i < gm.n; i++) cg[i] = ld_u32(buf, gm.off + 4 * i);
         }
     }
     n_events = __reduce_add_sync(0xffffffffu, n_events);

@@ -186,7 +186,7 @@ static uint64_t bgzf_tell(const bgzf_t *bz) {
 typedef struct { char *name; uint32_t length; int tid; } target_t;   /* hts.Target */
 
 typedef struct {
-    int32_t tid, pos; uint8_t l_qname, mapq; uint16_t n_cigar, flag; int32_t l_seq, mtid, mpos, isize;
+    int32_t tid, pos; uint8_t l_qname, mapq; uint32_t n_cigar; uint16_t flag; int32_t l_seq, mtid, mpos, isize;
     uint8_t *data; uint32_t l_data, m_data;   /* qname, cigar, seq, qual, aux */
 } rec_t;
 
@@ -204,9 +204,51 @@ static inline int cig_type(uint32_t op) { return (0x3C1A7 >> ((op & 15) << 1)) &
 /* htslib bam_endpos: pos + reference length (0 if unmapped), length 0 treated as 1 -> hts-nim Record.stop */
 static int64_t rec_stop(const rec_t *r) {
     int64_t rlen = 0;
-    if (!(r->flag & FLAG_UNMAP)) for (int i = 0; i < r->n_cigar; i++) { uint32_t c = cig_at(r, i); if (cig_type(c) & 2) rlen += c >> 4; }
+    if (!(r->flag & FLAG_UNMAP)) for (uint32_t i = 0; i < r->n_cigar; i++) { uint32_t c = cig_at(r, (int)i); if (cig_type(c) & 2) rlen += c >> 4; }
     if (rlen == 0) rlen = 1;
     return (int64_t)r->pos + rlen;
+}
+
+/* [ext] htslib sam.c bam_tag2cigar, called by bam_read1 (the reader behind hts-nim's `for rec in bam.query(...)`,
+ * mosdepth.nim:185): a CIGAR with more than 65,535 operations does not fit the 16-bit n_cigar_op field, so the writer
+ * stores the placeholder <l_seq>S<reflen>N and keeps the real CIGAR in a CG:B,I tag (SAM spec 4.2.2); the reader swaps
+ * it back in and drops the tag.  Conditions as in htslib: n_cigar > 0, tid >= 0, pos >= 0, first op == S of length
+ * l_seq, first "CG" tag is of type B with subtype I (or i), and its count is >= n_cigar and < 2^29. */
+static void rec_restore_long_cigar(rec_t *r) {
+    if (r->n_cigar == 0 || r->tid < 0 || r->pos < 0) return;
+    uint32_t c0; memcpy(&c0, r->data + r->l_qname, 4);
+    if ((c0 & 15) != 4 || (c0 >> 4) != (uint32_t)r->l_seq) return;
+    const size_t fake = 4 * (size_t)r->n_cigar;
+    size_t p = (size_t)r->l_qname + fake + (size_t)((r->l_seq + 1) / 2) + (size_t)r->l_seq;   /* first aux byte */
+    size_t tag_at = 0, tag_end = 0; int found = 0;
+    while (p + 3 <= r->l_data) {
+        const uint8_t *a = r->data + p; const uint8_t t = a[2]; const size_t at = p; p += 3;
+        const int match = a[0] == 'C' && a[1] == 'G';
+        switch (t) {
+        case 'A': case 'c': case 'C': p += 1; break;
+        case 's': case 'S': p += 2; break;
+        case 'i': case 'I': case 'f': p += 4; break;
+        case 'd': p += 8; break;
+        case 'Z': case 'H': p += strnlen((const char *)r->data + p, r->l_data - p) + 1; break;
+        case 'B': { if (p + 5 > r->l_data) return; uint8_t st = r->data[p]; uint32_t cnt; memcpy(&cnt, r->data + p + 1, 4); size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4; p += 5 + es * (size_t)cnt; break; }
+        default: return;                                                   /* bad aux data */
+        }
+        if (match) { if (p > r->l_data) return; tag_at = at; tag_end = p; found = 1; break; }   /* bam_aux_get: the first CG tag */
+    }
+    if (!found) return;
+    const uint8_t *cg = r->data + tag_at + 2;                              /* type byte */
+    if (cg[0] != 'B' || !(cg[1] == 'I' || cg[1] == 'i')) return;
+    uint32_t cg_len; memcpy(&cg_len, cg + 2, 4);
+    if (cg_len < r->n_cigar || cg_len >= (1u << 29)) return;
+    /* new layout: qname | real CIGAR | seq, qual, aux before CG | aux after CG */
+    const size_t real = 4 * (size_t)cg_len, mid_beg = (size_t)r->l_qname + fake;
+    const size_t new_len = (size_t)r->l_qname + real + (tag_at - mid_beg) + ((size_t)r->l_data - tag_end);
+    uint8_t *nd = (uint8_t *)xmalloc(new_len + 256), *w = nd;
+    memcpy(w, r->data, r->l_qname); w += r->l_qname;
+    memcpy(w, cg + 6, real); w += real;
+    memcpy(w, r->data + mid_beg, tag_at - mid_beg); w += tag_at - mid_beg;
+    memcpy(w, r->data + tag_end, (size_t)r->l_data - tag_end);
+    free(r->data); r->data = nd; r->l_data = (uint32_t)new_len; r->m_data = (uint32_t)new_len + 256; r->n_cigar = cg_len;
 }
 
 static int bam_read_record(bgzf_t *bz, rec_t *r) {
@@ -215,11 +257,12 @@ static int bam_read_record(bgzf_t *bz, rec_t *r) {
     if (k < 0 || bs < 32) die(1, "[oracle] truncated/corrupt BAM record");
     uint8_t core[32]; if (bgzf_read(bz, core, 32) != 32) die(1, "[oracle] truncated BAM record");
     memcpy(&r->tid, core, 4); memcpy(&r->pos, core + 4, 4); r->l_qname = core[8]; r->mapq = core[9];
-    memcpy(&r->n_cigar, core + 12, 2); memcpy(&r->flag, core + 14, 2); memcpy(&r->l_seq, core + 16, 4);
+    { uint16_t nc; memcpy(&nc, core + 12, 2); r->n_cigar = nc; } memcpy(&r->flag, core + 14, 2); memcpy(&r->l_seq, core + 16, 4);
     memcpy(&r->mtid, core + 20, 4); memcpy(&r->mpos, core + 24, 4); memcpy(&r->isize, core + 28, 4);
     r->l_data = (uint32_t)bs - 32;
     if (r->l_data > r->m_data) { r->m_data = r->l_data + 256; r->data = (uint8_t *)xrealloc(r->data, r->m_data); }
     if (r->l_data && bgzf_read(bz, r->data, r->l_data) != (int64_t)r->l_data) die(1, "[oracle] truncated BAM record");
+    rec_restore_long_cigar(r);
     return 1;
 }
 
@@ -359,7 +402,7 @@ static void gen_start_ends(const rec_t *r, int64_t ipos, pairvec *out) {
         pv_push(out, ipos, 1); pv_push(out, ipos + (cig_at(r, 0) >> 4), -1); return;
     }
     int64_t pos = ipos, last_stop = -1;
-    for (int i = 0; i < r->n_cigar; i++) {                        /* :155-166 */
+    for (uint32_t i = 0; i < r->n_cigar; i++) {                   /* :155-166 */
         uint32_t c = cig_at(r, i); int con = cig_type(c);
         if (!(con & 2)) continue;
         int64_t olen = c >> 4;

@@ -80,7 +80,12 @@ def synth(tmp_path_factory):
     for key, args in {"c3": ["--config", "c3", "--genome-fraction", "0.001"], "c2": ["--config", "c2", "--genome-fraction", "0.02"],
                       "c2_straddle": ["--config", "c2", "--genome-fraction", "0.01", "--straddle", "--level", "1"],
                       "c5": ["--config", "c5", "--genome-fraction", "0.0015", "--level", "1"],
-                      "c4": ["--config", "c4", "--genome-fraction", "0.002", "--bed", str(d / "c4.bed")]}.items():
+                      "c4": ["--config", "c4", "--genome-fraction", "0.002", "--bed", str(d / "c4.bed")],
+                      # CIGARs kept in CG:B,I tags behind the <l_seq>S<reflen>N placeholder: every second multi-op
+                      # record of a short-read BAM, one-op records too (htslib leaves those alone), and long reads with
+                      # more than 65,535 operations
+                      "c2_cg": ["--config", "c2", "--genome-fraction", "0.008", "--cg-every", "2", "--cg-short"],
+                      "c5_cg": ["--config", "c5", "--genome-fraction", "0.0008", "--level", "1", "--dense", "--cg-every", "2"]}.items():
         subprocess.run([str(GEN)] + args + ["--threads", "8", "-o", str(d / f"{key}.bam")], check=True, capture_output=True)
         out[key] = d / f"{key}.bam"
     out["c4_bed"] = d / "c4.bed"
@@ -92,6 +97,7 @@ SYN_CASES = [
     ("c2", []), ("c2", ["-x"]), ("c2", ["-F", "0", "-Q", "1"]), ("c2", ["-q", "0:1:10:30:", "-n"]), ("c2", ["-R", "grp1", "-n", "--by", "1000"]), ("c2", ["-R", "nope", "-n"]),
     ("c2_straddle", []), ("c2_straddle", ["-x", "--by", "500", "-n"]),
     ("c5", []), ("c5", ["-x", "-n", "--by", "500"]), ("c5", ["-a", "-n", "--by", "2000"]),
+    ("c2_cg", []), ("c2_cg", ["-x", "--by", "500"]), ("c5_cg", []), ("c5_cg", ["-x", "-n", "--by", "500"]), ("c5_cg", ["-a", "-n", "--by", "2000"]),
 ]
 
 
@@ -111,3 +117,5 @@ def test_small_chunks_exercise_carry_and_live_mates(oracle_bin, synth, tmp_path)
     compare(oracle_bin, tmp_path, synth["c2_straddle"], [], env=env)
     compare(oracle_bin, tmp_path, synth["c5"], ["--by", "1000"], env=env)
     compare(oracle_bin, tmp_path, synth["c2"], ["--by", "500"], env=env)
+    compare(oracle_bin, tmp_path, synth["c2_cg"], [], env=env)
+    compare(oracle_bin, tmp_path, synth["c5_cg"], ["--by", "1000"], env=env)

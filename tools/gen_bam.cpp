@@ -2,7 +2,7 @@
 // (SURVEY.md section 8d).  Test/bench infrastructure: produces coordinate-sorted, BGZF-compressed BAM files with
 // the record shapes of short-read paired-end WGS (C2/C3), exome capture (C4) and nanopore long reads (C5).
 //
-//   gen_bam --config c3 --genome-fraction 0.05 --threads 16 --level 6 -o /dev/shm/c3.bam [--straddle] [--bed out.bed]
+//   gen_bam --config c3 --genome-fraction 0.05 --threads 16 --level 6 -o /dev/shm/c3.bam [--straddle] [--bed out.bed] [--cg-every N [--cg-short]] [--dense]
 //
 // Everything is a pure function of (seed, contig, tile, index): threads generate disjoint position tiles and the
 // output is identical for any thread count.  BGZF blocks are written htslib-style (a record never straddles a block
@@ -62,18 +62,28 @@ struct ReadSpec {
 
 static int32_t cigar_reflen(const std::vector<uint32_t>& c) { int32_t r = 0; for (uint32_t x : c) { int op = x & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) r += x >> 4; } return r; }
 
+// --cg-every N: every Nth record (and every record with more than 65,535 operations, always) keeps its CIGAR in a CG:B,I
+// tag behind the <l_seq>S<reflen>N placeholder (SAM spec 4.2.2; htslib's bam_read1 swaps it back in)
+static int g_cg_every = 0;
+static bool g_cg_short = false;
+static bool g_dense = false;   // --dense: one long read in six gets an operation every ~2 bp (more than 65,535 on a long read)
+
 static void serialise(const ReadSpec& r, bool long_read, Record& out) {
     Rng g(r.seed);
     std::vector<uint8_t>& b = out.bytes; b.clear();
     const int32_t reflen = cigar_reflen(r.cigar);
+    // htslib leaves the placeholder alone when the tag holds fewer operations than the placeholder's two: one-operation
+    // CIGARs are only moved with --cg-short (they then count as <l_seq>S<reflen>N, in the reference as well)
+    const bool cg = r.cigar.size() > 65535 || (g_cg_every > 0 && r.cigar.size() >= (g_cg_short ? 1u : 2u) && (r.seed >> 7) % (uint64_t)g_cg_every == 0);
     out.pos = r.pos; out.end = r.pos + std::max(reflen, 1);
     put32(b, 0);   // block_size patched below
     put32(b, (uint32_t)r.tid); put32(b, (uint32_t)r.pos);
     b.push_back((uint8_t)(r.qname.size() + 1)); b.push_back(r.mapq); put16(b, (uint32_t)reg2bin(out.pos, out.end));
-    put16(b, (uint32_t)r.cigar.size()); put16(b, r.flag); put32(b, (uint32_t)r.l_seq);
+    put16(b, cg ? 2u : (uint32_t)r.cigar.size()); put16(b, r.flag); put32(b, (uint32_t)r.l_seq);
     put32(b, (uint32_t)((r.flag & 1) ? r.tid : -1)); put32(b, (uint32_t)((r.flag & 1) ? r.mpos : -1)); put32(b, (uint32_t)r.tlen);
     b.insert(b.end(), r.qname.begin(), r.qname.end()); b.push_back(0);
-    for (uint32_t c : r.cigar) put32(b, c);
+    if (cg) { put32(b, ((uint32_t)r.l_seq << 4) | 4u); put32(b, ((uint32_t)reflen << 4) | 3u); }
+    else for (uint32_t c : r.cigar) put32(b, c);
     static const uint8_t code[4] = {1, 2, 4, 8};
     for (int32_t i = 0; i < (r.l_seq + 1) / 2; i++) { uint32_t x = (uint32_t)g.next(); b.push_back((uint8_t)((code[x & 3] << 4) | code[(x >> 2) & 3])); }
     if (!long_read) {   // 4-level binned qualities with runs (NovaSeq-like)
@@ -86,7 +96,9 @@ static void serialise(const ReadSpec& r, bool long_read, Record& out) {
     const char* rg = "RGZgrp1"; b.insert(b.end(), rg, rg + 7); b.push_back(0);
     b.push_back('N'); b.push_back('M'); b.push_back('C'); b.push_back((uint8_t)(g.next() % 4));
     if (!long_read) { std::string md = "MDZ" + std::to_string(reflen); b.insert(b.end(), md.begin(), md.end()); b.push_back(0); }
+    if (cg && (r.seed & 64)) { b.push_back('C'); b.push_back('G'); b.push_back('B'); b.push_back('I'); put32(b, (uint32_t)r.cigar.size()); for (uint32_t c : r.cigar) put32(b, c); }
     b.push_back('A'); b.push_back('S'); b.push_back('C'); b.push_back((uint8_t)(100 + g.next() % 50));
+    if (cg && !(r.seed & 64)) { b.push_back('C'); b.push_back('G'); b.push_back('B'); b.push_back('I'); put32(b, (uint32_t)r.cigar.size()); for (uint32_t c : r.cigar) put32(b, c); }
     uint32_t bs = (uint32_t)b.size() - 4; memcpy(b.data(), &bs, 4);
 }
 
@@ -175,8 +187,9 @@ static void gen_long_tile(const Config& cfg, int tid, uint32_t clen, int64_t til
         // op every ~10 bp: M 50 % / D 28 % / I 21 % (tests/nanopore.bam histogram), geometric lengths
         int64_t ref = 0, qlen = 0;
         if (supp) { uint32_t h = 100 + g.below(2000); x.cigar.push_back((h << 4) | 5); }
-        while (ref < len && x.cigar.size() < 60000) {
-            uint32_t m = 1 + (uint32_t)(-std::log(1.0 - g.uni() * 0.999999) * 18.0);
+        const bool dense = g_dense && g.below(6) == 0;
+        while (ref < len && x.cigar.size() < (g_dense ? 250000u : 60000u)) {
+            uint32_t m = 1 + (uint32_t)(-std::log(1.0 - g.uni() * 0.999999) * (dense ? 1.2 : 18.0));
             m = (uint32_t)std::min<int64_t>(m, len - ref);
             if (m) { x.cigar.push_back(m << 4); ref += m; qlen += m; }
             if (ref >= len) break;
@@ -237,7 +250,7 @@ int main(int argc, char** argv) {
         if (a == "--config") cfg.name = val(); else if (a == "--genome-fraction") cfg.fraction = atof(val().c_str());
         else if (a == "--coverage") cfg.coverage = atof(val().c_str()); else if (a == "--seed") cfg.seed = strtoull(val().c_str(), nullptr, 10);
         else if (a == "--threads") cfg.threads = atoi(val().c_str()); else if (a == "--level") cfg.level = atoi(val().c_str());
-        else if (a == "--straddle") cfg.straddle = true; else if (a == "-o") cfg.out = val(); else if (a == "--bed") cfg.bed = val();
+        else if (a == "--straddle") cfg.straddle = true; else if (a == "--cg-every") g_cg_every = atoi(val().c_str()); else if (a == "--dense") g_dense = true; else if (a == "--cg-short") g_cg_short = true; else if (a == "-o") cfg.out = val(); else if (a == "--bed") cfg.bed = val();
         else if (a == "--contig") cfg.only_contig = atoi(val().c_str());
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
