@@ -44,30 +44,50 @@ def ensure_built():
         ge.build()
 
 
-def data_dir():
+def _candidates():
     for d in (os.environ.get("MSD_BENCH_DIR"), "/dev/shm", "/tmp"):
         if d and os.path.isdir(d) and os.access(d, os.W_OK):
             p = Path(d) / "msd_bench"
             p.mkdir(exist_ok=True)
+            yield p
+
+
+def data_dir(need_bytes=0, keep_tag=None):
+    """A writable directory (memory-backed when possible) with room for `need_bytes`; BAMs cached for other sizes are
+    dropped before a slower directory is tried."""
+    cands = list(_candidates())
+    if not cands:
+        raise RuntimeError("no writable data dir")
+    free = lambda p: os.statvfs(p).f_bavail * os.statvfs(p).f_frsize
+    for p in cands:
+        if free(p) >= need_bytes:
             return p
-    raise RuntimeError("no writable data dir")
+    for p in cands:
+        for f in p.iterdir():
+            if f.is_file() and (keep_tag is None or not f.name.startswith(keep_tag)):
+                f.unlink()
+        if free(p) >= need_bytes:
+            return p
+    raise RuntimeError(f"no data dir with {need_bytes / 1e9:.1f} GB free")
 
 
 def make_bam(config, fraction, seed, threads, level=6):
     """Generate (or reuse) the synthetic BAM. Returns (path, n_reads, n_bytes)."""
-    d = data_dir()
     tag = f"{config}_f{fraction:g}_s{seed}_l{level}"
-    bam = d / f"{tag}.bam"
-    meta = d / f"{tag}.json"
-    if not (bam.exists() and meta.exists() and Path(str(bam) + ".bai").exists()):
-        tmp = d / f"{tag}.tmp.{os.getpid()}.bam"
-        r = sh([str(ROOT / "tools" / "gen_bam"), "--config", config, "--genome-fraction", str(fraction), "--seed", str(seed),
-                "--threads", str(threads), "--level", str(level), "-o", str(tmp)])
-        info = json.loads(r.stdout.strip().splitlines()[-1])
-        os.replace(str(tmp) + ".bai", str(bam) + ".bai")
-        os.replace(tmp, bam)
-        meta.write_text(json.dumps(info))
-    info = json.loads(meta.read_text())
+    for d in _candidates():      # generated earlier (by this rank or by rank 0)
+        bam, meta = d / f"{tag}.bam", d / f"{tag}.json"
+        if bam.exists() and meta.exists() and Path(str(bam) + ".bai").exists():
+            info = json.loads(meta.read_text())
+            return bam, info["reads"], info["bytes"]
+    d = data_dir(int(fraction * 60e9 * 1.1) + (64 << 20), keep_tag=tag)     # a 30X genome is ~56 GB of BAM at level 6
+    bam, meta = d / f"{tag}.bam", d / f"{tag}.json"
+    tmp = d / f"{tag}.tmp.{os.getpid()}.bam"
+    r = sh([str(ROOT / "tools" / "gen_bam"), "--config", config, "--genome-fraction", str(fraction), "--seed", str(seed),
+            "--threads", str(threads), "--level", str(level), "-o", str(tmp)])
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    os.replace(str(tmp) + ".bai", str(bam) + ".bai")
+    os.replace(tmp, bam)
+    meta.write_text(json.dumps(info))
     return bam, info["reads"], info["bytes"]
 
 
