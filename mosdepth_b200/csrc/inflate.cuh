@@ -30,6 +30,7 @@
 //       a third of them contain a source of their own and had to be redone in halves).  Bytes whose source lies inside their own window find their
 //       root byte by pointer doubling over shuffles (5 steps; period folding for dist < len).
 #pragma once
+#include <cstdlib>
 #include "inflate_core.cuh"
 
 namespace msd {
@@ -551,8 +552,8 @@ bgzf_crc_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ b
             const CrcWords c = crc_head_cancel(CrcWords{v.x, v.y, v.z, v.w}, 0, pad);
             d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
         }
-#pragma unroll 4
-        for (uint32_t r = 0; r < R; r++) {
+#pragma unroll 8
+        for (uint32_t r = 0; r < R; r++) {                      // eight rows (4 KB per warp) of loads in flight
             const uint4 v = __ldg(q + r * 32);
             d[0] = step(v.x ^ d[0]); d[1] = step(v.y ^ d[1]); d[2] = step(v.z ^ d[2]); d[3] = step(v.w ^ d[3]);
         }
@@ -568,14 +569,26 @@ bgzf_crc_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ b
 
 // K1 = K1a + K1b (+ K1c) on one stream.  tickets: three zeroed words (K1a, K1b, K1c).  comp_read (may be null) is recorded
 // after K1a: from then on the compressed chunk buffer may be overwritten.  resolved (may be null) is recorded after K1b.
+// Tuning knobs (read at every launch so that one process can sweep them, tools/sweep_inflate.py): MSD_DEC_CTAS caps the decode
+// warps per SM (default 9 = what shared memory allows), MSD_RESOLVE_CTAS the resolve CTAs per SM the grid is sized for.
+inline int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    const int x = atoi(v);
+    return x < lo ? lo : x > hi ? hi : x;
+}
+
 inline void launch_inflate(cudaStream_t s, const uint8_t* d_comp, uint8_t* d_out, const BlockDesc* d_desc, int nb, uint32_t* tickets,
                            uint32_t* d_tokens, uint32_t* d_ntok, uint32_t* d_status, uint32_t* d_error_count, uint32_t* d_crc,
-                           bool check_crc, cudaEvent_t comp_read, cudaEvent_t resolved = nullptr) {
-    const int dctas = (nb + kDecThreads - 1) / kDecThreads < kSMs * kDecCtasPerSm ? (nb + kDecThreads - 1) / kDecThreads : kSMs * kDecCtasPerSm;
+                           bool check_crc, cudaEvent_t comp_read, cudaEvent_t resolved = nullptr, cudaEvent_t decoded_trace = nullptr) {
+    const int dec_cap = kSMs * env_int("MSD_DEC_CTAS", kDecCtasPerSm, 1, kDecCtasPerSm);
+    const int dctas = (nb + kDecThreads - 1) / kDecThreads < dec_cap ? (nb + kDecThreads - 1) / kDecThreads : dec_cap;
     huffman_decode_kernel<<<dctas, kDecThreads, kDecSmem, s>>>(d_comp, d_out, d_desc, nb, tickets, d_tokens, d_ntok, d_status, d_error_count, d_crc);
     if (comp_read) cudaEventRecord(comp_read, s);
+    if (decoded_trace) cudaEventRecord(decoded_trace, s);
     const int want = (nb + kResolveWarps - 1) / kResolveWarps;
-    const int rctas = want < kSMs * kResolveCtasPerSm ? want : kSMs * kResolveCtasPerSm;
+    const int res_cap = kSMs * env_int("MSD_RESOLVE_CTAS", kResolveCtasPerSm, 1, kResolveCtasPerSm);
+    const int rctas = want < res_cap ? want : res_cap;
     lz77_resolve_kernel<<<rctas, kResolveWarps * 32, 0, s>>>(d_out, d_desc, nb, tickets + 1, d_tokens, d_ntok);
     if (resolved) cudaEventRecord(resolved, s);      // the inflated bytes are final: framing need not wait for the CRC check
     if (check_crc) {

@@ -350,7 +350,7 @@ __global__ void init_accum_kernel(ContigAccum* a, RegionAccum* r) {
     if (r) { r->cum_length = 0; r->cum_depth = 0; r->min_depth = 0xffffffffu; r->max_depth = 0; r->neg_seen = 0; r->pad = 0; }
 }
 
-struct StageTimes { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> h2d, inflate, frame, records; };
+struct StageTimes { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> h2d, inflate, frame, records, k1; };   // k1: end of K1a, end of K1b
 
 double sum_ms(const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v) {
     double s = 0; for (auto& p : v) { float ms = 0; if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) s += ms; } return s;
@@ -659,6 +659,7 @@ int msd_run(msd_ctx* ctx) {
     for (auto& r : ctx->results) { r.have = false; r.dist.clear(); }
     cudaStream_t sc = ctx->s_compute, sx = ctx->s_copy;
     StageTimes times;
+    const bool trace = getenv("MSD_TRACE") != nullptr;
     cudaEvent_t ev_begin = next_event(ctx), ev_zero_end = next_event(ctx), ev_chunks_end = next_event(ctx), ev_end = next_event(ctx);
 
     MSD_CUDA_OK(cudaEventRecord(ev_begin, sc));
@@ -774,11 +775,12 @@ int msd_run(msd_ctx* ctx) {
             uint8_t* infl_buf = ctx->d_infl[k];
             cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
             cudaEvent_t f0 = next_event(ctx);
+            cudaEvent_t tr0 = trace ? next_event(ctx) : nullptr;
             MSD_CUDA_OK(cudaStreamWaitEvent(si, ctx->infl_free[k], 0));      // consumers of the previous contents of d_infl[k] are done
             MSD_CUDA_OK(cudaMemsetAsync(ctx->d_ticket + 3 * k, 0, 12, si));
             MSD_CUDA_OK(cudaEventRecord(e0, si));
             launch_inflate(si, d_comp, infl_buf, ctx->d_desc[kd], (int)nb, ctx->d_ticket + 3 * k, ctx->d_tokens[k], ctx->d_ntok[k],
-                           ctx->d_status + (size_t)k * ctx->max_blocks, ctx->d_inflate_err, ctx->d_crc[k], ctx->check_crc, ctx->comp_free[k], ctx->infl_done[k]);
+                           ctx->d_status + (size_t)k * ctx->max_blocks, ctx->d_inflate_err, ctx->d_crc[k], ctx->check_crc, ctx->comp_free[k], ctx->infl_done[k], tr0);
             ctx->info.n_launches += ctx->check_crc ? 3 : 2; ctx->info.n_inflate_launches++;
             MSD_CUDA_OK(cudaEventRecord(e1, si));
             MSD_CUDA_OK(cudaEventRecord(ctx->crc_done[kd], si));
@@ -818,7 +820,7 @@ int msd_run(msd_ctx* ctx) {
             MSD_CUDA_OK(cudaEventRecord(ctx->desc_free[kd], sc));  // d_desc[kd], d_rel[kd] may be overwritten from here on (d_comp[k]: after the decode kernel)
             MSD_CUDA_OK(cudaEventRecord(ctx->infl_free[k], sc));   // ... and so may d_infl[k]
             MSD_CUDA_OK(cudaGetLastError());
-            times.inflate.push_back({e0, e1}); times.frame.push_back({f0, e2}); times.records.push_back({e2, e3});
+            times.inflate.push_back({e0, e1}); times.frame.push_back({f0, e2}); times.records.push_back({e2, e3}); times.k1.push_back({tr0, f0});
             ctx->info.bytes_compressed += comp_bytes; ctx->info.bytes_inflated += infl; ctx->info.n_blocks += nb;
             first_of_span = false;
             chunk_idx++;
@@ -943,12 +945,12 @@ int msd_run(msd_ctx* ctx) {
     cudaEventElapsedTime(&ms, ev_begin, ev_end); ctx->info.ms_total = ms;
     cudaEventElapsedTime(&ms, ev_begin, ev_zero_end); ctx->info.ms_zero = ms;
     cudaEventElapsedTime(&ms, s0, s1); ctx->info.ms_scan = ms;
-    if (getenv("MSD_TRACE")) {
+    if (trace) {
         auto rel = [&](cudaEvent_t e) { float m = 0; cudaEventElapsedTime(&m, ev_begin, e); return m; };
         for (size_t i = 0; i < times.inflate.size(); i++)
-            fprintf(stderr, "[msd trace] chunk %zu: h2d %.2f..%.2f  inflate %.2f..%.2f  frame ..%.2f  records ..%.2f\n", i,
+            fprintf(stderr, "[msd trace] chunk %zu: h2d %.2f..%.2f  inflate %.2f (decoded %.2f, resolved <= %.2f) ..%.2f  frame ..%.2f  records ..%.2f\n", i,
                     i < times.h2d.size() ? rel(times.h2d[i].first) : -1.f, i < times.h2d.size() ? rel(times.h2d[i].second) : -1.f,
-                    rel(times.inflate[i].first), rel(times.inflate[i].second), rel(times.frame[i].second), rel(times.records[i].second));
+                    rel(times.inflate[i].first), times.k1[i].first ? rel(times.k1[i].first) : -1.f, rel(times.k1[i].second), rel(times.inflate[i].second), rel(times.frame[i].second), rel(times.records[i].second));
         fprintf(stderr, "[msd trace] chunks end %.2f  scans %.2f..%.2f  end %.2f\n", rel(ev_chunks_end), rel(s0), rel(s1), rel(ev_end));
     }
     if (!times.inflate.empty()) { float sp = 0; cudaEventElapsedTime(&sp, times.inflate.front().first, times.inflate.back().second); ctx->info.ms_inflate_span = sp; }

@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Sweep the inflate pipeline's knobs on one GPU in one process (resident input, device-timed msd_run only):
+chunk size (blocks per launch), decode warps per SM, resolve CTAs per SM, CRC on/off.  Prints one line per setting.
+usage: python tools/sweep_inflate.py [genome_fraction] [trace]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import mosdepth_b200 as m
+from mosdepth_b200 import hostio
+import bench
+
+frac = float(sys.argv[1]) if len(sys.argv) > 1 else 0.03
+bam, n_reads, n_bytes = bench.make_bam("c3", frac, 20261022, os.cpu_count() or 8)
+hdr = hostio.read_bam_header(bam)
+raw = np.fromfile(bam, dtype=np.uint8)
+host = torch.empty(raw.size, dtype=torch.uint8, pin_memory=True); host.numpy()[:] = raw
+
+
+def timed(ctx, steps=4, warm=2):
+    for _ in range(warm):
+        ctx.run()
+    torch.cuda.synchronize()
+    ctx.mark(0)
+    infos = [ctx.run() for _ in range(steps)]
+    ctx.mark(1)
+    torch.cuda.synchronize()
+    return ctx.elapsed_ms(0, 1) / steps, sum(i.ms_inflate_span for i in infos) / steps
+
+
+def with_ctx(env, fn):
+    for k, v in env.items():
+        os.environ[k] = str(v)
+    ctx = m.Context(0); ctx.open_mem(host, hdr); ctx.set_filters(mode=m.MODE_FAST); ctx.prefetch_windows(500); ctx.stage()
+    try:
+        return fn(ctx)
+    finally:
+        ctx.close()
+        for k in env:
+            os.environ.pop(k, None)
+
+
+def sweep(ctx, label):
+    for dc in (9, 8, 7, 6):
+        for rc in (16, 12, 8, 6, 4):
+            os.environ["MSD_DEC_CTAS"] = str(dc); os.environ["MSD_RESOLVE_CTAS"] = str(rc)
+            ms, span = timed(ctx)
+            print(f"{label} dec_ctas {dc} resolve_ctas {rc}: {ms:7.2f} ms/step  inflate span {span:7.2f}  {n_reads / ms / 1e3:7.1f} M reads/s", flush=True)
+    os.environ.pop("MSD_DEC_CTAS", None); os.environ.pop("MSD_RESOLVE_CTAS", None)
+
+
+for blocks in (24000, 12000, 16000, 32000, 44000):
+    with_ctx({"MSD_CHUNK_BLOCKS": blocks, "MSD_CHUNK_INFL_MB": 3200, "MSD_CHUNK_COMP_MB": 1200}, lambda c: sweep(c, f"chunk {blocks}") if blocks == 24000 else print(f"chunk {blocks}: %.2f ms/step span %.2f" % timed(c), flush=True))
+with_ctx({"MSD_NO_CRC": 1}, lambda c: print("no crc: %.2f ms/step span %.2f" % timed(c), flush=True))
+if len(sys.argv) > 2:
+    def tr(c):
+        timed(c, 1, 2)
+        os.environ["MSD_TRACE"] = "1"; c.run(); os.environ.pop("MSD_TRACE")
+    with_ctx({}, tr)
