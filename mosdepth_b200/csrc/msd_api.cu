@@ -34,8 +34,9 @@ struct Span { uint64_t beg, end; };
 
 // Chunks in flight.  One decode wave costs the same ~7 ms for 6,000 blocks as for 42,624 (the chain per block is serial), so
 // the pipeline wants several modest chunks whose decode launches share the SMs, not two big ones run back to back.
-constexpr int kSlots = 4;
-constexpr int kDescSets = 8;    // block descriptors: deeper than the slots, so that the copy stream never waits for a chunk's framing
+constexpr int kSlots = 8;       // most chunk slots a context can have; ctx->n_slots (MSD_SLOTS = 2, 4 or 8; default 4) are in use
+constexpr int kDescSets = 16;   // block descriptors: deeper than the slots, so that the copy stream never waits for a chunk's framing
+                                // (a multiple of n_slots: chunk i and chunk i - kDescSets share a slot and so an inflate stream)
 
 struct StageSet {              // pinned host staging for one in-flight chunk
     BlockDesc* h_desc = nullptr; uint32_t* h_rel = nullptr;
@@ -55,7 +56,7 @@ struct ContigResult {
 struct msd_ctx {
     int device = 0;
     char err[512] = "";
-    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_inflate[kSlots] = {};
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_inflate[kSlots] = {}; int n_slots = 4;
     // input
     const uint8_t* bytes = nullptr; uint64_t n_bytes = 0; bool mapped = false; bool src_pinned = false;
     int n_targets = 0; std::vector<uint32_t> tlen; uint64_t first_voff = 0;
@@ -193,7 +194,7 @@ void free_chunk_buffers(msd_ctx* ctx) {
         for (cudaEvent_t* e : evs) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
         ctx->stage[k].used = false;
     }
-    for (int k = 0; k < kSlots; k++) {
+    for (int k = 0; k < ctx->n_slots; k++) {
         dev_free(&ctx->d_comp[k]); dev_free(&ctx->d_infl[k]); dev_free(&ctx->d_tokens[k]); dev_free(&ctx->d_ntok[k]); dev_free(&ctx->d_crc[k]);
         cudaEvent_t* evs[] = {&ctx->comp_free[k], &ctx->h2d_done[k], &ctx->infl_done[k], &ctx->infl_free[k], &ctx->bounce_free[k]};
         for (cudaEvent_t* e : evs) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
@@ -205,7 +206,7 @@ int ensure_chunk_buffers(msd_ctx* ctx) {
     if (ctx->d_infl[0]) return 0;
     int rc;
     const uint64_t infl_bytes = (uint64_t)ctx->carry_cap + ctx->infl_cap + 256;
-    for (int k = 0; k < kSlots; k++) {
+    for (int k = 0; k < ctx->n_slots; k++) {
         if ((rc = dev_alloc(ctx, &ctx->d_comp[k], ctx->comp_cap + 256))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_infl[k], infl_bytes))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_tokens[k], (uint64_t)ctx->max_blocks * kTokenCap))) return rc;
@@ -231,7 +232,7 @@ int ensure_chunk_buffers(msd_ctx* ctx) {
     if ((rc = dev_alloc(ctx, &ctx->d_cnt, nb))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_recbase, nb))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_recoff, ctx->rec_cap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_status, (uint64_t)kSlots * ctx->max_blocks))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_status, (uint64_t)ctx->n_slots * ctx->max_blocks))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_ticket, 3 * kSlots))) return rc;
     ctx->check_crc = !getenv("MSD_NO_CRC");
     if ((rc = dev_alloc(ctx, &ctx->d_inflate_err, 4))) return rc;
@@ -242,7 +243,7 @@ int ensure_chunk_buffers(msd_ctx* ctx) {
 
 int ensure_bounce(msd_ctx* ctx) {
     if (ctx->src_pinned || ctx->stage[0].h_bounce) return 0;
-    for (int k = 0; k < kSlots; k++) MSD_CUDA_OK(cudaMallocHost((void**)&ctx->stage[k].h_bounce, ctx->comp_cap + 256));
+    for (int k = 0; k < ctx->n_slots; k++) MSD_CUDA_OK(cudaMallocHost((void**)&ctx->stage[k].h_bounce, ctx->comp_cap + 256));
     return 0;
 }
 
@@ -454,10 +455,16 @@ int msd_create(int device, msd_ctx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return ctx_fail(nullptr, MSD_ENODEV, "cudaSetDevice failed");
     msd_ctx* ctx = new msd_ctx();
     ctx->device = device;
-    if (cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) != cudaSuccess) {
+    { const uint64_t ns = env_u64("MSD_SLOTS", 4); ctx->n_slots = ns >= 8 ? 8 : ns >= 4 ? 4 : 2; }
+    // MSD_PRIO=1: framing / records / scans (short kernels that release a chunk slot) are scheduled ahead of the persistent
+    // inflate CTAs whenever an SM has room, instead of waiting behind them
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const int prio_compute = env_u64("MSD_PRIO", 0) ? prio_hi : prio_lo;
+    if (cudaStreamCreateWithPriority(&ctx->s_compute, cudaStreamNonBlocking, prio_compute) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cudaStreamCreate failed");
     }
-    for (int k = 0; k < kSlots; k++) if (cudaStreamCreateWithFlags(&ctx->s_inflate[k], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cudaStreamCreate failed"); }
+    for (int k = 0; k < ctx->n_slots; k++) if (cudaStreamCreateWithPriority(&ctx->s_inflate[k], cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cudaStreamCreate failed"); }
     cudaFuncSetAttribute(huffman_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecSmem);
     cudaFuncSetAttribute(huffman_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(bgzf_crc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCrcSmem);
@@ -475,7 +482,7 @@ void msd_destroy(msd_ctx* ctx) {
     release_input(ctx);
     dev_free(&ctx->d_rg); dev_free(&ctx->d_arena); dev_free(&ctx->d_depth_off); dev_free(&ctx->d_tlen); dev_free(&ctx->d_nprefilter); dev_free(&ctx->d_range_lo); dev_free(&ctx->d_range_hi); dev_free(&ctx->d_max_end); dev_free(&ctx->d_n_beyond);
     free_chunk_buffers(ctx);
-    for (int k = 0; k < kSlots; k++) if (ctx->s_inflate[k]) cudaStreamDestroy(ctx->s_inflate[k]);
+    for (int k = 0; k < ctx->n_slots; k++) if (ctx->s_inflate[k]) cudaStreamDestroy(ctx->s_inflate[k]);
     for (int k = 0; k < 2; k++) { dev_free(&ctx->live[k].e); dev_free(&ctx->live[k].arena); dev_free(&ctx->live[k].n); dev_free(&ctx->live[k].arena_used); }
     dev_free(&ctx->d_bstart); dev_free(&ctx->d_land); dev_free(&ctx->d_count); dev_free(&ctx->d_first); dev_free(&ctx->d_cnt);
     dev_free(&ctx->d_recbase); dev_free(&ctx->d_recoff); dev_free(&ctx->d_status); dev_free(&ctx->d_ticket); dev_free(&ctx->d_inflate_err);
@@ -678,7 +685,7 @@ int msd_run(msd_ctx* ctx) {
     {   // the inflate streams must not run ahead of the per-run resets above
         cudaEvent_t ev_init = next_event(ctx);
         MSD_CUDA_OK(cudaEventRecord(ev_init, sc));
-        for (int k = 0; k < kSlots; k++) MSD_CUDA_OK(cudaStreamWaitEvent(ctx->s_inflate[k], ev_init, 0));
+        for (int k = 0; k < ctx->n_slots; k++) MSD_CUDA_OK(cudaStreamWaitEvent(ctx->s_inflate[k], ev_init, 0));
         MSD_CUDA_OK(cudaStreamWaitEvent(sx, ev_init, 0));
     }
     ContigTable ct{ctx->d_depth_off, ctx->d_tlen, ctx->d_range_lo, ctx->d_range_hi, ctx->any_ranged ? ctx->d_max_end : nullptr, ctx->d_n_beyond};
@@ -703,7 +710,7 @@ int msd_run(msd_ctx* ctx) {
         bool first_of_span = true, span_done = false;
         while (!span_done) {
             // ---- plan one chunk (host: BSIZE chase) -------------------------------------------------------
-            const int k = (int)(chunk_idx % kSlots), kd = (int)(chunk_idx % kDescSets);
+            const int k = (int)(chunk_idx % ctx->n_slots), kd = (int)(chunk_idx % kDescSets);
             StageSet& st = ctx->stage[kd];
             if (st.used) MSD_CUDA_OK(cudaEventSynchronize(st.free_ev));
             uint32_t nb = 0; uint64_t comp_bytes = 0, infl = 0; const uint64_t chunk_src = pos; uint32_t total = 0; bool truncated_last = false;
@@ -815,7 +822,7 @@ int msd_run(msd_ctx* ctx) {
             }
             MSD_CUDA_OK(cudaEventRecord(e3, sc));
             // unfinished tail -> front of the other inflated buffer
-            carry_copy_kernel<<<64, 256, 0, sc>>>(infl_buf, ctx->d_infl[(k + 1) % kSlots], ctx->d_cs, base, ctx->carry_cap, &ctx->d_rc->error);
+            carry_copy_kernel<<<64, 256, 0, sc>>>(infl_buf, ctx->d_infl[(k + 1) % ctx->n_slots], ctx->d_cs, base, ctx->carry_cap, &ctx->d_rc->error);
             ctx->info.n_launches++;
             MSD_CUDA_OK(cudaEventRecord(ctx->desc_free[kd], sc));  // d_desc[kd], d_rel[kd] may be overwritten from here on (d_comp[k]: after the decode kernel)
             MSD_CUDA_OK(cudaEventRecord(ctx->infl_free[k], sc));   // ... and so may d_infl[k]
@@ -828,7 +835,7 @@ int msd_run(msd_ctx* ctx) {
     }
     MSD_CUDA_OK(cudaEventRecord(ev_chunks_end, sc));
     MSD_CUDA_OK(cudaStreamSynchronize(sc));
-    for (int k = 0; k < kSlots; k++) MSD_CUDA_OK(cudaStreamSynchronize(ctx->s_inflate[k]));   // the CRC kernels run beside framing and records
+    for (int k = 0; k < ctx->n_slots; k++) MSD_CUDA_OK(cudaStreamSynchronize(ctx->s_inflate[k]));   // the CRC kernels run beside framing and records
     // ---- errors raised by the kernels --------------------------------------------------------------------------
     uint32_t inflate_err = 0; ChunkState cs_h; RunCounters rc_h;
     MSD_CUDA_OK(cudaMemcpy(&inflate_err, ctx->d_inflate_err, 4, cudaMemcpyDeviceToHost));

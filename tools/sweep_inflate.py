@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Sweep the inflate pipeline's knobs on one GPU in one process (resident input, device-timed msd_run only):
 chunk size (blocks per launch), decode warps per SM, resolve CTAs per SM, CRC on/off.  Prints one line per setting.
-usage: python tools/sweep_inflate.py [genome_fraction] [trace]"""
+usage: python tools/sweep_inflate.py [genome_fraction] [knobs|pipe] [resident|e2e  (trace one run)]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -28,10 +28,12 @@ def timed(ctx, steps=4, warm=2):
     return ctx.elapsed_ms(0, 1) / steps, sum(i.ms_inflate_span for i in infos) / steps
 
 
-def with_ctx(env, fn):
+def with_ctx(env, fn, resident=True):
     for k, v in env.items():
         os.environ[k] = str(v)
-    ctx = m.Context(0); ctx.open_mem(host, hdr); ctx.set_filters(mode=m.MODE_FAST); ctx.prefetch_windows(500); ctx.stage()
+    ctx = m.Context(0); ctx.open_mem(host, hdr); ctx.set_filters(mode=m.MODE_FAST); ctx.prefetch_windows(500)
+    if resident:
+        ctx.stage()
     try:
         return fn(ctx)
     finally:
@@ -49,11 +51,33 @@ def sweep(ctx, label):
     os.environ.pop("MSD_DEC_CTAS", None); os.environ.pop("MSD_RESOLVE_CTAS", None)
 
 
-for blocks in (24000, 12000, 16000, 32000, 44000):
-    with_ctx({"MSD_CHUNK_BLOCKS": blocks, "MSD_CHUNK_INFL_MB": 3200, "MSD_CHUNK_COMP_MB": 1200}, lambda c: sweep(c, f"chunk {blocks}") if blocks == 24000 else print(f"chunk {blocks}: %.2f ms/step span %.2f" % timed(c), flush=True))
-with_ctx({"MSD_NO_CRC": 1}, lambda c: print("no crc: %.2f ms/step span %.2f" % timed(c), flush=True))
-if len(sys.argv) > 2:
-    def tr(c):
-        timed(c, 1, 2)
-        os.environ["MSD_TRACE"] = "1"; c.run(); os.environ.pop("MSD_TRACE")
-    with_ctx({}, tr)
+mode = sys.argv[2] if len(sys.argv) > 2 else "knobs"
+if mode == "knobs":
+    for blocks in (24000, 12000, 16000, 32000, 44000):
+        with_ctx({"MSD_CHUNK_BLOCKS": blocks, "MSD_CHUNK_INFL_MB": 3200, "MSD_CHUNK_COMP_MB": 1200}, lambda c: sweep(c, f"chunk {blocks}") if blocks == 24000 else print(f"chunk {blocks}: %.2f ms/step span %.2f" % timed(c), flush=True))
+    with_ctx({"MSD_NO_CRC": 1}, lambda c: print("no crc: %.2f ms/step span %.2f" % timed(c), flush=True))
+else:   # "pipe": chunk slots x stream priority x chunk plan, input resident in HBM and crossing PCIe
+    def show(label, resident):
+        def f(c):
+            ms, span = timed(c)
+            print(f"{label} {'resident' if resident else 'e2e     '}: {ms:7.2f} ms/step  inflate span {span:7.2f}  {n_reads / ms / 1e3:7.1f} M reads/s", flush=True)
+        return f
+    for slots in (4, 8):
+        for prio in (0, 1):
+            for extra in ({}, {"MSD_CHUNK_BLOCKS": 32000, "MSD_CHUNK_INFL_MB": 2200, "MSD_CHUNK_COMP_MB": 800}):
+                env = {"MSD_SLOTS": slots, "MSD_PRIO": prio, **extra}
+                label = f"slots {slots} prio {prio} blocks {extra.get('MSD_CHUNK_BLOCKS', 24000)}"
+                with_ctx(env, show(label, True), True)
+                with_ctx(env, show(label, False), False)
+    for r1 in (12000, 24000):
+        env = {"MSD_SLOTS": 8, "MSD_PRIO": 1, "MSD_COPY_BLOCKS": r1}
+        with_ctx(env, show(f"slots 8 prio 1 copy_blocks {r1}", False), False)
+
+
+def tr(c):
+    timed(c, 1, 2)
+    os.environ["MSD_TRACE"] = "1"; c.run(); os.environ.pop("MSD_TRACE")
+
+
+if len(sys.argv) > 3:
+    with_ctx({"MSD_SLOTS": 8, "MSD_PRIO": 1} if mode == "pipe" else {}, tr, resident=sys.argv[3] == "resident")
