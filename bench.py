@@ -130,7 +130,7 @@ def run_reference(args):
     ncores = os.cpu_count() or 1
     threads = max(0, min(ncores - 1, 64))
     # same workload as our arm at this N (weak scaling: genome_fraction x N), bounded so that W+K steps end in minutes
-    frac = args.cpu_fraction or min(args.genome_fraction * max(args.gpus, 1), 0.06)
+    frac = args.cpu_fraction or min(args.genome_fraction * max(args.gpus, 1), 0.06)   # N = 1: the same BAM as our arm
     bam, n_reads, n_bytes = make_bam(args.config, frac, args.seed, ncores)
     outp = data_dir() / "ref_out"
     cmd = [str(ROOT / "oracle" / "mosdepth_oracle"), "-t", str(threads), "-n", "-x", "--by", "500", str(outp), str(bam)]
@@ -161,7 +161,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3")
-    ap.add_argument("--genome-fraction", type=float, default=float(os.environ.get("MSD_BENCH_FRACTION", "0.03")))
+    ap.add_argument("--genome-fraction", type=float, default=float(os.environ.get("MSD_BENCH_FRACTION", "0.06")))
     ap.add_argument("--cpu-fraction", type=float, default=0.0, help="genome fraction for the CPU arm (default: same BAM)")
     ap.add_argument("--seed", type=int, default=20261022)
     ap.add_argument("--window", type=int, default=500)

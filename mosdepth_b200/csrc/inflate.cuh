@@ -210,7 +210,13 @@ enum DecPhase : int { kPhNeed = 0, kPhHeader = 1, kPhBuild = 2, kPhSym = 3, kPhF
 
 // K1a.  comp: compressed chunk buffer (4-byte aligned base); out: inflated chunk buffer.  Literals go to out, matches
 // to tokens[b * kTokenCap ..]; n_tokens[b] and status[b] are written for every block.
-__global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm)
+// The second launch bound only caps the registers: shared memory allows 9 decoder warps per SM whatever it says, and what
+// the decoder does not take of the register file is what lets resolve CTAs share its SM (MSD_DEC_MINBLOCKS 9 / 16 / 20 ->
+// 156 / 122 / 96 registers, no spills worth the name; A/B in profiles/README.md, r1n).
+#ifndef MSD_DEC_MINBLOCKS
+#define MSD_DEC_MINBLOCKS 9
+#endif
+__global__ void __launch_bounds__(kDecThreads, MSD_DEC_MINBLOCKS)
 huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, int n_blocks,
                       uint32_t* __restrict__ ticket, uint32_t* __restrict__ tokens, uint32_t* __restrict__ n_tokens,
                       uint32_t* __restrict__ status_out, uint32_t* __restrict__ error_count, uint32_t* __restrict__ crc_expected) {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Sweep the inflate pipeline's knobs on one GPU in one process (resident input, device-timed msd_run only):
 chunk size (blocks per launch), decode warps per SM, resolve CTAs per SM, CRC on/off.  Prints one line per setting.
-usage: python tools/sweep_inflate.py [genome_fraction] [knobs|pipe] [resident|e2e  (trace one run)]"""
+usage: python tools/sweep_inflate.py [genome_fraction] [knobs|pipe|repeat|one] [resident|e2e  (trace one run)]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -56,7 +56,7 @@ if mode == "knobs":
     for blocks in (24000, 12000, 16000, 32000, 44000):
         with_ctx({"MSD_CHUNK_BLOCKS": blocks, "MSD_CHUNK_INFL_MB": 3200, "MSD_CHUNK_COMP_MB": 1200}, lambda c: sweep(c, f"chunk {blocks}") if blocks == 24000 else print(f"chunk {blocks}: %.2f ms/step span %.2f" % timed(c), flush=True))
     with_ctx({"MSD_NO_CRC": 1}, lambda c: print("no crc: %.2f ms/step span %.2f" % timed(c), flush=True))
-else:   # "pipe": chunk slots x stream priority x chunk plan, input resident in HBM and crossing PCIe
+elif mode == "pipe":   # chunk slots x stream priority x chunk plan, input resident in HBM and crossing PCIe
     def show(label, resident):
         def f(c):
             ms, span = timed(c)
@@ -72,6 +72,27 @@ else:   # "pipe": chunk slots x stream priority x chunk plan, input resident in 
     for r1 in (12000, 24000):
         env = {"MSD_SLOTS": 8, "MSD_PRIO": 1, "MSD_COPY_BLOCKS": r1}
         with_ctx(env, show(f"slots 8 prio 1 copy_blocks {r1}", False), False)
+
+
+if mode == "repeat":    # the candidates for the defaults, interleaved three times (run-to-run noise is a few per cent)
+    cands = [(4, 0, 24000), (4, 1, 24000), (8, 1, 24000), (4, 1, 32000), (8, 1, 32000), (8, 1, 44000)]
+    for rep in range(3):
+        for slots, prio, blocks in cands:
+            env = {"MSD_SLOTS": slots, "MSD_PRIO": prio, "MSD_CHUNK_BLOCKS": blocks, "MSD_CHUNK_INFL_MB": 3000, "MSD_CHUNK_COMP_MB": 1100}
+            def f(c, resident):
+                ms, span = timed(c, 6, 2)
+                print(f"rep {rep} slots {slots} prio {prio} blocks {blocks} {'resident' if resident else 'e2e     '}: {ms:7.2f} ms/step  span {span:7.2f}  {n_reads / ms / 1e3:7.1f} M reads/s", flush=True)
+            with_ctx(env, lambda c: f(c, True), True)
+            with_ctx(env, lambda c: f(c, False), False)
+
+
+if mode == "one":       # the default configuration, three times (A/B of library builds)
+    for rep in range(3):
+        for resident in (True, False):
+            def f(c):
+                ms, span = timed(c, 6, 2)
+                print(f"rep {rep} {'resident' if resident else 'e2e     '}: {ms:7.2f} ms/step  span {span:7.2f}  {n_reads / ms / 1e3:7.1f} M reads/s", flush=True)
+            with_ctx({}, f, resident)
 
 
 def tr(c):
