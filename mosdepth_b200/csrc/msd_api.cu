@@ -700,6 +700,7 @@ int msd_run(msd_ctx* ctx) {
     // when the bytes still cross PCIe: a small first chunk (the pipeline starts after ~2 ms of copy), then chunks of
     // MSD_COPY_BLOCKS so that the serial tail behind the last byte is one modest chunk
     const uint32_t ramp0 = (uint32_t)env_u64("MSD_RAMP0_BLOCKS", 6000), copy_blocks = (uint32_t)env_u64("MSD_COPY_BLOCKS", 16000);
+    const bool ramp_double = env_u64("MSD_RAMP_DOUBLE", 0) != 0;   // chunk i of a copied input holds ramp0 << i blocks until copy_blocks is reached
     const uint8_t* F = ctx->bytes; const uint64_t N = ctx->n_bytes;
 
     for (const Span& sp : spans) {
@@ -717,7 +718,7 @@ int msd_run(msd_ctx* ctx) {
             // when the compressed bytes still have to cross PCIe, the first chunks are small so that the pipeline
             // (copy k+1 | inflate k) starts after a few milliseconds instead of after a full-size copy
             const bool will_copy = !(ctx->d_staged && pos >= ctx->staged_beg && pos < ctx->staged_end);
-            const uint32_t blk_limit = !will_copy ? ctx->max_blocks : std::min<uint32_t>(ctx->max_blocks, chunk_idx == 0 ? ramp0 : copy_blocks);   // (a small first chunk for resident input was tried: 5 chunks on 4 slots, 43.3 vs 39.2 ms)
+            const uint32_t blk_limit = !will_copy ? ctx->max_blocks : std::min<uint32_t>(ctx->max_blocks, chunk_idx == 0 ? ramp0 : ramp_double ? std::min<uint32_t>(copy_blocks, ramp0 << std::min<uint64_t>(chunk_idx, 8)) : copy_blocks);   // (a small first chunk for resident input was tried: 5 chunks on 4 slots, 43.3 vs 39.2 ms)
             while (nb < blk_limit) {
                 if (pos >= N || pos > end_c || (pos == end_c && end_u == 0)) { span_done = true; break; }
                 uint32_t xlen = 0, isize = 0;

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Sweep the inflate pipeline's knobs on one GPU in one process (resident input, device-timed msd_run only):
 chunk size (blocks per launch), decode warps per SM, resolve CTAs per SM, CRC on/off.  Prints one line per setting.
-usage: python tools/sweep_inflate.py [genome_fraction] [knobs|pipe|repeat|one] [resident|e2e  (trace one run)]"""
+usage: python tools/sweep_inflate.py [genome_fraction] [knobs|pipe|repeat|one|ramp] [resident|e2e  (trace one run)]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -93,6 +93,15 @@ if mode == "one":       # the default configuration, three times (A/B of library
                 ms, span = timed(c, 6, 2)
                 print(f"rep {rep} {'resident' if resident else 'e2e     '}: {ms:7.2f} ms/step  span {span:7.2f}  {n_reads / ms / 1e3:7.1f} M reads/s", flush=True)
             with_ctx({}, f, resident)
+
+
+if mode == "ramp":      # how the first chunks of a copied input are sized (end-to-end only)
+    for rep in range(2):
+        for dbl, r0, cb in ((0, 6000, 16000), (1, 6000, 16000), (1, 3000, 16000), (1, 1500, 16000), (1, 3000, 24000), (0, 3000, 16000), (1, 3000, 12000)):
+            def f(c):
+                ms, span = timed(c, 6, 2)
+                print(f"rep {rep} double {dbl} ramp0 {r0} copy_blocks {cb} e2e: {ms:7.2f} ms/step  span {span:7.2f}  {n_reads / ms / 1e3:7.1f} M reads/s", flush=True)
+            with_ctx({"MSD_RAMP_DOUBLE": dbl, "MSD_RAMP0_BLOCKS": r0, "MSD_COPY_BLOCKS": cb}, f, False)
 
 
 def tr(c):
