@@ -400,6 +400,21 @@ def main():
                                       "zero": sum(i.ms_zero for i in infos_res) / len(infos_res), "run_total": sum(i.ms_total for i in infos_res) / len(infos_res)},
                 "note": "inflate is bound by the serial Huffman chains (latency / issue), not by HBM; compressed GB/s and inflated GB/s are quoted against the HBM peak as north_star asks"}
 
+    # K1c alone, timed live: the one kernel of K1 that is HBM bound (it reads the inflated bytes once: algorithmic bytes = U)
+    try:
+        if rank != 0:
+            raise RuntimeError("rank 0 only")
+        blk = 65280
+        sample = np.random.default_rng(1).integers(0, 256, size=blk * 16384, dtype=np.uint8)      # 1.07 GB: far larger than L2
+        _crcs, crc_ms = ctx.debug_crc32(sample, blk, 0, reps=10)
+        roofline["k1c_crc"] = {"kernel": "bgzf_crc_kernel (K1c), timed alone over %d blocks of %d bytes" % (sample.size // blk, blk), "bound": "hbm",
+                               "achieved": sample.size / 1e9 / (crc_ms / 1e3), "peak": peak, "unit": "GB/s", "frac": sample.size / 1e9 / (crc_ms / 1e3) / peak,
+                               "ms_per_launch": crc_ms, "algorithmic_bytes_per_launch": int(sample.size),
+                               "traffic": 5.504065e9 / 85062 * (sample.size // blk), "traffic_source": "ncu --set full, profiles/r1m_crc_full_summary.txt, per block x blocks"}
+        del sample
+    except Exception as e:      # never let the side measurement take the bench line down
+        roofline["k1c_crc"] = {"error": str(e)}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = max(0, min(ncores - 1, 64))

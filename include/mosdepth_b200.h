@@ -199,6 +199,12 @@ int64_t msd_debug_inflate(msd_ctx *ctx, const void *bgzf_bytes, uint64_t n_bytes
 int msd_debug_depth(msd_ctx *ctx, int tid, int32_t *out, int64_t out_cap);
 /* In-place inclusive int32 prefix sum of a host array on the device (the scan kernel alone). */
 int msd_debug_cumsum(msd_ctx *ctx, int32_t *inout, int64_t n);
+/* K1c alone: the host bytes are placed `first_offset` bytes past a 256-byte boundary in device memory and cut into blocks of
+ * `block_bytes` (the last one shorter; block_bytes <= 65536); crc_out[i] receives the CRC-32 of block i (RFC 1952, what the
+ * gzip trailer holds).  The kernel is launched 1 + reps times; *ms_per_launch (may be NULL) is the average of the last `reps`
+ * launches, timed with CUDA events on the launching stream.  Returns the number of blocks. */
+int64_t msd_debug_crc32(msd_ctx *ctx, const void *bytes, uint64_t n_bytes, uint32_t block_bytes, uint32_t first_offset, int reps,
+                        uint32_t *crc_out, double *ms_per_launch);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ EXPORTS = [
     "msd_set_spans", "msd_set_targets", "msd_set_filters", "msd_run", "msd_last_run_info", "msd_contig_records",
     "msd_contig_stats", "msd_n_windows", "msd_prefetch_windows", "msd_windows", "msd_regions", "msd_per_base_runs", "msd_quantized_runs",
     "msd_set_contig_range", "msd_contig_spill", "msd_depth_copy", "msd_depth_add", "msd_contig_finalize",
-    "msd_totals_device", "msd_totals_reset", "msd_mark", "msd_elapsed_ms", "msd_launch_count", "msd_debug_inflate", "msd_debug_depth", "msd_debug_cumsum",
+    "msd_totals_device", "msd_totals_reset", "msd_mark", "msd_elapsed_ms", "msd_launch_count", "msd_debug_inflate", "msd_debug_depth", "msd_debug_cumsum", "msd_debug_crc32",
 ]
 
 
@@ -94,6 +94,7 @@ def load_library():
     lib.msd_debug_inflate.argtypes = [p, p, u64, p, u64]; lib.msd_debug_inflate.restype = i64
     lib.msd_debug_depth.argtypes = [p, i32, p, i64]
     lib.msd_debug_cumsum.argtypes = [p, p, i64]
+    lib.msd_debug_crc32.argtypes = [p, p, u64, u32, u32, i32, p, C.POINTER(C.c_double)]; lib.msd_debug_crc32.restype = i64
     _lib = lib
     return lib
 
@@ -287,6 +288,15 @@ class Context:
         n = self.lib.msd_debug_inflate(self.h, _ptr(src), src.size, _ptr(out), out_size)
         self._check(n)
         return out[:n].tobytes()
+
+    def debug_crc32(self, data, block_bytes=65280, first_offset=0, reps=0):
+        """K1c alone: CRC-32 of every `block_bytes` piece of `data` (bytes or uint8 array); returns (crcs, ms per launch)."""
+        src = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, dtype=np.uint8)
+        nb = (src.size + block_bytes - 1) // block_bytes
+        out = np.zeros(max(nb, 1), dtype=np.uint32); ms = C.c_double()
+        got = self.lib.msd_debug_crc32(self.h, _ptr(src), src.size, block_bytes, first_offset, reps, _ptr(out), C.byref(ms))
+        self._check(got)
+        return out[:got], ms.value
 
     def debug_depth(self, tid):
         out = np.zeros(int(self.tlen[tid]) + 1, dtype=np.int32)

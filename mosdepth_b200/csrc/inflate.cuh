@@ -510,7 +510,8 @@ inline cudaError_t crc_upload_tables() {
 
 __global__ void __launch_bounds__(kCrcThreads, 1)
 bgzf_crc_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, int n_blocks, uint32_t* __restrict__ ticket,
-                const uint32_t* __restrict__ crc_expected, uint32_t* __restrict__ status, uint32_t* __restrict__ error_count) {
+                const uint32_t* __restrict__ crc_expected, uint32_t* __restrict__ status, uint32_t* __restrict__ error_count,
+                uint32_t* __restrict__ crc_out /* test hook: the computed CRCs (null in msd_run) */) {
     extern __shared__ __align__(16) uint32_t crc_sm[];
     uint32_t* const U = crc_sm;
     uint32_t* const T0 = U + kCrcUWords;
@@ -569,8 +570,17 @@ bgzf_crc_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ b
         uint32_t v = crc_multmodp(xl, crc_lane_fold(d, t, t0));
         v = __reduce_xor_sync(full, v);
         const uint32_t crc = crc_finish(v, XA[tail], XA[n % kCrcRow], XBI[n / kCrcRow]);
-        if (lane == 0 && crc != crc_expected[b]) { status[b] = kBadCrc; atomicAdd(error_count, 1u); }
+        if (lane == 0) {
+            if (crc_out) crc_out[b] = crc;
+            if (crc != crc_expected[b]) { status[b] = kBadCrc; atomicAdd(error_count, 1u); }
+        }
     }
+}
+
+inline void launch_crc(cudaStream_t s, const uint8_t* d_out, const BlockDesc* d_desc, int nb, uint32_t* ticket, const uint32_t* d_crc,
+                       uint32_t* d_status, uint32_t* d_error_count, uint32_t* d_crc_out = nullptr) {
+    const int cw = (nb + kCrcThreads / 32 - 1) / (kCrcThreads / 32);
+    bgzf_crc_kernel<<<cw < kSMs ? cw : kSMs, kCrcThreads, kCrcSmem, s>>>(d_out, d_desc, nb, ticket, d_crc, d_status, d_error_count, d_crc_out);
 }
 
 // K1 = K1a + K1b (+ K1c) on one stream.  tickets: three zeroed words (K1a, K1b, K1c).  comp_read (may be null) is recorded
@@ -597,10 +607,7 @@ inline void launch_inflate(cudaStream_t s, const uint8_t* d_comp, uint8_t* d_out
     const int rctas = want < res_cap ? want : res_cap;
     lz77_resolve_kernel<<<rctas, kResolveWarps * 32, 0, s>>>(d_out, d_desc, nb, tickets + 1, d_tokens, d_ntok);
     if (resolved) cudaEventRecord(resolved, s);      // the inflated bytes are final: framing need not wait for the CRC check
-    if (check_crc) {
-        const int cw = (nb + kCrcThreads / 32 - 1) / (kCrcThreads / 32);
-        bgzf_crc_kernel<<<cw < kSMs ? cw : kSMs, kCrcThreads, kCrcSmem, s>>>(d_out, d_desc, nb, tickets + 2, d_crc, d_status, d_error_count);
-    }
+    if (check_crc) launch_crc(s, d_out, d_desc, nb, tickets + 2, d_crc, d_status, d_error_count);
 }
 
 }  // namespace msd

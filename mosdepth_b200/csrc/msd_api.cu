@@ -1280,6 +1280,52 @@ int64_t msd_debug_inflate(msd_ctx* ctx, const void* bgzf_bytes, uint64_t n_bytes
     return (int64_t)infl;
 }
 
+int64_t msd_debug_crc32(msd_ctx* ctx, const void* bytes, uint64_t n_bytes, uint32_t block_bytes, uint32_t first_offset, int reps,
+                        uint32_t* crc_out, double* ms_per_launch) {
+    if (!ctx || !bytes || !crc_out || n_bytes == 0 || block_bytes == 0 || block_bytes > 65536 || first_offset > 255 || reps < 0)
+        return ctx_fail(ctx, MSD_EINVAL, "msd_debug_crc32: bad arguments");
+    cudaSetDevice(ctx->device);
+    const uint64_t nb64 = (n_bytes + block_bytes - 1) / block_bytes;
+    if (nb64 > (1u << 30)) return ctx_fail(ctx, MSD_EINVAL, "msd_debug_crc32: too many blocks");
+    const int nb = (int)nb64;
+    std::vector<BlockDesc> desc((size_t)nb);
+    for (int i = 0; i < nb; i++) {
+        desc[i].src = 0; desc[i].clen = 0; desc[i].dst = first_offset + (uint64_t)i * block_bytes;
+        desc[i].isize = (uint32_t)std::min<uint64_t>(block_bytes, n_bytes - (uint64_t)i * block_bytes);
+    }
+    uint8_t* d_o = nullptr; BlockDesc* d_d = nullptr; uint32_t *d_s = nullptr, *d_t = nullptr, *d_exp = nullptr, *d_got = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, &d_o, n_bytes + 512)) || (rc = dev_alloc(ctx, &d_d, (uint64_t)nb)) || (rc = dev_alloc(ctx, &d_s, (uint64_t)nb)) ||
+        (rc = dev_alloc(ctx, &d_t, 4)) || (rc = dev_alloc(ctx, &d_exp, (uint64_t)nb)) || (rc = dev_alloc(ctx, &d_got, (uint64_t)nb))) {
+        dev_free(&d_o); dev_free(&d_d); dev_free(&d_s); dev_free(&d_t); dev_free(&d_exp); dev_free(&d_got); return rc;
+    }
+    cudaStream_t sc = ctx->s_compute;
+    cudaEvent_t e0 = nullptr, e1 = nullptr; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaMemsetAsync(d_o, 0, n_bytes + 512, sc);
+    cudaMemcpyAsync(d_o + first_offset, bytes, n_bytes, cudaMemcpyHostToDevice, sc);
+    cudaMemcpyAsync(d_d, desc.data(), sizeof(BlockDesc) * (size_t)nb, cudaMemcpyHostToDevice, sc);
+    cudaMemsetAsync(d_s, 0, 4ull * nb, sc); cudaMemsetAsync(d_exp, 0, 4ull * nb, sc);
+    for (int r = 0; r <= reps; r++) {
+        cudaMemsetAsync(d_t, 0, 16, sc);
+        if (r == 1) cudaEventRecord(e0, sc);
+        launch_crc(sc, d_o, d_d, nb, d_t, d_exp, d_s, d_t + 1, d_got);
+        if (r == 0) {   // the first launch marks every block whose CRC is not 0: from here on the expected values are the computed ones
+            cudaMemcpyAsync(d_exp, d_got, 4ull * nb, cudaMemcpyDeviceToDevice, sc);
+            cudaMemsetAsync(d_s, 0, 4ull * nb, sc);
+        }
+    }
+    cudaEventRecord(e1, sc);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(crc_out, d_got, 4ull * nb, cudaMemcpyDeviceToHost, sc);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sc);
+    float ms = 0; if (e == cudaSuccess && reps > 0) cudaEventElapsedTime(&ms, e0, e1);
+    if (ms_per_launch) *ms_per_launch = reps > 0 ? (double)ms / reps : 0.0;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    dev_free(&d_o); dev_free(&d_d); dev_free(&d_s); dev_free(&d_t); dev_free(&d_exp); dev_free(&d_got);
+    if (e != cudaSuccess) return ctx_fail(ctx, MSD_ECUDA, "msd_debug_crc32: %s", cudaGetErrorString(e));
+    return nb;
+}
+
 int msd_debug_depth(msd_ctx* ctx, int tid, int32_t* out, int64_t out_cap) {
     if (!ctx || !ctx->ran || tid < 0 || tid >= ctx->n_targets || !ctx->want[tid] || !out) return ctx_fail(ctx, MSD_EINVAL, "msd_debug_depth: bad arguments");
     cudaSetDevice(ctx->device);

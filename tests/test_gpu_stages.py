@@ -80,6 +80,30 @@ def test_inflate_checks_crc32(ctx):
     assert e.value.code == -14 and "status 10" in str(e.value)
 
 
+@pytest.mark.parametrize("block_bytes", [1, 3, 4, 15, 16, 17, 496, 511, 512, 513, 1023, 4099, 65279, 65280, 65519, 65536])
+def test_crc_kernel_matches_zlib(ctx, block_bytes):
+    """K1c alone (msd_debug_crc32): every block size class around the row / lane / tail boundaries of the row-strided
+    formulation, at several alignments of the first block (the following blocks then take every alignment by themselves)."""
+    rng = np.random.default_rng(block_bytes)
+    n_blocks = 3000 if block_bytes < 600 else 300
+    data = rng.integers(0, 256, size=block_bytes * n_blocks - (block_bytes // 3), dtype=np.uint8)   # last block shorter
+    for first_offset in (0, 1, 7, 13, 16, 31):
+        got, _ = ctx.debug_crc32(data, block_bytes, first_offset)
+        raw = data.tobytes()
+        want = np.array([zlib.crc32(raw[i:i + block_bytes]) for i in range(0, len(raw), block_bytes)], dtype=np.uint32)
+        assert got.size == want.size
+        bad = np.nonzero(got != want)[0]
+        assert bad.size == 0, f"first_offset {first_offset}: block {bad[0]} of {want.size}: {got[bad[0]]:08x} != {want[bad[0]]:08x}"
+
+
+def test_crc_kernel_extremes(ctx):
+    for fill in (0, 255):
+        data = np.full(65536 * 3 + 5, fill, dtype=np.uint8)
+        got, _ = ctx.debug_crc32(data, 65536, 9)
+        raw = data.tobytes()
+        assert [int(x) for x in got] == [zlib.crc32(raw[i:i + 65536]) for i in range(0, len(raw), 65536)]
+
+
 def test_inflate_rejects_corrupt_block(ctx):
     import mosdepth_b200 as m
     p = bytes(range(256)) * 40
