@@ -107,17 +107,7 @@ struct BitReader {
     MSD_D uint32_t take(int n) { const uint32_t v = (uint32_t)bb & ((1u << n) - 1u); drop(n); return v; }
 };
 
-// code length of the canonical code that the 15-bit MSB-first window c starts with, minus 1 (15 = no such code):
-// the number of per-length limits that are <= c.  The 15 limits (each <= 0x8000) are packed two per register;
-// (0x8000 + c) - limit is computed for both halves by ONE subtraction (no borrow can cross: each half stays >= 0) and
-// its bit 15 says c >= limit.  8 subtractions, 8 shift+mask-or's into two accumulators, one popc: short chains.
-MSD_D uint32_t canon_len_minus1(uint32_t c, const uint32_t (&limp)[8]) {
-    const uint32_t cc = c * 0x10001u + 0x80008000u;
-    uint32_t t[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) t[j] = ((cc - limp[j]) >> j) & (0x80008000u >> j);
-    return (uint32_t)__popc(((t[0] | t[1] | t[2]) | (t[3] | t[4] | t[5])) | (t[6] | t[7]));
-}
+// canon_len_minus1(): inflate_core.cuh (shared with the host replay).
 
 // Build the tables of lane `X` with all 32 lanes.  XM: X's region (same pointer in every lane).  Code lengths are
 // read from the region first (they alias the tables).  `keep` is true in lane X only: it keeps the per-length limits

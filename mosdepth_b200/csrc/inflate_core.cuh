@@ -88,6 +88,54 @@ enum Status : uint32_t {
     kOverflow = 6, kShort = 7, kOversubscribed = 8, kTruncated = 9, kBadCrc = 10
 };
 
+// code length of the canonical code that the 15-bit MSB-first window c starts with, minus 1 (15 = no such code):
+// the number of per-length limits that are <= c.  The 15 limits (each <= 0x8000; the 16th half-word is 0x8000, never
+// reached) are packed two per register; (0x8000 + c) - limit is computed for both halves by ONE subtraction (no borrow can
+// cross: each half stays >= 0) and its bit 15 says c >= limit.
+// r1a-r1n gathered the 16 flags with a shift + mask-or per register and one popc (24 instructions, an 8-deep dependent
+// chain).  r1o: PRMT in sign-replicate mode turns the four flags of a register pair into four bytes 0xFF / 0x00 and DP4A
+// against -1 counts them: 8 subtractions + 4 PRMT + 4 DP4A in two chains + 1 add = 17 instructions, 4 deep.
+#ifndef MSD_CANON_DP4A
+#define MSD_CANON_DP4A 1
+#endif
+MSD_HD uint32_t prmt_sign_bytes_1357(uint32_t a, uint32_t b) {     // bytes 1, 3 of a and 1, 3 of b, each replaced by 8 copies of its msb
+#if defined(__CUDA_ARCH__)
+    uint32_t r; asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(r) : "r"(a), "r"(b)); return r;
+#else
+    return ((a >> 15) & 1u ? 0xffu : 0u) | ((a >> 31) & 1u ? 0xff00u : 0u) | ((b >> 15) & 1u ? 0xff0000u : 0u) | ((b >> 31) & 1u ? 0xff000000u : 0u);
+#endif
+}
+MSD_HD int dp4a_minus1(uint32_t r, int acc) {                       // acc + sum over the four signed bytes of r of (byte * -1)
+#if defined(__CUDA_ARCH__)
+    return __dp4a((int)r, -1, acc);
+#else
+    for (int k = 0; k < 4; k++) acc -= (int)(int8_t)(r >> (8 * k));
+    return acc;
+#endif
+}
+MSD_HD uint32_t canon_len_minus1(uint32_t c, const uint32_t (&limp)[8]) {
+    const uint32_t cc = c * 0x10001u + 0x80008000u;
+#if MSD_CANON_DP4A
+    int a0 = dp4a_minus1(prmt_sign_bytes_1357(cc - limp[0], cc - limp[1]), 0);
+    int a1 = dp4a_minus1(prmt_sign_bytes_1357(cc - limp[2], cc - limp[3]), 0);
+    a0 = dp4a_minus1(prmt_sign_bytes_1357(cc - limp[4], cc - limp[5]), a0);
+    a1 = dp4a_minus1(prmt_sign_bytes_1357(cc - limp[6], cc - limp[7]), a1);
+    return (uint32_t)(a0 + a1);
+#else
+    uint32_t t[8];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 8; j++) t[j] = ((cc - limp[j]) >> j) & (0x80008000u >> j);
+    const uint32_t m = ((t[0] | t[1] | t[2]) | (t[3] | t[4] | t[5])) | (t[6] | t[7]);
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(m);
+#else
+    return (uint32_t)__builtin_popcount(m);
+#endif
+#endif
+}
+
 // ---- CRC-32 of the gzip trailer (RFC 1952; reflected polynomial 0xEDB88320), computed in parallel ---------------------
 // Polynomials over GF(2) modulo the CRC polynomial in the reflected representation zlib uses: bit 31 is x^0.
 constexpr uint32_t kCrcPoly = 0xedb88320u;

@@ -46,7 +46,14 @@ static uint32_t build(const uint8_t* lens, int hlit, int hdist, Tables& T) {
     return status;
 }
 
-static uint32_t len_minus1(uint32_t c, const uint32_t* lim) { uint32_t n = 0; for (int k = 0; k < 15; k++) n += c >= lim[k]; return n; }
+// the definition (number of limits <= c) checked against the kernels' packed evaluation (canon_len_minus1, inflate_core.cuh)
+static uint32_t len_minus1(uint32_t c, const uint32_t* lim) {
+    uint32_t n = 0; for (int k = 0; k < 15; k++) n += c >= lim[k];
+    uint32_t limp[8];
+    for (int j = 0; j < 8; j++) limp[j] = std::min(lim[2 * j], 0x8000u) | ((j == 7 ? 0x8000u : std::min(lim[2 * j + 1], 0x8000u)) << 16);
+    if (canon_len_minus1(c, limp) != n) { fprintf(stderr, "canon_len_minus1 disagrees with the definition (c = %u)\n", c); abort(); }
+    return n;
+}
 
 struct BitReader {
     uint64_t bb = 0; int bc = 0; uint32_t widx = 0, a0 = 0, a1 = 0;
