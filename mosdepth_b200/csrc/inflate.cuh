@@ -105,7 +105,14 @@ struct BitReader {
     MSD_D uint32_t lo() const { return (uint32_t)bb; }
     MSD_D void drop(int n) { bb >>= n; bc -= n; }
     MSD_D uint32_t take(int n) { const uint32_t v = (uint32_t)bb & ((1u << n) - 1u); drop(n); return v; }
+    MSD_D uint32_t bits_to_byte() const { return (uint32_t)bc & 7u; }
+    MSD_D uint32_t byte_pos() const { return widx * 4u - (uint32_t)bc / 8u; }   // byte index in the aligned stream
+    MSD_D uint32_t word_pos() const { return widx; }
 };
+// which reader the decode kernel uses: 0 = the bit buffer above, 1 = BitReader2 (inflate_core.cuh: windows read from the ring)
+#ifndef MSD_BITREADER2
+#define MSD_BITREADER2 0
+#endif
 
 // canon_len_minus1(): inflate_core.cuh (shared with the host replay).
 
@@ -223,7 +230,11 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
     uint32_t* __restrict__ tok = nullptr;   // this block's token list
     uint32_t ntok = 0;
     uint32_t clast = 0, total_words = 0, isize = 0, lead = 0, clen = 0, outp = 0, run_base = 0, err = 0;
+#if MSD_BITREADER2
+    BitReader2<32> br; br.ring.base = ring; br.bitpos = 0; br.cur = 0; br.p0 = br.p1 = br.p2 = br.p3 = 0;
+#else
     BitReader br; br.bb = 0; br.bc = 0; br.widx = 0; br.a0 = 0; br.a1 = 0; br.p0 = br.p1 = br.p2 = br.p3 = 0;
+#endif
     uint32_t llim[8], dlim[8];     // per-length limits of the two canonical codes, packed two per register
 #pragma unroll
     for (int k = 0; k < 8; k++) { llim[k] = 0; dlim[k] = 0; }
@@ -260,15 +271,15 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
         // ---- DEFLATE block headers (lanes in this phase run together) ------------------------------------------------------
         if (phase == kPhHeader) {
             br.refill(chunks, clast, ring);
-            if (br.widx > total_words + 4u) err = kTruncated;
+            if (br.word_pos() > total_words + 4u) err = kTruncated;
             bfinal = (int)br.take(1);
             const int btype = (int)br.take(2);
             if (err) {
             } else if (btype == 0) {
-                br.drop(br.bc & 7);
+                br.drop((int)br.bits_to_byte());
                 br.refill(chunks, clast, ring);
                 const uint32_t len = br.take(16), nlen = br.take(16);
-                const uint32_t sp = br.widx * 4u - (uint32_t)br.bc / 8u;   // byte index in the aligned stream
+                const uint32_t sp = br.byte_pos();                             // byte index in the aligned stream
                 if ((len ^ 0xffffu) != nlen || sp + len > lead + clen) err = kBadStored;
                 else if (outp + len > isize) err = kOverflow;
                 else {
@@ -373,7 +384,9 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
                         else err = kBadSymbol;
                     } else {
                         const uint32_t len = 3u + (e >> 8) + ext;
-                        br.refill(chunks, clast, ring);
+#if !MSD_BITREADER2
+                        br.refill(chunks, clast, ring);        // (BitReader2: the ring already holds the next two chunks)
+#endif
                         lo = br.lo();
                         c = __brev(lo) >> 17;
                         l1 = canon_len_minus1(c, dlim);

@@ -5,6 +5,7 @@
 //
 // Replaces htslib's BGZF inflate [ext] behind `open(bam, threads=)`, mosdepth.nim:888,968.  RFC 1951 throughout.
 #pragma once
+#include <cstring>
 #include "common.cuh"
 
 namespace msd {
@@ -135,6 +136,65 @@ MSD_HD uint32_t canon_len_minus1(uint32_t c, const uint32_t (&limp)[8]) {
 #endif
 #endif
 }
+
+// ---- bit reader, second form (MSD_BITREADER2): no bit buffer.  The state is the bit position; a decode step reads its
+// 32-bit window straight from the lane's 16-word ring (two loads + a funnel shift) and `drop` is one addition.  The first
+// form keeps a 64-bit buffer plus two look-ahead words in registers and merges a word whenever fewer than 33 bits are
+// left: ~28 instructions per refill, two refills per symbol iteration (lit/len and distance), executed by the warp in
+// nearly every iteration because some lane always needs one.  Here the ring is topped up once per iteration at most
+// (maintain(): a compare, and every 16 consumed bytes four stores + the 128-bit load of the chunk three ahead), since an
+// iteration consumes at most 48 bits and the ring always holds the chunk of the current bit and the two after it.
+// The price: the window loads sit on the decode chain (two shared-memory latencies per symbol).
+template <int kStride> struct RingRef {        // word x of the lane at base[(x & 15) * kStride] (kernel: 32, host replay: 1)
+    uint32_t* base;
+    MSD_HD uint32_t ld(uint32_t w) const { return base[(w & 15u) * kStride]; }
+    MSD_HD void st4(uint32_t chunk, uint32_t x, uint32_t y, uint32_t z, uint32_t w) const {
+        uint32_t* r = base + (chunk & 3u) * 4u * kStride;
+        r[0] = x; r[kStride] = y; r[2 * kStride] = z; r[3 * kStride] = w;
+    }
+};
+template <int kStride> struct BitReader2 {
+    uint32_t bitpos;            // next unread bit, counted from the 16-byte boundary at or before the stream's first byte
+    uint32_t cur;               // the ring holds chunks cur, cur + 1, cur + 2 (16 bytes each); bitpos >> 7 is cur or cur + 1
+    uint32_t p0, p1, p2, p3;    // chunk cur + 3, in flight or landed
+    RingRef<kStride> ring;
+    MSD_HD void fetch(const uint4* __restrict__ chunks, uint32_t clast, uint32_t chunk, bool pred) {
+        const uint4* addr = chunks + (chunk < clast ? chunk : clast);
+#if defined(__CUDA_ARCH__)
+        // predicated load whose destinations ARE p0..p3 (a conditional C++ load becomes load-into-temporaries + moves, i.e.
+        // a wait for the L2 latency in the same iteration; profiles/README.md r1i)
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+                     : "+r"(p0), "+r"(p1), "+r"(p2), "+r"(p3) : "l"(addr), "r"((uint32_t)pred));
+#else
+        if (pred) { uint32_t v[4]; memcpy(v, addr, 16); p0 = v[0]; p1 = v[1]; p2 = v[2]; p3 = v[3]; }   // (the replay's base is only 8-byte aligned)
+#endif
+    }
+    MSD_HD void seed(const uint4* __restrict__ chunks, uint32_t clast, uint32_t* /*ring (set once)*/, uint32_t byte_pos) {
+        bitpos = byte_pos * 8u; cur = byte_pos >> 4;
+        for (uint32_t i = 0; i < 3; i++) { fetch(chunks, clast, cur + i, true); ring.st4(cur + i, p0, p1, p2, p3); }
+        fetch(chunks, clast, cur + 3, true);
+    }
+    // call at least once per 128 consumed bits (the kernels: once per symbol iteration, once per header field group)
+    MSD_HD void refill(const uint4* __restrict__ chunks, uint32_t clast, uint32_t* /*ring*/) {
+        const bool moved = (bitpos >> 7) != cur;
+        if (moved) { cur++; ring.st4(cur + 2, p0, p1, p2, p3); }
+        fetch(chunks, clast, cur + 3, moved);
+    }
+    MSD_HD uint32_t lo() const {
+        const uint32_t w = bitpos >> 5, sh = bitpos & 31u;
+        const uint32_t x = ring.ld(w), y = ring.ld(w + 1u);
+#if defined(__CUDA_ARCH__)
+        return __funnelshift_r(x, y, sh);
+#else
+        return sh ? (x >> sh) | (y << (32u - sh)) : x;
+#endif
+    }
+    MSD_HD void drop(int n) { bitpos += (uint32_t)n; }
+    MSD_HD uint32_t take(int n) { const uint32_t v = lo() & ((1u << n) - 1u); drop(n); return v; }
+    MSD_HD uint32_t bits_to_byte() const { return (0u - bitpos) & 7u; }
+    MSD_HD uint32_t byte_pos() const { return bitpos >> 3; }      // byte index in the aligned stream (call on a byte boundary)
+    MSD_HD uint32_t word_pos() const { return bitpos >> 5; }
+};
 
 // ---- CRC-32 of the gzip trailer (RFC 1952; reflected polynomial 0xEDB88320), computed in parallel ---------------------
 // Polynomials over GF(2) modulo the CRC polynomial in the reflected representation zlib uses: bit 31 is x^0.

@@ -55,35 +55,57 @@ static uint32_t len_minus1(uint32_t c, const uint32_t* lim) {
     return n;
 }
 
-struct BitReader {
+struct BitReader {      // the kernel's first reader without its ring (the ring only stages the words)
     uint64_t bb = 0; int bc = 0; uint32_t widx = 0, a0 = 0, a1 = 0;
     const uint32_t* words; uint32_t wlast;
+    BitReader(const uint8_t* comp_aligned, uint32_t total_words) : words(reinterpret_cast<const uint32_t*>(comp_aligned)), wlast(total_words - 1) {}
     void seed(uint32_t byte_pos) { bb = 0; bc = 0; widx = byte_pos >> 2; a0 = words[std::min(widx, wlast)]; a1 = words[std::min(widx + 1, wlast)]; refill(); drop((int)(byte_pos & 3u) * 8); refill(); }
     void refill() { if (bc <= 32) { bb |= (uint64_t)a0 << bc; bc += 32; widx++; a0 = a1; a1 = words[std::min(widx + 1, wlast)]; } }
+    void refill_before_distance() { refill(); }
     uint32_t lo() const { return (uint32_t)bb; }
     void drop(int n) { bb >>= n; bc -= n; }
     uint32_t take(int n) { const uint32_t v = (uint32_t)bb & ((1u << n) - 1u); drop(n); return v; }
+    uint32_t bits_to_byte() const { return (uint32_t)bc & 7u; }
+    uint32_t byte_pos() const { return widx * 4u - (uint32_t)bc / 8u; }
+    uint32_t word_pos() const { return widx; }
+};
+// BitReader2 of inflate_core.cuh (the code the kernel runs with MSD_BITREADER2) over a host ring of 16 words
+struct RingReader {
+    BitReader2<1> r; uint32_t ringbuf[16]; const uint4* chunks; uint32_t clast;
+    RingReader(const uint8_t* comp_aligned, uint32_t total_words) : chunks(reinterpret_cast<const uint4*>(comp_aligned)), clast((total_words * 4u + 15u) / 16u - 1u) {
+        memset(ringbuf, 0xA5, sizeof ringbuf); r.ring.base = ringbuf; r.bitpos = 0; r.cur = 0; r.p0 = r.p1 = r.p2 = r.p3 = 0;
+    }
+    void seed(uint32_t byte_pos) { r.seed(chunks, clast, ringbuf, byte_pos); }
+    void refill() { r.refill(chunks, clast, ringbuf); }
+    void refill_before_distance() {}           // the kernel skips it: the ring holds the next two chunks
+    uint32_t lo() const { return r.lo(); }
+    void drop(int n) { r.drop(n); }
+    uint32_t take(int n) { return r.take(n); }
+    uint32_t bits_to_byte() const { return r.bits_to_byte(); }
+    uint32_t byte_pos() const { return r.byte_pos(); }
+    uint32_t word_pos() const { return r.word_pos(); }
 };
 
 static const uint8_t cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 // K1a for one block: literals into dst, matches into tok.  Returns status.
+template <class Reader>
 static uint32_t decode_block(const uint8_t* comp_aligned, uint32_t lead, uint32_t clen, uint32_t isize, uint8_t* dst, std::vector<uint32_t>& tok) {
-    BitReader br; br.words = reinterpret_cast<const uint32_t*>(comp_aligned);
-    const uint32_t total_words = std::max((lead + clen + 3) / 4, 1u); br.wlast = total_words - 1;
+    const uint32_t total_words = std::max((lead + clen + 3) / 4, 1u);
+    Reader br(comp_aligned, total_words);
     br.seed(lead);
     uint32_t outp = 0, run_base = 0; int bfinal = 0;
     Tables T;
     while (!bfinal) {
         br.refill();
-        if (br.widx > total_words + 4u) return kTruncated;
+        if (br.word_pos() > total_words + 4u) return kTruncated;
         bfinal = (int)br.take(1);
         const int btype = (int)br.take(2);
         uint8_t lens[320]; int hlit = 288, hdist = 30;
         if (btype == 0) {
-            br.drop(br.bc & 7); br.refill();
+            br.drop((int)br.bits_to_byte()); br.refill();
             const uint32_t len = br.take(16), nlen = br.take(16);
-            const uint32_t sp = br.widx * 4u - (uint32_t)br.bc / 8u;
+            const uint32_t sp = br.byte_pos();
             if ((len ^ 0xffffu) != nlen || sp + len > lead + clen) return kBadStored;
             if (outp + len > isize) return kOverflow;
             memcpy(dst + outp, comp_aligned + sp, len);
@@ -147,7 +169,7 @@ static uint32_t decode_block(const uint8_t* comp_aligned, uint32_t lead, uint32_
             if ((e & 0x83u) == kEntNotLen) { if (outp >= isize) return kOverflow; dst[outp++] = (uint8_t)(e >> 8); continue; }
             if (e & kEntNotLen) { if (e == kEntEob) break; return kBadSymbol; }
             const uint32_t len = 3u + (e >> 8) + ext;
-            br.refill();
+            br.refill_before_distance();
             lo = br.lo();
             c = brev32(lo) >> 17;
             l1 = len_minus1(c, T.dlim);
@@ -305,7 +327,13 @@ int main(int argc, char** argv) {
             std::vector<uint32_t> tok;
             const int mis = (int)(nblk % 32);
             std::fill(got.begin(), got.end(), 0xEE);
-            const uint32_t st = decode_block(raw.data() + 8, lead, clen, isize, got.data() + mis, tok);
+            const uint32_t st = decode_block<BitReader>(raw.data() + 8, lead, clen, isize, got.data() + mis, tok);
+            {   // the second reader must produce the same literals, tokens and status
+                std::vector<uint32_t> tok2; static std::vector<uint8_t> got2(65536 + 64 + 32);
+                std::fill(got2.begin(), got2.end(), 0xEE);
+                const uint32_t st2 = decode_block<RingReader>(raw.data() + 8, lead, clen, isize, got2.data() + mis, tok2);
+                if (st2 != st || tok2 != tok || memcmp(got2.data(), got.data(), got2.size()) != 0) { bad++; fprintf(stderr, "block %ld (lead %d): BitReader2 disagrees (status %u vs %u, %zu vs %zu tokens)\n", nblk, lead, st2, st, tok2.size(), tok.size()); if (bad > 5) return 1; }
+            }
             if (st == kOk) resolve_block(got.data() + mis, tok, mis);
             if (st != kOk || memcmp(got.data() + mis, want.data(), isize) != 0) {
                 bad++;
