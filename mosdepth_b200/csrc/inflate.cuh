@@ -111,7 +111,7 @@ struct BitReader {
 };
 // which reader the decode kernel uses: 0 = the bit buffer above, 1 = BitReader2 (inflate_core.cuh: windows read from the ring)
 #ifndef MSD_BITREADER2
-#define MSD_BITREADER2 0
+#define MSD_BITREADER2 1
 #endif
 
 // canon_len_minus1(): inflate_core.cuh (shared with the host replay).
