@@ -14,7 +14,7 @@ $(LIB): $(CSRC)
 
 mosdepth_b200/bin/mosdepth-b200: mosdepth_b200/host/main.cpp $(wildcard mosdepth_b200/host/*.hpp) include/mosdepth_b200.h $(LIB)
 	mkdir -p mosdepth_b200/bin
-	$(CXX) -O2 -g -std=c++17 -Wall -o $@ mosdepth_b200/host/main.cpp -Iinclude -Lmosdepth_b200 -lmosdepth_b200 -lz -Wl,-rpath,'$$ORIGIN/..'
+	$(CXX) -O2 -g -std=c++17 -Wall -pthread -o $@ mosdepth_b200/host/main.cpp -Iinclude -Lmosdepth_b200 -lmosdepth_b200 -lz -Wl,-rpath,'$$ORIGIN/..'
 
 tools/gen_bam: tools/gen_bam.cpp
 	$(CXX) -O3 -std=c++17 -Wall -pthread -o $@ $< -lz

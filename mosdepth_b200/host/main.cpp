@@ -7,8 +7,9 @@
 // the library (GPU); there is no CPU depth computation in this file.
 //
 // Output files: <prefix>.mosdepth.{global,region}.dist.txt, <prefix>.mosdepth.summary.txt and the bed.gz files
-// (BGZF-compressed with system zlib; no .csi index is written in this stand-in -- the reference's writer is
-// hts-nim's BGZI, which stays untouched when the Nim host binds the C ABI).
+// (BGZF-compressed with system zlib, each with a .csi index like hts-nim's BGZI writer; per-base and quantized runs are
+// formatted and deflated by a pool of host threads, bgzf_writer.hpp.  The reference's own writer stays untouched when the
+// Nim host binds the C ABI).
 #include <algorithm>
 #include <cerrno>
 #include <cinttypes>
@@ -28,37 +29,9 @@ static void die(int code, const char* fmt, ...) __attribute__((format(printf, 2,
 #include <cstdarg>
 static void die(int code, const char* fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); fputc('\n', stderr); exit(code); }
 
-// ---- BGZF text writer (replaces hts-nim wopen_bgzi / write_interval for the stand-in) ----------------------------
-struct BgzWriter {
-    FILE* f = nullptr; std::string buf; int level = 1; bool plain = false;
-    bool open(const std::string& path, int lvl, bool plain_text) { f = fopen(path.c_str(), "wb"); level = lvl; plain = plain_text; buf.reserve(1 << 17); return f != nullptr; }
-    void flush_block(size_t n) {
-        if (!n) return;
-        static uint8_t out[65536 + 1024];
-        z_stream zs; memset(&zs, 0, sizeof zs);
-        deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
-        zs.next_in = (Bytef*)buf.data(); zs.avail_in = (uInt)n; zs.next_out = out + 18; zs.avail_out = sizeof out - 26;
-        if (deflate(&zs, Z_FINISH) != Z_STREAM_END) die(1, "[mosdepth] deflate failed");
-        uint32_t clen = (uint32_t)zs.total_out, blen = clen + 26; deflateEnd(&zs);
-        static const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
-        memcpy(out, hdr, 16); out[16] = (uint8_t)(blen - 1); out[17] = (uint8_t)((blen - 1) >> 8);
-        uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef*)buf.data(), (uInt)n), isz = (uint32_t)n;
-        memcpy(out + 18 + clen, &crc, 4); memcpy(out + 22 + clen, &isz, 4);
-        fwrite(out, 1, blen, f);
-        buf.erase(0, n);
-    }
-    void write(const char* s, size_t n) {
-        if (plain) { fwrite(s, 1, n, f); return; }
-        buf.append(s, n);
-        while (buf.size() >= 0xff00) flush_block(0xff00);
-    }
-    void write(const std::string& s) { write(s.data(), s.size()); }
-    int close() {
-        if (!f) return 0;
-        if (!plain) { flush_block(buf.size()); static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 0x42, 0x43, 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0}; fwrite(eof, 1, 28, f); }
-        int r = fclose(f); f = nullptr; return r;
-    }
-};
+// ---- BGZF text writer + CSI index (replaces hts-nim wopen_bgzi / write_interval for the stand-in): bgzf_writer.hpp ------
+#include "bgzf_writer.hpp"
+using bgz::BgzWriter;
 
 // ---- BAM header + index parsing (what hts-nim does for the reference's host) -----------------------------------
 struct Target { std::string name; uint32_t length; };
@@ -302,12 +275,13 @@ int main(int argc, char** argv) {
     // ---- outputs (mosdepth.nim:641-682) -------------------------------------------------------------------------------
     const std::string gz = plain ? "" : ".gz";
     BgzWriter fbase, fquant, fthr, fregion; FILE *fh_gd, *fh_sum, *fh_rd = nullptr;
-    if (!no_per_base && !fbase.open(prefix + ".per-base.bed" + gz, 1, plain)) die(1, "[mosdepth] could not open per-base file");
-    if (!quant.empty() && !fquant.open(prefix + ".quantized.bed" + gz, 1, plain)) die(1, "[mosdepth] could not open quantized file");
-    if (!thr.empty()) { if (!fthr.open(prefix + ".thresholds.bed" + gz, 1, plain)) die(1, "[mosdepth] could not open thresholds file"); std::string h = "#chrom\tstart\tend\tregion"; for (int32_t t : thr) h += "\t" + std::to_string(t) + "X"; h += "\n"; fthr.write(h); }
+    const int wthreads = getenv("MOSDEPTH_B200_WRITER_THREADS") ? atoi(getenv("MOSDEPTH_B200_WRITER_THREADS")) : 0;   // 0: one per core, at most 32
+    if (!no_per_base && !fbase.open(prefix + ".per-base.bed" + gz, 1, plain, wthreads, !plain)) die(1, "[mosdepth] could not open per-base file");
+    if (!quant.empty() && !fquant.open(prefix + ".quantized.bed" + gz, 1, plain, wthreads, !plain)) die(1, "[mosdepth] could not open quantized file");
+    if (!thr.empty()) { if (!fthr.open(prefix + ".thresholds.bed" + gz, 1, plain, wthreads, !plain)) die(1, "[mosdepth] could not open thresholds file"); std::string h = "#chrom\tstart\tend\tregion"; for (int32_t t : thr) h += "\t" + std::to_string(t) + "X"; h += "\n"; fthr.write(h); }
     if (!(fh_gd = fopen((prefix + ".mosdepth.global.dist.txt").c_str(), "w"))) die(1, "[mosdepth] could not open file:%s.mosdepth.global.dist.txt", prefix.c_str());
     if (!(fh_sum = fopen((prefix + ".mosdepth.summary.txt").c_str(), "w"))) die(1, "[mosdepth] could not open file:%s.mosdepth.summary.txt", prefix.c_str());
-    if (by) { if (!(fh_rd = fopen((prefix + ".mosdepth.region.dist.txt").c_str(), "w"))) die(1, "could not open region dist"); if (!fregion.open(prefix + ".regions.bed" + gz, 6, plain)) die(1, "[mosdepth] could not open regions file"); }
+    if (by) { if (!(fh_rd = fopen((prefix + ".mosdepth.region.dist.txt").c_str(), "w"))) die(1, "could not open region dist"); if (!fregion.open(prefix + ".regions.bed" + gz, 6, plain, wthreads, !plain)) die(1, "[mosdepth] could not open regions file"); }
 
     msd_depth_stat global_stat, global_region_stat; stat_clear(global_stat); stat_clear(global_region_stat);
     std::vector<int64_t> region_distribution(512, 0), global_distribution(512, 0);
@@ -359,12 +333,12 @@ int main(int argc, char** argv) {
                 line.clear(); line += target.name; line += '\t'; char* p = fmt_u32(num, s); line.append(num, p - num); line += '\t'; p = fmt_u32(num, e); line.append(num, p - num); line += '\t';
                 if (name && !name->empty()) { line += *name; line += '\t'; }
                 int n = snprintf(num, sizeof num, "%.*f", g_precision, tid != -2 ? values[k] : 0.0); line.append(num, (size_t)n); line += '\n';
-                fregion.write(line);
+                fregion.write_interval(line, target.name, s, e);
                 if (!thr.empty()) {
                     line.clear(); line += target.name; line += '\t'; p = fmt_u32(num, s); line.append(num, p - num); line += '\t'; p = fmt_u32(num, e); line.append(num, p - num); line += '\t';
                     line += (name && !name->empty()) ? *name : std::string("unknown");
                     for (size_t j = 0; j < thr.size(); j++) { line += '\t'; line += tid == -2 ? std::string("0") : std::to_string(thr_counts[k * thr.size() + j]); }
-                    line += '\n'; fthr.write(line);
+                    line += '\n'; fthr.write_interval(line, target.name, s, e);
                 }
             }
             if (bc) bc->clear(), bed.erase(std::find_if(bed.begin(), bed.end(), [&](auto& kv) { return kv.first == target.name; }));   // bed_regions.del (:397)
@@ -382,11 +356,12 @@ int main(int argc, char** argv) {
         if (by) write_distribution(target.name, chrom_region, fh_rd);
         if (tid >= 0) { if (by) sum_into(chrom_region, region_distribution); sum_into(chrom_global, global_distribution); }   // :761-764
         if (!no_per_base) {                                                                    // :766-793
-            if (tid == -2) { line = target.name + "\t0\t" + std::to_string(target.length) + "\t0\n"; fbase.write(line); }
+            if (tid == -2) { line = target.name + "\t0\t" + std::to_string(target.length) + "\t0\n"; fbase.write_interval(line, target.name, 0, target.length); }
             else {
                 const int32_t *st, *en, *dp; int64_t nr = 0;
                 MSD(msd_per_base_runs(ctx, ti, &st, &en, &dp, &nr));
                 std::string pre = target.name + "\t"; line.clear();
+                if (!plain) { fbase.write_runs(target.name, st, en, dp, nr); nr = 0; }      // .gz: formatted + deflated by the writer's threads
                 for (int64_t k = 0; k < nr; k++) {
                     line += pre; char* p = fmt_i32(num, st[k]); *p++ = '\t'; p = fmt_i32(p, en[k]); *p++ = '\t'; p = fmt_i32(p, dp[k]); *p++ = '\n'; line.append(num, p - num);
                     if (line.size() > (1 << 19)) { fbase.write(line); line.clear(); }
@@ -395,11 +370,12 @@ int main(int argc, char** argv) {
             }
         }
         if (!quant.empty()) {                                                                  // :794-805
-            if (tid == -2 && quant[0] == 0) { line = target.name + "\t0\t" + std::to_string(target.length) + "\t" + lookup[0] + "\n"; fquant.write(line); }
+            if (tid == -2 && quant[0] == 0) { line = target.name + "\t0\t" + std::to_string(target.length) + "\t" + lookup[0] + "\n"; fquant.write_interval(line, target.name, 0, target.length); }
             else if (tid != -2) {
                 const int32_t *st, *en, *bn; int64_t nr = 0;
                 MSD(msd_quantized_runs(ctx, ti, quant.data(), (int)quant.size(), &st, &en, &bn, &nr));
                 line.clear();
+                if (!plain) { fquant.write_runs(target.name, st, en, bn, nr, &lookup); nr = 0; }
                 for (int64_t k = 0; k < nr; k++) { line += target.name; line += '\t'; line += std::to_string(st[k]); line += '\t'; line += std::to_string(en[k]); line += '\t'; line += lookup[(size_t)bn[k]]; line += '\n'; if (line.size() > (1 << 19)) { fquant.write(line); line.clear(); } }
                 fquant.write(line);
             }
