@@ -147,6 +147,25 @@ int msd_regions(msd_ctx *ctx, int tid, int64_t n, const uint32_t *start, const u
 int msd_per_base_runs(msd_ctx *ctx, int tid, const int32_t **start, const int32_t **stop, const int32_t **depth,
                       int64_t *n_runs);
 
+/* The per-base.bed.gz bytes of a contig, formatted and deflated on the device: replaces the loop mosdepth.nim:783-793
+ * (`chrom \t start \t stop \t depth \n` per run of gen_depths, numbers as int2str.nim:59-76 prints them) together with
+ * the BGZF compression hts-nim's writer does for it (wopen_bgzi :650-651).  *bgzf points at *n_bytes of complete BGZF
+ * members (no EOF marker: the caller appends it when it closes the file) that decompress to exactly that text; the
+ * compressed bytes differ from zlib's (parity is on decompressed content).  members[k] describes member k: its
+ * byte offset in *bgzf, the index of the run its first line holds (a line never straddles two members), its compressed
+ * and uncompressed sizes -- what the caller needs to build the .csi from the runs, which are returned as by
+ * msd_per_base_runs().  All buffers are library-owned pinned host memory, valid until the next call on this context that
+ * returns runs.  chrom: at most 200 bytes (MSD_EINVAL beyond; the caller then formats the runs itself). */
+typedef struct msd_bgzf_member {
+    uint64_t offset;      /* of the member inside *bgzf */
+    uint64_t first_run;   /* index of the run whose line opens the member */
+    uint32_t csize;       /* member bytes (BSIZE + 1) */
+    uint32_t isize;       /* text bytes */
+} msd_bgzf_member;
+int msd_per_base_bgzf(msd_ctx *ctx, int tid, const char *chrom, const uint8_t **bgzf, int64_t *n_bytes,
+                      const msd_bgzf_member **members, int64_t *n_members, const int32_t **start,
+                      const int32_t **stop, const int32_t **depth, int64_t *n_runs);
+
 /* gen_quantized(quants, arr) mosdepth.nim:124-141 with linear_search :98-109.  quants: the n_q sorted values of
  * get_quantize_args (:501-519; INT64_MAX for an open last bin).  Returns only the segments the reference
  * yields (bin != -1 and bin < n_q-1; the scan stops before the last base, :132; the last segment is closed

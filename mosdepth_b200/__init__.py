@@ -22,7 +22,7 @@ MODE_DEFAULT, MODE_FAST, MODE_FRAGMENT = 0, 1, 2
 EXPORTS = [
     "msd_abi_version", "msd_create", "msd_destroy", "msd_last_error", "msd_open", "msd_open_mem", "msd_stage",
     "msd_set_spans", "msd_set_targets", "msd_set_filters", "msd_run", "msd_last_run_info", "msd_contig_records",
-    "msd_contig_stats", "msd_n_windows", "msd_prefetch_windows", "msd_windows", "msd_regions", "msd_per_base_runs", "msd_quantized_runs",
+    "msd_contig_stats", "msd_n_windows", "msd_prefetch_windows", "msd_windows", "msd_regions", "msd_per_base_runs", "msd_per_base_bgzf", "msd_quantized_runs",
     "msd_set_contig_range", "msd_contig_spill", "msd_depth_copy", "msd_depth_add", "msd_contig_finalize",
     "msd_totals_device", "msd_totals_reset", "msd_mark", "msd_elapsed_ms", "msd_launch_count", "msd_debug_inflate", "msd_debug_depth", "msd_debug_cumsum", "msd_debug_crc32",
 ]
@@ -85,6 +85,7 @@ def load_library():
     lib.msd_windows.argtypes = [p, i32, u32, i32, p, i64, C.POINTER(DepthStat), p]; lib.msd_windows.restype = i64
     lib.msd_regions.argtypes = [p, i32, i64, p, p, i32, p, C.POINTER(DepthStat), p, i64, C.POINTER(i64), p, i32, p]
     lib.msd_per_base_runs.argtypes = [p, i32, C.POINTER(p), C.POINTER(p), C.POINTER(p), C.POINTER(i64)]
+    lib.msd_per_base_bgzf.argtypes = [p, i32, C.c_char_p, C.POINTER(p), C.POINTER(i64), C.POINTER(p), C.POINTER(i64), C.POINTER(p), C.POINTER(p), C.POINTER(p), C.POINTER(i64)]
     lib.msd_quantized_runs.argtypes = [p, i32, p, i32, C.POINTER(p), C.POINTER(p), C.POINTER(p), C.POINTER(i64)]
     lib.msd_totals_device.argtypes = [p, C.POINTER(p), C.POINTER(p), C.POINTER(i64), C.POINTER(p)]
     lib.msd_totals_reset.argtypes = [p]
@@ -257,6 +258,20 @@ class Context:
 
     def per_base_runs(self, tid):
         return self._runs(self.lib.msd_per_base_runs, tid)
+
+    def per_base_bgzf(self, tid, chrom):
+        """(BGZF bytes without the EOF marker, members as a structured array, (start, stop, depth)) -- msd_per_base_bgzf."""
+        z, m, a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(); nz, nm, n = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.lib.msd_per_base_bgzf(self.h, tid, chrom.encode() if isinstance(chrom, str) else chrom, C.byref(z), C.byref(nz), C.byref(m), C.byref(nm),
+                                               C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        def arr(p):
+            if n.value == 0:
+                return np.zeros(0, dtype=np.int32)
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(n.value,)).copy()
+        data = C.string_at(z, nz.value) if nz.value else b""
+        mdt = np.dtype([("offset", "<u8"), ("first_run", "<u8"), ("csize", "<u4"), ("isize", "<u4")])
+        members = np.frombuffer(C.string_at(m, nm.value * mdt.itemsize), dtype=mdt).copy() if nm.value else np.zeros(0, dtype=mdt)
+        return data, members, (arr(a), arr(b), arr(c))
 
     def quantized_runs(self, tid, quants):
         q = np.ascontiguousarray(quants, dtype=np.int64)

@@ -3,6 +3,7 @@
 //
 // Two paths:
 //   write()       serial: text is cut into 0xff00-byte blocks and deflated one block at a time (regions, thresholds, headers);
+//   write_members() members deflated on the device (msd_per_base_bgzf) are appended as they are, the index is built from the runs;
 //   write_runs()  parallel: the (start, stop, value) runs that msd_per_base_runs / msd_quantized_runs return are formatted
 //                 AND deflated by worker threads, 8,192 runs per task, each task a whole number of BGZF blocks; the main thread
 //                 writes the tasks in order.  per-base.bed.gz is the reference's own second-largest cost (README.md:157-159:
@@ -224,6 +225,29 @@ struct BgzWriter {
                 put(T.out);
             }
         }
+    }
+    // BGZF members that were deflated elsewhere (the device: msd_per_base_bgzf) holding the lines `chrom \t st \t en \t val \n` of the
+    // n runs; Member = {offset, first_run, csize, isize}.  The bytes are appended as they are; the index entries come from the runs
+    // (a line's length is a digit count) and the member table.  A line never straddles two members.
+    template <class Member>
+    void write_members(const std::string& chrom, const uint8_t* bytes, int64_t n_bytes, const Member* mem, int64_t n_mem, const int32_t* st, const int32_t* en, const int32_t* val, int64_t n) {
+        if (n_bytes <= 0 || plain) { if (plain) failed = true; return; }
+        flush_block(buf.size());
+        if (csi) {
+            auto digits = [](int64_t v) { int d = v < 0 ? 2 : 1; if (v < 0) v = -v; while (v >= 10) { v /= 10; d++; } return d; };
+            for (int64_t k = 0; k < n_mem; k++) {
+                const int64_t a = (int64_t)mem[k].first_run, b = k + 1 < n_mem ? (int64_t)mem[k + 1].first_run : n;
+                const uint64_t c0 = coff + mem[k].offset; uint64_t uoff = 0;
+                for (int64_t i = a; i < b; i++) {
+                    const uint64_t len = chrom.size() + 4 + (uint64_t)digits(st[i]) + (uint64_t)digits(en[i]) + (uint64_t)digits(val[i]);
+                    const uint64_t v0 = (c0 << 16) | uoff; uoff += len;
+                    csi->add(chrom, st[i], en[i], v0, i + 1 == b ? (c0 + mem[k].csize) << 16 : (c0 << 16) | uoff);
+                }
+                if (uoff != mem[k].isize) { failed = true; return; }
+            }
+        }
+        if (fwrite(bytes, 1, (size_t)n_bytes, f) != (size_t)n_bytes) failed = true;
+        coff += (uint64_t)n_bytes;
     }
     int close() {
         if (!f) return 0;

@@ -275,6 +275,7 @@ int main(int argc, char** argv) {
     // ---- outputs (mosdepth.nim:641-682) -------------------------------------------------------------------------------
     const std::string gz = plain ? "" : ".gz";
     BgzWriter fbase, fquant, fthr, fregion; FILE *fh_gd, *fh_sum, *fh_rd = nullptr;
+    const bool device_bgzf = getenv("MOSDEPTH_B200_DEVICE_BGZF") && atoi(getenv("MOSDEPTH_B200_DEVICE_BGZF")) != 0;   // per-base.bed.gz deflated on the device (K10)
     const int wthreads = getenv("MOSDEPTH_B200_WRITER_THREADS") ? atoi(getenv("MOSDEPTH_B200_WRITER_THREADS")) : 0;   // 0: one per core, at most 32
     if (!no_per_base && !fbase.open(prefix + ".per-base.bed" + gz, 1, plain, wthreads, !plain)) die(1, "[mosdepth] could not open per-base file");
     if (!quant.empty() && !fquant.open(prefix + ".quantized.bed" + gz, 1, plain, wthreads, !plain)) die(1, "[mosdepth] could not open quantized file");
@@ -359,9 +360,13 @@ int main(int argc, char** argv) {
             if (tid == -2) { line = target.name + "\t0\t" + std::to_string(target.length) + "\t0\n"; fbase.write_interval(line, target.name, 0, target.length); }
             else {
                 const int32_t *st, *en, *dp; int64_t nr = 0;
-                MSD(msd_per_base_runs(ctx, ti, &st, &en, &dp, &nr));
                 std::string pre = target.name + "\t"; line.clear();
-                if (!plain) { fbase.write_runs(target.name, st, en, dp, nr); nr = 0; }      // .gz: formatted + deflated by the writer's threads
+                if (!plain && device_bgzf && target.name.size() <= 200) {                     // K10: formatted + deflated on the device, appended as is
+                    const uint8_t* zb; int64_t zn = 0, nm = 0; const msd_bgzf_member* mem;
+                    MSD(msd_per_base_bgzf(ctx, ti, target.name.c_str(), &zb, &zn, &mem, &nm, &st, &en, &dp, &nr));
+                    fbase.write_members(target.name, zb, zn, mem, nm, st, en, dp, nr); nr = 0;
+                } else MSD(msd_per_base_runs(ctx, ti, &st, &en, &dp, &nr));
+                if (!plain && nr) { fbase.write_runs(target.name, st, en, dp, nr); nr = 0; }      // .gz: formatted + deflated by the writer's threads
                 for (int64_t k = 0; k < nr; k++) {
                     line += pre; char* p = fmt_i32(num, st[k]); *p++ = '\t'; p = fmt_i32(p, en[k]); *p++ = '\t'; p = fmt_i32(p, dp[k]); *p++ = '\n'; line.append(num, p - num);
                     if (line.size() > (1 << 19)) { fbase.write(line); line.clear(); }

@@ -42,6 +42,12 @@ proc msd_regions*(ctx: MsdCtx, tid: cint, n: int64, start, stop: ptr uint32, use
                   region_stat: ptr MsdDepthStat, region_dist: ptr int64, dist_cap: int64, dist_len: ptr int64,
                   thresholds: ptr int32, n_thr: cint, thr_counts: ptr int64): cint {.importc, dynlib: libmsd.}
 proc msd_per_base_runs*(ctx: MsdCtx, tid: cint, start, stop, depth: ptr ptr int32, n_runs: ptr int64): cint {.importc, dynlib: libmsd.}
+type MsdBgzfMember* {.bycopy.} = object   ## msd_bgzf_member
+  offset*, first_run*: uint64
+  csize*, isize*: uint32
+## per-base.bed.gz members deflated on the device (replaces the loop :783-793 and the BGZF compression of its writer, :650-651)
+proc msd_per_base_bgzf*(ctx: MsdCtx, tid: cint, chrom: cstring, bgzf: ptr ptr uint8, n_bytes: ptr int64, members: ptr ptr MsdBgzfMember, n_members: ptr int64,
+                        start, stop, depth: ptr ptr int32, n_runs: ptr int64): cint {.importc, dynlib: libmsd.}
 proc msd_quantized_runs*(ctx: MsdCtx, tid: cint, quants: ptr int64, n_q: cint, start, stop, bin: ptr ptr int32, n_runs: ptr int64): cint {.importc, dynlib: libmsd.}
 
 template check*(ctx: MsdCtx, call: untyped) =

@@ -38,11 +38,11 @@ def bgzf_blocks(data):
     return out
 
 
-@pytest.mark.parametrize("name", ["runs", "quant", "regions"])
+@pytest.mark.parametrize("name", ["runs", "quant", "regions", "members"])
 def test_content_structure_and_thread_independence(outputs, name):
     gz1 = (outputs / f"t1.{name}.bed.gz").read_bytes()
     gz5 = (outputs / f"t5.{name}.bed.gz").read_bytes()
-    plain = (outputs / f"t1.{name}.bed").read_bytes()
+    plain = (outputs / f"t1.{'runs' if name == 'members' else name}.bed").read_bytes()
     assert gz1 == gz5
     assert (outputs / f"t1.{name}.bed.gz.csi").read_bytes() == (outputs / f"t5.{name}.bed.gz.csi").read_bytes()
     assert gzip.decompress(gz1) == plain
@@ -125,13 +125,13 @@ def query(gz, idx, tid, beg, end):
     return hit, len(lines)
 
 
-@pytest.mark.parametrize("name", ["runs", "regions", "quant"])
+@pytest.mark.parametrize("name", ["runs", "regions", "quant", "members"])
 def test_csi_queries_find_exactly_the_overlapping_lines(outputs, name):
     gz = (outputs / f"t5.{name}.bed.gz").read_bytes()
     idx = parse_csi(gzip.decompress((outputs / f"t5.{name}.bed.gz.csi").read_bytes()))
     assert idx["min_shift"] == 14 and idx["depth"] == 5 and idx["conf"] == (0x10000, 1, 2, 3, ord("#"), 0)
     assert idx["names"] == [b"chr1", b"chr2_random_with_a_longer_name", b"chrM"]
-    plain = (outputs / f"t1.{name}.bed").read_bytes().splitlines(keepends=True)
+    plain = (outputs / f"t1.{'runs' if name == 'members' else name}.bed").read_bytes().splitlines(keepends=True)
     by_chrom = {}
     for ln in plain:
         f = ln.split(b"\t")

@@ -14,7 +14,9 @@ int main(int argc, char** argv) {
     auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
     const char* contigs[] = {"chr1", "chr2_random_with_a_longer_name", "chrM"};
     const std::vector<std::string> labels = {"NO_COVERAGE", "LOW_COVERAGE", "CALLABLE", "HIGH_COVERAGE"};
-    bgz::BgzWriter gz, plain, qz, qplain, rz, rplain;
+    struct Member { uint64_t offset, first_run; uint32_t csize, isize; };      // layout of msd_bgzf_member (include/mosdepth_b200.h)
+    bgz::BgzWriter gz, plain, qz, qplain, rz, rplain, mz;
+    if (!mz.open(prefix + ".members.bed.gz", 1, false, threads, true)) return 1;
     if (!gz.open(prefix + ".runs.bed.gz", 1, false, threads, true) || !plain.open(prefix + ".runs.bed", 1, true) ||
         !qz.open(prefix + ".quant.bed.gz", 1, false, threads, true) || !qplain.open(prefix + ".quant.bed", 1, true) ||
         !rz.open(prefix + ".regions.bed.gz", 6, false, threads, true) || !rplain.open(prefix + ".regions.bed", 6, true)) return 1;
@@ -30,6 +32,17 @@ int main(int argc, char** argv) {
         }
         gz.write_runs(contigs[c], st.data(), en.data(), dp.data(), m); plain.write_runs(contigs[c], st.data(), en.data(), dp.data(), m);
         qz.write_runs(contigs[c], st.data(), en.data(), bn.data(), m, &labels); qplain.write_runs(contigs[c], st.data(), en.data(), bn.data(), m, &labels);
+        {   // members deflated "elsewhere" (here: zlib over groups of 700 lines), appended through write_members
+            std::vector<uint8_t> bytes; std::vector<Member> mem; std::string text; char num[64];
+            for (int64_t a = 0; a < m; a += 700) {
+                text.clear();
+                for (int64_t k = a; k < std::min(m, a + 700); k++) { text += contigs[c]; text += '\t'; char* p = bgz::fmt_i32(num, st[(size_t)k]); *p++ = '\t'; p = bgz::fmt_i32(p, en[(size_t)k]); *p++ = '\t'; p = bgz::fmt_i32(p, dp[(size_t)k]); *p++ = '\n'; text.append(num, (size_t)(p - num)); }
+                const size_t before = bytes.size();
+                if (!bgz::deflate_block(text.data(), text.size(), 1, bytes)) return 1;
+                mem.push_back(Member{before, (uint64_t)a, (uint32_t)(bytes.size() - before), (uint32_t)text.size()});
+            }
+            mz.write_members(contigs[c], bytes.data(), (int64_t)bytes.size(), mem.data(), (int64_t)mem.size(), st.data(), en.data(), dp.data(), m);
+        }
         // regions: 500-base windows over the contig through the serial, line-indexed path
         for (int32_t s = 0; s < pos; s += 500) {
             const int32_t e = std::min(pos, s + 500);
@@ -38,6 +51,6 @@ int main(int argc, char** argv) {
         }
     }
     int rc = 0;
-    rc |= gz.close(); rc |= plain.close(); rc |= qz.close(); rc |= qplain.close(); rc |= rz.close(); rc |= rplain.close();
+    rc |= gz.close(); rc |= plain.close(); rc |= qz.close(); rc |= qplain.close(); rc |= rz.close(); rc |= rplain.close(); rc |= mz.close();
     return rc ? 1 : 0;
 }
