@@ -1,14 +1,16 @@
 // bgzf_writer.hpp -- BGZF text writer of the host CLI stand-in (replaces hts-nim's wopen_bgzi / write_interval,
 // mosdepth.nim:650-678,733,793,803, for the stand-in only: the reference's writer stays when the Nim host binds the C ABI).
 //
-// Two paths:
-//   write()       serial: text is cut into 0xff00-byte blocks and deflated one block at a time (regions, thresholds, headers);
-//   write_members() members deflated on the device (msd_per_base_bgzf) are appended as they are, the index is built from the runs;
-//   write_runs()  parallel: the (start, stop, value) runs that msd_per_base_runs / msd_quantized_runs return are formatted
-//                 AND deflated by worker threads, 8,192 runs per task, each task a whole number of BGZF blocks; the main thread
-//                 writes the tasks in order.  per-base.bed.gz is the reference's own second-largest cost (README.md:157-159:
-//                 24.8 s with per-base output vs 5.9 s without) and is pure host work here too: ~25 M runs / 0.5 GB of text for a
-//                 30X chr20.  The bytes written do not depend on the number of threads (task boundaries are fixed).
+// Paths:
+//   write() / write_interval()  serial: text is cut into blocks and deflated one block at a time (headers, the single rows of contigs
+//                 without reads);
+//   write_lines() parallel: the lines of one contig (region / threshold rows, per-base and quantized runs) are formatted by a callback
+//                 AND deflated on worker threads, 8,192 lines per task, each task a whole number of BGZF blocks; the main thread writes
+//                 the tasks in order, so the bytes do not depend on the number of threads.  per-base.bed.gz is the reference's own
+//                 second-largest cost (README.md:157-159: 24.8 s with per-base output vs 5.9 s without) and regions.bed.gz (level 6,
+//                 6.2 M window rows for a genome at --by 500) is the largest host cost of the north-star run; both are pure host work;
+//   write_runs()  = write_lines over the (start, stop, value) runs that msd_per_base_runs / msd_quantized_runs return;
+//   write_members() members deflated on the device (msd_per_base_bgzf) are appended as they are, the index is built from the runs.
 // With `plain` the text is written as is (parity tests compare decompressed content).
 // A CSI index (.csi, tabix preset bed: min_shift 14, depth 5, as hts-nim's BGZI writes next to every bed.gz) is built when
 // index_path is given: every line's (contig, start, stop) is registered with the virtual offsets of its first and
@@ -153,15 +155,26 @@ struct BgzWriter {
     }
     // chrom \t start \t stop \t (value | labels[value]) \n for every run, formatted and deflated by `threads` workers
     void write_runs(const std::string& chrom, const int32_t* st, const int32_t* en, const int32_t* val, int64_t n, const std::vector<std::string>* labels = nullptr) {
-        if (n <= 0) return;
-        auto format = [&](int64_t a, int64_t b, std::string& out, std::vector<uint32_t>* line_off) {
-            char num[48];
-            for (int64_t k = a; k < b; k++) {
-                if (line_off) line_off->push_back((uint32_t)out.size());
+        write_lines(chrom, n,
+            [&](int64_t k, std::string& out) {
+                char num[48];
                 out += chrom; out += '\t';
                 char* p = fmt_i32(num, st[k]); *p++ = '\t'; p = fmt_i32(p, en[k]); *p++ = '\t';
                 if (!labels) { p = fmt_i32(p, val[k]); *p++ = '\n'; out.append(num, (size_t)(p - num)); }
                 else { out.append(num, (size_t)(p - num)); out += (*labels)[(size_t)val[k]]; out += '\n'; }
+            },
+            [&](int64_t k, int64_t* beg, int64_t* end) { *beg = st[k]; *end = en[k]; });
+    }
+    // n lines of one contig: fmt(k, out) appends line k (newline included) and is called from the worker threads (it must only read
+    // shared state); interval(k, &beg, &end) is what the index records for it.  kRunsPerTask lines per task, each task a whole number
+    // of BGZF blocks, tasks written in order: the bytes do not depend on the number of threads.
+    template <class Fmt, class Iv>
+    void write_lines(const std::string& chrom, int64_t n, Fmt fmt, Iv interval) {
+        if (n <= 0) return;
+        auto format = [&](int64_t a, int64_t b, std::string& out, std::vector<uint32_t>* line_off) {
+            for (int64_t k = a; k < b; k++) {
+                if (line_off) line_off->push_back((uint32_t)out.size());
+                fmt(k, out);
             }
         };
         if (plain) {
@@ -219,7 +232,8 @@ struct BgzWriter {
                         // the line ends inside the same block (blocks end on line boundaries); the end offset of the last line of a block points at the next block
                         const bool last_in_block = end_text == blk_start_text + T.blk_in[b];
                         const uint64_t v1 = last_in_block ? ((blk_coff + T.blk_out[b]) << 16) : ((blk_coff << 16) | (uint64_t)(end_text - blk_start_text));
-                        csi->add(chrom, st[a + (int64_t)i], en[a + (int64_t)i], v0, v1);
+                        int64_t ib = 0, ie = 0; interval(a + (int64_t)i, &ib, &ie);
+                        csi->add(chrom, ib, ie, v0, v1);
                     }
                 }
                 put(T.out);

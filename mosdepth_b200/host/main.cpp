@@ -31,6 +31,7 @@ static void die(int code, const char* fmt, ...) { va_list ap; va_start(ap, fmt);
 
 // ---- BGZF text writer + CSI index (replaces hts-nim wopen_bgzi / write_interval for the stand-in): bgzf_writer.hpp ------
 #include "bgzf_writer.hpp"
+#include "lines.hpp"
 using bgz::BgzWriter;
 
 // ---- BAM header + index parsing (what hts-nim does for the reference's host) -----------------------------------
@@ -327,21 +328,19 @@ int main(int argc, char** argv) {
                     chrom_region.resize((size_t)std::max<int64_t>(dl, 512));
                 }
             }
-            // region lines (:725-735) + thresholds (:743 -> :522-557)
-            for (size_t k = 0; k < n_regions; k++) {
-                uint32_t s, e; const std::string* name = nullptr;
-                if (!have_bed) { s = (uint32_t)(k * (uint64_t)window); e = (uint32_t)std::min<uint64_t>((k + 1) * (uint64_t)window, target.length); } else { s = (*regs)[k].start; e = (*regs)[k].stop; name = &(*regs)[k].name; }
-                line.clear(); line += target.name; line += '\t'; char* p = fmt_u32(num, s); line.append(num, p - num); line += '\t'; p = fmt_u32(num, e); line.append(num, p - num); line += '\t';
-                if (name && !name->empty()) { line += *name; line += '\t'; }
-                int n = snprintf(num, sizeof num, "%.*f", g_precision, tid != -2 ? values[k] : 0.0); line.append(num, (size_t)n); line += '\n';
-                fregion.write_interval(line, target.name, s, e);
-                if (!thr.empty()) {
-                    line.clear(); line += target.name; line += '\t'; p = fmt_u32(num, s); line.append(num, p - num); line += '\t'; p = fmt_u32(num, e); line.append(num, p - num); line += '\t';
-                    line += (name && !name->empty()) ? *name : std::string("unknown");
-                    for (size_t j = 0; j < thr.size(); j++) { line += '\t'; line += tid == -2 ? std::string("0") : std::to_string(thr_counts[k * thr.size() + j]); }
-                    line += '\n'; fthr.write_interval(line, target.name, s, e);
-                }
-            }
+            // region lines (:725-735) + thresholds (:743 -> :522-557); formatted (and, for .gz, deflated) by the writer's threads
+            auto interval = [&](int64_t k, int64_t* s, int64_t* e) {
+                if (!have_bed) lines::window_interval(k, window, target.length, s, e);
+                else { *s = (*regs)[(size_t)k].start; *e = (*regs)[(size_t)k].stop; }
+            };
+            fregion.write_lines(target.name, (int64_t)n_regions, [&](int64_t k, std::string& out) {
+                int64_t s, e; interval(k, &s, &e);
+                lines::region_row(out, target.name, (uint32_t)s, (uint32_t)e, have_bed ? &(*regs)[(size_t)k].name : nullptr, tid != -2 ? values[(size_t)k] : 0.0, g_precision);
+            }, interval);
+            if (!thr.empty()) fthr.write_lines(target.name, (int64_t)n_regions, [&](int64_t k, std::string& out) {
+                int64_t s, e; interval(k, &s, &e);
+                lines::threshold_row(out, target.name, (uint32_t)s, (uint32_t)e, have_bed ? &(*regs)[(size_t)k].name : nullptr, tid == -2 ? nullptr : &thr_counts[(size_t)k * thr.size()], thr.size());
+            }, interval);
             if (bc) bc->clear(), bed.erase(std::find_if(bed.begin(), bed.end(), [&](auto& kv) { return kv.first == target.name; }));   // bed_regions.del (:397)
         }
         if (tid != -2) {                                                                       // :745-753

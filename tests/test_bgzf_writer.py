@@ -38,7 +38,7 @@ def bgzf_blocks(data):
     return out
 
 
-@pytest.mark.parametrize("name", ["runs", "quant", "regions", "members"])
+@pytest.mark.parametrize("name", ["runs", "quant", "regions", "members", "lines"])
 def test_content_structure_and_thread_independence(outputs, name):
     gz1 = (outputs / f"t1.{name}.bed.gz").read_bytes()
     gz5 = (outputs / f"t5.{name}.bed.gz").read_bytes()
@@ -125,7 +125,7 @@ def query(gz, idx, tid, beg, end):
     return hit, len(lines)
 
 
-@pytest.mark.parametrize("name", ["runs", "regions", "quant", "members"])
+@pytest.mark.parametrize("name", ["runs", "regions", "quant", "members", "lines"])
 def test_csi_queries_find_exactly_the_overlapping_lines(outputs, name):
     gz = (outputs / f"t5.{name}.bed.gz").read_bytes()
     idx = parse_csi(gzip.decompress((outputs / f"t5.{name}.bed.gz.csi").read_bytes()))

@@ -15,7 +15,8 @@ int main(int argc, char** argv) {
     const char* contigs[] = {"chr1", "chr2_random_with_a_longer_name", "chrM"};
     const std::vector<std::string> labels = {"NO_COVERAGE", "LOW_COVERAGE", "CALLABLE", "HIGH_COVERAGE"};
     struct Member { uint64_t offset, first_run; uint32_t csize, isize; };      // layout of msd_bgzf_member (include/mosdepth_b200.h)
-    bgz::BgzWriter gz, plain, qz, qplain, rz, rplain, mz;
+    bgz::BgzWriter gz, plain, qz, qplain, rz, rplain, mz, lz, lplain;
+    if (!lz.open(prefix + ".lines.bed.gz", 6, false, threads, true) || !lplain.open(prefix + ".lines.bed", 6, true)) return 1;
     if (!mz.open(prefix + ".members.bed.gz", 1, false, threads, true)) return 1;
     if (!gz.open(prefix + ".runs.bed.gz", 1, false, threads, true) || !plain.open(prefix + ".runs.bed", 1, true) ||
         !qz.open(prefix + ".quant.bed.gz", 1, false, threads, true) || !qplain.open(prefix + ".quant.bed", 1, true) ||
@@ -43,6 +44,12 @@ int main(int argc, char** argv) {
             }
             mz.write_members(contigs[c], bytes.data(), (int64_t)bytes.size(), mem.data(), (int64_t)mem.size(), st.data(), en.data(), dp.data(), m);
         }
+        {   // the same kind of rows through write_lines (formatted on the worker threads)
+            const int64_t nw = (pos + 499) / 500; const std::string chrom = contigs[c]; const int32_t top = pos;
+            auto fmt = [&](int64_t k, std::string& out) { char b[128]; const int len = snprintf(b, sizeof b, "%s\t%lld\t%lld\t%.2f\n", chrom.c_str(), (long long)k * 500, (long long)std::min<int64_t>(top, (k + 1) * 500), (double)((k * 2654435761u) % 4000) / 100.0); out.append(b, (size_t)len); };
+            auto iv = [&](int64_t k, int64_t* s, int64_t* e) { *s = k * 500; *e = std::min<int64_t>(top, (k + 1) * 500); };
+            lz.write_lines(chrom, nw, fmt, iv); lplain.write_lines(chrom, nw, fmt, iv);
+        }
         // regions: 500-base windows over the contig through the serial, line-indexed path
         for (int32_t s = 0; s < pos; s += 500) {
             const int32_t e = std::min(pos, s + 500);
@@ -51,6 +58,6 @@ int main(int argc, char** argv) {
         }
     }
     int rc = 0;
-    rc |= gz.close(); rc |= plain.close(); rc |= qz.close(); rc |= qplain.close(); rc |= rz.close(); rc |= rplain.close(); rc |= mz.close();
+    rc |= gz.close(); rc |= plain.close(); rc |= qz.close(); rc |= qplain.close(); rc |= rz.close(); rc |= rplain.close(); rc |= mz.close(); rc |= lz.close(); rc |= lplain.close();
     return rc ? 1 : 0;
 }
