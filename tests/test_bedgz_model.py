@@ -68,3 +68,18 @@ def test_name_longer_than_the_device_path_accepts_is_refused(model):
     exe, d = model
     r = subprocess.run([str(exe), str(d / "long"), "n" * 201, "5", "wgs"], capture_output=True, text=True)
     assert r.returncode == 3 and "refused" in r.stderr
+
+
+def test_k1_model_inflates_what_k10_deflates(model, tmp_path):
+    """Round trip inside the product's own arithmetic: the members K10 writes (dynamic code with all 316 symbols, repeat code 16,
+    32 KB members) go through the host replay of the inflate kernels (tools/inflate_model, K1a + K1b + K1c against zlib)."""
+    import json
+    exe, d = model
+    inf = tmp_path / "inflate_model"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I/usr/local/cuda/include", "-o", str(inf), str(ROOT / "tools" / "inflate_model.cpp"), "-lz"], check=True)
+    for chrom, n, pattern, seed in [("chr7", 150000, "wgs", 21), ("HLA-DRB1*15:01:01:01", 60000, "wide", 22), ("1", 40000, "sparse", 23)]:
+        subprocess.run([str(exe), str(tmp_path / "rt"), chrom, str(n), pattern, str(seed)], check=True, capture_output=True)
+        r = subprocess.run([str(inf), str(tmp_path / "rt.gz")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out = json.loads(r.stdout)
+        assert out["bad"] == 0 and out["blocks"] >= 2 and out["bytes"] >= (tmp_path / "rt.txt").stat().st_size      # every 8th block is replayed at a second alignment

@@ -44,6 +44,7 @@ def check_contig(ctx, tid, chrom):
         first = int(mem["first_run"][k])
         assert piece.startswith(f"{chrom}\t{int(s[first])}\t".encode())
         at += isz
+    assert ctx.debug_inflate(data + EOF_BLOCK, len(want)) == want          # and the product's own inflate kernels read it back
     return want
 
 
