@@ -24,6 +24,7 @@
 #include "runs.cuh"
 #include "scan.cuh"
 #include "bedgz.cuh"
+#include "ingest.hpp"
 
 using namespace msd;
 
@@ -729,6 +730,7 @@ int msd_run(msd_ctx* ctx) {
     const uint32_t ramp0 = (uint32_t)env_u64("MSD_RAMP0_BLOCKS", 6000), copy_blocks = (uint32_t)env_u64("MSD_COPY_BLOCKS", 16000);
     const bool ramp_double = env_u64("MSD_RAMP_DOUBLE", 0) != 0;   // chunk i of a copied input holds ramp0 << i blocks until copy_blocks is reached
     const uint8_t* F = ctx->bytes; const uint64_t N = ctx->n_bytes;
+    const int ingest_threads = ingest_threads_default();
 
     for (const Span& sp : spans) {
         if (sp.beg == ~0ull) continue;
@@ -796,7 +798,11 @@ int msd_run(msd_ctx* ctx) {
                 const uint8_t* srcp = F + chunk_src;
                 if (!ctx->src_pinned) {
                     if (ctx->bounce_used[k]) MSD_CUDA_OK(cudaEventSynchronize(ctx->bounce_free[k]));
-                    memcpy(ctx->stage[k].h_bounce, srcp, comp_bytes); srcp = ctx->stage[k].h_bounce;
+                    if (ctx->mapped && pos < N) {   // start the kernel's read-ahead for the next chunk while this one is copied
+                        const uint64_t a = pos & ~4095ull;
+                        madvise(const_cast<uint8_t*>(F) + a, (size_t)std::min<uint64_t>(2 * comp_bytes + 4096, N - a), MADV_WILLNEED);
+                    }
+                    parallel_copy(ctx->stage[k].h_bounce, srcp, comp_bytes, ingest_threads); srcp = ctx->stage[k].h_bounce;
                 }
                 MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_comp[k], srcp, comp_bytes, cudaMemcpyHostToDevice, sx));
                 MSD_CUDA_OK(cudaEventRecord(h1, sx));

@@ -1,6 +1,7 @@
 """CPU-only checks: the C-ABI library loads and exports every symbol include/mosdepth_b200.h declares, fails loudly
 without a GPU (no CPU fallback), and the host-side logic (header/index parsing, window arithmetic, sharding)."""
 import ctypes
+import json
 import re
 import subprocess
 from pathlib import Path
@@ -170,3 +171,12 @@ def test_split_contig_spans_hold_every_owned_record(tmp_path):
             assert hi == tlen or any(p >= hi for p in got)
             owned_total += len(owned)
         assert owned_total == len(every)
+
+
+def test_ingest_parallel_copy_equals_memcpy(tmp_path):
+    """mosdepth_b200/csrc/ingest.hpp: the multi-threaded bounce copy of msd_run for pageable / mapped input."""
+    exe = tmp_path / "ingest_test"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", str(exe), str(ROOT / "tools" / "ingest_test.cpp")], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert json.loads(r.stdout)["bad"] == 0
