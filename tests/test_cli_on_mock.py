@@ -1,0 +1,89 @@
+"""CPU test of the HOST side of the CLI stand-in (mosdepth_b200/host/main.cpp + bgzf_writer.hpp + lines.hpp): flags, header and
+index parsing, spans, BED tables, the per-contig loop and its emission order, row formatting, the BGZF/CSI writer.  The CLI is
+linked, in a temporary directory, against tests/mock/msd_mock.c -- a TEST DOUBLE of the C ABI that answers from the CPU oracle's
+own functions -- and every output file must equal the oracle's byte for byte on the reference's fixtures and flag combinations
+(the same cases tests/test_gpu_cli_parity.py runs against the real library on a GPU).  This says nothing about the kernels; it pins
+everything around them without a GPU."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT, run_tool
+from test_gpu_cli_parity import FIX_CASES, SUFFIXES
+
+
+@pytest.fixture(scope="module")
+def mock_cli(tmp_path_factory):
+    d = tmp_path_factory.mktemp("mockcli")
+    subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-w", "-o", str(d / "libmosdepth_b200.so"), str(ROOT / "tests" / "mock" / "msd_mock.c"), "-lz", "-lpthread", "-lm"], check=True)
+    exe = d / "mosdepth-b200-mock"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", str(exe), str(ROOT / "mosdepth_b200" / "host" / "main.cpp"), f"-I{ROOT / 'include'}",
+                    f"-L{d}", "-lmosdepth_b200", "-lz", f"-Wl,-rpath,{d}"], check=True)
+    return exe
+
+
+def compare(oracle_bin, cli, tmp_path, bam, flags, env=None, expect_rc=0, gz=False):
+    ro = run_tool(oracle_bin, flags + ["o", bam], tmp_path, env=env, check=False)
+    rg = run_tool(cli, ([] if gz else ["--plain"]) + flags + ["g", bam], tmp_path, env=env, check=False)
+    assert ro.returncode == expect_rc, ro.stderr
+    assert rg.returncode == expect_rc, rg.stderr
+    n = 0
+    for s in SUFFIXES:
+        po = tmp_path / ("o" + s)
+        pg = tmp_path / ("g" + s + (".gz" if gz and s.endswith(".bed") else ""))
+        assert po.exists() == pg.exists(), s
+        if po.exists():
+            a, b = po.read_bytes(), pg.read_bytes()
+            if gz and s.endswith(".bed"):
+                b = gzip.decompress(b)
+                assert gzip.decompress((tmp_path / ("g" + s + ".gz.csi")).read_bytes())[:4] == b"CSI\x01"
+            if a != b:
+                la, lb = a.splitlines(), b.splitlines()
+                for i, (x, y) in enumerate(zip(la, lb)):
+                    assert x == y, f"{s} line {i + 1}: oracle {x!r} != cli {y!r}"
+                assert len(la) == len(lb), f"{s}: {len(la)} vs {len(lb)} lines"
+            n += 1
+    assert n >= 2
+
+
+HEAVY = {"big.bam"}          # a 600 Mb contig: 2.4 GB depth array in the oracle and again in the mock; three cases are enough
+CASES = [(n, f) for n, f in FIX_CASES if n not in HEAVY] + [("big.bam", ["--by", "500", "-n", "-x"])]
+
+
+@pytest.mark.parametrize("name,flags", CASES, ids=[f"{n}:{' '.join(f)}" for n, f in CASES])
+def test_fixture_cli_parity_on_mock(oracle_bin, mock_cli, fixtures, tmp_path, name, flags):
+    flags = [f.replace("FIX", str(fixtures)) for f in flags]
+    compare(oracle_bin, mock_cli, tmp_path, fixtures / name, flags)
+
+
+GZ_CASES = [("ovl.bam", ["--by", "100", "-T", "0,1,2,3,4,5", "-c", "MT", "-q", "0:1:1000"]), ("empty-tids.bam", ["-b", "100", "-q", "0:1:5:150"]),
+            ("nanopore.bam", ["--by", "250", "-T", "50,100"]), ("empty-tids.bam", ["-n", "--thresholds", "1,5", "--by", "FIX/empty-tids.bed"])]
+
+
+@pytest.mark.parametrize("name,flags", GZ_CASES, ids=[f"gz:{n}:{' '.join(f)}" for n, f in GZ_CASES])
+@pytest.mark.parametrize("threads", ["1", "5"])
+def test_gz_outputs_on_mock(oracle_bin, mock_cli, fixtures, tmp_path, name, flags, threads):
+    flags = [f.replace("FIX", str(fixtures)) for f in flags]
+    compare(oracle_bin, mock_cli, tmp_path, fixtures / name, flags, env={"MOSDEPTH_B200_WRITER_THREADS": threads}, gz=True)
+
+
+def test_env_precision_and_labels_on_mock(oracle_bin, mock_cli, fixtures, tmp_path):
+    compare(oracle_bin, mock_cli, tmp_path, fixtures / "ovl.bam", ["-q", "0:1:1000", "--by", "77"], env={"MOSDEPTH_Q0": "AAA", "MOSDEPTH_Q1": "BBB", "MOSDEPTH_PRECISION": "7"})
+
+
+def test_error_paths_match_on_mock(oracle_bin, mock_cli, fixtures, tmp_path):
+    for flags, rc in ((["-c", "nonexistent", "--by", "20000"], 1), (["--min-frag-len", "10", "--max-frag-len", "9"], 2), (["-x", "-a"], 2), (["-T", "1"], 2)):
+        ro = run_tool(oracle_bin, flags + ["o", fixtures / "ovl.bam"], tmp_path, check=False)
+        rg = run_tool(mock_cli, flags + ["g", fixtures / "ovl.bam"], tmp_path, check=False)
+        assert ro.returncode == rc and rg.returncode == rc
+        assert ro.stderr.strip() == rg.stderr.strip()
+
+
+def test_synthetic_c3_on_mock(oracle_bin, mock_cli, tmp_path):
+    """25 contigs, 500-base windows: the north-star flags through the host loop (merged spans, prefetch hint, parallel row writer)."""
+    bam = tmp_path / "c3.bam"
+    subprocess.run([str(ROOT / "tools" / "gen_bam"), "--config", "c3", "--genome-fraction", "0.0005", "--threads", "4", "-o", str(bam)], check=True, capture_output=True)
+    compare(oracle_bin, mock_cli, tmp_path, bam, ["--by", "500", "-n", "-x"])
+    compare(oracle_bin, mock_cli, tmp_path, bam, ["--by", "500"], gz=True)
