@@ -145,8 +145,14 @@ int msd_per_base_runs(msd_ctx *ctx, int tid, const int32_t **start, const int32_
     *start = g_rs; *stop = g_re; *depth = g_rv; *n_runs = n;
     return MSD_OK;
 }
+/* msd_mock_bgzf.cpp: the host replay of K10's arithmetic */
+int msd_mock_per_base_bgzf(msd_ctx *ctx, int tid, const char *chrom, const uint8_t **z, int64_t *nz, const msd_bgzf_member **m, int64_t *nm, const int32_t **s, const int32_t **e,
+                           const int32_t **d, int64_t *n);
 int msd_per_base_bgzf(msd_ctx *ctx, int tid, const char *chrom, const uint8_t **z, int64_t *nz, const msd_bgzf_member **m, int64_t *nm, const int32_t **s, const int32_t **e,
-                      const int32_t **d, int64_t *n) { (void)ctx; (void)tid; (void)chrom; (void)z; (void)nz; (void)m; (void)nm; (void)s; (void)e; (void)d; (void)n; return fail(MSD_EINVAL, "mock: msd_per_base_bgzf is a device path"); }
+                      const int32_t **d, int64_t *n) {
+    if (strlen(chrom) > 200) return fail(MSD_EINVAL, "mock: contig name too long for msd_per_base_bgzf");
+    return msd_mock_per_base_bgzf(ctx, tid, chrom, z, nz, m, nm, s, e, d, n);
+}
 int msd_quantized_runs(msd_ctx *ctx, int tid, const int64_t *quants, int nq, const int32_t **start, const int32_t **stop, const int32_t **bin, int64_t *n_runs) {
     (void)ctx; int rc = need(tid, "msd_quantized_runs"); if (rc) return rc;
     int64_t n = 0;

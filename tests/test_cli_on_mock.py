@@ -17,7 +17,9 @@ from test_gpu_cli_parity import FIX_CASES, SUFFIXES
 @pytest.fixture(scope="module")
 def mock_cli(tmp_path_factory):
     d = tmp_path_factory.mktemp("mockcli")
-    subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-w", "-o", str(d / "libmosdepth_b200.so"), str(ROOT / "tests" / "mock" / "msd_mock.c"), "-lz", "-lpthread", "-lm"], check=True)
+    subprocess.run(["gcc", "-O2", "-fPIC", "-w", "-c", "-o", str(d / "msd_mock.o"), str(ROOT / "tests" / "mock" / "msd_mock.c")], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-w", "-I/usr/local/cuda/include", "-c", "-o", str(d / "msd_mock_bgzf.o"), str(ROOT / "tests" / "mock" / "msd_mock_bgzf.cpp")], check=True)
+    subprocess.run(["g++", "-shared", "-o", str(d / "libmosdepth_b200.so"), str(d / "msd_mock.o"), str(d / "msd_mock_bgzf.o"), "-lz", "-lpthread", "-lm"], check=True)
     exe = d / "mosdepth-b200-mock"
     subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", str(exe), str(ROOT / "mosdepth_b200" / "host" / "main.cpp"), f"-I{ROOT / 'include'}",
                     f"-L{d}", "-lmosdepth_b200", "-lz", f"-Wl,-rpath,{d}"], check=True)
@@ -85,5 +87,26 @@ def test_synthetic_c3_on_mock(oracle_bin, mock_cli, tmp_path):
     """25 contigs, 500-base windows: the north-star flags through the host loop (merged spans, prefetch hint, parallel row writer)."""
     bam = tmp_path / "c3.bam"
     subprocess.run([str(ROOT / "tools" / "gen_bam"), "--config", "c3", "--genome-fraction", "0.0005", "--threads", "4", "-o", str(bam)], check=True, capture_output=True)
-    compare(oracle_bin, mock_cli, tmp_path, bam, ["--by", "500", "-n", "-x"])
-    compare(oracle_bin, mock_cli, tmp_path, bam, ["--by", "500"], gz=True)
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    compare(oracle_bin, mock_cli, tmp_path / "a", bam, ["--by", "500", "-n", "-x"])
+    compare(oracle_bin, mock_cli, tmp_path / "b", bam, ["--by", "500"], gz=True)
+
+
+def test_device_bgzf_branch_on_mock(oracle_bin, mock_cli, fixtures, tmp_path):
+    """MOSDEPTH_B200_DEVICE_BGZF=1: the CLI takes ready BGZF members from msd_per_base_bgzf (here: the host replay of K10's arithmetic)
+    and only appends and indexes them; the per-base file must still decompress to the oracle's, and differ from the host writer's bytes."""
+    for k, (name, flags) in enumerate((("nanopore.bam", ["--by", "250"]), ("empty-tids.bam", ["-x"]), ("ovl.bam", []))):
+        d = tmp_path / str(k); d.mkdir()
+        compare(oracle_bin, mock_cli, d, fixtures / name, flags, env={"MOSDEPTH_B200_DEVICE_BGZF": "1"}, gz=True)
+        dev = (d / "g.per-base.bed.gz").read_bytes()
+        compare(oracle_bin, mock_cli, d, fixtures / name, flags, gz=True)
+        assert dev != (d / "g.per-base.bed.gz").read_bytes()
+
+
+def test_exome_bed_median_thresholds_quantize_on_mock(oracle_bin, mock_cli, tmp_path):
+    """BASELINE config C4 at small scale: unsorted overlapping BED, -T, -m, -q through the host loop."""
+    bam, bed = tmp_path / "c4.bam", tmp_path / "c4.bed"
+    subprocess.run([str(ROOT / "tools" / "gen_bam"), "--config", "c4", "--genome-fraction", "0.0008", "--bed", str(bed), "--threads", "4", "-o", str(bam)], check=True, capture_output=True)
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    compare(oracle_bin, mock_cli, tmp_path / "a", bam, ["--by", str(bed), "-T", "1,10,20,30", "-m", "-n", "-q", "0:1:10:30:"])
+    compare(oracle_bin, mock_cli, tmp_path / "b", bam, ["--by", str(bed), "-n"], gz=True)
