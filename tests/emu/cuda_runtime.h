@@ -1,0 +1,79 @@
+// tests/emu/cuda_runtime.h -- stand-in for <cuda_runtime.h> when the kernels of mosdepth_b200/csrc are compiled by g++ for the CPU
+// emulation test (tests/emu/bedgz_emu.cpp): CUDA's execution model for the few features K10's kernels use, on host threads.
+//   * a launch runs its CTAs one after the other; the threads of a CTA are real host threads;
+//   * __syncthreads is a barrier over the CTA, warp collectives (full mask only) go through a per-warp exchange buffer and barrier;
+//   * __shared__ variables are function-local statics (one CTA at a time, so one copy is the CTA's copy);
+//   * atomicOr is a real atomic, so the concurrent ORs of neighbouring lines are exercised as on the device.
+// TEST INFRASTRUCTURE ONLY.  It checks indexing, barriers and launch geometry -- not performance, not the memory model.
+#pragma once
+#include <atomic>
+#include <barrier>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __CUDA_ARCH__ 1000            // take the device branches of the MSD_HD functions (atomicOr, __clz)
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+typedef int cudaError_t;
+struct uint4 { uint32_t x, y, z, w; };
+
+namespace emu {
+struct Dim { unsigned x = 1, y = 1, z = 1; };
+inline thread_local Dim t_thread;
+inline Dim g_block, g_grid, g_bdim;
+struct Warp { uint64_t slot[32]; std::unique_ptr<std::barrier<>> bar; };
+inline std::vector<Warp> g_warps;
+inline std::unique_ptr<std::barrier<>> g_cta_bar;
+inline Warp& warp() { return g_warps[t_thread.x >> 5]; }
+inline unsigned lane() { return t_thread.x & 31u; }
+
+template <class F> void launch(unsigned grid, unsigned block, F body) {
+    g_grid.x = grid; g_bdim.x = block;
+    const unsigned nw = (block + 31) / 32;
+    for (unsigned b = 0; b < grid; b++) {
+        g_block.x = b;
+        g_warps.clear(); g_warps.resize(nw);
+        for (unsigned w = 0; w < nw; w++) g_warps[w].bar = std::make_unique<std::barrier<>>((std::ptrdiff_t)std::min(32u, block - 32 * w));
+        g_cta_bar = std::make_unique<std::barrier<>>((std::ptrdiff_t)block);
+        std::vector<std::thread> ts;
+        for (unsigned t = 0; t < block; t++) ts.emplace_back([&, t]() { t_thread.x = t; body(); g_cta_bar->arrive_and_drop(); warp().bar->arrive_and_drop(); });   // exited threads count as arrived
+        for (auto& th : ts) th.join();
+    }
+}
+}  // namespace emu
+
+#define threadIdx (emu::t_thread)
+#define blockIdx (emu::g_block)
+#define blockDim (emu::g_bdim)
+#define gridDim (emu::g_grid)
+
+inline void __syncthreads() { emu::g_cta_bar->arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp().bar->arrive_and_wait(); }
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned o) {
+    emu::Warp& w = emu::warp(); const unsigned l = emu::lane();
+    uint64_t bits = 0; memcpy(&bits, &v, sizeof v); w.slot[l] = bits;
+    w.bar->arrive_and_wait();
+    T r = v; if (l >= o) memcpy(&r, &w.slot[l - o], sizeof r);
+    w.bar->arrive_and_wait();
+    return r;
+}
+inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+    emu::Warp& w = emu::warp(); w.slot[emu::lane()] = v;
+    w.bar->arrive_and_wait();
+    unsigned s = 0; for (int i = 0; i < 32; i++) s += (unsigned)w.slot[i];
+    w.bar->arrive_and_wait();
+    return s;
+}
+inline unsigned atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { sh &= 31; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }

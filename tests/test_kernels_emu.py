@@ -1,0 +1,36 @@
+"""The K8 (runs.cuh) and K10 (bedgz.cuh) KERNELS themselves, compiled by g++ and executed on host threads under a small CUDA
+stand-in (tests/emu/cuda_runtime.h: CTAs one after the other, threads of a CTA as real threads, __syncthreads / warp shuffles as
+barriers, atomicOr as a real atomic), launched in the order and geometry of msd_per_base_bgzf.  From a depth array to BGZF
+members; gunzip must give the printf text of a plain host run-length pass.  This checks indexing, barriers, grid-stride loops and
+the three-launch scans without a GPU; it is not a substitute for the GPU tests (tests/test_gpu_zz_bedgz.py)."""
+import gzip
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    d = tmp_path_factory.mktemp("emu")
+    exe = d / "bedgz_emu"
+    subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", f"-I{ROOT / 'tests' / 'emu'}", "-o", str(exe), str(ROOT / "tests" / "emu" / "bedgz_emu.cpp"), "-lz"], check=True)
+    return exe, d
+
+
+# (contig name, bases, CTA cap of the grid-stride kernels, seed): many scan tiles with few CTAs; the library's own cap; tiny inputs
+CASES = [("chr1", 400000, 7, 2), ("HLA-DRB1*15:01:01:01", 150000, 1184, 3), ("X", 5000, 3, 4), ("MT", 17, 1184, 5), ("c", 1, 1, 6)]
+
+
+@pytest.mark.parametrize("chrom,n_bases,max_ctas,seed", CASES, ids=[f"{c[0][:8]}-{c[1]}-{c[2]}" for c in CASES])
+def test_kernels_under_emulation(emu, chrom, n_bases, max_ctas, seed):
+    exe, d = emu
+    prefix = d / f"e{seed}"
+    r = subprocess.run([str(exe), str(prefix), chrom, str(n_bases), str(max_ctas), str(seed)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr
+    n_dev, n_host, text_bytes, gz_bytes, n_members = (int(v) for v in r.stdout.split())
+    text = (d / f"e{seed}.txt").read_bytes()
+    gz = (d / f"e{seed}.gz").read_bytes()
+    assert n_dev == n_host and len(text) == text_bytes and len(gz) == gz_bytes and n_members >= 1
+    assert gzip.decompress(gz) == text
