@@ -2,7 +2,7 @@
 stand-in (tests/emu/cuda_runtime.h: CTAs one after the other, threads of a CTA as real threads, __syncthreads / warp shuffles as
 barriers, atomicOr as a real atomic), launched in the order and geometry of msd_per_base_bgzf.  From a depth array to BGZF
 members; gunzip must give the printf text of a plain host run-length pass.  This checks indexing, barriers, grid-stride loops and
-the three-launch scans without a GPU; it is not a substitute for the GPU tests (tests/test_gpu_zz_bedgz.py)."""
+the three-launch scans without a GPU; it is not a substitute for the GPU tests (tests/test_gpu_zzz_bedgz.py)."""
 import gzip
 import subprocess
 
