@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--seed", type=int, default=20261022)
     ap.add_argument("--window", type=int, default=500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the side measurement of K10 (per-base.bed.gz on the device), which runs in a process of its own after the timed region")
     ap.add_argument("--sharding", default="offsets", choices=["contigs", "offsets", "intra"],
                     help="N > 1: whole contigs per rank (LPT, no data-path exchange); N equal BGZF offset ranges of the file, cut inside contigs (the depth that reads leave beyond a cut goes to the next rank over NCCL); or every contig cut into N ranges")
     args = ap.parse_args()
@@ -425,6 +426,16 @@ def main():
         cpu_baseline = {"value": n_reads / dt, "unit": "reads/s", "cores": threads + 1, "kind": "port", "seconds": dt,
                         "sample": f"whole bench BAM ({n_reads} reads, genome_fraction={fraction:g}), oracle -t {threads} --by {args.window} -n -x"}
 
+    # side measurement, outside every timed region and in a process of its own (a failure there cannot touch this line):
+    # K10 (msd_per_base_bgzf) against msd_per_base_runs + zlib on a small default-mode BAM, members verified against the runs
+    aux = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_aux:
+        try:
+            r = subprocess.run([sys.executable, str(ROOT / "tools" / "bench_bedgz.py"), "0.004", "2", "--json"], capture_output=True, text=True, timeout=300)
+            aux = {"k10_per_base_bgzf": json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 and r.stdout.strip() else {"error": (r.stderr or r.stdout)[-600:]}}
+        except Exception as e:
+            aux = {"k10_per_base_bgzf": {"error": str(e)}}
+
     if rank == 0:
         line = {"metric": "reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
@@ -437,7 +448,7 @@ def main():
                         "h2d_bytes_per_step": int(infos_e2e[-1].bytes_compressed), "d2h_bytes_per_step": int(d2h["bytes"]),
                         "stage_ms_per_step": {"h2d": infos_e2e[-1].ms_h2d, "inflate": infos_e2e[-1].ms_inflate, "frame": infos_e2e[-1].ms_frame,
                                               "records": infos_e2e[-1].ms_records, "scan": infos_e2e[-1].ms_scan, "run_total": infos_e2e[-1].ms_total}},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "aux": aux}
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     ctx.close()
     if world > 1:
