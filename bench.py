@@ -431,7 +431,7 @@ def main():
     aux = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_aux:
         try:
-            r = subprocess.run([sys.executable, str(ROOT / "tools" / "bench_bedgz.py"), "0.004", "2", "--json"], capture_output=True, text=True, timeout=300)
+            r = subprocess.run([sys.executable, str(ROOT / "tools" / "bench_bedgz.py"), "0.004", "2", "--json"], capture_output=True, text=True, timeout=150)
             aux = {"k10_per_base_bgzf": json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 and r.stdout.strip() else {"error": (r.stderr or r.stdout)[-600:]}}
         except Exception as e:
             aux = {"k10_per_base_bgzf": {"error": str(e)}}
