@@ -170,3 +170,19 @@ int msd_quantized_runs(msd_ctx *ctx, int tid, const int64_t *quants, int nq, con
     *start = g_rs; *stop = g_re; *bin = g_rv; *n_runs = n;
     return MSD_OK;
 }
+
+/* the rest of the ABI: present so that the ctypes binding (mosdepth_b200/__init__.py) loads against the double; not provided */
+int msd_set_contig_range(msd_ctx *c, int t, uint32_t lo, uint32_t hi) { (void)c; (void)t; (void)lo; (void)hi; return fail(MSD_EINVAL, "mock: not provided"); }
+int msd_contig_spill(msd_ctx *c, int t, uint32_t *f, uint32_t *n) { (void)c; (void)t; (void)f; (void)n; return fail(MSD_EINVAL, "mock: not provided"); }
+int msd_depth_copy(msd_ctx *c, int t, uint32_t p, uint32_t n, int32_t *d, int dev) { (void)c; (void)t; (void)p; (void)n; (void)d; (void)dev; return fail(MSD_EINVAL, "mock: not provided"); }
+int msd_depth_add(msd_ctx *c, int t, uint32_t p, uint32_t n, const int32_t *s, int dev) { (void)c; (void)t; (void)p; (void)n; (void)s; (void)dev; return fail(MSD_EINVAL, "mock: not provided"); }
+int msd_contig_finalize(msd_ctx *c, int t) { (void)c; (void)t; return fail(MSD_EINVAL, "mock: not provided"); }
+int msd_totals_device(msd_ctx *c, void **g, void **r, int64_t *n, void **s) { (void)c; (void)g; (void)r; (void)n; (void)s; return fail(MSD_EINVAL, "mock: not provided"); }
+int msd_totals_reset(msd_ctx *c) { (void)c; return MSD_OK; }
+int msd_mark(msd_ctx *c, int slot) { (void)c; (void)slot; return MSD_OK; }
+int msd_elapsed_ms(msd_ctx *c, int a, int b, double *ms) { (void)c; (void)a; (void)b; if (ms) *ms = 0.0; return MSD_OK; }
+uint64_t msd_launch_count(const msd_ctx *c) { (void)c; return 0; }
+int64_t msd_debug_inflate(msd_ctx *c, const void *z, uint64_t n, void *o, uint64_t cap) { (void)c; (void)z; (void)n; (void)o; (void)cap; return fail(MSD_EINVAL, "mock: not provided"); }
+int msd_debug_depth(msd_ctx *c, int t, int32_t *o, int64_t cap) { (void)c; (void)t; (void)o; (void)cap; return fail(MSD_EINVAL, "mock: not provided"); }
+int msd_debug_cumsum(msd_ctx *c, int32_t *a, int64_t n) { (void)c; (void)a; (void)n; return fail(MSD_EINVAL, "mock: not provided"); }
+int64_t msd_debug_crc32(msd_ctx *c, const void *b, uint64_t n, uint32_t bb, uint32_t fo, int reps, uint32_t *out, double *ms) { (void)c; (void)b; (void)n; (void)bb; (void)fo; (void)reps; (void)out; (void)ms; return fail(MSD_EINVAL, "mock: not provided"); }

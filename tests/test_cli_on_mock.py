@@ -20,6 +20,7 @@ def mock_cli(tmp_path_factory):
     subprocess.run(["gcc", "-O2", "-fPIC", "-w", "-c", "-o", str(d / "msd_mock.o"), str(ROOT / "tests" / "mock" / "msd_mock.c")], check=True)
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-w", "-I/usr/local/cuda/include", "-c", "-o", str(d / "msd_mock_bgzf.o"), str(ROOT / "tests" / "mock" / "msd_mock_bgzf.cpp")], check=True)
     subprocess.run(["g++", "-shared", "-o", str(d / "libmosdepth_b200.so"), str(d / "msd_mock.o"), str(d / "msd_mock_bgzf.o"), "-lz", "-lpthread", "-lm"], check=True)
+    (d / "lib_path.txt").write_text(str(d / "libmosdepth_b200.so"))
     exe = d / "mosdepth-b200-mock"
     subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", str(exe), str(ROOT / "mosdepth_b200" / "host" / "main.cpp"), f"-I{ROOT / 'include'}",
                     f"-L{d}", "-lmosdepth_b200", "-lz", f"-Wl,-rpath,{d}"], check=True)
@@ -110,3 +111,26 @@ def test_exome_bed_median_thresholds_quantize_on_mock(oracle_bin, mock_cli, tmp_
     (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
     compare(oracle_bin, mock_cli, tmp_path / "a", bam, ["--by", str(bed), "-T", "1,10,20,30", "-m", "-n", "-q", "0:1:10:30:"])
     compare(oracle_bin, mock_cli, tmp_path / "b", bam, ["--by", str(bed), "-n"], gz=True)
+
+
+def test_python_binding_of_per_base_bgzf_on_mock(mock_cli, fixtures):
+    """The ctypes binding (mosdepth_b200.Context.per_base_bgzf: pointer-to-pointer outputs, the msd_bgzf_member layout) against the
+    double, in a process of its own whose LIB_PATH points at it: members parse, gunzip to the text of the runs, offsets chain."""
+    lib = mock_cli.parent / "libmosdepth_b200.so"
+    for name in ("nanopore.bam", "empty-tids.bam"):
+        r = subprocess.run([os.sys.executable, str(ROOT / "tests" / "mock" / "binding_check.py"), str(lib), str(fixtures / name)], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.startswith("ok"), r.stderr
+
+
+def test_bench_bedgz_script_on_mock(mock_cli, tmp_path):
+    """tools/bench_bedgz.py (the K10 side measurement bench.py runs in a process of its own) end to end against the double:
+    its JSON line parses and every contig's members were verified against the runs."""
+    import json
+    lib = mock_cli.parent / "libmosdepth_b200.so"
+    script = ROOT / "tools" / "bench_bedgz.py"
+    code = ("import sys; sys.path.insert(0, %r); import mosdepth_b200 as m; from pathlib import Path; m.LIB_PATH = Path(%r); m._lib = None; "
+            "sys.argv = [%r, '0.0003', '1', '--json']; __file__ = %r; exec(compile(open(%r).read(), %r, 'exec'))") % (str(ROOT), str(lib), str(script), str(script), str(script), str(script))
+    r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, env={**os.environ, "MSD_BENCH_DIR": str(tmp_path)})
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["contigs"] >= 20 and out["verified_contigs"] == out["contigs"] and out["lines"] > 10000 and 0 < out["dev_bytes"] < out["text"]
