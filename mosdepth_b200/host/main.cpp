@@ -56,12 +56,15 @@ static Header read_header(const std::string& path) {
             uint32_t xlen = h[10] | (h[11] << 8);
             std::vector<uint8_t> extra(xlen); memcpy(extra.data(), h + 12, std::min<uint32_t>(xlen, 6)); if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, f) != xlen - 6) die(1, "truncated");
             uint32_t bsize = 0; for (uint32_t q = 0; q + 4 <= xlen;) { uint32_t sl = extra[q + 2] | (extra[q + 3] << 8); if (extra[q] == 66 && extra[q + 1] == 67 && sl == 2) bsize = extra[q + 4] | (extra[q + 5] << 8); q += 4 + sl; }
-            uint32_t blen = bsize + 1, clen = blen - xlen - 20;
+            uint32_t blen = bsize + 1;
+            if (xlen < 6 || blen < xlen + 20 + 2) die(1, "[mosdepth] %s: invalid BGZF block in the header", path.c_str());
+            uint32_t clen = blen - xlen - 20;
             std::vector<uint8_t> c(clen + 8); if (fread(c.data(), 1, clen + 8, f) != clen + 8) die(1, "[mosdepth] truncated BAM header");
             uint32_t isz; memcpy(&isz, c.data() + clen + 4, 4);
+            if (isz > 65536) die(1, "[mosdepth] %s: invalid BGZF block in the header", path.c_str());
             std::vector<uint8_t> o(isz ? isz : 1);
             z_stream zs; memset(&zs, 0, sizeof zs); inflateInit2(&zs, -15); zs.next_in = c.data(); zs.avail_in = clen; zs.next_out = o.data(); zs.avail_out = isz;
-            int r = inflate(&zs, Z_FINISH); inflateEnd(&zs); if (r != Z_STREAM_END) die(1, "[mosdepth] corrupt BAM header block");
+            int r = inflate(&zs, Z_FINISH); const bool whole = zs.total_out == isz; inflateEnd(&zs); if (r != Z_STREAM_END || !whole) die(1, "[mosdepth] corrupt BAM header block");
             starts.push_back({inflated.size(), coff}); isizes.push_back(isz);
             inflated.insert(inflated.end(), o.begin(), o.begin() + isz); coff += blen;
         }
@@ -69,11 +72,16 @@ static Header read_header(const std::string& path) {
     };
     need(12);
     if (memcmp(inflated.data(), "BAM\1", 4)) die(1, "[mosdepth] %s is not a BAM file", path.c_str());
-    int32_t l_text; memcpy(&l_text, inflated.data() + 4, 4); need(12 + (size_t)l_text);
+    int32_t l_text; memcpy(&l_text, inflated.data() + 4, 4);
+    if (l_text < 0) die(1, "[mosdepth] %s: corrupt BAM header", path.c_str());
+    need(12 + (size_t)l_text);
     size_t off = 8 + (size_t)l_text; int32_t n_ref; memcpy(&n_ref, inflated.data() + off, 4); off += 4;
+    if (n_ref < 0) die(1, "[mosdepth] %s: corrupt BAM header", path.c_str());
     Header H;
     for (int i = 0; i < n_ref; i++) {
-        need(off + 4); int32_t l_name; memcpy(&l_name, inflated.data() + off, 4); need(off + 8 + (size_t)l_name);
+        need(off + 4); int32_t l_name; memcpy(&l_name, inflated.data() + off, 4);
+        if (l_name < 1 || l_name > (1 << 20)) die(1, "[mosdepth] %s: corrupt BAM header", path.c_str());
+        need(off + 8 + (size_t)l_name);
         Target t; t.name.assign((const char*)inflated.data() + off + 4, (size_t)l_name - 1); int32_t l; memcpy(&l, inflated.data() + off + 4 + l_name, 4); t.length = (uint32_t)l;
         H.targets.push_back(t); off += 8 + (size_t)l_name;
     }
@@ -100,17 +108,25 @@ static bool load_index(const std::string& bam, std::vector<ContigIndex>& out) {
     std::string p; bool csi = false;
     if (file_exists(bam + ".csi")) { p = bam + ".csi"; csi = true; } else if (file_exists(bam + ".bai")) p = bam + ".bai";
     else if (bam.size() > 4 && file_exists(bam.substr(0, bam.size() - 4) + ".bai")) p = bam.substr(0, bam.size() - 4) + ".bai"; else return false;
-    std::vector<uint8_t> d = gunzip_all(read_file(p, true)); size_t q = 4; uint32_t pseudo = 37450;
-    if (csi) { int32_t depth, l_aux; memcpy(&depth, d.data() + 8, 4); memcpy(&l_aux, d.data() + 12, 4); q = 16 + (size_t)l_aux; pseudo = (uint32_t)(((1u << ((depth + 1) * 3)) - 1) / 7 + 1); }
-    int32_t n_ref; memcpy(&n_ref, d.data() + q, 4); q += 4; out.assign((size_t)n_ref, ContigIndex());
+    const std::vector<uint8_t> d = gunzip_all(read_file(p, true)); size_t q = 0; uint32_t pseudo = 37450;
+    // every read is bounds-checked: a truncated or corrupt index ends the run with a message, like hts_idx_load failing (:969-971)
+    auto need = [&](size_t n) { if (n > d.size() - std::min(q, d.size())) die(1, "[mosdepth] %s: truncated or corrupt index", p.c_str()); };
+    auto i32 = [&]() { need(4); int32_t v; memcpy(&v, d.data() + q, 4); q += 4; return v; };
+    auto u64 = [&]() { need(8); uint64_t v; memcpy(&v, d.data() + q, 8); q += 8; return v; };
+    auto count = [&](size_t item_bytes) { const int32_t v = i32(); if (v < 0 || (uint64_t)v * item_bytes > d.size() - q) die(1, "[mosdepth] %s: truncated or corrupt index", p.c_str()); return v; };
+    need(4);
+    if (memcmp(d.data(), csi ? "CSI\1" : "BAI\1", 4)) die(1, "[mosdepth] %s: not a %s index", p.c_str(), csi ? "CSI" : "BAI");
+    q = 4;
+    if (csi) { i32(); const int32_t depth = i32(), l_aux = i32(); if (depth < 0 || depth > 9 || l_aux < 0) die(1, "[mosdepth] %s: truncated or corrupt index", p.c_str()); need((size_t)l_aux); q += (size_t)l_aux; pseudo = (uint32_t)(((1u << ((depth + 1) * 3)) - 1) / 7 + 1); }
+    const int32_t n_ref = count(4); out.assign((size_t)n_ref, ContigIndex());
     for (int r = 0; r < n_ref; r++) {
-        int32_t n_bin; memcpy(&n_bin, d.data() + q, 4); q += 4; uint64_t mn = UINT64_MAX, mx = 0;
+        const int32_t n_bin = count(csi ? 16 : 8); uint64_t mn = UINT64_MAX, mx = 0;
         for (int b = 0; b < n_bin; b++) {
-            uint32_t bin; memcpy(&bin, d.data() + q, 4); q += 4; if (csi) q += 8;
-            int32_t nc; memcpy(&nc, d.data() + q, 4); q += 4;
-            for (int c = 0; c < nc; c++) { uint64_t cb, ce; memcpy(&cb, d.data() + q, 8); memcpy(&ce, d.data() + q + 8, 8); q += 16; if (bin != pseudo) { mn = std::min(mn, cb); mx = std::max(mx, ce); } }
+            const uint32_t bin = (uint32_t)i32(); if (csi) u64();
+            const int32_t nc = count(16);
+            for (int c = 0; c < nc; c++) { const uint64_t cb = u64(), ce = u64(); if (bin != pseudo) { mn = std::min(mn, cb); mx = std::max(mx, ce); } }
         }
-        if (!csi) { int32_t ni; memcpy(&ni, d.data() + q, 4); q += 4 + 8 * (size_t)ni; }
+        if (!csi) { const int32_t ni = count(8); q += 8 * (size_t)ni; }
         if (mn != UINT64_MAX) { out[r].has = true; out[r].beg = mn; out[r].end = mx; }
     }
     return true;

@@ -134,3 +134,41 @@ def test_bench_bedgz_script_on_mock(mock_cli, tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["contigs"] >= 20 and out["verified_contigs"] == out["contigs"] and out["lines"] > 10000 and 0 < out["dev_bytes"] < out["text"]
+
+
+def test_truncated_or_corrupt_header_and_index_end_with_a_message(mock_cli, fixtures, tmp_path):
+    """The host's BAM-header and BAI/CSI parsers are bounds-checked: a cut or damaged file ends the run with `[mosdepth] ...` and
+    exit code 1 (found with an ASan build of this CLI: the unchecked parser read past a truncated .bai), never with a signal."""
+    import random
+    import shutil
+    rng = random.Random(3)
+    for name, ext in (("ovl.bam", ".bai"), ("big.bam", ".csi")):
+        bam = (fixtures / name).read_bytes(); idx = (fixtures / (name + ext)).read_bytes()
+        raw_idx = gzip.decompress(idx) if ext == ".csi" else idx
+        t = tmp_path / "t.bam"
+        for f in (tmp_path / "t.bam.bai", tmp_path / "t.bam.csi"):
+            f.unlink(missing_ok=True)
+        t.write_bytes(bam)
+        for cut in (0, 3, 4, 8, 12, 16, 20, 40, 100, len(raw_idx) - 20):      # (the last 8 bytes, n_no_coor, are optional)
+            (tmp_path / ("t.bam" + ext)).write_bytes(raw_idx[:cut])
+            r = run_tool(mock_cli, ["--plain", "-n", "--by", "100000", "x", t], tmp_path, check=False)
+            assert r.returncode == 1 and "[mosdepth]" in r.stderr, (name, cut, r.returncode, r.stderr[-300:])
+        for k in range(25 if name == "ovl.bam" else 5):      # (big.bam: a 600 Mb contig, every successful run fills a 2.4 GB array)
+            b = bytearray(raw_idx)
+            for _ in range(3):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+            (tmp_path / ("t.bam" + ext)).write_bytes(bytes(b))
+            r = run_tool(mock_cli, ["--plain", "-n", "--by", "100000", "x", t], tmp_path, check=False)
+            assert r.returncode in (0, 1), (name, k, r.returncode, r.stderr[-300:])
+        (tmp_path / ("t.bam" + ext)).write_bytes(idx)
+        for cut in (0, 10, 17, 18, 30, 100, 500):
+            t.write_bytes(bam[:cut])
+            r = run_tool(mock_cli, ["--plain", "-n", "--by", "100000", "x", t], tmp_path, check=False)
+            assert r.returncode == 1 and r.stderr.strip() if cut < 100 else r.returncode in (0, 1), (name, cut, r.returncode)
+        for k in range(20 if name == "ovl.bam" else 4):
+            b = bytearray(bam)
+            for _ in range(2):
+                b[rng.randrange(min(len(b), 400))] = rng.randrange(256)
+            t.write_bytes(bytes(b))
+            r = run_tool(mock_cli, ["--plain", "-n", "--by", "100000", "x", t], tmp_path, check=False)
+            assert r.returncode in (0, 1, 2), (name, k, r.returncode, r.stderr[-300:])
