@@ -158,7 +158,7 @@ uint32_t bgzf_header(const uint8_t* f, uint64_t n, uint64_t pos, uint32_t* xlen_
     if (pos + 12 + xlen > n) return 0;
     while (q + 4 <= 12 + xlen) {
         uint32_t slen = h[q + 2] | (h[q + 3] << 8);
-        if (h[q] == 66 && h[q + 1] == 67 && slen == 2) { bsize = h[q + 4] | (h[q + 5] << 8); have = true; }
+        if (h[q] == 66 && h[q + 1] == 67 && slen == 2 && q + 6 <= 12 + xlen) { bsize = h[q + 4] | (h[q + 5] << 8); have = true; }
         q += 4 + slen;
     }
     if (!have) return 0;
