@@ -23,7 +23,7 @@
 #include "regions.cuh"
 #include "runs.cuh"
 #include "scan.cuh"
-#include "bedgz.cuh"
+#include "bedgz_host.cuh"
 #include "ingest.hpp"
 
 using namespace msd;
@@ -102,8 +102,7 @@ struct msd_ctx {
     int32_t *d_run_start = nullptr, *d_run_stop = nullptr, *d_run_val = nullptr; uint64_t d_run_cap = 0;
     uint32_t* d_tile_count = nullptr; unsigned long long* d_tile_base = nullptr; uint64_t run_tile_cap = 0; unsigned long long* d_run_total = nullptr;
     // K10 (msd_per_base_bgzf): grow-only buffers (per line, per member + text, output) and the pinned copy of the output
-    void *d_bz_line = nullptr, *d_bz_blk = nullptr, *d_bz_out = nullptr; uint64_t bz_line_cap = 0, bz_blk_cap = 0, bz_out_cap = 0;
-    uint8_t* h_bz_out = nullptr; uint64_t h_bz_cap = 0; std::vector<msd_bgzf_member> bz_members;
+    BzBuffers bz;
     // generic scratch
     void* d_scratch = nullptr; uint64_t scratch_cap = 0;
     // msd_prefetch_windows: every contig's windows computed by one launch at the end of msd_run, results cached on the host
@@ -441,27 +440,6 @@ static int compute_runs(msd_ctx* ctx, const int32_t* arr, uint32_t n, int32_t en
 }
 
 
-// ---- K10: per-base.bed.gz on the device (bedgz.cuh) ---------------------------------------------------------------------
-int bz_grow(msd_ctx* ctx, void** p, uint64_t* cap, uint64_t bytes) {
-    if (bytes <= *cap) return 0;
-    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
-    bytes += bytes / 8 + 4096;
-    cudaError_t e = cudaMalloc(p, bytes);
-    if (e != cudaSuccess) return ctx_fail(ctx, MSD_ECUDA, "cudaMalloc(%llu bytes) for msd_per_base_bgzf: %s", (unsigned long long)bytes, cudaGetErrorString(e));
-    *cap = bytes;
-    return 0;
-}
-// carves 256-byte aligned pieces out of one allocation
-struct BzCarve { uint8_t* base; uint64_t used = 0; template <class T> T* take(uint64_t n) { T* r = base ? reinterpret_cast<T*>(base + used) : nullptr; used += (n * sizeof(T) + 255) & ~255ull; return r; } };
-
-// exclusive scan uint32 -> uint64 (+ total) in three launches
-void bz_scan(cudaStream_t s, const uint32_t* in, uint64_t n, uint32_t* tile_sum, unsigned long long* tile_base, unsigned long long* total, unsigned long long* out) {
-    const uint32_t nt = (uint32_t)((n + kBzScanTile - 1) / kBzScanTile);
-    bz_tile_sum_kernel<<<nt, kBzThreads, 0, s>>>(in, n, tile_sum);
-    runs_scan_kernel<<<1, 1024, 0, s>>>(tile_sum, nt, tile_base, total);
-    bz_tile_scan_kernel<<<nt, kBzThreads, 0, s>>>(in, n, tile_base, out);
-}
-
 }  // namespace
 
 extern "C" {
@@ -522,8 +500,7 @@ void msd_destroy(msd_ctx* ctx) {
     if (ctx->h_run_stop) cudaFreeHost(ctx->h_run_stop);
     if (ctx->h_run_val) cudaFreeHost(ctx->h_run_val);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
-    if (ctx->d_bz_line) cudaFree(ctx->d_bz_line); if (ctx->d_bz_blk) cudaFree(ctx->d_bz_blk); if (ctx->d_bz_out) cudaFree(ctx->d_bz_out);
-    if (ctx->h_bz_out) cudaFreeHost(ctx->h_bz_out);
+    bz_release(ctx->bz);
     dev_free(&ctx->d_acc_all); if (ctx->h_acc_all) cudaFreeHost(ctx->h_acc_all); if (ctx->h_hist_keep) cudaFreeHost(ctx->h_hist_keep);
     dev_free(&ctx->d_pf_values); dev_free(&ctx->d_pf_acc); dev_free(&ctx->d_pf_dist); dev_free(&ctx->d_pf_table);
     if (ctx->h_pf_values) cudaFreeHost(ctx->h_pf_values); if (ctx->h_pf_acc) cudaFreeHost(ctx->h_pf_acc); if (ctx->h_pf_dist) cudaFreeHost(ctx->h_pf_dist); if (ctx->h_pf_table) cudaFreeHost(ctx->h_pf_table);
@@ -1223,105 +1200,19 @@ int msd_per_base_bgzf(msd_ctx* ctx, int tid, const char* chrom, const uint8_t** 
     if ((rc = ensure_query_buffers(ctx))) return rc;
     const uint32_t tlen = ctx->tlen[tid];
     uint64_t n = 0;
-    if ((rc = compute_runs(ctx, ctx->d_arena + ctx->depth_off[tid], tlen, (int32_t)tlen, IdentityF(), &n))) return rc;   // runs on the device and in pinned memory
+    if ((rc = compute_runs(ctx, ctx->d_arena + ctx->depth_off[tid], tlen, (int32_t)tlen, IdentityF(), &n))) return rc;   // K8: runs on the device and in pinned memory
     if (start) *start = ctx->h_run_start; if (stop) *stop = ctx->h_run_stop; if (depth) *depth = ctx->h_run_val;
     if (n_runs) *n_runs = (int64_t)n;
-    ctx->bz_members.clear();
     *bgzf = nullptr; *n_bytes = 0; *members = nullptr; *n_members = 0;
+    // K10: the sequence lives in bedgz_host.cuh (the same code runs under the CPU emulation test); the CRC step is K1c
+    rc = bz_run(ctx->bz, ctx->s_compute, chrom, ctx->d_run_start, ctx->d_run_stop, ctx->d_run_val, ctx->h_run_start, ctx->h_run_stop, ctx->h_run_val, n, kSMs * 8,
+                [](cudaStream_t s, const uint8_t* d_text, const BlockDesc* d_desc, int nb, uint32_t* ticket, const uint32_t* expected, uint32_t* status, uint32_t* errors, uint32_t* crc_out) {
+                    launch_crc(s, d_text, d_desc, nb, ticket, expected, status, errors, crc_out);
+                });
+    ctx->launches += ctx->bz.launches;
+    if (rc) return ctx_fail(ctx, rc, "%s", ctx->bz.err);
     if (n == 0) return MSD_OK;
-    cudaStream_t sc = ctx->s_compute;
-    // the contig's Huffman code, from a sample of its own lines (host: 65,536 lines at most)
-    static_assert(sizeof(BzCodes) % 4 == 0, "BzCodes is copied as words");
-    BzCodes codes;
-    if (!bz_build_codes(chrom, ctx->h_run_start, ctx->h_run_stop, ctx->h_run_val, n, &codes)) return ctx_fail(ctx, MSD_EINVAL, "msd_per_base_bgzf: cannot build a code for contig '%s'", chrom);
-    // ---- per line: text length -> text offset ------------------------------------------------------------------------
-    const uint64_t n_tiles = (n + kBzScanTile - 1) / kBzScanTile;
-    BzCarve lay{nullptr};                          // first walk (null base) measures, second carves
-    lay.take<BzCodes>(1); lay.take<uint32_t>(n); lay.take<unsigned long long>(n); lay.take<uint32_t>(n); lay.take<unsigned long long>(n);
-    lay.take<uint32_t>(n_tiles); lay.take<unsigned long long>(n_tiles); lay.take<unsigned long long>(4);
-    if ((rc = bz_grow(ctx, &ctx->d_bz_line, &ctx->bz_line_cap, lay.used))) return rc;
-    lay.base = (uint8_t*)ctx->d_bz_line; lay.used = 0;
-    BzCodes* d_codes = lay.take<BzCodes>(1);
-    uint32_t* d_text_len = lay.take<uint32_t>(n); unsigned long long* d_text_off = lay.take<unsigned long long>(n);
-    uint32_t* d_bit_len = lay.take<uint32_t>(n); unsigned long long* d_bit_off = lay.take<unsigned long long>(n);
-    uint32_t* d_tsum = lay.take<uint32_t>(n_tiles); unsigned long long* d_tbase = lay.take<unsigned long long>(n_tiles);
-    unsigned long long* d_totals = lay.take<unsigned long long>(4);      // text bytes, bits, output bytes
-    MSD_CUDA_OK(cudaMemcpyAsync(d_codes, &codes, sizeof codes, cudaMemcpyHostToDevice, sc));
-    const int g_lines = grid_for(n, kBzThreads, kSMs * 8);
-    bz_len_kernel<<<g_lines, kBzThreads, 0, sc>>>(d_codes, ctx->d_run_start, ctx->d_run_stop, ctx->d_run_val, n, d_text_len);
-    bz_scan(sc, d_text_len, n, d_tsum, d_tbase, d_totals + 0, d_text_off);
-    ctx->launches += 4;
-    unsigned long long text_total = 0, last_off = 0;
-    MSD_CUDA_OK(cudaGetLastError());
-    MSD_CUDA_OK(cudaMemcpyAsync(&text_total, d_totals + 0, 8, cudaMemcpyDeviceToHost, sc));
-    MSD_CUDA_OK(cudaMemcpyAsync(&last_off, d_text_off + (n - 1), 8, cudaMemcpyDeviceToHost, sc));
-    MSD_CUDA_OK(cudaStreamSynchronize(sc));
-    const uint64_t nb = (uint64_t)bz_block_of(last_off) + 1;
-    if (text_total == 0 || last_off >= text_total || nb > (1ull << 30)) return ctx_fail(ctx, MSD_ECUDA, "msd_per_base_bgzf: text scan out of range (%llu bytes, last line at %llu)", text_total, last_off);
-    // ---- per member: first line, text range, payload bytes -> member offset -----------------------------------------------
-    const uint64_t nb_tiles = (nb + kBzScanTile - 1) / kBzScanTile;
-    BzCarve lb{nullptr};
-    lb.take<unsigned long long>(nb); lb.take<BlockDesc>(nb); lb.take<uint32_t>(nb); lb.take<uint32_t>(nb); lb.take<unsigned long long>(nb);
-    lb.take<uint32_t>(nb); lb.take<uint32_t>(nb); lb.take<uint32_t>(nb); lb.take<uint32_t>(nb_tiles); lb.take<unsigned long long>(nb_tiles); lb.take<uint32_t>(4);
-    lb.take<uint8_t>(text_total + 512);
-    if ((rc = bz_grow(ctx, &ctx->d_bz_blk, &ctx->bz_blk_cap, lb.used))) return rc;
-    lb.base = (uint8_t*)ctx->d_bz_blk; lb.used = 0;
-    unsigned long long* d_blk_first = lb.take<unsigned long long>(nb); BlockDesc* d_desc = lb.take<BlockDesc>(nb);
-    uint32_t* d_payload = lb.take<uint32_t>(nb); uint32_t* d_member_len = lb.take<uint32_t>(nb); unsigned long long* d_member_off = lb.take<unsigned long long>(nb);
-    uint32_t* d_crc = lb.take<uint32_t>(nb); uint32_t* d_crc_expected = lb.take<uint32_t>(nb); uint32_t* d_status = lb.take<uint32_t>(nb);
-    uint32_t* d_btsum = lb.take<uint32_t>(nb_tiles); unsigned long long* d_btbase = lb.take<unsigned long long>(nb_tiles); uint32_t* d_ticket = lb.take<uint32_t>(4);
-    uint8_t* d_text = lb.take<uint8_t>(text_total + 512);
-    MSD_CUDA_OK(cudaMemsetAsync(d_blk_first, 0xff, 8 * nb, sc));
-    bz_mark_kernel<<<g_lines, kBzThreads, 0, sc>>>(d_codes, ctx->d_run_start, ctx->d_run_stop, ctx->d_run_val, n, d_text_off, d_bit_len, d_blk_first);
-    bz_scan(sc, d_bit_len, n, d_tsum, d_tbase, d_totals + 1, d_bit_off);
-    unsigned long long bit_total = 0;
-    MSD_CUDA_OK(cudaMemcpyAsync(&bit_total, d_totals + 1, 8, cudaMemcpyDeviceToHost, sc));
-    MSD_CUDA_OK(cudaStreamSynchronize(sc));          // bz_blocks_kernel takes the totals by value
-    bz_blocks_kernel<<<(unsigned)((nb + kBzThreads - 1) / kBzThreads), kBzThreads, 0, sc>>>(d_codes, (uint32_t)nb, n, d_blk_first, d_text_off, text_total, d_bit_off, bit_total,
-                                                                                        d_desc, d_payload, d_member_len);
-    bz_scan(sc, d_member_len, nb, d_btsum, d_btbase, d_totals + 2, d_member_off);
-    ctx->launches += 8;
-    unsigned long long out_total = 0;
-    MSD_CUDA_OK(cudaGetLastError());
-    MSD_CUDA_OK(cudaMemcpyAsync(&out_total, d_totals + 2, 8, cudaMemcpyDeviceToHost, sc));
-    MSD_CUDA_OK(cudaStreamSynchronize(sc));
-    if (out_total < 27 * nb || out_total > 65536ull * nb) return ctx_fail(ctx, MSD_ECUDA, "msd_per_base_bgzf: member sizes out of range (%llu bytes in %llu members)", out_total, (unsigned long long)nb);
-    // ---- output: zeroed, lines OR their bits in, K1c sums the text, members get their frames ------------------------------
-    if ((rc = bz_grow(ctx, &ctx->d_bz_out, &ctx->bz_out_cap, out_total + 64))) return rc;
-    if (out_total + 64 > ctx->h_bz_cap) {
-        if (ctx->h_bz_out) { cudaFreeHost(ctx->h_bz_out); ctx->h_bz_out = nullptr; ctx->h_bz_cap = 0; }
-        const uint64_t cap = out_total + out_total / 8 + 4096;
-        MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_bz_out, cap));
-        ctx->h_bz_cap = cap;
-    }
-    uint8_t* d_out = (uint8_t*)ctx->d_bz_out;
-    MSD_CUDA_OK(cudaMemsetAsync(d_out, 0, out_total + 64, sc));
-    MSD_CUDA_OK(cudaMemsetAsync(d_text + text_total, 0, 512, sc));            // K1c reads whole 16-byte words
-    MSD_CUDA_OK(cudaMemsetAsync(d_crc_expected, 0, 4 * nb, sc)); MSD_CUDA_OK(cudaMemsetAsync(d_status, 0, 4 * nb, sc)); MSD_CUDA_OK(cudaMemsetAsync(d_ticket, 0, 16, sc));
-    bz_emit_kernel<<<g_lines, kBzThreads, 0, sc>>>(d_codes, ctx->d_run_start, ctx->d_run_stop, ctx->d_run_val, n, d_text_off, d_bit_off, d_blk_first, d_member_off, d_text,
-                                                  reinterpret_cast<uint32_t*>(d_out));
-    launch_crc(sc, d_text, d_desc, (int)nb, d_ticket, d_crc_expected, d_status, d_ticket + 1, d_crc);      // expected = 0: the status words are scratch here
-    bz_frame_kernel<<<(unsigned)((nb + kBzThreads - 1) / kBzThreads), kBzThreads, 0, sc>>>(d_codes, (uint32_t)nb, d_desc, d_payload, d_member_off, d_crc, d_out);
-    ctx->launches += 3;
-    MSD_CUDA_OK(cudaGetLastError());
-    std::vector<unsigned long long> h_first(nb), h_off(nb); std::vector<uint32_t> h_len(nb); std::vector<BlockDesc> h_desc(nb);
-    MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_bz_out, d_out, out_total, cudaMemcpyDeviceToHost, sc));
-    MSD_CUDA_OK(cudaMemcpyAsync(h_first.data(), d_blk_first, 8 * nb, cudaMemcpyDeviceToHost, sc));
-    MSD_CUDA_OK(cudaMemcpyAsync(h_off.data(), d_member_off, 8 * nb, cudaMemcpyDeviceToHost, sc));
-    MSD_CUDA_OK(cudaMemcpyAsync(h_len.data(), d_member_len, 4 * nb, cudaMemcpyDeviceToHost, sc));
-    MSD_CUDA_OK(cudaMemcpyAsync(h_desc.data(), d_desc, sizeof(BlockDesc) * nb, cudaMemcpyDeviceToHost, sc));
-    MSD_CUDA_OK(cudaStreamSynchronize(sc));
-    ctx->bz_members.resize(nb);
-    for (uint64_t b = 0; b < nb; b++) {
-        msd_bgzf_member& m = ctx->bz_members[b];
-        m.offset = h_off[b]; m.first_run = h_first[b]; m.csize = h_len[b]; m.isize = h_desc[b].isize;
-        const uint64_t next_first = b + 1 < nb ? h_first[b + 1] : n;
-        if (m.csize > 65536 || m.csize < 27 || m.isize == 0 || m.isize > kBzMaxBlockText || m.first_run >= next_first || (b == 0 && m.first_run != 0) ||
-            m.offset + m.csize != (b + 1 < nb ? h_off[b + 1] : out_total))
-            return ctx_fail(ctx, MSD_ECUDA, "msd_per_base_bgzf: member %llu of %llu is inconsistent (offset %llu, %u -> %u bytes, first run %llu)", (unsigned long long)b,
-                            (unsigned long long)nb, (unsigned long long)m.offset, m.isize, m.csize, (unsigned long long)m.first_run);
-    }
-    *bgzf = ctx->h_bz_out; *n_bytes = (int64_t)out_total; *members = ctx->bz_members.data(); *n_members = (int64_t)nb;
+    *bgzf = ctx->bz.h_out; *n_bytes = (int64_t)ctx->bz.out_bytes; *members = ctx->bz.members.data(); *n_members = (int64_t)ctx->bz.members.size();
     return MSD_OK;
 }
 
