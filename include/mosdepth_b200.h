@@ -173,6 +173,15 @@ int msd_per_base_bgzf(msd_ctx *ctx, int tid, const char *chrom, const uint8_t **
 int msd_quantized_runs(msd_ctx *ctx, int tid, const int64_t *quants, int n_q, const int32_t **start,
                        const int32_t **stop, const int32_t **bin, int64_t *n_runs);
 
+/* quantized.bed.gz the same way: msd_quantized_runs() followed by the formatting (`chrom \t start \t stop \t labels[bin] \n`,
+ * mosdepth.nim:802-805) and BGZF compression of its lines on the device.  labels: the host's make_lookup() strings (:111-122),
+ * n_labels >= n_q - 1, each at most 48 bytes (MSD_EINVAL beyond).  Outputs as for msd_per_base_bgzf(); the runs are those of
+ * msd_quantized_runs(). */
+int msd_quantized_bgzf(msd_ctx *ctx, int tid, const int64_t *quants, int n_q, const char *chrom, const char *const *labels,
+                       int n_labels, const uint8_t **bgzf, int64_t *n_bytes, const msd_bgzf_member **members,
+                       int64_t *n_members, const int32_t **start, const int32_t **stop, const int32_t **bin,
+                       int64_t *n_runs);
+
 /* -- multi-GPU plumbing ---------------------------------------------------------------------------------- *
  * Device pointer + element count of this context's genome-wide accumulators, kept up to date by
  * msd_contig_stats / msd_windows / msd_regions (sum_into, mosdepth.nim:761-764): int64 global dist bins,

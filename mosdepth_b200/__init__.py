@@ -22,7 +22,7 @@ MODE_DEFAULT, MODE_FAST, MODE_FRAGMENT = 0, 1, 2
 EXPORTS = [
     "msd_abi_version", "msd_create", "msd_destroy", "msd_last_error", "msd_open", "msd_open_mem", "msd_stage",
     "msd_set_spans", "msd_set_targets", "msd_set_filters", "msd_run", "msd_last_run_info", "msd_contig_records",
-    "msd_contig_stats", "msd_n_windows", "msd_prefetch_windows", "msd_windows", "msd_regions", "msd_per_base_runs", "msd_per_base_bgzf", "msd_quantized_runs",
+    "msd_contig_stats", "msd_n_windows", "msd_prefetch_windows", "msd_windows", "msd_regions", "msd_per_base_runs", "msd_per_base_bgzf", "msd_quantized_runs", "msd_quantized_bgzf",
     "msd_set_contig_range", "msd_contig_spill", "msd_depth_copy", "msd_depth_add", "msd_contig_finalize",
     "msd_totals_device", "msd_totals_reset", "msd_mark", "msd_elapsed_ms", "msd_launch_count", "msd_debug_inflate", "msd_debug_depth", "msd_debug_cumsum", "msd_debug_crc32",
 ]
@@ -86,6 +86,7 @@ def load_library():
     lib.msd_regions.argtypes = [p, i32, i64, p, p, i32, p, C.POINTER(DepthStat), p, i64, C.POINTER(i64), p, i32, p]
     lib.msd_per_base_runs.argtypes = [p, i32, C.POINTER(p), C.POINTER(p), C.POINTER(p), C.POINTER(i64)]
     lib.msd_per_base_bgzf.argtypes = [p, i32, C.c_char_p, C.POINTER(p), C.POINTER(i64), C.POINTER(p), C.POINTER(i64), C.POINTER(p), C.POINTER(p), C.POINTER(p), C.POINTER(i64)]
+    lib.msd_quantized_bgzf.argtypes = [p, i32, p, i32, C.c_char_p, C.POINTER(C.c_char_p), i32, C.POINTER(p), C.POINTER(i64), C.POINTER(p), C.POINTER(i64), C.POINTER(p), C.POINTER(p), C.POINTER(p), C.POINTER(i64)]
     lib.msd_quantized_runs.argtypes = [p, i32, p, i32, C.POINTER(p), C.POINTER(p), C.POINTER(p), C.POINTER(i64)]
     lib.msd_totals_device.argtypes = [p, C.POINTER(p), C.POINTER(p), C.POINTER(i64), C.POINTER(p)]
     lib.msd_totals_reset.argtypes = [p]
@@ -261,9 +262,17 @@ class Context:
 
     def per_base_bgzf(self, tid, chrom):
         """(BGZF bytes without the EOF marker, members as a structured array, (start, stop, depth)) -- msd_per_base_bgzf."""
+        return self._bgzf(lambda *out: self.lib.msd_per_base_bgzf(self.h, tid, chrom.encode() if isinstance(chrom, str) else chrom, *out))
+
+    def quantized_bgzf(self, tid, quants, chrom, labels):
+        """The same for quantized.bed.gz: labels[bin] is the 4th field -- msd_quantized_bgzf."""
+        q = np.ascontiguousarray(quants, dtype=np.int64)
+        lab = (C.c_char_p * max(1, len(labels)))(*[l.encode() if isinstance(l, str) else l for l in labels])
+        return self._bgzf(lambda *out: self.lib.msd_quantized_bgzf(self.h, tid, _ptr(q), len(q), chrom.encode() if isinstance(chrom, str) else chrom, lab, len(labels), *out))
+
+    def _bgzf(self, call):
         z, m, a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(); nz, nm, n = C.c_int64(), C.c_int64(), C.c_int64()
-        self._check(self.lib.msd_per_base_bgzf(self.h, tid, chrom.encode() if isinstance(chrom, str) else chrom, C.byref(z), C.byref(nz), C.byref(m), C.byref(nm),
-                                               C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        self._check(call(C.byref(z), C.byref(nz), C.byref(m), C.byref(nm), C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
         def arr(p):
             if n.value == 0:
                 return np.zeros(0, dtype=np.int32)

@@ -57,9 +57,8 @@ bz_tile_scan_kernel(const uint32_t* __restrict__ in, uint64_t n, const unsigned 
 __global__ void __launch_bounds__(kBzThreads)
 bz_len_kernel(const BzCodes* __restrict__ C, const int32_t* __restrict__ st, const int32_t* __restrict__ en, const int32_t* __restrict__ dp, uint64_t n,
               uint32_t* __restrict__ text_len) {
-    const uint32_t name_len = C->name_len;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        text_len[i] = bz_line_len(name_len, st[i], en[i], dp[i]);
+        text_len[i] = bz_line_len(*C, st[i], en[i], dp[i]);
 }
 
 struct BzTables { uint32_t litlen[286]; uint32_t dist[30]; };
@@ -76,7 +75,7 @@ bz_mark_kernel(const BzCodes* __restrict__ C, const int32_t* __restrict__ st, co
     bz_load_tables(C, &T);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t to = text_off[i];
-        const BzLineCtx lc = bz_line_ctx(C->name_len, st, en, dp, i, n, to);
+        const BzLineCtx lc = bz_line_ctx(*C, st, en, dp, i, n, to);
         if (lc.first) blk_first[bz_block_of(to)] = i;
         bit_len[i] = bz_line_bits(*C, T.litlen, T.dist, st, en, dp, i, lc);
     }
@@ -109,7 +108,7 @@ bz_emit_kernel(const BzCodes* __restrict__ C, const int32_t* __restrict__ st, co
     const uint32_t hdr_bits = C->hdr_bits;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t to = text_off[i];
-        const BzLineCtx lc = bz_line_ctx(C->name_len, st, en, dp, i, n, to);
+        const BzLineCtx lc = bz_line_ctx(*C, st, en, dp, i, n, to);
         const uint32_t b = bz_block_of(to);
         const uint64_t bitpos = (member_off[b] + 18) * 8 + hdr_bits + (bit_off[i] - bit_off[blk_first[b]]);
         bz_line_emit(*C, T.litlen, T.dist, st, en, dp, i, lc, text, to, out32, bitpos);

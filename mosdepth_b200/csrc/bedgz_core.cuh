@@ -28,11 +28,13 @@
 namespace msd {
 
 constexpr int kBzMaxName = 200;                       // contig name bytes the device path accepts
-constexpr uint32_t kBzMaxLine = kBzMaxName + 1 + 10 + 1 + 10 + 1 + 11 + 1;
-constexpr uint32_t kBzBlockSpan = 32768 - 256;        // lines that START in [b*span, (b+1)*span) of the text form member b
-constexpr uint32_t kBzMaxBlockText = kBzBlockSpan + kBzMaxLine;   // <= 32,747 bytes: 15 bits per byte still fit a 64 KB member
+constexpr int kBzMaxLabels = 64, kBzMaxLabel = 48;    // quantized.bed: the 4th field is a label (mosdepth.nim:111-122) instead of a depth
+constexpr uint32_t kBzMaxLine = kBzMaxName + 1 + 11 + 1 + 11 + 1 + kBzMaxLabel + 1;
+constexpr uint32_t kBzBlockSpan = 32768 - 320;        // lines that START in [b*span, (b+1)*span) of the text form member b
+constexpr uint32_t kBzMaxBlockText = kBzBlockSpan + kBzMaxLine;   // <= 32,768 bytes: 15 bits per byte still fit a 64 KB member
+static_assert(kBzMaxBlockText <= 32768, "member text bound");
 constexpr int kBzHdrMaxBytes = 512;
-constexpr int kBzNumMax = 40;
+constexpr int kBzNumMax = 11 + 1 + 11 + 1 + kBzMaxLabel + 1 + 7;
 
 struct BzCodes {
     uint32_t litlen[286];       // bit-reversed code | nbits << 16 (ready for LSB-first packing)
@@ -41,6 +43,9 @@ struct BzCodes {
     uint32_t name_len;          // without the tab
     uint8_t name[kBzMaxName + 8];   // NAME \t
     uint8_t hdr[kBzHdrMaxBytes];
+    uint32_t n_labels;          // 0: the 4th field is the decimal value (per-base.bed); else it is lab[value] (quantized.bed)
+    uint8_t lab_len[kBzMaxLabels];
+    uint8_t lab[kBzMaxLabels][kBzMaxLabel];
 };
 
 MSD_HD uint32_t bz_digits(uint32_t v) {
@@ -50,7 +55,8 @@ MSD_HD uint32_t bz_digits(uint32_t v) {
     return n;
 }
 MSD_HD uint32_t bz_idigits(int32_t v) { return v < 0 ? 1 + bz_digits((uint32_t)(-(int64_t)v)) : bz_digits((uint32_t)v); }
-MSD_HD uint32_t bz_line_len(uint32_t name_len, int32_t st, int32_t en, int32_t dp) { return name_len + 1 + bz_idigits(st) + 1 + bz_idigits(en) + 1 + bz_idigits(dp) + 1; }
+MSD_HD uint32_t bz_value_len(const BzCodes& C, int32_t v) { return C.n_labels ? ((uint32_t)v < C.n_labels ? C.lab_len[v] : 0u) : bz_idigits(v); }
+MSD_HD uint32_t bz_line_len(const BzCodes& C, int32_t st, int32_t en, int32_t v) { return C.name_len + 1 + bz_idigits(st) + 1 + bz_idigits(en) + 1 + bz_value_len(C, v) + 1; }
 
 MSD_HD char* bz_put_i32(char* p, int32_t v) {
     uint32_t u = (uint32_t)v;
@@ -59,11 +65,13 @@ MSD_HD char* bz_put_i32(char* p, int32_t v) {
     for (uint32_t k = n; k-- > 0;) { p[k] = (char)('0' + u % 10u); u /= 10u; }
     return p + n;
 }
-// "S \t E \t D \n" into num; returns its length, the lengths of S and E through ls / le
-MSD_HD uint32_t bz_format_num(char* num, int32_t st, int32_t en, int32_t dp, uint32_t* ls, uint32_t* le) {
+// "S \t E \t D \n" (D: the decimal value, or its label) into num; returns its length, the lengths of S and E through ls / le
+MSD_HD uint32_t bz_format_num(const BzCodes& C, char* num, int32_t st, int32_t en, int32_t v, uint32_t* ls, uint32_t* le) {
     char* p = bz_put_i32(num, st); *ls = (uint32_t)(p - num); *p++ = '\t';
     char* q = bz_put_i32(p, en); *le = (uint32_t)(q - p); *q++ = '\t';
-    q = bz_put_i32(q, dp); *q++ = '\n';
+    if (C.n_labels) { const uint32_t ll = bz_value_len(C, v); for (uint32_t k = 0; k < ll; k++) *q++ = (char)C.lab[v][k]; }
+    else q = bz_put_i32(q, v);
+    *q++ = '\n';
     return (uint32_t)(q - num);
 }
 
@@ -90,7 +98,7 @@ MSD_HD void bz_dist_symbol(uint32_t dist, uint32_t* code, uint32_t* ebits, uint3
 }
 
 // What a line knows about the line in front of it (same member): nothing else crosses lines.
-struct BzPrev { bool has; bool chained; uint32_t len, ls; };   // chained: previous stop == this start
+struct BzPrev { bool has; bool chained; uint32_t len, ls; uint32_t lab_dist; };   // chained: previous stop == this start; lab_dist: label mode, see bz_label_dist
 
 // The token walk shared by the bit counter, the bit emitter and the host's sampler.  Sink: lit(byte), match(len, dist).
 template <class Sink>
@@ -105,7 +113,10 @@ MSD_HD void bz_tokens(const uint8_t* name, uint32_t name_len, const char* num, u
     const uint32_t cmax = ls < le ? ls : le;
     while (c < cmax && num[c] == num[ls + 1 + c]) c++;
     if (c >= 3) { sink.match(c, ls + 1); k0 += c; }
-    for (; k0 < num_len; k0++) sink.lit((uint8_t)num[k0]);
+    const uint32_t lab_start = ls + 1 + le + 1;              // label mode: "LABEL \n" copied from the nearest line of the member that has it
+    const uint32_t lit_end = pv.lab_dist ? lab_start : num_len;
+    for (; k0 < lit_end; k0++) sink.lit((uint8_t)num[k0]);
+    if (pv.lab_dist) sink.match(num_len - lab_start, pv.lab_dist);
 }
 
 struct BzCountSink {
@@ -153,23 +164,42 @@ struct BzEmitSink {
 // ---- per-line steps of the kernels (bedgz.cuh) -- the host replay calls exactly these ---------------------------------
 MSD_HD uint32_t bz_block_of(uint64_t text_off) { return (uint32_t)(text_off / kBzBlockSpan); }
 
+// Label mode (quantized.bed): distance from the label of line i back to the label of the nearest of the 8 lines in front of it
+// that carries the same label (and, when `bounded`, starts in the same member); 0 if there is none.  No search structure: the
+// candidates are the lines themselves, their lengths are digit counts.
+MSD_HD uint32_t bz_label_dist(const BzCodes& C, const int32_t* st, const int32_t* en, const int32_t* dp, uint64_t i, bool bounded, uint64_t text_off) {
+    if (!C.n_labels || bz_value_len(C, dp[i]) + 1 < 3) return 0;
+    const uint32_t blk = bounded ? bz_block_of(text_off) : 0;
+    uint64_t back = 0, off = text_off;
+    for (uint64_t j = 1; j <= 8 && j <= i; j++) {
+        const uint32_t lj = bz_line_len(C, st[i - j], en[i - j], dp[i - j]);
+        back += lj;
+        if (bounded) { if (off < lj) break; off -= lj; if (bz_block_of(off) != blk) break; }
+        if (dp[i - j] == dp[i]) {
+            const uint64_t d = back + bz_idigits(st[i]) + bz_idigits(en[i]) - bz_idigits(st[i - j]) - bz_idigits(en[i - j]);
+            return d <= 32768 ? (uint32_t)d : 0u;
+        }
+    }
+    return 0;
+}
+
 struct BzLineCtx { bool first, last; BzPrev pv; };
 // line i of n: is it the first / last line of its member, and what does it know of line i-1
-MSD_HD BzLineCtx bz_line_ctx(uint32_t name_len, const int32_t* st, const int32_t* en, const int32_t* dp, uint64_t i, uint64_t n, uint64_t text_off) {
-    BzLineCtx c; c.pv.has = false; c.pv.chained = false; c.pv.len = 0; c.pv.ls = 0;
+MSD_HD BzLineCtx bz_line_ctx(const BzCodes& C, const int32_t* st, const int32_t* en, const int32_t* dp, uint64_t i, uint64_t n, uint64_t text_off) {
+    BzLineCtx c; c.pv.has = false; c.pv.chained = false; c.pv.len = 0; c.pv.ls = 0; c.pv.lab_dist = bz_label_dist(C, st, en, dp, i, true, text_off);
     const uint32_t blk = bz_block_of(text_off);
     c.first = true;
     if (i > 0) {
-        const uint32_t plen = bz_line_len(name_len, st[i - 1], en[i - 1], dp[i - 1]);
+        const uint32_t plen = bz_line_len(C, st[i - 1], en[i - 1], dp[i - 1]);
         if (bz_block_of(text_off - plen) == blk) { c.first = false; c.pv.has = true; c.pv.len = plen; c.pv.ls = bz_idigits(st[i - 1]); c.pv.chained = en[i - 1] == st[i]; }
     }
-    c.last = i + 1 == n || bz_block_of(text_off + bz_line_len(name_len, st[i], en[i], dp[i])) != blk;
+    c.last = i + 1 == n || bz_block_of(text_off + bz_line_len(C, st[i], en[i], dp[i])) != blk;
     return c;
 }
 // bits of line i (its tokens; plus the end-of-block code when it closes a member)
 MSD_HD uint32_t bz_line_bits(const BzCodes& C, const uint32_t* litlen, const uint32_t* dist, const int32_t* st, const int32_t* en, const int32_t* dp, uint64_t i, const BzLineCtx& lc) {
     char num[kBzNumMax]; uint32_t ls, le;
-    const uint32_t nn = bz_format_num(num, st[i], en[i], dp[i], &ls, &le);
+    const uint32_t nn = bz_format_num(C, num, st[i], en[i], dp[i], &ls, &le);
     BzCountSink s; s.litlen = litlen; s.dist = dist; s.bits = 0;
     bz_tokens(C.name, C.name_len, num, nn, ls, le, lc.pv, s);
     return s.bits + (lc.last ? (litlen[256] >> 16) : 0u);
@@ -178,7 +208,7 @@ MSD_HD uint32_t bz_line_bits(const BzCodes& C, const uint32_t* litlen, const uin
 MSD_HD void bz_line_emit(const BzCodes& C, const uint32_t* litlen, const uint32_t* dist, const int32_t* st, const int32_t* en, const int32_t* dp, uint64_t i, const BzLineCtx& lc,
                          uint8_t* text, uint64_t text_off, uint32_t* out32, uint64_t bitpos) {
     char num[kBzNumMax]; uint32_t ls, le;
-    const uint32_t nn = bz_format_num(num, st[i], en[i], dp[i], &ls, &le);
+    const uint32_t nn = bz_format_num(C, num, st[i], en[i], dp[i], &ls, &le);
     uint8_t* t = text + text_off;
     for (uint32_t k = 0; k <= C.name_len; k++) t[k] = C.name[k];
     t += C.name_len + 1;
@@ -246,20 +276,24 @@ inline void bz_canonical(const std::vector<uint8_t>& len, uint32_t* out) {
 
 // Builds the code of a contig from a sample of its own lines and the member header bits (BFINAL=1, BTYPE=2, HLIT/HDIST/HCLEN,
 // code-length code, the 316 code lengths with repeat symbol 16).  Returns false if the name is too long for the device path.
-inline bool bz_build_codes(const char* chrom, const int32_t* st, const int32_t* en, const int32_t* dp, uint64_t n, BzCodes* C) {
+// labels (n_labels > 0): dp[i] indexes them (quantized.bed); every dp[i] must be in range.
+inline bool bz_build_codes(const char* chrom, const int32_t* st, const int32_t* en, const int32_t* dp, uint64_t n, BzCodes* C, const char* const* labels = nullptr, int n_labels = 0) {
     const size_t nl = strlen(chrom);
-    if (nl > (size_t)kBzMaxName) return false;
+    if (nl > (size_t)kBzMaxName || n_labels < 0 || n_labels > kBzMaxLabels) return false;
     memset(C, 0, sizeof *C);
     C->name_len = (uint32_t)nl; memcpy(C->name, chrom, nl); C->name[nl] = '\t';
+    for (int k = 0; k < n_labels; k++) { const size_t ll = strlen(labels[k]); if (ll > (size_t)kBzMaxLabel) return false; C->lab_len[k] = (uint8_t)ll; memcpy(C->lab[k], labels[k], ll); }
+    C->n_labels = (uint32_t)n_labels;
+    if (n_labels) for (uint64_t i = 0; i < n; i++) if ((uint32_t)dp[i] >= (uint32_t)n_labels) return false;
     std::vector<uint64_t> fl(286, 0), fd(30, 0);
     BzHistSink hs; hs.litlen = fl.data(); hs.dist = fd.data();
     const uint64_t want = 1u << 16, step = n > want ? n / want : 1;
     uint64_t lines = 0;
     for (uint64_t i = 0; i < n; i += step) {                       // evenly spaced lines, each with its true predecessor
         char num[kBzNumMax]; uint32_t ls, le;
-        const uint32_t nn = bz_format_num(num, st[i], en[i], dp[i], &ls, &le);
-        BzPrev pv; pv.has = i > 0; pv.chained = false; pv.len = 0; pv.ls = 0;
-        if (i > 0) { pv.len = bz_line_len(C->name_len, st[i - 1], en[i - 1], dp[i - 1]); pv.ls = bz_idigits(st[i - 1]); pv.chained = en[i - 1] == st[i]; }
+        const uint32_t nn = bz_format_num(*C, num, st[i], en[i], dp[i], &ls, &le);
+        BzPrev pv; pv.has = i > 0; pv.chained = false; pv.len = 0; pv.ls = 0; pv.lab_dist = bz_label_dist(*C, st, en, dp, i, false, 0);
+        if (i > 0) { pv.len = bz_line_len(*C, st[i - 1], en[i - 1], dp[i - 1]); pv.ls = bz_idigits(st[i - 1]); pv.chained = en[i - 1] == st[i]; }
         bz_tokens(C->name, C->name_len, num, nn, ls, le, pv, hs);
         lines++;
     }

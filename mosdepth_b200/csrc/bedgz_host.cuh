@@ -55,10 +55,11 @@ inline void bz_scan(cudaStream_t s, const uint32_t* in, uint64_t n, uint32_t* ti
 
 // The n runs (start, stop, depth) of a contig sit in device memory (d_*) and in host memory (h_*, for the code sample).  On success
 // B.h_out holds B.out_bytes bytes of BGZF members and B.members describes them.  max_ctas caps the grid of the per-line kernels.
+// labels (n_labels > 0): the third array holds label indices and the 4th field of a line is labels[value] (quantized.bed).
 // crc(stream, d_text, d_desc, nb, d_ticket, d_expected, d_status, d_errors, d_crc_out) must leave the CRC-32 of every member's text in d_crc_out.
 template <class CrcFn>
 int bz_run(BzBuffers& B, cudaStream_t sc, const char* chrom, const int32_t* d_st, const int32_t* d_en, const int32_t* d_dp, const int32_t* h_st, const int32_t* h_en,
-           const int32_t* h_dp, uint64_t n, int max_ctas, CrcFn crc) {
+           const int32_t* h_dp, uint64_t n, int max_ctas, CrcFn crc, const char* const* labels = nullptr, int n_labels = 0) {
     typedef unsigned long long ull;
     B.members.clear(); B.out_bytes = 0; B.launches = 0; B.err[0] = 0;
     if (n == 0) return 0;
@@ -66,7 +67,9 @@ int bz_run(BzBuffers& B, cudaStream_t sc, const char* chrom, const int32_t* d_st
     // the contig's Huffman code, from a sample of its own lines (host: 65,536 lines at most)
     static_assert(sizeof(BzCodes) % 4 == 0, "BzCodes is copied as words");
     BzCodes codes;
-    if (!bz_build_codes(chrom, h_st, h_en, h_dp, n, &codes)) return bz_fail(B, MSD_EINVAL, "msd_per_base_bgzf: cannot build a code for contig '%s'", chrom);
+    if (!bz_build_codes(chrom, h_st, h_en, h_dp, n, &codes, labels, n_labels))
+        return bz_fail(B, MSD_EINVAL, "cannot build a code for contig '%s' (name longer than %d bytes, more than %d labels, a label longer than %d bytes, or a value without a label)", chrom,
+                       kBzMaxName, kBzMaxLabels, kBzMaxLabel);
     // ---- per line: text length -> text offset ------------------------------------------------------------------------
     const uint64_t n_tiles = (n + kBzScanTile - 1) / kBzScanTile;
     BzCarve lay{nullptr};

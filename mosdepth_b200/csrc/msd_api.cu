@@ -1216,10 +1216,11 @@ int msd_per_base_bgzf(msd_ctx* ctx, int tid, const char* chrom, const uint8_t** 
     return MSD_OK;
 }
 
-int msd_quantized_runs(msd_ctx* ctx, int tid, const int64_t* quants, int n_q, const int32_t** start, const int32_t** stop,
-                       const int32_t** bin, int64_t* n_runs) {
-    int rc = check_tid(ctx, tid, "msd_quantized_runs"); if (rc) return rc;
-    if (!quants || n_q < 2 || n_q > kMaxQuants) return ctx_fail(ctx, MSD_EINVAL, "msd_quantized_runs: need 2..%d quantize values", kMaxQuants);
+// gen_quantized for one contig: K9 runs, then the reference's filter (bin != -1 and bin < len(lookup) = n_q-1, :136,:140) compacts the
+// pinned arrays in place; *kept = the runs the reference yields
+static int quantized_runs_impl(msd_ctx* ctx, int tid, const int64_t* quants, int n_q, const char* who, uint64_t* kept) {
+    int rc = check_tid(ctx, tid, who); if (rc) return rc;
+    if (!quants || n_q < 2 || n_q > kMaxQuants) return ctx_fail(ctx, MSD_EINVAL, "%s: need 2..%d quantize values", who, kMaxQuants);
     if ((rc = ensure_query_buffers(ctx))) return rc;
     const uint32_t tlen = ctx->tlen[tid];
     QuantF f; f.qa.n = n_q; for (int i = 0; i < n_q; i++) f.qa.q[i] = quants[i];
@@ -1234,8 +1235,41 @@ int msd_quantized_runs(msd_ctx* ctx, int tid, const int64_t* quants, int n_q, co
         if (b == -1 || b >= n_q - 1) continue;
         ctx->h_run_start[w] = ctx->h_run_start[i]; ctx->h_run_stop[w] = ctx->h_run_stop[i]; ctx->h_run_val[w] = b; w++;
     }
+    *kept = w;
+    return MSD_OK;
+}
+
+int msd_quantized_runs(msd_ctx* ctx, int tid, const int64_t* quants, int n_q, const int32_t** start, const int32_t** stop,
+                       const int32_t** bin, int64_t* n_runs) {
+    uint64_t w = 0;
+    int rc = quantized_runs_impl(ctx, tid, quants, n_q, "msd_quantized_runs", &w); if (rc) return rc;
     if (start) *start = ctx->h_run_start; if (stop) *stop = ctx->h_run_stop; if (bin) *bin = ctx->h_run_val;
     if (n_runs) *n_runs = (int64_t)w;
+    return MSD_OK;
+}
+
+int msd_quantized_bgzf(msd_ctx* ctx, int tid, const int64_t* quants, int n_q, const char* chrom, const char* const* labels, int n_labels, const uint8_t** bgzf, int64_t* n_bytes,
+                       const msd_bgzf_member** members, int64_t* n_members, const int32_t** start, const int32_t** stop, const int32_t** bin, int64_t* n_runs) {
+    if (!ctx) return MSD_EINVAL;
+    if (!chrom || !labels || !bgzf || !n_bytes || !members || !n_members) return ctx_fail(ctx, MSD_EINVAL, "msd_quantized_bgzf: null argument");
+    if (n_labels < n_q - 1) return ctx_fail(ctx, MSD_EINVAL, "msd_quantized_bgzf: %d labels for %d quantize values", n_labels, n_q);
+    uint64_t w = 0;
+    int rc = quantized_runs_impl(ctx, tid, quants, n_q, "msd_quantized_bgzf", &w); if (rc) return rc;
+    if (start) *start = ctx->h_run_start; if (stop) *stop = ctx->h_run_stop; if (bin) *bin = ctx->h_run_val;
+    if (n_runs) *n_runs = (int64_t)w;
+    *bgzf = nullptr; *n_bytes = 0; *members = nullptr; *n_members = 0;
+    if (w == 0) return MSD_OK;
+    cudaStream_t sc = ctx->s_compute;     // the kept runs go back to the device arrays K9 left them in (w <= the runs those hold)
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_run_start, ctx->h_run_start, 4 * w, cudaMemcpyHostToDevice, sc));
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_run_stop, ctx->h_run_stop, 4 * w, cudaMemcpyHostToDevice, sc));
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_run_val, ctx->h_run_val, 4 * w, cudaMemcpyHostToDevice, sc));
+    rc = bz_run(ctx->bz, sc, chrom, ctx->d_run_start, ctx->d_run_stop, ctx->d_run_val, ctx->h_run_start, ctx->h_run_stop, ctx->h_run_val, w, kSMs * 8,
+                [](cudaStream_t s, const uint8_t* d_text, const BlockDesc* d_desc, int nb, uint32_t* ticket, const uint32_t* expected, uint32_t* status, uint32_t* errors, uint32_t* crc_out) {
+                    launch_crc(s, d_text, d_desc, nb, ticket, expected, status, errors, crc_out);
+                }, labels, n_labels);
+    ctx->launches += ctx->bz.launches;
+    if (rc) return ctx_fail(ctx, rc, "msd_quantized_bgzf: %s", ctx->bz.err);
+    *bgzf = ctx->bz.h_out; *n_bytes = (int64_t)ctx->bz.out_bytes; *members = ctx->bz.members.data(); *n_members = (int64_t)ctx->bz.members.size();
     return MSD_OK;
 }
 

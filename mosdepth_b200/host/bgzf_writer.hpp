@@ -244,7 +244,8 @@ struct BgzWriter {
     // n runs; Member = {offset, first_run, csize, isize}.  The bytes are appended as they are; the index entries come from the runs
     // (a line's length is a digit count) and the member table.  A line never straddles two members.
     template <class Member>
-    void write_members(const std::string& chrom, const uint8_t* bytes, int64_t n_bytes, const Member* mem, int64_t n_mem, const int32_t* st, const int32_t* en, const int32_t* val, int64_t n) {
+    void write_members(const std::string& chrom, const uint8_t* bytes, int64_t n_bytes, const Member* mem, int64_t n_mem, const int32_t* st, const int32_t* en, const int32_t* val, int64_t n,
+                       const std::vector<std::string>* labels = nullptr) {
         if (n_bytes <= 0 || plain) { if (plain) failed = true; return; }
         flush_block(buf.size());
         if (csi) {
@@ -253,7 +254,7 @@ struct BgzWriter {
                 const int64_t a = (int64_t)mem[k].first_run, b = k + 1 < n_mem ? (int64_t)mem[k + 1].first_run : n;
                 const uint64_t c0 = coff + mem[k].offset; uint64_t uoff = 0;
                 for (int64_t i = a; i < b; i++) {
-                    const uint64_t len = chrom.size() + 4 + (uint64_t)digits(st[i]) + (uint64_t)digits(en[i]) + (uint64_t)digits(val[i]);
+                    const uint64_t len = chrom.size() + 4 + (uint64_t)digits(st[i]) + (uint64_t)digits(en[i]) + (labels ? (uint64_t)(*labels)[(size_t)val[i]].size() : (uint64_t)digits(val[i]));
                     const uint64_t v0 = (c0 << 16) | uoff; uoff += len;
                     csi->add(chrom, st[i], en[i], v0, i + 1 == b ? (c0 + mem[k].csize) << 16 : (c0 << 16) | uoff);
                 }

@@ -393,7 +393,13 @@ int main(int argc, char** argv) {
             if (tid == -2 && quant[0] == 0) { line = target.name + "\t0\t" + std::to_string(target.length) + "\t" + lookup[0] + "\n"; fquant.write_interval(line, target.name, 0, target.length); }
             else if (tid != -2) {
                 const int32_t *st, *en, *bn; int64_t nr = 0;
-                MSD(msd_quantized_runs(ctx, ti, quant.data(), (int)quant.size(), &st, &en, &bn, &nr));
+                bool labels_fit = true; for (auto& l : lookup) if (l.size() > 48) labels_fit = false;
+                if (!plain && device_bgzf && target.name.size() <= 200 && labels_fit && lookup.size() <= 64) {     // K10, label mode
+                    std::vector<const char*> lab; for (auto& l : lookup) lab.push_back(l.c_str());
+                    const uint8_t* zb; int64_t zn = 0, nm = 0; const msd_bgzf_member* mem;
+                    MSD(msd_quantized_bgzf(ctx, ti, quant.data(), (int)quant.size(), target.name.c_str(), lab.data(), (int)lab.size(), &zb, &zn, &mem, &nm, &st, &en, &bn, &nr));
+                    fquant.write_members(target.name, zb, zn, mem, nm, st, en, bn, nr, &lookup); nr = 0;
+                } else MSD(msd_quantized_runs(ctx, ti, quant.data(), (int)quant.size(), &st, &en, &bn, &nr));
                 line.clear();
                 if (!plain) { fquant.write_runs(target.name, st, en, bn, nr, &lookup); nr = 0; }
                 for (int64_t k = 0; k < nr; k++) { line += target.name; line += '\t'; line += std::to_string(st[k]); line += '\t'; line += std::to_string(en[k]); line += '\t'; line += lookup[(size_t)bn[k]]; line += '\n'; if (line.size() > (1 << 19)) { fquant.write(line); line.clear(); } }

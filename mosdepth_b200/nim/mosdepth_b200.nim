@@ -48,6 +48,8 @@ type MsdBgzfMember* {.bycopy.} = object   ## msd_bgzf_member
 ## per-base.bed.gz members deflated on the device (replaces the loop :783-793 and the BGZF compression of its writer, :650-651)
 proc msd_per_base_bgzf*(ctx: MsdCtx, tid: cint, chrom: cstring, bgzf: ptr ptr uint8, n_bytes: ptr int64, members: ptr ptr MsdBgzfMember, n_members: ptr int64,
                         start, stop, depth: ptr ptr int32, n_runs: ptr int64): cint {.importc, dynlib: libmsd.}
+proc msd_quantized_bgzf*(ctx: MsdCtx, tid: cint, quants: ptr int64, n_q: cint, chrom: cstring, labels: cstringArray, n_labels: cint, bgzf: ptr ptr uint8, n_bytes: ptr int64,
+                         members: ptr ptr MsdBgzfMember, n_members: ptr int64, start, stop, bin: ptr ptr int32, n_runs: ptr int64): cint {.importc, dynlib: libmsd.}
 proc msd_quantized_runs*(ctx: MsdCtx, tid: cint, quants: ptr int64, n_q: cint, start, stop, bin: ptr ptr int32, n_runs: ptr int64): cint {.importc, dynlib: libmsd.}
 
 template check*(ctx: MsdCtx, call: untyped) =

@@ -26,6 +26,12 @@ for tid, name in enumerate(hdr.names):
     assert int(mem["offset"][0]) == 0 and int(mem["first_run"][0]) == 0 and int(mem["isize"].sum()) == len(want)
     assert int(mem["offset"][-1]) + int(mem["csize"][-1]) == len(data)
     assert all(int(mem["offset"][k]) + int(mem["csize"][k]) == int(mem["offset"][k + 1]) for k in range(len(mem) - 1))
+    quants = [0, 1, 50, 100, 2**63 - 1]; labels = ["0:1", "1:50", "50:100", "100:inf"]
+    zdata, zmem, (qs, qe, qb) = ctx.quantized_bgzf(tid, quants, name, labels)
+    qs2, qe2, qb2 = ctx.quantized_runs(tid, quants)
+    assert (qs == qs2).all() and (qe == qe2).all() and (qb == qb2).all()
+    qwant = "".join(f"{name}\t{a}\t{b}\t{labels[c]}\n" for a, b, c in zip(qs.tolist(), qe.tolist(), qb.tolist())).encode()
+    assert gzip.decompress(zdata + EOF_BLOCK) == qwant and int(zmem["isize"].sum()) == len(qwant)
     seen += 1
 assert seen >= 1
 print("ok", seen)

@@ -9,22 +9,38 @@
 
 using namespace msd;
 
+static int replay(const char* chrom, const int32_t* st, const int32_t* en, const int32_t* dp, int64_t nr, const char* const* labels, int n_labels, const uint8_t** bgzf, int64_t* n_bytes,
+                  const msd_bgzf_member** members, int64_t* n_members);
+
 extern "C" int msd_mock_per_base_bgzf(msd_ctx* ctx, int tid, const char* chrom, const uint8_t** bgzf, int64_t* n_bytes, const msd_bgzf_member** members, int64_t* n_members,
                                       const int32_t** start, const int32_t** stop, const int32_t** depth, int64_t* n_runs) {
-    static std::vector<uint32_t> out32; static std::vector<msd_bgzf_member> mem;
     const int32_t *st, *en, *dp; int64_t nr = 0;
     int rc = msd_per_base_runs(ctx, tid, &st, &en, &dp, &nr); if (rc) return rc;
-    *start = st; *stop = en; *depth = dp; *n_runs = nr; *bgzf = nullptr; *n_bytes = 0; *members = nullptr; *n_members = 0;
+    *start = st; *stop = en; *depth = dp; *n_runs = nr;
+    return replay(chrom, st, en, dp, nr, nullptr, 0, bgzf, n_bytes, members, n_members);
+}
+extern "C" int msd_quantized_bgzf(msd_ctx* ctx, int tid, const int64_t* quants, int n_q, const char* chrom, const char* const* labels, int n_labels, const uint8_t** bgzf, int64_t* n_bytes,
+                                  const msd_bgzf_member** members, int64_t* n_members, const int32_t** start, const int32_t** stop, const int32_t** bin, int64_t* n_runs) {
+    const int32_t *st, *en, *bn; int64_t nr = 0;
+    int rc = msd_quantized_runs(ctx, tid, quants, n_q, &st, &en, &bn, &nr); if (rc) return rc;
+    *start = st; *stop = en; *bin = bn; *n_runs = nr;
+    return replay(chrom, st, en, bn, nr, labels, n_labels, bgzf, n_bytes, members, n_members);
+}
+
+static int replay(const char* chrom, const int32_t* st, const int32_t* en, const int32_t* dp, int64_t nr, const char* const* labels, int n_labels, const uint8_t** bgzf, int64_t* n_bytes,
+                  const msd_bgzf_member** members, int64_t* n_members) {
+    static std::vector<uint32_t> out32; static std::vector<msd_bgzf_member> mem;
+    *bgzf = nullptr; *n_bytes = 0; *members = nullptr; *n_members = 0;
     if (nr == 0) return MSD_OK;
     const uint64_t n = (uint64_t)nr;
     BzCodes C;
-    if (!bz_build_codes(chrom, st, en, dp, n, &C)) return MSD_EINVAL;
+    if (!bz_build_codes(chrom, st, en, dp, n, &C, labels, n_labels)) return MSD_EINVAL;
     std::vector<uint64_t> text_off(n + 1, 0), bit_off(n + 1, 0);
-    for (uint64_t i = 0; i < n; i++) text_off[i + 1] = text_off[i] + bz_line_len(C.name_len, st[i], en[i], dp[i]);
+    for (uint64_t i = 0; i < n; i++) text_off[i + 1] = text_off[i] + bz_line_len(C, st[i], en[i], dp[i]);
     const uint32_t nb = bz_block_of(text_off[n - 1]) + 1;
     std::vector<uint64_t> blk_first(nb, ~0ull);
     for (uint64_t i = 0; i < n; i++) {
-        const BzLineCtx lc = bz_line_ctx(C.name_len, st, en, dp, i, n, text_off[i]);
+        const BzLineCtx lc = bz_line_ctx(C, st, en, dp, i, n, text_off[i]);
         if (lc.first) blk_first[bz_block_of(text_off[i])] = i;
         bit_off[i + 1] = bit_off[i] + bz_line_bits(C, C.litlen, C.dist, st, en, dp, i, lc);
     }
@@ -39,7 +55,7 @@ extern "C" int msd_mock_per_base_bgzf(msd_ctx* ctx, int tid, const char* chrom, 
     out32.assign(member_off[nb] / 4 + 4, 0);
     for (uint64_t k = 0; k < n; k++) {
         const uint64_t i = n - 1 - k;          // any order
-        const BzLineCtx lc = bz_line_ctx(C.name_len, st, en, dp, i, n, text_off[i]);
+        const BzLineCtx lc = bz_line_ctx(C, st, en, dp, i, n, text_off[i]);
         const uint32_t b = bz_block_of(text_off[i]);
         bz_line_emit(C, C.litlen, C.dist, st, en, dp, i, lc, text.data(), text_off[i], out32.data(), (member_off[b] + 18) * 8 + C.hdr_bits + (bit_off[i] - bit_off[blk_first[b]]));
     }

@@ -37,6 +37,8 @@ CASES = [
     ("chr20", 300000, "wgs", 1, 0.95), ("chr1", 120000, "sparse", 2, 0.9), ("chrUn_KI270442v1", 90000, "wide", 3, 0.9), ("1", 50000, "tiny", 4, 0.9),
     ("X", 3000, "tiny", 5, 0.5), ("n" * 200, 20000, "wgs", 6, 0.8), ("HLA-DRB1*15:01:01:01", 100000, "sparse", 7, 0.9), ("MT", 1, "wgs", 8, 0.0), ("MT", 2, "wide", 9, 0.0),
     ("ab", 70000, "wgs", 10, 0.9),
+    # label mode (quantized.bed): gaps between runs, labels of 3 to 48 bytes copied from the nearest line with the same label
+    ("chr5", 100000, "quant", 11, 0.7), ("1", 2000, "quant", 12, 0.0), ("chrUn_X", 3, "quant", 13, 0.0),
 ]
 
 

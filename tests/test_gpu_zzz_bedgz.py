@@ -45,6 +45,13 @@ def check_contig(ctx, tid, chrom):
         assert piece.startswith(f"{chrom}\t{int(s[first])}\t".encode())
         at += isz
     assert ctx.debug_inflate(data + EOF_BLOCK, len(want)) == want          # and the product's own inflate kernels read it back
+    # label mode (msd_quantized_bgzf): the members hold `chrom start stop labels[bin]` of the runs msd_quantized_runs returns
+    quants = [0, 1, 4, 100, 2**63 - 1]; labels = ["NO_COVERAGE", "1:4", "CALLABLE", "100:inf"]
+    zdata, zmem, (qs, qe, qb) = ctx.quantized_bgzf(tid, quants, chrom, labels)
+    qs2, qe2, qb2 = ctx.quantized_runs(tid, quants)
+    assert np.array_equal(qs, qs2) and np.array_equal(qe, qe2) and np.array_equal(qb, qb2)
+    qwant = "".join(f"{chrom}\t{a}\t{b}\t{labels[c]}\n" for a, b, c in zip(qs.tolist(), qe.tolist(), qb.tolist())).encode()
+    assert gzip.decompress(zdata + EOF_BLOCK) == qwant and int(zmem["isize"].sum()) == len(qwant)
     return want
 
 
@@ -85,13 +92,15 @@ def test_device_bgzf_many_members_and_cli(ctx, tmp_path):
         if tid < 3:
             check_contig(ctx, tid, cname)
     assert total_members > len(hdr.names)
-    run_tool(CLI, ["--plain", "p", bam], tmp_path)
-    run_tool(CLI, ["z", bam], tmp_path, env={"MOSDEPTH_B200_DEVICE_BGZF": "1"})
-    run_tool(CLI, ["h", bam], tmp_path, env={"MOSDEPTH_B200_DEVICE_BGZF": "0"})
+    run_tool(CLI, ["--plain", "-q", "0:1:10:30:", "p", bam], tmp_path)
+    run_tool(CLI, ["-q", "0:1:10:30:", "z", bam], tmp_path, env={"MOSDEPTH_B200_DEVICE_BGZF": "1"})
+    run_tool(CLI, ["-q", "0:1:10:30:", "h", bam], tmp_path, env={"MOSDEPTH_B200_DEVICE_BGZF": "0"})
     plain = (tmp_path / "p.per-base.bed").read_bytes()
     dev = (tmp_path / "z.per-base.bed.gz").read_bytes()
     assert gzip.decompress(dev) == plain
     assert gzip.decompress((tmp_path / "h.per-base.bed.gz").read_bytes()) == plain
     assert dev != (tmp_path / "h.per-base.bed.gz").read_bytes()          # the device path really wrote it
     assert gzip.decompress((tmp_path / "z.per-base.bed.gz.csi").read_bytes())[:4] == b"CSI\x01"
+    assert gzip.decompress((tmp_path / "z.quantized.bed.gz").read_bytes()) == (tmp_path / "p.quantized.bed").read_bytes()
+    assert gzip.decompress((tmp_path / "h.quantized.bed.gz").read_bytes()) == (tmp_path / "p.quantized.bed").read_bytes()
     assert (tmp_path / "z.mosdepth.summary.txt").read_bytes() == (tmp_path / "p.mosdepth.summary.txt").read_bytes()

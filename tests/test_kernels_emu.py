@@ -20,17 +20,19 @@ def emu(tmp_path_factory):
 
 
 # (contig name, bases, CTA cap of the grid-stride kernels, seed): many scan tiles with few CTAs; the library's own cap; tiny inputs
-CASES = [("chr1", 400000, 7, 2), ("HLA-DRB1*15:01:01:01", 150000, 1184, 3), ("X", 5000, 3, 4), ("MT", 17, 1184, 5), ("c", 1, 1, 6)]
+# the last field: "" = per-base (K8 + K10, msd_per_base_bgzf), "quant" = quantized (K9 + host filter + K10 in label mode, msd_quantized_bgzf)
+CASES = [("chr1", 400000, 7, 2, ""), ("HLA-DRB1*15:01:01:01", 150000, 1184, 3, ""), ("X", 5000, 3, 4, ""), ("MT", 17, 1184, 5, ""), ("c", 1, 1, 6, ""),
+         ("chr1", 600000, 9, 7, "quant"), ("MT", 17, 1184, 8, "quant"), ("chrUn_KI270442v1", 2, 1, 9, "quant")]
 
 
-@pytest.mark.parametrize("chrom,n_bases,max_ctas,seed", CASES, ids=[f"{c[0][:8]}-{c[1]}-{c[2]}" for c in CASES])
-def test_kernels_under_emulation(emu, chrom, n_bases, max_ctas, seed):
+@pytest.mark.parametrize("chrom,n_bases,max_ctas,seed,mode", CASES, ids=[f"{c[0][:8]}-{c[1]}-{c[2]}{c[4]}" for c in CASES])
+def test_kernels_under_emulation(emu, chrom, n_bases, max_ctas, seed, mode):
     exe, d = emu
     prefix = d / f"e{seed}"
-    r = subprocess.run([str(exe), str(prefix), chrom, str(n_bases), str(max_ctas), str(seed)], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([str(exe), str(prefix), chrom, str(n_bases), str(max_ctas), str(seed)] + ([mode] if mode else []), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr
     n_dev, n_host, text_bytes, gz_bytes, n_members = (int(v) for v in r.stdout.split())
     text = (d / f"e{seed}.txt").read_bytes()
     gz = (d / f"e{seed}.gz").read_bytes()
-    assert n_dev == n_host and len(text) == text_bytes and len(gz) == gz_bytes and n_members >= 1
+    assert n_dev == n_host and len(text) == text_bytes and len(gz) == gz_bytes and (n_members >= 1 or n_dev == 0)
     assert gzip.decompress(gz) == text
