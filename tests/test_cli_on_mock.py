@@ -52,7 +52,8 @@ def compare(oracle_bin, cli, tmp_path, bam, flags, env=None, expect_rc=0, gz=Fal
 
 
 HEAVY = {"big.bam"}          # a 600 Mb contig: 2.4 GB depth array in the oracle and again in the mock; three cases are enough
-CASES = [(n, f) for n, f in FIX_CASES if n not in HEAVY] + [("big.bam", ["--by", "500", "-n", "-x"])]
+SLOW = {("ovl.bam", ("-m", "--by", "37"))}      # 6.7 M rows of a contig without reads: 50 s here; replaced by the same flags on -c MT
+CASES = [(n, f) for n, f in FIX_CASES if n not in HEAVY and (n, tuple(f)) not in SLOW] + [("big.bam", ["--by", "500", "-n", "-x"]), ("ovl.bam", ["-m", "--by", "37", "-c", "MT"])]
 
 
 @pytest.mark.parametrize("name,flags", CASES, ids=[f"{n}:{' '.join(f)}" for n, f in CASES])
@@ -73,7 +74,7 @@ def test_gz_outputs_on_mock(oracle_bin, mock_cli, fixtures, tmp_path, name, flag
 
 
 def test_env_precision_and_labels_on_mock(oracle_bin, mock_cli, fixtures, tmp_path):
-    compare(oracle_bin, mock_cli, tmp_path, fixtures / "ovl.bam", ["-q", "0:1:1000", "--by", "77"], env={"MOSDEPTH_Q0": "AAA", "MOSDEPTH_Q1": "BBB", "MOSDEPTH_PRECISION": "7"})
+    compare(oracle_bin, mock_cli, tmp_path, fixtures / "ovl.bam", ["-q", "0:1:1000", "--by", "77", "-c", "MT"], env={"MOSDEPTH_Q0": "AAA", "MOSDEPTH_Q1": "BBB", "MOSDEPTH_PRECISION": "7"})
 
 
 def test_error_paths_match_on_mock(oracle_bin, mock_cli, fixtures, tmp_path):
