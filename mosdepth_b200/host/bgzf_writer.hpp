@@ -73,20 +73,22 @@ struct CsiBuilder {
         return 0;
     }
     void add(const std::string& chrom, int64_t beg, int64_t end, uint64_t voff_beg, uint64_t voff_end) {
+        if (beg < 0) beg = 0;
+        if (end <= beg) end = beg + 1;
+        add_seg(chrom, reg2bin(beg, end), (size_t)(beg >> kMinShift), (size_t)((end - 1) >> kMinShift), voff_beg, voff_end);
+    }
+    // a run of consecutive lines of one bin that covers the 16 KB windows w0..w1 and the virtual offsets [voff_beg, voff_end)
+    void add_seg(const std::string& chrom, uint32_t bin, size_t w0, size_t w1, uint64_t voff_beg, uint64_t voff_end) {
         if (last_tid < 0 || chrom != last_chrom) {
             auto it = tid_of.find(chrom);
             if (it == tid_of.end()) { it = tid_of.emplace(chrom, (int)names.size()).first; names.push_back(chrom); refs.emplace_back(); }
             last_tid = it->second; last_chrom = chrom;
         }
         Ref& r = refs[(size_t)last_tid];
-        if (beg < 0) beg = 0;
-        if (end <= beg) end = beg + 1;
-        const uint32_t bin = reg2bin(beg, end);
         if (bin != r.last_bin) { r.last_vec = &r.bins[bin]; r.last_bin = bin; }
         std::vector<Chunk>& v = *r.last_vec;
         if (!v.empty() && v.back().end == voff_beg) v.back().end = voff_end;                   // next line of the same bin: one chunk
         else v.push_back(Chunk{voff_beg, voff_end});
-        const size_t w0 = (size_t)(beg >> kMinShift), w1 = (size_t)((end - 1) >> kMinShift);
         if (r.lin.size() <= w1) r.lin.resize(w1 + 1, UINT64_MAX);
         for (size_t w = w0; w <= w1; w++) if (voff_beg < r.lin[w]) r.lin[w] = voff_beg;
         n_lines++;
@@ -119,6 +121,24 @@ struct CsiBuilder {
         put64(o, 0);                                              // n_no_coor
         return o;
     }
+};
+
+// Worker-side aggregation of the index entries of sorted lines: consecutive lines that lie in the same 16 KB window (so in the same
+// leaf bin) and follow each other without a gap become ONE segment, which is what CsiBuilder::add would have merged them into anyway
+// (same chunks, same linear-index minima); a line that spans windows stays a segment of its own.  Offsets are (block index, offset in
+// block) pairs relative to the worker's piece; the thread that writes the file turns them into virtual offsets.
+struct CsiSeg { uint32_t bin; uint32_t w0, w1; uint32_t b0, u0, b1, u1; };
+struct CsiSegAgg {
+    std::vector<CsiSeg> segs; bool have = false; CsiSeg cur{};
+    void line(int64_t beg, int64_t end, uint32_t b0, uint32_t u0, uint32_t b1, uint32_t u1) {
+        if (beg < 0) beg = 0;
+        if (end <= beg) end = beg + 1;
+        const uint32_t w0 = (uint32_t)(beg >> CsiBuilder::kMinShift), w1 = (uint32_t)((end - 1) >> CsiBuilder::kMinShift);
+        if (have && w0 == w1 && cur.w0 == w0 && cur.w1 == w0 && cur.b1 == b0 && cur.u1 == u0) { cur.b1 = b1; cur.u1 = u1; return; }
+        if (have) segs.push_back(cur);
+        cur = CsiSeg{CsiBuilder::reg2bin(beg, end), w0, w1, b0, u0, b1, u1}; have = true;
+    }
+    void finish() { if (have) segs.push_back(cur); have = false; }
 };
 
 struct BgzWriter {
@@ -184,7 +204,7 @@ struct BgzWriter {
         }
         flush_block(buf.size());                                   // tasks start on a block boundary
         const int64_t n_tasks = (n + kRunsPerTask - 1) / kRunsPerTask;
-        struct Task { std::vector<uint8_t> out; std::vector<uint32_t> line_off; std::vector<uint32_t> blk_in, blk_out; size_t text = 0; bool ok = true; };
+        struct Task { std::vector<uint8_t> out; std::vector<uint32_t> line_off; std::vector<uint32_t> blk_in, blk_out; std::vector<CsiSeg> segs; size_t text = 0; bool ok = true; };
         const int64_t wave = (int64_t)threads * 4;
         for (int64_t w0 = 0; w0 < n_tasks; w0 += wave) {
             const int64_t w1 = std::min(n_tasks, w0 + wave);
@@ -212,6 +232,19 @@ struct BgzWriter {
                         T.blk_in.push_back((uint32_t)len); T.blk_out.push_back((uint32_t)(T.out.size() - before));
                         pos += len;
                     }
+                    if (csi && T.ok) {      // index entries of the task's lines, as (block, offset) pairs: walk its blocks
+                        CsiSegAgg agg; size_t b = 0, blk_start_text = 0;
+                        const int64_t a = t * kRunsPerTask;
+                        for (size_t i = 0; i < T.line_off.size(); i++) {
+                            while (T.line_off[i] >= blk_start_text + T.blk_in[b]) { blk_start_text += T.blk_in[b]; b++; }
+                            const size_t end_text = i + 1 < T.line_off.size() ? T.line_off[i + 1] : T.text;
+                            // the line ends inside the same block (blocks end on line boundaries); the end offset of the last line of a block points at the next block
+                            const bool last_in_block = end_text == blk_start_text + T.blk_in[b];
+                            int64_t ib = 0, ie = 0; interval(a + (int64_t)i, &ib, &ie);
+                            agg.line(ib, ie, (uint32_t)b, (uint32_t)(T.line_off[i] - blk_start_text), last_in_block ? (uint32_t)b + 1 : (uint32_t)b, last_in_block ? 0u : (uint32_t)(end_text - blk_start_text));
+                        }
+                        agg.finish(); T.segs.swap(agg.segs);
+                    }
                 }
             };
             const int nt = (int)std::min<int64_t>(threads, w1 - w0);
@@ -222,19 +255,10 @@ struct BgzWriter {
             for (int64_t t = w0; t < w1; t++) {
                 Task& T = tasks[(size_t)(t - w0)];
                 if (!T.ok) { failed = true; return; }
-                if (csi) {      // virtual offsets of every line of the task: walk its blocks
-                    size_t b = 0, blk_start_text = 0; uint64_t blk_coff = coff;
-                    const int64_t a = t * kRunsPerTask;
-                    for (size_t i = 0; i < T.line_off.size(); i++) {
-                        while (T.line_off[i] >= blk_start_text + T.blk_in[b]) { blk_start_text += T.blk_in[b]; blk_coff += T.blk_out[b]; b++; }
-                        const size_t end_text = i + 1 < T.line_off.size() ? T.line_off[i + 1] : T.text;
-                        const uint64_t v0 = (blk_coff << 16) | (uint64_t)(T.line_off[i] - blk_start_text);
-                        // the line ends inside the same block (blocks end on line boundaries); the end offset of the last line of a block points at the next block
-                        const bool last_in_block = end_text == blk_start_text + T.blk_in[b];
-                        const uint64_t v1 = last_in_block ? ((blk_coff + T.blk_out[b]) << 16) : ((blk_coff << 16) | (uint64_t)(end_text - blk_start_text));
-                        int64_t ib = 0, ie = 0; interval(a + (int64_t)i, &ib, &ie);
-                        csi->add(chrom, ib, ie, v0, v1);
-                    }
+                if (csi) {
+                    std::vector<uint64_t> bc(T.blk_out.size() + 1, coff);
+                    for (size_t j = 0; j < T.blk_out.size(); j++) bc[j + 1] = bc[j] + T.blk_out[j];
+                    for (const CsiSeg& g : T.segs) csi->add_seg(chrom, g.bin, g.w0, g.w1, (bc[g.b0] << 16) | g.u0, (bc[g.b1] << 16) | g.u1);
                 }
                 put(T.out);
             }
@@ -250,16 +274,31 @@ struct BgzWriter {
         flush_block(buf.size());
         if (csi) {
             auto digits = [](int64_t v) { int d = v < 0 ? 2 : 1; if (v < 0) v = -v; while (v >= 10) { v /= 10; d++; } return d; };
-            for (int64_t k = 0; k < n_mem; k++) {
-                const int64_t a = (int64_t)mem[k].first_run, b = k + 1 < n_mem ? (int64_t)mem[k + 1].first_run : n;
-                const uint64_t c0 = coff + mem[k].offset; uint64_t uoff = 0;
-                for (int64_t i = a; i < b; i++) {
-                    const uint64_t len = chrom.size() + 4 + (uint64_t)digits(st[i]) + (uint64_t)digits(en[i]) + (labels ? (uint64_t)(*labels)[(size_t)val[i]].size() : (uint64_t)digits(val[i]));
-                    const uint64_t v0 = (c0 << 16) | uoff; uoff += len;
-                    csi->add(chrom, st[i], en[i], v0, i + 1 == b ? (c0 + mem[k].csize) << 16 : (c0 << 16) | uoff);
+            const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(threads, n_mem / 64));
+            std::vector<std::vector<CsiSeg>> segs((size_t)nt); std::vector<char> bad((size_t)nt, 0);
+            auto work = [&](int w) {      // members [k0, k1): their lines' index entries as (member, offset) pairs
+                const int64_t k0 = n_mem * w / nt, k1 = n_mem * (w + 1) / nt;
+                CsiSegAgg agg;
+                for (int64_t k = k0; k < k1; k++) {
+                    const int64_t a = (int64_t)mem[k].first_run, b = k + 1 < n_mem ? (int64_t)mem[k + 1].first_run : n;
+                    uint64_t uoff = 0;
+                    for (int64_t i = a; i < b; i++) {
+                        const uint64_t len = chrom.size() + 4 + (uint64_t)digits(st[i]) + (uint64_t)digits(en[i]) + (labels ? (uint64_t)(*labels)[(size_t)val[i]].size() : (uint64_t)digits(val[i]));
+                        const bool last = i + 1 == b;
+                        agg.line(st[i], en[i], (uint32_t)k, (uint32_t)uoff, last ? (uint32_t)k + 1 : (uint32_t)k, last ? 0u : (uint32_t)(uoff + len));
+                        uoff += len;
+                    }
+                    if (uoff != mem[k].isize) { bad[(size_t)w] = 1; return; }
                 }
-                if (uoff != mem[k].isize) { failed = true; return; }
-            }
+                agg.finish(); segs[(size_t)w].swap(agg.segs);
+            };
+            std::vector<std::thread> pool;
+            for (int w = 1; w < nt; w++) pool.emplace_back(work, w);
+            work(0);
+            for (auto& th : pool) th.join();
+            for (char b : bad) if (b) { failed = true; return; }
+            auto mc = [&](uint32_t k) { return coff + ((int64_t)k < n_mem ? mem[k].offset : (uint64_t)n_bytes); };
+            for (const auto& vs : segs) for (const CsiSeg& g : vs) csi->add_seg(chrom, g.bin, g.w0, g.w1, (mc(g.b0) << 16) | g.u0, (mc(g.b1) << 16) | g.u1);
         }
         if (fwrite(bytes, 1, (size_t)n_bytes, f) != (size_t)n_bytes) failed = true;
         coff += (uint64_t)n_bytes;
