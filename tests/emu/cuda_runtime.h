@@ -26,6 +26,8 @@
 #define __launch_bounds__(...)
 #define __shared__ static
 struct uint4 { uint32_t x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
+inline int4 make_int4(int x, int y, int z, int w) { int4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
 
 // ---- the few runtime calls the host sequence of K10 makes (bedgz_host.cuh): everything is synchronous host memory -----------------
 typedef int cudaError_t;
@@ -90,5 +92,46 @@ inline unsigned __reduce_add_sync(unsigned, unsigned v) {
     return s;
 }
 inline unsigned atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+template <class T> inline T __shfl_sync(unsigned, T v, int src) {
+    emu::Warp& w = emu::warp();
+    uint64_t bits = 0; memcpy(&bits, &v, sizeof v); w.slot[emu::lane()] = bits;
+    w.bar->arrive_and_wait();
+    T r; memcpy(&r, &w.slot[src & 31], sizeof r);
+    w.bar->arrive_and_wait();
+    return r;
+}
+template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned o) {
+    emu::Warp& w = emu::warp(); const unsigned l = emu::lane();
+    uint64_t bits = 0; memcpy(&bits, &v, sizeof v); w.slot[l] = bits;
+    w.bar->arrive_and_wait();
+    T r = v; if (l + o < 32) memcpy(&r, &w.slot[l + o], sizeof r);
+    w.bar->arrive_and_wait();
+    return r;
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+    emu::Warp& w = emu::warp(); w.slot[emu::lane()] = pred ? 1 : 0;
+    w.bar->arrive_and_wait();
+    unsigned m = 0; for (int i = 0; i < 32; i++) m |= (unsigned)(w.slot[i] & 1) << i;
+    w.bar->arrive_and_wait();
+    return m;
+}
+inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == 0xffffffffu; }
+// atomics: every CUDA overload the emulated kernels use, on the GCC builtins
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+template <class T> inline T emu_atomic_minmax(T* p, T v, bool is_min) { T o = __atomic_load_n(p, __ATOMIC_RELAXED); while ((is_min ? v < o : v > o) && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+inline unsigned atomicMin(unsigned* p, unsigned v) { return emu_atomic_minmax(p, v, true); }
+inline unsigned atomicMax(unsigned* p, unsigned v) { return emu_atomic_minmax(p, v, false); }
+inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { return emu_atomic_minmax(p, v, false); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+template <class T> inline T __ldg(const T* p) { return *p; }
+inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }      // (x86-64 SSE2: IEEE double, round to nearest)
+inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { sh &= 31; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }

@@ -1,0 +1,104 @@
+// reduce_emu.cpp -- K6 (scan.cuh: scan_fused_kernel) and K7 (regions.cuh: windows_mean_kernel, windows_kernel, regions_kernel)
+// executed on the CPU under tests/emu/cuda_runtime.h with the launch geometry of run_scan / msd_windows / msd_regions
+// (mosdepth_b200/csrc/msd_api.cu), against a plain restatement of the reference's arithmetic:
+//   to_coverage mosdepth.nim:54-56 (int32 prefix sum, wraps), inc :417-437, newDepthStat depthstat.nim:39-45, imean :399-413
+//   (sequential float64 chain / CountStat median depthstat.nim:16-30), window bins :737-739, thresholds :549-553.
+// Float means must be BIT-identical (Q1).  TEST INFRASTRUCTURE ONLY; prints "ok ..." or the first difference and exits non-zero.
+//   usage: reduce_emu <tlen> <window> <max_ctas> [seed]
+#include <cinttypes>
+#include <cstdlib>
+#include <string>
+#include "../../mosdepth_b200/csrc/scan.cuh"
+#include "../../mosdepth_b200/csrc/regions.cuh"
+
+using namespace msd;
+typedef unsigned long long ull;
+
+static unsigned grid_for(uint64_t n, int threads, int max_ctas) { uint64_t g = (n + threads - 1) / threads; if (g < 1) g = 1; if (g > (uint64_t)max_ctas) g = max_ctas; return (unsigned)g; }
+static int fail(const char* what, long long at, double a, double b) { printf("DIFF %s at %lld: kernel %.17g, expected %.17g\n", what, at, a, b); return 1; }
+static int64_t nim_to_int(double f) { return f >= 0 ? (int64_t)(f + 0.5) : (int64_t)(f - 0.5); }
+
+struct Stat { ull len = 0, sum = 0; uint32_t mn = 0xffffffffu, mx = 0; };
+static void stat_add(Stat& s, const int32_t* v, int64_t n) { s.len += (ull)(n > 0 ? n : 0); for (int64_t i = 0; i < n; i++) { const uint32_t x = (uint32_t)v[i]; s.sum += x; if (x < s.mn) s.mn = x; if (x > s.mx) s.mx = x; } }
+static double imean(const int32_t* arr, uint32_t len, uint32_t start, uint32_t stop, bool median) {
+    if (start > len) return 0;
+    const uint32_t e = stop < len ? stop : len;
+    if (median) {
+        static std::vector<uint32_t> cnt(65536); std::fill(cnt.begin(), cnt.end(), 0u); int64_t n = 0;
+        for (uint32_t i = start; i < e; i++) { const int32_t v = arr[i]; cnt[v > 65535 ? 65535 : v]++; n++; }
+        if (n == 0) return 0;
+        const int64_t stop_n = (int64_t)(0.5 + (double)n * 0.5); int64_t cum = 0;
+        for (int i = 0; i < 65536; i++) { cum += cnt[i]; if (cum >= stop_n) return (double)i; }
+        return 0;
+    }
+    const double L = (double)(uint32_t)(stop - start); volatile double r = 0;
+    for (uint32_t i = start; i < e; i++) { volatile double q = (double)arr[i] / L; r = r + q; }
+    return r;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 4) { fprintf(stderr, "usage: reduce_emu tlen window max_ctas [seed]\n"); return 2; }
+    const uint32_t tlen = (uint32_t)strtoul(argv[1], nullptr, 10), window = (uint32_t)strtoul(argv[2], nullptr, 10); const int max_ctas = atoi(argv[3]);
+    uint64_t x = 0x9e3779b97f4a7c15ull ^ (argc > 4 ? strtoull(argv[4], nullptr, 10) : 0);
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    // +1/-1 deltas of reads of 30..150 bases (depth stays >= 0), a few very deep spots (bins beyond the shared-memory histogram)
+    const uint32_t L = tlen + 1;
+    int32_t* arr = nullptr; if (posix_memalign((void**)&arr, 128, ((size_t)L + 64) * 4)) return 2;
+    memset(arr, 0, ((size_t)L + 64) * 4);
+    const uint64_t n_reads = (uint64_t)tlen * 30 / 100 + 3;
+    for (uint64_t r = 0; r < n_reads; r++) { const uint32_t s = (uint32_t)(rnd() % tlen), len = 30 + (uint32_t)(rnd() % 121); const uint32_t e = s + len < tlen ? s + len : tlen; arr[s] += 1; arr[e] -= 1; }
+    for (int k = 0; k < 3 && tlen > 1000; k++) { const uint32_t s = (uint32_t)(rnd() % (tlen - 600)); arr[s] += 2000 + 70000 * k; arr[s + 500] -= 2000 + 70000 * k; }
+    std::vector<int32_t> want(arr, arr + L);
+    { uint32_t s = 0; for (uint32_t i = 0; i < L; i++) { s += (uint32_t)want[i]; want[i] = (int32_t)s; } }
+    // ---- K6: run_scan(arr, n_scan = tlen + 1, n_stat = tlen, do_stats = 1) ----------------------------------------------------------
+    const uint64_t n_tiles = ((uint64_t)L + kScanTile - 1) / kScanTile;
+    std::vector<ull> tile_state(n_tiles, 0), hist(kDistBins, 0); uint32_t ticket = 0; ContigAccum acc{0, 0xffffffffu, 0, 0, 0};
+    emu::launch((unsigned)std::min<uint64_t>(n_tiles, (uint64_t)max_ctas), kScanThreads, [&]() { scan_fused_kernel(arr, L, tlen, tile_state.data(), &ticket, hist.data(), &acc, 1); });
+    for (uint32_t i = 0; i < L; i++) if (arr[i] != want[i]) return fail("prefix sum", i, arr[i], want[i]);
+    { std::vector<ull> h(kDistBins, 0); Stat st;
+      for (uint32_t i = 0; i < tlen; i++) { int32_t v = want[i]; if (v > (int32_t)kMaxCoverage) v = kMaxCoverage - 10; if (v >= 0) h[v]++; }
+      stat_add(st, want.data(), tlen);
+      for (int b = 0; b < kDistBins; b++) if (h[b] != hist[b]) return fail("contig dist bin", b, (double)hist[b], (double)h[b]);
+      if (acc.cum_depth != st.sum || acc.min_depth != st.mn || acc.max_depth != st.mx) return fail("contig stats (sum)", 0, (double)acc.cum_depth, (double)st.sum); }
+    // ---- K7 windows: msd_windows(mean) and msd_windows(median) ----------------------------------------------------------------------
+    const long long nw = tlen ? ((long long)tlen + window - 1) / window : 0;
+    for (int median = 0; median < 2; median++) {
+        std::vector<double> val((size_t)nw + 1, -1.0); RegionAccum ra{0, 0, 0xffffffffu, 0, 0, 0}; std::vector<ull> d512(kWindowDistBins, 0);
+        if (median) emu::launch(grid_for((uint64_t)nw, 256, max_ctas), 256, [&]() { windows_kernel(arr, tlen, window, nw, 1, val.data(), &ra, d512.data()); });
+        else emu::launch(grid_for((uint64_t)nw, kWinWarps * 32, std::max(1, max_ctas / 2)), kWinWarps * 32, [&]() { windows_mean_kernel(arr, tlen, window, nw, val.data(), &ra, d512.data()); });
+        std::vector<ull> w512(kWindowDistBins, 0); Stat st;
+        for (long long k = 0; k < nw; k++) {
+            const uint32_t s = (uint32_t)((ull)k * window), e = (uint32_t)std::min<ull>(((ull)k + 1) * window, tlen);
+            const double me = imean(want.data(), L, s, e, median != 0);
+            if (memcmp(&me, &val[(size_t)k], 8) != 0) return fail(median ? "window median" : "window mean (bit pattern)", k, val[(size_t)k], me);
+            const int64_t bin = nim_to_int(me); w512[bin < 511 ? bin : 511]++;
+            const uint32_t a = s < L ? s : L, b = L < e ? L : e; stat_add(st, want.data() + a, b > a ? (int64_t)(b - a) : 0);
+        }
+        for (int b = 0; b < kWindowDistBins; b++) if (w512[b] != d512[b]) return fail("window dist bin", b, (double)d512[b], (double)w512[b]);
+        if (ra.cum_length != st.len || ra.cum_depth != st.sum || ra.min_depth != st.mn || ra.max_depth != st.mx) return fail("window region stats (sum)", median, (double)ra.cum_depth, (double)st.sum);
+    }
+    // ---- K7 regions: msd_regions with thresholds, mean and median; intervals of 1..3000 bases, some reaching past the contig end (Q5) -----
+    const long long nr = std::min<long long>(20000, (long long)tlen / 50 + 5);
+    std::vector<uint32_t> rs((size_t)nr), re((size_t)nr);
+    for (long long k = 0; k < nr; k++) { const uint32_t s = (uint32_t)(rnd() % ((ull)tlen + 40)), len = 1 + (uint32_t)(rnd() % (k % 7 == 0 ? 3000 : 300)); rs[(size_t)k] = s; re[(size_t)k] = s + len; }
+    const int32_t thr[4] = {1, 10, 20, 30};
+    for (int median = 0; median < 2; median++) {
+        std::vector<double> val((size_t)nr, -1.0); RegionAccum ra{0, 0, 0xffffffffu, 0, 0, 0}; std::vector<ull> dist(kDistBins, 0), cnt((size_t)nr * 4, 0);
+        emu::launch(grid_for((uint64_t)nr, 256, max_ctas), 256, [&]() { regions_kernel(arr, tlen, nr, rs.data(), re.data(), median, val.data(), &ra, dist.data(), thr, 4, cnt.data()); });
+        std::vector<ull> h(kDistBins, 0); Stat st;
+        for (long long k = 0; k < nr; k++) {
+            const uint32_t s = rs[(size_t)k], e = re[(size_t)k];
+            const double me = imean(want.data(), L, s, e, median != 0);
+            if (memcmp(&me, &val[(size_t)k], 8) != 0) return fail(median ? "region median" : "region mean (bit pattern)", k, val[(size_t)k], me);
+            const uint32_t a = s < L ? s : L, b = L < e ? L : e; stat_add(st, want.data() + a, b > a ? (int64_t)(b - a) : 0);
+            if (s < L) for (uint32_t i = s; i < (e < L ? e : L); i++) { int32_t v = want[i]; if (v > (int32_t)kMaxCoverage) v = kMaxCoverage - 10; if (v >= 0) h[v]++; }      // inc, :417-437
+            for (uint32_t i = s; i < (e < L ? e : L); i++) for (int j = 0; j < 4; j++) { if (want[i] < thr[j]) break; if (--cnt[(size_t)k * 4 + j] == ~0ull) return fail("threshold count", k, -1, 0); }
+        }
+        for (size_t i = 0; i < cnt.size(); i++) if (cnt[i]) return fail("threshold count", (long long)(i / 4), (double)(long long)cnt[i], 0);
+        for (int b = 0; b < kDistBins; b++) if (h[b] != dist[b]) return fail("region dist bin", b, (double)dist[b], (double)h[b]);
+        if (ra.cum_length != st.len || ra.cum_depth != st.sum || ra.min_depth != st.mn || ra.max_depth != st.mx) return fail("region stats (length)", median, (double)ra.cum_length, (double)st.len);
+    }
+    printf("ok tlen %u window %u: %llu scan tiles, %lld windows, %lld regions\n", tlen, window, (ull)n_tiles, nw, nr);
+    free(arr);
+    return 0;
+}

@@ -36,3 +36,26 @@ def test_kernels_under_emulation(emu, chrom, n_bases, max_ctas, seed, mode):
     gz = (d / f"e{seed}.gz").read_bytes()
     assert n_dev == n_host and len(text) == text_bytes and len(gz) == gz_bytes and (n_members >= 1 or n_dev == 0)
     assert gzip.decompress(gz) == text
+
+
+@pytest.fixture(scope="module")
+def reduce_emu(tmp_path_factory):
+    d = tmp_path_factory.mktemp("remu")
+    exe = d / "reduce_emu"
+    subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", f"-I{ROOT / 'tests' / 'emu'}", "-o", str(exe), str(ROOT / "tests" / "emu" / "reduce_emu.cpp")], check=True)
+    return exe
+
+
+# (tlen, window, CTA cap, seed): many scan tiles on few persistent CTAs (decoupled look-back), window 1, a window longer than the contig,
+# windows wider than the quotient table's 1024 depths need, a contig of one tile + one cell
+REDUCE_CASES = [(300000, 500, 7, 4), (100000, 1, 16, 5), (65536, 100000000, 1184, 6), (123457, 3333, 5, 7), (4097, 4096, 2, 8), (200000, 33, 1184, 9), (16569, 100, 1184, 2),
+                (777, 37, 3, 3)]
+
+
+@pytest.mark.parametrize("tlen,window,max_ctas,seed", REDUCE_CASES, ids=[f"{c[0]}-{c[1]}-{c[2]}" for c in REDUCE_CASES])
+def test_scan_window_region_kernels_under_emulation(reduce_emu, tlen, window, max_ctas, seed):
+    """K6 scan_fused_kernel and K7 windows_mean_kernel / windows_kernel / regions_kernel under the CUDA stand-in against a plain
+    restatement of the reference's arithmetic: prefix sum with int32 wrap, dist bins, depth stats, the sequential float64 mean bit for
+    bit (Q1), the CountStat median (Q7), window bins (Q2), thresholds, intervals that reach past the contig end (Q5)."""
+    r = subprocess.run([str(reduce_emu), str(tlen), str(window), str(max_ctas), str(seed)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
