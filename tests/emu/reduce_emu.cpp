@@ -1,4 +1,4 @@
-// reduce_emu.cpp -- K6 (scan.cuh: scan_fused_kernel) and K7 (regions.cuh: windows_mean_kernel, windows_kernel, regions_kernel)
+// reduce_emu.cpp -- K6 (scan.cuh: scan_fused_kernel) and K7 (regions.cuh: windows_mean_kernel, windows_all_kernel, windows_kernel, regions_kernel)
 // executed on the CPU under tests/emu/cuda_runtime.h with the launch geometry of run_scan / msd_windows / msd_regions
 // (mosdepth_b200/csrc/msd_api.cu), against a plain restatement of the reference's arithmetic:
 //   to_coverage mosdepth.nim:54-56 (int32 prefix sum, wraps), inc :417-437, newDepthStat depthstat.nim:39-45, imean :399-413
@@ -97,6 +97,34 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < cnt.size(); i++) if (cnt[i]) return fail("threshold count", (long long)(i / 4), (double)(long long)cnt[i], 0);
         for (int b = 0; b < kDistBins; b++) if (h[b] != dist[b]) return fail("region dist bin", b, (double)dist[b], (double)h[b]);
         if (ra.cum_length != st.len || ra.cum_depth != st.sum || ra.min_depth != st.mn || ra.max_depth != st.mx) return fail("region stats (length)", median, (double)ra.cum_length, (double)st.len);
+    }
+    // ---- K7 windows_all_kernel (msd_prefetch_windows: every contig's windows in ONE launch, the kernel of the --by <int> -n -x path) ----------
+    {   // an arena of three contigs: this one, its first third, and a 1-base contig; each padded to 128 bytes like the library's arena
+        const uint32_t tl[3] = {tlen, tlen / 3 + 1, 1};
+        std::vector<ull> off(3); ull cells = 0;
+        for (int c = 0; c < 3; c++) { off[c] = cells; cells += (((ull)tl[c] + 1) * 4 + 127) / 128 * 32; }
+        int32_t* arena = nullptr; if (posix_memalign((void**)&arena, 128, (cells + 64) * 4)) return 2;
+        memset(arena, 0, (cells + 64) * 4);
+        for (int c = 0; c < 3; c++) for (uint32_t i = 0; i <= tl[c] && i < L; i++) arena[off[c] + i] = want[i];      // (the sentinel cell of a prefix is a depth like any other)
+        std::vector<WinContig> table; long long groups = 0, windows = 0;
+        for (int c = 0; c < 3; c++) { const long long n = ((long long)tl[c] + window - 1) / window; WinContig w; w.arr_off = off[c]; w.first_group = groups; w.first_window = windows; w.n_windows = n; w.tlen = tl[c]; w.pad = 0; table.push_back(w); groups += (n + 31) / 32; windows += n; }
+        std::vector<double> val((size_t)windows, -1.0); std::vector<RegionAccum> ra(3, RegionAccum{0, 0, 0xffffffffu, 0, 0, 0}); std::vector<ull> d512(3 * kWindowDistBins, 0);
+        const unsigned grid = (unsigned)std::min<long long>((groups + kWinWarps - 1) / kWinWarps, (long long)std::max(1, max_ctas / 2));
+        emu::launch(grid, kWinWarps * 32, [&]() { windows_all_kernel(arena, table.data(), 3, groups, window, val.data(), ra.data(), d512.data()); });
+        for (int c = 0; c < 3; c++) {
+            const int32_t* a0 = arena + off[c]; const uint32_t Lc = tl[c] + 1;
+            std::vector<ull> w512(kWindowDistBins, 0); Stat st;
+            for (long long k = 0; k < table[(size_t)c].n_windows; k++) {
+                const uint32_t s = (uint32_t)((ull)k * window), e = (uint32_t)std::min<ull>(((ull)k + 1) * window, tl[c]);
+                const double me = imean(a0, Lc, s, e, false), got = val[(size_t)(table[(size_t)c].first_window + k)];
+                if (memcmp(&me, &got, 8) != 0) return fail("windows_all mean (bit pattern)", k, got, me);
+                const int64_t bin = nim_to_int(me); w512[bin < 511 ? bin : 511]++;
+                stat_add(st, a0 + s, (int64_t)e - s);
+            }
+            for (int b = 0; b < kWindowDistBins; b++) if (w512[b] != d512[(size_t)c * kWindowDistBins + b]) return fail("windows_all dist bin", b, (double)d512[(size_t)c * kWindowDistBins + b], (double)w512[b]);
+            if (ra[(size_t)c].cum_length != st.len || ra[(size_t)c].cum_depth != st.sum || ra[(size_t)c].min_depth != st.mn || ra[(size_t)c].max_depth != st.mx) return fail("windows_all region stats (sum)", c, (double)ra[(size_t)c].cum_depth, (double)st.sum);
+        }
+        free(arena);
     }
     printf("ok tlen %u window %u: %llu scan tiles, %lld windows, %lld regions\n", tlen, window, (ull)n_tiles, nw, nr);
     free(arr);
