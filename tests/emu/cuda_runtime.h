@@ -127,6 +127,21 @@ template <class T> inline T emu_atomic_minmax(T* p, T v, bool is_min) { T o = __
 inline unsigned atomicMin(unsigned* p, unsigned v) { return emu_atomic_minmax(p, v, true); }
 inline unsigned atomicMax(unsigned* p, unsigned v) { return emu_atomic_minmax(p, v, false); }
 inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { return emu_atomic_minmax(p, v, false); }
+inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+    emu::Warp& w = emu::warp(); w.slot[emu::lane()] = v;
+    w.bar->arrive_and_wait();
+    unsigned m = 0xffffffffu; for (int i = 0; i < 32; i++) m = std::min(m, (unsigned)w.slot[i]);
+    w.bar->arrive_and_wait();
+    return m;
+}
+// Votes under divergence: the stand-in's threads are independent, so "the lanes that are converged here" is the caller alone -- a
+// legal answer for __activemask() on any Volta-or-later part, and what code written for independent thread scheduling must accept.
+// A single-lane mask needs no exchange; the aggregated atomics of records.cuh then degenerate to one atomic per thread.
+inline unsigned __activemask() { return 1u << emu::lane(); }
+template <class T> inline unsigned __match_any_sync(unsigned mask, T) { if (mask & (mask - 1)) { fprintf(stderr, "emu: __match_any_sync over several lanes is not provided\n"); abort(); } return mask; }
+inline unsigned __reduce_max_sync(unsigned mask, unsigned v) { if (mask & (mask - 1)) { fprintf(stderr, "emu: __reduce_max_sync over several lanes is not provided\n"); abort(); } return v; }
+inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }      // (x86-64 SSE2: IEEE double, round to nearest)

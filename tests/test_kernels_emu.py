@@ -59,3 +59,28 @@ def test_scan_window_region_kernels_under_emulation(reduce_emu, tlen, window, ma
     bit (Q1), the CountStat median (Q7), window bins (Q2), thresholds, intervals that reach past the contig end (Q5)."""
     r = subprocess.run([str(reduce_emu), str(tlen), str(window), str(max_ctas), str(seed)], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
+@pytest.fixture(scope="module")
+def records_emu(tmp_path_factory):
+    d = tmp_path_factory.mktemp("recemu")
+    exe = d / "records_emu"
+    subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", f"-I{ROOT / 'tests' / 'emu'}", "-o", str(exe), str(ROOT / "tests" / "emu" / "records_emu.cpp"), "-lz"], check=True)
+    return exe
+
+
+# (fixture, blocks per chunk): one block per chunk makes records and overlapping mates straddle chunk boundaries (carry buffer, live list)
+RECORD_CASES = [("empty-tids.bam", 1), ("nanopore.bam", 1), ("overlapping-pairs.bam", 1), ("full-fragment-pairs.bam", 2)]
+MODES = [(0, []), (1, ["-x"]), (2, ["-a"])]
+
+
+@pytest.mark.parametrize("name,per_chunk", RECORD_CASES, ids=[f"{c[0]}-{c[1]}" for c in RECORD_CASES])
+@pytest.mark.parametrize("mode,flags", MODES, ids=["default", "fast", "fragment"])
+def test_framing_records_and_mate_join_under_emulation(records_emu, oracle_bin, tmp_path, name, per_chunk, mode, flags):
+    """K2 (framing), K3/K5 (filters + CIGAR events) and K4 (mate join with its live list) under the CUDA stand-in, chunk by chunk in
+    msd_run's launch order, blocks inflated by zlib: the per-base output must equal the oracle's byte for byte in all three modes."""
+    from conftest import FIX, run_tool
+    run_tool(oracle_bin, flags + ["o", FIX / name], tmp_path)
+    r = subprocess.run([str(records_emu), str(FIX / name), str(tmp_path / "e.bed"), str(mode), str(per_chunk), "5"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+    assert (tmp_path / "e.bed").read_bytes() == (tmp_path / "o.per-base.bed").read_bytes()
