@@ -6,7 +6,7 @@ NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-f
 LIB := mosdepth_b200/libmosdepth_b200.so
 CSRC := $(wildcard mosdepth_b200/csrc/*.cu mosdepth_b200/csrc/*.cuh) include/mosdepth_b200.h
 
-all: $(LIB) mosdepth_b200/bin/mosdepth-b200 tools/gen_bam tools/inflate_model tools/bedgz_model oracle
+all: $(LIB) mosdepth_b200/bin/mosdepth-b200 tools/gen_bam tools/inflate_model tools/bedgz_model tools/h2d_probe oracle
 
 $(LIB): $(CSRC)
 	$(NVCC) $(NVFLAGS) -shared -o $@ mosdepth_b200/csrc/msd_api.cu 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
@@ -27,10 +27,14 @@ tools/inflate_model: tools/inflate_model.cpp mosdepth_b200/csrc/inflate_core.cuh
 tools/bedgz_model: tools/bedgz_model.cpp mosdepth_b200/csrc/bedgz_core.cuh mosdepth_b200/csrc/common.cuh
 	$(CXX) -O2 -std=c++17 -Wall -I/usr/local/cuda/include -o $@ $< -lz
 
+# host->device copy ceiling of the box at 1..N GPUs (pinned / registered mmap / bounce), profiles/*h2d_probe*
+tools/h2d_probe: tools/h2d_probe.cu
+	$(NVCC) $(ARCH) -O2 -std=c++17 -o $@ $< -Xcompiler -pthread
+
 oracle:
 	$(MAKE) -s -C oracle
 
 clean:
-	rm -f $(LIB) mosdepth_b200/bin/mosdepth-b200 tools/gen_bam tools/inflate_model tools/bedgz_model build_ptxas.log
+	rm -f $(LIB) mosdepth_b200/bin/mosdepth-b200 tools/gen_bam tools/inflate_model tools/bedgz_model tools/h2d_probe build_ptxas.log
 	$(MAKE) -C oracle clean
 .PHONY: all oracle clean

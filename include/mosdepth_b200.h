@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MSD_ABI_VERSION 1
+#define MSD_ABI_VERSION 2
 
 /* error codes */
 #define MSD_OK 0
@@ -32,6 +32,8 @@ extern "C" {
 #define MSD_EDATA (-14)      /* corrupt DEFLATE stream or BAM record (reference: quit on hts.BamError, mosdepth.nim:190-191) */
 #define MSD_ENOMEM (-15)     /* a device-side table overflowed (message says which knob) */
 #define MSD_ENEGDEPTH (-16)  /* negative depth met in median mode (reference raises IndexDefect, depthstat.nim:18-19) */
+#define MSD_ESPAN (-17)      /* a shard's span does not hold every record its owned records depend on (msd_set_contig_range) */
+#define MSD_ECOMM (-18)      /* NCCL missing or a collective failed */
 
 /* msd_set_filters mode: which branch of coverage() is taken (mosdepth.nim:292,342,346,355) */
 #define MSD_MODE_DEFAULT 0   /* CIGAR blocks + mate-overlap correction */
@@ -136,7 +138,9 @@ int64_t msd_windows(msd_ctx *ctx, int tid, uint32_t window, int use_median, doub
  * value_out[n] as above; region_stat accumulates newDepthStat(arr[min(start,L)..<min(L,stop)]) with L = tlen+1
  * (:719,:724); region_dist: per-base histogram inside the regions (inc, :741), same convention as
  * msd_contig_stats; thresholds (ascending, n_thr may be 0): thr_counts[i*n_thr + j] = #bases of region i with
- * depth >= thresholds[j] (:549-553; slices are clamped to the array, see DESIGN.md "Divergences"). */
+ * depth >= thresholds[j] (:549-553; slices are clamped to the array, see DESIGN.md "Divergences").
+ * region_stat == NULL: the call does not count towards the genome-wide `total_region` accumulators (msd_totals) -- the host
+ * uses that for the thresholds of --by <window>, whose windows msd_windows() has already accounted for. */
 int msd_regions(msd_ctx *ctx, int tid, int64_t n, const uint32_t *start, const uint32_t *stop, int use_median,
                 double *value_out, msd_depth_stat *region_stat, int64_t *region_dist, int64_t dist_cap,
                 int64_t *dist_len, const int32_t *thresholds, int n_thr, int64_t *thr_counts);
@@ -182,22 +186,52 @@ int msd_quantized_bgzf(msd_ctx *ctx, int tid, const int64_t *quants, int n_q, co
                        int64_t *n_members, const int32_t **start, const int32_t **stop, const int32_t **bin,
                        int64_t *n_runs);
 
-/* -- multi-GPU plumbing ---------------------------------------------------------------------------------- *
+/* -- multi-GPU: one context per GPU ------------------------------------------------------------------------ *
  * Device pointer + element count of this context's genome-wide accumulators, kept up to date by
- * msd_contig_stats / msd_windows / msd_regions (sum_into, mosdepth.nim:761-764): int64 global dist bins,
- * int64 region dist bins, and {cum_length, cum_depth, min, max} x {global, region} packed as 8 int64.
- * A host running one process per GPU all-reduces these over NCCL (sum; min/max for the two extremes) to get
- * the `total` rows (mosdepth.nim:807-813).  msd_totals_reset() zeroes them. */
+ * msd_run / msd_contig_finalize (global) and msd_windows / msd_regions (region) -- sum_into, mosdepth.nim:761-764:
+ * int64 global dist bins, int64 region dist bins, and {cum_length, cum_depth, min, max} x {global, region} packed
+ * as 8 int64.  msd_totals_reset() zeroes them. */
 int msd_totals_device(msd_ctx *ctx, void **global_dist, void **region_dist, int64_t *n_bins, void **stats8);
 int msd_totals_reset(msd_ctx *ctx);
+
+/* The collectives of the path (north_star: "only the small dist/summary histograms are combined, via NCCL
+ * allreduce over NVLink, and prefix-sum carries cross shard boundaries inside a contig").  Nothing in the single-process
+ * reference corresponds to them.  One context per GPU and per rank; the ranks may be processes (bench.py under torchrun)
+ * or host threads of one process (mosdepth-b200 --gpus N).  NCCL is loaded with dlopen("libnccl.so.2") on first use:
+ * a process that never calls these needs no NCCL.
+ *   msd_comm_unique_id : rank 0 obtains the 128-byte NCCL id and hands it to the other ranks by any means.
+ *   msd_comm_init      : joins the communicator (collective: every rank calls it); rank r's shards are followed by
+ *                        rank r+1's in genome order.
+ *   msd_exchange_spills: after msd_run() on every rank.  For every contig this rank owns a range of
+ *                        (msd_set_contig_range): the depth its reads leave beyond the range end goes to rank+1
+ *                        (ncclSend straight out of the depth arena's staging buffer over NVLink), what rank-1 hands over is
+ *                        added at the range start, and every shard is finalised (msd_contig_finalize): one fixed-size
+ *                        message per neighbour, no host round trip between receive and add.  Replaces
+ *                        msd_contig_spill + msd_depth_copy + msd_depth_add + msd_contig_finalize per shard.
+ *   msd_totals_allreduce: sum_into / depth_stat `+` across ranks (mosdepth.nim:761-764, 807-813): ncclAllReduce of the two
+ *                        dist histograms (sum) and the eight stats (sum / min / max) in place in every rank's accumulators.
+ *   msd_totals         : read the accumulators back: the `total` and `total_region` rows.  dist arrays as in
+ *                        msd_contig_stats (length = 1 + highest non-zero bin, at least 1). */
+#define MSD_COMM_ID_BYTES 128
+int msd_comm_unique_id(void *id_out128);
+int msd_comm_init(msd_ctx *ctx, int rank, int world, const void *id128);
+int msd_comm_destroy(msd_ctx *ctx);
+int msd_exchange_spills(msd_ctx *ctx);
+int msd_totals_allreduce(msd_ctx *ctx);
+int msd_totals(msd_ctx *ctx, msd_depth_stat *global_stat, msd_depth_stat *region_stat, int64_t *global_dist, int64_t global_cap,
+               int64_t *global_len, int64_t *region_dist, int64_t region_cap, int64_t *region_len);
 
 /* ---- intra-contig sharding across GPUs (nothing in the single-process reference corresponds to it) --------
  * One context per GPU.  msd_set_contig_range(tid, lo, hi) before msd_run() makes this context the OWNER of the records of
  * contig tid with lo <= pos < hi (hi = 0: to the contig end; lo a multiple of 32, and of the window / 16384 if windows
  * will be asked for).  The spans given to msd_set_spans() must cover every owned record, at least one record at or
- * beyond hi (msd_run fails otherwise: extend the span) and, in default mode, the records up to one read length before
- * lo (an owned record may have to take its mate from them: they go through the filters and the `seen` table but emit
- * nothing).  After msd_run() the contig's array holds the prefix sum of this shard's own events.  Reads that start
+ * beyond hi (msd_run fails otherwise: extend the span) and, in default mode, the mates in front of lo that owned records
+ * take from the `seen` table (they go through the filters and the table but emit nothing).  The caller declares how far back
+ * its spans reach with msd_set_contig_cover(tid, covered_from): "every record of the contig with pos >= covered_from is in the
+ * spans" (0: from the contig's first record; an index-derived span start that is the linear-index entry of the 16,384-bp
+ * window w covers w * 16384).  msd_run checks it: an owned read that finds no mate in `seen` although its mate position lies
+ * before covered_from fails the run with MSD_ESPAN (extend the span start; msd_contig_span_need() says how far) instead of
+ * silently skipping an overlap correction.  Never declared: covered_from = lo.  After msd_run() the contig's array holds the prefix sum of this shard's own events.  Reads that start
  * before hi still cover [hi, hi + n): msd_contig_spill() says how far; that piece of depth is copied out
  * (msd_depth_copy) and added by the next shard (msd_depth_add) -- the prefix-sum carry across the shard boundary, as
  * depth rather than as one integer, because the reads of a shard all end within one read length of it.  Host or device
@@ -207,6 +241,10 @@ int msd_totals_reset(msd_ctx *ctx);
  * not available on a shard; fragment mode is not supported with ranges (a fragment starts before its read 1).
  * msd_contig_records() counts owned records only. */
 int msd_set_contig_range(msd_ctx *ctx, int tid, uint32_t lo, uint32_t hi);
+int msd_set_contig_cover(msd_ctx *ctx, int tid, uint32_t covered_from);
+/* After msd_run() failed with MSD_ESPAN: the position the span of contig tid has to reach back to (the smallest mate
+ * position an owned read looked for in vain) and the covered_from the run was checked against. */
+int msd_contig_span_need(msd_ctx *ctx, int tid, uint32_t *need_from, uint32_t *covered_from);
 int msd_contig_spill(msd_ctx *ctx, int tid, uint32_t *from, uint32_t *n);
 int msd_depth_copy(msd_ctx *ctx, int tid, uint32_t pos, uint32_t n, int32_t *dst, int dst_is_device);
 int msd_depth_add(msd_ctx *ctx, int tid, uint32_t pos, uint32_t n, const int32_t *src, int src_is_device);

@@ -23,8 +23,8 @@ EXPORTS = [
     "msd_abi_version", "msd_create", "msd_destroy", "msd_last_error", "msd_open", "msd_open_mem", "msd_stage",
     "msd_set_spans", "msd_set_targets", "msd_set_filters", "msd_run", "msd_last_run_info", "msd_contig_records",
     "msd_contig_stats", "msd_n_windows", "msd_prefetch_windows", "msd_windows", "msd_regions", "msd_per_base_runs", "msd_per_base_bgzf", "msd_quantized_runs", "msd_quantized_bgzf",
-    "msd_set_contig_range", "msd_contig_spill", "msd_depth_copy", "msd_depth_add", "msd_contig_finalize",
-    "msd_totals_device", "msd_totals_reset", "msd_mark", "msd_elapsed_ms", "msd_launch_count", "msd_debug_inflate", "msd_debug_depth", "msd_debug_cumsum", "msd_debug_crc32",
+    "msd_set_contig_range", "msd_set_contig_cover", "msd_contig_span_need", "msd_contig_spill", "msd_depth_copy", "msd_depth_add", "msd_contig_finalize",
+    "msd_totals_device", "msd_totals_reset", "msd_comm_unique_id", "msd_comm_init", "msd_comm_destroy", "msd_exchange_spills", "msd_totals_allreduce", "msd_totals", "msd_mark", "msd_elapsed_ms", "msd_launch_count", "msd_debug_inflate", "msd_debug_depth", "msd_debug_cumsum", "msd_debug_crc32",
 ]
 
 
@@ -78,6 +78,14 @@ def load_library():
     lib.msd_n_windows.argtypes = [u32, u32]; lib.msd_n_windows.restype = i64
     lib.msd_prefetch_windows.argtypes = [p, u32]
     lib.msd_set_contig_range.argtypes = [p, i32, u32, u32]
+    lib.msd_set_contig_cover.argtypes = [p, i32, u32]
+    lib.msd_contig_span_need.argtypes = [p, i32, C.POINTER(u32), C.POINTER(u32)]
+    lib.msd_comm_unique_id.argtypes = [p]
+    lib.msd_comm_init.argtypes = [p, i32, i32, p]
+    lib.msd_comm_destroy.argtypes = [p]
+    lib.msd_exchange_spills.argtypes = [p]
+    lib.msd_totals_allreduce.argtypes = [p]
+    lib.msd_totals.argtypes = [p, C.POINTER(DepthStat), C.POINTER(DepthStat), p, i64, C.POINTER(i64), p, i64, C.POINTER(i64)]
     lib.msd_contig_spill.argtypes = [p, i32, C.POINTER(u32), C.POINTER(u32)]
     lib.msd_depth_copy.argtypes = [p, i32, u32, u32, p, i32]
     lib.msd_depth_add.argtypes = [p, i32, u32, u32, p, i32]
@@ -203,6 +211,43 @@ class Context:
     # ---- intra-contig sharding (include/mosdepth_b200.h) ----
     def set_contig_range(self, tid, lo, hi):
         self._check(self.lib.msd_set_contig_range(self.h, tid, int(lo), int(hi)))
+
+    def set_contig_cover(self, tid, covered_from):
+        """Promise: the spans hold every record of contig tid with pos >= covered_from (default mode checks mates against it)."""
+        self._check(self.lib.msd_set_contig_cover(self.h, tid, int(covered_from)))
+
+    def contig_span_need(self, tid):
+        a, b = C.c_uint32(), C.c_uint32()
+        self._check(self.lib.msd_contig_span_need(self.h, tid, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # ---- the collectives of the path (NCCL; one context per rank) ----
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        rc = self.lib.msd_comm_unique_id(buf)
+        if rc < 0:
+            raise MsdError(rc, self.lib.msd_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, rank, world, unique_id: bytes):
+        self._check(self.lib.msd_comm_init(self.h, int(rank), int(world), C.c_char_p(unique_id)))
+
+    def comm_destroy(self):
+        self._check(self.lib.msd_comm_destroy(self.h))
+
+    def exchange_spills(self):
+        self._check(self.lib.msd_exchange_spills(self.h))
+
+    def totals_allreduce(self):
+        self._check(self.lib.msd_totals_allreduce(self.h))
+
+    def totals(self):
+        """(global DepthStat, region DepthStat, global dist, region dist) of the `total` rows -- msd_totals."""
+        g, r = DepthStat(), DepthStat(); ng, nr = C.c_int64(), C.c_int64()
+        self._check(self.lib.msd_totals(self.h, C.byref(g), C.byref(r), None, 0, C.byref(ng), None, 0, C.byref(nr)))
+        gd = np.zeros(max(ng.value, 1), dtype=np.int64); rd = np.zeros(max(nr.value, 1), dtype=np.int64)
+        self._check(self.lib.msd_totals(self.h, C.byref(g), C.byref(r), _ptr(gd), gd.size, C.byref(ng), _ptr(rd), rd.size, C.byref(nr)))
+        return g, r, gd[:ng.value], rd[:nr.value]
 
     def contig_spill(self, tid):
         a, n = C.c_uint32(), C.c_uint32()

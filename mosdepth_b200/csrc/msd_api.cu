@@ -24,6 +24,7 @@
 #include "runs.cuh"
 #include "scan.cuh"
 #include "bedgz_host.cuh"
+#include "comm.cuh"
 #include "ingest.hpp"
 
 using namespace msd;
@@ -73,6 +74,7 @@ struct msd_ctx {
     // intra-contig sharding (msd_set_contig_range)
     std::vector<uint32_t> range_lo, range_hi, max_end; std::vector<uint8_t> ranged, pending; bool any_ranged = false;
     uint32_t *d_range_lo = nullptr, *d_range_hi = nullptr, *d_max_end = nullptr; unsigned long long* d_n_beyond = nullptr;
+    uint32_t* d_min_need = nullptr; std::vector<uint32_t> min_need, covered_from;   // soundness of a shard's span start (default mode, msd_set_contig_cover)
     unsigned long long* d_nprefilter = nullptr; std::vector<long long> n_prefilter;
     std::vector<ContigResult> results; bool ran = false;
     // chunk buffers
@@ -93,7 +95,9 @@ struct msd_ctx {
     unsigned long long* d_tile_state = nullptr; uint64_t tile_state_cap = 0; uint32_t* d_scan_ticket = nullptr;
     unsigned long long* d_hist = nullptr; ContigAccum* d_acc = nullptr; RegionAccum* d_racc = nullptr;
     // per-contig results of msd_run gathered without a host round trip per contig
-    ContigAccum *d_acc_all = nullptr, *h_acc_all = nullptr; unsigned long long* h_hist_keep = nullptr; int acc_all_cap = 0, hist_keep_cap = 0;
+    // K6: every segment (contig or shard) of a run in one launch; results per slot, gathered with one asynchronous copy
+    ScanSeg *d_segs = nullptr, *h_segs = nullptr; ContigAccum *d_acc_all = nullptr, *h_acc_all = nullptr;
+    unsigned long long *d_hist_all = nullptr, *h_hist_all = nullptr; int segs_cap = 0;
     unsigned long long* d_dist512 = nullptr; unsigned long long* d_rdist = nullptr;
     // totals for multi-GPU reduction
     long long* d_tot_global = nullptr; long long* d_tot_region = nullptr; long long* d_tot_stats = nullptr;
@@ -110,6 +114,9 @@ struct msd_ctx {
     double *d_pf_values = nullptr, *h_pf_values = nullptr; RegionAccum *d_pf_acc = nullptr, *h_pf_acc = nullptr;
     unsigned long long *d_pf_dist = nullptr, *h_pf_dist = nullptr; WinContig *d_pf_table = nullptr, *h_pf_table = nullptr;
     std::vector<int> pf_slot;   // tid -> row of the tables (-1: not prefetched)
+    // multi-GPU (comm.cuh): one communicator per context; fixed-size spill messages to / from the neighbouring ranks
+    ncclComm_t comm = nullptr; int comm_rank = 0, comm_world = 1;
+    uint32_t *d_spill_send = nullptr, *d_spill_recv = nullptr, *h_spill_hdr = nullptr, *d_comm_err = nullptr; uint32_t spill_words = 0; long long* d_stats_pack = nullptr;
     msd_run_info info{};
     uint64_t launches = 0; cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
@@ -175,6 +182,7 @@ int setup_common(msd_ctx* ctx, int n_targets, const uint32_t* target_len, uint64
     ctx->results.assign(n_targets, ContigResult()); ctx->n_prefilter.assign(n_targets, 0);
     ctx->range_lo.assign(n_targets, 0); ctx->range_hi.assign(n_targets, 0xffffffffu); ctx->max_end.assign(n_targets, 0);
     ctx->ranged.assign(n_targets, 0); ctx->pending.assign(n_targets, 0); ctx->any_ranged = false;
+    ctx->covered_from.assign(n_targets, 0xffffffffu); ctx->min_need.assign(n_targets, 0xffffffffu);
     cudaPointerAttributes pa; memset(&pa, 0, sizeof pa);
     ctx->src_pinned = (cudaPointerGetAttributes(&pa, ctx->bytes) == cudaSuccess && pa.type == cudaMemoryTypeHost);
     cudaGetLastError();
@@ -183,7 +191,7 @@ int setup_common(msd_ctx* ctx, int n_targets, const uint32_t* target_len, uint64
     ctx->infl_cap = std::min<uint64_t>(env_u64("MSD_CHUNK_INFL_MB", 1600) << 20, std::max<uint64_t>(8ull << 20, ctx->n_bytes * 16));
     ctx->carry_cap = (uint32_t)std::min<uint64_t>(env_u64("MSD_CARRY_MB", 64) << 20, ctx->infl_cap);
     ctx->max_blocks = (uint32_t)std::min<uint64_t>(env_u64("MSD_CHUNK_BLOCKS", 24000), ctx->n_bytes / 28 + 2);
-    ctx->rec_cap = (uint32_t)((ctx->infl_cap + ctx->carry_cap) / 37 + 2);
+    ctx->rec_cap = (uint32_t)((ctx->infl_cap + ctx->carry_cap) / 36 + 2);   // the smallest record framing accepts: block_size 32 = 36 bytes
     return 0;
 }
 
@@ -296,6 +304,7 @@ int ensure_arena(msd_ctx* ctx) {
         if ((rc = dev_alloc(ctx, &ctx->d_range_hi, (uint64_t)ctx->n_targets))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_max_end, (uint64_t)ctx->n_targets))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_n_beyond, (uint64_t)ctx->n_targets))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_min_need, (uint64_t)ctx->n_targets))) return rc;
     }
     MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_range_lo, ctx->range_lo.data(), sizeof(uint32_t) * ctx->n_targets, cudaMemcpyHostToDevice, ctx->s_compute));
     MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_range_hi, ctx->range_hi.data(), sizeof(uint32_t) * ctx->n_targets, cudaMemcpyHostToDevice, ctx->s_compute));
@@ -334,11 +343,6 @@ int ensure_scratch(msd_ctx* ctx, uint64_t bytes) {
 __global__ void add_hist_kernel(long long* __restrict__ to, const unsigned long long* __restrict__ from, int n) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { unsigned long long v = from[i]; if (v) to[i] += (long long)v; }
 }
-__global__ void add_stats_dev_kernel(long long* __restrict__ tot, long long cum_length, const ContigAccum* __restrict__ a) {
-    tot[0] += cum_length; tot[1] += (long long)a->cum_depth;
-    if ((long long)a->min_depth < tot[2]) tot[2] = a->min_depth;
-    if ((long long)a->max_depth > tot[3]) tot[3] = a->max_depth;
-}
 __global__ void init_acc_all_kernel(ContigAccum* a, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { a[i].cum_depth = 0; a[i].min_depth = 0xffffffffu; a[i].max_depth = 0; a[i].neg_seen = 0; a[i].pad = 0; }
@@ -361,15 +365,100 @@ double sum_ms(const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v) {
     double s = 0; for (auto& p : v) { float ms = 0; if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) s += ms; } return s;
 }
 
-int run_scan(msd_ctx* ctx, int32_t* arr, uint32_t n_scan, uint32_t n_stat, int do_stats, ContigAccum* acc = nullptr) {
-    const uint64_t n_tiles = ((uint64_t)n_scan + kScanTile - 1) / kScanTile;
-    if (n_tiles > ctx->tile_state_cap) { int rc = dev_alloc(ctx, &ctx->d_tile_state, n_tiles); if (rc) return rc; ctx->tile_state_cap = n_tiles; }
-    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_tile_state, 0, n_tiles * 8, ctx->s_compute));
-    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_scan_ticket, 0, 4, ctx->s_compute));
-    const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)kSMs * 8);
-    scan_fused_kernel<<<grid, kScanThreads, 0, ctx->s_compute>>>(arr, n_scan, n_stat, ctx->d_tile_state, ctx->d_scan_ticket, ctx->d_hist, acc ? acc : ctx->d_acc, do_stats);
-    ctx->info.n_launches++;
-    MSD_CUDA_OK(cudaGetLastError());
+// K6 for a batch of segments: prefix sum (scan = true) and / or the whole-segment stats + dist, one launch; the `total`
+// accumulators are updated on the device.  Nothing is read back here: collect_segments() does that after the caller's sync.
+constexpr int kMaxSegsPerLaunch = 4096;
+
+int ensure_segments(msd_ctx* ctx, int n_segs, uint64_t n_tiles) {
+    int rc;
+    if (n_segs > ctx->segs_cap) {
+        const int cap = std::max(n_segs, 64);
+        dev_free(&ctx->d_segs); dev_free(&ctx->d_acc_all); dev_free(&ctx->d_hist_all);
+        if (ctx->h_segs) { cudaFreeHost(ctx->h_segs); ctx->h_segs = nullptr; }
+        if (ctx->h_acc_all) { cudaFreeHost(ctx->h_acc_all); ctx->h_acc_all = nullptr; }
+        if (ctx->h_hist_all) { cudaFreeHost(ctx->h_hist_all); ctx->h_hist_all = nullptr; }
+        ctx->segs_cap = 0;
+        if ((rc = dev_alloc(ctx, &ctx->d_segs, (uint64_t)cap)) || (rc = dev_alloc(ctx, &ctx->d_acc_all, (uint64_t)cap)) || (rc = dev_alloc(ctx, &ctx->d_hist_all, (uint64_t)cap * kHistKeep))) return rc;
+        MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_segs, sizeof(ScanSeg) * cap));
+        MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_acc_all, sizeof(ContigAccum) * cap));
+        MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_hist_all, 8ull * kHistKeep * cap));
+        ctx->segs_cap = cap;
+    }
+    if (n_tiles > ctx->tile_state_cap) { if ((rc = dev_alloc(ctx, &ctx->d_tile_state, n_tiles))) return rc; ctx->tile_state_cap = n_tiles; }
+    return 0;
+}
+
+// segs[i].first_tile / .slot are filled here (slot = i)
+int run_segments(msd_ctx* ctx, int32_t* base, std::vector<ScanSeg>& segs, bool scan) {
+    const int n = (int)segs.size();
+    if (n == 0) return 0;
+    if (n > kMaxSegsPerLaunch) return ctx_fail(ctx, MSD_EINVAL, "run_segments: batch too large");
+    uint64_t n_tiles = 0; bool any_stats = false;
+    for (int i = 0; i < n; i++) { segs[i].first_tile = (uint32_t)n_tiles; segs[i].slot = (uint32_t)i; n_tiles += ((uint64_t)segs[i].n_scan + kScanTile - 1) / kScanTile; any_stats |= segs[i].n_stat != 0; }
+    if (n_tiles >= 0xffffffffull) return ctx_fail(ctx, MSD_EINVAL, "run_segments: too many tiles");
+    int rc = ensure_segments(ctx, n, n_tiles); if (rc) return rc;
+    cudaStream_t sc = ctx->s_compute;
+    memcpy(ctx->h_segs, segs.data(), sizeof(ScanSeg) * n);
+    MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_segs, ctx->h_segs, sizeof(ScanSeg) * n, cudaMemcpyHostToDevice, sc));
+    if (any_stats) {
+        init_acc_all_kernel<<<(n + 255) / 256, 256, 0, sc>>>(ctx->d_acc_all, n);
+        MSD_CUDA_OK(cudaMemsetAsync(ctx->d_hist_all, 0, 8ull * kHistKeep * n, sc));
+    }
+    if (n_tiles) {
+        const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)kSMs * 8);
+        if (scan) {
+            MSD_CUDA_OK(cudaMemsetAsync(ctx->d_tile_state, 0, n_tiles * 8, sc));
+            MSD_CUDA_OK(cudaMemsetAsync(ctx->d_scan_ticket, 0, 4, sc));
+            scan_segments_kernel<true><<<grid, kScanThreads, 0, sc>>>(base, ctx->d_segs, n, (uint32_t)n_tiles, ctx->d_tile_state, ctx->d_scan_ticket, ctx->d_acc_all, ctx->d_hist_all);
+        } else
+            scan_segments_kernel<false><<<grid, kScanThreads, 0, sc>>>(base, ctx->d_segs, n, (uint32_t)n_tiles, ctx->d_tile_state, ctx->d_scan_ticket, ctx->d_acc_all, ctx->d_hist_all);
+        MSD_CUDA_OK(cudaGetLastError());
+        ctx->info.n_launches++;
+    }
+    if (any_stats) {
+        totals_add_kernel<<<kTotalsParts * n, 256, 0, sc>>>(ctx->d_segs, n, ctx->d_acc_all, ctx->d_hist_all, ctx->d_tot_global, ctx->d_tot_stats);
+        MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_acc_all, ctx->d_acc_all, sizeof(ContigAccum) * n, cudaMemcpyDeviceToHost, sc));
+        MSD_CUDA_OK(cudaGetLastError());
+        ctx->info.n_launches += 2;
+    }
+    return 0;
+}
+
+// after the stream has been synchronised: the per-segment results of the last run_segments() -> ctx->results[tid_of[i]]
+int collect_segments(msd_ctx* ctx, const int32_t* base, const std::vector<ScanSeg>& segs, const std::vector<int>& tid_of) {
+    const int n = (int)segs.size();
+    cudaStream_t sc = ctx->s_compute;
+    uint32_t width = 0;
+    for (int i = 0; i < n; i++) if (segs[i].n_stat) { const uint32_t mx = ctx->h_acc_all[i].max_depth; width = std::max<uint32_t>(width, mx >= (uint32_t)kHistKeep ? 1u : mx + 1); }
+    if (width) {
+        MSD_CUDA_OK(cudaMemcpy2DAsync(ctx->h_hist_all, 8ull * kHistKeep, ctx->d_hist_all, 8ull * kHistKeep, 8ull * width, (size_t)n, cudaMemcpyDeviceToHost, sc));
+        MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    }
+    for (int i = 0; i < n; i++) {
+        if (!segs[i].n_stat) continue;
+        const ContigAccum acc = ctx->h_acc_all[i];
+        ContigResult& R = ctx->results[tid_of[i]];
+        R.have = true;
+        R.stat.cum_length = segs[i].n_stat; R.stat.cum_depth = acc.cum_depth; R.stat.min_depth = acc.min_depth; R.stat.max_depth = acc.max_depth;
+        // distribution: bins up to the maximum depth seen (signed view: negative depths are skipped by inc())
+        const uint32_t mx = acc.max_depth;
+        const int64_t top = (mx > 0x7fffffffu) ? (int64_t)kMaxCoverage : (int64_t)std::min<uint32_t>(mx, kMaxCoverage);
+        R.dist.assign((size_t)top + 1, 0);
+        if (mx < (uint32_t)kHistKeep) memcpy(R.dist.data(), ctx->h_hist_all + (size_t)i * kHistKeep, 8ull * (top + 1));
+        else {
+            // deeper than the bins kept per segment: count this one again with the full-width table, and add it to the totals here
+            // (totals_add_kernel skipped it)
+            init_accum_kernel<<<1, 1, 0, sc>>>(ctx->d_acc, nullptr);
+            MSD_CUDA_OK(cudaMemsetAsync(ctx->d_hist, 0, 8ull * kDistBins, sc));
+            range_stats_kernel<<<grid_for(segs[i].n_stat, 256, kSMs * 8), 256, 0, sc>>>(base + segs[i].arr_off, segs[i].n_stat, ctx->d_hist, ctx->d_acc);
+            add_hist_kernel<<<kSMs, 256, 0, sc>>>(ctx->d_tot_global, ctx->d_hist, kDistBins);
+            add_stats_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats, (long long)segs[i].n_stat, acc.cum_depth, acc.min_depth, acc.max_depth);
+            MSD_CUDA_OK(cudaMemcpyAsync(R.dist.data(), ctx->d_hist, 8ull * (top + 1), cudaMemcpyDeviceToHost, sc));
+            MSD_CUDA_OK(cudaStreamSynchronize(sc));
+            ctx->launches += 4;
+        }
+        while (R.dist.size() > 1 && R.dist.back() == 0) R.dist.pop_back();
+    }
     return 0;
 }
 
@@ -483,8 +572,9 @@ void msd_destroy(msd_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    msd_comm_destroy(ctx);
     release_input(ctx);
-    dev_free(&ctx->d_rg); dev_free(&ctx->d_arena); dev_free(&ctx->d_depth_off); dev_free(&ctx->d_tlen); dev_free(&ctx->d_nprefilter); dev_free(&ctx->d_range_lo); dev_free(&ctx->d_range_hi); dev_free(&ctx->d_max_end); dev_free(&ctx->d_n_beyond);
+    dev_free(&ctx->d_rg); dev_free(&ctx->d_arena); dev_free(&ctx->d_depth_off); dev_free(&ctx->d_tlen); dev_free(&ctx->d_nprefilter); dev_free(&ctx->d_range_lo); dev_free(&ctx->d_range_hi); dev_free(&ctx->d_max_end); dev_free(&ctx->d_n_beyond); dev_free(&ctx->d_min_need);
     free_chunk_buffers(ctx);
     for (int k = 0; k < ctx->n_slots; k++) if (ctx->s_inflate[k]) cudaStreamDestroy(ctx->s_inflate[k]);
     for (int k = 0; k < 2; k++) { dev_free(&ctx->live[k].e); dev_free(&ctx->live[k].arena); dev_free(&ctx->live[k].n); dev_free(&ctx->live[k].arena_used); }
@@ -501,7 +591,8 @@ void msd_destroy(msd_ctx* ctx) {
     if (ctx->h_run_val) cudaFreeHost(ctx->h_run_val);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     bz_release(ctx->bz);
-    dev_free(&ctx->d_acc_all); if (ctx->h_acc_all) cudaFreeHost(ctx->h_acc_all); if (ctx->h_hist_keep) cudaFreeHost(ctx->h_hist_keep);
+    dev_free(&ctx->d_acc_all); dev_free(&ctx->d_segs); dev_free(&ctx->d_hist_all);
+    if (ctx->h_acc_all) cudaFreeHost(ctx->h_acc_all); if (ctx->h_segs) cudaFreeHost(ctx->h_segs); if (ctx->h_hist_all) cudaFreeHost(ctx->h_hist_all);
     dev_free(&ctx->d_pf_values); dev_free(&ctx->d_pf_acc); dev_free(&ctx->d_pf_dist); dev_free(&ctx->d_pf_table);
     if (ctx->h_pf_values) cudaFreeHost(ctx->h_pf_values); if (ctx->h_pf_acc) cudaFreeHost(ctx->h_pf_acc); if (ctx->h_pf_dist) cudaFreeHost(ctx->h_pf_dist); if (ctx->h_pf_table) cudaFreeHost(ctx->h_pf_table);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -522,7 +613,7 @@ int msd_open_mem(msd_ctx* ctx, const void* bam_bytes, uint64_t n_bytes, int n_ta
     for (int k = 0; k < 2; k++) { dev_free(&ctx->live[k].e); dev_free(&ctx->live[k].arena); dev_free(&ctx->live[k].n); dev_free(&ctx->live[k].arena_used); }
     dev_free(&ctx->mc.cls); dev_free(&ctx->mc.qhash); dev_free(&ctx->mc.endpos); dev_free(&ctx->mc.next); dev_free(&ctx->mc.slot);
     dev_free(&ctx->mt.word); dev_free(&ctx->mt.head); dev_free(&ctx->mt.live); ctx->mate_ready = false;
-    dev_free(&ctx->d_depth_off); dev_free(&ctx->d_tlen); dev_free(&ctx->d_nprefilter); dev_free(&ctx->d_range_lo); dev_free(&ctx->d_range_hi); dev_free(&ctx->d_max_end); dev_free(&ctx->d_n_beyond);
+    dev_free(&ctx->d_depth_off); dev_free(&ctx->d_tlen); dev_free(&ctx->d_nprefilter); dev_free(&ctx->d_range_lo); dev_free(&ctx->d_range_hi); dev_free(&ctx->d_max_end); dev_free(&ctx->d_n_beyond); dev_free(&ctx->d_min_need);
     ctx->bytes = (const uint8_t*)bam_bytes; ctx->n_bytes = n_bytes; ctx->mapped = false;
     return setup_common(ctx, n_targets, target_len, first_record_voff);
 }
@@ -604,7 +695,7 @@ static int run_prefetch_windows(msd_ctx* ctx) {
     std::vector<WinContig> table;
     long long groups = 0, windows = 0;
     for (int t = 0; t < ctx->n_targets; t++) {
-        if (!ctx->results[t].have) continue;
+        if (!ctx->want[t] || ctx->ranged[t] || ctx->n_prefilter[t] <= 0) continue;   // contigs whose whole array msd_run has just scanned
         const long long nw = msd_n_windows(ctx->tlen[t], ctx->pf_window);
         if (nw <= 0) continue;
         WinContig c; c.arr_off = ctx->depth_off[t]; c.first_group = groups; c.first_window = windows; c.n_windows = nw; c.tlen = ctx->tlen[t]; c.pad = 0;
@@ -680,6 +771,7 @@ int msd_run(msd_ctx* ctx) {
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_nprefilter, 0, sizeof(unsigned long long) * ctx->n_targets, sc));
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_max_end, 0, sizeof(uint32_t) * ctx->n_targets, sc));
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_n_beyond, 0, sizeof(unsigned long long) * ctx->n_targets, sc));
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_min_need, 0xff, sizeof(uint32_t) * ctx->n_targets, sc));
     std::fill(ctx->pending.begin(), ctx->pending.end(), 0);
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_rc, 0, sizeof(RunCounters), sc));
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_cs, 0, sizeof(ChunkState), sc));
@@ -693,7 +785,9 @@ int msd_run(msd_ctx* ctx) {
         for (int k = 0; k < ctx->n_slots; k++) MSD_CUDA_OK(cudaStreamWaitEvent(ctx->s_inflate[k], ev_init, 0));
         MSD_CUDA_OK(cudaStreamWaitEvent(sx, ev_init, 0));
     }
-    ContigTable ct{ctx->d_depth_off, ctx->d_tlen, ctx->d_range_lo, ctx->d_range_hi, ctx->any_ranged ? ctx->d_max_end : nullptr, ctx->d_n_beyond};
+    const bool check_start = ctx->any_ranged && default_mode;
+    ContigTable ct{ctx->d_depth_off, ctx->d_tlen, ctx->d_range_lo, ctx->d_range_hi, ctx->any_ranged ? ctx->d_max_end : nullptr, ctx->d_n_beyond,
+                   check_start ? ctx->d_min_need : nullptr};
     if (ctx->any_ranged && ctx->fp.mode == MSD_MODE_FRAGMENT) return ctx_fail(ctx, MSD_EINVAL, "msd_set_contig_range is not supported in fragment mode (a fragment starts before its read 1)");
     const uint32_t base = ctx->carry_cap;
     // spans are taken as given (the caller merges neighbouring contigs when the bytes between them are genuine
@@ -824,8 +918,8 @@ int msd_run(msd_ctx* ctx) {
                 MSD_CUDA_OK(cudaMemsetAsync(Ln.n, 0, 4, sc));
                 MSD_CUDA_OK(cudaMemsetAsync(Ln.arena_used, 0, 4, sc));
                 mate_reinsert_kernel<<<kSMs * 2, 256, 0, sc>>>(ctx->mt, L, infl_buf, ctx->d_recoff, ctx->d_rc);
-                mate_link_kernel<<<rgrid, 256, 0, sc>>>(ctx->mt, L, infl_buf, ctx->d_recoff, ctx->d_cs, ctx->mc, 0, ctx->d_rc);
-                mate_link_kernel<<<rgrid, 256, 0, sc>>>(ctx->mt, L, infl_buf, ctx->d_recoff, ctx->d_cs, ctx->mc, 1, ctx->d_rc);
+                mate_link_kernel<<<rgrid, 256, 0, sc>>>(ctx->mt, L, infl_buf, ctx->d_recoff, ctx->d_cs, ctx->mc, 0, ctx->d_rc, ct);
+                mate_link_kernel<<<rgrid, 256, 0, sc>>>(ctx->mt, L, infl_buf, ctx->d_recoff, ctx->d_cs, ctx->mc, 1, ctx->d_rc, ct);
                 mate_replay_kernel<<<rgrid, 256, 0, sc>>>(ctx->mt, L, Ln, infl_buf, ctx->d_recoff, ctx->d_cs, ctx->mc, ct, ctx->d_arena, ctx->d_rc);
                 mate_carry_kernel<<<kSMs * 2, 256, 0, sc>>>(L, Ln, ctx->d_rc);
                 ctx->info.n_launches += 5;
@@ -863,102 +957,60 @@ int msd_run(msd_ctx* ctx) {
     MSD_CUDA_OK(cudaMemcpy(npre.data(), ctx->d_nprefilter, sizeof(unsigned long long) * ctx->n_targets, cudaMemcpyDeviceToHost));
     cudaEvent_t s0 = next_event(ctx), s1 = next_event(ctx);
     MSD_CUDA_OK(cudaEventRecord(s0, sc));
-    // contigs that get the whole-contig scan: their stats are gathered asynchronously unless there are very many of them
-    constexpr int kHistKeep = 4096;
-    std::vector<int> keep_slot(ctx->n_targets, -1); int n_scan_contigs = 0;
-    for (int t = 0; t < ctx->n_targets; t++) if (ctx->want[t] && npre[t] && !ctx->ranged[t]) keep_slot[t] = n_scan_contigs++;
-    const bool async_stats = n_scan_contigs > 0 && n_scan_contigs <= 2048 && !getenv("MSD_SYNC_STATS");
-    if (async_stats) {
-        if (ctx->n_targets > ctx->acc_all_cap) {
-            dev_free(&ctx->d_acc_all); if (ctx->h_acc_all) { cudaFreeHost(ctx->h_acc_all); ctx->h_acc_all = nullptr; }
-            if ((rc = dev_alloc(ctx, &ctx->d_acc_all, (uint64_t)ctx->n_targets))) return rc;
-            MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_acc_all, sizeof(ContigAccum) * ctx->n_targets));
-            ctx->acc_all_cap = ctx->n_targets;
-        }
-        if (n_scan_contigs > ctx->hist_keep_cap) {
-            if (ctx->h_hist_keep) { cudaFreeHost(ctx->h_hist_keep); ctx->h_hist_keep = nullptr; }
-            MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_hist_keep, 8ull * kHistKeep * n_scan_contigs));
-            ctx->hist_keep_cap = n_scan_contigs;
-        }
-        init_acc_all_kernel<<<(ctx->n_targets + 255) / 256, 256, 0, sc>>>(ctx->d_acc_all, ctx->n_targets);
-    }
     std::vector<unsigned long long> nbey(ctx->n_targets, 0);
     if (ctx->any_ranged) {
         MSD_CUDA_OK(cudaMemcpy(ctx->max_end.data(), ctx->d_max_end, sizeof(uint32_t) * ctx->n_targets, cudaMemcpyDeviceToHost));
         MSD_CUDA_OK(cudaMemcpy(nbey.data(), ctx->d_n_beyond, sizeof(unsigned long long) * ctx->n_targets, cudaMemcpyDeviceToHost));
+        ctx->min_need.assign(ctx->n_targets, 0xffffffffu);
+        if (check_start) {
+            MSD_CUDA_OK(cudaMemcpy(ctx->min_need.data(), ctx->d_min_need, sizeof(uint32_t) * ctx->n_targets, cudaMemcpyDeviceToHost));
+            for (int t = 0; t < ctx->n_targets; t++) {
+                const uint32_t cover = std::min(ctx->covered_from[t], ctx->range_lo[t]);   // never declared: only the owned range is known to be there
+                if (ctx->want[t] && ctx->ranged[t] && ctx->range_lo[t] && ctx->min_need[t] < cover)
+                    return ctx_fail(ctx, MSD_ESPAN, "contig %d: an owned read looked for a mate at position %u, but the span is only known to hold the records from %u on: extend the span start of this shard (msd_set_contig_cover)", t, ctx->min_need[t], cover);
+            }
+        }
     }
+    // one segment per contig that had records (tlen + 1 cells scanned, tlen of them feed the stats, :746-747) or per owned range of
+    // a sharded contig (prefix sum of this shard's own events over [lo, last event]; the depth it leaves beyond hi goes to the next
+    // shard -- msd_exchange_spills, or msd_depth_copy / msd_depth_add -- and its stats come with msd_contig_finalize)
+    std::vector<ScanSeg> segs; std::vector<int> seg_tid;
+    auto flush = [&](bool last) -> int {
+        if (segs.empty()) return 0;
+        int r = run_segments(ctx, ctx->d_arena, segs, true); if (r) return r;
+        if (last) return 0;
+        MSD_CUDA_OK(cudaStreamSynchronize(sc));
+        r = collect_segments(ctx, ctx->d_arena, segs, seg_tid);
+        segs.clear(); seg_tid.clear();
+        return r;
+    };
     for (int t = 0; t < ctx->n_targets; t++) {
         ctx->n_prefilter[t] = (long long)npre[t];
-        if (ctx->want[t] && ctx->ranged[t]) {
-            // a shard of a contig: prefix sum of this shard's own events over [lo, last event]; the depth it leaves
-            // beyond hi goes to the next shard (msd_depth_copy / msd_depth_add), then msd_contig_finalize()
+        if (!ctx->want[t]) continue;
+        ScanSeg sg{};
+        if (ctx->ranged[t]) {
             const uint32_t lo = ctx->range_lo[t], hi = std::min(ctx->range_hi[t], ctx->tlen[t]);
             if (hi < ctx->tlen[t] && nbey[t] == 0)
                 return ctx_fail(ctx, MSD_EINVAL, "contig %d: the span ends before any record at or beyond %u was seen; extend the span of this shard", t, hi);
             const uint32_t last = std::max(ctx->max_end[t], lo);
-            if ((rc = run_scan(ctx, ctx->d_arena + ctx->depth_off[t] + lo, std::min<uint32_t>(last, ctx->tlen[t]) + 1 - lo, 0, 0))) return rc;
+            sg.arr_off = ctx->depth_off[t] + lo; sg.n_scan = std::min<uint32_t>(last, ctx->tlen[t]) + 1 - lo; sg.n_stat = 0;
             ctx->pending[t] = 1;
             ctx->info.n_depth_cells += (uint64_t)hi - lo;
-            continue;
+        } else {
+            if (npre[t] == 0) continue;
+            sg.arr_off = ctx->depth_off[t]; sg.n_scan = ctx->tlen[t] + 1; sg.n_stat = ctx->tlen[t];
+            ctx->info.n_depth_cells += (uint64_t)ctx->tlen[t] + 1;
+            if (ctx->tlen[t] == 0) { ContigResult& R = ctx->results[t]; R.have = true; R.stat.cum_length = 0; R.stat.cum_depth = 0; R.stat.min_depth = 0xffffffffu; R.stat.max_depth = 0; R.dist.assign(1, 0); }
         }
-        if (!ctx->want[t] || npre[t] == 0) continue;
-        const uint32_t tlen = ctx->tlen[t];
-        ctx->info.n_depth_cells += (uint64_t)tlen + 1;
-        // scan + whole-contig stats; nothing is read back here: the accumulators stay on the device (the `total` rows are
-        // updated from there) and the first kHistKeep dist bins go to pinned memory asynchronously
-        if (!async_stats) init_accum_kernel<<<1, 1, 0, sc>>>(ctx->d_acc, nullptr);
-        MSD_CUDA_OK(cudaMemsetAsync(ctx->d_hist, 0, 8ull * kDistBins, sc));
-        if ((rc = run_scan(ctx, ctx->d_arena + ctx->depth_off[t], tlen + 1, tlen, 1, async_stats ? ctx->d_acc_all + t : nullptr))) return rc;
-        add_hist_kernel<<<kSMs, 256, 0, sc>>>(ctx->d_tot_global, ctx->d_hist, kDistBins);
-        ContigResult& R = ctx->results[t];
-        R.have = true;
-        if (async_stats) {
-            add_stats_dev_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats, (long long)tlen, ctx->d_acc_all + t);
-            MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_hist_keep + (size_t)keep_slot[t] * kHistKeep, ctx->d_hist, 8ull * kHistKeep, cudaMemcpyDeviceToHost, sc));
-            ctx->info.n_launches += 3;
-            continue;
-        }
-        ContigAccum acc;
-        MSD_CUDA_OK(cudaMemcpyAsync(&acc, ctx->d_acc, sizeof acc, cudaMemcpyDeviceToHost, sc));
-        MSD_CUDA_OK(cudaStreamSynchronize(sc));
-        R.stat.cum_length = tlen; R.stat.cum_depth = acc.cum_depth; R.stat.min_depth = acc.min_depth; R.stat.max_depth = acc.max_depth;
-        add_stats_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats, (long long)tlen, acc.cum_depth, acc.min_depth, acc.max_depth);
-        // distribution: bins up to the maximum depth seen (signed view: negative depths are skipped by inc())
-        int64_t top = 0;
-        if (tlen) { uint32_t mx = acc.max_depth; top = (mx > 0x7fffffffu) ? (int64_t)kMaxCoverage : (int64_t)std::min<uint32_t>(mx, kMaxCoverage); }
-        R.dist.assign((size_t)top + 1, 0);
-        MSD_CUDA_OK(cudaMemcpy(R.dist.data(), ctx->d_hist, 8ull * (top + 1), cudaMemcpyDeviceToHost));
-        while (R.dist.size() > 1 && R.dist.back() == 0) R.dist.pop_back();
-        ctx->info.n_launches += 4;
+        segs.push_back(sg); seg_tid.push_back(t);
+        if ((int)segs.size() == kMaxSegsPerLaunch && (rc = flush(false))) return rc;
     }
-    if (async_stats) MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_acc_all, ctx->d_acc_all, sizeof(ContigAccum) * ctx->n_targets, cudaMemcpyDeviceToHost, sc));
+    if ((rc = flush(true))) return rc;
     MSD_CUDA_OK(cudaEventRecord(s1, sc));
     if ((rc = run_prefetch_windows(ctx))) return rc;
     MSD_CUDA_OK(cudaEventRecord(ev_end, sc));
     MSD_CUDA_OK(cudaStreamSynchronize(sc));
-    if (async_stats) {
-        for (int t = 0; t < ctx->n_targets; t++) {
-            if (keep_slot[t] < 0) continue;
-            const uint32_t tlen = ctx->tlen[t];
-            const ContigAccum acc = ctx->h_acc_all[t];
-            ContigResult& R = ctx->results[t];
-            R.stat.cum_length = tlen; R.stat.cum_depth = acc.cum_depth; R.stat.min_depth = acc.min_depth; R.stat.max_depth = acc.max_depth;
-            // distribution: bins up to the maximum depth seen (signed view: negative depths are skipped by inc())
-            int64_t top = 0;
-            if (tlen) { uint32_t mx = acc.max_depth; top = (mx > 0x7fffffffu) ? (int64_t)kMaxCoverage : (int64_t)std::min<uint32_t>(mx, kMaxCoverage); }
-            R.dist.assign((size_t)top + 1, 0);
-            if (top < kHistKeep) memcpy(R.dist.data(), ctx->h_hist_keep + (size_t)keep_slot[t] * kHistKeep, 8ull * (top + 1));
-            else {
-                // deeper than the bins kept on the host: count this contig's dist again (the scan's histogram is gone)
-                init_accum_kernel<<<1, 1, 0, sc>>>(ctx->d_acc, nullptr);
-                MSD_CUDA_OK(cudaMemsetAsync(ctx->d_hist, 0, 8ull * kDistBins, sc));
-                range_stats_kernel<<<grid_for(tlen, 256, kSMs * 8), 256, 0, sc>>>(ctx->d_arena + ctx->depth_off[t], tlen, ctx->d_hist, ctx->d_acc);
-                MSD_CUDA_OK(cudaMemcpyAsync(R.dist.data(), ctx->d_hist, 8ull * (top + 1), cudaMemcpyDeviceToHost, sc));
-                MSD_CUDA_OK(cudaStreamSynchronize(sc));
-            }
-            while (R.dist.size() > 1 && R.dist.back() == 0) R.dist.pop_back();
-        }
-    }
+    if ((rc = collect_segments(ctx, ctx->d_arena, segs, seg_tid))) return rc;
     float ms = 0;
     cudaEventElapsedTime(&ms, ev_begin, ev_end); ctx->info.ms_total = ms;
     cudaEventElapsedTime(&ms, ev_begin, ev_zero_end); ctx->info.ms_zero = ms;
@@ -993,6 +1045,19 @@ int msd_set_contig_range(msd_ctx* ctx, int tid, uint32_t lo, uint32_t hi) {
     ctx->any_ranged = false;
     for (int t = 0; t < ctx->n_targets; t++) ctx->any_ranged |= ctx->ranged[t] != 0;
     ctx->ran = false;
+    return MSD_OK;
+}
+
+int msd_set_contig_cover(msd_ctx* ctx, int tid, uint32_t covered_from) {
+    if (!ctx || tid < 0 || tid >= ctx->n_targets) return ctx_fail(ctx, MSD_EINVAL, "msd_set_contig_cover: bad contig");
+    ctx->covered_from[tid] = covered_from;
+    return MSD_OK;
+}
+
+int msd_contig_span_need(msd_ctx* ctx, int tid, uint32_t* need_from, uint32_t* covered_from) {
+    if (!ctx || tid < 0 || tid >= ctx->n_targets) return ctx_fail(ctx, MSD_EINVAL, "msd_contig_span_need: bad contig");
+    if (need_from) *need_from = ctx->min_need[tid];
+    if (covered_from) *covered_from = std::min(ctx->covered_from[tid], ctx->range_lo[tid]);
     return MSD_OK;
 }
 
@@ -1034,30 +1099,30 @@ int msd_depth_add(msd_ctx* ctx, int tid, uint32_t pos, uint32_t n, const int32_t
     return MSD_OK;
 }
 
+// stats + dist of the owned ranges of the given shards (all of them in one launch), after their neighbours' spills were added
+static int finalize_shards(msd_ctx* ctx, const std::vector<int>& tids) {
+    int rc;
+    if ((rc = ensure_query_buffers(ctx))) return rc;
+    for (size_t b0 = 0; b0 < tids.size(); b0 += kMaxSegsPerLaunch) {
+        std::vector<ScanSeg> segs; std::vector<int> seg_tid;
+        for (size_t i = b0; i < std::min(tids.size(), b0 + (size_t)kMaxSegsPerLaunch); i++) {
+            const int t = tids[i];
+            const uint32_t tlen = ctx->tlen[t], lo = ctx->range_lo[t], hi = std::min(ctx->range_hi[t], tlen);
+            ScanSeg sg{}; sg.arr_off = ctx->depth_off[t] + lo; sg.n_scan = hi - lo; sg.n_stat = hi - lo;
+            segs.push_back(sg); seg_tid.push_back(t);
+        }
+        if ((rc = run_segments(ctx, ctx->d_arena, segs, false))) return rc;
+        MSD_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));
+        if ((rc = collect_segments(ctx, ctx->d_arena, segs, seg_tid))) return rc;
+        ctx->launches += 3;
+    }
+    for (int t : tids) ctx->pending[t] = 0;
+    return MSD_OK;
+}
+
 int msd_contig_finalize(msd_ctx* ctx, int tid) {
     int rc = check_pending(ctx, tid, "msd_contig_finalize"); if (rc) return rc;
-    if ((rc = ensure_query_buffers(ctx))) return rc;
-    cudaStream_t sc = ctx->s_compute;
-    const uint32_t tlen = ctx->tlen[tid], lo = ctx->range_lo[tid], hi = std::min(ctx->range_hi[tid], tlen);
-    const uint32_t n = hi - lo;
-    init_accum_kernel<<<1, 1, 0, sc>>>(ctx->d_acc, nullptr);
-    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_hist, 0, 8ull * kDistBins, sc));
-    range_stats_kernel<<<grid_for(n, 256, kSMs * 8), 256, 0, sc>>>(ctx->d_arena + ctx->depth_off[tid] + lo, n, ctx->d_hist, ctx->d_acc);
-    ContigAccum acc;
-    MSD_CUDA_OK(cudaMemcpyAsync(&acc, ctx->d_acc, sizeof acc, cudaMemcpyDeviceToHost, sc));
-    add_hist_kernel<<<kSMs, 256, 0, sc>>>(ctx->d_tot_global, ctx->d_hist, kDistBins);
-    MSD_CUDA_OK(cudaStreamSynchronize(sc));
-    ContigResult& R = ctx->results[tid];
-    R.have = true; R.stat.cum_length = n; R.stat.cum_depth = acc.cum_depth; R.stat.min_depth = acc.min_depth; R.stat.max_depth = acc.max_depth;
-    add_stats_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats, (long long)n, acc.cum_depth, acc.min_depth, acc.max_depth);
-    int64_t top = 0;
-    if (n) { uint32_t mx = acc.max_depth; top = (mx > 0x7fffffffu) ? (int64_t)kMaxCoverage : (int64_t)std::min<uint32_t>(mx, kMaxCoverage); }
-    R.dist.assign((size_t)top + 1, 0);
-    MSD_CUDA_OK(cudaMemcpy(R.dist.data(), ctx->d_hist, 8ull * (top + 1), cudaMemcpyDeviceToHost));
-    while (R.dist.size() > 1 && R.dist.back() == 0) R.dist.pop_back();
-    ctx->launches += 4;
-    ctx->pending[tid] = 0;
-    return MSD_OK;
+    return finalize_shards(ctx, std::vector<int>(1, tid));
 }
 
 int msd_contig_records(msd_ctx* ctx, int tid, int64_t* n) {
@@ -1160,12 +1225,15 @@ int msd_regions(msd_ctx* ctx, int tid, int64_t n, const uint32_t* start, const u
                                                                            (const int32_t*)(S + o_thr), n_thr, (unsigned long long*)(S + o_cnt));
         MSD_CUDA_OK(cudaGetLastError());
     }
-    add_hist_kernel<<<kSMs, 256, 0, sc>>>(ctx->d_tot_region, ctx->d_rdist, kDistBins);
+    // sum_into for the `total_region` rows (:761-764): not when the call only asks for threshold counts over windows that
+    // msd_windows() has already accounted for (region_stat == NULL)
+    const bool to_totals = region_stat != nullptr;
+    if (to_totals) add_hist_kernel<<<kSMs, 256, 0, sc>>>(ctx->d_tot_region, ctx->d_rdist, kDistBins);
     MSD_CUDA_OK(cudaStreamSynchronize(sc));
     ctx->launches += 4;
     RegionAccum h; fetch_region_accum(ctx, region_stat, &h);
     if (h.neg_seen) return ctx_fail(ctx, MSD_ENEGDEPTH, "error setting negative depth value (median mode)");
-    add_stats_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats + 4, (long long)h.cum_length, h.cum_depth, h.min_depth, h.max_depth);
+    if (to_totals) add_stats_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats + 4, (long long)h.cum_length, h.cum_depth, h.min_depth, h.max_depth);
     if (n > 0 && value_out) MSD_CUDA_OK(cudaMemcpy(value_out, S + o_val, (size_t)n * 8, cudaMemcpyDeviceToHost));
     if (n > 0 && n_thr) MSD_CUDA_OK(cudaMemcpy(thr_counts, S + o_cnt, (size_t)n * n_thr * 8, cudaMemcpyDeviceToHost));
     if (region_dist || dist_len) {
@@ -1404,18 +1472,150 @@ int msd_debug_depth(msd_ctx* ctx, int tid, int32_t* out, int64_t out_cap) {
 }
 
 int msd_debug_cumsum(msd_ctx* ctx, int32_t* inout, int64_t n) {
-    if (!ctx || !inout || n < 0 || n > 0xfffffff0ll) return ctx_fail(ctx, MSD_EINVAL, "msd_debug_cumsum: bad arguments");
+    if (!ctx || !inout || n < 0 || n > 0xffff0000ll) return ctx_fail(ctx, MSD_EINVAL, "msd_debug_cumsum: bad arguments");
     cudaSetDevice(ctx->device);
     int rc = ensure_query_buffers(ctx); if (rc) return rc;
     if (n == 0) return MSD_OK;
     int32_t* d = nullptr;
     if ((rc = dev_alloc(ctx, &d, (uint64_t)n + 32))) return rc;
     cudaError_t e = cudaMemcpyAsync(d, inout, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->s_compute);
-    if (e == cudaSuccess) { rc = run_scan(ctx, d, (uint32_t)n, 0, 0); if (rc) { dev_free(&d); return rc; } }
+    if (e == cudaSuccess) { std::vector<ScanSeg> one(1); one[0].arr_off = 0; one[0].n_scan = (uint32_t)n; one[0].n_stat = 0; rc = run_segments(ctx, d, one, true); if (rc) { dev_free(&d); return rc; } }
     if (e == cudaSuccess) e = cudaMemcpyAsync(inout, d, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->s_compute);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_compute);
     dev_free(&d);
     if (e != cudaSuccess) return ctx_fail(ctx, MSD_ECUDA, "msd_debug_cumsum: %s", cudaGetErrorString(e));
+    return MSD_OK;
+}
+
+// ---- multi-GPU: spill exchange + totals all-reduce (comm.cuh) -----------------------------------------------------------------------
+#define MSD_NCCL_OK(expr)                                                                                          \
+    do {                                                                                                           \
+        ncclResult_t _r = (expr);                                                                                  \
+        if (_r != ncclSuccess) return ctx_fail(ctx, MSD_ECOMM, "%s: %s", #expr, nccl_api()->GetErrorString(_r)); \
+    } while (0)
+
+int msd_comm_unique_id(void* id_out128) {
+    if (!id_out128) return MSD_EINVAL;
+    NcclApi* api = nccl_api();
+    if (!api->handle) return ctx_fail(nullptr, MSD_ECOMM, "%s", api->why);
+    ncclUniqueId id;
+    ncclResult_t r = api->GetUniqueId(&id);
+    if (r != ncclSuccess) return ctx_fail(nullptr, MSD_ECOMM, "ncclGetUniqueId: %s", api->GetErrorString(r));
+    static_assert(sizeof id == MSD_COMM_ID_BYTES, "NCCL unique id size");
+    memcpy(id_out128, &id, sizeof id);
+    return MSD_OK;
+}
+
+int msd_comm_init(msd_ctx* ctx, int rank, int world, const void* id128) {
+    if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return ctx_fail(ctx, MSD_EINVAL, "msd_comm_init: bad arguments");
+    NcclApi* api = nccl_api();
+    if (!api->handle) return ctx_fail(ctx, MSD_ECOMM, "%s", api->why);
+    cudaSetDevice(ctx->device);
+    msd_comm_destroy(ctx);
+    ncclUniqueId id; memcpy(&id, id128, sizeof id);
+    MSD_NCCL_OK(api->CommInitRank(&ctx->comm, world, id, rank));
+    ctx->comm_rank = rank; ctx->comm_world = world;
+    int rc;
+    ctx->spill_words = (uint32_t)std::max<uint64_t>(env_u64("MSD_SPILL_CELLS", 1u << 20), 4096) + kSpillHeaderWords;
+    if ((rc = dev_alloc(ctx, &ctx->d_spill_send, ctx->spill_words)) || (rc = dev_alloc(ctx, &ctx->d_spill_recv, ctx->spill_words)) ||
+        (rc = dev_alloc(ctx, &ctx->d_comm_err, 4)) || (rc = dev_alloc(ctx, &ctx->d_stats_pack, 8))) return rc;
+    MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_spill_hdr, 4 * kSpillHeaderWords));
+    MSD_CUDA_OK(cudaMemset(ctx->d_comm_err, 0, 16));
+    return MSD_OK;
+}
+
+int msd_comm_destroy(msd_ctx* ctx) {
+    if (!ctx) return MSD_EINVAL;
+    if (ctx->comm) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->s_compute); nccl_api()->CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    dev_free(&ctx->d_spill_send); dev_free(&ctx->d_spill_recv); dev_free(&ctx->d_comm_err); dev_free(&ctx->d_stats_pack);
+    if (ctx->h_spill_hdr) { cudaFreeHost(ctx->h_spill_hdr); ctx->h_spill_hdr = nullptr; }
+    ctx->comm_world = 1; ctx->comm_rank = 0;
+    return MSD_OK;
+}
+
+int msd_exchange_spills(msd_ctx* ctx) {
+    if (!ctx || !ctx->comm) return ctx_fail(ctx, MSD_EINVAL, "msd_exchange_spills: call msd_comm_init first");
+    if (!ctx->ran) return ctx_fail(ctx, MSD_EINVAL, "msd_exchange_spills: call msd_run first");
+    cudaSetDevice(ctx->device);
+    NcclApi* api = nccl_api();
+    cudaStream_t sc = ctx->s_compute;
+    const int rank = ctx->comm_rank, world = ctx->comm_world;
+    // what this rank's reads leave beyond the end of every range it owns (max_end came back with msd_run)
+    uint32_t* H = ctx->h_spill_hdr; uint32_t n_ent = 0; uint64_t cells = 0; std::vector<int> shards;
+    for (int t = 0; t < ctx->n_targets; t++) {
+        if (!ctx->want[t] || !ctx->ranged[t] || !ctx->pending[t]) continue;
+        shards.push_back(t);
+        const uint32_t tlen = ctx->tlen[t], hi = std::min(ctx->range_hi[t], tlen);
+        if (hi >= tlen || ctx->max_end[t] <= hi) continue;
+        const uint32_t n = std::min(ctx->max_end[t], tlen) - hi;
+        if (n_ent >= kSpillMaxEntries) return ctx_fail(ctx, MSD_ENOMEM, "msd_exchange_spills: more than %u cut contigs on one rank", kSpillMaxEntries);
+        H[1 + 3 * n_ent] = (uint32_t)t; H[2 + 3 * n_ent] = hi; H[3 + 3 * n_ent] = n; n_ent++; cells += n;
+    }
+    H[0] = n_ent;
+    if (kSpillHeaderWords + cells > ctx->spill_words) return ctx_fail(ctx, MSD_ENOMEM, "msd_exchange_spills: %llu depth cells reach beyond this rank's ranges: raise MSD_SPILL_CELLS (on every rank)", (unsigned long long)cells);
+    if (rank + 1 < world) {
+        MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_spill_send, H, 4ull * (1 + 3 * n_ent), cudaMemcpyHostToDevice, sc));
+        if (n_ent) { spill_pack_kernel<<<kSMs, 256, 0, sc>>>(ctx->d_arena, (const unsigned long long*)ctx->d_depth_off, ctx->d_spill_send); ctx->launches++; }
+    } else if (n_ent) return ctx_fail(ctx, MSD_EINVAL, "msd_exchange_spills: the last rank owns a range that ends inside a contig");
+    MSD_NCCL_OK(api->GroupStart());
+    if (rank + 1 < world) MSD_NCCL_OK(api->Send(ctx->d_spill_send, ctx->spill_words, ncclUint32, rank + 1, ctx->comm, sc));
+    if (rank > 0) MSD_NCCL_OK(api->Recv(ctx->d_spill_recv, ctx->spill_words, ncclUint32, rank - 1, ctx->comm, sc));
+    MSD_NCCL_OK(api->GroupEnd());
+    if (rank > 0) {
+        spill_unpack_kernel<<<kSMs, 256, 0, sc>>>(ctx->d_arena, (const unsigned long long*)ctx->d_depth_off, ctx->d_tlen, ctx->d_range_lo, ctx->d_range_hi, ctx->n_targets,
+                                                  ctx->d_spill_recv, ctx->spill_words, ctx->d_comm_err);
+        ctx->launches++;
+    }
+    MSD_CUDA_OK(cudaGetLastError());
+    int rc = finalize_shards(ctx, shards); if (rc) return rc;
+    uint32_t err = 0;
+    MSD_CUDA_OK(cudaMemcpy(&err, ctx->d_comm_err, 4, cudaMemcpyDeviceToHost));
+    if (err) { cudaMemset(ctx->d_comm_err, 0, 4); return ctx_fail(ctx, MSD_ESPAN, err == 2 ? "msd_exchange_spills: the previous rank's reads reach beyond this rank's whole range of a contig (shards too small)" : "msd_exchange_spills: the previous rank handed over depth for a range this rank does not own (shards of the ranks do not meet)"); }
+    return MSD_OK;
+}
+
+int msd_totals_allreduce(msd_ctx* ctx) {
+    if (!ctx || !ctx->comm) return ctx_fail(ctx, MSD_EINVAL, "msd_totals_allreduce: call msd_comm_init first");
+    cudaSetDevice(ctx->device);
+    int rc = ensure_query_buffers(ctx); if (rc) return rc;
+    NcclApi* api = nccl_api();
+    cudaStream_t sc = ctx->s_compute;
+    stats_pack_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats, ctx->d_stats_pack);
+    MSD_NCCL_OK(api->GroupStart());
+    MSD_NCCL_OK(api->AllReduce(ctx->d_tot_global, ctx->d_tot_global, (size_t)kDistBins, ncclInt64, ncclSum, ctx->comm, sc));
+    MSD_NCCL_OK(api->AllReduce(ctx->d_tot_region, ctx->d_tot_region, (size_t)kDistBins, ncclInt64, ncclSum, ctx->comm, sc));
+    MSD_NCCL_OK(api->AllReduce(ctx->d_stats_pack, ctx->d_stats_pack, 4, ncclInt64, ncclSum, ctx->comm, sc));
+    MSD_NCCL_OK(api->AllReduce(ctx->d_stats_pack + 4, ctx->d_stats_pack + 4, 2, ncclInt64, ncclMin, ctx->comm, sc));
+    MSD_NCCL_OK(api->AllReduce(ctx->d_stats_pack + 6, ctx->d_stats_pack + 6, 2, ncclInt64, ncclMax, ctx->comm, sc));
+    MSD_NCCL_OK(api->GroupEnd());
+    stats_unpack_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats, ctx->d_stats_pack);
+    ctx->launches += 2;
+    MSD_CUDA_OK(cudaGetLastError());
+    return MSD_OK;
+}
+
+int msd_totals(msd_ctx* ctx, msd_depth_stat* global_stat, msd_depth_stat* region_stat, int64_t* global_dist, int64_t global_cap, int64_t* global_len,
+               int64_t* region_dist, int64_t region_cap, int64_t* region_len) {
+    if (!ctx) return MSD_EINVAL;
+    cudaSetDevice(ctx->device);
+    int rc = ensure_query_buffers(ctx); if (rc) return rc;
+    long long st[8];
+    MSD_CUDA_OK(cudaMemcpyAsync(st, ctx->d_tot_stats, sizeof st, cudaMemcpyDeviceToHost, ctx->s_compute));
+    MSD_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));
+    auto put = [](msd_depth_stat* o, const long long* v) { if (!o) return; o->cum_length = v[0]; o->cum_depth = (uint64_t)v[1]; o->min_depth = (uint32_t)v[2]; o->max_depth = (uint32_t)v[3]; };
+    put(global_stat, st); put(region_stat, st + 4);
+    auto fetch = [&](const long long* d_bins, long long mx, int64_t floor_bins, int64_t* out, int64_t cap, int64_t* len, const char* what) -> int {
+        if (!out && !len) return 0;
+        const int64_t top = std::max<int64_t>(floor_bins - 1, (mx > 0x7fffffffll || mx < 0) ? (int64_t)kMaxCoverage : std::min<int64_t>(mx, kMaxCoverage));
+        std::vector<int64_t> tmp((size_t)top + 1, 0);
+        MSD_CUDA_OK(cudaMemcpy(tmp.data(), d_bins, 8ull * (top + 1), cudaMemcpyDeviceToHost));
+        while (tmp.size() > 1 && tmp.back() == 0) tmp.pop_back();
+        if (len) *len = (int64_t)tmp.size();
+        if (out) { if (cap < (int64_t)tmp.size()) return ctx_fail(ctx, MSD_EINVAL, "msd_totals: %s capacity %lld < %zu bins", what, (long long)cap, tmp.size()); memcpy(out, tmp.data(), 8 * tmp.size()); }
+        return 0;
+    };
+    if ((rc = fetch(ctx->d_tot_global, st[3], 1, global_dist, global_cap, global_len, "global_dist"))) return rc;
+    if ((rc = fetch(ctx->d_tot_region, st[7], kWindowDistBins, region_dist, region_cap, region_len, "region_dist"))) return rc;   // window mode bins by mean: up to 511 whatever the depths
     return MSD_OK;
 }
 

@@ -37,6 +37,11 @@ struct ContigTable {
     const uint32_t* range_hi;    // [n_targets]
     uint32_t* max_end;           // [n_targets] largest end position of an owned record (how far the depth spills past range_hi)
     unsigned long long* n_beyond;   // [n_targets] records with pos >= range_hi seen: proves that the span covered every owned record
+    // soundness of the span START of a shard with range_lo > 0 (default mode): min_need = smallest mate position of an owned
+    // record that looked for its mate in the `seen` table and did not find it.  The caller promises that its spans hold every
+    // record from `covered_from` on (msd_set_contig_cover); min_need < covered_from means that a mate may sit in front of the
+    // span: msd_run refuses the result (MSD_ESPAN) instead of silently skipping an overlap correction.  nullptr: not sharded.
+    uint32_t* min_need;          // [n_targets]
     MSD_D bool owned(int32_t tid, int32_t pos) const { return (uint32_t)pos >= range_lo[tid] && (uint32_t)pos < range_hi[tid]; }
 };
 
@@ -194,8 +199,10 @@ MSD_D bool rg_pass(const uint8_t* __restrict__ buf, uint32_t p, const RecCore& r
                 break;
             }
             case 'B': {
+                if (a + 5 > end) return false;
                 uint8_t st = buf[a]; uint32_t cnt = ld_u32(buf, a + 1);
                 uint32_t es = (st == 'c' || st == 'C') ? 1u : (st == 's' || st == 'S') ? 2u : 4u;
+                if ((uint64_t)a + 5 + (uint64_t)es * cnt > end) return false;
                 a += 5 + es * cnt; break;
             }
             default: return false;
@@ -370,7 +377,7 @@ __global__ void mate_reinsert_kernel(MateTable T, LiveList L, const uint8_t* __r
 
 // M1 (inserters: classes U and E) and M2 (takers: class T) -- two launches of the same kernel
 __global__ void mate_link_kernel(MateTable T, LiveList L, const uint8_t* __restrict__ buf, const uint32_t* __restrict__ rec_off,
-                                 const ChunkState* __restrict__ cs, MateChunk mc, int takers, RunCounters* __restrict__ rc) {
+                                 const ChunkState* __restrict__ cs, MateChunk mc, int takers, RunCounters* __restrict__ rc, ContigTable ct) {
     const uint32_t n_rec = cs->n_rec;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
         const uint8_t cl = mc.cls[r];
@@ -379,7 +386,16 @@ __global__ void mate_link_kernel(MateTable T, LiveList L, const uint8_t* __restr
         bool full = false;
         uint32_t s = table_find(T, mc.qhash[r], r, !takers, buf, rec_off, L, full);
         if (full) { atomicExch(&rc->error, 1u); continue; }
-        if (s == kNoOff) continue;
+        if (s == kNoOff) {
+            if (takers && ct.min_need) {
+                // a shard that starts inside its contig: this read found no mate in `seen`.  Fine when the mate does not reach
+                // it (it was never inserted, :297) -- unless the mate lies in front of the span, where nobody looked
+                const uint32_t p = rec_off[r];
+                const int32_t tid = (int32_t)ld_u32(buf, p + kRecRefID), pos = (int32_t)ld_u32(buf, p + kRecPos), mpos = (int32_t)ld_u32(buf, p + kRecNextPos);
+                if (ct.range_lo[tid] && ct.owned(tid, pos) && mpos >= 0 && mpos < pos) atomicMin(ct.min_need + tid, (uint32_t)mpos);
+            }
+            continue;
+        }
         mc.slot[r] = s;
         mc.next[r] = atomicExch(&T.head[s], r);
     }

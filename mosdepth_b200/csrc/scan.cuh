@@ -1,10 +1,18 @@
-// scan.cuh -- K6 scan_fused: per-contig int32 inclusive prefix sum (to_coverage -> hts-nim cumsum,
-// mosdepth.nim:54-56) fused with the two whole-contig consumers that are order independent:
-// inc(chrom_global_distribution, arr, 0, len-1) (:417-437,:746) and newDepthStat(arr[0..<len-1]) (:747,
-// depthstat.nim:39-45).  Single pass, decoupled look-back between tiles, 128-bit coalesced loads and stores.
-// Persistent CTAs take tiles from an atomic ticket, so the look-back never waits on a tile that has not started.
+// scan.cuh -- K6 scan_segments: int32 inclusive prefix sum of EVERY contig's array in one launch (to_coverage -> hts-nim
+// cumsum, mosdepth.nim:54-56, which the reference runs once per contig inside `for target in sub_targets`, :691,:713),
+// fused with the two whole-contig consumers that are order independent: inc(chrom_global_distribution, arr, 0, len-1)
+// (:417-437,:746) and newDepthStat(arr[0..<len-1]) (:747, depthstat.nim:39-45).
+//
+// A *segment* is a contiguous piece of the depth arena that gets its own prefix sum: a whole contig (tlen + 1 cells, the
+// first tlen of which feed the stats) or the owned range of a contig that is sharded across GPUs.  All segments are cut
+// into 4096-cell tiles that are numbered through (segment s owns tiles [first_tile, first_tile + ceil(n_scan / 4096)));
+// persistent CTAs take tile numbers from an atomic ticket, so the decoupled look-back never waits for a tile that has not
+// started, and it simply stops at the first tile of its own segment.  Single pass, 128-bit coalesced loads and stores,
+// warp-wide look-back (32 predecessors per probe).
 //
 // HBM traffic per base: 4 B read + 4 B written (the depth array is kept for the window / region / run kernels).
+// r1 ran one launch + one 3.2 MB histogram memset + one 3.2 MB histogram add per contig (25 x 3 launches for a human genome);
+// this is one launch for the genome, and the per-contig results stay on the device until one asynchronous copy.
 #pragma once
 #include "common.cuh"
 
@@ -14,11 +22,20 @@ constexpr int kScanThreads = 256;
 constexpr int kScanVecPerThread = 4;                                   // int4 per thread
 constexpr int kScanTile = kScanThreads * kScanVecPerThread * 4;        // 4096 cells = 16 KB
 constexpr int kHistSmemBins = 1024;
+constexpr int kHistKeep = 4096;   // dist bins kept per segment on the device (deeper contigs are counted again, one at a time)
 
 struct ContigAccum {            // device-side accumulators of one contig (also reused per query)
     unsigned long long cum_depth;
     unsigned int min_depth, max_depth;
     unsigned int neg_seen, pad;
+};
+
+struct ScanSeg {
+    unsigned long long arr_off;   // first cell of the segment in the depth arena (a multiple of 32: 128-bit accesses stay aligned)
+    uint32_t n_scan;              // cells that get the prefix sum
+    uint32_t n_stat;              // cells [0, n_stat) feed depth_stat + dist (0: none -- a shard gets them in msd_contig_finalize)
+    uint32_t first_tile;          // number of the segment's first tile among all tiles of the launch
+    uint32_t slot;                // row of acc_all / hist_all that receives the segment's stats
 };
 
 MSD_D void hist_add(uint32_t* __restrict__ sh, unsigned long long* __restrict__ gh, int32_t v, uint32_t n) {
@@ -27,27 +44,97 @@ MSD_D void hist_add(uint32_t* __restrict__ sh, unsigned long long* __restrict__ 
     if (v < kHistSmemBins) atomicAdd(&sh[v], n);
     else atomicAdd(&gh[v], (unsigned long long)n);
 }
+// same rule, for a per-segment table of kHistKeep bins: deeper values are not counted here -- the segment's max_depth tells the
+// host that it has to count this one contig again with the full-width table (range_stats_kernel)
+MSD_D void hist_add_keep(uint32_t* __restrict__ sh, unsigned long long* __restrict__ gh, int32_t v, uint32_t n) {
+    if (v < 0) return;
+    if (v < kHistSmemBins) atomicAdd(&sh[v], n);
+    else if (v < kHistKeep) atomicAdd(&gh[v], (unsigned long long)n);
+}
 
-// tile_state[i]: (flag << 32) | value, flag 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix
+struct SegStats { unsigned long long sum; uint32_t mn, mx; };
+
+// block-reduce the per-thread stats into acc[slot], flush the shared histogram into hist_all[slot]; all threads call it
+MSD_D void seg_flush(SegStats& my, uint32_t* __restrict__ s_hist, unsigned long long* __restrict__ s_sum, uint32_t* __restrict__ s_mn, uint32_t* __restrict__ s_mx,
+                     ContigAccum* __restrict__ acc, unsigned long long* __restrict__ hist) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my.sum += __shfl_down_sync(0xffffffffu, my.sum, o);
+        const uint32_t a = __shfl_down_sync(0xffffffffu, my.mn, o), b = __shfl_down_sync(0xffffffffu, my.mx, o);
+        my.mn = a < my.mn ? a : my.mn; my.mx = b > my.mx ? b : my.mx;
+    }
+    if (lane == 0) { s_sum[warp] = my.sum; s_mn[warp] = my.mn; s_mx[warp] = my.mx; }
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long S = 0; uint32_t mn = 0xffffffffu, mx = 0;
+        for (int w = 0; w < kScanThreads / 32; w++) { S += s_sum[w]; mn = s_mn[w] < mn ? s_mn[w] : mn; mx = s_mx[w] > mx ? s_mx[w] : mx; }
+        if (S) atomicAdd(&acc->cum_depth, S);
+        if (mn != 0xffffffffu || mx != 0) { atomicMin(&acc->min_depth, mn); atomicMax(&acc->max_depth, mx); }
+    }
+    for (int i = t; i < kHistSmemBins; i += kScanThreads) { const uint32_t c = s_hist[i]; if (c) { atomicAdd(&hist[i], (unsigned long long)c); s_hist[i] = 0; } }
+    my.sum = 0; my.mn = 0xffffffffu; my.mx = 0;
+    __syncthreads();
+}
+
+// the stats of four consecutive cells starting at segment index idx (cells at or beyond n_stat do not count)
+MSD_D void seg_stats4(const int4 x, uint32_t idx, uint32_t n_stat, SegStats& my, uint32_t* __restrict__ s_hist, unsigned long long* __restrict__ hist) {
+    const int32_t e[4] = {x.x, x.y, x.z, x.w};
+    int32_t cur = 0; uint32_t cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (idx + q >= n_stat) break;
+        const int32_t d = e[q];
+        my.sum += (unsigned long long)(long long)d;          // dp.uint64 (depthstat.nim:43)
+        const uint32_t u = (uint32_t)d;
+        my.mn = u < my.mn ? u : my.mn; my.mx = u > my.mx ? u : my.mx;
+        if (cnt && d == cur) cnt++;
+        else { if (cnt) hist_add_keep(s_hist, hist, cur, cnt); cur = d; cnt = 1; }
+    }
+    if (cnt) hist_add_keep(s_hist, hist, cur, cnt);
+}
+
+// tile_state[i]: (flag << 32) | value, flag 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix.
+// kScan = false: the arrays already hold depth (a shard after msd_exchange_spills): only the stats pass, tiles taken by stride.
+template <bool kScan>
 __global__ void __launch_bounds__(kScanThreads)
-scan_fused_kernel(int32_t* __restrict__ arr, uint32_t n_scan, uint32_t n_stat, unsigned long long* __restrict__ tile_state,
-                  uint32_t* __restrict__ ticket, unsigned long long* __restrict__ hist, ContigAccum* __restrict__ acc, int do_stats) {
+scan_segments_kernel(int32_t* __restrict__ arena, const ScanSeg* __restrict__ segs, int n_segs, uint32_t n_tiles,
+                     unsigned long long* __restrict__ tile_state, uint32_t* __restrict__ ticket,
+                     ContigAccum* __restrict__ acc_all, unsigned long long* __restrict__ hist_all /* [slot][kHistKeep] */) {
     __shared__ uint32_t s_hist[kHistSmemBins];
     __shared__ uint32_t s_warp[kScanThreads / 32];
     __shared__ uint32_t s_tile, s_prefix;
     __shared__ unsigned long long s_sum[kScanThreads / 32];
     __shared__ uint32_t s_mn[kScanThreads / 32], s_mx[kScanThreads / 32];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const uint32_t n_tiles = (n_scan + kScanTile - 1) / kScanTile;
-    if (do_stats) for (int i = t; i < kHistSmemBins; i += kScanThreads) s_hist[i] = 0;
-    unsigned long long my_sum = 0; uint32_t my_mn = 0xffffffffu, my_mx = 0;
+    for (int i = t; i < kHistSmemBins; i += kScanThreads) s_hist[i] = 0;
+    SegStats my{0, 0xffffffffu, 0};
+    int cur_seg = -1; bool cur_stats = false; uint32_t cur_slot = 0;
     __syncthreads();
-    for (;;) {
-        if (t == 0) s_tile = atomicAdd(ticket, 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
+    uint32_t tile = blockIdx.x;
+    for (;; tile += gridDim.x) {
+        if (kScan) {
+            if (t == 0) s_tile = atomicAdd(ticket, 1u);
+            __syncthreads();
+            tile = s_tile;
+        }
         if (tile >= n_tiles) break;
-        const uint32_t tile_base = tile * kScanTile;
+        // the segment of this tile: the last one with first_tile <= tile (uniform across the CTA; a CTA's tiles ascend, so the
+        // previous answer is right most of the time)
+        int sg = cur_seg;
+        if (sg < 0 || tile < segs[sg].first_tile || (sg + 1 < n_segs && tile >= segs[sg + 1].first_tile)) {
+            int lo = 0, hi = n_segs - 1;
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (segs[mid].first_tile <= tile) lo = mid; else hi = mid - 1; }
+            sg = lo;
+        }
+        if (sg != cur_seg) {
+            if (cur_stats) seg_flush(my, s_hist, s_sum, s_mn, s_mx, acc_all + cur_slot, hist_all + (size_t)cur_slot * kHistKeep);
+            cur_seg = sg; cur_stats = segs[sg].n_stat != 0; cur_slot = segs[sg].slot;
+        }
+        const ScanSeg S = segs[sg];
+        int32_t* __restrict__ arr = arena + S.arr_off;
+        const uint32_t n_scan = S.n_scan, rel = tile - S.first_tile, tile_base = rel * kScanTile;
+        unsigned long long* __restrict__ hist = hist_all + (size_t)S.slot * kHistKeep;
         // warp w owns cells [tile_base + w*512, +512): 4 rounds of 32 lanes x int4
         int4 v[kScanVecPerThread];
         uint32_t run = 0;
@@ -61,6 +148,7 @@ scan_fused_kernel(int32_t* __restrict__ arr, uint32_t n_scan, uint32_t n_stat, u
                 if (idx + 1 < n_scan) x.y = arr[idx + 1];
                 if (idx + 2 < n_scan) x.z = arr[idx + 2];
             }
+            if (!kScan) { v[j] = x; continue; }
             // local inclusive scan of the 4 cells (uint32 wrap-around like the reference's int32 cumsum)
             uint32_t a = (uint32_t)x.x, b = a + (uint32_t)x.y, c = b + (uint32_t)x.z, d = c + (uint32_t)x.w;
             uint32_t incl = d;
@@ -70,82 +158,85 @@ scan_fused_kernel(int32_t* __restrict__ arr, uint32_t n_scan, uint32_t n_stat, u
             v[j] = make_int4((int)(a + excl), (int)(b + excl), (int)(c + excl), (int)(d + excl));
             run += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (lane == 0) s_warp[warp] = run;
-        __syncthreads();
-        uint32_t warp_excl = 0, tile_total = 0;
+        uint32_t add = 0;
+        if (kScan) {
+            if (lane == 0) s_warp[warp] = run;
+            __syncthreads();
+            uint32_t warp_excl = 0, tile_total = 0;
 #pragma unroll
-        for (int w = 0; w < kScanThreads / 32; w++) { uint32_t x = s_warp[w]; if (w < warp) warp_excl += x; tile_total += x; }
-        // decoupled look-back (thread 0)
-        if (t == 0) {
-            uint32_t prefix = 0;
-            if (tile == 0) {
-                atomicExch(&tile_state[0], (2ull << 32) | tile_total);
-            } else {
-                atomicExch(&tile_state[tile], (1ull << 32) | tile_total);
-                int64_t k = (int64_t)tile - 1;
-                for (;;) {
-                    unsigned long long s = *((volatile unsigned long long*)&tile_state[k]);
-                    uint32_t flag = (uint32_t)(s >> 32);
-                    if (flag == 0) continue;
-                    prefix += (uint32_t)s;
-                    if (flag == 2) break;
-                    k--;
+            for (int w = 0; w < kScanThreads / 32; w++) { uint32_t x = s_warp[w]; if (w < warp) warp_excl += x; tile_total += x; }
+            // decoupled look-back by warp 0: lane l probes tile - 1 - l; tiles in front of the segment count as "inclusive prefix 0"
+            if (warp == 0) {
+                uint32_t prefix = 0;
+                if (rel == 0) {
+                    if (lane == 0) atomicExch(&tile_state[tile], (2ull << 32) | tile_total);
+                } else {
+                    if (lane == 0) atomicExch(&tile_state[tile], (1ull << 32) | tile_total);
+                    int64_t k = (int64_t)tile - 1;
+                    for (;;) {
+                        const int64_t idx = k - lane;
+                        unsigned long long s = (2ull << 32);
+                        if (idx >= (int64_t)S.first_tile) s = *((volatile unsigned long long*)&tile_state[idx]);
+                        const uint32_t flag = (uint32_t)(s >> 32);
+                        const unsigned ready = __ballot_sync(0xffffffffu, flag != 0), incl = __ballot_sync(0xffffffffu, flag == 2);
+                        const int f = incl ? __ffs((int)incl) - 1 : 32;                       // nearest tile that knows its inclusive prefix
+                        const unsigned need = f >= 31 ? 0xffffffffu : ((2u << f) - 1u);       // lanes 0..f (all 32 when none does)
+                        if ((ready & need) != need) continue;                                  // some tile in between has not published yet
+                        uint32_t val = (lane <= f) ? (uint32_t)s : 0u;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
+                        prefix += __shfl_sync(0xffffffffu, val, 0);
+                        if (f < 32) break;
+                        k -= 32;
+                    }
+                    if (lane == 0) atomicExch(&tile_state[tile], (2ull << 32) | (uint32_t)(prefix + tile_total));
                 }
-                atomicExch(&tile_state[tile], (2ull << 32) | (uint32_t)(prefix + tile_total));
+                if (lane == 0) s_prefix = prefix;
             }
-            s_prefix = prefix;
+            __syncthreads();
+            add = s_prefix + warp_excl;
         }
-        __syncthreads();
-        const uint32_t add = s_prefix + warp_excl;
 #pragma unroll
         for (int j = 0; j < kScanVecPerThread; j++) {
             const uint32_t idx = tile_base + warp * 512 + j * 128 + lane * 4;
-            int4 x = make_int4((int)((uint32_t)v[j].x + add), (int)((uint32_t)v[j].y + add), (int)((uint32_t)v[j].z + add), (int)((uint32_t)v[j].w + add));
-            if (idx + 3 < n_scan) *reinterpret_cast<int4*>(arr + idx) = x;
-            else {
-                if (idx < n_scan) arr[idx] = x.x;
-                if (idx + 1 < n_scan) arr[idx + 1] = x.y;
-                if (idx + 2 < n_scan) arr[idx + 2] = x.z;
-            }
-            if (do_stats) {
-                const int32_t e[4] = {x.x, x.y, x.z, x.w};
-                int32_t cur = 0; uint32_t cnt = 0;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (idx + q >= n_stat) break;
-                    const int32_t d = e[q];
-                    my_sum += (unsigned long long)(long long)d;          // dp.uint64 (depthstat.nim:43)
-                    const uint32_t u = (uint32_t)d;
-                    my_mn = u < my_mn ? u : my_mn; my_mx = u > my_mx ? u : my_mx;
-                    if (cnt && d == cur) cnt++;
-                    else { if (cnt) hist_add(s_hist, hist, cur, cnt); cur = d; cnt = 1; }
+            const int4 x = make_int4((int)((uint32_t)v[j].x + add), (int)((uint32_t)v[j].y + add), (int)((uint32_t)v[j].z + add), (int)((uint32_t)v[j].w + add));
+            if (kScan) {
+                if (idx + 3 < n_scan) *reinterpret_cast<int4*>(arr + idx) = x;
+                else {
+                    if (idx < n_scan) arr[idx] = x.x;
+                    if (idx + 1 < n_scan) arr[idx + 1] = x.y;
+                    if (idx + 2 < n_scan) arr[idx + 2] = x.z;
                 }
-                if (cnt) hist_add(s_hist, hist, cur, cnt);
             }
+            if (cur_stats) seg_stats4(x, idx, S.n_stat, my, s_hist, hist);
         }
-        __syncthreads();   // s_tile / s_warp reuse
+        if (kScan) __syncthreads();   // s_tile / s_warp / s_prefix reuse
     }
-    if (!do_stats) return;
-    // block reduction of the stats, flush the shared histogram
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        my_sum += __shfl_down_sync(0xffffffffu, my_sum, o);
-        uint32_t a = __shfl_down_sync(0xffffffffu, my_mn, o), b = __shfl_down_sync(0xffffffffu, my_mx, o);
-        my_mn = a < my_mn ? a : my_mn; my_mx = b > my_mx ? b : my_mx;
-    }
-    if (lane == 0) { s_sum[warp] = my_sum; s_mn[warp] = my_mn; s_mx[warp] = my_mx; }
-    __syncthreads();
-    if (t == 0) {
-        unsigned long long S = 0; uint32_t mn = 0xffffffffu, mx = 0;
-        for (int w = 0; w < kScanThreads / 32; w++) { S += s_sum[w]; mn = s_mn[w] < mn ? s_mn[w] : mn; mx = s_mx[w] > mx ? s_mx[w] : mx; }
-        atomicAdd(&acc->cum_depth, S); atomicMin(&acc->min_depth, mn); atomicMax(&acc->max_depth, mx);
-    }
-    for (int i = t; i < kHistSmemBins; i += kScanThreads) { uint32_t c = s_hist[i]; if (c) atomicAdd(&hist[i], (unsigned long long)c); }
+    if (cur_stats) seg_flush(my, s_hist, s_sum, s_mn, s_mx, acc_all + cur_slot, hist_all + (size_t)cur_slot * kHistKeep);
 }
 
-// The two whole-contig consumers (inc :417-437, newDepthStat depthstat.nim:39-45) over cells [0, n) of an array that is
-// already a depth array: the shard of a contig after msd_depth_add() (msd_contig_finalize).  Same arithmetic as the
-// do_stats branch of scan_fused_kernel.
+// sum_into (mosdepth.nim:491-499, :761-764) and depth_stat `+` (depthstat.nim:53-57) for every segment with stats, in one launch:
+// the genome-wide `total` accumulators get each segment's bins up to its own maximum depth (not 400,001 bins per contig).
+// kTotalsParts CTAs per segment.  Segments deeper than kHistKeep are skipped here (the host counts them again and adds them itself).
+constexpr int kTotalsParts = 4;
+__global__ void totals_add_kernel(const ScanSeg* __restrict__ segs, int n_segs, const ContigAccum* __restrict__ acc_all,
+                                  const unsigned long long* __restrict__ hist_all, long long* __restrict__ tot_hist, long long* __restrict__ tot_stats) {
+    const int sg = blockIdx.x / kTotalsParts, part = blockIdx.x % kTotalsParts;
+    if (sg >= n_segs) return;
+    const ScanSeg S = segs[sg];
+    if (!S.n_stat) return;
+    const ContigAccum a = acc_all[S.slot];
+    if (a.max_depth >= (uint32_t)kHistKeep) return;
+    const unsigned long long* __restrict__ h = hist_all + (size_t)S.slot * kHistKeep;
+    for (uint32_t i = part * blockDim.x + threadIdx.x; i <= a.max_depth; i += kTotalsParts * blockDim.x) { const unsigned long long c = h[i]; if (c) atomicAdd((unsigned long long*)&tot_hist[i], c); }
+    if (part == 0 && threadIdx.x == 0) {
+        atomicAdd((unsigned long long*)&tot_stats[0], (unsigned long long)S.n_stat); atomicAdd((unsigned long long*)&tot_stats[1], a.cum_depth);
+        atomicMin(&tot_stats[2], (long long)a.min_depth); atomicMax(&tot_stats[3], (long long)a.max_depth);
+    }
+}
+
+// The two whole-contig consumers (inc :417-437, newDepthStat depthstat.nim:39-45) over cells [0, n) of ONE array with the full-width
+// dist table: contigs deeper than kHistKeep, counted again.  Same arithmetic as the stats branch of scan_segments_kernel.
 __global__ void __launch_bounds__(256)
 range_stats_kernel(const int32_t* __restrict__ arr, uint32_t n, unsigned long long* __restrict__ hist, ContigAccum* __restrict__ acc) {
     __shared__ uint32_t s_hist[kHistSmemBins];

@@ -18,8 +18,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <map>
+#include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 #include <zlib.h>
 
@@ -92,7 +95,7 @@ static Header read_header(const std::string& path) {
     return H;
 }
 
-struct ContigIndex { bool has = false; uint64_t beg = 0, end = 0; };
+struct ContigIndex { bool has = false; uint64_t beg = 0, end = 0; std::vector<uint64_t> linear; };   // linear: BAI ioffset per 16,384-bp window (empty for CSI)
 static std::vector<uint8_t> gunzip_all(const std::vector<uint8_t>& raw) {
     if (raw.size() < 2 || raw[0] != 0x1f || raw[1] != 0x8b) return raw;
     std::vector<uint8_t> out; size_t p = 0;
@@ -126,7 +129,7 @@ static bool load_index(const std::string& bam, std::vector<ContigIndex>& out) {
             const int32_t nc = count(16);
             for (int c = 0; c < nc; c++) { const uint64_t cb = u64(), ce = u64(); if (bin != pseudo) { mn = std::min(mn, cb); mx = std::max(mx, ce); } }
         }
-        if (!csi) { const int32_t ni = count(8); q += 8 * (size_t)ni; }
+        if (!csi) { const int32_t ni = count(8); out[r].linear.resize((size_t)ni); for (int k = 0; k < ni; k++) out[r].linear[(size_t)k] = u64(); }
         if (mn != UINT64_MAX) { out[r].has = true; out[r].beg = mn; out[r].end = mx; }
     }
     return true;
@@ -207,11 +210,83 @@ static std::vector<std::string> make_lookup(const std::vector<int64_t>& q) {
 static inline char* fmt_u32(char* p, uint32_t v) { char t[12]; int n = 0; do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) *p++ = t[--n]; return p; }
 static inline char* fmt_i32(char* p, int32_t v) { if (v < 0) { *p++ = '-'; return fmt_u32(p, (uint32_t)(-(int64_t)v)); } return fmt_u32(p, (uint32_t)v); }
 
+
+// ---- multi-GPU sharding (nothing in the single-process reference corresponds to it) -----------------------------------
+// A Piece is what one rank owns of one contig: the records with lo <= pos < hi, read from the virtual-offset span [vb, ve).
+// cover = the position from which on the span is known to hold every record (linear-index window start), see msd_set_contig_cover.
+struct Piece { int tid; uint32_t lo, hi; uint64_t vb, ve; uint32_t cover; bool cut; };
+
+// N contiguous BGZF offset ranges of equal compressed size; the cuts fall inside contigs at BAI linear-index entries, at multiples
+// of lcm(32, window) so that no --by window straddles a cut.  A rank's pieces are adjacent in the file.
+static std::vector<std::vector<Piece>> offset_shards(const std::vector<ContigIndex>& index, const std::vector<uint32_t>& tlen, const std::vector<uint8_t>& want,
+                                                     int n, uint32_t window, uint32_t margin_bp, uint32_t beyond_windows = 8) {
+    std::vector<int> have; for (int t = 0; t < (int)index.size() && t < (int)tlen.size(); t++) if (want[(size_t)t] && index[(size_t)t].has) have.push_back(t);
+    std::vector<std::vector<Piece>> out((size_t)n);
+    if (have.empty()) return out;
+    const uint64_t align = window ? std::lcm<uint64_t>(32, window) : 32;
+    const uint64_t c_beg = index[(size_t)have.front()].beg >> 16, c_end = index[(size_t)have.back()].end >> 16;
+    std::vector<std::pair<int, uint64_t>> cuts;      // (contig, position); position 0 = at the start of the contig
+    for (int k = 1; k < n; k++) {
+        const uint64_t target = c_beg + (c_end - c_beg) * (uint64_t)k / (uint64_t)n;
+        int t = have.back(); for (int u : have) if ((index[(size_t)u].end >> 16) > target) { t = u; break; }
+        const auto& lin = index[(size_t)t].linear;
+        size_t w = lin.size(); for (size_t j = 0; j < lin.size(); j++) if (lin[j] && (lin[j] >> 16) >= target) { w = j; break; }
+        uint64_t pos = ((uint64_t)w * 16384 + align / 2) / align * align;
+        if (pos >= tlen[(size_t)t]) { int nx = -1; for (int u : have) if (u > t) { nx = u; break; } if (nx < 0) continue; t = nx; pos = 0; }
+        if (!cuts.empty() && std::make_pair(t, pos) <= cuts.back()) continue;
+        cuts.push_back({t, pos});
+    }
+    std::vector<std::pair<int, uint64_t>> bounds; bounds.push_back({have.front(), 0}); for (auto& c : cuts) bounds.push_back(c); bounds.push_back({-1, 0});
+    for (size_t r = 0; r + 1 < bounds.size(); r++) {
+        const int t0 = bounds[r].first, t1 = bounds[r + 1].first; const uint64_t p0 = bounds[r].second, p1 = bounds[r + 1].second;
+        for (int t : have) {
+            if (t < t0 || (t1 >= 0 && (t > t1 || (t == t1 && p1 == 0)))) continue;
+            const ContigIndex& ci = index[(size_t)t]; const uint32_t L = tlen[(size_t)t];
+            Piece pc; pc.tid = t; pc.lo = t == t0 ? (uint32_t)p0 : 0; pc.hi = (t1 >= 0 && t == t1) ? (uint32_t)p1 : L; pc.cut = pc.lo > 0 || pc.hi < L;
+            // span start: the linear-index entry of a window at least margin_bp in front of lo (an empty entry: the nearest one before it)
+            pc.cover = 0; pc.vb = ci.beg;
+            if (pc.lo > margin_bp) {
+                int64_t wi = std::min<int64_t>(((int64_t)pc.lo - (int64_t)margin_bp) / 16384, (int64_t)ci.linear.size() - 1);
+                while (wi > 0 && !ci.linear[(size_t)wi]) wi--;
+                if (wi > 0) { pc.vb = ci.linear[(size_t)wi]; pc.cover = (uint32_t)wi * 16384u; }
+            }
+            // span end: beyond_windows index windows after hi (an empty entry: the next one after it), so that a record at or beyond hi is seen
+            pc.ve = ci.end;
+            if (pc.hi < L) { size_t wi = (size_t)pc.hi / 16384 + beyond_windows; while (wi < ci.linear.size() && !ci.linear[wi]) wi++; if (wi < ci.linear.size()) pc.ve = ci.linear[wi]; }
+            out[r].push_back(pc);
+        }
+    }
+    return out;
+}
+
+// whole contigs, longest-processing-time bin packing on compressed span size (modes whose queries need the whole array on one GPU)
+static std::vector<std::vector<Piece>> contig_shards(const std::vector<ContigIndex>& index, const std::vector<uint32_t>& tlen, const std::vector<uint8_t>& want, int n) {
+    std::vector<int> order; for (int t = 0; t < (int)index.size() && t < (int)tlen.size(); t++) if (want[(size_t)t] && index[(size_t)t].has) order.push_back(t);
+    auto weight = [&](int t) { return (index[(size_t)t].end >> 16) - (index[(size_t)t].beg >> 16) + 1; };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weight(a) > weight(b); });
+    std::vector<uint64_t> load((size_t)n, 0); std::vector<std::vector<Piece>> out((size_t)n);
+    for (int t : order) { size_t r = 0; for (size_t k = 1; k < load.size(); k++) if (load[k] < load[r]) r = k; load[r] += weight(t); out[r].push_back(Piece{t, 0, tlen[(size_t)t], index[(size_t)t].beg, index[(size_t)t].end, 0, false}); }
+    for (auto& v : out) std::sort(v.begin(), v.end(), [](const Piece& a, const Piece& b) { return a.tid < b.tid; });
+    return out;
+}
+
+// neighbouring spans of one genuine BAM file merge when the bytes between them are few: they are whole records of other contigs,
+// which the library's target mask drops
+static void merge_spans(std::vector<uint64_t>& sb, std::vector<uint64_t>& se) {
+    std::vector<size_t> ord(sb.size()); std::iota(ord.begin(), ord.end(), 0); std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return sb[a] < sb[b]; });
+    std::vector<uint64_t> mb, me;
+    for (size_t i : ord) { if (!mb.empty() && sb[i] >= me.back() && (sb[i] >> 16) - (me.back() >> 16) <= (1u << 20)) me.back() = std::max(me.back(), se[i]); else if (!mb.empty() && sb[i] < me.back()) me.back() = std::max(me.back(), se[i]); else { mb.push_back(sb[i]); me.push_back(se[i]); } }
+    sb = mb; se = me;
+}
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 #define MSD(call) do { int _rc = (int)(call); if (_rc < 0) die(1, "[mosdepth] %s", msd_last_error(ctx)); } while (0)
 
 int main(int argc, char** argv) {
+    const double t_main = now_s();
     const char *chrom_arg = nullptr, *by = nullptr, *quant_arg = nullptr, *thr_arg = nullptr, *rg_arg = nullptr;
-    int no_per_base = 0, fast_mode = 0, fragment_mode = 0, use_median = 0, mapq = 0, device = 0, plain = 0; int64_t min_len = -1, max_len = -1;
+    int print_shards = 0, no_per_base = 0, fast_mode = 0, fragment_mode = 0, use_median = 0, mapq = 0, device = 0, plain = 0, n_gpus = getenv("MOSDEPTH_B200_GPUS") ? atoi(getenv("MOSDEPTH_B200_GPUS")) : 1; int64_t min_len = -1, max_len = -1;
     uint16_t eflag = 1796, iflag = 0; std::vector<std::string> pos;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -234,6 +309,8 @@ int main(int argc, char** argv) {
         else if (is("-m", "--use-median")) use_median = 1;
         else if (is("-R", "--read-groups")) rg_arg = val();
         else if (a == "--device") device = (int)nim_parse_int(val());
+        else if (a == "--gpus") n_gpus = (int)nim_parse_int(val());         // shard the genome over GPUs device .. device + gpus - 1 (one context and one host thread each)
+        else if (a == "--print-shards") print_shards = 1;                  // test hook: print the multi-GPU plan as JSON and exit (no GPU is touched)
         else if (a == "--plain") plain = 1;                                // write *.bed (uncompressed) instead of *.bed.gz
         else if (a.size() > 1 && a[0] == '-') die(1, "error parsing arguments");
         else pos.push_back(a);
@@ -266,28 +343,99 @@ int main(int argc, char** argv) {
     if (by) { by_digit = *by != 0; for (const char* p = by; *p; p++) if (*p < '0' || *p > '9') by_digit = false; if (by_digit) window = (uint32_t)nim_parse_int(by); else { bed = bed_to_table(by); have_bed = true; } }
 
     // ---- which contigs does the main loop visit (get_targets :482-488, skip rule :703-705)? ------------------------
-    std::vector<uint8_t> want(nt, 0); std::vector<uint64_t> sb, se;
+    std::vector<uint8_t> want(nt, 0);
     auto bed_find = [&](const std::string& name) -> std::vector<Region>* { for (auto& kv : bed) if (kv.first == name) return &kv.second; return nullptr; };
     for (int t = 0; t < nt; t++) {
         if (!chrom.empty() && H.targets[t].name != chrom) continue;
         if (no_per_base && thr.empty() && quant.empty() && have_bed && !bed_find(H.targets[t].name)) continue;
         want[t] = 1;
-        if (t < (int)index.size() && index[t].has) { sb.push_back(index[t].beg); se.push_back(index[t].end); }
     }
-    msd_ctx* ctx = nullptr;
-    if (msd_create(device, &ctx) != 0) die(1, "[mosdepth] %s", msd_last_error(nullptr));
+    // ---- contexts: one per GPU; the genome is cut into one shard per GPU ---------------------------------------------------
+    const double t_start = now_s();
     std::vector<uint32_t> tl(nt); for (int t = 0; t < nt; t++) tl[t] = H.targets[t].length;
-    MSD(msd_open(ctx, bam_path.c_str(), nt, tl.data(), H.first_voff));
-    MSD(msd_set_targets(ctx, want.data()));
-    // merge adjacent contig spans so neighbouring contigs are read in one go
-    { std::vector<uint64_t> mb, me; for (size_t i = 0; i < sb.size(); i++) { if (!mb.empty() && sb[i] >= me.back() && (sb[i] >> 16) - (me.back() >> 16) <= (1u << 20)) me.back() = se[i]; /* bytes in between are whole records of other contigs */ else { mb.push_back(sb[i]); me.push_back(se[i]); } }
-      if (mb.empty()) { mb.push_back(1ull << 16); me.push_back(1ull << 16); }   // nothing indexed: read nothing
-      MSD(msd_set_spans(ctx, (int)mb.size(), mb.data(), me.data())); }
+    if (n_gpus < 1) n_gpus = 1;
+    const int mode = fast_mode ? MSD_MODE_FAST : fragment_mode ? MSD_MODE_FRAGMENT : MSD_MODE_DEFAULT;
+    // ranges inside contigs need: window / whole-contig outputs only (msd_regions and the run calls want the whole array on one GPU),
+    // no fragment mode (a fragment starts before its read 1), and a linear index (BAI)
+    bool any_linear = false; for (auto& ci : index) if (!ci.linear.empty()) any_linear = true;
+    const bool cut_contigs = n_gpus > 1 && no_per_base && quant.empty() && thr.empty() && !have_bed && !fragment_mode && any_linear && !getenv("MOSDEPTH_B200_SHARD_CONTIGS");
+    std::vector<std::vector<Piece>> shards;
+    std::vector<msd_ctx*> ctxs((size_t)n_gpus, nullptr);
+    std::vector<std::string> rank_err((size_t)n_gpus);
     std::vector<const char*> rgs; std::vector<std::string> rg_store;
     if (rg_arg) { std::string s = rg_arg; size_t p = 0; for (;;) { size_t c = s.find(',', p); rg_store.push_back(s.substr(p, c == std::string::npos ? std::string::npos : c - p)); if (c == std::string::npos) break; p = c + 1; } for (auto& r : rg_store) rgs.push_back(r.c_str()); }
-    MSD(msd_set_filters(ctx, mapq, min_len, max_len, eflag, iflag, rgs.empty() ? nullptr : rgs.data(), (int)rgs.size(), fast_mode ? MSD_MODE_FAST : fragment_mode ? MSD_MODE_FRAGMENT : MSD_MODE_DEFAULT));
-    if (by_digit && window && !use_median) MSD(msd_prefetch_windows(ctx, window));   // --by <int>: every contig's window loop in one launch
-    MSD(msd_run(ctx));   // coverage() + to_coverage() for every visited contig
+    if (print_shards) {
+        const auto plan = (n_gpus > 1 && cut_contigs) ? offset_shards(index, tl, want, n_gpus, window, 65536) : contig_shards(index, tl, want, n_gpus);
+        printf("{\"sharding\": \"%s\", \"ranks\": [", (n_gpus > 1 && cut_contigs) ? "offsets" : "contigs");
+        for (size_t r = 0; r < plan.size(); r++) { printf("%s[", r ? ", " : ""); for (size_t k = 0; k < plan[r].size(); k++) { const Piece& pc = plan[r][k]; printf("%s[%d, %u, %u, %llu, %llu, %u]", k ? ", " : "", pc.tid, pc.lo, pc.hi, (unsigned long long)pc.vb, (unsigned long long)pc.ve, pc.cover); } printf("]"); }
+        printf("]}\n");
+        return 0;
+    }
+    uint8_t comm_id[MSD_COMM_ID_BYTES];
+    if (n_gpus > 1 && msd_comm_unique_id(comm_id) != 0) die(1, "[mosdepth] %s", msd_last_error(nullptr));
+    uint32_t margin_bp = 65536;
+    for (int attempt = 0;; attempt++) {
+        if (n_gpus == 1) { shards.assign(1, {}); for (int t = 0; t < nt; t++) if (want[t] && t < (int)index.size() && index[t].has) shards[0].push_back(Piece{t, 0, tl[t], index[t].beg, index[t].end, 0, false}); }
+        else shards = cut_contigs ? offset_shards(index, tl, want, n_gpus, window, margin_bp) : contig_shards(index, tl, want, n_gpus);
+        bool any_cut = false; for (auto& v : shards) for (auto& pc : v) any_cut |= pc.cut;
+        std::vector<int> rank_rc((size_t)n_gpus, 0);
+        auto run_rank = [&](int r) {
+            msd_ctx*& ctx = ctxs[(size_t)r];
+            auto fail = [&](const char* what) { rank_rc[(size_t)r] = -1; rank_err[(size_t)r] = std::string(what) + ": " + msd_last_error(ctx); };
+            if (!ctx) {
+                if (msd_create(device + r, &ctx) != 0) { rank_rc[(size_t)r] = -1; rank_err[(size_t)r] = msd_last_error(nullptr); ctx = nullptr; return; }
+                if (msd_open(ctx, bam_path.c_str(), nt, tl.data(), H.first_voff) < 0) return fail("msd_open");
+                if (msd_set_filters(ctx, mapq, min_len, max_len, eflag, iflag, rgs.empty() ? nullptr : rgs.data(), (int)rgs.size(), mode) < 0) return fail("msd_set_filters");
+                if (n_gpus > 1 && msd_comm_init(ctx, r, n_gpus, comm_id) < 0) return fail("msd_comm_init");
+            }
+            std::vector<uint8_t> mine((size_t)nt, 0); std::vector<uint64_t> sb, se;
+            if (attempt > 0) for (int t = 0; t < nt; t++) msd_set_contig_range(ctx, t, 0, 0);   // a retry with a longer margin: drop the previous ranges
+            for (auto& pc : shards[(size_t)r]) {
+                mine[(size_t)pc.tid] = 1; sb.push_back(pc.vb); se.push_back(pc.ve);
+                if (pc.cut) { if (msd_set_contig_range(ctx, pc.tid, pc.lo, pc.hi) < 0 || msd_set_contig_cover(ctx, pc.tid, pc.cover) < 0) return fail("msd_set_contig_range"); }
+            }
+            // with one GPU every visited contig is selected even when the index has nothing for it (coverage() then returns -2)
+            if (n_gpus == 1) mine = want;
+            if (msd_set_targets(ctx, mine.data()) < 0) return fail("msd_set_targets");
+            merge_spans(sb, se);
+            if (sb.empty()) { sb.push_back(1ull << 16); se.push_back(1ull << 16); }   // nothing indexed for this rank: read nothing
+            if (msd_set_spans(ctx, (int)sb.size(), sb.data(), se.data()) < 0) return fail("msd_set_spans");
+            if (by_digit && window && !use_median && msd_prefetch_windows(ctx, window) < 0) return fail("msd_prefetch_windows");   // --by <int>: every contig's window loop in one launch
+            const int rc = msd_run(ctx);                                              // coverage() + to_coverage() for this rank's pieces
+            if (rc < 0) { rank_rc[(size_t)r] = rc; rank_err[(size_t)r] = msd_last_error(ctx); }
+        };
+        if (n_gpus == 1) run_rank(0);
+        else { std::vector<std::thread> th; for (int r = 0; r < n_gpus; r++) th.emplace_back(run_rank, r); for (auto& t : th) t.join(); }
+        bool retry = false;
+        for (int r = 0; r < n_gpus; r++) {
+            if (rank_rc[(size_t)r] == MSD_ESPAN && margin_bp < (1u << 30)) retry = true;       // a mate lies in front of a shard's span: reach further back
+            else if (rank_rc[(size_t)r] < 0) die(1, "[mosdepth] %s", rank_err[(size_t)r].c_str());
+        }
+        if (retry) { margin_bp = margin_bp >= (1u << 26) ? 0xfffffff0u : margin_bp * 16; if (attempt > 6) die(1, "[mosdepth] %s", rank_err[0].c_str()); continue; }
+        if (any_cut) {   // the depth that reads leave beyond a cut goes to the next rank (NCCL send / recv), then every shard gets its stats
+            std::vector<std::thread> th;
+            for (int r = 0; r < n_gpus; r++) th.emplace_back([&, r] { if (msd_exchange_spills(ctxs[(size_t)r]) < 0) { rank_rc[(size_t)r] = -1; rank_err[(size_t)r] = msd_last_error(ctxs[(size_t)r]); } });
+            for (auto& t : th) t.join();
+            for (int r = 0; r < n_gpus; r++) if (rank_rc[(size_t)r] < 0) die(1, "[mosdepth] %s", rank_err[(size_t)r].c_str());
+        }
+        break;
+    }
+    const double t_run = now_s();
+    // which ranks hold which piece of every contig, in genome (= rank) order
+    struct Owner { int rank; Piece pc; };
+    std::vector<std::vector<Owner>> owners((size_t)nt);
+    for (int r = 0; r < n_gpus; r++) for (auto& pc : shards[(size_t)r]) owners[(size_t)pc.tid].push_back(Owner{r, pc});
+    msd_ctx* ctx = ctxs[0];
+    // coverage()'s return value for a contig: the records of all its pieces
+    auto contig_records = [&](int ti, int64_t* nrec) -> int {
+        if (n_gpus == 1) return msd_contig_records(ctx, ti, nrec);
+        int64_t total = 0;
+        for (auto& o : owners[(size_t)ti]) { int64_t n = 0; const int rc = msd_contig_records(ctxs[(size_t)o.rank], ti, &n); if (rc < -2) { ctx = ctxs[(size_t)o.rank]; return rc; } total += n; }
+        if (nrec) *nrec = total;
+        return total > 0 ? ti : -2;
+    };
+    auto owner_ctx = [&](int ti) -> msd_ctx* { return (n_gpus == 1 || owners[(size_t)ti].empty()) ? ctxs[0] : ctxs[(size_t)owners[(size_t)ti][0].rank]; };
+    auto is_cut = [&](int ti) { return n_gpus > 1 && (owners[(size_t)ti].size() > 1 || (owners[(size_t)ti].size() == 1 && owners[(size_t)ti][0].pc.cut)); };
 
     // ---- outputs (mosdepth.nim:641-682) -------------------------------------------------------------------------------
     const std::string gz = plain ? "" : ".gz";
@@ -312,7 +460,8 @@ int main(int argc, char** argv) {
         std::vector<Region>* bc = have_bed ? bed_find(target.name) : nullptr;
         if (no_per_base && thr.empty() && quant.empty() && have_bed && !bc) continue;       // :703-705
         int64_t nrec = 0;
-        int tid = msd_contig_records(ctx, ti, &nrec);                                          // coverage() return value
+        ctx = owner_ctx(ti);                                                                   // the context the MSD() macro reports errors of
+        int tid = contig_records(ti, &nrec);                                                   // coverage() return value
         if (tid < -2) die(1, "[mosdepth] %s", msd_last_error(ctx));
         std::vector<int64_t> chrom_global(512, 0), chrom_region(512, 0);
         msd_depth_stat chrom_stat, chrom_region_stat; stat_clear(chrom_stat); stat_clear(chrom_region_stat);
@@ -327,13 +476,24 @@ int main(int argc, char** argv) {
                 if (!have_bed) {
                     int64_t d512[512];
                     if (!thr.empty() || false) { /* thresholds in window mode go through the region call below */ }
-                    MSD(msd_windows(ctx, ti, window, use_median, values.data(), (int64_t)values.size(), &chrom_region_stat, d512));
-                    chrom_region.assign(d512, d512 + 512);
+                    if (!is_cut(ti)) { MSD(msd_windows(ctx, ti, window, use_median, values.data(), (int64_t)values.size(), &chrom_region_stat, d512)); chrom_region.assign(d512, d512 + 512); }
+                    else {   // the contig's windows, shard by shard in genome order (cuts are multiples of the window)
+                        int64_t at = 0;
+                        for (auto& o : owners[(size_t)ti]) {
+                            ctx = ctxs[(size_t)o.rank]; msd_depth_stat st1;
+                            const int64_t got = msd_windows(ctx, ti, window, use_median, values.data() + at, (int64_t)values.size() - at, &st1, d512);
+                            if (got < 0) die(1, "[mosdepth] %s", msd_last_error(ctx));
+                            if ((uint64_t)at * window != o.pc.lo) die(1, "[mosdepth] internal error: the shards of %s do not meet at a window boundary", target.name.c_str());
+                            at += got; chrom_region_stat = stat_add(chrom_region_stat, st1);
+                            for (int k = 0; k < 512; k++) chrom_region[(size_t)k] += d512[k];
+                        }
+                        if (at != (int64_t)n_regions) die(1, "[mosdepth] internal error: the shards of %s returned %lld of %zu windows", target.name.c_str(), (long long)at, n_regions);
+                    }
                     if (!thr.empty()) {   // thresholds need per-window counts: same windows as explicit regions
                         rs.resize(n_regions); re.resize(n_regions);
                         for (size_t k = 0; k < n_regions; k++) { rs[k] = (uint32_t)(k * (uint64_t)window); re[k] = (uint32_t)std::min<uint64_t>((k + 1) * (uint64_t)window, target.length); }
-                        std::vector<double> dummy(n_regions); msd_depth_stat dst; int64_t dl = 0;
-                        MSD(msd_regions(ctx, ti, (int64_t)n_regions, rs.data(), re.data(), use_median, dummy.data(), &dst, nullptr, 0, &dl, thr.data(), (int)thr.size(), thr_counts.data()));
+                        std::vector<double> dummy(n_regions);
+                        MSD(msd_regions(ctx, ti, (int64_t)n_regions, rs.data(), re.data(), use_median, dummy.data(), nullptr, nullptr, 0, nullptr, thr.data(), (int)thr.size(), thr_counts.data()));
                     }
                 } else {
                     rs.resize(n_regions); re.resize(n_regions);
@@ -361,8 +521,13 @@ int main(int argc, char** argv) {
         }
         if (tid != -2) {                                                                       // :745-753
             int64_t dl = 0; std::vector<int64_t> d(400001);
-            MSD(msd_contig_stats(ctx, ti, &chrom_stat, d.data(), (int64_t)d.size(), &dl));
-            d.resize((size_t)std::max<int64_t>(dl, 512)); chrom_global = d;
+            if (!is_cut(ti)) { MSD(msd_contig_stats(ctx, ti, &chrom_stat, d.data(), (int64_t)d.size(), &dl)); d.resize((size_t)std::max<int64_t>(dl, 512)); chrom_global = d; }
+            else for (auto& o : owners[(size_t)ti]) {   // a sharded contig: lengths / sums add up, extremes combine, bins add up (depth_stat `+`, sum_into)
+                ctx = ctxs[(size_t)o.rank]; msd_depth_stat st1;
+                MSD(msd_contig_stats(ctx, ti, &st1, d.data(), (int64_t)d.size(), &dl));
+                chrom_stat = stat_add(chrom_stat, st1);
+                sum_into(std::vector<int64_t>(d.begin(), d.begin() + dl), chrom_global);
+            }
             global_stat = stat_add(global_stat, chrom_stat);
             write_summary(target.name, chrom_stat, fh_sum);
             if (by) write_summary(target.name + "_region", chrom_region_stat, fh_sum);
@@ -407,6 +572,23 @@ int main(int argc, char** argv) {
             }
         }
     }
+    const double t_emit = now_s();
+    if (n_gpus > 1) {
+        // the `total` rows across GPUs: every context has accumulated what it was asked for (sum_into, depth_stat `+`); all-reduce them
+        // over NCCL and check them against the sums this host kept in header order like the reference (:761-764)
+        std::vector<int> arc((size_t)n_gpus, 0); std::vector<std::thread> th;
+        for (int r = 0; r < n_gpus; r++) th.emplace_back([&, r] { arc[(size_t)r] = msd_totals_allreduce(ctxs[(size_t)r]); });
+        for (auto& t : th) t.join();
+        for (int r = 0; r < n_gpus; r++) if (arc[(size_t)r] < 0) die(1, "[mosdepth] %s", msd_last_error(ctxs[(size_t)r]));
+        msd_depth_stat tg, tr; std::vector<int64_t> gd(400001), rd(400001); int64_t gl = 0, rl = 0;
+        ctx = ctxs[0];
+        MSD(msd_totals(ctx, &tg, &tr, gd.data(), (int64_t)gd.size(), &gl, rd.data(), (int64_t)rd.size(), &rl));
+        auto same_stat = [](const msd_depth_stat& a, const msd_depth_stat& b) { return a.cum_length == b.cum_length && a.cum_depth == b.cum_depth && a.min_depth == b.min_depth && a.max_depth == b.max_depth; };
+        auto same_dist = [](const std::vector<int64_t>& host, const std::vector<int64_t>& dev, int64_t n) { for (size_t i = 0; i < std::max(host.size(), (size_t)n); i++) { const int64_t a = i < host.size() ? host[i] : 0, b = (int64_t)i < n ? dev[i] : 0; if (a != b) return false; } return true; };
+        if (!same_stat(tg, global_stat) || !same_dist(global_distribution, gd, gl) || (by && (!same_stat(tr, global_region_stat) || !same_dist(region_distribution, rd, rl))))
+            die(1, "[mosdepth] internal error: the all-reduced totals of the %d GPUs differ from the per-contig sums", n_gpus);
+        global_stat = tg; if (by) global_region_stat = tr;
+    }
     write_summary("total", global_stat, fh_sum);                                               // :807-813
     if (by) write_summary("total_region", global_region_stat, fh_sum);
     write_distribution("total", global_distribution, fh_gd);
@@ -417,7 +599,13 @@ int main(int argc, char** argv) {
     if (fthr.f && fthr.close() != 0) { fprintf(stderr, "[mosdepth] error writing thresholds file\n\n"); return 1; }
     if (fbase.f && fbase.close() != 0) { fprintf(stderr, "[mosdepth] error writing per-base file\n\n"); return 1; }
     fclose(fh_gd); fclose(fh_sum);
-    if (getenv("MOSDEPTH_B200_STATS")) { msd_run_info ri; msd_last_run_info(ctx, &ri); fprintf(stderr, "[mosdepth-b200] records=%llu blocks=%llu inflate_ms=%.3f frame_ms=%.3f records_ms=%.3f scan_ms=%.3f total_ms=%.3f\n", (unsigned long long)ri.n_records, (unsigned long long)ri.n_blocks, ri.ms_inflate, ri.ms_frame, ri.ms_records, ri.ms_scan, ri.ms_total); }
-    msd_destroy(ctx);
+    const double t_close = now_s();
+    if (getenv("MOSDEPTH_B200_STATS")) {
+        unsigned long long recs = 0, blocks = 0; double dev_ms = 0;
+        for (int r = 0; r < n_gpus; r++) { msd_run_info ri; msd_last_run_info(ctxs[(size_t)r], &ri); recs += ri.n_records; blocks += ri.n_blocks; dev_ms = std::max(dev_ms, ri.ms_total); }
+        fprintf(stderr, "[mosdepth-b200] {\"gpus\": %d, \"sharding\": \"%s\", \"records\": %llu, \"blocks\": %llu, \"device_ms_max\": %.3f, \"wall_s\": {\"parse_header_index\": %.3f, \"create_open_run\": %.3f, \"emit\": %.3f, \"totals_close\": %.3f}}\n",
+                n_gpus, n_gpus == 1 ? "none" : cut_contigs ? "offsets" : "contigs", recs, blocks, dev_ms, t_start - t_main, t_run - t_start, t_emit - t_run, t_close - t_emit);
+    }
+    for (msd_ctx* c : ctxs) msd_destroy(c);
     return 0;
 }

@@ -80,12 +80,14 @@ def split_contig(ci, tlen, n_parts, window=0, margin_bp=65536, beyond_windows=8)
     return parts
 
 
-def offset_shards(index, lengths, n, window=0, margin_bp=65536, beyond_windows=8):
+def offset_shards(index, lengths, n, window=0, margin_bp=65536, beyond_windows=8, with_cover=False):
     """Shard the genome into n contiguous BGZF offset ranges of equal compressed size (north_star: "index-derived BGZF
     offset ranges"): the cuts fall inside contigs, at BAI linear-index entries aligned like split_contig()'s.  Returns,
     per rank, a list of (tid, lo, hi, voff_beg, voff_end) in file order; lo == 0 and hi == tlen mark a whole contig.  A
     rank's pieces are adjacent in the file, so they merge into one span; only the (at most two) cut contigs of a rank
-    need the spill exchange."""
+    need the spill exchange.  with_cover: a sixth element per piece, the position from which on the span is known to hold
+    every record of the contig (the start of the linear-index window the span begins at; msd_set_contig_cover).  The same plan
+    as the host CLI's (mosdepth_b200/host/main.cpp offset_shards, `--print-shards`)."""
     import math
     have = [t for t in range(len(index)) if index[t].has_data]
     if not have:
@@ -127,9 +129,21 @@ def offset_shards(index, lengths, n, window=0, margin_bp=65536, beyond_windows=8
                     return ci.ref_end
                 return lin[wi] if lin[wi] else ci.ref_beg
 
-            vb = ci.ref_beg if lo == 0 else voff_at(max(0, (lo - margin_bp) // 16384))
-            ve = ci.ref_end if hi >= lengths[t] else voff_at(hi // 16384 + beyond_windows)
-            pieces.append((t, lo, hi, vb, ve))
+            vb, cover = ci.ref_beg, 0
+            if lo > margin_bp:
+                wi = min((lo - margin_bp) // 16384, len(lin) - 1)
+                while wi > 0 and not lin[wi]:
+                    wi -= 1
+                if wi > 0:
+                    vb, cover = lin[wi], wi * 16384
+            ve = ci.ref_end
+            if hi < lengths[t]:
+                wi = hi // 16384 + beyond_windows
+                while wi < len(lin) and not lin[wi]:
+                    wi += 1
+                if wi < len(lin):
+                    ve = lin[wi]
+            pieces.append((t, lo, hi, vb, ve, cover) if with_cover else (t, lo, hi, vb, ve))
         out.append(pieces)
     while len(out) < n:
         out.append([])

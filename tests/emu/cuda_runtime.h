@@ -127,6 +127,8 @@ template <class T> inline T emu_atomic_minmax(T* p, T v, bool is_min) { T o = __
 inline unsigned atomicMin(unsigned* p, unsigned v) { return emu_atomic_minmax(p, v, true); }
 inline unsigned atomicMax(unsigned* p, unsigned v) { return emu_atomic_minmax(p, v, false); }
 inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { return emu_atomic_minmax(p, v, false); }
+inline long long atomicMin(long long* p, long long v) { return emu_atomic_minmax(p, v, true); }
+inline long long atomicMax(long long* p, long long v) { return emu_atomic_minmax(p, v, false); }
 inline unsigned __reduce_min_sync(unsigned, unsigned v) {
     emu::Warp& w = emu::warp(); w.slot[emu::lane()] = v;
     w.bar->arrive_and_wait();

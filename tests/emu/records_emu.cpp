@@ -41,7 +41,7 @@ int main(int argc, char** argv) {
     std::vector<uint64_t> depth_off((size_t)n_ref); ull cells = 0; for (int t = 0; t < n_ref; t++) { depth_off[(size_t)t] = cells; cells += (((ull)tlen[(size_t)t] + 1) * 4 + 127) / 128 * 32; }
     std::vector<int32_t> arena(cells + 64, 0);
     std::vector<uint32_t> range_lo((size_t)n_ref, 0), range_hi((size_t)n_ref, 0xffffffffu); std::vector<ull> n_beyond((size_t)n_ref, 0), nprefilter((size_t)n_ref, 0);
-    ContigTable ct{depth_off.data(), tlen.data(), range_lo.data(), range_hi.data(), nullptr, n_beyond.data()};
+    ContigTable ct{depth_off.data(), tlen.data(), range_lo.data(), range_hi.data(), nullptr, n_beyond.data(), nullptr};
     FilterParams fp; memset(&fp, 0, sizeof fp); fp.mapq = 0; fp.min_len = -1; fp.max_len = INT64_MAX; fp.eflag = 1796; fp.iflag = 0; fp.mode = mode; fp.n_rg = 0; fp.rg_names = nullptr; fp.n_targets = n_ref;
     const uint32_t carry_cap = 4u << 20; const size_t chunk_infl = per_chunk * 65536 + 65536;
     std::vector<uint8_t> infl[2]; for (auto& v : infl) v.assign((size_t)carry_cap + chunk_infl + 4096, 0);
@@ -76,8 +76,8 @@ int main(int argc, char** argv) {
             memset(mt_word.data(), 0xff, 8ull * slots); memset(mt_head.data(), 0xff, 4ull * slots); memset(mt_live.data(), 0xff, 4ull * slots);
             *Ln.n = 0; *Ln.arena_used = 0;
             emu::launch((unsigned)std::max(1, max_ctas / 4), 256, [&]() { mate_reinsert_kernel(mt, L, buf, recoff.data(), &rc); });
-            emu::launch((unsigned)max_ctas, 256, [&]() { mate_link_kernel(mt, L, buf, recoff.data(), &cs, mc, 0, &rc); });
-            emu::launch((unsigned)max_ctas, 256, [&]() { mate_link_kernel(mt, L, buf, recoff.data(), &cs, mc, 1, &rc); });
+            emu::launch((unsigned)max_ctas, 256, [&]() { mate_link_kernel(mt, L, buf, recoff.data(), &cs, mc, 0, &rc, ct); });
+            emu::launch((unsigned)max_ctas, 256, [&]() { mate_link_kernel(mt, L, buf, recoff.data(), &cs, mc, 1, &rc, ct); });
             emu::launch((unsigned)max_ctas, 256, [&]() { mate_replay_kernel(mt, L, Ln, buf, recoff.data(), &cs, mc, ct, arena.data(), &rc); });
             emu::launch((unsigned)std::max(1, max_ctas / 4), 256, [&]() { mate_carry_kernel(L, Ln, &rc); });
             live_cur ^= 1;

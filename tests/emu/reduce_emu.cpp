@@ -1,4 +1,4 @@
-// reduce_emu.cpp -- K6 (scan.cuh: scan_fused_kernel) and K7 (regions.cuh: windows_mean_kernel, windows_all_kernel, windows_kernel, regions_kernel)
+// reduce_emu.cpp -- K6 (scan.cuh: scan_segments_kernel, totals_add_kernel) and K7 (regions.cuh: windows_mean_kernel, windows_all_kernel, windows_kernel, regions_kernel)
 // executed on the CPU under tests/emu/cuda_runtime.h with the launch geometry of run_scan / msd_windows / msd_regions
 // (mosdepth_b200/csrc/msd_api.cu), against a plain restatement of the reference's arithmetic:
 //   to_coverage mosdepth.nim:54-56 (int32 prefix sum, wraps), inc :417-437, newDepthStat depthstat.nim:39-45, imean :399-413
@@ -50,16 +50,48 @@ int main(int argc, char** argv) {
     for (int k = 0; k < 3 && tlen > 1000; k++) { const uint32_t s = (uint32_t)(rnd() % (tlen - 600)); arr[s] += 2000 + 70000 * k; arr[s + 500] -= 2000 + 70000 * k; }
     std::vector<int32_t> want(arr, arr + L);
     { uint32_t s = 0; for (uint32_t i = 0; i < L; i++) { s += (uint32_t)want[i]; want[i] = (int32_t)s; } }
-    // ---- K6: run_scan(arr, n_scan = tlen + 1, n_stat = tlen, do_stats = 1) ----------------------------------------------------------
+    // ---- K6: run_segments(): three segments in one launch -- this contig (tlen + 1 cells scanned, tlen feed the stats), a copy of its
+    //      first third as a second contig, and a shard-like segment without stats; then the stats-only pass (msd_contig_finalize) ----
+    {
+        const uint32_t n2 = tlen / 3 + 1, n3 = std::min<uint32_t>(tlen, 5000) + 1;
+        std::vector<ull> off(3); ull cells = 0; const uint32_t ns[3] = {L, n2 + 1, n3};
+        for (int c = 0; c < 3; c++) { off[c] = cells; cells += ((ull)ns[c] + 31) / 32 * 32; }
+        int32_t* arena = nullptr; if (posix_memalign((void**)&arena, 128, (cells + 64) * 4)) return 2;
+        memset(arena, 0, (cells + 64) * 4);
+        for (int c = 0; c < 3; c++) memcpy(arena + off[c], arr, (size_t)ns[c] * 4);          // deltas (a prefix of a delta array is a delta array)
+        std::vector<ScanSeg> segs(3); uint32_t tiles = 0;
+        for (int c = 0; c < 3; c++) { segs[c].arr_off = off[c]; segs[c].n_scan = ns[c]; segs[c].n_stat = c == 0 ? tlen : c == 1 ? n2 : 0; segs[c].first_tile = tiles; segs[c].slot = (uint32_t)c; tiles += (ns[c] + kScanTile - 1) / kScanTile; }
+        std::vector<ull> tile_state(tiles, 0), hist_all(3 * (size_t)kHistKeep, 0); uint32_t ticket = 0;
+        std::vector<ContigAccum> acc(3, ContigAccum{0, 0xffffffffu, 0, 0, 0});
+        emu::launch((unsigned)std::min<uint64_t>(tiles, (uint64_t)max_ctas), kScanThreads, [&]() { scan_segments_kernel<true>(arena, segs.data(), 3, tiles, tile_state.data(), &ticket, acc.data(), hist_all.data()); });
+        for (int c = 0; c < 3; c++) for (uint32_t i = 0; i < ns[c]; i++) if (arena[off[c] + i] != want[i]) return fail("prefix sum (segment)", (long long)c * 1000000000ll + i, arena[off[c] + i], want[i]);
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 1) {   // the stats-only pass over the same (now depth) arrays, taken by stride: must give the same numbers
+                std::fill(hist_all.begin(), hist_all.end(), 0ull); for (auto& a : acc) a = ContigAccum{0, 0xffffffffu, 0, 0, 0};
+                emu::launch((unsigned)std::min<uint64_t>(tiles, (uint64_t)std::max(1, max_ctas / 2)), kScanThreads, [&]() { scan_segments_kernel<false>(arena, segs.data(), 3, tiles, tile_state.data(), &ticket, acc.data(), hist_all.data()); });
+                for (int c = 0; c < 3; c++) for (uint32_t i = 0; i < ns[c]; i++) if (arena[off[c] + i] != want[i]) return fail("stats pass changed the array", i, arena[off[c] + i], want[i]);
+            }
+            for (int c = 0; c < 3; c++) {
+                const uint32_t nst = segs[c].n_stat;
+                std::vector<ull> h(kHistKeep, 0); Stat st;
+                for (uint32_t i = 0; i < nst; i++) { const int32_t v = want[i]; if (v >= 0 && v < kHistKeep) h[v]++; }
+                stat_add(st, want.data(), nst);
+                if (nst == 0) { st.mn = 0xffffffffu; st.mx = 0; }
+                for (int b = 0; b < kHistKeep; b++) if (h[b] != hist_all[(size_t)c * kHistKeep + b]) return fail(pass ? "segment dist bin (stats pass)" : "segment dist bin", (long long)c * 1000000 + b, (double)hist_all[(size_t)c * kHistKeep + b], (double)h[b]);
+                if (acc[c].cum_depth != st.sum || acc[c].min_depth != st.mn || acc[c].max_depth != st.mx) return fail("segment stats (sum)", c, (double)acc[c].cum_depth, (double)st.sum);
+            }
+        }
+        // sum_into for the segments: bins up to each segment's maximum (segments deeper than kHistKeep are left to the host)
+        std::vector<long long> tot(kDistBins, 0), ts = {0, 0, 0xffffffffll, 0};
+        emu::launch(kTotalsParts * 3, 256, [&]() { totals_add_kernel(segs.data(), 3, acc.data(), hist_all.data(), tot.data(), ts.data()); });
+        { std::vector<long long> h(kDistBins, 0); long long len = 0, sum = 0, mn = 0xffffffffll, mx = 0;
+          for (int c = 0; c < 3; c++) { if (!segs[c].n_stat || acc[c].max_depth >= (uint32_t)kHistKeep) continue; for (uint32_t i = 0; i < segs[c].n_stat; i++) if (want[i] >= 0) h[want[i]]++; len += segs[c].n_stat; sum += (long long)acc[c].cum_depth; mn = std::min<long long>(mn, acc[c].min_depth); mx = std::max<long long>(mx, acc[c].max_depth); }
+          for (int b = 0; b < kDistBins; b++) if (h[b] != tot[b]) return fail("total dist bin", b, (double)tot[b], (double)h[b]);
+          if (ts[0] != len || ts[1] != sum || ts[2] != mn || ts[3] != mx) return fail("total stats", 0, (double)ts[1], (double)sum); }
+        memcpy(arr, arena, (size_t)L * 4);      // the kernels below read the contig's depth array
+        free(arena);
+    }
     const uint64_t n_tiles = ((uint64_t)L + kScanTile - 1) / kScanTile;
-    std::vector<ull> tile_state(n_tiles, 0), hist(kDistBins, 0); uint32_t ticket = 0; ContigAccum acc{0, 0xffffffffu, 0, 0, 0};
-    emu::launch((unsigned)std::min<uint64_t>(n_tiles, (uint64_t)max_ctas), kScanThreads, [&]() { scan_fused_kernel(arr, L, tlen, tile_state.data(), &ticket, hist.data(), &acc, 1); });
-    for (uint32_t i = 0; i < L; i++) if (arr[i] != want[i]) return fail("prefix sum", i, arr[i], want[i]);
-    { std::vector<ull> h(kDistBins, 0); Stat st;
-      for (uint32_t i = 0; i < tlen; i++) { int32_t v = want[i]; if (v > (int32_t)kMaxCoverage) v = kMaxCoverage - 10; if (v >= 0) h[v]++; }
-      stat_add(st, want.data(), tlen);
-      for (int b = 0; b < kDistBins; b++) if (h[b] != hist[b]) return fail("contig dist bin", b, (double)hist[b], (double)h[b]);
-      if (acc.cum_depth != st.sum || acc.min_depth != st.mn || acc.max_depth != st.mx) return fail("contig stats (sum)", 0, (double)acc.cum_depth, (double)st.sum); }
     // ---- K7 windows: msd_windows(mean) and msd_windows(median) ----------------------------------------------------------------------
     const long long nw = tlen ? ((long long)tlen + window - 1) / window : 0;
     for (int median = 0; median < 2; median++) {

@@ -172,6 +172,17 @@ int msd_quantized_runs(msd_ctx *ctx, int tid, const int64_t *quants, int nq, con
 }
 
 /* the rest of the ABI: present so that the ctypes binding (mosdepth_b200/__init__.py) loads against the double; not provided */
+/* multi-GPU calls: the test double is one context on no GPU; the CLI only makes these calls with --gpus > 1 */
+int msd_set_contig_cover(msd_ctx *ctx, int tid, uint32_t covered_from) { (void)ctx; (void)tid; (void)covered_from; return MSD_OK; }
+int msd_contig_span_need(msd_ctx *ctx, int tid, uint32_t *a, uint32_t *b) { (void)ctx; (void)tid; if (a) *a = 0xffffffffu; if (b) *b = 0; return MSD_OK; }
+int msd_comm_unique_id(void *id) { (void)id; return fail(MSD_ECOMM, "mock: no NCCL in the test double"); }
+int msd_comm_init(msd_ctx *ctx, int rank, int world, const void *id) { (void)ctx; (void)rank; (void)world; (void)id; return fail(MSD_ECOMM, "mock: no NCCL in the test double"); }
+int msd_comm_destroy(msd_ctx *ctx) { (void)ctx; return MSD_OK; }
+int msd_exchange_spills(msd_ctx *ctx) { (void)ctx; return fail(MSD_ECOMM, "mock: no NCCL in the test double"); }
+int msd_totals_allreduce(msd_ctx *ctx) { (void)ctx; return fail(MSD_ECOMM, "mock: no NCCL in the test double"); }
+int msd_totals(msd_ctx *ctx, msd_depth_stat *g, msd_depth_stat *r, int64_t *gd, int64_t gc, int64_t *gl, int64_t *rd, int64_t rc, int64_t *rl) {
+    (void)ctx; (void)g; (void)r; (void)gd; (void)gc; (void)gl; (void)rd; (void)rc; (void)rl; return fail(MSD_EINVAL, "mock: msd_totals is not provided");
+}
 int msd_set_contig_range(msd_ctx *c, int t, uint32_t lo, uint32_t hi) { (void)c; (void)t; (void)lo; (void)hi; return fail(MSD_EINVAL, "mock: not provided"); }
 int msd_contig_spill(msd_ctx *c, int t, uint32_t *f, uint32_t *n) { (void)c; (void)t; (void)f; (void)n; return fail(MSD_EINVAL, "mock: not provided"); }
 int msd_depth_copy(msd_ctx *c, int t, uint32_t p, uint32_t n, int32_t *d, int dev) { (void)c; (void)t; (void)p; (void)n; (void)d; (void)dev; return fail(MSD_EINVAL, "mock: not provided"); }

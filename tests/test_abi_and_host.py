@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(built):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     import mosdepth_b200 as m
     assert set(m.EXPORTS) == declared
-    assert m.load_library().msd_abi_version() == 1
+    assert m.load_library().msd_abi_version() == 2
 
 
 def test_no_cpu_fallback(built):
@@ -180,3 +180,27 @@ def test_ingest_parallel_copy_equals_memcpy(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert json.loads(r.stdout)["bad"] == 0
+
+
+def test_cli_shard_plan_equals_python_plan(tmp_path):
+    """The host CLI's multi-GPU plan (`--print-shards`, no GPU touched) is the plan of mosdepth_b200.shard: offset ranges cut inside
+    contigs for window mode, whole contigs (LPT) for the modes whose queries need a contig on one GPU."""
+    import json
+    from mosdepth_b200 import hostio
+    from mosdepth_b200.shard import contig_weights, lpt_shards, offset_shards
+    bam = tmp_path / "s.bam"
+    subprocess.run([str(ROOT / "tools" / "gen_bam"), "--config", "c3", "--genome-fraction", "0.003", "--threads", "4", "-o", str(bam)], check=True, capture_output=True)
+    hdr, idx = hostio.read_bam_header(bam), hostio.read_index(bam)
+    cli = ROOT / "mosdepth_b200" / "bin" / "mosdepth-b200"
+    for n in (2, 3, 8):
+        got = json.loads(subprocess.run([str(cli), "--print-shards", "--gpus", str(n), "-n", "-x", "--by", "500", "x", str(bam)], check=True, capture_output=True, text=True).stdout)
+        assert got["sharding"] == "offsets"
+        want = offset_shards(idx, hdr.lengths, n, window=500, with_cover=True)
+        assert [[tuple(p) for p in r] for r in got["ranks"]] == [[tuple(int(x) for x in p) for p in r] for r in want]
+        for r in got["ranks"]:      # a cut piece's cover never lies beyond its margin
+            for t, lo, hi, vb, ve, cover in r:
+                assert cover <= max(lo - 65536, 0) and vb < ve
+        # per-base output needs whole contigs: LPT
+        got = json.loads(subprocess.run([str(cli), "--print-shards", "--gpus", str(n), "--by", "500", "x", str(bam)], check=True, capture_output=True, text=True).stdout)
+        assert got["sharding"] == "contigs"
+        assert [[p[0] for p in r] for r in got["ranks"]] == lpt_shards(contig_weights(idx), n)
