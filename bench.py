@@ -2,21 +2,25 @@
 """bench.py -- headline benchmark of the mosdepth depth hot path on B200.
 
 Metric (BASELINE.json): reads/s (and wall seconds) for a synthetic 30X whole-genome BAM with `--by 500 -n -x`
-(config C3: fast mode, 500-bp windows, no per-base output), contigs sharded across 1/2/4/8 GPUs.
+(config C3: fast mode, 500-bp windows, no per-base output) on 1/2/4/8 GPUs of one node.
 
 A "step" is one full pass of the hot path over the synthetic BAM: BGZF inflate -> record framing -> filters ->
-+1/-1 depth events -> per-contig prefix sum + contig stats + global dist -> window means / window stats /
-window dist for every contig (what the reference's main loop computes for `--by 500 -n -x`, mosdepth.nim:691-764),
-plus the NCCL all-reduce of the `total` histograms/stats when N > 1.
++1/-1 depth events -> prefix sum + contig stats + global dist of every contig (one launch) -> window means / window stats /
+window dist of every contig (what the reference's main loop computes for `--by 500 -n -x`, mosdepth.nim:691-764); with
+N > 1 GPUs the genome is cut into N equal BGZF offset ranges (cuts inside contigs), the depth that reads leave beyond a cut
+goes to the next rank (ncclSend/ncclRecv inside the library, msd_exchange_spills) and the `total` rows are all-reduced
+(msd_totals_allreduce).  The SAME BAM is used at every N ("scaling": "strong": the metric is one 30X genome on 1/2/4/8 GPUs).
 
   value : compressed BAM bytes already staged in HBM (msd_stage) when the timed region starts.
-  e2e   : the same pass from a pinned HOST buffer holding the BAM file (host->device copies of the compressed
-          bytes and device->host copies of every result inside the timed region), through the C ABI.
+  e2e   : the same pass from a pinned HOST buffer holding this rank's bytes of the BAM file (host->device copies of the
+          compressed bytes and device->host copies of every result inside the timed region), through the C ABI.
+          e2e.cli_wall_s is the wall clock of the `mosdepth-b200` PROCESS on the same BAM (file in the page cache ->
+          regions.bed.gz + .csi closed), which is what BASELINE.json's "wall s" names.
   --impl reference : the CPU oracle (oracle/mosdepth_oracle, a restatement of mosdepth; the real binary cannot be
-          built here) on the same BAM with all host threads, `-t nproc-1 --by 500 -n -x`.
+          built here) with the best of T in {0, 3, 7, 15, nproc-1} inflate threads, on a BOUNDED SAMPLE of the same workload.
 
-The genome is scaled by --genome-fraction (25 GRCh38 contigs, 30X, 150-bp pairs are kept) because a full 30X
-WGS BAM (~60 GB) cannot be generated on the box inside the bench budget; reads/s is what is reported.
+Before anything is timed, a small BAM of the same shape goes through the very same code path (all N ranks) and every output
+file is rendered and compared byte for byte with the oracle's: `config.parity_checked`.
 """
 from __future__ import annotations
 
@@ -25,6 +29,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 from pathlib import Path
@@ -32,14 +37,17 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+SAMPLE_FRACTION = 0.03      # the bounded CPU sample: 18.5 M reads, ~1.7 GB of BAM, 2-4 s of oracle time per pass
+PARITY_FRACTION = 0.004     # the small BAM every output of which is compared with the oracle before the timed region
+
 
 def sh(cmd, **kw):
     return subprocess.run(cmd, check=True, capture_output=True, text=True, **kw)
 
 
 def ensure_built():
-    if not (ROOT / "mosdepth_b200" / "libmosdepth_b200.so").exists() or not (ROOT / "tools" / "gen_bam").exists() \
-            or not (ROOT / "oracle" / "mosdepth_oracle").exists():
+    need = ["mosdepth_b200/libmosdepth_b200.so", "mosdepth_b200/bin/mosdepth-b200", "tools/gen_bam", "oracle/mosdepth_oracle"]
+    if not all((ROOT / n).exists() for n in need):
         import __graft_entry__ as ge
         ge.build()
 
@@ -52,7 +60,7 @@ def _candidates():
             yield p
 
 
-def data_dir(need_bytes=0, keep_tag=None):
+def data_dir(need_bytes=0, keep_tags=()):
     """A writable directory (memory-backed when possible) with room for `need_bytes`; BAMs cached for other sizes are
     dropped before a slower directory is tried."""
     cands = list(_candidates())
@@ -64,31 +72,46 @@ def data_dir(need_bytes=0, keep_tag=None):
             return p
     for p in cands:
         for f in p.iterdir():
-            if f.is_file() and (keep_tag is None or not f.name.startswith(keep_tag)):
+            if f.is_file() and not any(f.name.startswith(t) for t in keep_tags):
                 f.unlink()
         if free(p) >= need_bytes:
             return p
     raise RuntimeError(f"no data dir with {need_bytes / 1e9:.1f} GB free")
 
 
-def make_bam(config, fraction, seed, threads, level=6):
+def bam_tag(config, fraction, seed, level=6):
+    return f"{config}_f{fraction:g}_s{seed}_l{level}"
+
+
+def make_bam(config, fraction, seed, threads, level=6, keep_tags=()):
     """Generate (or reuse) the synthetic BAM. Returns (path, n_reads, n_bytes)."""
-    tag = f"{config}_f{fraction:g}_s{seed}_l{level}"
-    for d in _candidates():      # generated earlier (by this rank or by rank 0)
+    tag = bam_tag(config, fraction, seed, level)
+    for d in _candidates():      # generated earlier (by this rank, by rank 0, or by an earlier N of the same scaling run)
         bam, meta = d / f"{tag}.bam", d / f"{tag}.json"
         if bam.exists() and meta.exists() and Path(str(bam) + ".bai").exists():
             info = json.loads(meta.read_text())
             return bam, info["reads"], info["bytes"]
-    d = data_dir(int(fraction * 60e9 * 1.1) + (64 << 20), keep_tag=tag)     # a 30X genome is ~56 GB of BAM at level 6
+    d = data_dir(int(fraction * 60e9 * 1.1) + (64 << 20), keep_tags=(tag,) + tuple(keep_tags))     # a 30X genome is ~56 GB of BAM at level 6
     bam, meta = d / f"{tag}.bam", d / f"{tag}.json"
     tmp = d / f"{tag}.tmp.{os.getpid()}.bam"
+    t0 = time.perf_counter()
     r = sh([str(ROOT / "tools" / "gen_bam"), "--config", config, "--genome-fraction", str(fraction), "--seed", str(seed),
             "--threads", str(threads), "--level", str(level), "-o", str(tmp)])
     info = json.loads(r.stdout.strip().splitlines()[-1])
+    info["gen_s"] = time.perf_counter() - t0
     os.replace(str(tmp) + ".bai", str(bam) + ".bai")
     os.replace(tmp, bam)
     meta.write_text(json.dumps(info))
     return bam, info["reads"], info["bytes"]
+
+
+def workload_config(args, world, parity):
+    """The `config` object: the same keys and values in both arms (the reference arm runs a bounded sample OF THIS workload)."""
+    f = args.genome_fraction
+    return {"workload": f"C3 synthetic 30X WGS (25 GRCh38 contigs x {f:g} = {f * 3088286401 / 1e6:.0f} Mbp, 150-bp pairs, BGZF level 6) --by {args.window} -n -x",
+            "genome_fraction": f, "flags": f"--by {args.window} -n -x", "window": args.window, "gpus": world,
+            "l2": "inputs (compressed BAM, depth arrays) are far larger than the 126 MB L2; no flush needed",
+            "parity_checked": bool(parity)}
 
 
 class ClockSampler(threading.Thread):
@@ -121,37 +144,137 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+# ---- the CPU arm ------------------------------------------------------------------------------------------------------------------
+def clean_env():
+    return {k: v for k, v in os.environ.items() if not k.startswith("MOSDEPTH_")}
+
+
+def oracle_cmd(threads, window, outp, bam):
+    return [str(ROOT / "oracle" / "mosdepth_oracle"), "-t", str(threads), "-n", "-x", "--by", str(window), str(outp), str(bam)]
+
+
+def time_oracle(bam, window, t_list, repeats):
+    """Process wall seconds of the oracle per thread count (best of `repeats`); the first run of all warms the page cache."""
+    outp = data_dir() / f"cpu_out_{os.getpid()}"
+    subprocess.run(oracle_cmd(t_list[0], window, outp, bam), check=True, capture_output=True, env=clean_env())
+    best = {}
+    for t in t_list:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            subprocess.run(oracle_cmd(t, window, outp, bam), check=True, capture_output=True, env=clean_env())
+            dt = time.perf_counter() - t0
+            best[t] = min(best.get(t, 1e30), dt)
+    return best, outp
+
+
+def thread_choices():
+    n = os.cpu_count() or 1
+    return sorted({t for t in (0, 3, 7, 15, n - 1) if 0 <= t <= max(n - 1, 0)})
+
+
+def golden_check(tmp):
+    """The CPU arm checks itself against the reference's own known answer before it is timed (functional-tests.sh:34-41,
+    `ovl.bam --fast-mode`)."""
+    fix = ROOT / "tests" / "golden" / "fixtures" / "ovl.bam"
+    subprocess.run([str(ROOT / "oracle" / "mosdepth_oracle"), "-x", str(Path(tmp) / "g"), str(fix)], check=True, capture_output=True, env=clean_env())
+    rows = [l.split("\t") for l in (Path(tmp) / "g.per-base.bed").read_text().splitlines() if l.startswith("MT\t")]
+    return rows == [["MT", "0", "6", "1"], ["MT", "6", "42", "2"], ["MT", "42", "80", "1"], ["MT", "80", "16569", "0"]]
+
+
 def run_reference(args):
-    """CPU arm: the oracle restatement with all host threads on the same BAM."""
+    """CPU arm: the oracle restatement on a bounded sample of the workload, best thread count of {0, 3, 7, 15, nproc-1}."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     ensure_built()
     ncores = os.cpu_count() or 1
-    threads = max(0, min(ncores - 1, 64))
-    # same workload as our arm at this N (weak scaling: genome_fraction x N), bounded so that W+K steps end in minutes
-    frac = args.cpu_fraction or min(args.genome_fraction * max(args.gpus, 1), 0.06)   # N = 1: the same BAM as our arm
-    bam, n_reads, n_bytes = make_bam(args.config, frac, args.seed, ncores)
-    outp = data_dir() / "ref_out"
-    cmd = [str(ROOT / "oracle" / "mosdepth_oracle"), "-t", str(threads), "-n", "-x", "--by", "500", str(outp), str(bam)]
+    frac = min(args.cpu_fraction or SAMPLE_FRACTION, args.genome_fraction)
+    bam, n_reads, n_bytes = make_bam(args.config, frac, args.seed, ncores, keep_tags=(bam_tag(args.config, args.genome_fraction, args.seed),))
+    with tempfile.TemporaryDirectory() as tmp:
+        parity = golden_check(tmp)
+    # which -t is best on this box: one pass per candidate, best of 2 (these passes are also the warm-up)
+    best, outp = time_oracle(bam, args.window, thread_choices(), 2)
+    t_best = min(best, key=best.get)
+    cmd = oracle_cmd(t_best, args.window, outp, bam)
+    for _ in range(max(args.warmup - 2 * len(best), 0)):
+        subprocess.run(cmd, check=True, capture_output=True, env=clean_env())
     times = []
-    for i in range(args.warmup + args.steps):
+    for _ in range(args.steps):
         t0 = time.perf_counter()
-        subprocess.run(cmd, check=True, capture_output=True)
-        dt = time.perf_counter() - t0
-        if i >= args.warmup:
-            times.append(dt)
+        subprocess.run(cmd, check=True, capture_output=True, env=clean_env())
+        times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
     val = n_reads / sec
-    sample = f"{args.config} synthetic 30X WGS, genome_fraction={frac:g}, {n_reads} reads, {n_bytes} BAM bytes, whole file per step"
+    sample = (f"bounded sample of the workload: the same generator at genome_fraction={frac:g} ({n_reads} reads, {n_bytes} BAM bytes), whole file per step, "
+              f"process wall incl. writing regions.bed.gz; oracle -t {t_best} (best of -t {sorted(best)}: " + ", ".join(f"{t}: {n_reads / best[t] / 1e6:.2f} M reads/s" for t in sorted(best)) + ")")
     line = {"metric": "reads_per_s", "value": val, "unit": "reads/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"C3 synthetic 30X WGS (25 GRCh38 contigs x {frac:g}, 150-bp pairs) --by 500 -n -x", "genome_fraction": frac, "reads": n_reads, "bam_bytes": n_bytes,
-                       "flags": "--by 500 -n -x", "note": "CPU oracle restatement of mosdepth (zlib inflate threads + single record thread); the mosdepth binary cannot be built in this image"},
-            "cpu_baseline": {"value": val, "unit": "reads/s", "cores": threads + 1, "kind": "port", "sample": sample},
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": workload_config(args, max(args.gpus, 1), parity),
+            "cpu_baseline": {"value": val, "unit": "reads/s", "cores": t_best + 1, "kind": "port", "sample": sample, "best_value": n_reads / min(times), "host_cores": ncores,
+                             "note": "CPU oracle restatement of mosdepth (zlib inflate on -t worker threads + one record thread, the reference's own structure); the mosdepth binary (Nim + htslib/libdeflate) cannot be built in this image"},
             "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
+
+
+# ---- rendering the output files from the library's results (parity check; mirrors mosdepth_b200/host/main.cpp) --------------------------
+def _dist_text(chrom, d, precision=2):
+    total = int(sum(d))
+    if total < 1:
+        return ""
+    out, cum, n = [], 0.0, len(d)
+    for i in range(n):
+        irev = n - 1 - i
+        v = int(d[irev])
+        if irev > 300 and v == 0:
+            continue
+        cum += v / total
+        if cum < 8e-5:
+            continue
+        out.append(f"{chrom}\t{irev}\t{cum:.{precision}f}\n")
+    return "".join(out)
+
+
+def _summary_row(name, st):
+    length, bases, mn, mx = st
+    mean = bases / length if length > 0 else 0.0
+    return f"{name}\t{length}\t{bases}\t{mean:.2f}\t{0 if mn == 0xFFFFFFFF else mn}\t{mx}\n"
+
+
+def render_outputs(names, lengths, window, per_contig):
+    """per_contig[tid] = None (no records: coverage() returned -2) or dict(values, stat, dist, rstat, rdist).  Returns the four texts of
+    `--by <window> -n` exactly as the reference's main loop emits them (mosdepth.nim:691-813)."""
+    import numpy as np
+    regions, summary, gdist, rdist = [], ["chrom\tlength\tbases\tmean\tmin\tmax\n"], [], []
+    tot_g, tot_r = np.zeros(512, dtype=np.int64), np.zeros(512, dtype=np.int64)
+    gs, rs = [0, 0, 0xFFFFFFFF, 0], [0, 0, 0xFFFFFFFF, 0]
+    add = lambda a, b: [a[0] + b[0], a[1] + b[1], min(a[2], b[2]), max(a[3], b[3])]
+
+    def grow(a, n):
+        if n > a.size:
+            b = np.zeros(n, dtype=np.int64); b[:a.size] = a; return b
+        return a
+    for tid, (name, tlen) in enumerate(zip(names, lengths)):
+        pc = per_contig.get(tid)
+        nw = (tlen + window - 1) // window if tlen else 0
+        starts = np.arange(nw, dtype=np.int64) * window
+        stops = np.minimum(starts + window, tlen)
+        vals = pc["values"] if pc else np.zeros(nw)
+        assert len(vals) == nw, (name, len(vals), nw)
+        regions.append("".join(f"{name}\t{s}\t{e}\t{v:.2f}\n" for s, e, v in zip(starts.tolist(), stops.tolist(), vals.tolist())))
+        cg, cr = np.zeros(512, dtype=np.int64), np.zeros(512, dtype=np.int64)
+        if pc:
+            cg = grow(cg, len(pc["dist"])); cg[:len(pc["dist"])] += pc["dist"]
+            cr[:512] += pc["rdist"]
+            summary.append(_summary_row(name, pc["stat"])); summary.append(_summary_row(name + "_region", pc["rstat"]))
+            gs, rs = add(gs, pc["stat"]), add(rs, pc["rstat"])
+        gdist.append(_dist_text(name, cg)); rdist.append(_dist_text(name, cr))
+        if pc:
+            tot_g = grow(tot_g, cg.size); tot_g[:cg.size] += cg; tot_r += cr
+    summary.append(_summary_row("total", gs)); summary.append(_summary_row("total_region", rs))
+    gdist.append(_dist_text("total", tot_g)); rdist.append(_dist_text("total", tot_r))
+    return {".regions.bed": "".join(regions), ".mosdepth.summary.txt": "".join(summary), ".mosdepth.global.dist.txt": "".join(gdist),
+            ".mosdepth.region.dist.txt": "".join(rdist)}, (gs, rs, tot_g, tot_r)
 
 
 def main():
@@ -161,19 +284,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3")
-    ap.add_argument("--genome-fraction", type=float, default=float(os.environ.get("MSD_BENCH_FRACTION", "0.06")))
-    ap.add_argument("--cpu-fraction", type=float, default=0.0, help="genome fraction for the CPU arm (default: same BAM)")
+    ap.add_argument("--genome-fraction", type=float, default=float(os.environ.get("MSD_BENCH_FRACTION", "0.5")),
+                    help="scale of the 30X genome (every contig length x f).  0.5 = 1.54 Gbp, 309 M reads, 28 GB of BAM: the largest the 1-GPU box generates (16 cores, ~5 min of zlib level 6) and holds twice (page cache + pinned image) inside the bench budget; 1.0 needs ~11 min of generation and 112 GB of host memory")
+    ap.add_argument("--cpu-fraction", type=float, default=0.0, help="genome fraction of the CPU arm's bounded sample (default 0.03)")
     ap.add_argument("--seed", type=int, default=20261022)
     ap.add_argument("--window", type=int, default=500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-aux", action="store_true", help="skip the side measurement of K10 (per-base.bed.gz on the device), which runs in a process of its own after the timed region")
-    ap.add_argument("--sharding", default="offsets", choices=["contigs", "offsets", "intra"],
-                    help="N > 1: whole contigs per rank (LPT, no data-path exchange); N equal BGZF offset ranges of the file, cut inside contigs (the depth that reads leave beyond a cut goes to the next rank over NCCL); or every contig cut into N ranges")
+    ap.add_argument("--no-cli", action="store_true", help="skip the wall-clock run of the mosdepth-b200 process on the bench BAM")
+    ap.add_argument("--sharding", default="offsets", choices=["contigs", "offsets"],
+                    help="N > 1: N equal BGZF offset ranges of the file, cut inside contigs (the depth that reads leave beyond a cut goes to the next rank over NCCL), or whole contigs per rank (LPT, no data-path exchange)")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
-        args.warmup = max(args.warmup, 1)
     if args.impl == "reference":
         return run_reference(args)
+    args.warmup = max(args.warmup, 1)
 
     # stdout carries exactly ONE JSON line (rank 0): everything else that native code prints to fd 1 while we run (NCCL's
     # version banner under NCCL_DEBUG=VERSION/WARN, for one) goes to stderr
@@ -195,157 +318,163 @@ def main():
         dist.barrier()
     import mosdepth_b200 as m
     from mosdepth_b200 import hostio
-    from mosdepth_b200.shard import contig_weights, load_compact, lpt_shards, merge_adjacent_spans, offset_shards, split_contig
+    from mosdepth_b200.shard import contig_weights, load_compact, lpt_shards, merge_adjacent_spans, offset_shards
 
-    # ---- data: weak scaling = every rank count sees `fraction * world` of the genome, i.e. fixed work per GPU --------
-    fraction = args.genome_fraction * world
     ncores = os.cpu_count() or 1
-    if rank == 0:
-        bam, n_reads, n_bytes = make_bam(args.config, fraction, args.seed, ncores)
-    if world > 1:
-        dist.barrier()
-    bam, n_reads, n_bytes = make_bam(args.config, fraction, args.seed, ncores)
-    hdr = hostio.read_bam_header(bam)
-    index = hostio.read_index(bam)
-    nt = len(hdr.names)
-    weights = contig_weights(index)
-    intra = args.sharding == "intra" and world > 1
-    parts = {}      # tid -> (lo, hi) owned by this rank (intra-contig sharding)
-    if intra:
-        # every contig is cut into `world` position ranges at index windows; rank r owns range r of every contig
-        mine, sb, se = [], [], []
-        for t in range(nt):
-            if weights[t] <= 0:
-                continue
-            pr = split_contig(index[t], hdr.lengths[t], world, window=args.window)
-            if len(pr) != world:            # too short to cut (chrM): rank 0 takes it whole
-                if rank == 0:
-                    mine.append(t); sb.append(index[t].ref_beg); se.append(index[t].ref_end)
-                continue
-            lo, hi, vb, ve = pr[rank]
-            mine.append(t); parts[t] = (lo, hi); sb.append(vb); se.append(ve)
-        begs, ends = merge_adjacent_spans(sb, se)
-    elif args.sharding == "offsets" and world > 1:
-        intra = True
-        mine, sb, se = [], [], []
-        for t, lo, hi, vb, ve in offset_shards(index, hdr.lengths, world, window=args.window)[rank]:
-            mine.append(t); sb.append(vb); se.append(ve)
-            if lo > 0 or hi < hdr.lengths[t]:
-                parts[t] = (lo, hi)
-        begs, ends = merge_adjacent_spans(sb, se)
-    else:
-        shards = lpt_shards(weights, world)
-        mine = shards[rank]
-        begs, ends = merge_adjacent_spans([index[t].ref_beg for t in mine], [index[t].ref_end for t in mine])
-    want = np.zeros(nt, dtype=np.uint8); want[mine] = 1
+    t_begin = time.perf_counter()
 
-    # pinned host image of this rank's byte ranges of the BAM file (the e2e input), virtual offsets rebased onto it
-    keep = {}
-
-    def alloc(n):
-        keep["t"] = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-        return keep["t"].numpy()
-
-    _buf, begs, ends, used = load_compact(bam, begs, ends, alloc)
-    host = keep["t"]
-
-    ctx = m.Context(local)
-    ctx.open_mem(host, hdr)
-    ctx.set_targets(want)
-    ctx.set_spans(begs, ends)
-    ctx.set_filters(mode=m.MODE_FAST)   # -x; defaults -F 1796 -Q 0
-    ctx.prefetch_windows(args.window)   # --by 500: the host will ask for every contig's windows
-    for t, (lo, hi) in parts.items():
-        ctx.set_contig_range(t, lo, hi)
-    g_ptr, r_ptr, n_bins, s_ptr = ctx.totals_device()
-
-    class DevView:
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
-
-    tot_g = torch.as_tensor(DevView(g_ptr, n_bins), device=f"cuda:{local}")
-    tot_r = torch.as_tensor(DevView(r_ptr, n_bins), device=f"cuda:{local}")
-    tot_s = torch.as_tensor(DevView(s_ptr, 8), device=f"cuda:{local}")
-
-    d2h = {"bytes": 0}
-    check = {}
-
-    def exchange_spills():
-        """Sharding inside contigs: the depth that this rank's reads leave beyond the end of a range it owns goes to the rank
-        that owns the next range of that contig (always rank + 1): one NCCL send/recv pair per neighbour, straight out of /
-        into GPU memory; then every shard is finalised."""
-        dev = f"cuda:{local}"
-        out_t = [t for t in sorted(parts) if parts[t][1] < hdr.lengths[t]]     # ranges that end inside their contig
-        in_t = [t for t in sorted(parts) if parts[t][0] > 0]                   # ranges that start inside their contig
-        n_out = torch.zeros(nt, dtype=torch.int64, device=dev)
-        spill = {t: ctx.contig_spill(t) for t in out_t}
-        for t in out_t:
-            n_out[t] = spill[t][1]
-        all_n = [torch.zeros_like(n_out) for _ in range(world)]
-        dist.all_gather(all_n, n_out)
-        total_out = int(n_out.sum())
-        send_buf = torch.empty(max(total_out, 1), dtype=torch.int32, device=dev)
-        off = 0
-        for t in out_t:
-            start, n = spill[t]
-            if n:
-                ctx.depth_copy(t, start, n, device_ptr=send_buf.data_ptr() + 4 * off)
-            off += n
-        n_in = [int(all_n[rank - 1][t]) for t in in_t] if rank > 0 else []
-        recv_buf = torch.empty(max(sum(n_in), 1), dtype=torch.int32, device=dev)
-        ops = []
-        if rank + 1 < world and total_out:
-            ops.append(dist.P2POp(dist.isend, send_buf[:total_out], rank + 1))
-        if rank > 0 and sum(n_in):
-            ops.append(dist.P2POp(dist.irecv, recv_buf[:sum(n_in)], rank - 1))
-        if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
-        torch.cuda.synchronize()
-        off = 0
-        for t, n in zip(in_t, n_in):
-            if n:
-                ctx.depth_add(t, parts[t][0], device_ptr=recv_buf.data_ptr() + 4 * off, n=n)
-            off += n
-        for t in sorted(parts):
-            ctx.contig_finalize(t)
-        return 4 * total_out
-
-    def step():
-        """One pass of the hot path for this rank's contigs + the cross-rank reduction of the totals."""
-        ctx.totals_reset()
-        info = ctx.run()
-        nbytes = 0
-        if parts:
-            nbytes += exchange_spills()
-        for t in mine:
-            if t not in parts:
-                rc, _n = ctx.contig_records(t)
-                if rc < 0:
-                    continue
-            st, distv = ctx.contig_stats(t)
-            vals, rst, rdist = ctx.windows(t, args.window)
-            nbytes += vals.nbytes + rdist.nbytes + distv.nbytes + 48
+    def barrier():
         if world > 1:
-            dist.all_reduce(tot_g[:1024]); dist.all_reduce(tot_r[:512])
-            mm = torch.stack([tot_s[2], tot_s[6]]); dist.all_reduce(mm, op=dist.ReduceOp.MIN)
-            mx = torch.stack([tot_s[3], tot_s[7]]); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            sums = torch.stack([tot_s[0], tot_s[1], tot_s[4], tot_s[5]]); dist.all_reduce(sums)
-            check["totals"] = [int(tot_g[:1024].sum()), int((tot_g[:1024] * torch.arange(1024, device=tot_g.device)).sum()), int(tot_r[:512].sum()), int(sums[0]), int(sums[1]), int(mm[0]), int(mx[0])]
-        else:
-            check["totals"] = [int(tot_g[:1024].sum()), int((tot_g[:1024] * torch.arange(1024, device=tot_g.device)).sum()), int(tot_r[:512].sum()), int(tot_s[0]), int(tot_s[1]), int(tot_s[2]), int(tot_s[3])]
-        d2h["bytes"] = nbytes
-        return info
+            dist.barrier()
+
+    def get_bam(fraction, keep=()):
+        if rank == 0:
+            make_bam(args.config, fraction, args.seed, ncores, keep_tags=keep)
+        barrier()
+        return make_bam(args.config, fraction, args.seed, ncores, keep_tags=keep)
+
+    # the library's own communicator: one NCCL id from rank 0 (torch.distributed is only the messenger)
+    comm_id = None
+    if world > 1:
+        box = [m.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm_id = box[0]
+
+    class Job:
+        """One BAM through this rank's context: the shard plan, the pinned host image of this rank's bytes, and the step."""
+
+        def __init__(self, bam, pin=True):
+            self.bam = bam
+            self.hdr = hostio.read_bam_header(bam)
+            index = hostio.read_index(bam)
+            self.nt = len(self.hdr.names)
+            L = self.hdr.lengths
+            if world > 1 and args.sharding == "offsets":
+                plan = offset_shards(index, L, world, window=args.window, with_cover=True)
+            else:
+                plan = [[(t, 0, L[t], index[t].ref_beg, index[t].ref_end, 0) for t in r] for r in lpt_shards(contig_weights(index), world)]
+            self.plan = plan
+            self.pieces = plan[rank]
+            self.cut = [(t, lo, hi, cover) for t, lo, hi, _vb, _ve, cover in self.pieces if lo > 0 or hi < L[t]]
+            self.any_cut = any(lo > 0 or hi < L[t] for r in plan for t, lo, hi, *_ in r)
+            begs, ends = merge_adjacent_spans([p[3] for p in self.pieces], [p[4] for p in self.pieces]) if self.pieces else ([1 << 16], [1 << 16])
+            keep = {}
+
+            def alloc(n):
+                keep["t"] = torch.empty(n, dtype=torch.uint8, pin_memory=pin)
+                return keep["t"].numpy()
+            if self.pieces:
+                _buf, self.begs, self.ends, self.used = load_compact(bam, begs, ends, alloc)
+            else:   # nothing for this rank: an empty image with one span that reads nothing
+                alloc(1 << 16); self.begs, self.ends, self.used = [1 << 16], [1 << 16], 0
+            self.host = keep["t"]
+            want = np.zeros(self.nt, dtype=np.uint8)
+            for p in self.pieces:
+                want[p[0]] = 1
+            self.ctx = ctx = m.Context(local)
+            ctx.open_mem(self.host, self.hdr)
+            ctx.set_targets(want)
+            ctx.set_spans(self.begs, self.ends)
+            ctx.set_filters(mode=m.MODE_FAST)       # -x; defaults -F 1796 -Q 0
+            ctx.prefetch_windows(args.window)       # --by 500: the host will ask for every contig's windows
+            for t, lo, hi, cover in self.cut:
+                ctx.set_contig_range(t, lo, hi); ctx.set_contig_cover(t, cover)
+            if world > 1:
+                ctx.comm_init(rank, world, comm_id)
+            self.d2h = 0
+            self.results = None
+
+        def step(self, keep_results=False):
+            """One pass of the hot path for this rank's pieces + the two exchanges."""
+            ctx = self.ctx
+            ctx.totals_reset()
+            info = ctx.run()
+            if self.any_cut:
+                ctx.exchange_spills()
+            nbytes, res = 0, []
+            for t, lo, hi, *_ in self.pieces:
+                is_cut = lo > 0 or hi < self.hdr.lengths[t]
+                rc, n = ctx.contig_records(t)
+                if rc < 0 and not is_cut:
+                    continue
+                st, distv = ctx.contig_stats(t)
+                vals, rst, rdist = ctx.windows(t, args.window)
+                nbytes += vals.nbytes + rdist.nbytes + distv.nbytes + 48
+                if keep_results:
+                    res.append((t, lo, max(n, 0), (st.cum_length, st.cum_depth, st.min_depth, st.max_depth), distv.copy(), vals.copy(),
+                                (rst.cum_length, rst.cum_depth, rst.min_depth, rst.max_depth), rdist.copy()))
+            if world > 1:
+                ctx.totals_allreduce()
+            g, r, gd, rd = ctx.totals()
+            nbytes += gd.nbytes + rd.nbytes + 64
+            self.d2h = nbytes
+            if keep_results:
+                self.results = (res, ((g.cum_length, g.cum_depth, g.min_depth, g.max_depth), (r.cum_length, r.cum_depth, r.min_depth, r.max_depth), gd.copy(), rd.copy()))
+            return info
+
+        def close(self):
+            self.ctx.close()
+
+    # ---- parity first: a small BAM of the same shape through the same path, every output file against the oracle ------------------
+    keep_main = (bam_tag(args.config, args.genome_fraction, args.seed), bam_tag(args.config, SAMPLE_FRACTION, args.seed))
+    pbam, p_reads, _ = get_bam(PARITY_FRACTION, keep_main)
+    pj = Job(pbam, pin=True)
+    pj.ctx.stage()
+    pj.step(keep_results=True)
+    gathered = [None] * world
+    if world > 1:
+        dist.all_gather_object(gathered, pj.results)
+    else:
+        gathered = [pj.results]
+    parity, parity_note = False, ""
+    if rank == 0:
+        per = {}
+        for res, _tot in gathered:          # ranks are in genome order: the shards of a contig arrive in position order
+            for t, lo, nrec, st, dv, vals, rst, rdv in res:
+                e = per.setdefault(t, {"n": 0, "values": [], "stat": [0, 0, 0xFFFFFFFF, 0], "rstat": [0, 0, 0xFFFFFFFF, 0], "dist": np.zeros(1, dtype=np.int64), "rdist": np.zeros(512, dtype=np.int64), "at": 0})
+                assert lo == e["at"] * args.window, "shards of a contig do not meet at a window boundary"
+                e["n"] += nrec; e["values"].append(vals); e["at"] += len(vals)
+                e["stat"] = [e["stat"][0] + st[0], e["stat"][1] + st[1], min(e["stat"][2], st[2]), max(e["stat"][3], st[3])]
+                e["rstat"] = [e["rstat"][0] + rst[0], e["rstat"][1] + rst[1], min(e["rstat"][2], rst[2]), max(e["rstat"][3], rst[3])]
+                d = np.zeros(max(e["dist"].size, dv.size), dtype=np.int64); d[:e["dist"].size] += e["dist"]; d[:dv.size] += dv; e["dist"] = d
+                e["rdist"] += rdv
+        per = {t: dict(e, values=np.concatenate(e["values"])) if e["n"] > 0 else None for t, e in per.items()}
+        texts, (gs, rs, tot_g, tot_r) = render_outputs(pj.hdr.names, pj.hdr.lengths, args.window, per)
+        with tempfile.TemporaryDirectory() as tmp:
+            subprocess.run(oracle_cmd(min(ncores - 1, 7), args.window, Path(tmp) / "o", pbam), check=True, capture_output=True, env=clean_env())
+            bad = [s for s, txt in texts.items() if (Path(tmp) / ("o" + s)).read_text() != txt]
+            # the same BAM through the mosdepth-b200 process (N GPUs: host threads + the library's NCCL exchange): files against the oracle's
+            cli_bad = []
+            if world == 1:
+                subprocess.run([str(ROOT / "mosdepth_b200" / "bin" / "mosdepth-b200"), "--plain", "--device", str(local), "-n", "-x", "--by", str(args.window), str(Path(tmp) / "g"), str(pbam)],
+                               check=True, capture_output=True, env=clean_env())
+                cli_bad = [s for s in texts if (Path(tmp) / ("o" + s)).read_bytes() != (Path(tmp) / ("g" + s)).read_bytes()]
+        # the all-reduced `total` rows every rank holds must be the sums of the per-contig results
+        _, (tg, tr, tgd, trd) = gathered[0]
+        tot_ok = list(tg) == gs and list(tr) == rs and np.array_equal(np.trim_zeros(tgd, "b"), np.trim_zeros(tot_g, "b")) and np.array_equal(np.trim_zeros(trd, "b"), np.trim_zeros(tot_r, "b"))
+        parity = not bad and not cli_bad and tot_ok
+        parity_note = (f"{p_reads} reads (genome_fraction {PARITY_FRACTION:g}) through the same {world}-rank path: regions.bed, summary, global.dist, region.dist byte-identical to the oracle"
+                       if parity else f"PARITY FAILED: files {bad} cli {cli_bad} totals_ok {tot_ok}")
+        if not parity:
+            print("[bench] " + parity_note, file=sys.stderr)
+    pj.close(); del pj
+    barrier()
+
+    # ---- the workload ---------------------------------------------------------------------------------------------------------------
+    bam, n_reads, n_bytes = get_bam(args.genome_fraction, keep_main)
+    t_load = time.perf_counter()
+    job = Job(bam)
+    t_loaded = time.perf_counter()
+    ctx = job.ctx
 
     def timed(resident):
         if resident:
             ctx.stage()
         else:
-            ctx.set_spans(begs, ends)   # drops the staged copy
+            ctx.set_spans(job.begs, job.ends)   # drops the staged copy
         for _ in range(args.warmup):
-            step()
-        if world > 1:
-            dist.barrier()
+            job.step()
+        barrier()
         torch.cuda.synchronize()
         sampler = ClockSampler(local); sampler.start()
         infos = []
@@ -353,13 +482,12 @@ def main():
         t0 = time.perf_counter()
         ctx.mark(0)
         for _ in range(args.steps):
-            infos.append(step())
+            infos.append(job.step())
         ctx.mark(1)
         torch.cuda.synchronize()
         ms_dev = ctx.elapsed_ms(0, 1)
         wall = time.perf_counter() - t0
-        if world > 1:
-            dist.barrier()
+        barrier()
         sampler.stop_flag.set(); sampler.join()
         # the step makes blocking host calls (results come back per contig), so the device-side span between
         # the two marks is the honest step time; the host wall clock is reported beside it
@@ -368,12 +496,14 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return tt[0].item() / args.steps, tt[1].item() / args.steps, infos, ctx.launch_count() - lc0, sampler.summary()
 
-    total_reads = n_reads
     ms_res, wall_res, infos_res, launches, clocks = timed(True)
-    ms_e2e, wall_e2e, infos_e2e, _, clocks2 = timed(False)
+    ms_e2e, wall_e2e, infos_e2e, _, _clocks2 = timed(False)
     info = infos_res[-1]
-    value = total_reads / (ms_res / 1e3)
-    e2e_val = total_reads / (ms_e2e / 1e3)
+    value = n_reads / (ms_res / 1e3)
+    e2e_val = n_reads / (ms_e2e / 1e3)
+    h2d = torch.tensor([float(infos_e2e[-1].bytes_compressed), float(job.d2h)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(h2d)
 
     # roofline of the dominant kernel pair K1 = huffman_decode_kernel + lz77_resolve_kernel (BGZF inflate, > 80 % of the
     # step): algorithmic bytes per launch = compressed bytes of the chunk, read once
@@ -383,22 +513,26 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    inf_ms = sum(i.ms_inflate_span for i in infos_res) / len(infos_res)   # launches of consecutive chunks overlap: use the span
+    avg = lambda f: sum(f(i) for i in infos_res) / len(infos_res)
+    inf_ms = avg(lambda i: i.ms_inflate_span)      # launches of consecutive chunks overlap: use the span
     inf_launches = info.n_inflate_launches
-    alg_bytes_per_launch = info.bytes_compressed / max(inf_launches, 1)
     achieved = (info.bytes_compressed / 1e9) / (inf_ms / 1e3) if inf_ms > 0 else 0.0
-    # DRAM bytes per BGZF block from the ncu --set full capture profiles/r1j_inflate_full_summary.txt (85,062 blocks:
-    # decode 5.30 GB read + 5.87 GB written, resolve 16.78 GB read + 5.45 GB written), scaled to this run's blocks per launch
-    traffic_per_block = (5.298858e9 + 5.873518e9 + 16.775090e9 + 5.448415e9) / 85062.0
+    # DRAM bytes per BGZF block from the ncu --set full capture of the shipped kernels (profiles/r2a_fast_full_summary.txt, 85,062 blocks in one launch each:
+    # decode 5.32 GB read + 5.91 GB written, resolve 16.78 GB read + 5.45 GB written), scaled to this run's blocks per launch
+    traffic_per_block = (5.321760e9 + 5.912786e9 + 16.776851e9 + 5.449551e9) / 85062.0
+    scan_ms = avg(lambda i: i.ms_scan)
+    scan_bytes = 8.0 * info.n_depth_cells
     roofline = {"kernel": "huffman_decode_kernel + lz77_resolve_kernel (K1, BGZF inflate)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic_per_block * info.n_blocks / max(inf_launches, 1),
-                "traffic_source": "ncu --set full, profiles/r1j_inflate_full_summary.txt, per block x blocks per launch",
+                "traffic_source": "ncu --set full, profiles/r2a_fast_full_summary.txt, DRAM bytes per block x blocks per launch",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launches_per_step": inf_launches, "ms_per_launch": inf_ms / max(inf_launches, 1),
+                "algorithmic_bytes_per_launch": info.bytes_compressed / max(inf_launches, 1), "launches_per_step": inf_launches, "ms_per_launch": inf_ms / max(inf_launches, 1),
                 "inflated_gbs": (info.bytes_inflated / 1e9) / (inf_ms / 1e3) if inf_ms > 0 else 0.0,
-                "stage_ms_per_step": {"inflate_span": inf_ms, "inflate_sum": sum(i.ms_inflate for i in infos_res) / len(infos_res), "frame": sum(i.ms_frame for i in infos_res) / len(infos_res),
-                                      "records": sum(i.ms_records for i in infos_res) / len(infos_res), "scan": sum(i.ms_scan for i in infos_res) / len(infos_res),
-                                      "zero": sum(i.ms_zero for i in infos_res) / len(infos_res), "run_total": sum(i.ms_total for i in infos_res) / len(infos_res)},
+                "inflate_span_ms": inf_ms, "inflate_sum_ms": avg(lambda i: i.ms_inflate), "frame_ms": avg(lambda i: i.ms_frame), "records_ms": avg(lambda i: i.ms_records),
+                "scan_ms": scan_ms, "zero_ms": avg(lambda i: i.ms_zero), "run_total_ms": avg(lambda i: i.ms_total),
+                # K6 (one segmented launch: prefix sum + stats + dist of every contig), live: 4 B read + 4 B written per depth cell
+                "k6_scan_gbs": scan_bytes / 1e9 / (scan_ms / 1e3) if scan_ms > 0 else 0.0, "k6_scan_frac": (scan_bytes / 1e9 / (scan_ms / 1e3) / peak) if scan_ms > 0 else 0.0,
+                "k6_scan_bytes": scan_bytes,
                 "note": "inflate is bound by the serial Huffman chains (latency / issue), not by HBM; compressed GB/s and inflated GB/s are quoted against the HBM peak as north_star asks"}
 
     # K1c alone, timed live: the one kernel of K1 that is HBM bound (it reads the inflated bytes once: algorithmic bytes = U)
@@ -408,49 +542,78 @@ def main():
         blk = 65280
         sample = np.random.default_rng(1).integers(0, 256, size=blk * 16384, dtype=np.uint8)      # 1.07 GB: far larger than L2
         _crcs, crc_ms = ctx.debug_crc32(sample, blk, 0, reps=10)
-        roofline["k1c_crc"] = {"kernel": "bgzf_crc_kernel (K1c), timed alone over %d blocks of %d bytes" % (sample.size // blk, blk), "bound": "hbm",
-                               "achieved": sample.size / 1e9 / (crc_ms / 1e3), "peak": peak, "unit": "GB/s", "frac": sample.size / 1e9 / (crc_ms / 1e3) / peak,
-                               "ms_per_launch": crc_ms, "algorithmic_bytes_per_launch": int(sample.size),
-                               "traffic": 5.504065e9 / 85062 * (sample.size // blk), "traffic_source": "ncu --set full, profiles/r1m_crc_full_summary.txt, per block x blocks"}
+        roofline["k1c_crc_gbs"] = sample.size / 1e9 / (crc_ms / 1e3)
+        roofline["k1c_crc_frac"] = roofline["k1c_crc_gbs"] / peak
+        roofline["k1c_crc_ms_per_launch"] = crc_ms
         del sample
     except Exception as e:      # never let the side measurement take the bench line down
-        roofline["k1c_crc"] = {"error": str(e)}
+        roofline["k1c_crc_error"] = str(e)
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = max(0, min(ncores - 1, 64))
-        outp = data_dir() / "cpu_out"
-        cmd = [str(ROOT / "oracle" / "mosdepth_oracle"), "-t", str(threads), "-n", "-x", "--by", str(args.window), str(outp), str(bam)]
-        subprocess.run(cmd, check=True, capture_output=True)   # warm page cache
-        t0 = time.perf_counter(); subprocess.run(cmd, check=True, capture_output=True); dt = time.perf_counter() - t0
-        cpu_baseline = {"value": n_reads / dt, "unit": "reads/s", "cores": threads + 1, "kind": "port", "seconds": dt,
-                        "sample": f"whole bench BAM ({n_reads} reads, genome_fraction={fraction:g}), oracle -t {threads} --by {args.window} -n -x"}
+    job.close()
+    del job
+    barrier()
 
-    # side measurement, outside every timed region and in a process of its own (a failure there cannot touch this line):
-    # K10 (msd_per_base_bgzf) against msd_per_base_runs + zlib on a small default-mode BAM, members verified against the runs
-    aux = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_aux:
-        try:
-            r = subprocess.run([sys.executable, str(ROOT / "tools" / "bench_bedgz.py"), "0.004", "2", "--json"], capture_output=True, text=True, timeout=150)
-            aux = {"k10_per_base_bgzf": json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 and r.stdout.strip() else {"error": (r.stderr or r.stdout)[-600:]}}
-        except Exception as e:
-            aux = {"k10_per_base_bgzf": {"error": str(e)}}
+    cpu_baseline, cli = None, {}
+    if rank == 0:
+        env = dict(clean_env(), MOSDEPTH_B200_STATS="1")
+        exe = str(ROOT / "mosdepth_b200" / "bin" / "mosdepth-b200")
+        outp = data_dir() / f"cli_out_{os.getpid()}"
+
+        def cli_wall(path, reps=2):
+            best, stats = 1e30, None
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                r = subprocess.run([exe, "--gpus", str(world), "-n", "-x", "--by", str(args.window), str(outp), str(path)], capture_output=True, text=True, env=env)
+                dt = time.perf_counter() - t0
+                if r.returncode != 0:
+                    return None, r.stderr[-400:]
+                if dt < best:
+                    best = dt
+                    for l in r.stderr.splitlines():
+                        if l.startswith("[mosdepth-b200] {"):
+                            stats = json.loads(l[len("[mosdepth-b200] "):])
+            return best, stats
+        if not args.no_cli:
+            try:
+                w, st = cli_wall(bam)
+                cli = {"cli_wall_s": w, "cli_reads_per_s": (n_reads / w) if w else None, "cli_stages": st}
+            except Exception as e:
+                cli = {"cli_error": str(e)}
+        if world == 1 and not args.no_cpu_baseline:
+            frac = min(args.cpu_fraction or SAMPLE_FRACTION, args.genome_fraction)
+            sbam, s_reads, s_bytes = make_bam(args.config, frac, args.seed, ncores, keep_tags=keep_main)
+            t_list = [t for t in thread_choices() if t >= 3] or thread_choices()
+            best, _o = time_oracle(sbam, args.window, t_list, 2)
+            t_best = min(best, key=best.get)
+            cpu_baseline = {"value": s_reads / best[t_best], "unit": "reads/s", "cores": t_best + 1, "kind": "port", "seconds": best[t_best], "host_cores": ncores,
+                            "sample": f"bounded sample: the same generator at genome_fraction={frac:g} ({s_reads} reads, {s_bytes} BAM bytes), whole file, oracle process wall, best of -t {sorted(best)} x 2 runs: "
+                                      + ", ".join(f"-t {t}: {s_reads / best[t] / 1e6:.2f} M reads/s" for t in sorted(best))}
+            if not args.no_cli:
+                try:
+                    w, _st = cli_wall(sbam)
+                    cpu_baseline["gpu_cli_wall_s_same_sample"] = w      # the mosdepth-b200 process on the very file the oracle was timed on
+                    cpu_baseline["gpu_cli_reads_per_s_same_sample"] = (s_reads / w) if w else None
+                except Exception:
+                    pass
+        for f in data_dir().glob(f"cli_out_{os.getpid()}*"):
+            f.unlink()
+        for f in data_dir().glob(f"cpu_out_{os.getpid()}*"):
+            f.unlink()
 
     if rank == 0:
+        cfg = workload_config(args, world, parity)
         line = {"metric": "reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                "config": {"workload": f"C3 synthetic 30X WGS (25 GRCh38 contigs x {fraction:g}, 150-bp pairs) --by {args.window} -n -x", "genome_fraction": fraction,
-                           "reads": n_reads, "bam_bytes": n_bytes, "flags": f"--by {args.window} -n -x", "sharding": (f"{world} equal BGZF offset ranges cut inside contigs, depth spill to the next rank over NCCL send/recv" if (args.sharding == "offsets" and world > 1) else f"every contig cut into {world} position ranges, depth spill over NCCL send/recv" if intra else f"contigs LPT over {world} GPU(s)"),
-                           "totals_check": check.get("totals"),
-                           "l2": "inputs (compressed BAM, depth arrays) are far larger than the 126 MB L2; no flush needed",
-                           "wall_s_per_step": wall_res / 1e3, "extrapolated_full_genome_wall_s": (ms_res / 1e3) / fraction * world},
-                "e2e": {"value": e2e_val, "unit": "reads/s", "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e,
-                        "h2d_bytes_per_step": int(infos_e2e[-1].bytes_compressed), "d2h_bytes_per_step": int(d2h["bytes"]),
-                        "stage_ms_per_step": {"h2d": infos_e2e[-1].ms_h2d, "inflate": infos_e2e[-1].ms_inflate, "frame": infos_e2e[-1].ms_frame,
-                                              "records": infos_e2e[-1].ms_records, "scan": infos_e2e[-1].ms_scan, "run_total": infos_e2e[-1].ms_total}},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "aux": aux}
+                "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": cfg,
+                "e2e": dict({"value": e2e_val, "unit": "reads/s", "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e,
+                             "h2d_bytes_per_step": int(h2d[0].item()), "d2h_bytes_per_step": int(h2d[1].item()),
+                             "h2d_ms": infos_e2e[-1].ms_h2d, "inflate_ms": infos_e2e[-1].ms_inflate, "run_total_ms": infos_e2e[-1].ms_total},
+                            **{k: v for k, v in cli.items() if not isinstance(v, dict)}),
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "detail": {"reads": n_reads, "bam_bytes": n_bytes, "parity": parity_note, "wall_s_per_step": wall_res / 1e3, "genome_wall_s_at_f1": (ms_res / 1e3) / args.genome_fraction,
+                           "sharding": ("one GPU" if world == 1 else f"{world} equal BGZF offset ranges cut inside contigs; depth spill to the next rank and `total` rows over NCCL inside the library (msd_exchange_spills, msd_totals_allreduce)" if args.sharding == "offsets" else f"whole contigs, LPT over {world} GPUs"),
+                           "load_pin_s": t_loaded - t_load, "setup_s": t_load - t_begin, "cli_stages": cli.get("cli_stages")}}
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

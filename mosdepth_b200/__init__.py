@@ -113,6 +113,16 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def comm_unique_id() -> bytes:
+    """The 128-byte NCCL id rank 0 hands to every rank's Context.comm_init (msd_comm_unique_id)."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.msd_comm_unique_id(buf)
+    if rc < 0:
+        raise MsdError(rc, lib.msd_last_error(None).decode())
+    return buf.raw
+
+
 class Context:
     """One msd_ctx on one GPU. Mirrors the call order of the reference's main loop (mosdepth.nim:589-840)."""
 
@@ -223,11 +233,7 @@ class Context:
 
     # ---- the collectives of the path (NCCL; one context per rank) ----
     def comm_unique_id(self):
-        buf = C.create_string_buffer(128)
-        rc = self.lib.msd_comm_unique_id(buf)
-        if rc < 0:
-            raise MsdError(rc, self.lib.msd_last_error(None).decode())
-        return buf.raw
+        return comm_unique_id()
 
     def comm_init(self, rank, world, unique_id: bytes):
         self._check(self.lib.msd_comm_init(self.h, int(rank), int(world), C.c_char_p(unique_id)))

@@ -40,18 +40,19 @@ def merge_adjacent_spans(begs, ends, max_gap_bytes=1 << 20):
     return [o[0] for o in out], [o[1] for o in out]
 
 
-def split_contig(ci, tlen, n_parts, window=0, margin_bp=65536, beyond_windows=8):
+def split_contig(ci, tlen, n_parts, window=0, margin_bp=65536, beyond_windows=8, with_cover=False):
     """Intra-contig sharding: cut one contig into n_parts position ranges of roughly equal
     compressed size near BAI linear-index entries (16,384-bp windows), cut positions being multiples of
     lcm(32, window) so that no --by window straddles a cut.  Returns a list of (lo, hi, voff_beg, voff_end):
     part i owns the records with lo <= pos < hi; its span starts `margin_bp` before lo (default mode: an owned record may
     have to take its mate from there) and ends `beyond_windows` index windows after hi, so that it holds every owned
     record and at least one record at or beyond hi (the library checks that).  Fewer parts come back when the contig
-    has too few possible cut positions."""
+    has too few possible cut positions.  with_cover: a fifth element, the position from which on the span is known to hold every
+    record (msd_set_contig_cover: default mode checks the mates it could not find against it)."""
     import math
     lin = list(ci.linear)
     if n_parts <= 1 or not ci.has_data or len(lin) < 2:
-        return [(0, tlen, ci.ref_beg, ci.ref_end)]
+        return [(0, tlen, ci.ref_beg, ci.ref_end, 0) if with_cover else (0, tlen, ci.ref_beg, ci.ref_end)]
     align = 32 if not window else 32 * window // math.gcd(32, window)   # scans are 128-bit aligned; no window straddles a cut
 
     def voff_at_window(w):
@@ -74,9 +75,11 @@ def split_contig(ci, tlen, n_parts, window=0, margin_bp=65536, beyond_windows=8)
     parts = []
     for i in range(len(bounds) - 1):
         lo, hi = bounds[i], bounds[i + 1]
-        vb = ci.ref_beg if lo == 0 else voff_at_window(max(0, (lo - margin_bp) // 16384))
+        w0 = max(0, (lo - margin_bp) // 16384)
+        vb = ci.ref_beg if lo == 0 else voff_at_window(w0)
+        cover = w0 * 16384 if (lo > 0 and 0 < w0 < len(lin) and lin[w0]) else 0
         ve = ci.ref_end if hi >= tlen else voff_at_window(hi // 16384 + beyond_windows)
-        parts.append((lo, hi, vb, ve))
+        parts.append((lo, hi, vb, ve, cover) if with_cover else (lo, hi, vb, ve))
     return parts
 
 

@@ -177,3 +177,36 @@ def test_truncated_or_corrupt_header_and_index_end_with_a_message(mock_cli, fixt
             t.write_bytes(bytes(b))
             r = run_tool(mock_cli, ["--plain", "-n", "--by", "100000", "x", t], tmp_path, check=False)
             assert r.returncode in (0, 1, 2), (name, k, r.returncode, r.stderr[-300:])
+
+
+def test_bench_renders_the_reference_files_from_library_results(oracle_bin, mock_cli, tmp_path):
+    """bench.py's parity gate renders regions.bed / summary / global.dist / region.dist from what the library returns per contig
+    (bench.render_outputs) and compares them with the oracle's files.  Here the renderer itself is pinned on the CPU: the results come
+    from the ABI test double (= the oracle's arithmetic), so any difference is the renderer's."""
+    bam = tmp_path / "c3.bam"
+    subprocess.run([str(ROOT / "tools" / "gen_bam"), "--config", "c3", "--genome-fraction", "0.0006", "--threads", "4", "-o", str(bam)], check=True, capture_output=True)
+    run_tool(oracle_bin, ["-n", "-x", "--by", "500", "o", bam], tmp_path)
+    lib = mock_cli.parent / "libmosdepth_b200.so"
+    code = f"""
+import sys; sys.path.insert(0, {str(ROOT)!r})
+from pathlib import Path
+import numpy as np
+import mosdepth_b200 as m
+m.LIB_PATH = Path({str(lib)!r}); m._lib = None
+import bench
+ctx = m.Context(0); hdr = ctx.open({str(bam)!r}); ctx.set_filters(mode=m.MODE_FAST); ctx.run()
+per = {{}}
+for t in range(len(hdr.names)):
+    rc, n = ctx.contig_records(t)
+    if rc < 0:
+        continue
+    st, d = ctx.contig_stats(t); v, rst, rd = ctx.windows(t, 500)
+    per[t] = dict(values=v, stat=[st.cum_length, st.cum_depth, st.min_depth, st.max_depth], dist=d, rstat=[rst.cum_length, rst.cum_depth, rst.min_depth, rst.max_depth], rdist=rd)
+texts, _tot = bench.render_outputs(hdr.names, hdr.lengths, 500, per)
+for suf, txt in texts.items():
+    want = (Path({str(tmp_path)!r}) / ("o" + suf)).read_text()
+    assert txt == want, suf
+print("ok", len(per))
+"""
+    r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stderr[-3000:]
