@@ -117,6 +117,7 @@ struct msd_ctx {
     // multi-GPU (comm.cuh): one communicator per context; fixed-size spill messages to / from the neighbouring ranks
     ncclComm_t comm = nullptr; int comm_rank = 0, comm_world = 1;
     uint32_t *d_spill_send = nullptr, *d_spill_recv = nullptr, *h_spill_hdr = nullptr, *d_comm_err = nullptr; uint32_t spill_words = 0; long long* d_stats_pack = nullptr;
+    IngestPump* pump = nullptr;   // pageable input: pinned-ring copy thread (ingest.hpp), created by the first msd_run that needs it
     msd_run_info info{};
     uint64_t launches = 0; cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
@@ -147,6 +148,7 @@ cudaEvent_t next_event(msd_ctx* ctx) {
 uint64_t env_u64(const char* name, uint64_t dflt) { const char* v = getenv(name); return (v && *v) ? strtoull(v, nullptr, 10) : dflt; }
 
 void release_input(msd_ctx* ctx) {
+    if (ctx->pump) { delete ctx->pump; ctx->pump = nullptr; }
     if (ctx->mapped && ctx->bytes) munmap((void*)ctx->bytes, ctx->n_bytes);
     ctx->bytes = nullptr; ctx->n_bytes = 0; ctx->mapped = false; ctx->src_pinned = false;
     dev_free(&ctx->d_staged); ctx->staged_beg = ctx->staged_end = 0;
@@ -250,12 +252,6 @@ int ensure_chunk_buffers(msd_ctx* ctx) {
     if ((rc = dev_alloc(ctx, &ctx->d_inflate_err, 4))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_cs, 1))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_rc, 1))) return rc;
-    return 0;
-}
-
-int ensure_bounce(msd_ctx* ctx) {
-    if (ctx->src_pinned || ctx->stage[0].h_bounce) return 0;
-    for (int k = 0; k < ctx->n_slots; k++) MSD_CUDA_OK(cudaMallocHost((void**)&ctx->stage[k].h_bounce, ctx->comp_cap + 256));
     return 0;
 }
 
@@ -795,7 +791,6 @@ int msd_run(msd_ctx* ctx) {
     std::vector<Span> spans = ctx->spans;
     if (spans.empty()) spans.push_back({ctx->first_voff, 0});
     std::sort(spans.begin(), spans.end(), [](const Span& a, const Span& b) { return a.beg < b.beg; });
-    uint64_t chunk_idx = 0;
     // when the bytes still cross PCIe: a small first chunk (the pipeline starts after ~2 ms of copy), then chunks of
     // MSD_COPY_BLOCKS so that the serial tail behind the last byte is one modest chunk
     const uint32_t ramp0 = (uint32_t)env_u64("MSD_RAMP0_BLOCKS", 6000), copy_blocks = (uint32_t)env_u64("MSD_COPY_BLOCKS", 16000);
@@ -803,48 +798,84 @@ int msd_run(msd_ctx* ctx) {
     const uint8_t* F = ctx->bytes; const uint64_t N = ctx->n_bytes;
     const int ingest_threads = ingest_threads_default();
 
-    for (const Span& sp : spans) {
-        if (sp.beg == ~0ull) continue;
-        uint64_t pos = sp.beg >> 16;
-        const uint32_t first_uoff = (uint32_t)(sp.beg & 0xffff);
-        const uint64_t end_c = sp.end ? (sp.end >> 16) : N; const uint32_t end_u = sp.end ? (uint32_t)(sp.end & 0xffff) : 0;
-        bool first_of_span = true, span_done = false;
-        while (!span_done) {
-            // ---- plan one chunk (host: BSIZE chase) -------------------------------------------------------
+    // ---- plan: every BGZF block of every span (all host threads chase BSIZE at once, ingest.hpp), cut into chunks ----------------------
+    struct Plan { uint32_t b0, b1; uint64_t src, comp_bytes, infl; uint32_t nb, total, first_uoff; bool first_of_span, will_copy; };
+    std::vector<BlockInfo> blocks; std::vector<Plan> plans;
+    {
+        std::vector<BlockInfo> sb;
+        for (const Span& sp : spans) {
+            if (sp.beg == ~0ull) continue;
+            const uint64_t beg_c = sp.beg >> 16, end_c = sp.end ? (sp.end >> 16) : N; const uint32_t end_u = sp.end ? (uint32_t)(sp.end & 0xffff) : 0;
+            // blocks that start in [beg_c, stop): the block at end_c itself belongs to the span when the span ends inside it
+            const uint64_t stop = (sp.end && end_u) ? std::min<uint64_t>(end_c + 1, N) : end_c;
+            uint64_t bad = 0;
+            if (!chase_blocks(F, N, beg_c, stop, 2 * ingest_threads, sb, &bad)) return ctx_fail(ctx, MSD_EIO, "invalid BGZF block header at file offset %llu", (unsigned long long)bad);
+            size_t i = 0; bool first = true;
+            while (i < sb.size()) {
+                Plan P{}; P.b0 = (uint32_t)(blocks.size() + i); P.src = sb[i].coff; P.first_of_span = first; P.first_uoff = first ? (uint32_t)(sp.beg & 0xffff) : 0u;
+                P.will_copy = !(ctx->d_staged && P.src >= ctx->staged_beg && P.src < ctx->staged_end);
+                const uint64_t ci = plans.size();
+                const uint32_t blk_limit = !P.will_copy ? ctx->max_blocks : std::min<uint32_t>(ctx->max_blocks, ci == 0 ? ramp0 : ramp_double ? std::min<uint32_t>(copy_blocks, ramp0 << std::min<uint64_t>(ci, 8)) : copy_blocks);   // (a small first chunk for resident input was tried: 5 chunks on 4 slots, 43.3 vs 39.2 ms)
+                bool truncated_last = false;
+                while (i < sb.size() && P.nb < blk_limit) {
+                    const BlockInfo& B = sb[i];
+                    if (B.isize > 65536) return ctx_fail(ctx, MSD_EIO, "BGZF block at %llu claims %u inflated bytes", (unsigned long long)B.coff, B.isize);
+                    if (P.comp_bytes + B.blen > ctx->comp_cap || P.infl + B.isize > ctx->infl_cap) { if (P.nb == 0 && P.comp_bytes == 0) return ctx_fail(ctx, MSD_ENOMEM, "chunk buffers too small for one BGZF block"); break; }
+                    if (B.isize > 0) P.nb++;
+                    P.comp_bytes += B.blen; i++;
+                    if (sp.end && B.coff == end_c) { P.total = (uint32_t)P.infl + std::min(end_u, B.isize); truncated_last = true; P.infl += B.isize; break; }   // the span ends inside this block
+                    P.infl += B.isize;
+                }
+                if (!truncated_last) P.total = (uint32_t)P.infl;
+                P.b1 = (uint32_t)(blocks.size() + i);
+                if (first && P.nb) { size_t j = P.b0 - blocks.size(); while (sb[j].isize == 0) j++; if (P.first_uoff > sb[j].isize) return ctx_fail(ctx, MSD_EINVAL, "span start offset %u beyond its block", P.first_uoff); }
+                if (P.nb) { plans.push_back(P); first = false; }
+                if (truncated_last) break;
+            }
+            blocks.insert(blocks.end(), sb.begin(), sb.end());
+        }
+    }
+    // pageable input: the bytes cross a ring of small pinned pieces on a thread of their own (IngestPump), up to n_slots - 1 chunks ahead
+    bool any_copy = false; for (const Plan& P : plans) any_copy |= P.will_copy;
+    const bool use_pump = any_copy && !ctx->src_pinned;
+    if (use_pump && !ctx->pump) ctx->pump = new IngestPump(ctx->device, sx, ingest_threads, (size_t)env_u64("MSD_BOUNCE_MB", 32) << 20, (int)std::max<uint64_t>(2, env_u64("MSD_BOUNCE_PIECES", 8)));
+    std::vector<uint64_t> ticket(plans.size(), 0); std::vector<cudaEvent_t> h2d_t0(plans.size(), nullptr), h2d_t1(plans.size(), nullptr);
+    size_t enq = 0;
+    auto enqueue_upto = [&](size_t limit) {      // chunk j may be copied once chunk j - n_slots has been launched (its decode kernel frees d_comp[k])
+        for (; enq < std::min(limit, plans.size()); enq++) {
+            const Plan& P = plans[enq];
+            if (!P.will_copy) continue;
+            const int k = (int)(enq % ctx->n_slots);
+            CopyRequest r; r.src = F + P.src; r.dst = ctx->d_comp[k]; r.bytes = P.comp_bytes; r.wait_before = ctx->comp_free[k];
+            r.t0 = h2d_t0[enq] = next_event(ctx); r.t1 = h2d_t1[enq] = next_event(ctx); r.done = ctx->h2d_done[k];
+            ticket[enq] = ctx->pump->submit(r);
+        }
+    };
+
+    for (size_t chunk_idx = 0; chunk_idx < plans.size(); chunk_idx++) {
+        const Plan& P = plans[chunk_idx];
+        {
+            // ---- descriptors of one chunk ---------------------------------------------------------------------------------------
             const int k = (int)(chunk_idx % ctx->n_slots), kd = (int)(chunk_idx % kDescSets);
             StageSet& st = ctx->stage[kd];
             if (st.used) MSD_CUDA_OK(cudaEventSynchronize(st.free_ev));
-            uint32_t nb = 0; uint64_t comp_bytes = 0, infl = 0; const uint64_t chunk_src = pos; uint32_t total = 0; bool truncated_last = false;
-            // when the compressed bytes still have to cross PCIe, the first chunks are small so that the pipeline
-            // (copy k+1 | inflate k) starts after a few milliseconds instead of after a full-size copy
-            const bool will_copy = !(ctx->d_staged && pos >= ctx->staged_beg && pos < ctx->staged_end);
-            const uint32_t blk_limit = !will_copy ? ctx->max_blocks : std::min<uint32_t>(ctx->max_blocks, chunk_idx == 0 ? ramp0 : ramp_double ? std::min<uint32_t>(copy_blocks, ramp0 << std::min<uint64_t>(chunk_idx, 8)) : copy_blocks);   // (a small first chunk for resident input was tried: 5 chunks on 4 slots, 43.3 vs 39.2 ms)
-            while (nb < blk_limit) {
-                if (pos >= N || pos > end_c || (pos == end_c && end_u == 0)) { span_done = true; break; }
-                uint32_t xlen = 0, isize = 0;
-                uint32_t blen = bgzf_header(F, N, pos, &xlen, &isize);
-                if (!blen) return ctx_fail(ctx, MSD_EIO, "invalid BGZF block header at file offset %llu", (unsigned long long)pos);
-                if (isize > 65536) return ctx_fail(ctx, MSD_EIO, "BGZF block at %llu claims %u inflated bytes", (unsigned long long)pos, isize);
-                if (comp_bytes + blen > ctx->comp_cap || infl + isize > ctx->infl_cap) { if (nb == 0 && comp_bytes == 0) return ctx_fail(ctx, MSD_ENOMEM, "chunk buffers too small for one BGZF block"); break; }
-                if (isize > 0) {
-                    st.h_desc[nb].src = (pos - chunk_src) + 12 + xlen; st.h_desc[nb].clen = blen - xlen - 20; st.h_desc[nb].isize = isize;
+            uint32_t nb = 0; uint64_t infl = 0; const uint64_t chunk_src = P.src, comp_bytes = P.comp_bytes; const uint32_t total = P.total;
+            const bool first_of_span = P.first_of_span; const uint32_t first_uoff = P.first_uoff;
+            for (uint32_t bi = P.b0; bi < P.b1; bi++) {
+                const BlockInfo& B = blocks[bi];
+                if (B.isize > 0) {
+                    st.h_desc[nb].src = (B.coff - chunk_src) + 12 + B.xlen; st.h_desc[nb].clen = B.blen - B.xlen - 20; st.h_desc[nb].isize = B.isize;
                     st.h_desc[nb].dst = (uint64_t)base + infl; st.h_rel[nb] = (uint32_t)infl; nb++;
                 }
-                const bool is_end_block = (pos == end_c);
-                comp_bytes += blen; pos += blen;
-                if (is_end_block) { total = (uint32_t)infl + std::min(end_u, isize); truncated_last = true; infl += isize; span_done = true; break; }
-                infl += isize;
+                infl += B.isize;
             }
-            if (!truncated_last) total = (uint32_t)infl;
-            if (first_of_span && nb && first_uoff > st.h_desc[0].isize) return ctx_fail(ctx, MSD_EINVAL, "span start offset %u beyond its block", first_uoff);
-            if (nb == 0) { if (span_done) break; continue; }
             st.h_rel[nb] = (uint32_t)infl;
             st.used = true;
             // ---- compressed bytes -> device -------------------------------------------------------------------
-            cudaStream_t si = ctx->s_inflate[k];   // inflate launches alternate between two streams so that chunk k+1 fills
+            cudaStream_t si = ctx->s_inflate[k];   // inflate launches alternate between the slots' streams so that chunk k+1 fills
                                                    // the SMs while the last blocks of chunk k drain (a block takes ~10 ms)
             const uint8_t* d_comp;
-            if (ctx->d_staged && chunk_src >= ctx->staged_beg && chunk_src + comp_bytes <= ctx->staged_end) {
+            if (!P.will_copy) {
                 d_comp = ctx->d_staged + (chunk_src - ctx->staged_beg);
                 // descriptor src offsets assume a 4-byte aligned base: fold the misalignment into src
                 const uint32_t mis = (uint32_t)((uintptr_t)d_comp & 3u);
@@ -853,31 +884,33 @@ int msd_run(msd_ctx* ctx) {
                 MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_desc[kd], st.h_desc, sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, si));
                 MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_rel[kd], st.h_rel, sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, si));
                 MSD_CUDA_OK(cudaEventRecord(st.free_ev, si));
+            } else if (use_pump) {
+                // the descriptors go through the inflate stream (small copies; the pump's pieces in front of them on the copy engine are
+                // 32 MB = ~0.6 ms each), the bytes through the pump: wait until it has handed this chunk's last piece to the copy stream
+                enqueue_upto(chunk_idx + (size_t)ctx->n_slots);
+                MSD_CUDA_OK(cudaStreamWaitEvent(si, ctx->desc_free[kd], 0));
+                MSD_CUDA_OK(cudaStreamWaitEvent(si, ctx->crc_done[kd], 0));
+                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_desc[kd], st.h_desc, sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, si));
+                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_rel[kd], st.h_rel, sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, si));
+                MSD_CUDA_OK(cudaEventRecord(st.free_ev, si));
+                if (!ctx->pump->wait_issued(ticket[chunk_idx])) return ctx_fail(ctx, MSD_ECUDA, "%s", ctx->pump->error());
+                MSD_CUDA_OK(cudaStreamWaitEvent(si, ctx->h2d_done[k], 0));
+                times.h2d.push_back({h2d_t0[chunk_idx], h2d_t1[chunk_idx]});
+                d_comp = ctx->d_comp[k];
             } else {
-                if ((rc = ensure_bounce(ctx))) return rc;
-                // everything this chunk needs goes through the copy stream in one batch, small descriptor copies first:
+                // pinned source: everything this chunk needs goes through the copy stream in one batch, small descriptor copies first:
                 // a copy engine is FIFO, so a descriptor copy queued behind the NEXT chunk's bulk copy would hold this
                 // chunk's kernels back until that bulk copy ends
-                MSD_CUDA_OK(cudaStreamWaitEvent(sx, ctx->desc_free[kd], 0));   // eight sets: chunk k-8 is long gone
+                MSD_CUDA_OK(cudaStreamWaitEvent(sx, ctx->desc_free[kd], 0));   // sixteen sets: chunk k-16 is long gone
                 MSD_CUDA_OK(cudaStreamWaitEvent(sx, ctx->crc_done[kd], 0));    // ... and so is its CRC kernel, which reads the descriptors off the critical path
                 MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_desc[kd], st.h_desc, sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, sx));
                 MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_rel[kd], st.h_rel, sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, sx));
                 MSD_CUDA_OK(cudaEventRecord(st.free_ev, sx));       // h_desc and h_rel of this set are free again
-                MSD_CUDA_OK(cudaStreamWaitEvent(sx, ctx->comp_free[k], 0));     // the decode kernel of chunk k-2 has read d_comp[k]
+                MSD_CUDA_OK(cudaStreamWaitEvent(sx, ctx->comp_free[k], 0));     // the decode kernel of chunk k-n_slots has read d_comp[k]
                 cudaEvent_t h0 = next_event(ctx), h1 = next_event(ctx);
                 MSD_CUDA_OK(cudaEventRecord(h0, sx));
-                const uint8_t* srcp = F + chunk_src;
-                if (!ctx->src_pinned) {
-                    if (ctx->bounce_used[k]) MSD_CUDA_OK(cudaEventSynchronize(ctx->bounce_free[k]));
-                    if (ctx->mapped && pos < N) {   // start the kernel's read-ahead for the next chunk while this one is copied
-                        const uint64_t a = pos & ~4095ull;
-                        madvise(const_cast<uint8_t*>(F) + a, (size_t)std::min<uint64_t>(2 * comp_bytes + 4096, N - a), MADV_WILLNEED);
-                    }
-                    parallel_copy(ctx->stage[k].h_bounce, srcp, comp_bytes, ingest_threads); srcp = ctx->stage[k].h_bounce;
-                }
-                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_comp[k], srcp, comp_bytes, cudaMemcpyHostToDevice, sx));
+                MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_comp[k], F + chunk_src, comp_bytes, cudaMemcpyHostToDevice, sx));
                 MSD_CUDA_OK(cudaEventRecord(h1, sx));
-                if (!ctx->src_pinned) { MSD_CUDA_OK(cudaEventRecord(ctx->bounce_free[k], sx)); ctx->bounce_used[k] = true; }
                 MSD_CUDA_OK(cudaEventRecord(ctx->h2d_done[k], sx));
                 MSD_CUDA_OK(cudaStreamWaitEvent(si, ctx->h2d_done[k], 0));
                 times.h2d.push_back({h0, h1});
@@ -934,8 +967,6 @@ int msd_run(msd_ctx* ctx) {
             MSD_CUDA_OK(cudaGetLastError());
             times.inflate.push_back({e0, e1}); times.frame.push_back({f0, e2}); times.records.push_back({e2, e3}); times.k1.push_back({tr0, f0});
             ctx->info.bytes_compressed += comp_bytes; ctx->info.bytes_inflated += infl; ctx->info.n_blocks += nb;
-            first_of_span = false;
-            chunk_idx++;
         }
     }
     MSD_CUDA_OK(cudaEventRecord(ev_chunks_end, sc));
@@ -1220,7 +1251,7 @@ int msd_regions(msd_ctx* ctx, int tid, int64_t n, const uint32_t* start, const u
         MSD_CUDA_OK(cudaMemcpyAsync(S + o_start, start, (size_t)n * 4, cudaMemcpyHostToDevice, sc));
         MSD_CUDA_OK(cudaMemcpyAsync(S + o_stop, stop, (size_t)n * 4, cudaMemcpyHostToDevice, sc));
         if (n_thr) MSD_CUDA_OK(cudaMemcpyAsync(S + o_thr, thresholds, (size_t)n_thr * 4, cudaMemcpyHostToDevice, sc));
-        regions_kernel<<<grid_for((uint64_t)n, 256, kSMs * 8), 256, 0, sc>>>(ctx->d_arena + ctx->depth_off[tid], tlen, n, (const uint32_t*)(S + o_start),
+        regions_kernel<<<grid_for((uint64_t)n, kRegWarps, kSMs * 8), kRegWarps * 32, 0, sc>>>(ctx->d_arena + ctx->depth_off[tid], tlen, n, (const uint32_t*)(S + o_start),
                                                                            (const uint32_t*)(S + o_stop), use_median, (double*)(S + o_val), ctx->d_racc, ctx->d_rdist,
                                                                            (const int32_t*)(S + o_thr), n_thr, (unsigned long long*)(S + o_cnt));
         MSD_CUDA_OK(cudaGetLastError());
@@ -1351,8 +1382,9 @@ int msd_totals_device(msd_ctx* ctx, void** global_dist, void** region_dist, int6
 }
 
 int msd_totals_reset(msd_ctx* ctx) {
-    if (!ctx || !ctx->d_tot_global) return MSD_EINVAL;
+    if (!ctx) return MSD_EINVAL;
     cudaSetDevice(ctx->device);
+    if (!ctx->d_tot_global) return ensure_query_buffers(ctx);      // allocates the accumulators and comes back here to zero them
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_tot_global, 0, 8ull * kDistBins, ctx->s_compute));
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_tot_region, 0, 8ull * kDistBins, ctx->s_compute));
     init_stats_kernel<<<1, 1, 0, ctx->s_compute>>>(ctx->d_tot_stats);

@@ -232,8 +232,19 @@ windows_all_kernel(const int32_t* __restrict__ arena, const WinContig* __restric
     }
 }
 
-// BED mode: one thread per region (regions sorted by start on the host, mosdepth.nim:376-377)
-__global__ void __launch_bounds__(256)
+// BED mode (r2): one WARP per region (regions sorted by start on the host, mosdepth.nim:376-377).  r1 ran one thread per region:
+// 3 + n_thr + up to 16 bisection passes of scalar loads 4 bytes apart between consecutive iterations and kilobases apart between
+// lanes, one ~300-cycle division on the chain per depth change -- 1.12 ms for 4.8 k regions (profiles/r2a_regions_full_summary.txt,
+// 12 % of the warps active).  Here the warp reads the region in coalesced chunks of 32 cells, ONE pass feeds everything that is
+// order independent -- slice stats (:723-724), the per-base region dist (inc, :741), the threshold counts (:549-553: a ballot and
+// a popc per threshold), the value range for the median -- and the one thing that is not, the float64 mean (Q1), keeps its exact
+// chain: every lane divides its own cell (32 divisions at once instead of one after the other), then all lanes add the 32 quotients
+// in index order (shuffle + __dadd_rn), so the chain costs an addition per cell and nothing else.  The median (CountStat,
+// depthstat.nim:16-30) is the same bisection on the value range as before, each probe a coalesced pass + one warp reduction.
+constexpr int kRegWarps = 8;
+constexpr int kRegMaxThr = 16;      // thresholds counted in the main pass; more of them take extra passes of 16
+
+__global__ void __launch_bounds__(kRegWarps * 32)
 regions_kernel(const int32_t* __restrict__ arr, uint32_t tlen, long long n, const uint32_t* __restrict__ starts,
                const uint32_t* __restrict__ stops, int use_median, double* __restrict__ value_out, RegionAccum* __restrict__ acc,
                unsigned long long* __restrict__ dist, const int32_t* __restrict__ thresholds, int n_thr,
@@ -241,37 +252,102 @@ regions_kernel(const int32_t* __restrict__ arr, uint32_t tlen, long long n, cons
     __shared__ uint32_t s_hist[kHistSmemBins];
     for (int i = threadIdx.x; i < kHistSmemBins; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t L = tlen + 1;   // len(arr), mosdepth.nim:274,719
-    unsigned long long len = 0, sum = 0; uint32_t mn = 0xffffffffu, mx = 0;
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    unsigned long long len = 0, sum = 0; uint32_t mn = 0xffffffffu, mx = 0;     // lane 0 keeps the warp's totals
+    int32_t thr[kRegMaxThr];
+    const int nt0 = n_thr < kRegMaxThr ? n_thr : kRegMaxThr;
+#pragma unroll
+    for (int j = 0; j < kRegMaxThr; j++) thr[j] = j < nt0 ? thresholds[j] : 0x7fffffff;
+    for (long long r = (long long)blockIdx.x * kRegWarps + warp; r < n; r += (long long)gridDim.x * kRegWarps) {
         const uint32_t start = starts[r], stop = stops[r];
-        const uint32_t e = stop < L ? stop : L;
-        double me = 0.0;
-        if (!(start > L)) {                                                 // imean :401-402
-            if (use_median) me = region_median(arr, start, e > start ? e : start, &acc->neg_seen);
-            else me = region_mean_seq(arr, start, e, (double)(uint32_t)(stop - start));
-        }
-        value_out[r] = me;
-        const uint32_t a = start < L ? start : L, b = L < stop ? L : stop;   // :724
-        if (b > a) { slice_stats(arr, a, b, sum, mn, mx); len += b - a; }
-        if (start < L) {                                                    // inc(): start >= len -> warning + return (:421-424)
-            int32_t cur = 0; uint32_t cnt = 0;
-            for (uint32_t i = start; i < e; i++) {
-                const int32_t d = __ldg(arr + i);
-                if (cnt && d == cur) cnt++;
-                else { if (cnt) hist_add(s_hist, dist, cur, cnt); cur = d; cnt = 1; }
+        const uint32_t e = stop < L ? stop : L;                              // imean / inc / thresholds stop at the array end (Q5)
+        const bool in_arr = start < L;
+        const double Ld = (double)(uint32_t)(stop - start);                  // the mean divides by the unclamped length (:411)
+        double a = 0.0;
+        unsigned long long rsum = 0; uint32_t rmn = 0xffffffffu, rmx = 0; uint32_t cnt[kRegMaxThr];
+#pragma unroll
+        for (int j = 0; j < kRegMaxThr; j++) cnt[j] = 0;
+        int32_t vlo = 65535, vhi = 0; bool neg = false;
+        if (in_arr && e > start) {
+            for (uint32_t c0 = start; c0 < e; c0 += 32) {
+                const uint32_t i = c0 + lane;
+                const bool ok = i < e;
+                const int32_t v = ok ? __ldg(arr + i) : 0;
+                const int nn = (int)((e - c0) < 32u ? (e - c0) : 32u);
+                if (!use_median) {                                           // :410-413, strictly in index order
+                    const double q = __ddiv_rn((double)v, Ld);
+                    for (int j = 0; j < nn; j++) a = __dadd_rn(a, __shfl_sync(0xffffffffu, q, j));
+                }
+                if (ok) {
+                    rsum += (unsigned long long)(long long)v;                // slice stats: the clamped slice equals [start, e) here (:724)
+                    const uint32_t u = (uint32_t)v; rmn = u < rmn ? u : rmn; rmx = u > rmx ? u : rmx;
+                    hist_add(s_hist, dist, v, 1u);                           // inc(chrom_region_distribution, arr, start, stop) :741
+                    int32_t w = v; if (w < 0) { neg = true; w = 0; } if (w > 65535) w = 65535;
+                    vlo = w < vlo ? w : vlo; vhi = w > vhi ? w : vhi;
+                }
+#pragma unroll
+                for (int j = 0; j < kRegMaxThr; j++) if (j < nt0) cnt[j] += __popc(__ballot_sync(0xffffffffu, ok && v >= thr[j]));
             }
-            if (cnt) hist_add(s_hist, dist, cur, cnt);
         }
-        if (n_thr > 0) {                                                    // :549-553 (slice clamped to the array)
-            for (int j = 0; j < n_thr; j++) {
-                const int32_t th = thresholds[j];
-                unsigned long long c = 0;
-                for (uint32_t i = start; i < e; i++) c += (__ldg(arr + i) >= th);
-                thr_counts[r * n_thr + j] = c;
+        // warp totals of the one pass
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            rsum += __shfl_down_sync(0xffffffffu, rsum, o);
+            const uint32_t x = __shfl_down_sync(0xffffffffu, rmn, o), y = __shfl_down_sync(0xffffffffu, rmx, o);
+            rmn = x < rmn ? x : rmn; rmx = y > rmx ? y : rmx;
+        }
+        double me = a;
+        if (use_median) {
+            me = 0.0;
+            const long long nn = in_arr ? (long long)e - (long long)start : 0;
+            if (nn > 0) {
+                if (__any_sync(0xffffffffu, neg)) { if (lane == 0) atomicExch(&acc->neg_seen, 1u); }
+                int32_t lo = vlo, hi = vhi;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { const int32_t x = __shfl_xor_sync(0xffffffffu, lo, o), y = __shfl_xor_sync(0xffffffffu, hi, o); lo = x < lo ? x : lo; hi = y > hi ? y : hi; }
+                const long long stop_n = (long long)(0.5 + (double)nn * 0.5);     // depthstat.nim:24
+                while (lo < hi) {                                                  // smallest x with #{v <= x} >= stop_n
+                    const int32_t mid = lo + ((hi - lo) >> 1);
+                    uint32_t c = 0;
+                    for (uint32_t i = start + lane; i < e; i += 32) { int32_t v = __ldg(arr + i); if (v < 0) v = 0; if (v > 65535) v = 65535; c += (v <= mid); }
+                    long long tot = (long long)__reduce_add_sync(0xffffffffu, c);
+                    if (nn > 0xffffffffll / 32) { /* regions longer than 2^27 cells: the 32-bit reduction cannot overflow per lane, but widen the sum */
+                        unsigned long long c64 = c;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) c64 += __shfl_xor_sync(0xffffffffu, c64, o);
+                        tot = (long long)c64;
+                    }
+                    if (tot >= stop_n) hi = mid; else lo = mid + 1;
+                }
+                me = (double)lo;
+            }
+        }
+        if (lane == 0) {
+            value_out[r] = me;
+            const uint32_t sa = start < L ? start : L, sb = L < stop ? L : stop;   // :724
+            if (sb > sa) { len += sb - sa; sum += rsum; mn = rmn < mn ? rmn : mn; mx = rmx > mx ? rmx : mx; }
+#pragma unroll
+            for (int j = 0; j < kRegMaxThr; j++) if (j < nt0) thr_counts[r * n_thr + j] = cnt[j];
+        }
+        // thresholds beyond the first kRegMaxThr: one more coalesced pass per group
+        for (int j0 = kRegMaxThr; j0 < n_thr; j0 += kRegMaxThr) {
+            const int m = (n_thr - j0) < kRegMaxThr ? (n_thr - j0) : kRegMaxThr;
+            uint32_t c2[kRegMaxThr];
+#pragma unroll
+            for (int j = 0; j < kRegMaxThr; j++) c2[j] = 0;
+            if (in_arr) for (uint32_t c0 = start; c0 < e; c0 += 32) {
+                const uint32_t i = c0 + lane; const bool ok = i < e; const int32_t v = ok ? __ldg(arr + i) : 0;
+#pragma unroll
+                for (int j = 0; j < kRegMaxThr; j++) if (j < m) c2[j] += __popc(__ballot_sync(0xffffffffu, ok && v >= thresholds[j0 + j]));
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < kRegMaxThr; j++) if (j < m) thr_counts[r * n_thr + j0 + j] = c2[j];
             }
         }
     }
+    if (lane != 0) { len = 0; sum = 0; mn = 0xffffffffu; mx = 0; }
     block_accumulate(acc, len, sum, mn, mx);
     __syncthreads();
     for (int i = threadIdx.x; i < kHistSmemBins; i += blockDim.x) { uint32_t c = s_hist[i]; if (c) atomicAdd(&dist[i], (unsigned long long)c); }

@@ -97,7 +97,7 @@ MSD_D void seg_stats4(const int4 x, uint32_t idx, uint32_t n_stat, SegStats& my,
 // tile_state[i]: (flag << 32) | value, flag 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix.
 // kScan = false: the arrays already hold depth (a shard after msd_exchange_spills): only the stats pass, tiles taken by stride.
 template <bool kScan>
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kScanThreads, 4)
 scan_segments_kernel(int32_t* __restrict__ arena, const ScanSeg* __restrict__ segs, int n_segs, uint32_t n_tiles,
                      unsigned long long* __restrict__ tile_state, uint32_t* __restrict__ ticket,
                      ContigAccum* __restrict__ acc_all, unsigned long long* __restrict__ hist_all /* [slot][kHistKeep] */) {

@@ -23,6 +23,7 @@
 #include <numeric>
 #include <string>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 #include <zlib.h>
 
@@ -606,6 +607,9 @@ int main(int argc, char** argv) {
         fprintf(stderr, "[mosdepth-b200] {\"gpus\": %d, \"sharding\": \"%s\", \"records\": %llu, \"blocks\": %llu, \"device_ms_max\": %.3f, \"wall_s\": {\"parse_header_index\": %.3f, \"create_open_run\": %.3f, \"emit\": %.3f, \"totals_close\": %.3f}}\n",
                 n_gpus, n_gpus == 1 ? "none" : cut_contigs ? "offsets" : "contigs", recs, blocks, dev_ms, t_start - t_main, t_run - t_start, t_emit - t_run, t_close - t_emit);
     }
-    for (msd_ctx* c : ctxs) msd_destroy(c);
-    return 0;
+    // every output file is closed.  Tearing the contexts down by hand (cudaFree of ~20 GB, unpinning the ingest ring, destroying the CUDA
+    // context) costs 0.3-0.7 s of wall clock for nothing: the process ends here and the driver reclaims everything.
+    if (getenv("MOSDEPTH_B200_CLEAN_EXIT")) { for (msd_ctx* c : ctxs) msd_destroy(c); return 0; }
+    fflush(nullptr);
+    _exit(0);
 }

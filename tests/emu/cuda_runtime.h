@@ -108,6 +108,14 @@ template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned o) {
     w.bar->arrive_and_wait();
     return r;
 }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) {
+    emu::Warp& w = emu::warp(); const unsigned l = emu::lane();
+    uint64_t bits = 0; memcpy(&bits, &v, sizeof v); w.slot[l] = bits;
+    w.bar->arrive_and_wait();
+    T r; memcpy(&r, &w.slot[(l ^ (unsigned)m) & 31], sizeof r);
+    w.bar->arrive_and_wait();
+    return r;
+}
 inline unsigned __ballot_sync(unsigned, int pred) {
     emu::Warp& w = emu::warp(); w.slot[emu::lane()] = pred ? 1 : 0;
     w.bar->arrive_and_wait();

@@ -113,10 +113,11 @@ int main(int argc, char** argv) {
     const long long nr = std::min<long long>(20000, (long long)tlen / 50 + 5);
     std::vector<uint32_t> rs((size_t)nr), re((size_t)nr);
     for (long long k = 0; k < nr; k++) { const uint32_t s = (uint32_t)(rnd() % ((ull)tlen + 40)), len = 1 + (uint32_t)(rnd() % (k % 7 == 0 ? 3000 : 300)); rs[(size_t)k] = s; re[(size_t)k] = s + len; }
-    const int32_t thr[4] = {1, 10, 20, 30};
+    // 4 thresholds (the C4 case), or 18 on odd contig lengths: more than the kernel counts in its main pass (kRegMaxThr)
+    const int32_t thr_all[18] = {1, 10, 20, 30, 31, 32, 33, 34, 35, 36, 37, 38, 40, 45, 50, 100, 1000, 50000}; const int32_t* thr = thr_all; const int NT = (tlen & 1) ? 18 : 4;
     for (int median = 0; median < 2; median++) {
-        std::vector<double> val((size_t)nr, -1.0); RegionAccum ra{0, 0, 0xffffffffu, 0, 0, 0}; std::vector<ull> dist(kDistBins, 0), cnt((size_t)nr * 4, 0);
-        emu::launch(grid_for((uint64_t)nr, 256, max_ctas), 256, [&]() { regions_kernel(arr, tlen, nr, rs.data(), re.data(), median, val.data(), &ra, dist.data(), thr, 4, cnt.data()); });
+        std::vector<double> val((size_t)nr, -1.0); RegionAccum ra{0, 0, 0xffffffffu, 0, 0, 0}; std::vector<ull> dist(kDistBins, 0), cnt((size_t)nr * NT, 0);
+        emu::launch(grid_for((uint64_t)nr, kRegWarps, max_ctas), kRegWarps * 32, [&]() { regions_kernel(arr, tlen, nr, rs.data(), re.data(), median, val.data(), &ra, dist.data(), thr, NT, cnt.data()); });
         std::vector<ull> h(kDistBins, 0); Stat st;
         for (long long k = 0; k < nr; k++) {
             const uint32_t s = rs[(size_t)k], e = re[(size_t)k];
@@ -124,9 +125,9 @@ int main(int argc, char** argv) {
             if (memcmp(&me, &val[(size_t)k], 8) != 0) return fail(median ? "region median" : "region mean (bit pattern)", k, val[(size_t)k], me);
             const uint32_t a = s < L ? s : L, b = L < e ? L : e; stat_add(st, want.data() + a, b > a ? (int64_t)(b - a) : 0);
             if (s < L) for (uint32_t i = s; i < (e < L ? e : L); i++) { int32_t v = want[i]; if (v > (int32_t)kMaxCoverage) v = kMaxCoverage - 10; if (v >= 0) h[v]++; }      // inc, :417-437
-            for (uint32_t i = s; i < (e < L ? e : L); i++) for (int j = 0; j < 4; j++) { if (want[i] < thr[j]) break; if (--cnt[(size_t)k * 4 + j] == ~0ull) return fail("threshold count", k, -1, 0); }
+            for (uint32_t i = s; i < (e < L ? e : L); i++) for (int j = 0; j < NT; j++) { if (want[i] < thr[j]) break; if (--cnt[(size_t)k * NT + j] == ~0ull) return fail("threshold count", k, -1, 0); }
         }
-        for (size_t i = 0; i < cnt.size(); i++) if (cnt[i]) return fail("threshold count", (long long)(i / 4), (double)(long long)cnt[i], 0);
+        for (size_t i = 0; i < cnt.size(); i++) if (cnt[i]) return fail("threshold count", (long long)(i / NT), (double)(long long)cnt[i], 0);
         for (int b = 0; b < kDistBins; b++) if (h[b] != dist[b]) return fail("region dist bin", b, (double)dist[b], (double)h[b]);
         if (ra.cum_length != st.len || ra.cum_depth != st.sum || ra.min_depth != st.mn || ra.max_depth != st.mx) return fail("region stats (length)", median, (double)ra.cum_length, (double)st.len);
     }

@@ -2,6 +2,7 @@
 without a GPU (no CPU fallback), and the host-side logic (header/index parsing, window arithmetic, sharding)."""
 import ctypes
 import json
+import os
 import re
 import subprocess
 from pathlib import Path
@@ -173,13 +174,18 @@ def test_split_contig_spans_hold_every_owned_record(tmp_path):
         assert owned_total == len(every)
 
 
-def test_ingest_parallel_copy_equals_memcpy(tmp_path):
-    """mosdepth_b200/csrc/ingest.hpp: the multi-threaded bounce copy of msd_run for pageable / mapped input."""
+def test_ingest_parallel_copy_and_block_chase(tmp_path):
+    """mosdepth_b200/csrc/ingest.hpp on the CPU: the multi-threaded copies of the pinned-ring pump equal memcpy, and the parallel BSIZE
+    chase (slices found by block signature, stitched) returns exactly the blocks of the serial walk -- also when block signatures are
+    planted inside payloads.  (MSD_CHASE_SLICE_KB shrinks the slices so that a 100 MB test file is cut into many.)"""
     exe = tmp_path / "ingest_test"
-    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", str(exe), str(ROOT / "tools" / "ingest_test.cpp")], check=True)
-    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-I/usr/local/cuda/include", "-o", str(exe), str(ROOT / "tools" / "ingest_test.cpp")], check=True)
+    bam = tmp_path / "c3.bam"
+    subprocess.run([str(ROOT / "tools" / "gen_bam"), "--config", "c3", "--genome-fraction", "0.002", "--threads", "4", "-o", str(bam)], check=True, capture_output=True)
+    r = subprocess.run([str(exe), str(bam)], capture_output=True, text=True, env={**os.environ, "MSD_CHASE_SLICE_KB": "512"})
     assert r.returncode == 0, r.stderr
-    assert json.loads(r.stdout)["bad"] == 0
+    out = json.loads(r.stdout)
+    assert out["bad"] == 0 and out["chase_cases"] == 72
 
 
 def test_cli_shard_plan_equals_python_plan(tmp_path):
