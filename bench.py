@@ -83,8 +83,9 @@ def bam_tag(config, fraction, seed, level=6):
     return f"{config}_f{fraction:g}_s{seed}_l{level}"
 
 
-def make_bam(config, fraction, seed, threads, level=6, keep_tags=()):
-    """Generate (or reuse) the synthetic BAM. Returns (path, n_reads, n_bytes)."""
+def make_bam(config, fraction, seed, threads, level=None, keep_tags=()):
+    """Generate (or reuse) the synthetic BAM (+ BAI, + the exon BED for c4: <bam>.bed). Returns (path, n_reads, n_bytes)."""
+    level = level if level is not None else (1 if config == "c5" else 6)      # nanopore BAMs: QUAL barely compresses, level 1 like the fixture
     tag = bam_tag(config, fraction, seed, level)
     for d in _candidates():      # generated earlier (by this rank, by rank 0, or by an earlier N of the same scaling run)
         bam, meta = d / f"{tag}.bam", d / f"{tag}.json"
@@ -96,9 +97,11 @@ def make_bam(config, fraction, seed, threads, level=6, keep_tags=()):
     tmp = d / f"{tag}.tmp.{os.getpid()}.bam"
     t0 = time.perf_counter()
     r = sh([str(ROOT / "tools" / "gen_bam"), "--config", config, "--genome-fraction", str(fraction), "--seed", str(seed),
-            "--threads", str(threads), "--level", str(level), "-o", str(tmp)])
+            "--threads", str(threads), "--level", str(level), "-o", str(tmp)] + (["--bed", str(tmp) + ".bed"] if config == "c4" else []))
     info = json.loads(r.stdout.strip().splitlines()[-1])
     info["gen_s"] = time.perf_counter() - t0
+    if config == "c4":
+        os.replace(str(tmp) + ".bed", str(bam) + ".bed")
     os.replace(str(tmp) + ".bai", str(bam) + ".bai")
     os.replace(tmp, bam)
     meta.write_text(json.dumps(info))
@@ -277,13 +280,243 @@ def render_outputs(names, lengths, window, per_contig):
             ".mosdepth.region.dist.txt": "".join(rdist)}, (gs, rs, tot_g, tot_r)
 
 
+# ---- the other BASELINE.json configs (C2, C4, C5): one GPU, same contract (value resident / e2e from pinned host memory / parity / CPU sample) ----
+OTHER = {
+    "c2": {"fraction": 1.0, "parity_fraction": 0.02, "sample_fraction": 0.25, "flags": lambda bam: [],
+           "workload": "C2 synthetic 30X chr20 (64,444,167 bp x {f:g}, 150-bp pairs, BGZF level 6), default mode (CIGAR + mate-overlap correction), per-base output"},
+    "c4": {"fraction": 1.0, "parity_fraction": 0.01, "sample_fraction": 0.1, "flags": lambda bam: ["-n", "--by", str(bam) + ".bed", "-T", "1,10,20,30", "-m", "-q", "0:1:10:30:"],
+           "workload": "C4 synthetic 100X exome (25 GRCh38 contigs x {f:g}) + {n_bed} -interval BED (unsorted, overlapping), -n --by BED -T 1,10,20,30 -m -q 0:1:10:30:"},
+    "c5": {"fraction": 0.1, "parity_fraction": 0.0015, "sample_fraction": 0.01, "flags": lambda bam: ["-a", "-n", "--by", "1000"],
+           "workload": "C5 synthetic nanopore 30X WGS (25 GRCh38 contigs x {f:g}, reads 10-100 kb, an operation every ~10 bp, + 2 % short proper pairs), -a -n --by 1000 (fragment mode on the paired subset); default (CIGAR) mode reported beside it"},
+}
+SUFFIXES = [".mosdepth.summary.txt", ".mosdepth.global.dist.txt", ".mosdepth.region.dist.txt", ".regions.bed", ".per-base.bed", ".quantized.bed", ".thresholds.bed"]
+
+
+def other_config(args, frac):
+    spec = OTHER[args.config]
+    return {"workload": spec["workload"].format(f=frac, n_bed=int(round(1195764 * frac))), "genome_fraction": frac, "flags": " ".join(spec["flags"]("BAM")).replace("BAM.bed", "exons.bed"), "gpus": 1,
+            "l2": "inputs (compressed BAM, depth arrays) are far larger than the 126 MB L2; no flush needed"}
+
+
+def cli_vs_oracle(bam, flags, threads):
+    """Every output file of the mosdepth-b200 process against the oracle's, byte for byte.  Returns (ok, detail, oracle_wall_s, cli_wall_s)."""
+    with tempfile.TemporaryDirectory(dir=str(data_dir())) as tmp:
+        t0 = time.perf_counter()
+        subprocess.run([str(ROOT / "oracle" / "mosdepth_oracle"), "-t", str(threads)] + flags + [str(Path(tmp) / "o"), str(bam)], check=True, capture_output=True, env=clean_env())
+        t1 = time.perf_counter()
+        subprocess.run([str(ROOT / "mosdepth_b200" / "bin" / "mosdepth-b200"), "--plain"] + flags + [str(Path(tmp) / "g"), str(bam)], check=True, capture_output=True, env=clean_env())
+        t2 = time.perf_counter()
+        bad, n = [], 0
+        for s in SUFFIXES:
+            po, pg = Path(tmp) / ("o" + s), Path(tmp) / ("g" + s)
+            if po.exists() != pg.exists():
+                bad.append(s + " (missing)")
+            elif po.exists():
+                n += 1
+                if po.read_bytes() != pg.read_bytes():
+                    bad.append(s)
+        return (not bad and n >= 3), (f"{n} files byte-identical" if not bad else f"DIFFER: {bad}"), t1 - t0, t2 - t1
+
+
+def load_bed(path, names):
+    """bed_to_table (mosdepth.nim:362-380): per contig, stable sort by start."""
+    import numpy as np
+    by = {}
+    with open(path) as f:
+        for line in f:
+            c = line.rstrip("\n").split("\t")
+            by.setdefault(c[0], []).append((int(c[1]), int(c[2])))
+    out = {}
+    for t, name in enumerate(names):
+        if name in by:
+            a = np.array(by[name], dtype=np.int64)
+            a = a[np.argsort(a[:, 0], kind="stable")]
+            out[t] = (a[:, 0].astype(np.uint32), a[:, 1].astype(np.uint32))
+    return out
+
+
+def run_other(args):
+    """`--config c2|c4|c5` on one GPU."""
+    spec = OTHER[args.config]
+    frac = args.genome_fraction if args.fraction_given else spec["fraction"]
+    ncores = os.cpu_count() or 1
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    ensure_built()
+    if args.impl == "reference":
+        sfrac = min(args.cpu_fraction or spec["sample_fraction"], frac)
+        bam, n_reads, n_bytes = make_bam(args.config, sfrac, args.seed, ncores)
+        flags = spec["flags"](bam)
+        with tempfile.TemporaryDirectory() as tmp:
+            parity = golden_check(tmp)
+        outp = data_dir() / f"cpu_out_{os.getpid()}"
+        best = {}
+        for t in [x for x in thread_choices() if x >= 3] or thread_choices():
+            cmd = [str(ROOT / "oracle" / "mosdepth_oracle"), "-t", str(t)] + flags + [str(outp), str(bam)]
+            for _ in range(2):
+                t0 = time.perf_counter(); subprocess.run(cmd, check=True, capture_output=True, env=clean_env()); best[t] = min(best.get(t, 1e30), time.perf_counter() - t0)
+        t_best = min(best, key=best.get)
+        cmd = [str(ROOT / "oracle" / "mosdepth_oracle"), "-t", str(t_best)] + flags + [str(outp), str(bam)]
+        times = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter(); subprocess.run(cmd, check=True, capture_output=True, env=clean_env()); times.append(time.perf_counter() - t0)
+        for f in data_dir().glob(f"cpu_out_{os.getpid()}*"):
+            f.unlink()
+        sec = sum(times) / len(times); val = n_reads / sec
+        print(json.dumps({"metric": "reads_per_s", "value": val, "unit": "reads/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": dict(other_config(args, frac), parity_checked=parity),
+                          "cpu_baseline": {"value": val, "unit": "reads/s", "cores": t_best + 1, "kind": "port", "host_cores": ncores,
+                                           "sample": f"bounded sample: the same generator at genome_fraction={sfrac:g} ({n_reads} reads, {n_bytes} BAM bytes), oracle process wall (writes every output file), best of -t {sorted(best)}"},
+                          "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import numpy as np
+    import torch
+    import mosdepth_b200 as m
+    from mosdepth_b200 import hostio
+    torch.cuda.set_device(0)
+    # parity first (small), optionally at bench size as well
+    pbam, p_reads, _ = make_bam(args.config, spec["parity_fraction"], args.seed, ncores)
+    ok, detail, _ow, _cw = cli_vs_oracle(pbam, spec["flags"](pbam), min(ncores - 1, 7))
+    parity_note = f"{p_reads} reads (genome_fraction {spec['parity_fraction']:g}): mosdepth-b200 vs oracle, {detail}"
+    bam, n_reads, n_bytes = make_bam(args.config, frac, args.seed, ncores, keep_tags=(bam_tag(args.config, spec["parity_fraction"], args.seed, 1 if args.config == "c5" else 6),))
+    full = None
+    if args.full_parity:
+        fok, fdetail, ow, cw = cli_vs_oracle(bam, spec["flags"](bam), min(ncores - 1, 15))
+        full = {"ok": fok, "detail": fdetail, "oracle_wall_s": ow, "cli_plain_wall_s": cw}
+        ok = ok and fok
+        parity_note += f"; bench size ({n_reads} reads): {fdetail} (oracle {ow:.1f} s, mosdepth-b200 --plain {cw:.1f} s)"
+    hdr = hostio.read_bam_header(bam)
+    raw = np.fromfile(bam, dtype=np.uint8)
+    host = torch.empty(raw.size, dtype=torch.uint8, pin_memory=True); host.numpy()[:] = raw; del raw
+    ctx = m.Context(0)
+    ctx.open_mem(host, hdr)
+    nt = len(hdr.names)
+    quants = [0, 1, 10, 30, 2**63 - 1]
+    bed = load_bed(str(bam) + ".bed", hdr.names) if args.config == "c4" else None
+    mode = {"c2": m.MODE_DEFAULT, "c4": m.MODE_DEFAULT, "c5": m.MODE_FRAGMENT}[args.config]
+    ctx.set_filters(mode=mode)
+    if args.config == "c5":
+        ctx.prefetch_windows(1000)
+    state = {"d2h": 0, "query_ms": 0.0, "units": 0}
+
+    def step(time_queries=False):
+        ctx.totals_reset()
+        info = ctx.run()
+        nbytes = 0
+        if time_queries:
+            ctx.mark(2)
+        for t in range(nt):
+            if ctx.contig_records(t)[0] < 0:
+                continue
+            st, dist = ctx.contig_stats(t); nbytes += dist.nbytes + 24
+            if args.config == "c2":          # gen_depths (:58-96) for the per-base file
+                a, b, c = ctx.per_base_runs(t); nbytes += 12 * len(a); state["units"] = len(a)
+            elif args.config == "c4":        # BED loop :720-743 with median + thresholds, then gen_quantized :124-141
+                if t in bed:
+                    v, rst, rd, cnt = ctx.regions(t, bed[t][0], bed[t][1], use_median=True, thresholds=(1, 10, 20, 30)); nbytes += v.nbytes + rd.nbytes + cnt.nbytes
+                a, b, c = ctx.quantized_runs(t, quants); nbytes += 12 * len(a)
+            else:                            # window loop :720-741
+                v, rst, rd = ctx.windows(t, 1000); nbytes += v.nbytes + rd.nbytes
+        if time_queries:
+            ctx.mark(3); state["query_ms"] = ctx.elapsed_ms(2, 3)
+        state["d2h"] = nbytes
+        return info
+
+    def timed(resident):
+        if resident:
+            ctx.stage()
+        else:
+            ctx.set_spans([], [])
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(0); sampler.start()
+        lc0 = ctx.launch_count()
+        ctx.mark(0)
+        infos = [step() for _ in range(args.steps)]
+        ctx.mark(1)
+        torch.cuda.synchronize()
+        ms = ctx.elapsed_ms(0, 1) / args.steps
+        sampler.stop_flag.set(); sampler.join()
+        return ms, infos, ctx.launch_count() - lc0, sampler.summary()
+
+    ms_res, infos_res, launches, clocks = timed(True)
+    step(time_queries=True)
+    query_ms = state["query_ms"]
+    ms_e2e, infos_e2e, _l, _c = timed(False)
+    info = infos_res[-1]
+    extra = {}
+    if args.config == "c5":      # the CIGAR-heavy path of the same BAM: default mode (every long read's blocks, no pairs to join)
+        ctx.set_filters(mode=m.MODE_DEFAULT); ctx.stage()
+        for _ in range(2):
+            step()
+        ctx.mark(4); i2 = [step() for _ in range(3)]; ctx.mark(5)
+        ms_def = ctx.elapsed_ms(4, 5) / 3
+        extra = {"default_mode_ms_per_step": ms_def, "default_mode_reads_per_s": n_reads / (ms_def / 1e3), "default_mode_records_ms": i2[-1].ms_records, "default_mode_events": i2[-1].n_events,
+                 "default_mode_events_per_s": i2[-1].n_events / (i2[-1].ms_records / 1e3) if i2[-1].ms_records > 0 else None}
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    avg = lambda f: sum(f(i) for i in infos_res) / len(infos_res)
+    inf_ms = avg(lambda i: i.ms_inflate_span)
+    achieved = (info.bytes_compressed / 1e9) / (inf_ms / 1e3) if inf_ms > 0 else 0.0
+    traffic_per_block = (5.321760e9 + 5.912786e9 + 16.776851e9 + 5.449551e9) / 85062.0
+    cells = info.n_depth_cells
+    # algorithmic bytes of the query stage (SURVEY 8d): C2 runs = 8 B per base (two passes) + 12 B per run; C4 regions = 4 B per covered base
+    # (+ the bisection passes of the median) + quantized runs 8 B per base; C5 windows = 4 B per base + 8 B per window
+    q_bytes = {"c2": 8.0 * cells + 12.0 * state["units"], "c4": 4.0 * (sum(int((e.astype(np.int64) - s.astype(np.int64)).sum()) for s, e in bed.values()) if bed else 0) + 8.0 * cells, "c5": 4.0 * cells}[args.config]
+    roofline = {"kernel": "huffman_decode_kernel + lz77_resolve_kernel (K1, BGZF inflate): the largest share of the step in this config too", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic_per_block * info.n_blocks / max(info.n_inflate_launches, 1), "traffic_source": "ncu --set full, profiles/r2a_fast_full_summary.txt, DRAM bytes per block x blocks per launch",
+                "algorithmic_bytes_per_launch": info.bytes_compressed / max(info.n_inflate_launches, 1), "launches_per_step": info.n_inflate_launches, "ms_per_launch": inf_ms / max(info.n_inflate_launches, 1),
+                "inflate_span_ms": inf_ms, "frame_ms": avg(lambda i: i.ms_frame), "records_ms": avg(lambda i: i.ms_records), "scan_ms": avg(lambda i: i.ms_scan), "run_total_ms": avg(lambda i: i.ms_total),
+                "records_events_per_s": info.n_events / (avg(lambda i: i.ms_records) / 1e3) if avg(lambda i: i.ms_records) > 0 else None, "events": info.n_events,
+                "query_ms": query_ms, "query_algorithmic_bytes": q_bytes, "query_gbs": q_bytes / 1e9 / (query_ms / 1e3) if query_ms > 0 else None,
+                "query_frac": (q_bytes / 1e9 / (query_ms / 1e3) / peak) if query_ms > 0 else None,
+                "query_kernels": {"c2": "K8 runs_count/scan/write/stops (gen_depths)", "c4": "K7 regions_kernel (median + thresholds) + K9 quantized runs", "c5": "K7 windows_all_kernel (served from msd_run)"}[args.config]}
+    roofline.update(extra)
+    ctx.close()
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        sfrac = min(args.cpu_fraction or spec["sample_fraction"], frac)
+        sbam, s_reads, s_bytes = make_bam(args.config, sfrac, args.seed, ncores, keep_tags=(bam_tag(args.config, frac, args.seed, 1 if args.config == "c5" else 6),))
+        flags = spec["flags"](sbam); outp = data_dir() / f"cpu_out_{os.getpid()}"; best = {}
+        for t in [x for x in thread_choices() if x >= 7] or thread_choices():
+            cmd = [str(ROOT / "oracle" / "mosdepth_oracle"), "-t", str(t)] + flags + [str(outp), str(sbam)]
+            for _ in range(2):
+                t0 = time.perf_counter(); subprocess.run(cmd, check=True, capture_output=True, env=clean_env()); best[t] = min(best.get(t, 1e30), time.perf_counter() - t0)
+        t_best = min(best, key=best.get)
+        t0 = time.perf_counter()
+        subprocess.run([str(ROOT / "mosdepth_b200" / "bin" / "mosdepth-b200")] + flags + [str(outp), str(sbam)], check=True, capture_output=True, env=clean_env())
+        cw = time.perf_counter() - t0
+        for f in data_dir().glob(f"cpu_out_{os.getpid()}*"):
+            f.unlink()
+        cpu_baseline = {"value": s_reads / best[t_best], "unit": "reads/s", "cores": t_best + 1, "kind": "port", "seconds": best[t_best], "host_cores": ncores,
+                        "gpu_cli_wall_s_same_sample": cw, "gpu_cli_reads_per_s_same_sample": s_reads / cw,
+                        "sample": f"bounded sample: the same generator at genome_fraction={sfrac:g} ({s_reads} reads, {s_bytes} BAM bytes), oracle process wall with every output file written (.gz), best of -t {sorted(best)} x 2"}
+    line = {"metric": "reads_per_s", "value": n_reads / (ms_res / 1e3), "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": dict(other_config(args, frac), parity_checked=bool(ok)),
+            "e2e": {"value": n_reads / (ms_e2e / 1e3), "unit": "reads/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(infos_e2e[-1].bytes_compressed), "d2h_bytes_per_step": int(state["d2h"])},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "detail": {"reads": n_reads, "bam_bytes": n_bytes, "parity": parity_note, "full_parity": full, "depth_cells": cells}}
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c3")
+    ap.add_argument("--config", default="c3", choices=["c3", "c2", "c4", "c5"], help="BASELINE.json configs: c3 = the headline (30X WGS --by 500 -n -x, 1..8 GPUs); c2 / c4 / c5 run on one GPU")
+    ap.add_argument("--full-parity", action="store_true", help="c2 / c4 / c5: also diff every output file of mosdepth-b200 against the oracle at BENCH size (minutes of CPU time)")
     ap.add_argument("--genome-fraction", type=float, default=float(os.environ.get("MSD_BENCH_FRACTION", "0.5")),
                     help="scale of the 30X genome (every contig length x f).  0.5 = 1.54 Gbp, 309 M reads, 28 GB of BAM: the largest the 1-GPU box generates (16 cores, ~5 min of zlib level 6) and holds twice (page cache + pinned image) inside the bench budget; 1.0 needs ~11 min of generation and 112 GB of host memory")
     ap.add_argument("--cpu-fraction", type=float, default=0.0, help="genome fraction of the CPU arm's bounded sample (default 0.03)")
@@ -294,6 +527,9 @@ def main():
     ap.add_argument("--sharding", default="offsets", choices=["contigs", "offsets"],
                     help="N > 1: N equal BGZF offset ranges of the file, cut inside contigs (the depth that reads leave beyond a cut goes to the next rank over NCCL), or whole contigs per rank (LPT, no data-path exchange)")
     args = ap.parse_args()
+    args.fraction_given = any(a.startswith("--genome-fraction") for a in sys.argv[1:]) or "MSD_BENCH_FRACTION" in os.environ
+    if args.config != "c3":
+        return run_other(args)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 1)
