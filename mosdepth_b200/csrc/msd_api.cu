@@ -105,6 +105,7 @@ struct msd_ctx {
     int32_t *h_run_start = nullptr, *h_run_stop = nullptr, *h_run_val = nullptr; uint64_t h_run_cap = 0;
     int32_t *d_run_start = nullptr, *d_run_stop = nullptr, *d_run_val = nullptr; uint64_t d_run_cap = 0;
     uint32_t* d_tile_count = nullptr; unsigned long long* d_tile_base = nullptr; uint64_t run_tile_cap = 0; unsigned long long* d_run_total = nullptr;
+    int32_t *d_keep_start = nullptr, *d_keep_stop = nullptr, *d_keep_val = nullptr; uint64_t d_keep_cap = 0;      // K9's filter compacts into these, then the two sets swap
     // K10 (msd_per_base_bgzf): grow-only buffers (per line, per member + text, output) and the pinned copy of the output
     BzBuffers bz;
     // generic scratch
@@ -478,7 +479,7 @@ static void fetch_region_accum(msd_ctx* ctx, msd_depth_stat* out, RegionAccum* h
 
 
 template <class F>
-static int compute_runs(msd_ctx* ctx, const int32_t* arr, uint32_t n, int32_t end, F f, uint64_t* n_runs_out) {
+static int compute_runs(msd_ctx* ctx, const int32_t* arr, uint32_t n, int32_t end, F f, uint64_t* n_runs_out, int32_t keep_labels = -1) {
     cudaStream_t sc = ctx->s_compute;
     const uint32_t n_tiles = (n + kRunTile - 1) / kRunTile;
     int rc;
@@ -516,6 +517,31 @@ static int compute_runs(msd_ctx* ctx, const int32_t* arr, uint32_t n, int32_t en
     runs_stops_kernel<<<grid_for(total, 256, kSMs * 8), 256, 0, sc>>>(ctx->d_run_start, total, end, ctx->d_run_stop);
     ctx->launches += 4;
     MSD_CUDA_OK(cudaGetLastError());
+    if (keep_labels >= 0 && total > 0) {
+        // K9's filter (bins without a label are not yielded, :136,:140): order-preserving compaction of the runs on the device
+        const uint32_t kt = (uint32_t)((total + kRunTile - 1) / kRunTile);
+        if (kt > ctx->run_tile_cap) {
+            if ((rc = dev_alloc(ctx, &ctx->d_tile_count, (uint64_t)kt))) return rc;
+            if ((rc = dev_alloc(ctx, &ctx->d_tile_base, (uint64_t)kt))) return rc;
+            ctx->run_tile_cap = kt;
+        }
+        if (ctx->d_keep_cap < ctx->d_run_cap) {
+            if ((rc = dev_alloc(ctx, &ctx->d_keep_start, ctx->d_run_cap))) return rc;
+            if ((rc = dev_alloc(ctx, &ctx->d_keep_stop, ctx->d_run_cap))) return rc;
+            if ((rc = dev_alloc(ctx, &ctx->d_keep_val, ctx->d_run_cap))) return rc;
+            ctx->d_keep_cap = ctx->d_run_cap;
+        }
+        keep_count_kernel<<<kt, kRunThreads, 0, sc>>>(ctx->d_run_val, total, keep_labels, ctx->d_tile_count);
+        runs_scan_kernel<<<1, 1024, 0, sc>>>(ctx->d_tile_count, kt, ctx->d_tile_base, ctx->d_run_total);
+        keep_write_kernel<<<kt, kRunThreads, 0, sc>>>(ctx->d_run_start, ctx->d_run_stop, ctx->d_run_val, total, keep_labels, ctx->d_tile_base, ctx->d_keep_start, ctx->d_keep_stop, ctx->d_keep_val);
+        unsigned long long kept = 0;
+        MSD_CUDA_OK(cudaMemcpyAsync(&kept, ctx->d_run_total, 8, cudaMemcpyDeviceToHost, sc));
+        MSD_CUDA_OK(cudaStreamSynchronize(sc));
+        std::swap(ctx->d_run_start, ctx->d_keep_start); std::swap(ctx->d_run_stop, ctx->d_keep_stop); std::swap(ctx->d_run_val, ctx->d_keep_val);   // same capacity: the kept runs are now "the runs"
+        total = kept;
+        ctx->launches += 3;
+        MSD_CUDA_OK(cudaGetLastError());
+    }
     MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_run_start, ctx->d_run_start, total * 4, cudaMemcpyDeviceToHost, sc));
     MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_run_stop, ctx->d_run_stop, total * 4, cudaMemcpyDeviceToHost, sc));
     MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_run_val, ctx->d_run_val, total * 4, cudaMemcpyDeviceToHost, sc));
@@ -581,6 +607,7 @@ void msd_destroy(msd_ctx* ctx) {
     dev_free(&ctx->mt.word); dev_free(&ctx->mt.head); dev_free(&ctx->mt.live);
     dev_free(&ctx->d_tile_state); dev_free(&ctx->d_scan_ticket); dev_free(&ctx->d_hist); dev_free(&ctx->d_acc); dev_free(&ctx->d_racc);
     dev_free(&ctx->d_dist512); dev_free(&ctx->d_rdist); dev_free(&ctx->d_tot_global); dev_free(&ctx->d_tot_region); dev_free(&ctx->d_tot_stats);
+    dev_free(&ctx->d_keep_start); dev_free(&ctx->d_keep_stop); dev_free(&ctx->d_keep_val);
     dev_free(&ctx->d_run_start); dev_free(&ctx->d_run_stop); dev_free(&ctx->d_run_val); dev_free(&ctx->d_tile_count); dev_free(&ctx->d_tile_base); dev_free(&ctx->d_run_total);
     if (ctx->h_run_start) cudaFreeHost(ctx->h_run_start);
     if (ctx->h_run_stop) cudaFreeHost(ctx->h_run_stop);
@@ -1325,15 +1352,9 @@ static int quantized_runs_impl(msd_ctx* ctx, int tid, const int64_t* quants, int
     QuantF f; f.qa.n = n_q; for (int i = 0; i < n_q; i++) f.qa.q[i] = quants[i];
     // gen_quantized scans pos in 0 ..< arr.high-1 = tlen-1 (:132) but seeds from arr[0] even when that range is empty (:129)
     const uint32_t n_eff = tlen >= 2 ? tlen - 1 : (tlen ? 1u : 0u);
-    uint64_t total = 0;
-    if ((rc = compute_runs(ctx, ctx->d_arena + ctx->depth_off[tid], n_eff, (int32_t)tlen, f, &total))) return rc;
-    // keep what the reference yields: bin != -1 and bin < len(lookup) = n_q-1 (:136,:140); segments stay in order
+    // the reference only yields bins that have a label: bin != -1 and bin < len(lookup) = n_q-1 (:136,:140); the compaction keeps the order
     uint64_t w = 0;
-    for (uint64_t i = 0; i < total; i++) {
-        const int32_t b = ctx->h_run_val[i];
-        if (b == -1 || b >= n_q - 1) continue;
-        ctx->h_run_start[w] = ctx->h_run_start[i]; ctx->h_run_stop[w] = ctx->h_run_stop[i]; ctx->h_run_val[w] = b; w++;
-    }
+    if ((rc = compute_runs(ctx, ctx->d_arena + ctx->depth_off[tid], n_eff, (int32_t)tlen, f, &w, n_q - 1))) return rc;
     *kept = w;
     return MSD_OK;
 }
@@ -1358,10 +1379,7 @@ int msd_quantized_bgzf(msd_ctx* ctx, int tid, const int64_t* quants, int n_q, co
     if (n_runs) *n_runs = (int64_t)w;
     *bgzf = nullptr; *n_bytes = 0; *members = nullptr; *n_members = 0;
     if (w == 0) return MSD_OK;
-    cudaStream_t sc = ctx->s_compute;     // the kept runs go back to the device arrays K9 left them in (w <= the runs those hold)
-    MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_run_start, ctx->h_run_start, 4 * w, cudaMemcpyHostToDevice, sc));
-    MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_run_stop, ctx->h_run_stop, 4 * w, cudaMemcpyHostToDevice, sc));
-    MSD_CUDA_OK(cudaMemcpyAsync(ctx->d_run_val, ctx->h_run_val, 4 * w, cudaMemcpyHostToDevice, sc));
+    cudaStream_t sc = ctx->s_compute;     // K9 left the kept runs on the device (and in pinned memory)
     rc = bz_run(ctx->bz, sc, chrom, ctx->d_run_start, ctx->d_run_stop, ctx->d_run_val, ctx->h_run_start, ctx->h_run_stop, ctx->h_run_val, w, kSMs * 8,
                 [](cudaStream_t s, const uint8_t* d_text, const BlockDesc* d_desc, int nb, uint32_t* ticket, const uint32_t* expected, uint32_t* status, uint32_t* errors, uint32_t* crc_out) {
                     launch_crc(s, d_text, d_desc, nb, ticket, expected, status, errors, crc_out);

@@ -119,4 +119,47 @@ __global__ void runs_stops_kernel(const int32_t* __restrict__ start, unsigned lo
         stop[i] = (i + 1 < n_runs) ? start[i + 1] : end;
 }
 
+
+// K9's filter: gen_quantized only yields the segments whose bin has a label (bin != -1 and bin < n_labels, mosdepth.nim:136,:140).  The
+// stops are fixed before the filter (a dropped segment leaves a gap), so this is a second, order-preserving compaction over the runs
+// themselves: count the kept runs per tile, runs_scan_kernel, then move (start, stop, bin) to their final rank.  r1 did this in a
+// host loop over the pinned arrays.
+MSD_D bool quant_keep(int32_t bin, int32_t n_labels) { return bin != -1 && bin < n_labels; }
+
+__global__ void __launch_bounds__(kRunThreads)
+keep_count_kernel(const int32_t* __restrict__ val, unsigned long long n_runs, int32_t n_labels, uint32_t* __restrict__ tile_count) {
+    __shared__ uint32_t s_w[kRunThreads / 32];
+    const unsigned long long base = (unsigned long long)blockIdx.x * kRunTile;
+    uint32_t c = 0;
+    for (int k = 0; k < kRunItems; k++) { const unsigned long long i = base + (unsigned long long)k * kRunThreads + threadIdx.x; if (i < n_runs) c += quant_keep(val[i], n_labels); }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < kRunThreads / 32; w++) t += s_w[w]; tile_count[blockIdx.x] = t; }
+}
+
+__global__ void __launch_bounds__(kRunThreads)
+keep_write_kernel(const int32_t* __restrict__ start, const int32_t* __restrict__ stop, const int32_t* __restrict__ val, unsigned long long n_runs, int32_t n_labels,
+                  const unsigned long long* __restrict__ tile_base, int32_t* __restrict__ o_start, int32_t* __restrict__ o_stop, int32_t* __restrict__ o_val) {
+    __shared__ uint32_t s_w[kRunThreads / 32];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = tile_base[blockIdx.x];
+    __syncthreads();
+    const unsigned long long base = (unsigned long long)blockIdx.x * kRunTile;
+    for (int k = 0; k < kRunItems; k++) {      // rows of 256 consecutive runs: coalesced, and the order is kept row by row
+        const unsigned long long i = base + (unsigned long long)k * kRunThreads + threadIdx.x;
+        const bool keep = i < n_runs && quant_keep(val[i], n_labels);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        uint32_t wex = 0, row = 0;
+        for (int w = 0; w < kRunThreads / 32; w++) { const uint32_t x = s_w[w]; if (w < warp) wex += x; row += x; }
+        if (keep) { const unsigned long long o = s_base + wex + __popc(m & ((1u << lane) - 1u)); o_start[o] = start[i]; o_stop[o] = stop[i]; o_val[o] = val[i]; }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += row;
+        __syncthreads();
+    }
+}
+
 }  // namespace msd

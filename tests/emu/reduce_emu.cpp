@@ -10,6 +10,7 @@
 #include <string>
 #include "../../mosdepth_b200/csrc/scan.cuh"
 #include "../../mosdepth_b200/csrc/regions.cuh"
+#include "../../mosdepth_b200/csrc/runs.cuh"
 
 using namespace msd;
 typedef unsigned long long ull;
@@ -158,6 +159,20 @@ int main(int argc, char** argv) {
             if (ra[(size_t)c].cum_length != st.len || ra[(size_t)c].cum_depth != st.sum || ra[(size_t)c].min_depth != st.mn || ra[(size_t)c].max_depth != st.mx) return fail("windows_all region stats (sum)", c, (double)ra[(size_t)c].cum_depth, (double)st.sum);
         }
         free(arena);
+    }
+    // ---- K9's filter: keep_count_kernel / runs_scan_kernel / keep_write_kernel (order-preserving compaction of the quantized runs) ----
+    {
+        const ull nr2 = (ull)tlen / 3 + 7; const int32_t n_labels = 3;
+        std::vector<int32_t> st(nr2), en(nr2), bn(nr2), o_st(nr2), o_en(nr2), o_bn(nr2);
+        for (ull i = 0; i < nr2; i++) { st[i] = (int32_t)(3 * i); en[i] = (int32_t)(3 * i + 3); bn[i] = (int32_t)(rnd() % 6) - 1; }      // bins -1 .. 4: -1, 3 and 4 are dropped
+        const unsigned kt = (unsigned)((nr2 + kRunTile - 1) / kRunTile);
+        std::vector<uint32_t> tc(kt); std::vector<ull> tb(kt); ull total = 0;
+        emu::launch(kt, kRunThreads, [&]() { keep_count_kernel(bn.data(), nr2, n_labels, tc.data()); });
+        emu::launch(1, 1024, [&]() { runs_scan_kernel(tc.data(), kt, tb.data(), &total); });
+        emu::launch(kt, kRunThreads, [&]() { keep_write_kernel(st.data(), en.data(), bn.data(), nr2, n_labels, tb.data(), o_st.data(), o_en.data(), o_bn.data()); });
+        ull w = 0;
+        for (ull i = 0; i < nr2; i++) { if (bn[i] == -1 || bn[i] >= n_labels) continue; if (w >= total || o_st[w] != st[i] || o_en[w] != en[i] || o_bn[w] != bn[i]) return fail("kept quantized run", (long long)i, w < total ? o_st[w] : -1, st[i]); w++; }
+        if (w != total) return fail("kept quantized runs (count)", 0, (double)total, (double)w);
     }
     printf("ok tlen %u window %u: %llu scan tiles, %lld windows, %lld regions\n", tlen, window, (ull)n_tiles, nw, nr);
     free(arr);
