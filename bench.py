@@ -414,11 +414,11 @@ def run_other(args):
                 continue
             st, dist = ctx.contig_stats(t); nbytes += dist.nbytes + 24
             if args.config == "c2":          # gen_depths (:58-96) for the per-base file
-                a, b, c = ctx.per_base_runs(t); nbytes += 12 * len(a); state["units"] = len(a)
+                a, b, c = ctx.per_base_runs(t, copy=False); nbytes += 12 * len(a); state["units"] = len(a)      # the runs stay in the library's pinned buffers, as for a C host
             elif args.config == "c4":        # BED loop :720-743 with median + thresholds, then gen_quantized :124-141
                 if t in bed:
                     v, rst, rd, cnt = ctx.regions(t, bed[t][0], bed[t][1], use_median=True, thresholds=(1, 10, 20, 30)); nbytes += v.nbytes + rd.nbytes + cnt.nbytes
-                a, b, c = ctx.quantized_runs(t, quants); nbytes += 12 * len(a)
+                a, b, c = ctx.quantized_runs(t, quants, copy=False); nbytes += 12 * len(a)
             else:                            # window loop :720-741
                 v, rst, rd = ctx.windows(t, 1000); nbytes += v.nbytes + rd.nbytes
         if time_queries:

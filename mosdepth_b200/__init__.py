@@ -15,7 +15,7 @@ import numpy as np
 from . import hostio  # noqa: F401
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libmosdepth_b200.so"
+LIB_PATH = Path(os.environ["MSD_LIB_PATH"]) if os.environ.get("MSD_LIB_PATH") else _HERE / "libmosdepth_b200.so"      # MSD_LIB_PATH: A/B of two builds in one GPU session
 
 MODE_DEFAULT, MODE_FAST, MODE_FRAGMENT = 0, 1, 2
 
@@ -299,17 +299,18 @@ class Context:
                                          C.byref(dl), _ptr(thr) if len(thr) else None, len(thr), _ptr(cnt) if len(thr) else None))
         return vals[:n], st, dist[:dl.value], cnt[:n, :len(thr)]
 
-    def _runs(self, fn, tid, *extra):
+    def _runs(self, fn, tid, *extra, copy=True):
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p(); n = C.c_int64()
         self._check(fn(self.h, tid, *extra, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
         def arr(p):
             if n.value == 0:
                 return np.zeros(0, dtype=np.int32)
-            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(n.value,)).copy()
+            v = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(n.value,))
+            return v.copy() if copy else v      # copy=False: a view of the library-owned pinned buffer, valid until the next call that returns runs
         return arr(a), arr(b), arr(c)
 
-    def per_base_runs(self, tid):
-        return self._runs(self.lib.msd_per_base_runs, tid)
+    def per_base_runs(self, tid, copy=True):
+        return self._runs(self.lib.msd_per_base_runs, tid, copy=copy)
 
     def per_base_bgzf(self, tid, chrom):
         """(BGZF bytes without the EOF marker, members as a structured array, (start, stop, depth)) -- msd_per_base_bgzf."""
@@ -333,9 +334,9 @@ class Context:
         members = np.frombuffer(C.string_at(m, nm.value * mdt.itemsize), dtype=mdt).copy() if nm.value else np.zeros(0, dtype=mdt)
         return data, members, (arr(a), arr(b), arr(c))
 
-    def quantized_runs(self, tid, quants):
+    def quantized_runs(self, tid, quants, copy=True):
         q = np.ascontiguousarray(quants, dtype=np.int64)
-        return self._runs(self.lib.msd_quantized_runs, tid, _ptr(q), len(q))
+        return self._runs(self.lib.msd_quantized_runs, tid, _ptr(q), len(q), copy=copy)
 
     def totals_device(self):
         g, r, s = C.c_void_p(), C.c_void_p(), C.c_void_p(); n = C.c_int64()
