@@ -159,7 +159,9 @@ int msd_per_base_runs(msd_ctx *ctx, int tid, const int32_t **start, const int32_
  * byte offset in *bgzf, the index of the run its first line holds (a line never straddles two members), its compressed
  * and uncompressed sizes -- what the caller needs to build the .csi from the runs, which are returned as by
  * msd_per_base_runs().  All buffers are library-owned pinned host memory, valid until the next call on this context that
- * returns runs.  chrom: at most 200 bytes (MSD_EINVAL beyond; the caller then formats the runs itself). */
+ * returns runs.  chrom: at most 200 bytes (MSD_EINVAL beyond; the caller then formats the runs itself).
+ * A contig with fewer than MSD_BGZF_MIN_RUNS runs (environment, default 50,000) is not worth the fixed cost of the device path: the call
+ * then returns the runs with *n_members = 0 and the caller formats them itself (as after msd_per_base_runs). */
 typedef struct msd_bgzf_member {
     uint64_t offset;      /* of the member inside *bgzf */
     uint64_t first_run;   /* index of the run whose line opens the member */

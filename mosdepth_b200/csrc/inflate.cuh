@@ -228,8 +228,7 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
     const uint4* __restrict__ chunks = nullptr;   // the block's DEFLATE stream from the 16-byte boundary at or before its first byte
     uint8_t* __restrict__ dst = nullptr;
     uint32_t* __restrict__ tok = nullptr;   // this block's token list
-    uint8_t* __restrict__ lit_top = nullptr;   // literal k of the block goes to lit_top[-k]: the top of the block's token region, downwards (r2d)
-    uint32_t ntok = 0, nlit = 0;
+    uint32_t ntok = 0;
     uint32_t clast = 0, total_words = 0, isize = 0, lead = 0, clen = 0, outp = 0, run_base = 0, err = 0;
 #if MSD_BITREADER2
     BitReader2<32> br; br.ring.base = ring; br.bitpos = 0; br.cur = 0; br.p0 = br.p1 = br.p2 = br.p3 = 0;
@@ -244,10 +243,7 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
         // ---- blocks that ended during the last burst; new tickets --------------------------------------------------
         if (phase == kPhFinish) {
             if (outp != isize) { err = kShort; phase = kPhFail; }
-            else {
-                if (outp > run_base) st_stream_u32(tok + ntok++, (kTokSkip << 23) | (outp - run_base));   // the literals behind the last match
-                n_tokens[b] = ntok; status_out[b] = kOk; phase = kPhNeed;
-            }
+            else { n_tokens[b] = ntok; status_out[b] = kOk; phase = kPhNeed; }
         }
         if (phase == kPhFail) {
             n_tokens[b] = 0; status_out[b] = err ? err : (uint32_t)kBadSymbol; atomicAdd(error_count, 1u); phase = kPhNeed;
@@ -264,8 +260,7 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
                   crc_expected[b] = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24); }
                 total_words = (lead + clen + 3) / 4; clast = (lead + clen + 15) / 16; if (clast) clast--;
                 dst = out + bd.dst;
-                tok = tokens + (size_t)b * kTokenCap; ntok = 0; nlit = 0;
-                lit_top = reinterpret_cast<uint8_t*>(tok + kTokenCap) - 1;
+                tok = tokens + (size_t)b * kTokenCap; ntok = 0;
                 outp = 0; run_base = 0; err = 0; bfinal = 0;
                 br.seed(chunks, clast, ring, lead);
                 phase = kPhHeader;
@@ -289,8 +284,8 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
                 else if (outp + len > isize) err = kOverflow;
                 else {
                     const uint8_t* sb = reinterpret_cast<const uint8_t*>(chunks) + sp;
-                    for (uint32_t k = 0; k < len; k++) *(lit_top - (nlit + k)) = sb[k];
-                    outp += len; nlit += len;                               // stored bytes count as literals of the next token
+                    for (uint32_t k = 0; k < len; k++) dst[outp + k] = sb[k];
+                    outp += len;                                            // stored bytes count as literals of the next token
                     br.seed(chunks, clast, ring, sp + len);
                     if (bfinal) phase = kPhFinish;
                 }
@@ -382,7 +377,7 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
                     const uint32_t ext = (lo >> (l1 + 1)) & ((1u << x) - 1u);
                     br.drop((int)(l1 + 1 + x));
                     if ((e & 0x83u) == kEntNotLen) {                               // literal
-                        if (outp < isize) { st_stream_u8(lit_top - nlit, e >> 8); outp++; nlit++; }
+                        if (outp < isize) { st_stream_u8(dst + outp, e >> 8); outp++; }
                         else err = kOverflow;
                     } else if (e & kEntNotLen) {
                         if (e == kEntEob) phase = bfinal ? kPhFinish : kPhHeader;
@@ -440,9 +435,8 @@ lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_bl
         asm volatile("" : "+l"(dst));                  // keep the block base as ONE 64-bit register pair
         const int mis = (int)((uintptr_t)dst & 31u);
         const uint32_t* __restrict__ tok = tokens + (size_t)b * kTokenCap;
-        const uint8_t* __restrict__ lit_top = reinterpret_cast<const uint8_t*>(tok + kTokenCap) - 1;   // literal k of the block: lit_top[-k]
         const int nt = (int)n_tokens[b];
-        int pos_base = 0, lit_base = 0;
+        int pos_base = 0;
         uint32_t w_next = (lane >= 1 && lane - 1 < nt) ? __ldg(tok + lane - 1) : 0u;
         for (int t0 = 0; t0 < nt; t0 += kResolveBatch) {
             const uint32_t w = w_next;
@@ -459,12 +453,7 @@ lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_bl
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, incl, o); if (lane >= o) incl += y; }
             const int total = __shfl_sync(full, incl, 31);
-            int lincl = lr;                                          // literals up to and including this token's run
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, lincl, o); if (lane >= o) lincl += y; }
             const int start = pos_base + incl - adv;                 // first output byte of this token (its literals)
-            const int ldelta = (lit_base + lincl - lr) - start;      // byte p of this token's literal run is literal number p + ldelta of the block
-            lit_base += __shfl_sync(full, lincl, 31);
             const int mstart = is_match ? start + lr : 0x3fffffff;   // first byte of its match (sentinel / skip: never)
             const int hi = pos_base + total;
             const int wb0 = ((pos_base + mis) & ~31) - mis;          // windows are 32-byte aligned in memory
@@ -479,29 +468,25 @@ lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_bl
                 before += __popc(heads);
                 const int ms = __shfl_sync(full, mstart, m);
                 const int md = __shfl_sync(full, dist, m);
-                const int ld = __shfl_sync(full, ldelta, m);
                 const int p = wb + lane;
                 const int k = p - ms;
                 const bool is_copy = k >= 0 && p < hi;
-                const bool is_lit = !is_copy && p >= pos_base && p < hi;   // a literal of this batch: fetched from the packed literals, so that
-                                                                          // every window is written whole (full 32-byte sectors, no read-modify-write)
                 int back = md;                                       // source = p - back
                 if (is_copy && k >= md) back = k - k % md + md;      // dist < len: fold onto the first period
                 const bool far = is_copy && back > lane;            // source lies before this window: final already
                 const bool near = is_copy && back <= lane;          // source is a byte of this window
                 uint8_t v = 0;
                 if (far) v = *(pp - back);
-                if (is_lit) v = *(lit_top - (p + ld));
                 if (__any_sync(full, near)) {
                     // sources inside the window: every lane follows its source lane to a root (a byte that is final:
                     // a literal, a byte of an earlier batch, or a far copy) by pointer doubling, then takes its value
-                    if (!is_copy && !is_lit && p >= 0 && p < hi) v = *pp;
+                    if (!is_copy && p >= 0 && p < hi) v = *pp;
                     int root = near ? lane - back : lane;
 #pragma unroll
                     for (int r = 0; r < 5; r++) root = __shfl_sync(full, root, root);
                     v = (uint8_t)__shfl_sync(full, (int)v, root);
                 }
-                if (is_copy || is_lit) *pp = v;
+                if (is_copy) *pp = v;
                 __syncwarp();
             }
             pos_base = hi;

@@ -81,7 +81,7 @@ struct msd_ctx {
     uint64_t comp_cap = 0, infl_cap = 0; uint32_t carry_cap = 0, max_blocks = 0, rec_cap = 0;
     uint8_t* d_comp[kSlots] = {}; uint8_t* d_infl[kSlots] = {};
     BlockDesc* d_desc[kDescSets] = {}; uint32_t* d_rel[kDescSets] = {};
-    uint32_t *d_bstart = nullptr, *d_land = nullptr, *d_count = nullptr, *d_first = nullptr, *d_cnt = nullptr, *d_recbase = nullptr, *d_recoff = nullptr;
+    uint32_t *d_guess = nullptr, *d_seg = nullptr, *d_bstart = nullptr, *d_land = nullptr, *d_count = nullptr, *d_first = nullptr, *d_cnt = nullptr, *d_recbase = nullptr, *d_recoff = nullptr;
     uint32_t *d_status = nullptr, *d_ticket = nullptr, *d_inflate_err = nullptr;
     uint32_t* d_tokens[kSlots] = {}; uint32_t* d_ntok[kSlots] = {};   // match tokens between K1a and K1b
     uint32_t* d_crc[kSlots] = {}; bool check_crc = true;              // CRC32 fields of the gzip trailers (K1c)
@@ -242,6 +242,8 @@ int ensure_chunk_buffers(msd_ctx* ctx) {
     const uint32_t nb = ctx->max_blocks + 2;
     if ((rc = dev_alloc(ctx, &ctx->d_bstart, nb + 1))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_land, nb))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_guess, nb + 1))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_seg, nb + 2))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_count, nb))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_first, nb))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_cnt, nb))) return rc;
@@ -600,6 +602,7 @@ void msd_destroy(msd_ctx* ctx) {
     free_chunk_buffers(ctx);
     for (int k = 0; k < ctx->n_slots; k++) if (ctx->s_inflate[k]) cudaStreamDestroy(ctx->s_inflate[k]);
     for (int k = 0; k < 2; k++) { dev_free(&ctx->live[k].e); dev_free(&ctx->live[k].arena); dev_free(&ctx->live[k].n); dev_free(&ctx->live[k].arena_used); }
+    dev_free(&ctx->d_guess); dev_free(&ctx->d_seg);
     dev_free(&ctx->d_bstart); dev_free(&ctx->d_land); dev_free(&ctx->d_count); dev_free(&ctx->d_first); dev_free(&ctx->d_cnt);
     dev_free(&ctx->d_recbase); dev_free(&ctx->d_recoff); dev_free(&ctx->d_status); dev_free(&ctx->d_ticket); dev_free(&ctx->d_inflate_err);
     dev_free(&ctx->d_cs); dev_free(&ctx->d_rc);
@@ -961,10 +964,12 @@ int msd_run(msd_ctx* ctx) {
             // ---- K2 framing ---------------------------------------------------------------------------------
             const int nblk = (int)nb + 1;   // + carry pseudo-block
             frame_setup_kernel<<<(nb + 255) / 256, 256, 0, sc>>>(ctx->d_cs, ctx->d_rel[kd], (int)nb, base, first_of_span ? first_uoff : 0u, total, first_of_span ? 1 : 0, ctx->d_bstart);
-            frame_spec_kernel<<<(nblk + 127) / 128, 128, 0, sc>>>(infl_buf, ctx->d_cs, ctx->d_bstart, nblk, ctx->d_land, ctx->d_count);
-            frame_link_kernel<<<1, 1024, 0, sc>>>(infl_buf, ctx->d_cs, ctx->d_bstart, nblk, ctx->d_land, ctx->d_count, ctx->d_first, ctx->d_cnt, ctx->d_recbase);
-            frame_emit_kernel<<<(nblk + 127) / 128, 128, 0, sc>>>(infl_buf, ctx->d_first, ctx->d_cnt, ctx->d_recbase, nblk, ctx->d_recoff);
-            ctx->info.n_launches += 4;
+            frame_guess_kernel<<<(nblk * 32 + 255) / 256, 256, 0, sc>>>(infl_buf, ctx->d_cs, ctx->d_bstart, nblk, ctx->n_targets, ctx->d_guess);
+            frame_segments_kernel<<<1, 1024, 0, sc>>>(ctx->d_cs, ctx->d_guess, nblk, ctx->d_seg);
+            frame_spec_kernel<<<(nblk + 127) / 128, 128, 0, sc>>>(infl_buf, ctx->d_cs, ctx->d_seg, nblk, ctx->d_land, ctx->d_count);
+            frame_link_kernel<<<1, 1024, 0, sc>>>(infl_buf, ctx->d_cs, ctx->d_seg, nblk, ctx->d_land, ctx->d_count, ctx->d_first, ctx->d_cnt, ctx->d_recbase);
+            frame_emit_kernel<<<(nblk + 127) / 128, 128, 0, sc>>>(infl_buf, ctx->d_cs, ctx->d_first, ctx->d_cnt, ctx->d_recbase, nblk, ctx->d_recoff);
+            ctx->info.n_launches += 6;
             MSD_CUDA_OK(cudaEventRecord(e2, sc));
             // ---- K3/K5 (+K4) ------------------------------------------------------------------------------------
             const int rgrid = kSMs * 8;
@@ -1330,6 +1335,9 @@ int msd_per_base_bgzf(msd_ctx* ctx, int tid, const char* chrom, const uint8_t** 
     if (start) *start = ctx->h_run_start; if (stop) *stop = ctx->h_run_stop; if (depth) *depth = ctx->h_run_val;
     if (n_runs) *n_runs = (int64_t)n;
     *bgzf = nullptr; *n_bytes = 0; *members = nullptr; *n_members = 0;
+    // a short contig is not worth K10's fixed cost (a code built from its lines, ~20 launches, four small read-backs): the caller gets the
+    // runs only and formats them itself (MSD_BGZF_MIN_RUNS, default 50,000 lines; 0 = always on the device)
+    if (n < env_u64("MSD_BGZF_MIN_RUNS", 50000)) return MSD_OK;
     // K10: the sequence lives in bedgz_host.cuh (the same code runs under the CPU emulation test); the CRC step is K1c
     rc = bz_run(ctx->bz, ctx->s_compute, chrom, ctx->d_run_start, ctx->d_run_stop, ctx->d_run_val, ctx->h_run_start, ctx->h_run_stop, ctx->h_run_val, n, kSMs * 8,
                 [](cudaStream_t s, const uint8_t* d_text, const BlockDesc* d_desc, int nb, uint32_t* ticket, const uint32_t* expected, uint32_t* status, uint32_t* errors, uint32_t* crc_out) {
@@ -1378,7 +1386,7 @@ int msd_quantized_bgzf(msd_ctx* ctx, int tid, const int64_t* quants, int n_q, co
     if (start) *start = ctx->h_run_start; if (stop) *stop = ctx->h_run_stop; if (bin) *bin = ctx->h_run_val;
     if (n_runs) *n_runs = (int64_t)w;
     *bgzf = nullptr; *n_bytes = 0; *members = nullptr; *n_members = 0;
-    if (w == 0) return MSD_OK;
+    if (w == 0 || w < env_u64("MSD_BGZF_MIN_RUNS", 50000)) return MSD_OK;      // short contig: runs only, see msd_per_base_bgzf
     cudaStream_t sc = ctx->s_compute;     // K9 left the kept runs on the device (and in pinned memory)
     rc = bz_run(ctx->bz, sc, chrom, ctx->d_run_start, ctx->d_run_stop, ctx->d_run_val, ctx->h_run_start, ctx->h_run_stop, ctx->h_run_val, w, kSMs * 8,
                 [](cudaStream_t s, const uint8_t* d_text, const BlockDesc* d_desc, int nb, uint32_t* ticket, const uint32_t* expected, uint32_t* status, uint32_t* errors, uint32_t* crc_out) {

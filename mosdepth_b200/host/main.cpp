@@ -441,7 +441,7 @@ int main(int argc, char** argv) {
     // ---- outputs (mosdepth.nim:641-682) -------------------------------------------------------------------------------
     const std::string gz = plain ? "" : ".gz";
     BgzWriter fbase, fquant, fthr, fregion; FILE *fh_gd, *fh_sum, *fh_rd = nullptr;
-    const bool device_bgzf = getenv("MOSDEPTH_B200_DEVICE_BGZF") && atoi(getenv("MOSDEPTH_B200_DEVICE_BGZF")) != 0;   // per-base.bed.gz deflated on the device (K10)
+    const bool device_bgzf = !getenv("MOSDEPTH_B200_DEVICE_BGZF") || atoi(getenv("MOSDEPTH_B200_DEVICE_BGZF")) != 0;   // per-base / quantized .bed.gz formatted + deflated on the device (K10): the default for .gz output since r2 (0: host threads)
     const int wthreads = getenv("MOSDEPTH_B200_WRITER_THREADS") ? atoi(getenv("MOSDEPTH_B200_WRITER_THREADS")) : 0;   // 0: one per core, at most 32
     if (!no_per_base && !fbase.open(prefix + ".per-base.bed" + gz, 1, plain, wthreads, !plain)) die(1, "[mosdepth] could not open per-base file");
     if (!quant.empty() && !fquant.open(prefix + ".quantized.bed" + gz, 1, plain, wthreads, !plain)) die(1, "[mosdepth] could not open quantized file");
@@ -545,7 +545,7 @@ int main(int argc, char** argv) {
                 if (!plain && device_bgzf && target.name.size() <= 200) {                     // K10: formatted + deflated on the device, appended as is
                     const uint8_t* zb; int64_t zn = 0, nm = 0; const msd_bgzf_member* mem;
                     MSD(msd_per_base_bgzf(ctx, ti, target.name.c_str(), &zb, &zn, &mem, &nm, &st, &en, &dp, &nr));
-                    fbase.write_members(target.name, zb, zn, mem, nm, st, en, dp, nr); nr = 0;
+                    if (nm > 0) { fbase.write_members(target.name, zb, zn, mem, nm, st, en, dp, nr); nr = 0; }      // (a short contig comes back as runs only)
                 } else MSD(msd_per_base_runs(ctx, ti, &st, &en, &dp, &nr));
                 if (!plain && nr) { fbase.write_runs(target.name, st, en, dp, nr); nr = 0; }      // .gz: formatted + deflated by the writer's threads
                 for (int64_t k = 0; k < nr; k++) {
@@ -564,7 +564,7 @@ int main(int argc, char** argv) {
                     std::vector<const char*> lab; for (auto& l : lookup) lab.push_back(l.c_str());
                     const uint8_t* zb; int64_t zn = 0, nm = 0; const msd_bgzf_member* mem;
                     MSD(msd_quantized_bgzf(ctx, ti, quant.data(), (int)quant.size(), target.name.c_str(), lab.data(), (int)lab.size(), &zb, &zn, &mem, &nm, &st, &en, &bn, &nr));
-                    fquant.write_members(target.name, zb, zn, mem, nm, st, en, bn, nr, &lookup); nr = 0;
+                    if (nm > 0) { fquant.write_members(target.name, zb, zn, mem, nm, st, en, bn, nr, &lookup); nr = 0; }
                 } else MSD(msd_quantized_runs(ctx, ti, quant.data(), (int)quant.size(), &st, &en, &bn, &nr));
                 line.clear();
                 if (!plain) { fquant.write_runs(target.name, st, en, bn, nr, &lookup); nr = 0; }

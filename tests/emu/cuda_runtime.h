@@ -148,7 +148,18 @@ inline unsigned __reduce_min_sync(unsigned, unsigned v) {
 // legal answer for __activemask() on any Volta-or-later part, and what code written for independent thread scheduling must accept.
 // A single-lane mask needs no exchange; the aggregated atomics of records.cuh then degenerate to one atomic per thread.
 inline unsigned __activemask() { return 1u << emu::lane(); }
-template <class T> inline unsigned __match_any_sync(unsigned mask, T) { if (mask & (mask - 1)) { fprintf(stderr, "emu: __match_any_sync over several lanes is not provided\n"); abort(); } return mask; }
+// full mask: a real exchange (the K6 histogram aggregation); a single-lane mask (the aggregated atomics of records.cuh under divergence): the caller alone
+template <class T> inline unsigned __match_any_sync(unsigned mask, T v) {
+    if (!(mask & (mask - 1))) return mask;
+    if (mask != 0xffffffffu) { fprintf(stderr, "emu: __match_any_sync over a partial mask is not provided\n"); abort(); }
+    emu::Warp& w = emu::warp(); const unsigned l = emu::lane();
+    uint64_t bits = 0; memcpy(&bits, &v, sizeof v); w.slot[l] = bits;
+    w.bar->arrive_and_wait();
+    const unsigned n = std::min(32u, (unsigned)emu::g_bdim.x - 32u * (emu::t_thread.x >> 5));
+    unsigned m = 0; for (unsigned i = 0; i < n; i++) if (w.slot[i] == bits) m |= 1u << i;
+    w.bar->arrive_and_wait();
+    return m;
+}
 inline unsigned __reduce_max_sync(unsigned mask, unsigned v) { if (mask & (mask - 1)) { fprintf(stderr, "emu: __reduce_max_sync over several lanes is not provided\n"); abort(); } return v; }
 inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
 inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }

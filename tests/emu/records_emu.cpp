@@ -45,8 +45,8 @@ int main(int argc, char** argv) {
     FilterParams fp; memset(&fp, 0, sizeof fp); fp.mapq = 0; fp.min_len = -1; fp.max_len = INT64_MAX; fp.eflag = 1796; fp.iflag = 0; fp.mode = mode; fp.n_rg = 0; fp.rg_names = nullptr; fp.n_targets = n_ref;
     const uint32_t carry_cap = 4u << 20; const size_t chunk_infl = per_chunk * 65536 + 65536;
     std::vector<uint8_t> infl[2]; for (auto& v : infl) v.assign((size_t)carry_cap + chunk_infl + 4096, 0);
-    const uint32_t rec_cap = (uint32_t)((chunk_infl + carry_cap) / 37 + 2), nbmax = (uint32_t)per_chunk + 4;
-    std::vector<uint32_t> rel(nbmax + 2), bstart(nbmax + 4), land(nbmax + 4), count(nbmax + 4), first(nbmax + 4), cnt(nbmax + 4), recbase(nbmax + 4), recoff(rec_cap);
+    const uint32_t rec_cap = (uint32_t)((chunk_infl + carry_cap) / 36 + 2), nbmax = (uint32_t)per_chunk + 4;
+    std::vector<uint32_t> rel(nbmax + 2), guess(nbmax + 4), seg(nbmax + 4), bstart(nbmax + 4), land(nbmax + 4), count(nbmax + 4), first(nbmax + 4), cnt(nbmax + 4), recbase(nbmax + 4), recoff(rec_cap);
     ChunkState cs; memset(&cs, 0, sizeof cs); RunCounters rc; memset(&rc, 0, sizeof rc);
     std::vector<uint8_t> cls(rec_cap); std::vector<uint64_t> qhash(rec_cap); std::vector<int32_t> endpos(rec_cap); std::vector<uint32_t> nxt(rec_cap), slot(rec_cap);
     MateChunk mc{cls.data(), qhash.data(), endpos.data(), nxt.data(), slot.data()};
@@ -59,16 +59,19 @@ int main(int argc, char** argv) {
     int live_cur = 0;
     const uint32_t base = carry_cap;
     // ---- the chunk loop of msd_run ----------------------------------------------------------------------------------------------------
-    size_t k = 0; bool first_of_span = true; ull n_chunks = 0;
+    size_t k = 0; bool first_of_span = true; ull n_chunks = 0, n_segments = 0;
     for (size_t b = b0; b < blocks.size();) {
         uint8_t* buf = infl[k].data(); uint32_t nb = 0, total = 0;
         while (b < blocks.size() && nb < per_chunk) { rel[nb] = total; memcpy(buf + base + total, blocks[b].data.data(), blocks[b].data.size()); total += (uint32_t)blocks[b].data.size(); nb++; b++; }
         rel[nb] = total;
         const int nblk = (int)nb + 1;
         emu::launch((nb + 255) / 256, 256, [&]() { frame_setup_kernel(&cs, rel.data(), (int)nb, base, first_of_span ? first_uoff : 0u, total, first_of_span ? 1 : 0, bstart.data()); });
-        emu::launch((unsigned)(nblk + 127) / 128, 128, [&]() { frame_spec_kernel(buf, &cs, bstart.data(), nblk, land.data(), count.data()); });
-        emu::launch(1, 1024, [&]() { frame_link_kernel(buf, &cs, bstart.data(), nblk, land.data(), count.data(), first.data(), cnt.data(), recbase.data()); });
-        emu::launch((unsigned)(nblk + 127) / 128, 128, [&]() { frame_emit_kernel(buf, first.data(), cnt.data(), recbase.data(), nblk, recoff.data()); });
+        emu::launch((unsigned)(nblk * 32 + 255) / 256, 256, [&]() { frame_guess_kernel(buf, &cs, bstart.data(), nblk, n_ref, guess.data()); });
+        emu::launch(1, 1024, [&]() { frame_segments_kernel(&cs, guess.data(), nblk, seg.data()); });
+        n_segments += cs.n_seg;
+        emu::launch((unsigned)(nblk + 127) / 128, 128, [&]() { frame_spec_kernel(buf, &cs, seg.data(), nblk, land.data(), count.data()); });
+        emu::launch(1, 1024, [&]() { frame_link_kernel(buf, &cs, seg.data(), nblk, land.data(), count.data(), first.data(), cnt.data(), recbase.data()); });
+        emu::launch((unsigned)(nblk + 127) / 128, 128, [&]() { frame_emit_kernel(buf, &cs, first.data(), cnt.data(), recbase.data(), nblk, recoff.data()); });
         if (cs.n_rec > rec_cap) { fprintf(stderr, "rec_cap\n"); return 3; }
         emu::launch((unsigned)max_ctas, 256, [&]() { records_kernel(buf, recoff.data(), &cs, fp, ct, arena.data(), nprefilter.data(), mc, &rc); });
         if (mode == MSD_MODE_DEFAULT) {
@@ -96,6 +99,6 @@ int main(int argc, char** argv) {
         for (uint32_t st = 0, i = 1; i <= tl; i++) if (i == tl || a[i] != a[st]) { fprintf(o, "%s\t%u\t%u\t%d\n", names[(size_t)t].c_str(), st, i, a[st]); st = i; }
     }
     fclose(o);
-    printf("ok %llu chunks, %llu records, %llu events\n", n_chunks, rc.n_records, rc.n_events);
+    printf("ok %llu chunks, %llu segments, %llu records, %llu events\n", n_chunks, n_segments, rc.n_records, rc.n_events);
     return 0;
 }

@@ -111,7 +111,7 @@ int main(int argc, char** argv) {
         if (ra.cum_length != st.len || ra.cum_depth != st.sum || ra.min_depth != st.mn || ra.max_depth != st.mx) return fail("window region stats (sum)", median, (double)ra.cum_depth, (double)st.sum);
     }
     // ---- K7 regions: msd_regions with thresholds, mean and median; intervals of 1..3000 bases, some reaching past the contig end (Q5) -----
-    const long long nr = std::min<long long>(20000, (long long)tlen / 50 + 5);
+    const long long nr = std::min<long long>(300, (long long)tlen / 150 + 5);      // (a warp-per-region kernel costs ~1,000 barrier exchanges per region under the stand-in)
     std::vector<uint32_t> rs((size_t)nr), re((size_t)nr);
     for (long long k = 0; k < nr; k++) { const uint32_t s = (uint32_t)(rnd() % ((ull)tlen + 40)), len = 1 + (uint32_t)(rnd() % (k % 7 == 0 ? 3000 : 300)); rs[(size_t)k] = s; re[(size_t)k] = s + len; }
     // 4 thresholds (the C4 case), or 18 on odd contig lengths: more than the kernel counts in its main pass (kRegMaxThr)

@@ -95,13 +95,13 @@ def test_synthetic_c3_on_mock(oracle_bin, mock_cli, tmp_path):
 
 
 def test_device_bgzf_branch_on_mock(oracle_bin, mock_cli, fixtures, tmp_path):
-    """MOSDEPTH_B200_DEVICE_BGZF=1: the CLI takes ready BGZF members from msd_per_base_bgzf (here: the host replay of K10's arithmetic)
+    """MOSDEPTH_B200_DEVICE_BGZF=1 (the default for .gz output): the CLI takes ready BGZF members from msd_per_base_bgzf (here: the host replay of K10's arithmetic)
     and only appends and indexes them; the per-base file must still decompress to the oracle's, and differ from the host writer's bytes."""
     for k, (name, flags) in enumerate((("nanopore.bam", ["--by", "250", "-q", "0:1:50:100:"]), ("empty-tids.bam", ["-x", "-q", "0:1:5:150"]), ("ovl.bam", ["-q", "0:1:1000"]))):
         d = tmp_path / str(k); d.mkdir()
         compare(oracle_bin, mock_cli, d, fixtures / name, flags, env={"MOSDEPTH_B200_DEVICE_BGZF": "1"}, gz=True)
         dev = (d / "g.per-base.bed.gz").read_bytes()
-        compare(oracle_bin, mock_cli, d, fixtures / name, flags, gz=True)
+        compare(oracle_bin, mock_cli, d, fixtures / name, flags, env={"MOSDEPTH_B200_DEVICE_BGZF": "0"}, gz=True)      # the host writer (the device path is the default since r2)
         assert dev != (d / "g.per-base.bed.gz").read_bytes()
     # labels from the environment (mosdepth.nim:111-122), one of them longer than the device path takes: the CLI falls back to its own writer
     d = tmp_path / "env"; d.mkdir()

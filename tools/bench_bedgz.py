@@ -7,6 +7,7 @@
 and checks that the device members decompress to the text of the runs.
 usage: python tools/bench_bedgz.py [genome_fraction=0.02] [reps=3] [--json]      (--json: one JSON line at the end, for bench.py)"""
 import gzip, json, os, sys, time, zlib
+os.environ.setdefault("MSD_BGZF_MIN_RUNS", "0")      # time the device path on every contig, however short
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import mosdepth_b200 as m
