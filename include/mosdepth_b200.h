@@ -129,7 +129,9 @@ int64_t msd_n_windows(uint32_t tlen, uint32_t window);
 /* Optional hint, call before msd_run(): the host is going to ask msd_windows(tid, window, use_median = 0) for every
  * contig (mosdepth --by <window>, the loop :720-741 inside `for target in sub_targets` :691).  msd_run() then computes
  * the windows of all contigs in one launch and msd_windows() returns them from pinned host memory -- same values, no
- * launch/sync latency per contig.  window = 0 switches the hint off.  Nothing in the reference corresponds to it. */
+ * launch/sync latency per contig; their contribution to the genome-wide `total_region` accumulators (msd_totals) is made by
+ * msd_run() for every such contig, whether or not msd_windows() is called for it.  window = 0 switches the hint off.  Nothing
+ * in the reference corresponds to it. */
 int msd_prefetch_windows(msd_ctx *ctx, uint32_t window);
 int64_t msd_windows(msd_ctx *ctx, int tid, uint32_t window, int use_median, double *value_out, int64_t value_cap,
                     msd_depth_stat *region_stat, int64_t *region_dist512);
@@ -192,7 +194,7 @@ int msd_quantized_bgzf(msd_ctx *ctx, int tid, const int64_t *quants, int n_q, co
  * Device pointer + element count of this context's genome-wide accumulators, kept up to date by
  * msd_run / msd_contig_finalize (global) and msd_windows / msd_regions (region) -- sum_into, mosdepth.nim:761-764:
  * int64 global dist bins, int64 region dist bins, and {cum_length, cum_depth, min, max} x {global, region} packed
- * as 8 int64.  msd_totals_reset() zeroes them. */
+ * as 8 int64.  msd_run() zeroes them when it starts; msd_totals_reset() zeroes them on request. */
 int msd_totals_device(msd_ctx *ctx, void **global_dist, void **region_dist, int64_t *n_bins, void **stats8);
 int msd_totals_reset(msd_ctx *ctx);
 

@@ -342,6 +342,17 @@ int ensure_scratch(msd_ctx* ctx, uint64_t bytes) {
 __global__ void add_hist_kernel(long long* __restrict__ to, const unsigned long long* __restrict__ from, int n) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { unsigned long long v = from[i]; if (v) to[i] += (long long)v; }
 }
+// sum_into + depth_stat `+` for the window rows of every prefetched contig (one CTA per contig)
+__global__ void window_totals_kernel(const RegionAccum* __restrict__ acc, const unsigned long long* __restrict__ dist512, int n_contigs, long long* __restrict__ tot_region, long long* __restrict__ tot_stats4) {
+    const int c = blockIdx.x;
+    if (c >= n_contigs) return;
+    for (int i = threadIdx.x; i < kWindowDistBins; i += blockDim.x) { const unsigned long long v = dist512[(size_t)c * kWindowDistBins + i]; if (v) atomicAdd((unsigned long long*)&tot_region[i], v); }
+    if (threadIdx.x == 0) {
+        const RegionAccum a = acc[c];
+        atomicAdd((unsigned long long*)&tot_stats4[0], a.cum_length); atomicAdd((unsigned long long*)&tot_stats4[1], a.cum_depth);
+        atomicMin(&tot_stats4[2], (long long)a.min_depth); atomicMax(&tot_stats4[3], (long long)a.max_depth);
+    }
+}
 __global__ void init_acc_all_kernel(ContigAccum* a, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { a[i].cum_depth = 0; a[i].min_depth = 0xffffffffu; a[i].max_depth = 0; a[i].neg_seen = 0; a[i].pad = 0; }
@@ -758,10 +769,13 @@ static int run_prefetch_windows(msd_ctx* ctx) {
     const int grid = (int)std::min<long long>((groups + kWinWarps - 1) / kWinWarps, (long long)kSMs * 6);
     windows_all_kernel<<<grid, kWinWarps * 32, 0, sc>>>(ctx->d_arena, ctx->d_pf_table, nc, groups, ctx->pf_window, ctx->d_pf_values, ctx->d_pf_acc, ctx->d_pf_dist);
     MSD_CUDA_OK(cudaGetLastError());
+    // sum_into (:761-764) for the window rows of every prefetched contig, here and once: msd_windows() then answers from the host cache
+    // without a launch or a synchronisation (r1: two launches + one stream sync per contig and call)
+    window_totals_kernel<<<nc, 256, 0, sc>>>(ctx->d_pf_acc, ctx->d_pf_dist, nc, ctx->d_tot_region, ctx->d_tot_stats + 4);
     MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_pf_values, ctx->d_pf_values, (size_t)windows * 8, cudaMemcpyDeviceToHost, sc));
     MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_pf_acc, ctx->d_pf_acc, sizeof(RegionAccum) * nc, cudaMemcpyDeviceToHost, sc));
     MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_pf_dist, ctx->d_pf_dist, 8ull * kWindowDistBins * nc, cudaMemcpyDeviceToHost, sc));
-    ctx->info.n_launches += 1;
+    ctx->info.n_launches += 2;
     ctx->pf_valid = true;    // the caller synchronises the stream before msd_run returns
     return MSD_OK;
 }
@@ -792,6 +806,10 @@ int msd_run(msd_ctx* ctx) {
     cudaEvent_t ev_begin = next_event(ctx), ev_zero_end = next_event(ctx), ev_chunks_end = next_event(ctx), ev_end = next_event(ctx);
 
     MSD_CUDA_OK(cudaEventRecord(ev_begin, sc));
+    // a run starts the genome-wide accumulators afresh: they hold what THIS run and the queries after it add (sum_into, :761-764)
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_tot_global, 0, 8ull * kDistBins, sc));
+    MSD_CUDA_OK(cudaMemsetAsync(ctx->d_tot_region, 0, 8ull * kDistBins, sc));
+    init_stats_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats);
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_arena, 0, ctx->arena_cells * 4, sc));                       // init, mosdepth.nim:238-248
     MSD_CUDA_OK(cudaEventRecord(ev_zero_end, sc));
     MSD_CUDA_OK(cudaMemsetAsync(ctx->d_nprefilter, 0, sizeof(unsigned long long) * ctx->n_targets, sc));
@@ -1226,17 +1244,12 @@ int64_t msd_windows(msd_ctx* ctx, int tid, uint32_t window, int use_median, doub
     const int64_t nw = msd_n_windows(tlen, window);
     if (value_out && value_cap < nw) return ctx_fail(ctx, MSD_EINVAL, "msd_windows: value_cap %lld < %lld windows", (long long)value_cap, (long long)nw);
     if (ctx->pf_valid && window == ctx->pf_window && !use_median && nw > 0 && tid < (int)ctx->pf_slot.size() && ctx->pf_slot[tid] >= 0) {
-        // computed by msd_run (msd_prefetch_windows): serve from the host cache; the totals are still added per call (sum_into)
+        // computed by msd_run (msd_prefetch_windows), totals included: serve from the host cache
         const int i = ctx->pf_slot[tid];
         const RegionAccum& h = ctx->h_pf_acc[i];
-        cudaStream_t sc = ctx->s_compute;
-        add_hist_kernel<<<2, 256, 0, sc>>>(ctx->d_tot_region, ctx->d_pf_dist + (size_t)i * kWindowDistBins, kWindowDistBins);
-        add_stats_kernel<<<1, 1, 0, sc>>>(ctx->d_tot_stats + 4, (long long)h.cum_length, h.cum_depth, h.min_depth, h.max_depth);
-        ctx->launches += 2;
         if (region_stat) { region_stat->cum_length = (int64_t)h.cum_length; region_stat->cum_depth = h.cum_depth; region_stat->min_depth = h.min_depth; region_stat->max_depth = h.max_depth; }
         if (value_out) memcpy(value_out, ctx->h_pf_values + ctx->h_pf_table[i].first_window, (size_t)nw * 8);
         if (region_dist512) memcpy(region_dist512, ctx->h_pf_dist + (size_t)i * kWindowDistBins, 8 * kWindowDistBins);
-        MSD_CUDA_OK(cudaStreamSynchronize(sc));
         return nw;
     }
     if ((rc = ensure_scratch(ctx, (uint64_t)std::max<int64_t>(nw, 1) * 8))) return rc;
