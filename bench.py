@@ -569,12 +569,12 @@ def main():
         barrier()
         return make_bam(args.config, fraction, args.seed, ncores, keep_tags=keep)
 
-    # the library's own communicator: one NCCL id from rank 0 (torch.distributed is only the messenger)
-    comm_id = None
-    if world > 1:
+    def fresh_comm_id():
+        """The library's own communicator: a new NCCL id from rank 0 for every communicator (an id is good for one ncclCommInitRank round);
+        torch.distributed is only the messenger."""
         box = [m.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        comm_id = box[0]
+        return box[0]
 
     class Job:
         """One BAM through this rank's context: the shard plan, the pinned host image of this rank's bytes, and the step."""
@@ -616,7 +616,7 @@ def main():
             for t, lo, hi, cover in self.cut:
                 ctx.set_contig_range(t, lo, hi); ctx.set_contig_cover(t, cover)
             if world > 1:
-                ctx.comm_init(rank, world, comm_id)
+                ctx.comm_init(rank, world, fresh_comm_id())
             self.d2h = 0
             self.results = None
 

@@ -77,30 +77,23 @@ MSD_D void seg_flush(SegStats& my, uint32_t* __restrict__ s_hist, unsigned long 
     __syncthreads();
 }
 
-// the stats of four consecutive cells starting at segment index idx (cells at or beyond n_stat do not count).  EVERY lane of the warp
-// calls it (full-mask votes inside).  Histogram: depths cluster around the coverage (30X: most cells hold 20..40), so one shared-memory
-// atomic per cell -- or per run of equal cells in a lane, as in r1 -- makes 256 threads queue on a dozen addresses.  Per cell position the
-// warp groups its lanes by value (match.any) and the first lane of each group adds the group's size: ~10 conflict-free atomics per 32
-// cells (r2e).
+// the stats of four consecutive cells starting at segment index idx (cells at or beyond n_stat do not count).  Equal neighbouring cells
+// of a lane share one histogram atomic.  (r2e tried grouping the lanes of a warp by value with match.any, one atomic per group: 2.13 TB/s at
+// f = 0.12 against 2.41 / 2.70 TB/s at f = 0.06 / 0.5 for this version -- no gain, dropped.)
 MSD_D void seg_stats4(const int4 x, uint32_t idx, uint32_t n_stat, SegStats& my, uint32_t* __restrict__ s_hist, unsigned long long* __restrict__ hist) {
     const int32_t e[4] = {x.x, x.y, x.z, x.w};
-    const unsigned lane = threadIdx.x & 31u;
+    int32_t cur = 0; uint32_t cnt = 0;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const bool valid = idx + q < n_stat;
+        if (idx + q >= n_stat) break;
         const int32_t d = e[q];
-        if (valid) {
-            my.sum += (unsigned long long)(long long)d;          // dp.uint64 (depthstat.nim:43)
-            const uint32_t u = (uint32_t)d;
-            my.mn = u < my.mn ? u : my.mn; my.mx = u > my.mx ? u : my.mx;
-        }
-        const int32_t bin = (valid && d >= 0 && d < kHistKeep) ? d : -1;      // negative: skipped by inc() (:436); deeper than kHistKeep: the host counts the contig again
-        const unsigned m = __match_any_sync(0xffffffffu, bin);
-        if (bin >= 0 && lane == (unsigned)(__ffs((int)m) - 1)) {
-            const uint32_t c = (uint32_t)__popc(m);
-            if (bin < kHistSmemBins) atomicAdd(&s_hist[bin], c); else atomicAdd(&hist[bin], (unsigned long long)c);
-        }
+        my.sum += (unsigned long long)(long long)d;          // dp.uint64 (depthstat.nim:43)
+        const uint32_t u = (uint32_t)d;
+        my.mn = u < my.mn ? u : my.mn; my.mx = u > my.mx ? u : my.mx;
+        if (cnt && d == cur) cnt++;
+        else { if (cnt) hist_add_keep(s_hist, hist, cur, cnt); cur = d; cnt = 1; }
     }
+    if (cnt) hist_add_keep(s_hist, hist, cur, cnt);
 }
 
 // tile_state[i]: (flag << 32) | value, flag 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix.

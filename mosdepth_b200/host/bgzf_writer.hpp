@@ -57,7 +57,10 @@ inline bool deflate_block(const char* in, size_t n, int level, std::vector<uint8
 
 // ---- CSI index of a BGZF-compressed, position-sorted, tab-separated text (tabix "bed" preset) -----------------------
 struct CsiBuilder {
-    static constexpr int kMinShift = 14, kDepth = 5;
+    static constexpr int kMinShift = 14;
+    // levels of the binning scheme: the reference derives them from the longest target (get_min_levels, mosdepth.nim:565-577, passed to
+    // wopen_bgzi :636-678); 5 levels reach 2^29 bp.  Set once per process (csi_set_depth) before any writer is opened.
+    static int& depth_ref() { static int d = 5; return d; }
     struct Chunk { uint64_t beg, end; };
     struct Ref {
         std::map<uint32_t, std::vector<Chunk>> bins;
@@ -68,7 +71,7 @@ struct CsiBuilder {
     std::string last_chrom; int last_tid = -1;
     uint64_t n_lines = 0;
     static uint32_t reg2bin(int64_t beg, int64_t end) {         // CSIv1 spec, section 3
-        int l = kDepth, s = kMinShift; uint32_t t = ((1u << (kDepth * 3)) - 1) / 7;
+        int l = depth_ref(), s = kMinShift; uint32_t t = ((1u << (depth_ref() * 3)) - 1) / 7;
         for (--end; l > 0; --l, s += 3, t -= 1u << (l * 3)) if (beg >> s == end >> s) return t + (uint32_t)(beg >> s);
         return 0;
     }
@@ -98,7 +101,7 @@ struct CsiBuilder {
     std::vector<uint8_t> serialise() const {
         std::vector<uint8_t> o;
         o.insert(o.end(), {'C', 'S', 'I', 1});
-        put32(o, (uint32_t)kMinShift); put32(o, (uint32_t)kDepth);
+        put32(o, (uint32_t)kMinShift); put32(o, (uint32_t)depth_ref());
         std::vector<uint8_t> aux;                                 // tabix header: format=0x10000 (UCSC/BED: 0-based, half-open), col_seq 1, col_beg 2, col_end 3, meta '#', skip 0
         put32(aux, 0x10000u); put32(aux, 1); put32(aux, 2); put32(aux, 3); put32(aux, (uint32_t)'#'); put32(aux, 0);
         std::string nm; for (const auto& n : names) { nm += n; nm.push_back('\0'); }
@@ -112,8 +115,8 @@ struct CsiBuilder {
             for (const auto& kv : r.bins) {
                 // loffset of a bin = linear-index entry of its first window: a lower bound for every line that overlaps the bin
                 int l = 0; uint32_t first = 0;
-                for (int k = kDepth; k >= 0; k--) { const uint32_t f = ((1u << (3 * k)) - 1) / 7; if (kv.first >= f) { l = k; first = f; break; } }
-                const size_t w = (size_t)(kv.first - first) << (3 * (kDepth - l));
+                for (int k = depth_ref(); k >= 0; k--) { const uint32_t f = ((1u << (3 * k)) - 1) / 7; if (kv.first >= f) { l = k; first = f; break; } }
+                const size_t w = (size_t)(kv.first - first) << (3 * (depth_ref() - l));
                 put32(o, kv.first); put64(o, w < lin.size() ? lin[w] : 0); put32(o, (uint32_t)kv.second.size());
                 for (const Chunk& c : kv.second) { put64(o, c.beg); put64(o, c.end); }
             }
@@ -122,6 +125,10 @@ struct CsiBuilder {
         return o;
     }
 };
+
+// get_min_levels (mosdepth.nim:565-577): how many levels the longest target needs above the 16 KB leaves
+inline int csi_min_levels(uint64_t max_len) { int r = 0; uint64_t s = 1ull << 14; while (max_len > s) { r++; s <<= 3; } return r; }
+inline void csi_set_depth(int d) { CsiBuilder::depth_ref() = d < 0 ? 0 : d > 9 ? 9 : d; }
 
 // Worker-side aggregation of the index entries of sorted lines: consecutive lines that lie in the same 16 KB window (so in the same
 // leaf bin) and follow each other without a gap become ONE segment, which is what CsiBuilder::add would have merged them into anyway

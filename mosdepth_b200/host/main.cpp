@@ -438,6 +438,7 @@ int main(int argc, char** argv) {
     auto owner_ctx = [&](int ti) -> msd_ctx* { return (n_gpus == 1 || owners[(size_t)ti].empty()) ? ctxs[0] : ctxs[(size_t)owners[(size_t)ti][0].rank]; };
     auto is_cut = [&](int ti) { return n_gpus > 1 && (owners[(size_t)ti].size() > 1 || (owners[(size_t)ti].size() == 1 && owners[(size_t)ti][0].pc.cut)); };
 
+    { uint64_t mx = 0; for (auto& t : H.targets) mx = std::max<uint64_t>(mx, t.length); bgz::csi_set_depth(bgz::csi_min_levels(mx)); }   // levels = get_min_levels(targets) :636
     // ---- outputs (mosdepth.nim:641-682) -------------------------------------------------------------------------------
     const std::string gz = plain ? "" : ".gz";
     BgzWriter fbase, fquant, fthr, fregion; FILE *fh_gd, *fh_sum, *fh_rd = nullptr;
