@@ -374,6 +374,8 @@ int main(int argc, char** argv) {
     }
     uint8_t comm_id[MSD_COMM_ID_BYTES];
     if (n_gpus > 1 && msd_comm_unique_id(comm_id) != 0) die(1, "[mosdepth] %s", msd_last_error(nullptr));
+    std::vector<std::thread> comm_threads((size_t)n_gpus); std::vector<int> comm_rc((size_t)n_gpus, 0);
+    auto join_comm = [&]() { for (int r = 0; r < n_gpus; r++) if (comm_threads[(size_t)r].joinable()) { comm_threads[(size_t)r].join(); if (comm_rc[(size_t)r] < 0) die(1, "[mosdepth] msd_comm_init: %s", msd_last_error(ctxs[(size_t)r])); } };
     uint32_t margin_bp = 65536;
     for (int attempt = 0;; attempt++) {
         if (n_gpus == 1) { shards.assign(1, {}); for (int t = 0; t < nt; t++) if (want[t] && t < (int)index.size() && index[t].has) shards[0].push_back(Piece{t, 0, tl[t], index[t].beg, index[t].end, 0, false}); }
@@ -387,7 +389,9 @@ int main(int argc, char** argv) {
                 if (msd_create(device + r, &ctx) != 0) { rank_rc[(size_t)r] = -1; rank_err[(size_t)r] = msd_last_error(nullptr); ctx = nullptr; return; }
                 if (msd_open(ctx, bam_path.c_str(), nt, tl.data(), H.first_voff) < 0) return fail("msd_open");
                 if (msd_set_filters(ctx, mapq, min_len, max_len, eflag, iflag, rgs.empty() ? nullptr : rgs.data(), (int)rgs.size(), mode) < 0) return fail("msd_set_filters");
-                if (n_gpus > 1 && msd_comm_init(ctx, r, n_gpus, comm_id) < 0) return fail("msd_comm_init");
+                // joining the NCCL communicator takes a few hundred milliseconds and is only needed after msd_run (spill exchange, totals):
+                // it runs on a thread of its own beside open / plan / run (it touches the context's communicator fields only)
+                if (n_gpus > 1) comm_threads[(size_t)r] = std::thread([&, r] { comm_rc[(size_t)r] = msd_comm_init(ctxs[(size_t)r], r, n_gpus, comm_id); });
             }
             std::vector<uint8_t> mine((size_t)nt, 0); std::vector<uint64_t> sb, se;
             if (attempt > 0) for (int t = 0; t < nt; t++) msd_set_contig_range(ctx, t, 0, 0);   // a retry with a longer margin: drop the previous ranges
@@ -410,9 +414,10 @@ int main(int argc, char** argv) {
         bool retry = false;
         for (int r = 0; r < n_gpus; r++) {
             if (rank_rc[(size_t)r] == MSD_ESPAN && margin_bp < (1u << 30)) retry = true;       // a mate lies in front of a shard's span: reach further back
-            else if (rank_rc[(size_t)r] < 0) die(1, "[mosdepth] %s", rank_err[(size_t)r].c_str());
+            else if (rank_rc[(size_t)r] < 0) { fprintf(stderr, "[mosdepth] %s\n", rank_err[(size_t)r].c_str()); fflush(nullptr); _exit(1); }   // (other ranks may still be joining the communicator: no unwinding)
         }
         if (retry) { margin_bp = margin_bp >= (1u << 26) ? 0xfffffff0u : margin_bp * 16; if (attempt > 6) die(1, "[mosdepth] %s", rank_err[0].c_str()); continue; }
+        join_comm();
         if (any_cut) {   // the depth that reads leave beyond a cut goes to the next rank (NCCL send / recv), then every shard gets its stats
             std::vector<std::thread> th;
             for (int r = 0; r < n_gpus; r++) th.emplace_back([&, r] { if (msd_exchange_spills(ctxs[(size_t)r]) < 0) { rank_rc[(size_t)r] = -1; rank_err[(size_t)r] = msd_last_error(ctxs[(size_t)r]); } });
