@@ -213,13 +213,18 @@ enum DecPhase : int { kPhNeed = 0, kPhHeader = 1, kPhBuild = 2, kPhSym = 3, kPhF
 #ifndef MSD_DEC_MINBLOCKS
 #define MSD_DEC_MINBLOCKS 9
 #endif
-__global__ void __launch_bounds__(kDecThreads, MSD_DEC_MINBLOCKS)
-huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, int n_blocks,
-                      uint32_t* __restrict__ ticket, uint32_t* __restrict__ tokens, uint32_t* __restrict__ n_tokens,
-                      uint32_t* __restrict__ status_out, uint32_t* __restrict__ error_count, uint32_t* __restrict__ crc_expected) {
-    extern __shared__ __align__(16) uint16_t smem16[];
+// One decode warp: 32 lanes = 32 blocks in lock step (see the header comment).  kPacked = false: literal bytes go straight to their final
+// position in `out` (the two-kernel pipeline).  kPacked = true (the fused kernel): literals are written packed, downwards from the top of
+// the block's own token region, so that the resolve warp is the only writer of `out` and can pick the block up while this kernel is still
+// running (no other SM's L1 can hold a stale line of bytes that a decode lane wrote); a finished block is announced in `done_ring`.
+template <bool kPacked>
+__device__ __forceinline__ void
+decode_warp(uint16_t* __restrict__ smem16, const uint8_t* __restrict__ comp, uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, int n_blocks,
+            uint32_t* __restrict__ ticket, uint32_t* __restrict__ tokens, uint32_t* __restrict__ n_tokens,
+            uint32_t* __restrict__ status_out, uint32_t* __restrict__ error_count, uint32_t* __restrict__ crc_expected,
+            unsigned long long* __restrict__ done_ring, uint32_t* __restrict__ done_tail) {
     constexpr unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const LaneMem M{smem16 + lane};
     uint32_t* const ring = reinterpret_cast<uint32_t*>(smem16 + kLaneHw * 32) + lane;   // word w of this lane: ring[(w & 15) * 32]
     uint32_t* const scratch = reinterpret_cast<uint32_t*>(smem16 + kLaneHw * 32) + kRingWords * 32;
@@ -228,7 +233,8 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
     const uint4* __restrict__ chunks = nullptr;   // the block's DEFLATE stream from the 16-byte boundary at or before its first byte
     uint8_t* __restrict__ dst = nullptr;
     uint32_t* __restrict__ tok = nullptr;   // this block's token list
-    uint32_t ntok = 0;
+    uint8_t* __restrict__ lit_top = nullptr;   // literal k of the block goes to lit_top[-k]: the top of the block's token region, downwards (r2d)
+    uint32_t ntok = 0, nlit = 0;
     uint32_t clast = 0, total_words = 0, isize = 0, lead = 0, clen = 0, outp = 0, run_base = 0, err = 0;
 #if MSD_BITREADER2
     BitReader2<32> br; br.ring.base = ring; br.bitpos = 0; br.cur = 0; br.p0 = br.p1 = br.p2 = br.p3 = 0;
@@ -243,10 +249,15 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
         // ---- blocks that ended during the last burst; new tickets --------------------------------------------------
         if (phase == kPhFinish) {
             if (outp != isize) { err = kShort; phase = kPhFail; }
-            else { n_tokens[b] = ntok; status_out[b] = kOk; phase = kPhNeed; }
+            else {
+                if (kPacked && outp > run_base) st_stream_u32(tok + ntok++, (kTokSkip << 23) | (outp - run_base));   // the literals behind the last match
+                n_tokens[b] = ntok; status_out[b] = kOk; phase = kPhNeed;
+                if (kPacked) { __threadfence(); done_ring[atomicAdd(done_tail, 1u)] = ((unsigned long long)ntok << 32) | (uint32_t)(b + 1); }   // literals + tokens are visible: a resolve warp may take the block
+            }
         }
         if (phase == kPhFail) {
             n_tokens[b] = 0; status_out[b] = err ? err : (uint32_t)kBadSymbol; atomicAdd(error_count, 1u); phase = kPhNeed;
+            if (kPacked) { __threadfence(); done_ring[atomicAdd(done_tail, 1u)] = (unsigned long long)(uint32_t)(b + 1); }    // nothing to resolve
         }
         if (phase == kPhNeed) {
             b = (int)atomicAdd(ticket, 1u);
@@ -260,7 +271,8 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
                   crc_expected[b] = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24); }
                 total_words = (lead + clen + 3) / 4; clast = (lead + clen + 15) / 16; if (clast) clast--;
                 dst = out + bd.dst;
-                tok = tokens + (size_t)b * kTokenCap; ntok = 0;
+                tok = tokens + (size_t)b * kTokenCap; ntok = 0; nlit = 0;
+                lit_top = reinterpret_cast<uint8_t*>(tok + kTokenCap) - 1;
                 outp = 0; run_base = 0; err = 0; bfinal = 0;
                 br.seed(chunks, clast, ring, lead);
                 phase = kPhHeader;
@@ -284,8 +296,9 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
                 else if (outp + len > isize) err = kOverflow;
                 else {
                     const uint8_t* sb = reinterpret_cast<const uint8_t*>(chunks) + sp;
-                    for (uint32_t k = 0; k < len; k++) dst[outp + k] = sb[k];
-                    outp += len;                                            // stored bytes count as literals of the next token
+                    if (kPacked) { for (uint32_t k = 0; k < len; k++) *(lit_top - (nlit + k)) = sb[k]; }
+                    else { for (uint32_t k = 0; k < len; k++) dst[outp + k] = sb[k]; }
+                    outp += len; nlit += len;                               // stored bytes count as literals of the next token
                     br.seed(chunks, clast, ring, sp + len);
                     if (bfinal) phase = kPhFinish;
                 }
@@ -377,7 +390,7 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
                     const uint32_t ext = (lo >> (l1 + 1)) & ((1u << x) - 1u);
                     br.drop((int)(l1 + 1 + x));
                     if ((e & 0x83u) == kEntNotLen) {                               // literal
-                        if (outp < isize) { st_stream_u8(dst + outp, e >> 8); outp++; }
+                        if (outp < isize) { st_stream_u8(kPacked ? lit_top - nlit : dst + outp, e >> 8); outp++; nlit++; }
                         else err = kOverflow;
                     } else if (e & kEntNotLen) {
                         if (e == kEntEob) phase = bfinal ? kPhFinish : kPhHeader;
@@ -413,6 +426,14 @@ huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ ou
     }
 }
 
+__global__ void __launch_bounds__(kDecThreads, MSD_DEC_MINBLOCKS)
+huffman_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, int n_blocks,
+                      uint32_t* __restrict__ ticket, uint32_t* __restrict__ tokens, uint32_t* __restrict__ n_tokens,
+                      uint32_t* __restrict__ status_out, uint32_t* __restrict__ error_count, uint32_t* __restrict__ crc_expected) {
+    extern __shared__ __align__(16) uint16_t smem16[];
+    decode_warp<false>(smem16, comp, out, blocks, n_blocks, ticket, tokens, n_tokens, status_out, error_count, crc_expected, nullptr, nullptr);
+}
+
 // K1b.  One warp per BGZF block: copies every match of the block's token list; literals are already in place.
 // A batch is 31 tokens in lanes 1..31 (lane 0 is a sentinel "no token"), so that a byte's token index -- the number of
 // token starts at or before it -- is used as a shuffle lane directly.
@@ -420,28 +441,24 @@ constexpr int kResolveWarps = 4;
 constexpr int kResolveCtasPerSm = 16;
 constexpr int kResolveBatch = 31;
 
-__global__ void __launch_bounds__(kResolveWarps * 32, kResolveCtasPerSm)
-lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_blocks, uint32_t* __restrict__ ticket,
-                    const uint32_t* __restrict__ tokens, const uint32_t* __restrict__ n_tokens) {
+// the matches (kPacked: and the literals) of ONE block, by one warp.  nt tokens at tok; kPacked: literal k of the block at lit_top[-k].
+template <bool kPacked>
+__device__ __forceinline__ void resolve_block(uint8_t* dst, const uint32_t* __restrict__ tok, int nt, int lane) {
     constexpr unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
     const uint32_t le = 0xffffffffu >> (31 - lane);   // lanes <= this one
-    for (;;) {
-        int b = 0;
-        if (lane == 0) b = (int)atomicAdd(ticket, 1u);
-        b = __shfl_sync(full, b, 0);
-        if (b >= n_blocks) return;
-        uint8_t* dst = out + blocks[b].dst;
+    {
+        {
         asm volatile("" : "+l"(dst));                  // keep the block base as ONE 64-bit register pair
         const int mis = (int)((uintptr_t)dst & 31u);
-        const uint32_t* __restrict__ tok = tokens + (size_t)b * kTokenCap;
-        const int nt = (int)n_tokens[b];
-        int pos_base = 0;
-        uint32_t w_next = (lane >= 1 && lane - 1 < nt) ? __ldg(tok + lane - 1) : 0u;
+        const uint8_t* lit_top = reinterpret_cast<const uint8_t*>(tok + kTokenCap) - 1;   // literal k of the block: lit_top[-k]
+        int pos_base = 0, lit_base = 0;
+        // kPacked: the tokens were written during THIS kernel (by a decode lane, before it announced the block): ordinary loads, not ld.global.nc
+        auto ldtok = [&](int i) -> uint32_t { return kPacked ? tok[i] : __ldg(tok + i); };
+        uint32_t w_next = (lane >= 1 && lane - 1 < nt) ? ldtok(lane - 1) : 0u;
         for (int t0 = 0; t0 < nt; t0 += kResolveBatch) {
             const uint32_t w = w_next;
             const bool have = lane >= 1 && t0 + lane - 1 < nt;
-            { const int tn = t0 + kResolveBatch + lane - 1; w_next = (lane >= 1 && tn < nt) ? __ldg(tok + tn) : 0u; }   // next batch: in flight during this one
+            { const int tn = t0 + kResolveBatch + lane - 1; w_next = (lane >= 1 && tn < nt) ? ldtok(tn) : 0u; }   // next batch: in flight during this one
             int lr = 0, dist = 0, adv = 0;
             bool is_match = false;
             if (have) {
@@ -454,6 +471,14 @@ lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_bl
             for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, incl, o); if (lane >= o) incl += y; }
             const int total = __shfl_sync(full, incl, 31);
             const int start = pos_base + incl - adv;                 // first output byte of this token (its literals)
+            int ldelta = 0;
+            if (kPacked) {
+                int lincl = lr;                                      // literals up to and including this token's run
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, lincl, o); if (lane >= o) lincl += y; }
+                ldelta = (lit_base + lincl - lr) - start;            // byte p of this token's literal run is literal number p + ldelta of the block
+                lit_base += __shfl_sync(full, lincl, 31);
+            }
             const int mstart = is_match ? start + lr : 0x3fffffff;   // first byte of its match (sentinel / skip: never)
             const int hi = pos_base + total;
             const int wb0 = ((pos_base + mis) & ~31) - mis;          // windows are 32-byte aligned in memory
@@ -468,28 +493,94 @@ lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_bl
                 before += __popc(heads);
                 const int ms = __shfl_sync(full, mstart, m);
                 const int md = __shfl_sync(full, dist, m);
+                const int ld = kPacked ? __shfl_sync(full, ldelta, m) : 0;
                 const int p = wb + lane;
                 const int k = p - ms;
                 const bool is_copy = k >= 0 && p < hi;
+                const bool is_lit = kPacked && !is_copy && p >= pos_base && p < hi;   // a literal of this batch: fetched from the packed literals; the window is written whole
                 int back = md;                                       // source = p - back
                 if (is_copy && k >= md) back = k - k % md + md;      // dist < len: fold onto the first period
                 const bool far = is_copy && back > lane;            // source lies before this window: final already
                 const bool near = is_copy && back <= lane;          // source is a byte of this window
                 uint8_t v = 0;
                 if (far) v = *(pp - back);
+                if (is_lit) v = *(lit_top - (p + ld));
                 if (__any_sync(full, near)) {
                     // sources inside the window: every lane follows its source lane to a root (a byte that is final:
                     // a literal, a byte of an earlier batch, or a far copy) by pointer doubling, then takes its value
-                    if (!is_copy && p >= 0 && p < hi) v = *pp;
+                    if (!is_copy && !is_lit && p >= 0 && p < hi) v = *pp;
                     int root = near ? lane - back : lane;
 #pragma unroll
                     for (int r = 0; r < 5; r++) root = __shfl_sync(full, root, root);
                     v = (uint8_t)__shfl_sync(full, (int)v, root);
                 }
-                if (is_copy) *pp = v;
+                if (is_copy || is_lit) *pp = v;
                 __syncwarp();
             }
             pos_base = hi;
+        }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kResolveWarps * 32, kResolveCtasPerSm)
+lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_blocks, uint32_t* __restrict__ ticket,
+                    const uint32_t* __restrict__ tokens, const uint32_t* __restrict__ n_tokens) {
+    constexpr unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = (int)atomicAdd(ticket, 1u);
+        b = __shfl_sync(full, b, 0);
+        if (b >= n_blocks) return;
+        resolve_block<false>(out + blocks[b].dst, tokens + (size_t)b * kTokenCap, (int)n_tokens[b], lane);
+    }
+}
+
+// K1 fused (r2h): decode and resolve in ONE kernel, warp-specialised.  A CTA is 4 decode warps (warpgroup 0: the tables of 128 blocks in
+// shared memory, 152 registers per thread) + 12 resolve warps (warpgroups 1-3, 32 registers per thread); two CTAs per SM.  A decode lane
+// announces a finished block in `done_ring`; resolve warps take ring slots in order and wait for their slot to be filled.  Decode never
+// waits for resolve and every block in progress belongs to a resident CTA, so the waits end.  Why: as two kernels the pair runs as the
+// SUM of its stand-alone times (16.8 + 10.6 ms per 85 k blocks) although decode leaves 65 % of the issue slots idle -- its CTAs hold the
+// shared memory and most of the register file, so a concurrently launched resolve kernel only gets a few warps per SM; and between the
+// two kernels ~9.5 k blocks x 64 KB overflow L2, so resolve's match sources come back from HBM.  Here resolve runs in decode's idle
+// slots and picks a block up microseconds after it was decoded.
+constexpr int kFusedDecWarps = 4, kFusedResWarps = 12, kFusedThreads = (kFusedDecWarps + kFusedResWarps) * 32, kFusedCtasPerSm = 2;
+constexpr size_t kFusedSmem = kFusedDecWarps * ((kDecSmem + 127) / 128 * 128);
+constexpr uint32_t kFusedSpinLimit = 1u << 22;      // x ~0.5 us: a resolve warp gives up after ~2 s without progress (status word, no hang)
+
+__global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm)
+inflate_fused_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, int n_blocks,
+                     uint32_t* __restrict__ ticket /* [0] decode ticket, [1] ring tail, [2] ring head */, uint32_t* __restrict__ tokens,
+                     uint32_t* __restrict__ n_tokens, uint32_t* __restrict__ status_out, uint32_t* __restrict__ error_count,
+                     uint32_t* __restrict__ crc_expected, unsigned long long* __restrict__ done_ring) {
+    extern __shared__ __align__(128) uint16_t smem16[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < kFusedDecWarps) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;\n");
+        decode_warp<true>(smem16 + (size_t)warp * (((kDecSmem + 127) / 128 * 128) / 2), comp, out, blocks, n_blocks, ticket, tokens, n_tokens, status_out, error_count,
+                          crc_expected, done_ring, ticket + 1);
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
+        constexpr unsigned full = 0xffffffffu;
+        for (;;) {
+            uint32_t slot = 0;
+            if (lane == 0) slot = atomicAdd(ticket + 2, 1u);
+            slot = __shfl_sync(full, slot, 0);
+            if (slot >= (uint32_t)n_blocks) return;
+            unsigned long long v = 0;
+            if (lane == 0) {
+                uint32_t spins = 0;
+                while ((v = *((volatile unsigned long long*)(done_ring + slot))) == 0ull) {
+                    __nanosleep(400);
+                    if (++spins > kFusedSpinLimit) { v = ~0ull; break; }
+                }
+                __threadfence();        // the block's literals and tokens were written before the announcement
+            }
+            v = __shfl_sync(full, v, 0);
+            if (v == ~0ull) { if (lane == 0) atomicAdd(error_count, 1u); return; }     // (cannot happen: see above; a bound instead of a hang)
+            const int b = (int)(uint32_t)v - 1, nt = (int)(v >> 32);
+            resolve_block<true>(out + blocks[b].dst, tokens + (size_t)b * kTokenCap, nt, lane);
         }
     }
 }
@@ -597,9 +688,23 @@ inline int env_int(const char* name, int dflt, int lo, int hi) {
     return x < lo ? lo : x > hi ? hi : x;
 }
 
+// tickets: FOUR zeroed words (K1a / ring tail, K1b / ring head ... see below, K1c at [2], fused ring head at [3]).  d_ring (nb zeroed 64-bit words) selects
+// the fused kernel when MSD_FUSED=1.
+inline bool inflate_fused_enabled() { static const int on = env_int("MSD_FUSED", 0, 0, 1); return on != 0; }
 inline void launch_inflate(cudaStream_t s, const uint8_t* d_comp, uint8_t* d_out, const BlockDesc* d_desc, int nb, uint32_t* tickets,
                            uint32_t* d_tokens, uint32_t* d_ntok, uint32_t* d_status, uint32_t* d_error_count, uint32_t* d_crc,
-                           bool check_crc, cudaEvent_t comp_read, cudaEvent_t resolved = nullptr, cudaEvent_t decoded_trace = nullptr) {
+                           bool check_crc, cudaEvent_t comp_read, cudaEvent_t resolved = nullptr, cudaEvent_t decoded_trace = nullptr,
+                           unsigned long long* d_ring = nullptr) {
+    if (d_ring && inflate_fused_enabled()) {
+        cudaMemsetAsync(d_ring, 0, 8ull * (size_t)nb, s);
+        const int want = (nb + kFusedDecWarps * 32 - 1) / (kFusedDecWarps * 32), cap = kSMs * kFusedCtasPerSm;
+        inflate_fused_kernel<<<want < cap ? want : cap, kFusedThreads, kFusedSmem, s>>>(d_comp, d_out, d_desc, nb, tickets, d_tokens, d_ntok, d_status, d_error_count, d_crc, d_ring);
+        if (comp_read) cudaEventRecord(comp_read, s);
+        if (decoded_trace) cudaEventRecord(decoded_trace, s);
+        if (resolved) cudaEventRecord(resolved, s);
+        if (check_crc) launch_crc(s, d_out, d_desc, nb, tickets + 3, d_crc, d_status, d_error_count);
+        return;
+    }
     const int dec_cap = kSMs * env_int("MSD_DEC_CTAS", kDecCtasPerSm, 1, kDecCtasPerSm);
     const int dctas = (nb + kDecThreads - 1) / kDecThreads < dec_cap ? (nb + kDecThreads - 1) / kDecThreads : dec_cap;
     huffman_decode_kernel<<<dctas, kDecThreads, kDecSmem, s>>>(d_comp, d_out, d_desc, nb, tickets, d_tokens, d_ntok, d_status, d_error_count, d_crc);

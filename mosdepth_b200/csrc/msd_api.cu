@@ -84,7 +84,8 @@ struct msd_ctx {
     uint32_t *d_guess = nullptr, *d_seg = nullptr, *d_bstart = nullptr, *d_land = nullptr, *d_count = nullptr, *d_first = nullptr, *d_cnt = nullptr, *d_recbase = nullptr, *d_recoff = nullptr;
     uint32_t *d_status = nullptr, *d_ticket = nullptr, *d_inflate_err = nullptr;
     uint32_t* d_tokens[kSlots] = {}; uint32_t* d_ntok[kSlots] = {};   // match tokens between K1a and K1b
-    uint32_t* d_crc[kSlots] = {}; bool check_crc = true;              // CRC32 fields of the gzip trailers (K1c)
+    uint32_t* d_crc[kSlots] = {}; bool check_crc = true;
+    unsigned long long* d_ring[kSlots] = {};                          // fused K1 (MSD_FUSED=1): blocks announced by decode lanes, taken by resolve warps              // CRC32 fields of the gzip trailers (K1c)
     ChunkState* d_cs = nullptr; RunCounters* d_rc = nullptr;
     StageSet stage[kDescSets];   // h_desc / h_rel per descriptor set; h_bounce in the first kSlots sets only
     cudaEvent_t desc_free[kDescSets] = {}, crc_done[kDescSets] = {}, bounce_free[kSlots] = {}; bool bounce_used[kSlots] = {};
@@ -210,7 +211,7 @@ void free_chunk_buffers(msd_ctx* ctx) {
         ctx->stage[k].used = false;
     }
     for (int k = 0; k < ctx->n_slots; k++) {
-        dev_free(&ctx->d_comp[k]); dev_free(&ctx->d_infl[k]); dev_free(&ctx->d_tokens[k]); dev_free(&ctx->d_ntok[k]); dev_free(&ctx->d_crc[k]);
+        dev_free(&ctx->d_comp[k]); dev_free(&ctx->d_infl[k]); dev_free(&ctx->d_tokens[k]); dev_free(&ctx->d_ntok[k]); dev_free(&ctx->d_crc[k]); dev_free(&ctx->d_ring[k]);
         cudaEvent_t* evs[] = {&ctx->comp_free[k], &ctx->h2d_done[k], &ctx->infl_done[k], &ctx->infl_free[k], &ctx->bounce_free[k]};
         for (cudaEvent_t* e : evs) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
         ctx->bounce_used[k] = false;
@@ -227,6 +228,7 @@ int ensure_chunk_buffers(msd_ctx* ctx) {
         if ((rc = dev_alloc(ctx, &ctx->d_tokens[k], (uint64_t)ctx->max_blocks * kTokenCap))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_ntok[k], ctx->max_blocks))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_crc[k], ctx->max_blocks))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_ring[k], ctx->max_blocks))) return rc;
         MSD_CUDA_OK(cudaMemset(ctx->d_infl[k], 0, infl_bytes));
         cudaEvent_t* evs[] = {&ctx->comp_free[k], &ctx->h2d_done[k], &ctx->infl_done[k], &ctx->infl_free[k], &ctx->bounce_free[k]};
         for (cudaEvent_t* e : evs) MSD_CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
@@ -250,7 +252,7 @@ int ensure_chunk_buffers(msd_ctx* ctx) {
     if ((rc = dev_alloc(ctx, &ctx->d_recbase, nb))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_recoff, ctx->rec_cap))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_status, (uint64_t)ctx->n_slots * ctx->max_blocks))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_ticket, 3 * kSlots))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_ticket, 4 * kSlots))) return rc;
     ctx->check_crc = !getenv("MSD_NO_CRC");
     if ((rc = dev_alloc(ctx, &ctx->d_inflate_err, 4))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_cs, 1))) return rc;
@@ -596,6 +598,8 @@ int msd_create(int device, msd_ctx** out) {
     cudaFuncSetAttribute(huffman_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecSmem);
     cudaFuncSetAttribute(huffman_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(bgzf_crc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCrcSmem);
+    cudaFuncSetAttribute(inflate_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
+    cudaFuncSetAttribute(inflate_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (crc_upload_tables() != cudaSuccess) { delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cannot upload the CRC tables"); }
     // default filters = mosdepth defaults (-F 1796, -Q 0, no length limits, default mode)
     ctx->fp.mapq = 0; ctx->fp.min_len = -1; ctx->fp.max_len = INT64_MAX; ctx->fp.eflag = 1796; ctx->fp.iflag = 0; ctx->fp.mode = MSD_MODE_DEFAULT; ctx->fp.n_rg = 0; ctx->fp.rg_names = nullptr;
@@ -970,11 +974,11 @@ int msd_run(msd_ctx* ctx) {
             cudaEvent_t f0 = next_event(ctx);
             cudaEvent_t tr0 = trace ? next_event(ctx) : nullptr;
             MSD_CUDA_OK(cudaStreamWaitEvent(si, ctx->infl_free[k], 0));      // consumers of the previous contents of d_infl[k] are done
-            MSD_CUDA_OK(cudaMemsetAsync(ctx->d_ticket + 3 * k, 0, 12, si));
+            MSD_CUDA_OK(cudaMemsetAsync(ctx->d_ticket + 4 * k, 0, 16, si));
             MSD_CUDA_OK(cudaEventRecord(e0, si));
-            launch_inflate(si, d_comp, infl_buf, ctx->d_desc[kd], (int)nb, ctx->d_ticket + 3 * k, ctx->d_tokens[k], ctx->d_ntok[k],
-                           ctx->d_status + (size_t)k * ctx->max_blocks, ctx->d_inflate_err, ctx->d_crc[k], ctx->check_crc, ctx->comp_free[k], ctx->infl_done[k], tr0);
-            ctx->info.n_launches += ctx->check_crc ? 3 : 2; ctx->info.n_inflate_launches++;
+            launch_inflate(si, d_comp, infl_buf, ctx->d_desc[kd], (int)nb, ctx->d_ticket + 4 * k, ctx->d_tokens[k], ctx->d_ntok[k],
+                           ctx->d_status + (size_t)k * ctx->max_blocks, ctx->d_inflate_err, ctx->d_crc[k], ctx->check_crc, ctx->comp_free[k], ctx->infl_done[k], tr0, ctx->d_ring[k]);
+            ctx->info.n_launches += (ctx->check_crc ? 1 : 0) + (inflate_fused_enabled() ? 1 : 2); ctx->info.n_inflate_launches++;
             MSD_CUDA_OK(cudaEventRecord(e1, si));
             MSD_CUDA_OK(cudaEventRecord(ctx->crc_done[kd], si));
             MSD_CUDA_OK(cudaStreamWaitEvent(sc, ctx->infl_done[k], 0));
@@ -1463,25 +1467,25 @@ int64_t msd_debug_inflate(msd_ctx* ctx, const void* bgzf_bytes, uint64_t n_bytes
     }
     if (infl > out_cap) return ctx_fail(ctx, MSD_EINVAL, "msd_debug_inflate: need %llu bytes", (unsigned long long)infl);
     if (desc.empty()) return 0;
-    uint8_t *d_c = nullptr, *d_o = nullptr; BlockDesc* d_d = nullptr; uint32_t *d_s = nullptr, *d_t = nullptr, *d_tok = nullptr, *d_nt = nullptr, *d_cr = nullptr;
+    uint8_t *d_c = nullptr, *d_o = nullptr; BlockDesc* d_d = nullptr; uint32_t *d_s = nullptr, *d_t = nullptr, *d_tok = nullptr, *d_nt = nullptr, *d_cr = nullptr; unsigned long long* d_rg = nullptr;
     int rc;
     if ((rc = dev_alloc(ctx, &d_c, n_bytes + 256)) || (rc = dev_alloc(ctx, &d_o, infl + 256)) || (rc = dev_alloc(ctx, &d_d, desc.size())) ||
-        (rc = dev_alloc(ctx, &d_s, desc.size())) || (rc = dev_alloc(ctx, &d_t, 4)) || (rc = dev_alloc(ctx, &d_tok, desc.size() * (uint64_t)kTokenCap)) ||
-        (rc = dev_alloc(ctx, &d_nt, desc.size())) || (rc = dev_alloc(ctx, &d_cr, desc.size()))) { dev_free(&d_c); dev_free(&d_o); dev_free(&d_d); dev_free(&d_s); dev_free(&d_t); dev_free(&d_tok); dev_free(&d_nt); dev_free(&d_cr); return rc; }
+        (rc = dev_alloc(ctx, &d_s, desc.size())) || (rc = dev_alloc(ctx, &d_t, 8)) || (rc = dev_alloc(ctx, &d_tok, desc.size() * (uint64_t)kTokenCap)) ||
+        (rc = dev_alloc(ctx, &d_nt, desc.size())) || (rc = dev_alloc(ctx, &d_cr, desc.size())) || (rc = dev_alloc(ctx, &d_rg, desc.size()))) { dev_free(&d_c); dev_free(&d_o); dev_free(&d_d); dev_free(&d_s); dev_free(&d_t); dev_free(&d_tok); dev_free(&d_nt); dev_free(&d_cr); dev_free(&d_rg); return rc; }
     cudaStream_t sc = ctx->s_compute;
     cudaMemcpyAsync(d_c, F, n_bytes, cudaMemcpyHostToDevice, sc);
     cudaMemcpyAsync(d_d, desc.data(), sizeof(BlockDesc) * desc.size(), cudaMemcpyHostToDevice, sc);
-    cudaMemsetAsync(d_t, 0, 16, sc);
+    cudaMemsetAsync(d_t, 0, 32, sc);
     const int nb = (int)desc.size();
-    launch_inflate(sc, d_c, d_o, d_d, nb, d_t, d_tok, d_nt, d_s, d_t + 3, d_cr, !getenv("MSD_NO_CRC"), nullptr);   // tickets: d_t[0..2]; error count: d_t[3]
+    launch_inflate(sc, d_c, d_o, d_d, nb, d_t, d_tok, d_nt, d_s, d_t + 4, d_cr, !getenv("MSD_NO_CRC"), nullptr, nullptr, nullptr, d_rg);   // tickets: d_t[0..3]; error count: d_t[4]
     cudaError_t e = cudaGetLastError();
     uint32_t errs[2] = {0, 0};
-    if (e == cudaSuccess) e = cudaMemcpyAsync(errs, d_t + 2, 8, cudaMemcpyDeviceToHost, sc);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(errs, d_t + 3, 8, cudaMemcpyDeviceToHost, sc);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, infl, cudaMemcpyDeviceToHost, sc);
     if (e == cudaSuccess) e = cudaStreamSynchronize(sc);
     std::vector<uint32_t> status(desc.size());
     if (e == cudaSuccess && errs[1]) cudaMemcpy(status.data(), d_s, 4 * desc.size(), cudaMemcpyDeviceToHost);
-    dev_free(&d_c); dev_free(&d_o); dev_free(&d_d); dev_free(&d_s); dev_free(&d_t); dev_free(&d_tok); dev_free(&d_nt); dev_free(&d_cr);
+    dev_free(&d_c); dev_free(&d_o); dev_free(&d_d); dev_free(&d_s); dev_free(&d_t); dev_free(&d_tok); dev_free(&d_nt); dev_free(&d_cr); dev_free(&d_rg);
     if (e != cudaSuccess) return ctx_fail(ctx, MSD_ECUDA, "msd_debug_inflate: %s", cudaGetErrorString(e));
     if (errs[1]) { size_t b = 0; while (b < status.size() && !status[b]) b++; return ctx_fail(ctx, MSD_EDATA, "%u block(s) failed to inflate; first: block %zu status %u", errs[1], b, b < status.size() ? status[b] : 0u); }
     return (int64_t)infl;

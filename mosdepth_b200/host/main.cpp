@@ -372,6 +372,12 @@ int main(int argc, char** argv) {
         printf("]}\n");
         return 0;
     }
+    if (n_gpus > 1) {      // N ingest pumps share the host: each gets its share of the cores and a smaller pinned ring (cudaMallocHost is serialised by the driver: 0.45 s per GB)
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        if (!getenv("MSD_INGEST_THREADS")) setenv("MSD_INGEST_THREADS", std::to_string(std::max(2u, hw / (2u * (unsigned)n_gpus))).c_str(), 0);
+        if (!getenv("MSD_BOUNCE_MB")) setenv("MSD_BOUNCE_MB", "16", 0);
+        if (!getenv("MSD_BOUNCE_PIECES")) setenv("MSD_BOUNCE_PIECES", "4", 0);
+    }
     uint8_t comm_id[MSD_COMM_ID_BYTES];
     if (n_gpus > 1 && msd_comm_unique_id(comm_id) != 0) die(1, "[mosdepth] %s", msd_last_error(nullptr));
     std::vector<std::thread> comm_threads((size_t)n_gpus); std::vector<int> comm_rc((size_t)n_gpus, 0);

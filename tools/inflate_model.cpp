@@ -88,9 +88,10 @@ struct RingReader {
 
 static const uint8_t cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-// K1a for one block: literals into dst, matches into tok.  Returns status.
+// K1a for one block: literals, packed in stream order, into `lits` (the kernel: downwards from the top of the block's token region),
+// matches into tok, a final skip token for the literals behind the last match.  Returns status.
 template <class Reader>
-static uint32_t decode_block(const uint8_t* comp_aligned, uint32_t lead, uint32_t clen, uint32_t isize, uint8_t* dst, std::vector<uint32_t>& tok) {
+static uint32_t decode_block(const uint8_t* comp_aligned, uint32_t lead, uint32_t clen, uint32_t isize, std::vector<uint8_t>& lits, std::vector<uint32_t>& tok, bool packed, uint8_t* dst) {
     const uint32_t total_words = std::max((lead + clen + 3) / 4, 1u);
     Reader br(comp_aligned, total_words);
     br.seed(lead);
@@ -108,7 +109,7 @@ static uint32_t decode_block(const uint8_t* comp_aligned, uint32_t lead, uint32_
             const uint32_t sp = br.byte_pos();
             if ((len ^ 0xffffu) != nlen || sp + len > lead + clen) return kBadStored;
             if (outp + len > isize) return kOverflow;
-            memcpy(dst + outp, comp_aligned + sp, len);
+            if (packed) lits.insert(lits.end(), comp_aligned + sp, comp_aligned + sp + len); else memcpy(dst + outp, comp_aligned + sp, len);
             outp += len;
             br.seed(sp + len);
             continue;
@@ -166,7 +167,7 @@ static uint32_t decode_block(const uint8_t* comp_aligned, uint32_t lead, uint32_
             const uint32_t x = (e >> 4) & 7u;
             const uint32_t ext = (lo >> (l1 + 1)) & ((1u << x) - 1u);
             br.drop((int)(l1 + 1 + x));
-            if ((e & 0x83u) == kEntNotLen) { if (outp >= isize) return kOverflow; dst[outp++] = (uint8_t)(e >> 8); continue; }
+            if ((e & 0x83u) == kEntNotLen) { if (outp >= isize) return kOverflow; if (packed) lits.push_back((uint8_t)(e >> 8)); else dst[outp] = (uint8_t)(e >> 8); outp++; continue; }
             if (e & kEntNotLen) { if (e == kEntEob) break; return kBadSymbol; }
             const uint32_t len = 3u + (e >> 8) + ext;
             br.refill_before_distance();
@@ -185,17 +186,19 @@ static uint32_t decode_block(const uint8_t* comp_aligned, uint32_t lead, uint32_
             tok.push_back(make_token(lit_run, len, dist)); outp += len; run_base = outp;
         }
     }
-    return outp == isize ? kOk : kShort;
+    if (outp != isize) return kShort;
+    if (packed && outp > run_base) tok.push_back((kTokSkip << 23) | (outp - run_base));      // the literals behind the last match
+    return kOk;
 }
 
 // K1b for one block, lane by lane with the kernel's batch/window/round schedule (31 tokens in lanes 1..31, lane 0 a
 // sentinel).  `mis` plays the output misalignment.
-static void resolve_block(uint8_t* dst, const std::vector<uint32_t>& tok, int mis) {
+static void resolve_block(uint8_t* dst, const std::vector<uint32_t>& tok, const std::vector<uint8_t>& lits, int mis, bool packed) {
     const int nt = (int)tok.size();
-    int pos_base = 0;
+    int pos_base = 0, lit_base = 0;
     for (int t0 = 0; t0 < nt; t0 += 31) {
-        int lr[32], dist[32], adv[32], incl[32], start[32], mstart[32], head_win[32]; uint32_t head_bit[32];
-        int run = 0;
+        int lr[32], dist[32], adv[32], incl[32], start[32], mstart[32], head_win[32], ldelta[32]; uint32_t head_bit[32];
+        int run = 0, lrun = 0;
         for (int lane = 0; lane < 32; lane++) {
             lr[lane] = dist[lane] = adv[lane] = 0; bool is_match = false;
             if (lane >= 1 && t0 + lane - 1 < nt) {
@@ -206,6 +209,8 @@ static void resolve_block(uint8_t* dst, const std::vector<uint32_t>& tok, int mi
             }
             run += adv[lane]; incl[lane] = run;
             start[lane] = pos_base + incl[lane] - adv[lane]; mstart[lane] = is_match ? start[lane] + lr[lane] : 0x3fffffff;
+            ldelta[lane] = (lit_base + lrun) - start[lane];        // literal index of byte p of this token's literal run = p + ldelta
+            lrun += lr[lane];
         }
         const int total = incl[31], hi = pos_base + total;
         const int wb0 = ((pos_base + mis) & ~31) - mis;
@@ -214,13 +219,15 @@ static void resolve_block(uint8_t* dst, const std::vector<uint32_t>& tok, int mi
         for (int wb = wb0; wb < hi; wb += 32, j++) {
             uint32_t heads = 0;
             for (int lane = 0; lane < 32; lane++) if (head_win[lane] == j) heads |= head_bit[lane];
-            bool far[32], near[32]; int back[32]; uint8_t v[32];
+            bool far[32], near[32], is_lit[32]; int back[32]; uint8_t v[32];
             for (int lane = 0; lane < 32; lane++) {
                 const uint32_t le = 0xffffffffu >> (31 - lane);
                 const int p = wb + lane, m = before + __builtin_popcount(heads & le);
                 const int ms = mstart[m], md = dist[m];
                 const int k = p - ms;
                 const bool is_copy = k >= 0 && p < hi;
+                is_lit[lane] = packed && !is_copy && p >= pos_base && p < hi;
+                if (is_lit[lane]) v[lane] = lits[(size_t)(p + ldelta[m])];
                 back[lane] = md;
                 if (is_copy && k >= md) back[lane] = k - k % md + md;
                 far[lane] = is_copy && back[lane] > lane; near[lane] = is_copy && back[lane] <= lane;
@@ -233,7 +240,7 @@ static void resolve_block(uint8_t* dst, const std::vector<uint32_t>& tok, int mi
                 int root[32];
                 for (int lane = 0; lane < 32; lane++) {
                     const int p = wb + lane;
-                    if (!far[lane] && !near[lane] && p >= 0 && p < hi) v[lane] = dst[p];
+                    if (!far[lane] && !near[lane] && !is_lit[lane] && p >= 0 && p < hi) v[lane] = dst[p];      // a byte of an earlier batch
                     root[lane] = near[lane] ? lane - back[lane] : lane;
                 }
                 for (int r = 0; r < 5; r++) { int nr[32]; for (int lane = 0; lane < 32; lane++) nr[lane] = root[root[lane]]; memcpy(root, nr, sizeof nr); }
@@ -241,9 +248,9 @@ static void resolve_block(uint8_t* dst, const std::vector<uint32_t>& tok, int mi
                 for (int lane = 0; lane < 32; lane++) nv[lane] = v[root[lane]];
                 memcpy(v, nv, sizeof nv);
             }
-            for (int lane = 0; lane < 32; lane++) if (far[lane] || near[lane]) dst[wb + lane] = v[lane];
+            for (int lane = 0; lane < 32; lane++) if (far[lane] || near[lane] || is_lit[lane]) dst[wb + lane] = v[lane];
         }
-        pos_base = hi;
+        pos_base = hi; lit_base += lrun;
     }
 }
 
@@ -327,19 +334,26 @@ int main(int argc, char** argv) {
             std::vector<uint32_t> tok;
             const int mis = (int)(nblk % 32);
             std::fill(got.begin(), got.end(), 0xEE);
-            const uint32_t st = decode_block<BitReader>(raw.data() + 8, lead, clen, isize, got.data() + mis, tok);
-            {   // the second reader must produce the same literals, tokens and status
-                std::vector<uint32_t> tok2; static std::vector<uint8_t> got2(65536 + 64 + 32);
-                std::fill(got2.begin(), got2.end(), 0xEE);
-                const uint32_t st2 = decode_block<RingReader>(raw.data() + 8, lead, clen, isize, got2.data() + mis, tok2);
-                if (st2 != st || tok2 != tok || memcmp(got2.data(), got.data(), got2.size()) != 0) { bad++; fprintf(stderr, "block %ld (lead %d): BitReader2 disagrees (status %u vs %u, %zu vs %zu tokens)\n", nblk, lead, st2, st, tok2.size(), tok.size()); if (bad > 5) return 1; }
-            }
-            if (st == kOk) resolve_block(got.data() + mis, tok, mis);
-            if (st != kOk || memcmp(got.data() + mis, want.data(), isize) != 0) {
-                bad++;
-                size_t d = 0; while (d < isize && got[mis + d] == want[d]) d++;
-                fprintf(stderr, "block %ld (lead %d): status %u, first difference at %zu of %u\n", nblk, lead, st, d, isize);
-                if (bad > 5) return 1;
+            uint32_t st = kOk;
+            for (int packed = 0; packed < 2; packed++) {       // 0: literals in place (the two-kernel pipeline); 1: packed literals (the fused kernel)
+                tok.clear();
+                std::fill(got.begin(), got.end(), 0xEE);
+                std::vector<uint8_t> lits;
+                st = decode_block<BitReader>(raw.data() + 8, lead, clen, isize, lits, tok, packed != 0, got.data() + mis);
+                {   // the second reader must produce the same literals, tokens and status
+                    std::vector<uint32_t> tok2; std::vector<uint8_t> lits2; static std::vector<uint8_t> got2(65536 + 64 + 32);
+                    std::fill(got2.begin(), got2.end(), 0xEE);
+                    const uint32_t st2 = decode_block<RingReader>(raw.data() + 8, lead, clen, isize, lits2, tok2, packed != 0, got2.data() + mis);
+                    if (st2 != st || tok2 != tok || lits2 != lits || memcmp(got2.data(), got.data(), got2.size()) != 0) { bad++; fprintf(stderr, "block %ld (lead %d): BitReader2 disagrees (status %u vs %u, %zu vs %zu tokens)\n", nblk, lead, st2, st, tok2.size(), tok.size()); if (bad > 5) return 1; }
+                }
+                if (st == kOk) resolve_block(got.data() + mis, tok, lits, mis, packed != 0);
+                if (st == kOk && lits.size() + 4 * tok.size() > (size_t)kTokenCap * 4) { fprintf(stderr, "literals and tokens do not fit the block's token region\n"); return 1; }
+                if (st != kOk || memcmp(got.data() + mis, want.data(), isize) != 0) {
+                    bad++;
+                    size_t d = 0; while (d < isize && got[mis + d] == want[d]) d++;
+                    fprintf(stderr, "block %ld (lead %d, packed %d): status %u, first difference at %zu of %u\n", nblk, lead, packed, st, d, isize);
+                    if (bad > 5) return 1;
+                }
             }
             if ((int)tok.size() > kTokenCap) { fprintf(stderr, "token cap exceeded\n"); return 1; }
             if (lead == 0) {     // K1c: the block's CRC-32 by the row-strided formulation against the gzip trailer, at a varying alignment
