@@ -545,7 +545,17 @@ lz77_resolve_kernel(uint8_t* out, const BlockDesc* __restrict__ blocks, int n_bl
 // shared memory and most of the register file, so a concurrently launched resolve kernel only gets a few warps per SM; and between the
 // two kernels ~9.5 k blocks x 64 KB overflow L2, so resolve's match sources come back from HBM.  Here resolve runs in decode's idle
 // slots and picks a block up microseconds after it was decoded.
-constexpr int kFusedDecWarps = 4, kFusedResWarps = 12, kFusedThreads = (kFusedDecWarps + kFusedResWarps) * 32, kFusedCtasPerSm = 2;
+#ifndef MSD_FUSED_RES_WARPS
+#define MSD_FUSED_RES_WARPS 12       // resolve warps per CTA (a multiple of 4: setmaxnreg works on warpgroups)
+#endif
+#ifndef MSD_FUSED_DEC_REGS
+#define MSD_FUSED_DEC_REGS 152       // registers per decode thread after setmaxnreg.inc
+#endif
+constexpr int kFusedDecWarps = 4, kFusedResWarps = MSD_FUSED_RES_WARPS, kFusedThreads = (kFusedDecWarps + kFusedResWarps) * 32, kFusedCtasPerSm = 2;
+// setmaxnreg.inc waits until the CTA's pool holds the registers: what the resolve warps give back (launch allocation - 32 each) must cover what
+// the decode warps ask for, or the kernel hangs (r2i: 20 resolve warps + 96 decode registers = 40 at launch, 160 returned, 224 wanted).
+constexpr int kFusedLaunchRegs = (65536 / (kFusedCtasPerSm * kFusedThreads)) / 8 * 8;
+static_assert(kFusedResWarps * (kFusedLaunchRegs - 32) >= kFusedDecWarps * (MSD_FUSED_DEC_REGS - kFusedLaunchRegs), "fused inflate: the decode warps would wait for registers that are never released");
 constexpr size_t kFusedSmem = kFusedDecWarps * ((kDecSmem + 127) / 128 * 128);
 constexpr uint32_t kFusedSpinLimit = 1u << 22;      // x ~0.5 us: a resolve warp gives up after ~2 s without progress (status word, no hang)
 
@@ -557,7 +567,7 @@ inflate_fused_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ out
     extern __shared__ __align__(128) uint16_t smem16[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp < kFusedDecWarps) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;\n");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(MSD_FUSED_DEC_REGS));
         decode_warp<true>(smem16 + (size_t)warp * (((kDecSmem + 127) / 128 * 128) / 2), comp, out, blocks, n_blocks, ticket, tokens, n_tokens, status_out, error_count,
                           crc_expected, done_ring, ticket + 1);
     } else {
@@ -637,37 +647,69 @@ bgzf_crc_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ b
         return lk(b0, 0) ^ lk(b1, 1) ^ lk(b2, 2) ^ lk(b3, 3);
     };
     auto t0 = [&](uint32_t i) -> uint32_t { return T0[i]; };
-    for (;;) {
-        int b = 0;
-        if (lane == 0) b = (int)atomicAdd(ticket, 1u);
-        b = __shfl_sync(full, b, 0);
-        if (b >= n_blocks) return;
-        if (status[b] != kOk) continue;                         // already failed in K1a
-        const uint32_t n = blocks[b].isize;
-        const uint8_t* p = out + blocks[b].dst;
-        const uint32_t pad = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u), n2 = n + pad, R = n2 / kCrcRow, tail = n2 % kCrcRow;
-        const uint4* q = reinterpret_cast<const uint4*>(p - pad) + lane;
-        uint32_t d[4] = {0u, 0u, 0u, 0u};
-        if (R && pad && lane == 0) {                            // the bytes in front of the message cancel themselves
-            const uint4 v = __ldg(q);
-            const CrcWords c = crc_head_cancel(CrcWords{v.x, v.y, v.z, v.w}, 0, pad);
+    // Software pipeline (r2i).  kCrcDepth rows of a block live in registers; a row's registers are loaded again (kCrcDepth rows further
+    // on) right after the row is folded, so every warp keeps kCrcDepth x 512 bytes of loads in flight all the time (r1m issued eight
+    // rows, folded them, and only then issued the next eight: the DRAM latency was paid once per 4 KB and the kernel stopped at 58-60 %
+    // of the HBM rate).  The warp also holds two tickets: the descriptor of the next block is read while this one streams, its first
+    // rows are requested before this block's serial epilogue (28 dependent table steps + three 32-step products), and the ticket
+    // after that is in flight the whole time.
+    struct Blk { int b; bool ok; uint32_t n, pad, n2, R, tail; const uint4* q; };
+    auto fetch = [&](int b) -> Blk {
+        Blk k; k.b = b; k.ok = false; k.n = 0; k.pad = 0; k.n2 = 0; k.R = 0; k.tail = 0; k.q = nullptr;
+        if (b < n_blocks && status[b] == kOk) {                 // (a block that already failed in K1a is skipped)
+            k.ok = true; k.n = blocks[b].isize;
+            const uint8_t* p = out + blocks[b].dst;
+            k.pad = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u); k.n2 = k.n + k.pad; k.R = k.n2 / kCrcRow; k.tail = k.n2 % kCrcRow;
+            k.q = reinterpret_cast<const uint4*>(p - k.pad) + lane;
+        }
+        return k;
+    };
+    constexpr int kCrcDepth = 16;
+    uint4 buf[kCrcDepth];
+    auto load_first = [&](const Blk& k) {
+#pragma unroll
+        for (int j = 0; j < kCrcDepth; j++) if ((uint32_t)j < k.R) buf[j] = __ldg(k.q + (size_t)j * 32);
+    };
+    uint32_t d[4];
+    int b0 = 0, b1 = 0;
+    if (lane == 0) { b0 = (int)atomicAdd(ticket, 1u); b1 = (int)atomicAdd(ticket, 1u); }
+    b0 = __shfl_sync(full, b0, 0); b1 = __shfl_sync(full, b1, 0);
+    Blk cur = fetch(b0);
+    load_first(cur);
+    while (cur.b < n_blocks) {                                  // a warp's tickets ascend: nothing is left once one is out of range
+        const Blk nxt = fetch(b1);
+        int b2 = 0;
+        if (lane == 0) b2 = (int)atomicAdd(ticket, 1u);
+        // the lane's 16 bytes of the tail row, requested now and used in the epilogue
+        uint4 tv = make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t g0 = cur.R * kCrcRow + (uint32_t)lane * 16u;
+        if (cur.ok && g0 < cur.n2) tv = __ldg(cur.q + (size_t)cur.R * 32);
+        d[0] = d[1] = d[2] = d[3] = 0u;
+        if (cur.R && cur.pad && lane == 0) {                    // the bytes in front of the message cancel themselves (row 0 is buf[0])
+            const CrcWords c = crc_head_cancel(CrcWords{buf[0].x, buf[0].y, buf[0].z, buf[0].w}, 0, cur.pad);
             d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
         }
-#pragma unroll 8
-        for (uint32_t r = 0; r < R; r++) {                      // eight rows (4 KB per warp) of loads in flight
-            const uint4 v = __ldg(q + r * 32);
-            d[0] = step(v.x ^ d[0]); d[1] = step(v.y ^ d[1]); d[2] = step(v.z ^ d[2]); d[3] = step(v.w ^ d[3]);
+        for (uint32_t r0 = 0; r0 < cur.R; r0 += kCrcDepth) {
+#pragma unroll
+            for (int j = 0; j < kCrcDepth; j++) {
+                const uint32_t r = r0 + j;
+                if (r < cur.R) { d[0] = step(buf[j].x ^ d[0]); d[1] = step(buf[j].y ^ d[1]); d[2] = step(buf[j].z ^ d[2]); d[3] = step(buf[j].w ^ d[3]); }
+                if (r + kCrcDepth < cur.R) buf[j] = __ldg(cur.q + (size_t)(r + kCrcDepth) * 32);
+            }
         }
-        CrcWords t{0u, 0u, 0u, 0u};
-        const uint32_t g0 = R * kCrcRow + (uint32_t)lane * 16u;
-        if (g0 < n2) { const uint4 v = __ldg(q + R * 32); t = crc_tail_keep(CrcWords{v.x, v.y, v.z, v.w}, g0, pad, n2); }
-        uint32_t v = crc_multmodp(xl, crc_lane_fold(d, t, t0));
-        v = __reduce_xor_sync(full, v);
-        const uint32_t crc = crc_finish(v, XA[tail], XA[n % kCrcRow], XBI[n / kCrcRow]);
-        if (lane == 0) {
-            if (crc_out) crc_out[b] = crc;
-            if (crc != crc_expected[b]) { status[b] = kBadCrc; atomicAdd(error_count, 1u); }
+        load_first(nxt);                                        // in flight during the epilogue
+        if (cur.ok) {
+            const CrcWords t = (g0 < cur.n2) ? crc_tail_keep(CrcWords{tv.x, tv.y, tv.z, tv.w}, g0, cur.pad, cur.n2) : CrcWords{0u, 0u, 0u, 0u};
+            uint32_t v = crc_multmodp(xl, crc_lane_fold(d, t, t0));
+            v = __reduce_xor_sync(full, v);
+            const uint32_t crc = crc_finish(v, XA[cur.tail], XA[cur.n % kCrcRow], XBI[cur.n / kCrcRow]);
+            if (lane == 0) {
+                if (crc_out) crc_out[cur.b] = crc;
+                if (crc != crc_expected[cur.b]) { status[cur.b] = kBadCrc; atomicAdd(error_count, 1u); }
+            }
         }
+        cur = nxt;
+        b1 = __shfl_sync(full, b2, 0);
     }
 }
 

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cerrno>
+#include <chrono>
 #include <climits>
 #include <cstdarg>
 #include <cstdlib>
@@ -505,11 +506,15 @@ static int compute_runs(msd_ctx* ctx, const int32_t* arr, uint32_t n, int32_t en
     }
     *n_runs_out = 0;
     if (n == 0) return 0;
+    const bool trace = getenv("MSD_TRACE") != nullptr;
+    const auto w0 = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count(); };
     runs_count_kernel<F><<<n_tiles, kRunThreads, 0, sc>>>(arr, n, f, ctx->d_tile_count);
     runs_scan_kernel<<<1, 1024, 0, sc>>>(ctx->d_tile_count, n_tiles, ctx->d_tile_base, ctx->d_run_total);
     unsigned long long total = 0;
     MSD_CUDA_OK(cudaMemcpyAsync(&total, ctx->d_run_total, 8, cudaMemcpyDeviceToHost, sc));
     MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    const double w_count = since();
     if (total > ctx->d_run_cap) {
         const uint64_t cap = total + total / 8 + 1024;
         if ((rc = dev_alloc(ctx, &ctx->d_run_start, cap))) return rc;
@@ -528,6 +533,7 @@ static int compute_runs(msd_ctx* ctx, const int32_t* arr, uint32_t n, int32_t en
         MSD_CUDA_OK(cudaMallocHost((void**)&ctx->h_run_val, cap * 4));
         ctx->h_run_cap = cap;
     }
+    const double w_alloc = since();
     runs_write_kernel<F><<<n_tiles, kRunThreads, 0, sc>>>(arr, n, f, ctx->d_tile_base, ctx->d_run_start, ctx->d_run_val);
     runs_stops_kernel<<<grid_for(total, 256, kSMs * 8), 256, 0, sc>>>(ctx->d_run_start, total, end, ctx->d_run_stop);
     ctx->launches += 4;
@@ -557,10 +563,14 @@ static int compute_runs(msd_ctx* ctx, const int32_t* arr, uint32_t n, int32_t en
         ctx->launches += 3;
         MSD_CUDA_OK(cudaGetLastError());
     }
+    if (trace) MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    const double w_write = since();
     MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_run_start, ctx->d_run_start, total * 4, cudaMemcpyDeviceToHost, sc));
     MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_run_stop, ctx->d_run_stop, total * 4, cudaMemcpyDeviceToHost, sc));
     MSD_CUDA_OK(cudaMemcpyAsync(ctx->h_run_val, ctx->d_run_val, total * 4, cudaMemcpyDeviceToHost, sc));
     MSD_CUDA_OK(cudaStreamSynchronize(sc));
+    if (trace) fprintf(stderr, "[msd trace] runs: %u cells -> %llu runs; count+scan %.3f ms, buffers %.3f, write+stops%s %.3f, copy to host (%.1f MB) %.3f\n", n, total, w_count, w_alloc - w_count,
+                       keep_labels >= 0 ? "+keep" : "", w_write - w_alloc, total * 12 / 1e6, since() - w_write);
     *n_runs_out = total;
     return 0;
 }
@@ -794,11 +804,23 @@ int msd_run(msd_ctx* ctx) {
     if (!ctx || !ctx->bytes) return ctx_fail(ctx, MSD_EINVAL, "msd_run: no input open");
     cudaSetDevice(ctx->device);
     int rc;
+    const bool trace = getenv("MSD_TRACE") != nullptr;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    double host_last = 0;
+    auto host_lap = [&](const char* what) {      // MSD_TRACE: where the HOST time of a run goes (allocations of the first run, planning, the launch loop)
+        if (!trace) return;
+        const double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+        fprintf(stderr, "[msd trace] host: %-28s %9.3f ms (at %9.3f)\n", what, now - host_last, now);
+        host_last = now;
+    };
     if ((rc = ensure_chunk_buffers(ctx))) return rc;
+    host_lap("chunk buffers");
     if ((rc = ensure_arena(ctx))) return rc;
+    host_lap("depth arena");
     if ((rc = ensure_query_buffers(ctx))) return rc;
     const bool default_mode = ctx->fp.mode == MSD_MODE_DEFAULT;
     if (default_mode && (rc = ensure_mate(ctx))) return rc;
+    host_lap("query + mate buffers");
     ctx->fp.n_targets = ctx->n_targets;
     ctx->ev_used = 0;
     memset(&ctx->info, 0, sizeof ctx->info);
@@ -806,7 +828,6 @@ int msd_run(msd_ctx* ctx) {
     for (auto& r : ctx->results) { r.have = false; r.dist.clear(); }
     cudaStream_t sc = ctx->s_compute, sx = ctx->s_copy;
     StageTimes times;
-    const bool trace = getenv("MSD_TRACE") != nullptr;
     cudaEvent_t ev_begin = next_event(ctx), ev_zero_end = next_event(ctx), ev_chunks_end = next_event(ctx), ev_end = next_event(ctx);
 
     MSD_CUDA_OK(cudaEventRecord(ev_begin, sc));
@@ -887,10 +908,12 @@ int msd_run(msd_ctx* ctx) {
             blocks.insert(blocks.end(), sb.begin(), sb.end());
         }
     }
+    host_lap("plan (BSIZE chase)");
     // pageable input: the bytes cross a ring of small pinned pieces on a thread of their own (IngestPump), up to n_slots - 1 chunks ahead
     bool any_copy = false; for (const Plan& P : plans) any_copy |= P.will_copy;
     const bool use_pump = any_copy && !ctx->src_pinned;
     if (use_pump && !ctx->pump) ctx->pump = new IngestPump(ctx->device, sx, ingest_threads, (size_t)env_u64("MSD_BOUNCE_MB", 32) << 20, (int)std::max<uint64_t>(2, env_u64("MSD_BOUNCE_PIECES", 8)));
+    host_lap("ingest pump");
     std::vector<uint64_t> ticket(plans.size(), 0); std::vector<cudaEvent_t> h2d_t0(plans.size(), nullptr), h2d_t1(plans.size(), nullptr);
     size_t enq = 0;
     auto enqueue_upto = [&](size_t limit) {      // chunk j may be copied once chunk j - n_slots has been launched (its decode kernel frees d_comp[k])
@@ -1024,6 +1047,7 @@ int msd_run(msd_ctx* ctx) {
         }
     }
     MSD_CUDA_OK(cudaEventRecord(ev_chunks_end, sc));
+    host_lap("chunk loop (launches)");
     MSD_CUDA_OK(cudaStreamSynchronize(sc));
     for (int k = 0; k < ctx->n_slots; k++) MSD_CUDA_OK(cudaStreamSynchronize(ctx->s_inflate[k]));   // the CRC kernels run beside framing and records
     // ---- errors raised by the kernels --------------------------------------------------------------------------
@@ -1040,6 +1064,7 @@ int msd_run(msd_ctx* ctx) {
     // ---- per contig: prefix sum + whole-contig stats -----------------------------------------------------------
     std::vector<unsigned long long> npre(ctx->n_targets);
     MSD_CUDA_OK(cudaMemcpy(npre.data(), ctx->d_nprefilter, sizeof(unsigned long long) * ctx->n_targets, cudaMemcpyDeviceToHost));
+    host_lap("wait for the device");
     cudaEvent_t s0 = next_event(ctx), s1 = next_event(ctx);
     MSD_CUDA_OK(cudaEventRecord(s0, sc));
     std::vector<unsigned long long> nbey(ctx->n_targets, 0);
@@ -1096,6 +1121,7 @@ int msd_run(msd_ctx* ctx) {
     MSD_CUDA_OK(cudaEventRecord(ev_end, sc));
     MSD_CUDA_OK(cudaStreamSynchronize(sc));
     if ((rc = collect_segments(ctx, ctx->d_arena, segs, seg_tid))) return rc;
+    host_lap("scans + windows + collect");
     float ms = 0;
     cudaEventElapsedTime(&ms, ev_begin, ev_end); ctx->info.ms_total = ms;
     cudaEventElapsedTime(&ms, ev_begin, ev_zero_end); ctx->info.ms_zero = ms;

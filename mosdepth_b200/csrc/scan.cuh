@@ -54,6 +54,15 @@ MSD_D void hist_add_keep(uint32_t* __restrict__ sh, unsigned long long* __restri
 
 struct SegStats { unsigned long long sum; uint32_t mn, mx; };
 
+constexpr int kLookGroups = 4;    // the look-back reads 4 x 32 tile states per probe
+MSD_D void prefetch_l2(const void* p) {
+#if defined(__CUDACC__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // block-reduce the per-thread stats into acc[slot], flush the shared histogram into hist_all[slot]; all threads call it
 MSD_D void seg_flush(SegStats& my, uint32_t* __restrict__ s_hist, unsigned long long* __restrict__ s_sum, uint32_t* __restrict__ s_mn, uint32_t* __restrict__ s_mx,
                      ContigAccum* __restrict__ acc, unsigned long long* __restrict__ hist) {
@@ -114,13 +123,18 @@ scan_segments_kernel(int32_t* __restrict__ arena, const ScanSeg* __restrict__ se
     int cur_seg = -1; bool cur_stats = false; uint32_t cur_slot = 0;
     __syncthreads();
     uint32_t tile = blockIdx.x;
-    for (;; tile += gridDim.x) {
-        if (kScan) {
-            if (t == 0) s_tile = atomicAdd(ticket, 1u);
-            __syncthreads();
-            tile = s_tile;
-        }
+    if (kScan) {
+        if (t == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        tile = s_tile;
+    }
+    for (;;) {
         if (tile >= n_tiles) break;
+        // the ticket of the NEXT tile is taken now and read at the end of this one: its latency hides behind the tile's loads, and warp 0
+        // can ask L2 for the next tile's lines while it waits in the look-back.  (Tickets still ascend per CTA and every tile with a
+        // smaller number belongs to a CTA that reaches it without waiting for a larger one, so the look-back cannot deadlock.)
+        uint32_t next_ticket = 0;
+        if (kScan && t == 0) next_ticket = atomicAdd(ticket, 1u);
         // the segment of this tile: the last one with first_tile <= tile (uniform across the CTA; a CTA's tiles ascend, so the
         // previous answer is right most of the time)
         int sg = cur_seg;
@@ -167,29 +181,52 @@ scan_segments_kernel(int32_t* __restrict__ arena, const ScanSeg* __restrict__ se
             uint32_t warp_excl = 0, tile_total = 0;
 #pragma unroll
             for (int w = 0; w < kScanThreads / 32; w++) { uint32_t x = s_warp[w]; if (w < warp) warp_excl += x; tile_total += x; }
-            // decoupled look-back by warp 0: lane l probes tile - 1 - l; tiles in front of the segment count as "inclusive prefix 0"
+            // decoupled look-back by warp 0.  One probe reads the states of the kLookGroups * 32 tiles in front (lane l of group g: tile
+            // k - 32 g - l); tiles in front of the segment count as "inclusive prefix 0".  The width matters: with T tiles per microsecond
+            // in flight and a probe round trip of p microseconds, a tile finds the nearest finished look-back T * (its own look-back
+            // time) tiles behind it, so a walk of 32 tiles per probe caps the kernel at 32 / p tiles per microsecond whatever the occupancy
+            // (r2c: 2.4-2.7 TB/s with 32-KB tiles, p = 0.4 us); 128 per probe lifts that cap above the HBM rate.
             if (warp == 0) {
                 uint32_t prefix = 0;
+                // ask L2 for the lines of this CTA's next tile (same segment only; 128 lines of 128 bytes, four per lane)
+                const uint32_t nt = __shfl_sync(0xffffffffu, next_ticket, 0);
+                if (nt < n_tiles && nt >= S.first_tile) {
+                    const uint64_t nb = (uint64_t)(nt - S.first_tile) * kScanTile;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint64_t c = nb + (uint64_t)(q * 32 + lane) * 32u;
+                        if (c < n_scan) prefetch_l2(arr + c);
+                    }
+                }
                 if (rel == 0) {
                     if (lane == 0) atomicExch(&tile_state[tile], (2ull << 32) | tile_total);
                 } else {
                     if (lane == 0) atomicExch(&tile_state[tile], (1ull << 32) | tile_total);
                     int64_t k = (int64_t)tile - 1;
-                    for (;;) {
-                        const int64_t idx = k - lane;
-                        unsigned long long s = (2ull << 32);
-                        if (idx >= (int64_t)S.first_tile) s = *((volatile unsigned long long*)&tile_state[idx]);
-                        const uint32_t flag = (uint32_t)(s >> 32);
-                        const unsigned ready = __ballot_sync(0xffffffffu, flag != 0), incl = __ballot_sync(0xffffffffu, flag == 2);
-                        const int f = incl ? __ffs((int)incl) - 1 : 32;                       // nearest tile that knows its inclusive prefix
-                        const unsigned need = f >= 31 ? 0xffffffffu : ((2u << f) - 1u);       // lanes 0..f (all 32 when none does)
-                        if ((ready & need) != need) continue;                                  // some tile in between has not published yet
-                        uint32_t val = (lane <= f) ? (uint32_t)s : 0u;
+                    bool done = false;
+                    while (!done) {
+                        unsigned long long s[kLookGroups];
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
-                        prefix += __shfl_sync(0xffffffffu, val, 0);
-                        if (f < 32) break;
-                        k -= 32;
+                        for (int g = 0; g < kLookGroups; g++) {
+                            const int64_t idx = k - 32 * g - lane;
+                            s[g] = (2ull << 32);
+                            if (idx >= (int64_t)S.first_tile) s[g] = *((volatile unsigned long long*)&tile_state[idx]);
+                        }
+                        bool stall = false;
+#pragma unroll
+                        for (int g = 0; g < kLookGroups; g++) {
+                            if (done || stall) continue;                                           // (warp-uniform)
+                            const uint32_t flag = (uint32_t)(s[g] >> 32);
+                            const unsigned ready = __ballot_sync(0xffffffffu, flag != 0), incl = __ballot_sync(0xffffffffu, flag == 2);
+                            const int f = incl ? __ffs((int)incl) - 1 : 32;                       // nearest tile that knows its inclusive prefix
+                            const unsigned need = f >= 31 ? 0xffffffffu : ((2u << f) - 1u);       // lanes 0..f (all 32 when none does)
+                            if ((ready & need) != need) { stall = true; continue; }                // some tile in between has not published yet
+                            uint32_t val = (lane <= f) ? (uint32_t)s[g] : 0u;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
+                            prefix += __shfl_sync(0xffffffffu, val, 0);
+                            if (f < 32) done = true; else k -= 32;
+                        }
                     }
                     if (lane == 0) atomicExch(&tile_state[tile], (2ull << 32) | (uint32_t)(prefix + tile_total));
                 }
@@ -212,7 +249,11 @@ scan_segments_kernel(int32_t* __restrict__ arena, const ScanSeg* __restrict__ se
             }
             if (cur_stats) seg_stats4(x, idx, S.n_stat, my, s_hist, hist);
         }
-        if (kScan) __syncthreads();   // s_tile / s_warp / s_prefix reuse
+        if (kScan) {
+            if (t == 0) s_tile = next_ticket;
+            __syncthreads();              // s_tile is written; s_warp / s_prefix may be reused
+            tile = s_tile;
+        } else tile += gridDim.x;
     }
     if (cur_stats) seg_flush(my, s_hist, s_sum, s_mn, s_mx, acc_all + cur_slot, hist_all + (size_t)cur_slot * kHistKeep);
 }

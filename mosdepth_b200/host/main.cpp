@@ -383,6 +383,7 @@ int main(int argc, char** argv) {
     std::vector<std::thread> comm_threads((size_t)n_gpus); std::vector<int> comm_rc((size_t)n_gpus, 0);
     auto join_comm = [&]() { for (int r = 0; r < n_gpus; r++) if (comm_threads[(size_t)r].joinable()) { comm_threads[(size_t)r].join(); if (comm_rc[(size_t)r] < 0) die(1, "[mosdepth] msd_comm_init: %s", msd_last_error(ctxs[(size_t)r])); } };
     uint32_t margin_bp = 65536;
+    double wall_create = 0, wall_run = 0;      // rank 0's msd_create (CUDA context) and msd_run (first-run allocations + the run), for MOSDEPTH_B200_STATS
     for (int attempt = 0;; attempt++) {
         if (n_gpus == 1) { shards.assign(1, {}); for (int t = 0; t < nt; t++) if (want[t] && t < (int)index.size() && index[t].has) shards[0].push_back(Piece{t, 0, tl[t], index[t].beg, index[t].end, 0, false}); }
         else shards = cut_contigs ? offset_shards(index, tl, want, n_gpus, window, margin_bp) : contig_shards(index, tl, want, n_gpus);
@@ -392,7 +393,9 @@ int main(int argc, char** argv) {
             msd_ctx*& ctx = ctxs[(size_t)r];
             auto fail = [&](const char* what) { rank_rc[(size_t)r] = -1; rank_err[(size_t)r] = std::string(what) + ": " + msd_last_error(ctx); };
             if (!ctx) {
+                const double tc0 = now_s();
                 if (msd_create(device + r, &ctx) != 0) { rank_rc[(size_t)r] = -1; rank_err[(size_t)r] = msd_last_error(nullptr); ctx = nullptr; return; }
+                if (r == 0) wall_create = now_s() - tc0;
                 if (msd_open(ctx, bam_path.c_str(), nt, tl.data(), H.first_voff) < 0) return fail("msd_open");
                 if (msd_set_filters(ctx, mapq, min_len, max_len, eflag, iflag, rgs.empty() ? nullptr : rgs.data(), (int)rgs.size(), mode) < 0) return fail("msd_set_filters");
                 // joining the NCCL communicator takes a few hundred milliseconds and is only needed after msd_run (spill exchange, totals):
@@ -412,7 +415,9 @@ int main(int argc, char** argv) {
             if (sb.empty()) { sb.push_back(1ull << 16); se.push_back(1ull << 16); }   // nothing indexed for this rank: read nothing
             if (msd_set_spans(ctx, (int)sb.size(), sb.data(), se.data()) < 0) return fail("msd_set_spans");
             if (by_digit && window && !use_median && msd_prefetch_windows(ctx, window) < 0) return fail("msd_prefetch_windows");   // --by <int>: every contig's window loop in one launch
+            const double tr0 = now_s();
             const int rc = msd_run(ctx);                                              // coverage() + to_coverage() for this rank's pieces
+            if (r == 0) wall_run = now_s() - tr0;
             if (rc < 0) { rank_rc[(size_t)r] = rc; rank_err[(size_t)r] = msd_last_error(ctx); }
         };
         if (n_gpus == 1) run_rank(0);
@@ -616,8 +621,8 @@ int main(int argc, char** argv) {
     if (getenv("MOSDEPTH_B200_STATS")) {
         unsigned long long recs = 0, blocks = 0; double dev_ms = 0;
         for (int r = 0; r < n_gpus; r++) { msd_run_info ri; msd_last_run_info(ctxs[(size_t)r], &ri); recs += ri.n_records; blocks += ri.n_blocks; dev_ms = std::max(dev_ms, ri.ms_total); }
-        fprintf(stderr, "[mosdepth-b200] {\"gpus\": %d, \"sharding\": \"%s\", \"records\": %llu, \"blocks\": %llu, \"device_ms_max\": %.3f, \"wall_s\": {\"parse_header_index\": %.3f, \"create_open_run\": %.3f, \"emit\": %.3f, \"totals_close\": %.3f}}\n",
-                n_gpus, n_gpus == 1 ? "none" : cut_contigs ? "offsets" : "contigs", recs, blocks, dev_ms, t_start - t_main, t_run - t_start, t_emit - t_run, t_close - t_emit);
+        fprintf(stderr, "[mosdepth-b200] {\"gpus\": %d, \"sharding\": \"%s\", \"records\": %llu, \"blocks\": %llu, \"device_ms_max\": %.3f, \"wall_s\": {\"parse_header_index\": %.3f, \"create_open_run\": %.3f, \"msd_create_rank0\": %.3f, \"msd_run_rank0\": %.3f, \"emit\": %.3f, \"totals_close\": %.3f}}\n",
+                n_gpus, n_gpus == 1 ? "none" : cut_contigs ? "offsets" : "contigs", recs, blocks, dev_ms, t_start - t_main, t_run - t_start, wall_create, wall_run, t_emit - t_run, t_close - t_emit);
     }
     // every output file is closed.  Tearing the contexts down by hand (cudaFree of ~20 GB, unpinning the ingest ring, destroying the CUDA
     // context) costs 0.3-0.7 s of wall clock for nothing: the process ends here and the driver reclaims everything.
