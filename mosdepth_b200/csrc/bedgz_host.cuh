@@ -4,6 +4,7 @@
 // host threads, copies as memcpy) -- under AddressSanitizer if one wishes.  The CRC step is passed in: K1c (bgzf_crc_kernel) in
 // the library, zlib in the emulation (K1c is inline PTX and has GPU tests of its own).
 #pragma once
+#include <chrono>
 #include <cstdarg>
 #include <vector>
 #include "../../include/mosdepth_b200.h"
@@ -64,12 +65,20 @@ int bz_run(BzBuffers& B, cudaStream_t sc, const char* chrom, const int32_t* d_st
     B.members.clear(); B.out_bytes = 0; B.launches = 0; B.err[0] = 0;
     if (n == 0) return 0;
     int rc;
+    const bool trace = getenv("MSD_TRACE") != nullptr;
+    const auto w0 = std::chrono::steady_clock::now(); double w_last = 0;
+    auto lap = [&](const char* what) {      // MSD_TRACE: host wall clock between the synchronisation points of the sequence
+        if (!trace) return;
+        const double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+        fprintf(stderr, "[msd trace] bgzf: %-34s %9.3f ms\n", what, now - w_last); w_last = now;
+    };
     // the contig's Huffman code, from a sample of its own lines (host: 65,536 lines at most)
     static_assert(sizeof(BzCodes) % 4 == 0, "BzCodes is copied as words");
     BzCodes codes;
     if (!bz_build_codes(chrom, h_st, h_en, h_dp, n, &codes, labels, n_labels))
         return bz_fail(B, MSD_EINVAL, "cannot build a code for contig '%s' (name longer than %d bytes, more than %d labels, a label longer than %d bytes, or a value without a label)", chrom,
                        kBzMaxName, kBzMaxLabels, kBzMaxLabel);
+    lap("code from a sample of the lines");
     // ---- per line: text length -> text offset ------------------------------------------------------------------------
     const uint64_t n_tiles = (n + kBzScanTile - 1) / kBzScanTile;
     BzCarve lay{nullptr};
@@ -92,6 +101,7 @@ int bz_run(BzBuffers& B, cudaStream_t sc, const char* chrom, const int32_t* d_st
     BZ_CUDA_OK(cudaMemcpyAsync(&text_total, d_totals + 0, 8, cudaMemcpyDeviceToHost, sc));
     BZ_CUDA_OK(cudaMemcpyAsync(&last_off, d_text_off + (n - 1), 8, cudaMemcpyDeviceToHost, sc));
     BZ_CUDA_OK(cudaStreamSynchronize(sc));
+    lap("line lengths + scan");
     const uint64_t nb = (uint64_t)bz_block_of(last_off) + 1;
     if (text_total == 0 || last_off >= text_total || nb > (1ull << 30)) return bz_fail(B, MSD_ECUDA, "msd_per_base_bgzf: text scan out of range (%llu bytes, last line at %llu)", text_total, last_off);
     // ---- per member: first line, text range, payload bytes -> member offset -----------------------------------------------
@@ -113,6 +123,7 @@ int bz_run(BzBuffers& B, cudaStream_t sc, const char* chrom, const int32_t* d_st
     ull bit_total = 0;
     BZ_CUDA_OK(cudaMemcpyAsync(&bit_total, d_totals + 1, 8, cudaMemcpyDeviceToHost, sc));
     BZ_CUDA_OK(cudaStreamSynchronize(sc));          // bz_blocks_kernel takes the totals by value
+    lap("members of lines, bits + scan");
     BZ_LAUNCH(bz_blocks_kernel, (unsigned)((nb + kBzThreads - 1) / kBzThreads), kBzThreads, sc, d_codes, (uint32_t)nb, n, d_blk_first, d_text_off, text_total, d_bit_off, bit_total,
               d_desc, d_payload, d_member_len);
     bz_scan(sc, d_member_len, nb, d_btsum, d_btbase, d_totals + 2, d_member_off);
@@ -121,6 +132,7 @@ int bz_run(BzBuffers& B, cudaStream_t sc, const char* chrom, const int32_t* d_st
     BZ_CUDA_OK(cudaGetLastError());
     BZ_CUDA_OK(cudaMemcpyAsync(&out_total, d_totals + 2, 8, cudaMemcpyDeviceToHost, sc));
     BZ_CUDA_OK(cudaStreamSynchronize(sc));
+    lap("member sizes + scan");
     if (out_total < 27 * nb || out_total > 65536ull * nb) return bz_fail(B, MSD_ECUDA, "msd_per_base_bgzf: member sizes out of range (%llu bytes in %llu members)", out_total, (ull)nb);
     // ---- output: zeroed, lines OR their bits in, the CRC step sums the text, members get their frames -----------------------
     if ((rc = bz_grow(B, &B.d_out, &B.out_cap, out_total + 64))) return rc;
@@ -130,6 +142,7 @@ int bz_run(BzBuffers& B, cudaStream_t sc, const char* chrom, const int32_t* d_st
         BZ_CUDA_OK(cudaMallocHost((void**)&B.h_out, cap));
         B.h_cap = cap;
     }
+    lap("output buffers");
     uint8_t* d_out = (uint8_t*)B.d_out;
     BZ_CUDA_OK(cudaMemsetAsync(d_out, 0, out_total + 64, sc));
     BZ_CUDA_OK(cudaMemsetAsync(d_text + text_total, 0, 512, sc));            // K1c reads whole 16-byte words
@@ -146,6 +159,7 @@ int bz_run(BzBuffers& B, cudaStream_t sc, const char* chrom, const int32_t* d_st
     BZ_CUDA_OK(cudaMemcpyAsync(h_len.data(), d_member_len, 4 * nb, cudaMemcpyDeviceToHost, sc));
     BZ_CUDA_OK(cudaMemcpyAsync(h_desc.data(), d_desc, sizeof(BlockDesc) * nb, cudaMemcpyDeviceToHost, sc));
     BZ_CUDA_OK(cudaStreamSynchronize(sc));
+    lap("emit + CRC + frames + copy to host");
     B.members.resize(nb);
     for (uint64_t b = 0; b < nb; b++) {
         msd_bgzf_member& m = B.members[b];
@@ -157,6 +171,7 @@ int bz_run(BzBuffers& B, cudaStream_t sc, const char* chrom, const int32_t* d_st
                            m.csize, (ull)m.first_run);
     }
     B.out_bytes = out_total;
+    lap("member table");
     return 0;
 }
 

@@ -422,7 +422,13 @@ int run_segments(msd_ctx* ctx, int32_t* base, std::vector<ScanSeg>& segs, bool s
         if (scan) {
             MSD_CUDA_OK(cudaMemsetAsync(ctx->d_tile_state, 0, n_tiles * 8, sc));
             MSD_CUDA_OK(cudaMemsetAsync(ctx->d_scan_ticket, 0, 4, sc));
-            scan_segments_kernel<true><<<grid, kScanThreads, 0, sc>>>(base, ctx->d_segs, n, (uint32_t)n_tiles, ctx->d_tile_state, ctx->d_scan_ticket, ctx->d_acc_all, ctx->d_hist_all);
+            // MSD_SCAN (A/B hook): 0 = the r2c kernel (every latency of a tile in sequence), 1 = the pipelined kernel (bulk asynchronous copies into a
+            // shared-memory ring, three tiles ahead), 4 = the same with a look-back that reads 128 tile states per probe
+            const uint64_t variant = env_u64("MSD_SCAN", 0);
+            const int pgrid = (int)std::min<uint64_t>(n_tiles, (uint64_t)kSMs * 4);
+            if (variant == 0) scan_segments_kernel<true><<<grid, kScanThreads, 0, sc>>>(base, ctx->d_segs, n, (uint32_t)n_tiles, ctx->d_tile_state, ctx->d_scan_ticket, ctx->d_acc_all, ctx->d_hist_all);
+            else if (variant == 4) scan_segments_pipe_kernel<4><<<pgrid, kScanThreads, kScanPipeSmem, sc>>>(base, ctx->d_segs, n, (uint32_t)n_tiles, ctx->d_tile_state, ctx->d_scan_ticket, ctx->d_acc_all, ctx->d_hist_all);
+            else scan_segments_pipe_kernel<1><<<pgrid, kScanThreads, kScanPipeSmem, sc>>>(base, ctx->d_segs, n, (uint32_t)n_tiles, ctx->d_tile_state, ctx->d_scan_ticket, ctx->d_acc_all, ctx->d_hist_all);
         } else
             scan_segments_kernel<false><<<grid, kScanThreads, 0, sc>>>(base, ctx->d_segs, n, (uint32_t)n_tiles, ctx->d_tile_state, ctx->d_scan_ticket, ctx->d_acc_all, ctx->d_hist_all);
         MSD_CUDA_OK(cudaGetLastError());
@@ -586,13 +592,23 @@ int msd_create(int device, msd_ctx** out) {
     if (!out) return MSD_EINVAL;
     *out = nullptr;
     int n = 0;
+    const bool trace = getenv("MSD_TRACE") != nullptr;
+    const auto c0 = std::chrono::steady_clock::now(); double c_last = 0;
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        const double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count();
+        fprintf(stderr, "[msd trace] create: %-26s %9.3f ms\n", what, now - c_last); c_last = now;
+    };
     cudaError_t e = cudaGetDeviceCount(&n);
+    lap("driver init (device count)");
     if (e != cudaSuccess || n <= 0) return ctx_fail(nullptr, MSD_ENODEV, "no CUDA device: %s (libmosdepth_b200 has no CPU fallback)", cudaGetErrorString(e));
     if (device < 0 || device >= n) return ctx_fail(nullptr, MSD_ENODEV, "device %d out of range (%d devices)", device, n);
     cudaDeviceProp p;
     if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return ctx_fail(nullptr, MSD_ENODEV, "cudaGetDeviceProperties failed");
     if (p.major != 10) return ctx_fail(nullptr, MSD_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, p.major, p.minor);
-    if (cudaSetDevice(device) != cudaSuccess) return ctx_fail(nullptr, MSD_ENODEV, "cudaSetDevice failed");
+    lap("device properties");
+    if (cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) return ctx_fail(nullptr, MSD_ENODEV, "cudaSetDevice failed");
+    lap("context");
     msd_ctx* ctx = new msd_ctx();
     ctx->device = device;
     { const uint64_t ns = env_u64("MSD_SLOTS", 4); ctx->n_slots = ns >= 8 ? 8 : ns >= 4 ? 4 : 2; }
@@ -608,9 +624,15 @@ int msd_create(int device, msd_ctx** out) {
     cudaFuncSetAttribute(huffman_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecSmem);
     cudaFuncSetAttribute(huffman_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(bgzf_crc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCrcSmem);
+    cudaFuncSetAttribute(scan_segments_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanPipeSmem);
+    cudaFuncSetAttribute(scan_segments_pipe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanPipeSmem);
+    cudaFuncSetAttribute(scan_segments_pipe_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(scan_segments_pipe_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(inflate_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
     cudaFuncSetAttribute(inflate_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    lap("streams + kernel attributes");
     if (crc_upload_tables() != cudaSuccess) { delete ctx; return ctx_fail(nullptr, MSD_ENODEV, "cannot upload the CRC tables"); }
+    lap("CRC tables (module load)");
     // default filters = mosdepth defaults (-F 1796, -Q 0, no length limits, default mode)
     ctx->fp.mapq = 0; ctx->fp.min_len = -1; ctx->fp.max_len = INT64_MAX; ctx->fp.eflag = 1796; ctx->fp.iflag = 0; ctx->fp.mode = MSD_MODE_DEFAULT; ctx->fp.n_rg = 0; ctx->fp.rg_names = nullptr;
     *out = ctx;

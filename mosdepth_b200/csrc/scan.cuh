@@ -54,15 +54,6 @@ MSD_D void hist_add_keep(uint32_t* __restrict__ sh, unsigned long long* __restri
 
 struct SegStats { unsigned long long sum; uint32_t mn, mx; };
 
-constexpr int kLookGroups = 4;    // the look-back reads 4 x 32 tile states per probe
-MSD_D void prefetch_l2(const void* p) {
-#if defined(__CUDACC__)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
-
 // block-reduce the per-thread stats into acc[slot], flush the shared histogram into hist_all[slot]; all threads call it
 MSD_D void seg_flush(SegStats& my, uint32_t* __restrict__ s_hist, unsigned long long* __restrict__ s_sum, uint32_t* __restrict__ s_mn, uint32_t* __restrict__ s_mx,
                      ContigAccum* __restrict__ acc, unsigned long long* __restrict__ hist) {
@@ -105,6 +96,47 @@ MSD_D void seg_stats4(const int4 x, uint32_t idx, uint32_t n_stat, SegStats& my,
     if (cnt) hist_add_keep(s_hist, hist, cur, cnt);
 }
 
+// Decoupled look-back of one tile, by one warp.  tile_state[i] = (flag << 32) | value, flag 0 = not ready, 1 = tile aggregate, 2 = inclusive
+// prefix.  Publishes the tile's aggregate, walks back kGroups x 32 tiles per probe (lane l of group g reads tile k - 32 g - l; tiles in front of
+// the segment count as "inclusive prefix 0"), publishes the inclusive prefix and returns the exclusive one (the same value in every lane).
+template <int kGroups>
+MSD_D uint32_t look_back(unsigned long long* __restrict__ tile_state, uint32_t tile, uint32_t first_tile, uint32_t tile_total, int lane) {
+    if (tile == first_tile) {
+        if (lane == 0) atomicExch(&tile_state[tile], (2ull << 32) | tile_total);
+        return 0u;
+    }
+    if (lane == 0) atomicExch(&tile_state[tile], (1ull << 32) | tile_total);
+    uint32_t prefix = 0;
+    int64_t k = (int64_t)tile - 1;
+    bool done = false;
+    while (!done) {
+        unsigned long long s[kGroups];
+#pragma unroll
+        for (int g = 0; g < kGroups; g++) {
+            const int64_t idx = k - 32 * g - lane;
+            s[g] = (2ull << 32);
+            if (idx >= (int64_t)first_tile) s[g] = *((volatile unsigned long long*)&tile_state[idx]);
+        }
+        bool stall = false;
+#pragma unroll
+        for (int g = 0; g < kGroups; g++) {
+            if (done || stall) continue;                                           // (warp-uniform)
+            const uint32_t flag = (uint32_t)(s[g] >> 32);
+            const unsigned ready = __ballot_sync(0xffffffffu, flag != 0), incl = __ballot_sync(0xffffffffu, flag == 2);
+            const int f = incl ? __ffs((int)incl) - 1 : 32;                       // nearest tile that knows its inclusive prefix
+            const unsigned need = f >= 31 ? 0xffffffffu : ((2u << f) - 1u);       // lanes 0..f (all 32 when none does)
+            if ((ready & need) != need) { stall = true; continue; }                // some tile in between has not published yet
+            uint32_t val = (lane <= f) ? (uint32_t)s[g] : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
+            prefix += __shfl_sync(0xffffffffu, val, 0);
+            if (f < 32) done = true; else k -= 32;
+        }
+    }
+    if (lane == 0) atomicExch(&tile_state[tile], (2ull << 32) | (uint32_t)(prefix + tile_total));
+    return prefix;
+}
+
 // tile_state[i]: (flag << 32) | value, flag 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix.
 // kScan = false: the arrays already hold depth (a shard after msd_exchange_spills): only the stats pass, tiles taken by stride.
 template <bool kScan>
@@ -123,18 +155,13 @@ scan_segments_kernel(int32_t* __restrict__ arena, const ScanSeg* __restrict__ se
     int cur_seg = -1; bool cur_stats = false; uint32_t cur_slot = 0;
     __syncthreads();
     uint32_t tile = blockIdx.x;
-    if (kScan) {
-        if (t == 0) s_tile = atomicAdd(ticket, 1u);
-        __syncthreads();
-        tile = s_tile;
-    }
-    for (;;) {
+    for (;; tile += gridDim.x) {
+        if (kScan) {
+            if (t == 0) s_tile = atomicAdd(ticket, 1u);
+            __syncthreads();
+            tile = s_tile;
+        }
         if (tile >= n_tiles) break;
-        // the ticket of the NEXT tile is taken now and read at the end of this one: its latency hides behind the tile's loads, and warp 0
-        // can ask L2 for the next tile's lines while it waits in the look-back.  (Tickets still ascend per CTA and every tile with a
-        // smaller number belongs to a CTA that reaches it without waiting for a larger one, so the look-back cannot deadlock.)
-        uint32_t next_ticket = 0;
-        if (kScan && t == 0) next_ticket = atomicAdd(ticket, 1u);
         // the segment of this tile: the last one with first_tile <= tile (uniform across the CTA; a CTA's tiles ascend, so the
         // previous answer is right most of the time)
         int sg = cur_seg;
@@ -181,55 +208,8 @@ scan_segments_kernel(int32_t* __restrict__ arena, const ScanSeg* __restrict__ se
             uint32_t warp_excl = 0, tile_total = 0;
 #pragma unroll
             for (int w = 0; w < kScanThreads / 32; w++) { uint32_t x = s_warp[w]; if (w < warp) warp_excl += x; tile_total += x; }
-            // decoupled look-back by warp 0.  One probe reads the states of the kLookGroups * 32 tiles in front (lane l of group g: tile
-            // k - 32 g - l); tiles in front of the segment count as "inclusive prefix 0".  The width matters: with T tiles per microsecond
-            // in flight and a probe round trip of p microseconds, a tile finds the nearest finished look-back T * (its own look-back
-            // time) tiles behind it, so a walk of 32 tiles per probe caps the kernel at 32 / p tiles per microsecond whatever the occupancy
-            // (r2c: 2.4-2.7 TB/s with 32-KB tiles, p = 0.4 us); 128 per probe lifts that cap above the HBM rate.
             if (warp == 0) {
-                uint32_t prefix = 0;
-                // ask L2 for the lines of this CTA's next tile (same segment only; 128 lines of 128 bytes, four per lane)
-                const uint32_t nt = __shfl_sync(0xffffffffu, next_ticket, 0);
-                if (nt < n_tiles && nt >= S.first_tile) {
-                    const uint64_t nb = (uint64_t)(nt - S.first_tile) * kScanTile;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const uint64_t c = nb + (uint64_t)(q * 32 + lane) * 32u;
-                        if (c < n_scan) prefetch_l2(arr + c);
-                    }
-                }
-                if (rel == 0) {
-                    if (lane == 0) atomicExch(&tile_state[tile], (2ull << 32) | tile_total);
-                } else {
-                    if (lane == 0) atomicExch(&tile_state[tile], (1ull << 32) | tile_total);
-                    int64_t k = (int64_t)tile - 1;
-                    bool done = false;
-                    while (!done) {
-                        unsigned long long s[kLookGroups];
-#pragma unroll
-                        for (int g = 0; g < kLookGroups; g++) {
-                            const int64_t idx = k - 32 * g - lane;
-                            s[g] = (2ull << 32);
-                            if (idx >= (int64_t)S.first_tile) s[g] = *((volatile unsigned long long*)&tile_state[idx]);
-                        }
-                        bool stall = false;
-#pragma unroll
-                        for (int g = 0; g < kLookGroups; g++) {
-                            if (done || stall) continue;                                           // (warp-uniform)
-                            const uint32_t flag = (uint32_t)(s[g] >> 32);
-                            const unsigned ready = __ballot_sync(0xffffffffu, flag != 0), incl = __ballot_sync(0xffffffffu, flag == 2);
-                            const int f = incl ? __ffs((int)incl) - 1 : 32;                       // nearest tile that knows its inclusive prefix
-                            const unsigned need = f >= 31 ? 0xffffffffu : ((2u << f) - 1u);       // lanes 0..f (all 32 when none does)
-                            if ((ready & need) != need) { stall = true; continue; }                // some tile in between has not published yet
-                            uint32_t val = (lane <= f) ? (uint32_t)s[g] : 0u;
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
-                            prefix += __shfl_sync(0xffffffffu, val, 0);
-                            if (f < 32) done = true; else k -= 32;
-                        }
-                    }
-                    if (lane == 0) atomicExch(&tile_state[tile], (2ull << 32) | (uint32_t)(prefix + tile_total));
-                }
+                const uint32_t prefix = look_back<1>(tile_state, tile, S.first_tile, tile_total, lane);
                 if (lane == 0) s_prefix = prefix;
             }
             __syncthreads();
@@ -249,11 +229,155 @@ scan_segments_kernel(int32_t* __restrict__ arena, const ScanSeg* __restrict__ se
             }
             if (cur_stats) seg_stats4(x, idx, S.n_stat, my, s_hist, hist);
         }
-        if (kScan) {
-            if (t == 0) s_tile = next_ticket;
-            __syncthreads();              // s_tile is written; s_warp / s_prefix may be reused
-            tile = s_tile;
-        } else tile += gridDim.x;
+        if (kScan) __syncthreads();   // s_tile / s_warp / s_prefix reuse
+    }
+    if (cur_stats) seg_flush(my, s_hist, s_sum, s_mn, s_mx, acc_all + cur_slot, hist_all + (size_t)cur_slot * kHistKeep);
+}
+
+// ---- K6, pipelined (r2j) ---------------------------------------------------------------------------------------------------------------
+// The kernel above pays every latency of a tile in sequence -- ticket, segment table, the tile's loads, the look-back, the stores and
+// stats -- so a CTA has loads in flight for ~1 us of the ~7 us a tile takes and four CTAs per SM keep ~9 KB of reads outstanding where the
+// HBM rate needs ~35 KB (r2c: 37-41 % of the measured peak).  Here each CTA owns a ring of kScanStages 16-KB tiles in shared memory that one
+// thread fills with bulk asynchronous copies (cp.async.bulk global -> shared, completion counted on an mbarrier), kScanStages tiles ahead of
+// the tile the CTA is scanning; the ticket of the tile after those is already on its way.  The rest -- int4 per thread, local scan, warp-wide
+// look-back, stores and stats from registers -- is the arithmetic of the kernel above, unchanged.
+// Deadlock freedom is the ticket argument again: a CTA's tickets ascend and it scans them in order, so the smallest unfinished tile of the
+// launch is always the current tile of its CTA and never waits.
+constexpr int kScanStages = 3;
+constexpr int kScanProducer = 32;      // thread that takes tickets and issues the copies (lane 0 of warp 1: warp 0 walks the look-back)
+constexpr size_t kScanPipeSmem = (size_t)kScanStages * kScanTile * 4;
+
+MSD_D void pipe_bar_init(unsigned long long* bar) {
+#if defined(__CUDACC__)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)));
+#else
+    (void)bar;
+#endif
+}
+// the source must be 16-byte aligned and `bytes` a multiple of 16
+MSD_D void pipe_issue(void* dst_smem, const void* src, uint32_t bytes, unsigned long long* bar) {
+#if defined(__CUDACC__)
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+#else
+    (void)bar; memcpy(dst_smem, src, bytes);      // the emulation copies at once; a __syncthreads lies between every issue and the first read
+#endif
+}
+MSD_D void pipe_wait(unsigned long long* bar, uint32_t parity) {
+#if defined(__CUDACC__)
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t ok = 0;
+    while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }" : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+#else
+    (void)bar; (void)parity;
+#endif
+}
+// the segment that owns `tile`: the last one with first_tile <= tile
+MSD_D int seg_of_tile(const ScanSeg* __restrict__ segs, int n_segs, uint32_t tile, int hint) {
+    if (hint >= 0 && tile >= segs[hint].first_tile && (hint + 1 >= n_segs || tile < segs[hint + 1].first_tile)) return hint;
+    int lo = 0, hi = n_segs - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (segs[mid].first_tile <= tile) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
+template <int kGroups>
+__global__ void __launch_bounds__(kScanThreads, 4)
+scan_segments_pipe_kernel(int32_t* __restrict__ arena, const ScanSeg* __restrict__ segs, int n_segs, uint32_t n_tiles,
+                          unsigned long long* __restrict__ tile_state, uint32_t* __restrict__ ticket,
+                          ContigAccum* __restrict__ acc_all, unsigned long long* __restrict__ hist_all /* [slot][kHistKeep] */) {
+#if defined(__CUDACC__)
+    extern __shared__ __align__(128) int4 s_ring[];                              // kScanStages tiles of 1024 int4
+#else
+    __shared__ int4 s_ring[kScanStages * (kScanTile / 4)];
+#endif
+    __shared__ unsigned long long s_full[kScanStages];
+    __shared__ uint32_t s_slot_tile[kScanStages];
+    __shared__ uint32_t s_hist[kHistSmemBins];
+    __shared__ uint32_t s_warp[kScanThreads / 32];
+    __shared__ uint32_t s_prefix;
+    __shared__ unsigned long long s_sum[kScanThreads / 32];
+    __shared__ uint32_t s_mn[kScanThreads / 32], s_mx[kScanThreads / 32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < kHistSmemBins; i += kScanThreads) s_hist[i] = 0;
+    SegStats my{0, 0xffffffffu, 0};
+    int cur_seg = -1; bool cur_stats = false; uint32_t cur_slot = 0;
+    // producer state (thread kScanProducer only): the ticket that has no copy yet, and the segment of the last tile it looked up
+    uint32_t pending = 0; int prod_seg = -1;
+    auto fill = [&](int slot, uint32_t tk) {         // producer: tile tk goes to ring slot `slot` (nothing to copy once the tickets run out)
+        s_slot_tile[slot] = tk;
+        if (tk >= n_tiles) return;
+        prod_seg = seg_of_tile(segs, n_segs, tk, prod_seg);
+        const ScanSeg P = segs[prod_seg];
+        const uint32_t base = (tk - P.first_tile) * kScanTile, cells = P.n_scan - base < (uint32_t)kScanTile ? P.n_scan - base : (uint32_t)kScanTile;
+        pipe_issue(s_ring + (size_t)slot * (kScanTile / 4), arena + P.arr_off + base, (cells * 4u + 15u) & ~15u, &s_full[slot]);
+    };
+    if (t == kScanProducer) {
+        for (int k = 0; k < kScanStages; k++) pipe_bar_init(&s_full[k]);
+#if defined(__CUDACC__)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+        for (int k = 0; k < kScanStages; k++) fill(k, atomicAdd(ticket, 1u));
+        pending = atomicAdd(ticket, 1u);
+    }
+    __syncthreads();
+    for (uint32_t it = 0;; it++) {
+        const int slot = (int)(it % kScanStages);
+        const uint32_t tile = s_slot_tile[slot];
+        if (tile >= n_tiles) break;                     // a CTA's tickets ascend: the later slots hold nothing either
+        const int sg = seg_of_tile(segs, n_segs, tile, cur_seg);
+        if (sg != cur_seg) {
+            if (cur_stats) seg_flush(my, s_hist, s_sum, s_mn, s_mx, acc_all + cur_slot, hist_all + (size_t)cur_slot * kHistKeep);
+            cur_seg = sg; cur_stats = segs[sg].n_stat != 0; cur_slot = segs[sg].slot;
+        }
+        const ScanSeg S = segs[sg];
+        int32_t* __restrict__ arr = arena + S.arr_off;
+        const uint32_t n_scan = S.n_scan, rel = tile - S.first_tile, tile_base = rel * kScanTile;
+        unsigned long long* __restrict__ hist = hist_all + (size_t)S.slot * kHistKeep;
+        pipe_wait(&s_full[slot], (it / kScanStages) & 1u);
+        const int4* __restrict__ ring = s_ring + (size_t)slot * (kScanTile / 4);
+        // warp w owns cells [tile_base + w*512, +512): 4 rounds of 32 lanes x int4 (what lies beyond n_scan in the slot is stale: masked)
+        int4 v[kScanVecPerThread];
+        uint32_t run = 0;
+#pragma unroll
+        for (int j = 0; j < kScanVecPerThread; j++) {
+            const uint32_t off = warp * 512 + j * 128 + lane * 4, idx = tile_base + off;
+            int4 x = ring[off >> 2];
+            if (idx + 3 >= n_scan) { if (idx >= n_scan) x.x = 0; if (idx + 1 >= n_scan) x.y = 0; if (idx + 2 >= n_scan) x.z = 0; x.w = 0; }
+            uint32_t a = (uint32_t)x.x, b = a + (uint32_t)x.y, c = b + (uint32_t)x.z, d = c + (uint32_t)x.w;
+            uint32_t incl = d;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            const uint32_t excl = incl - d + run;
+            v[j] = make_int4((int)(a + excl), (int)(b + excl), (int)(c + excl), (int)(d + excl));
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) s_warp[warp] = run;
+        __syncthreads();                                // every thread has read its part of the slot: it may be filled again
+        if (t == kScanProducer) { fill(slot, pending); pending = atomicAdd(ticket, 1u); }
+        uint32_t warp_excl = 0, tile_total = 0;
+#pragma unroll
+        for (int w = 0; w < kScanThreads / 32; w++) { uint32_t x = s_warp[w]; if (w < warp) warp_excl += x; tile_total += x; }
+        if (warp == 0) {
+            const uint32_t prefix = look_back<kGroups>(tile_state, tile, S.first_tile, tile_total, lane);
+            if (lane == 0) s_prefix = prefix;
+        }
+        __syncthreads();
+        const uint32_t add = s_prefix + warp_excl;
+#pragma unroll
+        for (int j = 0; j < kScanVecPerThread; j++) {
+            const uint32_t idx = tile_base + warp * 512 + j * 128 + lane * 4;
+            const int4 x = make_int4((int)((uint32_t)v[j].x + add), (int)((uint32_t)v[j].y + add), (int)((uint32_t)v[j].z + add), (int)((uint32_t)v[j].w + add));
+            if (idx + 3 < n_scan) *reinterpret_cast<int4*>(arr + idx) = x;
+            else {
+                if (idx < n_scan) arr[idx] = x.x;
+                if (idx + 1 < n_scan) arr[idx + 1] = x.y;
+                if (idx + 2 < n_scan) arr[idx + 2] = x.z;
+            }
+            if (cur_stats) seg_stats4(x, idx, S.n_stat, my, s_hist, hist);
+        }
+        // (no barrier here: s_warp is written again after the next tile's first barrier-free stretch only by threads that have passed the
+        // second barrier above, and s_prefix by warp 0 after the next first barrier, which every thread reaches after reading s_prefix)
     }
     if (cur_stats) seg_flush(my, s_hist, s_sum, s_mn, s_mx, acc_all + cur_slot, hist_all + (size_t)cur_slot * kHistKeep);
 }
