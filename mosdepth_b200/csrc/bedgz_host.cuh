@@ -72,7 +72,7 @@ int bz_run(BzBuffers& B, cudaStream_t sc, const char* chrom, const int32_t* d_st
         const double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
         fprintf(stderr, "[msd trace] bgzf: %-34s %9.3f ms\n", what, now - w_last); w_last = now;
     };
-    // the contig's Huffman code, from a sample of its own lines (host: 65,536 lines at most)
+    // the contig's Huffman code, from a sample of its own lines (host: 16,384 lines at most)
     static_assert(sizeof(BzCodes) % 4 == 0, "BzCodes is copied as words");
     BzCodes codes;
     if (!bz_build_codes(chrom, h_st, h_en, h_dp, n, &codes, labels, n_labels))

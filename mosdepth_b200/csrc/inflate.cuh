@@ -689,7 +689,15 @@ bgzf_crc_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ b
             const CrcWords c = crc_head_cancel(CrcWords{buf[0].x, buf[0].y, buf[0].z, buf[0].w}, 0, cur.pad);
             d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
         }
-        for (uint32_t r0 = 0; r0 < cur.R; r0 += kCrcDepth) {
+        uint32_t r0 = 0;
+        for (; r0 + 2 * kCrcDepth <= cur.R; r0 += kCrcDepth) {     // every row of this group and of the next one exists: no bounds checks
+#pragma unroll
+            for (int j = 0; j < kCrcDepth; j++) {
+                d[0] = step(buf[j].x ^ d[0]); d[1] = step(buf[j].y ^ d[1]); d[2] = step(buf[j].z ^ d[2]); d[3] = step(buf[j].w ^ d[3]);
+                buf[j] = __ldg(cur.q + (size_t)(r0 + j + kCrcDepth) * 32);
+            }
+        }
+        for (; r0 < cur.R; r0 += kCrcDepth) {                       // the last rows (fewer than two groups)
 #pragma unroll
             for (int j = 0; j < kCrcDepth; j++) {
                 const uint32_t r = r0 + j;

@@ -5,10 +5,21 @@
 //
 // A *segment* is a contiguous piece of the depth arena that gets its own prefix sum: a whole contig (tlen + 1 cells, the
 // first tlen of which feed the stats) or the owned range of a contig that is sharded across GPUs.  All segments are cut
-// into 4096-cell tiles that are numbered through (segment s owns tiles [first_tile, first_tile + ceil(n_scan / 4096)));
-// persistent CTAs take tile numbers from an atomic ticket, so the decoupled look-back never waits for a tile that has not
-// started, and it simply stops at the first tile of its own segment.  Single pass, 128-bit coalesced loads and stores,
-// warp-wide look-back (32 predecessors per probe).
+// into tiles (8192 cells = 32 KB in the scan launch) that are numbered through (segment s owns tiles [first_tile, first_tile +
+// ceil(n_scan / tile))); persistent CTAs take tile numbers from an atomic ticket AT THE MOMENT they are ready for one, so the
+// decoupled look-back never waits for a tile that has not started, and it simply stops at the first tile of its own segment.
+// Single pass, 128-bit coalesced loads and stores, warp-wide look-back (32 predecessors per probe).
+//
+// What round 2 measured (profiles/README.md, r2j-r2n), in the order it mattered:
+//   * every load of a tile must be issued before anything waits for one (the bounds checks of a partial tile sat between the loads:
+//     four DRAM latencies per tile) -- 38 % -> 54 % of the HBM peak together with
+//   * lean stats: a cell below 1024 only touches its shared-memory bin, one atomic per run of equal neighbours, no branches; sum / min /
+//     max are read off the bins when a CTA leaves a segment (43 -> 26 thread instructions per cell);
+//   * 32-KB tiles on three CTAs per SM instead of 16 KB on four, and an L2 prefetch of the tile one grid further on (tickets ascend,
+//     so that is about the tile somebody takes next): 54 % -> 66-68 %;
+//   * tickets must NOT be taken ahead of time: a kernel that fed a shared-memory ring with bulk asynchronous copies three tiles ahead
+//     (profiles/r2k_scan_pipe_kernel.cuh.txt) ran at 27 % -- a tile that is assigned early waits for its CTA while every later tile
+//     waits for its aggregate; a look-back that reads 128 states per probe changed nothing (the walk is short; the wait is for aggregates).
 //
 // HBM traffic per base: 4 B read + 4 B written (the depth array is kept for the window / region / run kernels).
 // r1 ran one launch + one 3.2 MB histogram memset + one 3.2 MB histogram add per contig (25 x 3 launches for a human genome);
@@ -19,8 +30,9 @@
 namespace msd {
 
 constexpr int kScanThreads = 256;
-constexpr int kScanVecPerThread = 4;                                   // int4 per thread
+constexpr int kScanVecPerThread = 4;                                   // int4 per thread (the stats-only pass and the default scan)
 constexpr int kScanTile = kScanThreads * kScanVecPerThread * 4;        // 4096 cells = 16 KB
+constexpr int scan_tile_cells(int vec) { return kScanThreads * vec * 4; }
 constexpr int kHistSmemBins = 1024;
 constexpr int kHistKeep = 4096;   // dist bins kept per segment on the device (deeper contigs are counted again, one at a time)
 
@@ -44,20 +56,31 @@ MSD_D void hist_add(uint32_t* __restrict__ sh, unsigned long long* __restrict__ 
     if (v < kHistSmemBins) atomicAdd(&sh[v], n);
     else atomicAdd(&gh[v], (unsigned long long)n);
 }
-// same rule, for a per-segment table of kHistKeep bins: deeper values are not counted here -- the segment's max_depth tells the
-// host that it has to count this one contig again with the full-width table (range_stats_kernel)
-MSD_D void hist_add_keep(uint32_t* __restrict__ sh, unsigned long long* __restrict__ gh, int32_t v, uint32_t n) {
-    if (v < 0) return;
-    if (v < kHistSmemBins) atomicAdd(&sh[v], n);
-    else if (v < kHistKeep) atomicAdd(&gh[v], (unsigned long long)n);
-}
-
 struct SegStats { unsigned long long sum; uint32_t mn, mx; };
 
-// block-reduce the per-thread stats into acc[slot], flush the shared histogram into hist_all[slot]; all threads call it
+MSD_D void prefetch_l2(const void* p) {
+#if defined(__CUDACC__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
+// flush the shared histogram into hist_all[slot] and block-reduce the stats into acc[slot]; all threads call it.  Cells whose depth is below
+// kHistSmemBins only ever touch their shared bin (seg_stats4): their part of the sum, the minimum and the maximum is read off the bins here --
+// sum = sum of bin x count, min / max = lowest / highest bin in use -- which takes the per-cell 64-bit add and the two compares out of the tile loop.
 MSD_D void seg_flush(SegStats& my, uint32_t* __restrict__ s_hist, unsigned long long* __restrict__ s_sum, uint32_t* __restrict__ s_mn, uint32_t* __restrict__ s_mx,
                      ContigAccum* __restrict__ acc, unsigned long long* __restrict__ hist) {
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    __syncthreads();                                     // every warp's shared-memory atomics of the last tile have landed
+    for (int i = t; i < kHistSmemBins; i += kScanThreads) {
+        const uint32_t c = s_hist[i];
+        if (c) {
+            atomicAdd(&hist[i], (unsigned long long)c); s_hist[i] = 0;
+            my.sum += (unsigned long long)c * (unsigned long long)i;
+            my.mn = (uint32_t)i < my.mn ? (uint32_t)i : my.mn; my.mx = (uint32_t)i > my.mx ? (uint32_t)i : my.mx;
+        }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         my.sum += __shfl_down_sync(0xffffffffu, my.sum, o);
@@ -72,28 +95,35 @@ MSD_D void seg_flush(SegStats& my, uint32_t* __restrict__ s_hist, unsigned long 
         if (S) atomicAdd(&acc->cum_depth, S);
         if (mn != 0xffffffffu || mx != 0) { atomicMin(&acc->min_depth, mn); atomicMax(&acc->max_depth, mx); }
     }
-    for (int i = t; i < kHistSmemBins; i += kScanThreads) { const uint32_t c = s_hist[i]; if (c) { atomicAdd(&hist[i], (unsigned long long)c); s_hist[i] = 0; } }
     my.sum = 0; my.mn = 0xffffffffu; my.mx = 0;
     __syncthreads();
 }
 
-// the stats of four consecutive cells starting at segment index idx (cells at or beyond n_stat do not count).  Equal neighbouring cells
-// of a lane share one histogram atomic.  (r2e tried grouping the lanes of a warp by value with match.any, one atomic per group: 2.13 TB/s at
-// f = 0.12 against 2.41 / 2.70 TB/s at f = 0.06 / 0.5 for this version -- no gain, dropped.)
+// The stats of four consecutive cells starting at segment index idx (cells at or beyond n_stat do not count).
+// Common case -- four counted cells, all in [0, kHistSmemBins): only the shared bins are touched (sum / min / max follow in seg_flush), one
+// atomic per run of equal neighbours, no branches (r2l: the per-cell version spent ~30 instructions per cell, 14 % of them branches).
+// (r2e tried grouping the lanes of a warp by value with match.any, one atomic per group: no gain, dropped.)
 MSD_D void seg_stats4(const int4 x, uint32_t idx, uint32_t n_stat, SegStats& my, uint32_t* __restrict__ s_hist, unsigned long long* __restrict__ hist) {
+    if (idx + 3 < n_stat && (uint32_t)(x.x | x.y | x.z | x.w) < (uint32_t)kHistSmemBins) {
+        const bool p1 = x.y != x.x, p2 = x.z != x.y, p3 = x.w != x.z;
+        const uint32_t l2 = p3 ? 1u : 2u, l1 = p2 ? 1u : 1u + l2, l0 = p1 ? 1u : 1u + l1;     // length of the run that starts at cell 2 / 1 / 0
+        atomicAdd(&s_hist[x.x], l0);
+        if (p1) atomicAdd(&s_hist[x.y], l1);
+        if (p2) atomicAdd(&s_hist[x.z], l2);
+        if (p3) atomicAdd(&s_hist[x.w], 1u);
+        return;
+    }
     const int32_t e[4] = {x.x, x.y, x.z, x.w};
-    int32_t cur = 0; uint32_t cnt = 0;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         if (idx + q >= n_stat) break;
         const int32_t d = e[q];
+        if (d >= 0 && d < kHistSmemBins) { atomicAdd(&s_hist[d], 1u); continue; }
         my.sum += (unsigned long long)(long long)d;          // dp.uint64 (depthstat.nim:43)
         const uint32_t u = (uint32_t)d;
         my.mn = u < my.mn ? u : my.mn; my.mx = u > my.mx ? u : my.mx;
-        if (cnt && d == cur) cnt++;
-        else { if (cnt) hist_add_keep(s_hist, hist, cur, cnt); cur = d; cnt = 1; }
+        if (d >= 0 && d < kHistKeep) atomicAdd(&hist[d], 1ull);      // deeper values: the segment's max_depth tells the host to count this contig again
     }
-    if (cnt) hist_add_keep(s_hist, hist, cur, cnt);
 }
 
 // Decoupled look-back of one tile, by one warp.  tile_state[i] = (flag << 32) | value, flag 0 = not ready, 1 = tile aggregate, 2 = inclusive
@@ -139,8 +169,10 @@ MSD_D uint32_t look_back(unsigned long long* __restrict__ tile_state, uint32_t t
 
 // tile_state[i]: (flag << 32) | value, flag 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix.
 // kScan = false: the arrays already hold depth (a shard after msd_exchange_spills): only the stats pass, tiles taken by stride.
-template <bool kScan>
-__global__ void __launch_bounds__(kScanThreads, 4)
+// kVec int4 per thread: a tile is 256 x kVec x 4 cells (4: 16 KB, four CTAs per SM; 8: 32 KB, three CTAs per SM).  kAhead: every CTA asks L2 for the
+// lines of the tile gridDim.x tiles further on -- tickets are handed out in order, so that is about the tile some CTA will take next.
+template <bool kScan, int kGroups = 1, int kVec = kScanVecPerThread, bool kAhead = false>
+__global__ void __launch_bounds__(kScanThreads, kVec <= 4 ? 4 : 3)
 scan_segments_kernel(int32_t* __restrict__ arena, const ScanSeg* __restrict__ segs, int n_segs, uint32_t n_tiles,
                      unsigned long long* __restrict__ tile_state, uint32_t* __restrict__ ticket,
                      ContigAccum* __restrict__ acc_all, unsigned long long* __restrict__ hist_all /* [slot][kHistKeep] */) {
@@ -149,6 +181,7 @@ scan_segments_kernel(int32_t* __restrict__ arena, const ScanSeg* __restrict__ se
     __shared__ uint32_t s_tile, s_prefix;
     __shared__ unsigned long long s_sum[kScanThreads / 32];
     __shared__ uint32_t s_mn[kScanThreads / 32], s_mx[kScanThreads / 32];
+    constexpr int kTile = kScanThreads * kVec * 4;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int i = t; i < kHistSmemBins; i += kScanThreads) s_hist[i] = 0;
     SegStats my{0, 0xffffffffu, 0};
@@ -176,30 +209,47 @@ scan_segments_kernel(int32_t* __restrict__ arena, const ScanSeg* __restrict__ se
         }
         const ScanSeg S = segs[sg];
         int32_t* __restrict__ arr = arena + S.arr_off;
-        const uint32_t n_scan = S.n_scan, rel = tile - S.first_tile, tile_base = rel * kScanTile;
+        const uint32_t n_scan = S.n_scan, rel = tile - S.first_tile, tile_base = rel * (uint32_t)kTile;
         unsigned long long* __restrict__ hist = hist_all + (size_t)S.slot * kHistKeep;
-        // warp w owns cells [tile_base + w*512, +512): 4 rounds of 32 lanes x int4
-        int4 v[kScanVecPerThread];
-        uint32_t run = 0;
+        // warp w owns cells [tile_base + w * kVec * 128, + kVec * 128): kVec rounds of 32 lanes x int4.  All the loads are issued before anything waits for one
+        // (r2l: with the bounds checks of a partial tile between them, each load was waited for in turn -- four DRAM latencies per tile).
+        int4 v[kVec];
+        const bool whole = tile_base + (uint32_t)kTile <= n_scan && tile_base + (uint32_t)kTile > tile_base;     // (CTA-uniform)
+        if (whole) {
 #pragma unroll
-        for (int j = 0; j < kScanVecPerThread; j++) {
-            const uint32_t idx = tile_base + warp * 512 + j * 128 + lane * 4;
-            int4 x = make_int4(0, 0, 0, 0);
-            if (idx + 3 < n_scan) x = *reinterpret_cast<const int4*>(arr + idx);
-            else {
-                if (idx < n_scan) x.x = arr[idx];
-                if (idx + 1 < n_scan) x.y = arr[idx + 1];
-                if (idx + 2 < n_scan) x.z = arr[idx + 2];
+            for (int j = 0; j < kVec; j++) v[j] = *reinterpret_cast<const int4*>(arr + tile_base + warp * (kVec * 128) + j * 128 + lane * 4);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kVec; j++) {
+                const uint32_t idx = tile_base + warp * (kVec * 128) + j * 128 + lane * 4;
+                int4 x = make_int4(0, 0, 0, 0);
+                if (idx + 3 < n_scan) x = *reinterpret_cast<const int4*>(arr + idx);
+                else {
+                    if (idx < n_scan) x.x = arr[idx];
+                    if (idx + 1 < n_scan) x.y = arr[idx + 1];
+                    if (idx + 2 < n_scan) x.z = arr[idx + 2];
+                }
+                v[j] = x;
             }
-            if (!kScan) { v[j] = x; continue; }
-            // local inclusive scan of the 4 cells (uint32 wrap-around like the reference's int32 cumsum)
-            uint32_t a = (uint32_t)x.x, b = a + (uint32_t)x.y, c = b + (uint32_t)x.z, d = c + (uint32_t)x.w;
-            uint32_t incl = d;
+        }
+        if (kAhead && t < kTile / 32) {          // one 128-byte line per thread
+            const uint64_t c = (uint64_t)tile_base + (uint64_t)gridDim.x * kTile + (uint64_t)t * 32u;
+            if (c < n_scan) prefetch_l2(arr + c);
+        }
+        uint32_t run = 0;
+        if (kScan) {
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-            const uint32_t excl = incl - d + run;
-            v[j] = make_int4((int)(a + excl), (int)(b + excl), (int)(c + excl), (int)(d + excl));
-            run += __shfl_sync(0xffffffffu, incl, 31);
+            for (int j = 0; j < kVec; j++) {
+                // local inclusive scan of the 4 cells (uint32 wrap-around like the reference's int32 cumsum)
+                const int4 x = v[j];
+                uint32_t a = (uint32_t)x.x, b = a + (uint32_t)x.y, c = b + (uint32_t)x.z, d = c + (uint32_t)x.w;
+                uint32_t incl = d;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                const uint32_t excl = incl - d + run;
+                v[j] = make_int4((int)(a + excl), (int)(b + excl), (int)(c + excl), (int)(d + excl));
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
         }
         uint32_t add = 0;
         if (kScan) {
@@ -209,18 +259,18 @@ scan_segments_kernel(int32_t* __restrict__ arena, const ScanSeg* __restrict__ se
 #pragma unroll
             for (int w = 0; w < kScanThreads / 32; w++) { uint32_t x = s_warp[w]; if (w < warp) warp_excl += x; tile_total += x; }
             if (warp == 0) {
-                const uint32_t prefix = look_back<1>(tile_state, tile, S.first_tile, tile_total, lane);
+                const uint32_t prefix = look_back<kGroups>(tile_state, tile, S.first_tile, tile_total, lane);
                 if (lane == 0) s_prefix = prefix;
             }
             __syncthreads();
             add = s_prefix + warp_excl;
         }
 #pragma unroll
-        for (int j = 0; j < kScanVecPerThread; j++) {
-            const uint32_t idx = tile_base + warp * 512 + j * 128 + lane * 4;
+        for (int j = 0; j < kVec; j++) {
+            const uint32_t idx = tile_base + warp * (kVec * 128) + j * 128 + lane * 4;
             const int4 x = make_int4((int)((uint32_t)v[j].x + add), (int)((uint32_t)v[j].y + add), (int)((uint32_t)v[j].z + add), (int)((uint32_t)v[j].w + add));
             if (kScan) {
-                if (idx + 3 < n_scan) *reinterpret_cast<int4*>(arr + idx) = x;
+                if (whole || idx + 3 < n_scan) *reinterpret_cast<int4*>(arr + idx) = x;
                 else {
                     if (idx < n_scan) arr[idx] = x.x;
                     if (idx + 1 < n_scan) arr[idx + 1] = x.y;
@@ -230,154 +280,6 @@ scan_segments_kernel(int32_t* __restrict__ arena, const ScanSeg* __restrict__ se
             if (cur_stats) seg_stats4(x, idx, S.n_stat, my, s_hist, hist);
         }
         if (kScan) __syncthreads();   // s_tile / s_warp / s_prefix reuse
-    }
-    if (cur_stats) seg_flush(my, s_hist, s_sum, s_mn, s_mx, acc_all + cur_slot, hist_all + (size_t)cur_slot * kHistKeep);
-}
-
-// ---- K6, pipelined (r2j) ---------------------------------------------------------------------------------------------------------------
-// The kernel above pays every latency of a tile in sequence -- ticket, segment table, the tile's loads, the look-back, the stores and
-// stats -- so a CTA has loads in flight for ~1 us of the ~7 us a tile takes and four CTAs per SM keep ~9 KB of reads outstanding where the
-// HBM rate needs ~35 KB (r2c: 37-41 % of the measured peak).  Here each CTA owns a ring of kScanStages 16-KB tiles in shared memory that one
-// thread fills with bulk asynchronous copies (cp.async.bulk global -> shared, completion counted on an mbarrier), kScanStages tiles ahead of
-// the tile the CTA is scanning; the ticket of the tile after those is already on its way.  The rest -- int4 per thread, local scan, warp-wide
-// look-back, stores and stats from registers -- is the arithmetic of the kernel above, unchanged.
-// Deadlock freedom is the ticket argument again: a CTA's tickets ascend and it scans them in order, so the smallest unfinished tile of the
-// launch is always the current tile of its CTA and never waits.
-constexpr int kScanStages = 3;
-constexpr int kScanProducer = 32;      // thread that takes tickets and issues the copies (lane 0 of warp 1: warp 0 walks the look-back)
-constexpr size_t kScanPipeSmem = (size_t)kScanStages * kScanTile * 4;
-
-MSD_D void pipe_bar_init(unsigned long long* bar) {
-#if defined(__CUDACC__)
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)));
-#else
-    (void)bar;
-#endif
-}
-// the source must be 16-byte aligned and `bytes` a multiple of 16
-MSD_D void pipe_issue(void* dst_smem, const void* src, uint32_t bytes, unsigned long long* bar) {
-#if defined(__CUDACC__)
-    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), d = (uint32_t)__cvta_generic_to_shared(dst_smem);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
-#else
-    (void)bar; memcpy(dst_smem, src, bytes);      // the emulation copies at once; a __syncthreads lies between every issue and the first read
-#endif
-}
-MSD_D void pipe_wait(unsigned long long* bar, uint32_t parity) {
-#if defined(__CUDACC__)
-    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
-    uint32_t ok = 0;
-    while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }" : "=r"(ok) : "r"(b), "r"(parity) : "memory");
-#else
-    (void)bar; (void)parity;
-#endif
-}
-// the segment that owns `tile`: the last one with first_tile <= tile
-MSD_D int seg_of_tile(const ScanSeg* __restrict__ segs, int n_segs, uint32_t tile, int hint) {
-    if (hint >= 0 && tile >= segs[hint].first_tile && (hint + 1 >= n_segs || tile < segs[hint + 1].first_tile)) return hint;
-    int lo = 0, hi = n_segs - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (segs[mid].first_tile <= tile) lo = mid; else hi = mid - 1; }
-    return lo;
-}
-
-template <int kGroups>
-__global__ void __launch_bounds__(kScanThreads, 4)
-scan_segments_pipe_kernel(int32_t* __restrict__ arena, const ScanSeg* __restrict__ segs, int n_segs, uint32_t n_tiles,
-                          unsigned long long* __restrict__ tile_state, uint32_t* __restrict__ ticket,
-                          ContigAccum* __restrict__ acc_all, unsigned long long* __restrict__ hist_all /* [slot][kHistKeep] */) {
-#if defined(__CUDACC__)
-    extern __shared__ __align__(128) int4 s_ring[];                              // kScanStages tiles of 1024 int4
-#else
-    __shared__ int4 s_ring[kScanStages * (kScanTile / 4)];
-#endif
-    __shared__ unsigned long long s_full[kScanStages];
-    __shared__ uint32_t s_slot_tile[kScanStages];
-    __shared__ uint32_t s_hist[kHistSmemBins];
-    __shared__ uint32_t s_warp[kScanThreads / 32];
-    __shared__ uint32_t s_prefix;
-    __shared__ unsigned long long s_sum[kScanThreads / 32];
-    __shared__ uint32_t s_mn[kScanThreads / 32], s_mx[kScanThreads / 32];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    for (int i = t; i < kHistSmemBins; i += kScanThreads) s_hist[i] = 0;
-    SegStats my{0, 0xffffffffu, 0};
-    int cur_seg = -1; bool cur_stats = false; uint32_t cur_slot = 0;
-    // producer state (thread kScanProducer only): the ticket that has no copy yet, and the segment of the last tile it looked up
-    uint32_t pending = 0; int prod_seg = -1;
-    auto fill = [&](int slot, uint32_t tk) {         // producer: tile tk goes to ring slot `slot` (nothing to copy once the tickets run out)
-        s_slot_tile[slot] = tk;
-        if (tk >= n_tiles) return;
-        prod_seg = seg_of_tile(segs, n_segs, tk, prod_seg);
-        const ScanSeg P = segs[prod_seg];
-        const uint32_t base = (tk - P.first_tile) * kScanTile, cells = P.n_scan - base < (uint32_t)kScanTile ? P.n_scan - base : (uint32_t)kScanTile;
-        pipe_issue(s_ring + (size_t)slot * (kScanTile / 4), arena + P.arr_off + base, (cells * 4u + 15u) & ~15u, &s_full[slot]);
-    };
-    if (t == kScanProducer) {
-        for (int k = 0; k < kScanStages; k++) pipe_bar_init(&s_full[k]);
-#if defined(__CUDACC__)
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#endif
-        for (int k = 0; k < kScanStages; k++) fill(k, atomicAdd(ticket, 1u));
-        pending = atomicAdd(ticket, 1u);
-    }
-    __syncthreads();
-    for (uint32_t it = 0;; it++) {
-        const int slot = (int)(it % kScanStages);
-        const uint32_t tile = s_slot_tile[slot];
-        if (tile >= n_tiles) break;                     // a CTA's tickets ascend: the later slots hold nothing either
-        const int sg = seg_of_tile(segs, n_segs, tile, cur_seg);
-        if (sg != cur_seg) {
-            if (cur_stats) seg_flush(my, s_hist, s_sum, s_mn, s_mx, acc_all + cur_slot, hist_all + (size_t)cur_slot * kHistKeep);
-            cur_seg = sg; cur_stats = segs[sg].n_stat != 0; cur_slot = segs[sg].slot;
-        }
-        const ScanSeg S = segs[sg];
-        int32_t* __restrict__ arr = arena + S.arr_off;
-        const uint32_t n_scan = S.n_scan, rel = tile - S.first_tile, tile_base = rel * kScanTile;
-        unsigned long long* __restrict__ hist = hist_all + (size_t)S.slot * kHistKeep;
-        pipe_wait(&s_full[slot], (it / kScanStages) & 1u);
-        const int4* __restrict__ ring = s_ring + (size_t)slot * (kScanTile / 4);
-        // warp w owns cells [tile_base + w*512, +512): 4 rounds of 32 lanes x int4 (what lies beyond n_scan in the slot is stale: masked)
-        int4 v[kScanVecPerThread];
-        uint32_t run = 0;
-#pragma unroll
-        for (int j = 0; j < kScanVecPerThread; j++) {
-            const uint32_t off = warp * 512 + j * 128 + lane * 4, idx = tile_base + off;
-            int4 x = ring[off >> 2];
-            if (idx + 3 >= n_scan) { if (idx >= n_scan) x.x = 0; if (idx + 1 >= n_scan) x.y = 0; if (idx + 2 >= n_scan) x.z = 0; x.w = 0; }
-            uint32_t a = (uint32_t)x.x, b = a + (uint32_t)x.y, c = b + (uint32_t)x.z, d = c + (uint32_t)x.w;
-            uint32_t incl = d;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-            const uint32_t excl = incl - d + run;
-            v[j] = make_int4((int)(a + excl), (int)(b + excl), (int)(c + excl), (int)(d + excl));
-            run += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) s_warp[warp] = run;
-        __syncthreads();                                // every thread has read its part of the slot: it may be filled again
-        if (t == kScanProducer) { fill(slot, pending); pending = atomicAdd(ticket, 1u); }
-        uint32_t warp_excl = 0, tile_total = 0;
-#pragma unroll
-        for (int w = 0; w < kScanThreads / 32; w++) { uint32_t x = s_warp[w]; if (w < warp) warp_excl += x; tile_total += x; }
-        if (warp == 0) {
-            const uint32_t prefix = look_back<kGroups>(tile_state, tile, S.first_tile, tile_total, lane);
-            if (lane == 0) s_prefix = prefix;
-        }
-        __syncthreads();
-        const uint32_t add = s_prefix + warp_excl;
-#pragma unroll
-        for (int j = 0; j < kScanVecPerThread; j++) {
-            const uint32_t idx = tile_base + warp * 512 + j * 128 + lane * 4;
-            const int4 x = make_int4((int)((uint32_t)v[j].x + add), (int)((uint32_t)v[j].y + add), (int)((uint32_t)v[j].z + add), (int)((uint32_t)v[j].w + add));
-            if (idx + 3 < n_scan) *reinterpret_cast<int4*>(arr + idx) = x;
-            else {
-                if (idx < n_scan) arr[idx] = x.x;
-                if (idx + 1 < n_scan) arr[idx + 1] = x.y;
-                if (idx + 2 < n_scan) arr[idx + 2] = x.z;
-            }
-            if (cur_stats) seg_stats4(x, idx, S.n_stat, my, s_hist, hist);
-        }
-        // (no barrier here: s_warp is written again after the next tile's first barrier-free stretch only by threads that have passed the
-        // second barrier above, and s_prefix by warp 0 after the next first barrier, which every thread reaches after reading s_prefix)
     }
     if (cur_stats) seg_flush(my, s_hist, s_sum, s_mn, s_mx, acc_all + cur_slot, hist_all + (size_t)cur_slot * kHistKeep);
 }

@@ -64,23 +64,26 @@ int main(int argc, char** argv) {
         for (int c = 0; c < 3; c++) { segs[c].arr_off = off[c]; segs[c].n_scan = ns[c]; segs[c].n_stat = c == 0 ? tlen : c == 1 ? n2 : 0; segs[c].first_tile = tiles; segs[c].slot = (uint32_t)c; tiles += (ns[c] + kScanTile - 1) / kScanTile; }
         std::vector<ull> tile_state(tiles, 0), hist_all(3 * (size_t)kHistKeep, 0); uint32_t ticket = 0;
         std::vector<ContigAccum> acc(3, ContigAccum{0, 0xffffffffu, 0, 0, 0});
-        // the pipelined kernel (shared-memory ring filled by bulk copies; both look-back widths) first, on copies of the deltas: same arrays, same stats
+        // the other instantiations of the scan first, on copies of the deltas (wide look-back; 32-KB tiles with the L2 prefetch): same arrays, same stats
         {
             std::vector<int32_t> deltas(arena, arena + cells);
-            for (int groups : {1, 4}) {
-                std::vector<ull> ts2(tiles, 0), h2(3 * (size_t)kHistKeep, 0); uint32_t tk2 = 0; std::vector<ContigAccum> a2(3, ContigAccum{0, 0xffffffffu, 0, 0, 0});
-                const unsigned g = (unsigned)std::min<uint64_t>(tiles, (uint64_t)max_ctas);
-                if (groups == 1) emu::launch(g, kScanThreads, [&]() { scan_segments_pipe_kernel<1>(arena, segs.data(), 3, tiles, ts2.data(), &tk2, a2.data(), h2.data()); });
-                else emu::launch(g, kScanThreads, [&]() { scan_segments_pipe_kernel<4>(arena, segs.data(), 3, tiles, ts2.data(), &tk2, a2.data(), h2.data()); });
-                for (int c = 0; c < 3; c++) for (uint32_t i = 0; i < ns[c]; i++) if (arena[off[c] + i] != want[i]) return fail("prefix sum (pipelined kernel)", (long long)c * 1000000000ll + i, arena[off[c] + i], want[i]);
+            for (int variant : {2, 6}) {
+                const uint32_t tc = variant == 6 ? (uint32_t)scan_tile_cells(8) : (uint32_t)kScanTile;
+                std::vector<ScanSeg> sv = segs; uint32_t tl = 0;
+                for (int c = 0; c < 3; c++) { sv[c].first_tile = tl; tl += (ns[c] + tc - 1) / tc; }
+                std::vector<ull> ts2(tl, 0), h2(3 * (size_t)kHistKeep, 0); uint32_t tk2 = 0; std::vector<ContigAccum> a2(3, ContigAccum{0, 0xffffffffu, 0, 0, 0});
+                const unsigned g = (unsigned)std::min<uint64_t>(tl, (uint64_t)max_ctas);
+                if (variant == 2) emu::launch(g, kScanThreads, [&]() { scan_segments_kernel<true, 4, 4, false>(arena, sv.data(), 3, tl, ts2.data(), &tk2, a2.data(), h2.data()); });
+                else emu::launch(g, kScanThreads, [&]() { scan_segments_kernel<true, 1, 8, true>(arena, sv.data(), 3, tl, ts2.data(), &tk2, a2.data(), h2.data()); });
+                for (int c = 0; c < 3; c++) for (uint32_t i = 0; i < ns[c]; i++) if (arena[off[c] + i] != want[i]) return fail("prefix sum (scan variant)", (long long)c * 1000000000ll + i, arena[off[c] + i], want[i]);
                 for (int c = 0; c < 3; c++) {
                     const uint32_t nst = segs[c].n_stat;
                     std::vector<ull> h(kHistKeep, 0); Stat st;
                     for (uint32_t i = 0; i < nst; i++) { const int32_t v = want[i]; if (v >= 0 && v < kHistKeep) h[v]++; }
                     stat_add(st, want.data(), nst);
                     if (nst == 0) { st.mn = 0xffffffffu; st.mx = 0; }
-                    for (int b = 0; b < kHistKeep; b++) if (h[b] != h2[(size_t)c * kHistKeep + b]) return fail("segment dist bin (pipelined kernel)", (long long)c * 1000000 + b, (double)h2[(size_t)c * kHistKeep + b], (double)h[b]);
-                    if (a2[c].cum_depth != st.sum || a2[c].min_depth != st.mn || a2[c].max_depth != st.mx) return fail("segment stats (pipelined kernel)", c, (double)a2[c].cum_depth, (double)st.sum);
+                    for (int b = 0; b < kHistKeep; b++) if (h[b] != h2[(size_t)c * kHistKeep + b]) return fail("segment dist bin (scan variant)", (long long)c * 1000000 + b, (double)h2[(size_t)c * kHistKeep + b], (double)h[b]);
+                    if (a2[c].cum_depth != st.sum || a2[c].min_depth != st.mn || a2[c].max_depth != st.mx) return fail("segment stats (scan variant)", c, (double)a2[c].cum_depth, (double)st.sum);
                 }
                 memcpy(arena, deltas.data(), cells * 4);
             }

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""K6 A/B in one process: the classic scan kernel (MSD_SCAN=0), the pipelined one (1) and the pipelined one with the wide look-back (4), interleaved.
+"""K6 A/B in one process: the variants of the scan launch (MSD_SCAN, see run_segments in msd_api.cu), interleaved.
 Prints the device time between the events around run_segments (ms_scan) and a checksum of the window means (identical for every variant).
 usage: python tools/sweep_scan.py [genome_fraction]"""
 import os, sys
@@ -17,7 +17,7 @@ raw = np.fromfile(bam, dtype=np.uint8)
 host = torch.empty(raw.size, dtype=torch.uint8, pin_memory=True); host.numpy()[:] = raw
 ctx = m.Context(0); ctx.open_mem(host, hdr); ctx.set_filters(mode=m.MODE_FAST); ctx.prefetch_windows(500); ctx.stage()
 for rep in range(3):
-    for variant in (0, 1, 4):
+    for variant in (0, 3, 5, 6):
         os.environ["MSD_SCAN"] = str(variant)
         ms = []
         for _ in range(3):
