@@ -612,7 +612,14 @@ inline cudaError_t crc_upload_tables() {
     return e;
 }
 
-__global__ void __launch_bounds__(kCrcThreads, 1)
+// MSD_CRC_DEPTH rows of a block in registers.  16 rows need 128 registers x 512 threads = the whole register file of an SM: alone the kernel streams at 79 % of the
+// HBM peak (r2j); 8 rows fit 64 registers and reach 63 % (r2p).  In msd_run the kernel runs beside the persistent decode / resolve CTAs of the next chunks, where the
+// footprint could matter: interleaved A/B at f = 0.06 (r2p) 70.5 ms per step with 8 rows, 71.0-71.3 with 16 -- inside the run-to-run noise, so the faster kernel ships.
+// (An unguarded main loop for the rows that surely exist was slower: 70 % alone, r2o.)
+#ifndef MSD_CRC_DEPTH
+#define MSD_CRC_DEPTH 16
+#endif
+__global__ void __launch_bounds__(kCrcThreads, MSD_CRC_DEPTH > 8 ? 1 : 2)
 bgzf_crc_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, int n_blocks, uint32_t* __restrict__ ticket,
                 const uint32_t* __restrict__ crc_expected, uint32_t* __restrict__ status, uint32_t* __restrict__ error_count,
                 uint32_t* __restrict__ crc_out /* test hook: the computed CRCs (null in msd_run) */) {
@@ -664,7 +671,7 @@ bgzf_crc_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ b
         }
         return k;
     };
-    constexpr int kCrcDepth = 16;
+    constexpr int kCrcDepth = MSD_CRC_DEPTH;
     uint4 buf[kCrcDepth];
     auto load_first = [&](const Blk& k) {
 #pragma unroll
@@ -689,15 +696,7 @@ bgzf_crc_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ b
             const CrcWords c = crc_head_cancel(CrcWords{buf[0].x, buf[0].y, buf[0].z, buf[0].w}, 0, cur.pad);
             d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
         }
-        uint32_t r0 = 0;
-        for (; r0 + 2 * kCrcDepth <= cur.R; r0 += kCrcDepth) {     // every row of this group and of the next one exists: no bounds checks
-#pragma unroll
-            for (int j = 0; j < kCrcDepth; j++) {
-                d[0] = step(buf[j].x ^ d[0]); d[1] = step(buf[j].y ^ d[1]); d[2] = step(buf[j].z ^ d[2]); d[3] = step(buf[j].w ^ d[3]);
-                buf[j] = __ldg(cur.q + (size_t)(r0 + j + kCrcDepth) * 32);
-            }
-        }
-        for (; r0 < cur.R; r0 += kCrcDepth) {                       // the last rows (fewer than two groups)
+        for (uint32_t r0 = 0; r0 < cur.R; r0 += kCrcDepth) {
 #pragma unroll
             for (int j = 0; j < kCrcDepth; j++) {
                 const uint32_t r = r0 + j;

@@ -229,6 +229,53 @@ struct RunCounters {
     uint32_t pad;
 };
 
+// K5 for long reads: one CIGAR walked by the whole warp, 32 operations per step.  A thread that walks a 10-100 kb nanopore read alone
+// runs thousands of dependent iterations while the few thousand reads of a chunk leave most of the GPU idle (r2f: 4.6 G events/s on C5, default
+// mode); here lane i takes operation i0 + i: a warp scan of the reference-consuming lengths gives every operation its start, and the events are
+// exactly those of gen_start_ends (mosdepth.nim:146-168) -- aligned operations that abut are one block: an operation emits its +1 unless it starts
+// where the previous aligned one ended, and its -1 unless the next aligned one starts there (across steps the last end is carried).
+// fast = true: only the reference length is needed (rec_endpos).  All 32 lanes call it with the same arguments; returns the end of the last
+// block (fast: pos + max(reference length, 1)) in every lane.
+constexpr uint32_t kCoopOps = 48;      // CIGARs at least this long are walked by the warp
+MSD_D int64_t coop_cigar(const uint8_t* __restrict__ buf, uint32_t cig, uint32_t n, int64_t pos0, bool fast, int32_t* __restrict__ arr, uint32_t tlen, uint32_t& n_events) {
+    constexpr unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int64_t pos = pos0, carry_end = pos0; bool have = false;
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t i = i0 + (uint32_t)lane;
+        const bool valid = i < n;
+        const uint32_t op = valid ? ld_u32(buf, cig + 4 * i) : 0u;
+        const int t = valid ? cigar_type(op) : 0;
+        const int64_t len = (int64_t)(op >> 4);
+        unsigned long long incl = (t & 2) ? (unsigned long long)len : 0ull;
+        const unsigned long long mine = incl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(full, incl, o); if (lane >= o) incl += y; }
+        const int64_t s = pos + (int64_t)(incl - mine), e = s + len;
+        if (!fast) {
+            const bool A = (t & 3) == 3;
+            const unsigned mask = __ballot_sync(full, A);
+            const unsigned below = mask & ((1u << lane) - 1u), above = lane == 31 ? 0u : (mask & ~((2u << lane) - 1u));
+            const int64_t e_prev = __shfl_sync(full, e, below ? 31 - __clz((int)below) : 0);
+            const int64_t s_next = __shfl_sync(full, s, above ? __ffs((int)above) - 1 : 0);
+            if (A) {
+                const bool has_prev = below ? true : have;
+                const int64_t pe = below ? e_prev : carry_end;
+                if (!has_prev || s != pe) {
+                    if (!below && have) depth_add(arr, tlen, carry_end, -1, n_events);      // the block carried over from the last step ends here
+                    depth_add(arr, tlen, s, 1, n_events);
+                }
+                if (above && s_next != e) depth_add(arr, tlen, e, -1, n_events);               // (the last aligned operation of the step is carried)
+            }
+            if (mask) { carry_end = __shfl_sync(full, e, 31 - __clz((int)mask)); have = true; }
+        }
+        pos += (int64_t)__shfl_sync(full, incl, 31);
+    }
+    if (fast) { const int64_t rlen = pos - pos0; return pos0 + (rlen ? rlen : 1); }
+    if (have && lane == 0) depth_add(arr, tlen, carry_end, -1, n_events);
+    return have ? carry_end : pos0;
+}
+
 __global__ void __launch_bounds__(256)
 records_kernel(const uint8_t* __restrict__ buf, const uint32_t* __restrict__ rec_off, const ChunkState* __restrict__ cs,
                FilterParams fp, ContigTable ct, int32_t* __restrict__ arena, unsigned long long* __restrict__ n_prefilter,
@@ -236,7 +283,12 @@ records_kernel(const uint8_t* __restrict__ buf, const uint32_t* __restrict__ rec
     const uint32_t n_rec = cs->n_rec;
     uint32_t n_events = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n_rec) atomicAdd(&rc->n_records, (unsigned long long)n_rec);
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
+    // every lane of a warp makes the same number of trips (a lane beyond n_rec idles): the warp meets after each record for the long CIGARs
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_rec; base += gridDim.x * blockDim.x) {
+        const uint32_t r = base + (threadIdx.x & 31u);
+        // what this lane hands to the warp: a long CIGAR (coop_n != 0), the read's start and contig, and whether only its end is wanted (fast mode)
+        uint32_t coop_cig = 0, coop_n = 0; int32_t coop_pos = 0, coop_tid = 0;
+        if (r < n_rec) do {
         const uint32_t p = rec_off[r];
         const RecCore c = load_core(buf, p);
         if (fp.mode == MSD_MODE_DEFAULT) mc.cls[r] = kClsNone;
@@ -266,6 +318,7 @@ records_kernel(const uint8_t* __restrict__ buf, const uint32_t* __restrict__ rec
         const uint32_t cig = cg.off;
         if (fp.mode == MSD_MODE_FAST) {                                      // :342-344
             if (!own) continue;
+            if (cg.n >= kCoopOps && !(c.flag & kFlagUnmap)) { coop_cig = cig; coop_n = cg.n; coop_pos = c.pos; coop_tid = c.tid; continue; }
             const int64_t stop = rec_endpos(buf, cig, cg.n, c.flag, c.pos);
             depth_add(arr, tlen, c.pos, 1, n_events);
             depth_add(arr, tlen, stop, -1, n_events);
@@ -289,10 +342,25 @@ records_kernel(const uint8_t* __restrict__ buf, const uint32_t* __restrict__ rec
                 mc.slot[r] = kNoOff;
             }
             if (own) {
+                if (cg.n >= kCoopOps) { coop_cig = cig; coop_n = cg.n; coop_pos = c.pos; coop_tid = c.tid; continue; }
                 BlockIter it; it.init(buf, cig, cg.n, c.pos);
                 int64_t s, e, last_e = c.pos;
                 while (it.next(s, e)) { depth_add(arr, tlen, s, 1, n_events); depth_add(arr, tlen, e, -1, n_events); last_e = e; }
                 note_end(ct, c.tid, last_e, tlen);
+            }
+        }
+        } while (0);
+        __syncwarp();
+        for (unsigned todo = __ballot_sync(0xffffffffu, coop_n != 0); todo; todo &= todo - 1) {
+            const int X = __ffs((int)todo) - 1;
+            const uint32_t xc = __shfl_sync(0xffffffffu, coop_cig, X), xn = __shfl_sync(0xffffffffu, coop_n, X);
+            const int32_t xp = __shfl_sync(0xffffffffu, coop_pos, X), xt = __shfl_sync(0xffffffffu, coop_tid, X);
+            const uint32_t xl = ct.tlen[xt];
+            const bool fast = fp.mode == MSD_MODE_FAST;
+            const int64_t last = coop_cigar(buf, xc, xn, xp, fast, arena + ct.depth_off[xt], xl, n_events);
+            if ((int)(threadIdx.x & 31) == X) {
+                if (fast) { depth_add(arena + ct.depth_off[xt], xl, xp, 1, n_events); depth_add(arena + ct.depth_off[xt], xl, last, -1, n_events); }
+                note_end(ct, xt, last, xl);
             }
         }
     }

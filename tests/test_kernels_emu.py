@@ -86,3 +86,20 @@ def test_framing_records_and_mate_join_under_emulation(records_emu, oracle_bin, 
     r = subprocess.run([str(records_emu), str(FIX / name), str(tmp_path / "e.bed"), str(mode), str(per_chunk), "5"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
     assert (tmp_path / "e.bed").read_bytes() == (tmp_path / "o.per-base.bed").read_bytes()
+
+
+@pytest.mark.parametrize("mode,flags", [(0, []), (1, ["-x"])], ids=["default", "fast"])
+def test_long_read_cigars_walked_by_the_warp_under_emulation(records_emu, oracle_bin, tmp_path, mode, flags):
+    """K5's warp-cooperative CIGAR walk (records.cuh: coop_cigar, CIGARs of 48 operations or more) on synthetic nanopore reads (10-100 kb, an operation
+    every ~10 bases, so thousands of operations per read and blocks that abut across the 32-operation steps): per-base output equal to the oracle's."""
+    from conftest import run_tool
+    gen = ROOT / "tools" / "gen_bam"
+    if not gen.exists():
+        subprocess.run(["make", "-C", str(ROOT), "tools/gen_bam"], check=True, capture_output=True)
+    bam = tmp_path / "lr.bam"
+    subprocess.run([str(gen), "--config", "c5", "--genome-fraction", "0.00004", "--threads", "2", "-o", str(bam)], check=True, capture_output=True)
+    run_tool(oracle_bin, flags + ["o", bam], tmp_path)
+    r = subprocess.run([str(records_emu), str(bam), str(tmp_path / "e.bed"), str(mode), "3", "5"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+    assert (tmp_path / "e.bed").read_bytes() == (tmp_path / "o.per-base.bed").read_bytes()
+    assert (tmp_path / "e.bed").stat().st_size > 10000
